@@ -1,0 +1,201 @@
+/* jsso.h -- C ABI of the B200-native JaxSSO hot path (libjsso.so).
+ *
+ * One handle = one frozen finite-element model (the arrays Model.model_ready()
+ * produces, JaxSSO/model.py:221-246) on one GPU.  The handle owns everything that
+ * is a function of the connectivity (block-CSR pattern, contributor maps, boundary
+ * mask) plus the block-CSR values and the PCG work vectors; no allocation happens
+ * on the hot path after jsso_create.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference
+ * checkout):
+ *   jsso_quad_ke        vmap(Quad.element_K_quad)       JaxSSO/element.py:1190-1241 (1073-1084)
+ *   jsso_beam_ke        vmap(BeamCol.element_K_beamcol) JaxSSO/element.py:228-275 (130-139)
+ *   jsso_pattern        element_K_*_indices + sort_indices/sum_duplicates
+ *                                                       JaxSSO/element.py:141-149, 1097-1106;
+ *                                                       JaxSSO/assemblemodel.py:156-162
+ *   jsso_assemble*      K_func + K_aug                  JaxSSO/assemblemodel.py:111-163, 196-229
+ *   jsso_pcg/jsso_solve sci_sparse_solve / jax_sparse_solve  JaxSSO/solver.py:102-125, 176-210
+ *   jsso_adjoint        jax.vjp(f_Ax_b)(lam) + XLA transpose of K_aug/K_func/vmap(element_K_*)
+ *                                                       JaxSSO/solver.py:157-166, 239-248
+ *   jsso_forward        body of SSO_model.params_u      JaxSSO/SSO_model.py:243-248
+ *   jsso_backward       *_sparse_solve_bwd + transposes JaxSSO/solver.py:138-166, 221-248
+ *
+ * Conventions
+ *   - all floating point is FP64, all indices int32 (model.py:284-313).
+ *   - dof order per node [ux,uy,uz,rx,ry,rz], global dof = 6*node + k (model.py:197).
+ *   - crds (n_node,3) row-major; prop_q (n_quad,5) = t,E,nu,kx_mod,ky_mod;
+ *     prop_b (n_beam,6) = E,G,Iy,Iz,J,A (model.py:315-338).
+ *   - pointers named *_d are device pointers on the handle's device, *_h host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
+ *     enqueued on it; calls that return statistics synchronise it before returning.
+ *   - block-CSR values are stored per block COLUMN-major: entry (i,j) of block s is
+ *     vals[36*s + 6*j + i].
+ *   - every function returns 0 on success or a JSSO_ERR_* code; the message is
+ *     available from jsso_last_error().  No exception crosses this boundary.
+ *   - a handle is not re-entrant: one host thread at a time.
+ */
+#ifndef JSSO_H_
+#define JSSO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  JSSO_OK = 0,
+  JSSO_ERR_ARG = 1,             /* bad argument / inconsistent mesh */
+  JSSO_ERR_CUDA = 2,            /* a CUDA runtime call or kernel failed */
+  JSSO_ERR_NOCONV = 3,          /* PCG hit maxiter before reaching rtol */
+  JSSO_ERR_NAN = 4,             /* NaN/Inf met in the solve */
+  JSSO_ERR_BADJAC = 5,          /* non-positive Jacobian determinant in a quad */
+  JSSO_ERR_DEGENERATE_BEAM = 6, /* beam exactly parallel to global Y (element.py:92-94) */
+  JSSO_ERR_NOT_SPD = 7,         /* diagonal block not positive definite / kx_mod != ky_mod */
+  JSSO_ERR_NCCL = 8,
+  JSSO_ERR_STATE = 9            /* call order violated (e.g. solve before assemble) */
+};
+
+typedef struct jsso_handle jsso_handle;
+
+/* device ordinal for a symbolic-only handle: jsso_create runs the host symbolic pass,
+ * jsso_get_sizes / jsso_pattern work, every compute entry point returns JSSO_ERR_STATE. */
+#define JSSO_DEVICE_NONE (-1)
+
+typedef struct {
+  int32_t n_node;            /* local nodes (owned first, then ghosts) */
+  int32_t n_row;             /* owned nodes = block rows of K kept on this GPU; = n_node on one GPU */
+  int32_t n_quad;
+  const int32_t* cnct_quads; /* host, (n_quad,4): i,j,m,n */
+  int32_t n_beam;
+  const int32_t* cnct_beams; /* host, (n_beam,2) */
+  int32_t n_known;
+  const int32_t* known;      /* host, prescribed (zero) dof ids */
+  int32_t device;            /* CUDA device ordinal */
+} jsso_mesh_desc;
+
+typedef struct {
+  int32_t n_node, n_row, n_quad, n_beam;
+  int64_t nnzb;     /* stored 6x6 blocks */
+  int64_t n_items;  /* (element, a, b) contributions = 16 n_quad + 4 n_beam on one GPU */
+  int32_t n_chunk;  /* assembly work chunks */
+} jsso_sizes;
+
+typedef struct {
+  int32_t iterations;
+  int32_t restarts;      /* residual replacements taken */
+  int32_t converged;
+  int32_t flags;         /* element flags seen in assembly: bit0 bad Jacobian, bit1 degenerate beam, bit2 kx!=ky */
+  double relres;         /* final TRUE relative residual |b - A x| / |b| of the block-Jacobi scaled system */
+  double relres_recur;   /* recurrence residual at exit */
+} jsso_stats;
+
+typedef struct {
+  double rtol;           /* relative residual target (scaled system); default 1e-10 */
+  int32_t maxiter;       /* default 200000 */
+  int32_t check_every;   /* iterations per convergence poll; default 50 */
+  int32_t use_x0;        /* 1: `u`/`x` holds an initial guess */
+  int32_t compliance;    /* jsso_backward only: 1 => g == f/2, take lam = u/2 (K symmetric) */
+} jsso_solve_opts;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+int jsso_create(const jsso_mesh_desc* desc, jsso_handle** out);
+void jsso_destroy(jsso_handle* h);
+const char* jsso_last_error(const jsso_handle* h); /* h may be NULL: last create error */
+int jsso_get_sizes(const jsso_handle* h, jsso_sizes* out);
+
+/* ---- symbolic pass results (host copies) -------------------------------------- */
+/* rowptr[n_row+1], colidx[nnzb] (sorted within each row): the bit-exact pattern. */
+int jsso_pattern(const jsso_handle* h, int32_t* rowptr_h, int32_t* colidx_h);
+
+/* ---- element stiffness, materialised (tests / ncu) ----------------------------- */
+/* ke_d: (n_quad,24,24) row-major, the reference's `data` layout (element.py:1236-1237). */
+int jsso_quad_ke(jsso_handle* h, const double* crds_d, const double* prop_q_d, double* ke_d, void* stream);
+/* ke_d: (n_beam,12,12) row-major (element.py:270-271). */
+int jsso_beam_ke(jsso_handle* h, const double* crds_d, const double* prop_b_d, double* ke_d, void* stream);
+
+/* ---- assembly ------------------------------------------------------------------ */
+/* Fused Ke + numeric assembly into the handle-owned block-CSR values (K_e never
+ * touches HBM).  apply_bc != 0 imposes the prescribed dofs (rows/cols -> identity). */
+int jsso_assemble(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
+                  int apply_bc, void* stream);
+/* Stand-alone segmented reduction of materialised element matrices. */
+int jsso_assemble_from_ke(jsso_handle* h, const double* ke_q_d, const double* ke_b_d, int apply_bc,
+                          void* stream);
+/* Copy the handle's values (nnzb*36, column-major blocks) to a device / host buffer. */
+int jsso_get_values(jsso_handle* h, double* vals_d, void* stream);
+int jsso_get_values_host(jsso_handle* h, double* vals_h);
+/* Element flags accumulated by the last assembly (see jsso_stats.flags). */
+int jsso_get_flags(jsso_handle* h, int32_t* flags_out);
+
+/* ---- linear algebra on the assembled matrix ------------------------------------- */
+/* y = K x with the current values (x has 6*n_node entries, y 6*n_row). */
+int jsso_spmv(jsso_handle* h, const double* x_d, double* y_d, void* stream);
+/* Block-Jacobi preconditioned CG on the assembled (BC-imposed) matrix:
+ * K x = b with b zeroed at prescribed dofs.  Synchronises `stream`. */
+int jsso_pcg(jsso_handle* h, const double* b_d, double* x_d, const jsso_solve_opts* opts,
+             jsso_stats* stats, void* stream);
+
+/* ---- adjoint sensitivity reduction ---------------------------------------------- */
+/* d_crds[n,c] = sum_e sum_ab (-lam_e[a] u_e[b]) dK_e[a,b]/dcrds[n,c], same for the
+ * element properties.  Any of the three outputs may be NULL. */
+int jsso_adjoint(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
+                 const double* u_d, const double* lam_d, double* d_crds_d, double* d_prop_q_d,
+                 double* d_prop_b_d, void* stream);
+
+/* ---- the drop-in pair (params_u and its VJP) ------------------------------------- */
+/* u = K(crds, props)^-1 f with zero prescribed displacements. */
+int jsso_forward(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
+                 const double* f_d, double* u_d, const jsso_solve_opts* opts, jsso_stats* stats,
+                 void* stream);
+/* Given g = dL/du: solve K^T lam = g (lam = 0 at prescribed dofs), then reduce the
+ * element sensitivities.  Uses the matrix assembled by the preceding jsso_forward
+ * (same crds/props).  lam_d may be NULL. */
+int jsso_backward(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
+                  const double* u_d, const double* g_d, double* d_crds_d, double* d_prop_q_d,
+                  double* d_prop_b_d, double* lam_d, const jsso_solve_opts* opts, jsso_stats* stats,
+                  void* stream);
+
+/* ---- host-buffer convenience (end-to-end path: H2D, forward, backward, D2H) ------- */
+/* Strain-energy objective 0.5 f.u (SSO_model.py:297-301) and its gradient.
+ * All pointers are HOST pointers; d_* outputs may be NULL. */
+int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double* prop_q_h,
+                             const double* prop_b_h, const double* f_h, double* value_out, double* u_h,
+                             double* d_crds_h, double* d_prop_q_h, double* d_prop_b_h,
+                             const jsso_solve_opts* opts, jsso_stats* fwd_stats, jsso_stats* bwd_stats);
+
+/* ---- multi-GPU: halo exchange plan + NCCL communicator (one process per GPU) ------- */
+/* 128-byte NCCL unique id, generated by rank 0 and distributed by the caller. */
+int jsso_nccl_unique_id(uint8_t id_out[128]);
+/* n_peer peers; peer p receives send_idx[send_ptr[p]..send_ptr[p+1]) (owned node ids)
+ * and fills ghost nodes [recv_start[p], recv_start[p] + recv_count[p]). */
+int jsso_set_halo(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_peer,
+                  const int32_t* peer_rank, const int32_t* send_ptr, const int32_t* send_idx,
+                  const int32_t* recv_start, const int32_t* recv_count);
+/* Fill the ghost entries of a 6-dof-per-node vector from their owners. */
+int jsso_halo_exchange(jsso_handle* h, double* vec_d, void* stream);
+
+/* ---- thin device-memory utilities for bindings without their own CUDA runtime ------ */
+int jsso_set_device(int device);
+void* jsso_dev_alloc(size_t bytes);
+void jsso_dev_free(void* p);
+void* jsso_host_alloc_pinned(size_t bytes);
+void jsso_host_free_pinned(void* p);
+int jsso_memcpy_h2d(void* dst_d, const void* src_h, size_t bytes, void* stream);
+int jsso_memcpy_d2h(void* dst_h, const void* src_d, size_t bytes, void* stream);
+int jsso_memset(void* dst_d, int value, size_t bytes, void* stream);
+int jsso_stream_sync(void* stream);
+int jsso_device_count(void);
+/* CUDA-event timing on a caller stream (bench.py): returns an opaque event. */
+void* jsso_event_create(void);
+int jsso_event_record(void* ev, void* stream);
+int jsso_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out); /* syncs on ev_stop */
+void jsso_event_destroy(void* ev);
+/* Number of kernels this library has launched since load (bench `gpu_launches`). */
+int64_t jsso_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSSO_H_ */

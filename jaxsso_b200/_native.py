@@ -1,0 +1,343 @@
+"""ctypes binding of libjsso.so (include/jsso.h).
+
+There is NO CPU fallback: importing this module without the built library, or
+creating a handle without a CUDA device, raises.  Device memory is managed
+through the library's own thin cudart wrappers, so the product path needs
+neither PyTorch nor cuda-python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libjsso.so')
+
+ERR_NAMES = {0: 'OK', 1: 'ARG', 2: 'CUDA', 3: 'NOCONV', 4: 'NAN', 5: 'BADJAC', 6: 'DEGENERATE_BEAM',
+             7: 'NOT_SPD', 8: 'NCCL', 9: 'STATE'}
+JSSO_ERR_NOCONV = 3
+
+
+class JssoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'libjsso error {code} ({ERR_NAMES.get(code, "?")}): {msg}')
+        self.code = code
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [('n_node', C.c_int32), ('n_row', C.c_int32), ('n_quad', C.c_int32),
+                ('cnct_quads', C.c_void_p), ('n_beam', C.c_int32), ('cnct_beams', C.c_void_p),
+                ('n_known', C.c_int32), ('known', C.c_void_p), ('device', C.c_int32)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [('n_node', C.c_int32), ('n_row', C.c_int32), ('n_quad', C.c_int32), ('n_beam', C.c_int32),
+                ('nnzb', C.c_int64), ('n_items', C.c_int64), ('n_chunk', C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [('iterations', C.c_int32), ('restarts', C.c_int32), ('converged', C.c_int32),
+                ('flags', C.c_int32), ('relres', C.c_double), ('relres_recur', C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [('rtol', C.c_double), ('maxiter', C.c_int32), ('check_every', C.c_int32),
+                ('use_x0', C.c_int32), ('compliance', C.c_int32)]
+
+
+# every symbol include/jsso.h declares (checked by tests/test_abi.py)
+SYMBOLS = ['jsso_create', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
+           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
+           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_adjoint',
+           'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_nccl_unique_id',
+           'jsso_set_halo', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
+           'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
+           'jsso_memset', 'jsso_stream_sync', 'jsso_device_count', 'jsso_event_create',
+           'jsso_event_record', 'jsso_event_elapsed_ms', 'jsso_event_destroy', 'jsso_launch_count']
+
+_lib = None
+
+
+def lib():
+    """Load libjsso.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing: build it with `python -m jaxsso_b200.build` '
+                          '(jaxsso_b200 has no CPU fallback)')
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.jsso_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(vp)]
+    L.jsso_destroy.argtypes = [vp]
+    L.jsso_destroy.restype = None
+    L.jsso_last_error.argtypes = [vp]
+    L.jsso_last_error.restype = C.c_char_p
+    L.jsso_get_sizes.argtypes = [vp, C.POINTER(Sizes)]
+    L.jsso_pattern.argtypes = [vp, vp, vp]
+    L.jsso_quad_ke.argtypes = [vp, vp, vp, vp, vp]
+    L.jsso_beam_ke.argtypes = [vp, vp, vp, vp, vp]
+    L.jsso_assemble.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    L.jsso_assemble_from_ke.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.jsso_get_values.argtypes = [vp, vp, vp]
+    L.jsso_get_values_host.argtypes = [vp, vp]
+    L.jsso_get_flags.argtypes = [vp, C.POINTER(i32)]
+    L.jsso_spmv.argtypes = [vp, vp, vp, vp]
+    L.jsso_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
+    L.jsso_adjoint.argtypes = [vp] + [vp] * 8 + [vp]
+    L.jsso_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
+    L.jsso_backward.argtypes = [vp] + [vp] * 9 + [C.POINTER(SolveOpts), C.POINTER(Stats), vp]
+    L.jsso_value_and_grad_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(dbl), vp, vp, vp, vp,
+                                           C.POINTER(SolveOpts), C.POINTER(Stats), C.POINTER(Stats)]
+    L.jsso_nccl_unique_id.argtypes = [vp]
+    L.jsso_set_halo.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.jsso_halo_exchange.argtypes = [vp, vp, vp]
+    L.jsso_set_device.argtypes = [C.c_int]
+    L.jsso_dev_alloc.argtypes = [C.c_size_t]
+    L.jsso_dev_alloc.restype = vp
+    L.jsso_dev_free.argtypes = [vp]
+    L.jsso_dev_free.restype = None
+    L.jsso_host_alloc_pinned.argtypes = [C.c_size_t]
+    L.jsso_host_alloc_pinned.restype = vp
+    L.jsso_host_free_pinned.argtypes = [vp]
+    L.jsso_host_free_pinned.restype = None
+    L.jsso_memcpy_h2d.argtypes = [vp, vp, C.c_size_t, vp]
+    L.jsso_memcpy_d2h.argtypes = [vp, vp, C.c_size_t, vp]
+    L.jsso_memset.argtypes = [vp, C.c_int, C.c_size_t, vp]
+    L.jsso_stream_sync.argtypes = [vp]
+    L.jsso_device_count.argtypes = []
+    L.jsso_event_create.argtypes = []
+    L.jsso_event_create.restype = vp
+    L.jsso_event_record.argtypes = [vp, vp]
+    L.jsso_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.jsso_event_destroy.argtypes = [vp]
+    L.jsso_event_destroy.restype = None
+    L.jsso_launch_count.argtypes = []
+    L.jsso_launch_count.restype = i64
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceArray:
+    """A flat device buffer with a NumPy dtype/shape tag."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self.ptr = lib().jsso_dev_alloc(max(self.nbytes, 8))
+        if not self.ptr:
+            raise MemoryError(f'cudaMalloc({self.nbytes}) failed')
+
+    @classmethod
+    def from_host(cls, a, dtype=None, stream=None):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        d = cls(a.shape, a.dtype)
+        d.upload(a, stream)
+        return d
+
+    def upload(self, a, stream=None):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        if self.nbytes:
+            rc = lib().jsso_memcpy_h2d(self.ptr, _ptr(a), self.nbytes, stream)
+            if rc:
+                raise JssoError(rc, 'memcpy h2d')
+            lib().jsso_stream_sync(stream)   # the source is pageable NumPy memory
+
+    def download(self, stream=None):
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            rc = lib().jsso_memcpy_d2h(_ptr(out), self.ptr, self.nbytes, stream)
+            if rc:
+                raise JssoError(rc, 'memcpy d2h')
+        return out
+
+    def zero(self, stream=None):
+        lib().jsso_memset(self.ptr, 0, self.nbytes, stream)
+
+    def free(self):
+        if getattr(self, 'ptr', None):
+            lib().jsso_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _dp(a):
+    """Device pointer of a DeviceArray / raw int / None."""
+    if a is None:
+        return None
+    if isinstance(a, DeviceArray):
+        return a.ptr
+    return C.c_void_p(int(a))
+
+
+def make_opts(rtol=1e-10, maxiter=200000, check_every=50, use_x0=False, compliance=False):
+    return SolveOpts(float(rtol), int(maxiter), int(check_every), int(bool(use_x0)), int(bool(compliance)))
+
+
+class Handle:
+    """One frozen model on one GPU (jsso_handle)."""
+
+    def __init__(self, n_node, cnct_quads=None, cnct_beams=None, known=None, device=0, n_row=None):
+        L = lib()
+        cq = np.ascontiguousarray(np.zeros((0, 4)) if cnct_quads is None else cnct_quads, dtype=np.int32).reshape(-1, 4)
+        cb = np.ascontiguousarray(np.zeros((0, 2)) if cnct_beams is None else cnct_beams, dtype=np.int32).reshape(-1, 2)
+        kn = np.ascontiguousarray(np.zeros(0) if known is None else known, dtype=np.int32).ravel()
+        self._keep = (cq, cb, kn)
+        desc = MeshDesc(int(n_node), int(n_node if n_row is None else n_row), cq.shape[0], _ptr(cq),
+                        cb.shape[0], _ptr(cb), kn.shape[0], _ptr(kn), int(device))
+        h = C.c_void_p()
+        rc = L.jsso_create(C.byref(desc), C.byref(h))
+        if rc:
+            raise JssoError(rc, L.jsso_last_error(None).decode())
+        self.h = h
+        s = Sizes()
+        L.jsso_get_sizes(self.h, C.byref(s))
+        self.sizes = s
+        self.n_node, self.n_row, self.n_quad, self.n_beam = s.n_node, s.n_row, s.n_quad, s.n_beam
+        self.nnzb, self.n_items, self.n_chunk = s.nnzb, s.n_items, s.n_chunk
+        self.device = device
+
+    def _ck(self, rc, allow=()):
+        if rc and rc not in allow:
+            raise JssoError(rc, lib().jsso_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, 'h', None):
+            lib().jsso_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- symbolic
+    def pattern(self):
+        rowptr = np.empty(self.n_row + 1, np.int32)
+        colidx = np.empty(self.nnzb, np.int32)
+        self._ck(lib().jsso_pattern(self.h, _ptr(rowptr), _ptr(colidx)))
+        return rowptr, colidx
+
+    # ---- element matrices
+    def quad_ke(self, crds, prop_q, out=None, stream=None):
+        out = DeviceArray((self.n_quad, 24, 24)) if out is None else out
+        self._ck(lib().jsso_quad_ke(self.h, _dp(crds), _dp(prop_q), _dp(out), stream))
+        return out
+
+    def beam_ke(self, crds, prop_b, out=None, stream=None):
+        out = DeviceArray((self.n_beam, 12, 12)) if out is None else out
+        self._ck(lib().jsso_beam_ke(self.h, _dp(crds), _dp(prop_b), _dp(out), stream))
+        return out
+
+    # ---- assembly
+    def assemble(self, crds, prop_q, prop_b, apply_bc=True, stream=None):
+        self._ck(lib().jsso_assemble(self.h, _dp(crds), _dp(prop_q), _dp(prop_b), int(apply_bc), stream))
+
+    def assemble_from_ke(self, ke_q, ke_b, apply_bc=True, stream=None):
+        self._ck(lib().jsso_assemble_from_ke(self.h, _dp(ke_q), _dp(ke_b), int(apply_bc), stream))
+
+    def values_host(self):
+        """(nnzb, 6, 6) blocks in the usual [row, col] orientation (transposed from
+        the library's column-major block storage)."""
+        v = np.empty((self.nnzb, 6, 6))
+        self._ck(lib().jsso_get_values_host(self.h, _ptr(v)))
+        return np.ascontiguousarray(v.transpose(0, 2, 1))
+
+    def flags(self):
+        f = C.c_int32()
+        self._ck(lib().jsso_get_flags(self.h, C.byref(f)))
+        return f.value
+
+    # ---- linear algebra
+    def spmv(self, x, y, stream=None):
+        self._ck(lib().jsso_spmv(self.h, _dp(x), _dp(y), stream))
+
+    def pcg(self, b, x, opts=None, stream=None, allow_noconv=False):
+        st = Stats()
+        o = opts or make_opts()
+        self._ck(lib().jsso_pcg(self.h, _dp(b), _dp(x), C.byref(o), C.byref(st), stream),
+                 allow=(JSSO_ERR_NOCONV,) if allow_noconv else ())
+        return st
+
+    # ---- adjoint
+    def adjoint(self, crds, prop_q, prop_b, u, lam, d_crds=None, d_prop_q=None, d_prop_b=None, stream=None):
+        self._ck(lib().jsso_adjoint(self.h, _dp(crds), _dp(prop_q), _dp(prop_b), _dp(u), _dp(lam),
+                                    _dp(d_crds), _dp(d_prop_q), _dp(d_prop_b), stream))
+
+    # ---- drop-in pair
+    def forward(self, crds, prop_q, prop_b, f, u, opts=None, stream=None):
+        st = Stats()
+        o = opts or make_opts()
+        self._ck(lib().jsso_forward(self.h, _dp(crds), _dp(prop_q), _dp(prop_b), _dp(f), _dp(u),
+                                    C.byref(o), C.byref(st), stream))
+        return st
+
+    def backward(self, crds, prop_q, prop_b, u, g, d_crds=None, d_prop_q=None, d_prop_b=None, lam=None,
+                 opts=None, stream=None):
+        st = Stats()
+        o = opts or make_opts()
+        self._ck(lib().jsso_backward(self.h, _dp(crds), _dp(prop_q), _dp(prop_b), _dp(u), _dp(g),
+                                     _dp(d_crds), _dp(d_prop_q), _dp(d_prop_b), _dp(lam),
+                                     C.byref(o), C.byref(st), stream))
+        return st
+
+    def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None):
+        """End-to-end strain-energy value + gradient with HOST (NumPy) buffers."""
+        crds = np.ascontiguousarray(crds, np.float64)
+        prop_q = np.ascontiguousarray(prop_q, np.float64)
+        prop_b = np.ascontiguousarray(prop_b, np.float64)
+        f = np.ascontiguousarray(f, np.float64)
+        u = np.empty(6 * self.n_node)
+        dc = np.empty((self.n_node, 3)) if 'crds' in want else None
+        dq = np.empty((self.n_quad, 5)) if ('prop_q' in want and self.n_quad) else None
+        db = np.empty((self.n_beam, 6)) if ('prop_b' in want and self.n_beam) else None
+        val = C.c_double()
+        fs, bs = Stats(), Stats()
+        o = opts or make_opts()
+        self._ck(lib().jsso_value_and_grad_host(self.h, _ptr(crds), _ptr(prop_q), _ptr(prop_b), _ptr(f),
+                                                C.byref(val), _ptr(u), _ptr(dc), _ptr(dq), _ptr(db),
+                                                C.byref(o), C.byref(fs), C.byref(bs)))
+        return val.value, u, dc, dq, db, fs, bs
+
+    # ---- multi-GPU
+    def set_halo(self, nccl_id, rank, n_rank, peer_rank, send_ptr, send_idx, recv_start, recv_count):
+        a = [np.ascontiguousarray(x, np.int32) for x in (peer_rank, send_ptr, send_idx, recv_start, recv_count)]
+        idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
+        self._ck(lib().jsso_set_halo(self.h, _ptr(idb), rank, n_rank, len(a[0]), *[_ptr(x) for x in a]))
+
+    def halo_exchange(self, vec, stream=None):
+        self._ck(lib().jsso_halo_exchange(self.h, _dp(vec), stream))
+
+
+def nccl_unique_id():
+    buf = np.zeros(128, np.uint8)
+    rc = lib().jsso_nccl_unique_id(_ptr(buf))
+    if rc:
+        raise JssoError(rc, lib().jsso_last_error(None).decode())
+    return buf.tobytes()
+
+
+def bsr_to_scipy(rowptr, colidx, blocks, n_col_nodes=None):
+    """scipy.sparse.bsr_matrix from pattern + (nnzb,6,6) [row,col]-oriented blocks."""
+    import scipy.sparse as sp
+    n_row = rowptr.shape[0] - 1
+    n_col = n_row if n_col_nodes is None else n_col_nodes
+    return sp.bsr_matrix((blocks, colidx, rowptr), shape=(6 * n_row, 6 * n_col))

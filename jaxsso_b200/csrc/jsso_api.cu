@@ -1,0 +1,715 @@
+// libjsso.so -- C ABI (include/jsso.h) over the sm_100a kernels.
+#include "../../include/jsso.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jsso_adjoint.cuh"
+#include "jsso_assemble.cuh"
+#include "jsso_solver.cuh"
+#include "jsso_symbolic.h"
+
+using namespace jsso;
+
+static std::atomic<long long> g_launches{0};
+static thread_local std::string g_create_error;
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct HaloPeer {
+  int rank;
+  int send_off, send_cnt;   // into send_idx (nodes)
+  int recv_start, recv_cnt; // ghost node range
+};
+
+struct jsso_handle {
+  int device = 0;
+  Symbolic sym;
+  std::string err;
+  // device copies of the symbolic data
+  int32_t *cnct_q = nullptr, *cnct_b = nullptr;
+  int32_t *rowptr = nullptr, *colidx = nullptr, *blk_row = nullptr, *diag_slot = nullptr;
+  int32_t *blk_item_ptr = nullptr, *item_code = nullptr;
+  uint8_t *item_lel = nullptr, *node_mask = nullptr;
+  int32_t *chunk_blk = nullptr, *chunk_el_ptr = nullptr, *chunk_els = nullptr;
+  int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
+  // numeric state
+  double* vals = nullptr;   // nnzb*36, column-major blocks
+  double* W = nullptr;      // n_node*36 block-Jacobi factors (ghosts filled by halo exchange)
+  double *vb = nullptr, *vx = nullptr, *vr = nullptr, *vp = nullptr, *vq = nullptr;  // PCG vectors
+  double *corner_q = nullptr, *corner_b = nullptr;   // per-corner gradient partials
+  double *tmp_lam = nullptr, *tmp_g = nullptr;
+  CgScalars* sc = nullptr;
+  CgScalars* sc_host = nullptr;  // pinned
+  double* partials = nullptr;
+  unsigned* counters = nullptr;
+  int* flags = nullptr;
+  int* flags_host = nullptr;     // pinned
+  bool assembled = false, assembled_bc = false, scaled = false;
+  int red_blocks = 148 * 4;
+  int spmv_blocks = 148 * 8;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_rank = 1;
+  std::vector<HaloPeer> peers;
+  int32_t* send_idx = nullptr;
+  double *send_buf = nullptr;
+  int n_send_nodes = 0;
+  // host staging for the host-buffer entry point
+  double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
+  double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
+  // device scratch of the host-buffer entry point
+  double *s_crds = nullptr, *s_pq = nullptr, *s_pb = nullptr, *s_f = nullptr, *s_u = nullptr;
+  double *s_dc = nullptr, *s_dpq = nullptr, *s_dpb = nullptr;
+};
+
+static int fail(jsso_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, JSSO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+#define CKL(name)                                                                             \
+  do {                                                                                        \
+    LAUNCHED();                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, JSSO_ERR_CUDA, std::string(name) + " launch: " + cudaGetErrorString(e_)); \
+  } while (0)
+#define CKN(call)                                                                             \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return fail(h, JSSO_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));      \
+  } while (0)
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+  const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)dst, bytes);
+  if (e != cudaSuccess) return e;
+  if (v.size()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+template <class T>
+static cudaError_t dalloc(T** dst, size_t n) {
+  return cudaMalloc((void**)dst, (n ? n : 1) * sizeof(T));
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+#define NEED_GPU()                                                                            \
+  do {                                                                                        \
+    if (h->device == JSSO_DEVICE_NONE)                                                        \
+      return fail(h, JSSO_ERR_STATE, "symbolic-only handle (device = JSSO_DEVICE_NONE): no compute"); \
+  } while (0)
+
+extern "C" {
+
+const char* jsso_last_error(const jsso_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
+  jsso_handle* h = nullptr;
+  if (!d || !out) return fail(h, JSSO_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (d->device != JSSO_DEVICE_NONE) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(h, JSSO_ERR_CUDA, "no CUDA device: the jaxsso_b200 hot path has no CPU fallback");
+    if (d->device < 0 || d->device >= ndev) return fail(h, JSSO_ERR_ARG, "bad device ordinal");
+  }
+  jsso_handle* nh = new jsso_handle();
+  nh->device = d->device;
+  std::string msg = build_symbolic(d->n_node, d->n_row, d->n_quad, d->cnct_quads, d->n_beam, d->cnct_beams,
+                                   d->n_known, d->known, nh->sym);
+  if (!msg.empty()) { delete nh; return fail(h, JSSO_ERR_ARG, msg); }
+  h = nh;
+  if (d->device == JSSO_DEVICE_NONE) { *out = h; return JSSO_OK; }   // symbolic-only handle
+  const Symbolic& S = h->sym;
+  CK(cudaSetDevice(h->device));
+  std::vector<int32_t> cq(d->cnct_quads, d->cnct_quads + 4 * (size_t)d->n_quad);
+  std::vector<int32_t> cb(d->cnct_beams, d->cnct_beams + 2 * (size_t)d->n_beam);
+  CK(upload(&h->cnct_q, cq)); CK(upload(&h->cnct_b, cb));
+  CK(upload(&h->rowptr, S.rowptr)); CK(upload(&h->colidx, S.colidx));
+  CK(upload(&h->blk_row, S.blk_row)); CK(upload(&h->diag_slot, S.diag_slot));
+  CK(upload(&h->blk_item_ptr, S.blk_item_ptr)); CK(upload(&h->item_code, S.item_code));
+  CK(upload(&h->item_lel, S.item_lel)); CK(upload(&h->node_mask, S.node_mask));
+  CK(upload(&h->chunk_blk, S.chunk_blk)); CK(upload(&h->chunk_el_ptr, S.chunk_el_ptr));
+  CK(upload(&h->chunk_els, S.chunk_els));
+  CK(upload(&h->node_inc_ptr, S.node_inc_ptr)); CK(upload(&h->node_inc, S.node_inc));
+  const size_t nd = 6 * (size_t)S.n_node;
+  CK(dalloc(&h->vals, (size_t)S.nnzb() * 36));
+  CK(dalloc(&h->W, (size_t)S.n_node * 36));
+  CK(dalloc(&h->vb, nd)); CK(dalloc(&h->vx, nd)); CK(dalloc(&h->vr, nd));
+  CK(dalloc(&h->vp, nd)); CK(dalloc(&h->vq, nd));
+  CK(dalloc(&h->tmp_lam, nd)); CK(dalloc(&h->tmp_g, nd));
+  CK(cudaMemset(h->vp, 0, nd * sizeof(double)));
+  CK(cudaMemset(h->vx, 0, nd * sizeof(double)));
+  CK(dalloc(&h->corner_q, (size_t)S.n_quad * 12)); CK(dalloc(&h->corner_b, (size_t)S.n_beam * 6));
+  CK(dalloc(&h->sc, 1)); CK(cudaMemset(h->sc, 0, sizeof(CgScalars)));
+  CK(cudaMallocHost((void**)&h->sc_host, sizeof(CgScalars)));
+  CK(dalloc(&h->partials, 2 * (size_t)RED_MAX_BLOCKS));
+  CK(dalloc(&h->counters, 4)); CK(cudaMemset(h->counters, 0, 4 * sizeof(unsigned)));
+  CK(dalloc(&h->flags, 1)); CK(cudaMemset(h->flags, 0, sizeof(int)));
+  CK(cudaMallocHost((void**)&h->flags_host, sizeof(int)));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  h->red_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 4);
+  h->spmv_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 8);
+  CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          FUSED_SMEM_DOUBLES * (int)sizeof(double)));
+  *out = h;
+  return JSSO_OK;
+}
+
+void jsso_destroy(jsso_handle* h) {
+  if (!h) return;
+  if (h->device == JSSO_DEVICE_NONE) { delete h; return; }
+  cudaSetDevice(h->device);
+  void* dev[] = {h->cnct_q, h->cnct_b, h->rowptr, h->colidx, h->blk_row, h->diag_slot, h->blk_item_ptr,
+                 h->item_code, h->item_lel, h->node_mask, h->chunk_blk, h->chunk_el_ptr, h->chunk_els,
+                 h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
+                 h->corner_q, h->corner_b, h->tmp_lam, h->tmp_g, h->sc, h->partials, h->counters, h->flags,
+                 h->send_idx, h->send_buf, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
+                 h->s_dpb};
+  for (void* p : dev) if (p) cudaFree(p);
+  void* hst[] = {h->sc_host, h->flags_host, h->h_crds, h->h_pq, h->h_pb, h->h_f, h->h_u, h->h_dc, h->h_dpq,
+                 h->h_dpb};
+  for (void* p : hst) if (p) cudaFreeHost(p);
+  if (h->comm) ncclCommDestroy(h->comm);
+  delete h;
+}
+
+int jsso_get_sizes(const jsso_handle* h, jsso_sizes* o) {
+  if (!h || !o) return JSSO_ERR_ARG;
+  o->n_node = h->sym.n_node; o->n_row = h->sym.n_row; o->n_quad = h->sym.n_quad; o->n_beam = h->sym.n_beam;
+  o->nnzb = h->sym.nnzb(); o->n_items = h->sym.n_items(); o->n_chunk = h->sym.n_chunk();
+  return JSSO_OK;
+}
+
+int jsso_pattern(const jsso_handle* h, int32_t* rowptr, int32_t* colidx) {
+  if (!h || !rowptr || !colidx) return JSSO_ERR_ARG;
+  std::memcpy(rowptr, h->sym.rowptr.data(), h->sym.rowptr.size() * sizeof(int32_t));
+  std::memcpy(colidx, h->sym.colidx.data(), h->sym.colidx.size() * sizeof(int32_t));
+  return JSSO_OK;
+}
+
+int jsso_quad_ke(jsso_handle* h, const double* crds, const double* prop_q, double* ke, void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  const int n = h->sym.n_quad;
+  if (n == 0) return JSSO_OK;
+  quad_ke_kernel<<<cdiv(n, 16), 256, 0, (cudaStream_t)stream>>>(n, crds, h->cnct_q, prop_q, ke, h->flags);
+  CKL("quad_ke_kernel");
+  return JSSO_OK;
+}
+
+int jsso_beam_ke(jsso_handle* h, const double* crds, const double* prop_b, double* ke, void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  const int n = h->sym.n_beam;
+  if (n == 0) return JSSO_OK;
+  beam_ke_kernel<<<cdiv(4LL * n, 256), 256, 0, (cudaStream_t)stream>>>(n, crds, h->cnct_b, prop_b, ke, h->flags);
+  CKL("beam_ke_kernel");
+  return JSSO_OK;
+}
+
+int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, int apply_bc,
+                  void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  AsmArgs A;
+  A.crds = crds; A.cnct_q = h->cnct_q; A.prop_q = prop_q; A.cnct_b = h->cnct_b; A.prop_b = prop_b;
+  A.chunk_blk = h->chunk_blk; A.chunk_el_ptr = h->chunk_el_ptr; A.chunk_els = h->chunk_els;
+  A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
+  A.blk_row = h->blk_row; A.colidx = h->colidx; A.node_mask = h->node_mask;
+  A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
+  if (h->sym.nnzb() > 0) {
+    assemble_fused_kernel<<<h->sym.n_chunk(), kChunkItems, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
+    CKL("assemble_fused_kernel");
+  }
+  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false;
+  return JSSO_OK;
+}
+
+int jsso_assemble_from_ke(jsso_handle* h, const double* ke_q, const double* ke_b, int apply_bc, void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  const long long n_out = (long long)h->sym.nnzb() * 36;
+  if (n_out > 0) {
+    assemble_from_ke_kernel<<<cdiv(n_out, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_out, h->sym.n_quad, ke_q, ke_b, h->blk_item_ptr, h->item_code, h->blk_row, h->colidx, h->node_mask,
+        h->vals, apply_bc);
+    CKL("assemble_from_ke_kernel");
+  }
+  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false;
+  return JSSO_OK;
+}
+
+int jsso_get_values(jsso_handle* h, double* vals_d, void* stream) {
+  if (!h || !vals_d) return JSSO_ERR_ARG;
+  NEED_GPU();
+  if (!h->assembled) return fail(h, JSSO_ERR_STATE, "no assembled matrix");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(vals_d, h->vals, (size_t)h->sym.nnzb() * 36 * sizeof(double), cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return JSSO_OK;
+}
+
+int jsso_get_values_host(jsso_handle* h, double* vals_h) {
+  if (!h || !vals_h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  if (!h->assembled) return fail(h, JSSO_ERR_STATE, "no assembled matrix");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(vals_h, h->vals, (size_t)h->sym.nnzb() * 36 * sizeof(double), cudaMemcpyDeviceToHost));
+  return JSSO_OK;
+}
+
+int jsso_get_flags(jsso_handle* h, int32_t* out) {
+  if (!h || !out) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, h->flags, sizeof(int), cudaMemcpyDeviceToHost));
+  return JSSO_OK;
+}
+
+// ---------------------------------------------------------------- halo exchange
+int jsso_nccl_unique_id(uint8_t id_out[128]) {
+  jsso_handle* h = nullptr;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  CKN(ncclGetUniqueId(&id));
+  std::memcpy(id_out, &id, 128);
+  return JSSO_OK;
+}
+
+int jsso_set_halo(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_peer,
+                  const int32_t* peer_rank, const int32_t* send_ptr, const int32_t* send_idx,
+                  const int32_t* recv_start, const int32_t* recv_count) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  h->rank = rank; h->n_rank = n_rank;
+  h->peers.clear();
+  for (int p = 0; p < n_peer; ++p)
+    h->peers.push_back(HaloPeer{peer_rank[p], send_ptr[p], send_ptr[p + 1] - send_ptr[p], recv_start[p],
+                                recv_count[p]});
+  h->n_send_nodes = n_peer ? send_ptr[n_peer] : 0;
+  std::vector<int32_t> si(send_idx, send_idx + h->n_send_nodes);
+  for (int v : si) if (v < 0 || v >= h->sym.n_row) return fail(h, JSSO_ERR_ARG, "halo send index not owned");
+  CK(upload(&h->send_idx, si));
+  CK(dalloc(&h->send_buf, (size_t)h->n_send_nodes * 36));
+  if (n_rank > 1) {
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_id, 128);
+    CKN(ncclCommInitRank(&h->comm, n_rank, id, rank));
+  }
+  return JSSO_OK;
+}
+
+// Fill the ghost part of a 6-doubles-per-node vector from the owning ranks: pack the
+// owned interface nodes, then one grouped ncclSend/ncclRecv per neighbour.
+static int halo_exchange_w(jsso_handle* h, double* vec, int width, cudaStream_t st) {
+  if (h->n_rank <= 1 || h->peers.empty()) return JSSO_OK;
+  if (width != 6) return fail(h, JSSO_ERR_ARG, "unsupported halo width");
+  if (h->n_send_nodes > 0) {
+    halo_pack_kernel<<<cdiv(6LL * h->n_send_nodes, 256), 256, 0, st>>>(h->n_send_nodes, h->send_idx, vec,
+                                                                      h->send_buf);
+    CKL("halo_pack_kernel");
+  }
+  CKN(ncclGroupStart());
+  for (const HaloPeer& p : h->peers) {
+    if (p.send_cnt)
+      CKN(ncclSend(h->send_buf + 6 * (size_t)p.send_off, 6 * (size_t)p.send_cnt, ncclDouble, p.rank, h->comm, st));
+    if (p.recv_cnt)
+      CKN(ncclRecv(vec + 6 * (size_t)p.recv_start, 6 * (size_t)p.recv_cnt, ncclDouble, p.rank, h->comm, st));
+  }
+  CKN(ncclGroupEnd());
+  return JSSO_OK;
+}
+
+int jsso_halo_exchange(jsso_handle* h, double* vec_d, void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  return halo_exchange_w(h, vec_d, 6, (cudaStream_t)stream);
+}
+
+static int allreduce_scalar(jsso_handle* h, double* p, int count, cudaStream_t st) {
+  if (h->n_rank <= 1) return JSSO_OK;
+  CKN(ncclAllReduce(p, p, count, ncclDouble, ncclSum, h->comm, st));
+  return JSSO_OK;
+}
+
+// ---------------------------------------------------------------- SpMV / PCG
+static int spmv_plain(jsso_handle* h, const double* x, double* y, cudaStream_t st) {
+  const int n_row = h->sym.n_row;
+  if (n_row == 0) return JSSO_OK;
+  const int blocks = std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32));
+  bsr_spmv_kernel<0><<<blocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, x, y, h->sc, 0,
+                                                   h->partials, h->counters);
+  CKL("bsr_spmv_kernel<0>");
+  return JSSO_OK;
+}
+
+int jsso_spmv(jsso_handle* h, const double* x, double* y, void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  if (!h->assembled) return fail(h, JSSO_ERR_STATE, "spmv before assemble");
+  CK(cudaSetDevice(h->device));
+  return spmv_plain(h, x, y, (cudaStream_t)stream);
+}
+
+// block-Jacobi scaling of the assembled matrix (once per assembly)
+static int ensure_scaled(jsso_handle* h, cudaStream_t st) {
+  if (h->scaled) return JSSO_OK;
+  const int n_row = h->sym.n_row;
+  if (n_row > 0) {
+    diag_factor_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->diag_slot, h->vals, h->W, h->flags);
+    CKL("diag_factor_kernel");
+  }
+  if (h->n_rank > 1) {
+    // ghost columns need the factor of their owner: W is (n_node, 6, 6) row-major, so row s of
+    // every factor is a strided 6-vector; exchange the six rows through a dof-vector scratch
+    const int n_node = h->sym.n_node;
+    for (int s = 0; s < 6; ++s) {
+      CK(cudaMemcpy2DAsync(h->vq, 6 * sizeof(double), h->W + 6 * s, 36 * sizeof(double), 6 * sizeof(double),
+                           n_node, cudaMemcpyDeviceToDevice, st));
+      int rc = halo_exchange_w(h, h->vq, 6, st);
+      if (rc) return rc;
+      CK(cudaMemcpy2DAsync(h->W + 6 * s, 36 * sizeof(double), h->vq, 6 * sizeof(double), 6 * sizeof(double),
+                           n_node, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  const long long nnzb = h->sym.nnzb();
+  if (nnzb > 0) {
+    scale_blocks_kernel<<<cdiv(nnzb, 128), 128, 0, st>>>(nnzb, h->blk_row, h->colidx, h->W, h->vals);
+    CKL("scale_blocks_kernel");
+  }
+  h->scaled = true;
+  return JSSO_OK;
+}
+
+static void default_opts(const jsso_solve_opts* in, jsso_solve_opts& o) {
+  o.rtol = 1e-10; o.maxiter = 200000; o.check_every = 50; o.use_x0 = 0; o.compliance = 0;
+  if (in) {
+    if (in->rtol > 0) o.rtol = in->rtol;
+    if (in->maxiter > 0) o.maxiter = in->maxiter;
+    if (in->check_every > 0) o.check_every = in->check_every;
+    o.use_x0 = in->use_x0; o.compliance = in->compliance;
+  }
+}
+
+// One CG iteration on the scaled system (3 kernels; + halo exchange and 2 scalar
+// all-reduces on several GPUs).
+static int cg_iteration(jsso_handle* h, int cur, cudaStream_t st) {
+  const int n_row = h->sym.n_row;
+  const long long n = 6LL * n_row;
+  int rc = halo_exchange_w(h, h->vp, 6, st);
+  if (rc) return rc;
+  const int sblocks = std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
+  bsr_spmv_kernel<1><<<sblocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, h->vp, h->vq, h->sc,
+                                                   cur, h->partials, h->counters);
+  CKL("bsr_spmv_kernel<1>");
+  if ((rc = allreduce_scalar(h, &h->sc->pq, 1, st))) return rc;
+  const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
+  cg_update_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vp, h->vq, h->vx, h->vr, h->sc, h->partials,
+                                                  h->counters + 1);
+  CKL("cg_update_kernel");
+  if ((rc = allreduce_scalar(h, &h->sc->rr[cur ^ 1], 1, st))) return rc;
+  cg_direction_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vr, h->vp, h->sc);
+  CKL("cg_direction_kernel");
+  return JSSO_OK;
+}
+
+// Solve A^ y = b^ (both already scaled) into h->vx; b^ in h->vb.
+static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, jsso_stats* stats,
+                           cudaStream_t st) {
+  const int n_row = h->sym.n_row;
+  const long long n = 6LL * n_row;
+  const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
+  int restarts = 0, total_iter = 0;
+  double relres_true = 0.0, relres_rec = 0.0;
+  bool first = true, converged = false;
+  int rc;
+  for (;;) {
+    // (re)start: r = b - A x
+    const double* q = nullptr;
+    if (!first || use_x0) {
+      if ((rc = halo_exchange_w(h, h->vx, 6, st))) return rc;
+      if ((rc = spmv_plain(h, h->vx, h->vq, st))) return rc;
+      q = h->vq;
+    } else {
+      CK(cudaMemsetAsync(h->vx, 0, 6 * (size_t)h->sym.n_node * sizeof(double), st));
+    }
+    if (first) {
+      cg_init_kernel<1><<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, q, h->vr, h->vp, h->sc, h->partials,
+                                                       h->counters + 2, o.rtol);
+      CKL("cg_init_kernel<1>");
+      if ((rc = allreduce_scalar(h, &h->sc->bb, 1, st))) return rc;
+    } else {
+      cg_init_kernel<0><<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, q, h->vr, h->vp, h->sc, h->partials,
+                                                       h->counters + 2, o.rtol);
+      CKL("cg_init_kernel<0>");
+    }
+    if (h->n_rank > 1) {
+      // rr[0] and rr[1] hold the same local value; reduce both
+      if ((rc = allreduce_scalar(h, &h->sc->rr[0], 2, st))) return rc;
+    }
+    first = false;
+    int cur = 0, it_local = 0;
+    bool stop = false;
+    while (!stop) {
+      const int batch = std::min(o.check_every, o.maxiter - total_iter - it_local);
+      if (batch <= 0) break;
+      for (int k = 0; k < batch; ++k) {
+        if ((rc = cg_iteration(h, cur, st))) return rc;
+        cur ^= 1;
+      }
+      it_local += batch;
+      CK(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const CgScalars& s = *h->sc_host;
+      const double rr = s.rr[cur];
+      if (!(rr == rr) || !(s.bb == s.bb)) {
+        if (stats) { stats->iterations = total_iter + s.iter; stats->converged = 0; }
+        return fail(h, JSSO_ERR_NAN, "PCG breakdown: NaN or non-positive curvature (matrix not SPD?)");
+      }
+      if (s.bb == 0.0) { stop = true; converged = true; relres_rec = 0.0; it_local = s.iter; break; }
+      relres_rec = std::sqrt(rr / s.bb);
+      if (!(rr > s.tol2 * s.bb)) { stop = true; it_local = s.iter; }
+    }
+    total_iter += it_local;
+    // true residual
+    if ((rc = halo_exchange_w(h, h->vx, 6, st))) return rc;
+    if ((rc = spmv_plain(h, h->vx, h->vq, st))) return rc;
+    residual_norm_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, h->vq, h->sc, h->partials, h->counters + 2);
+    CKL("residual_norm_kernel");
+    if ((rc = allreduce_scalar(h, &h->sc->aux, 1, st))) return rc;
+    CK(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    relres_true = (h->sc_host->bb > 0) ? std::sqrt(h->sc_host->aux / h->sc_host->bb) : 0.0;
+    if (relres_true <= o.rtol * 1.5 || h->sc_host->bb == 0.0) { converged = true; break; }
+    if (total_iter >= o.maxiter || restarts >= 20) break;
+    ++restarts;   // residual replacement: restart from the current iterate
+  }
+  if (stats) {
+    stats->iterations = total_iter; stats->restarts = restarts; stats->converged = converged ? 1 : 0;
+    stats->relres = relres_true; stats->relres_recur = relres_rec;
+  }
+  if (!converged) return fail(h, JSSO_ERR_NOCONV, "PCG did not reach rtol within maxiter");
+  return JSSO_OK;
+}
+
+// K x = b on the assembled BC-imposed matrix: scale, solve, unscale.
+static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_solve_opts& o, jsso_stats* stats,
+                        cudaStream_t st) {
+  if (!h->assembled || !h->assembled_bc)
+    return fail(h, JSSO_ERR_STATE, "solve needs a matrix assembled with apply_bc=1");
+  int rc = ensure_scaled(h, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->flags_host, h->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int fl = *h->flags_host;
+  if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->flags = fl; }
+  if (fl & FLAG_DEGBEAM) return fail(h, JSSO_ERR_DEGENERATE_BEAM, "beam parallel to global Y: K_e is unsymmetric in the reference (element.py:92-94); not solvable by CG");
+  if (fl & FLAG_UNSYM) return fail(h, JSSO_ERR_NOT_SPD, "kx_mod != ky_mod makes K unsymmetric (element.py:871-873); PCG path supports kx_mod == ky_mod only");
+  if (fl & FLAG_BADJAC) return fail(h, JSSO_ERR_BADJAC, "non-positive Jacobian determinant in a quad");
+  if (fl & 8) return fail(h, JSSO_ERR_NOT_SPD, "a diagonal 6x6 block is not positive definite");
+  const int n_row = h->sym.n_row;
+  if (n_row == 0) return JSSO_OK;
+  // b^ = W b (prescribed dofs zeroed), x0^ = W^-T x0 is not needed: we iterate on y = W^-T x, so
+  // an initial guess x0 must be mapped with y0 = L^T x0; keep it simple: y0 = 0 unless use_x0, then
+  // solve for the correction instead (b <- b - K x0 is done in scaled space via the restart path).
+  block_apply_kernel<0><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, b, h->node_mask, h->vb);
+  CKL("block_apply_kernel<0>");
+  rc = cg_solve_scaled(h, o, false, stats, st);
+  if (stats) stats->flags = fl;
+  if (rc && rc != JSSO_ERR_NOCONV) return rc;
+  block_apply_kernel<1><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->vx, nullptr, x);
+  CKL("block_apply_kernel<1>");
+  if (h->n_rank > 1) { int r2 = halo_exchange_w(h, x, 6, st); if (r2) return r2; }
+  CK(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int jsso_pcg(jsso_handle* h, const double* b, double* x, const jsso_solve_opts* opts, jsso_stats* stats,
+             void* stream) {
+  if (!h || !b || !x) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  jsso_solve_opts o; default_opts(opts, o);
+  return solve_system(h, b, x, o, stats, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- adjoint
+int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, const double* u,
+                 const double* lam, double* d_crds, double* d_prop_q, double* d_prop_b, void* stream) {
+  if (!h || !u || !lam) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Symbolic& S = h->sym;
+  if (S.n_quad > 0) {
+    quad_adjoint_kernel<<<cdiv(4LL * S.n_quad, 128), 128, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
+                                                                  d_crds ? h->corner_q : nullptr, d_prop_q);
+    CKL("quad_adjoint_kernel");
+  }
+  if (S.n_beam > 0) {
+    beam_adjoint_kernel<<<cdiv(2LL * S.n_beam, 128), 128, 0, st>>>(S.n_beam, crds, h->cnct_b, prop_b, u, lam,
+                                                                  d_crds ? h->corner_b : nullptr, d_prop_b,
+                                                                  h->flags);
+    CKL("beam_adjoint_kernel");
+  }
+  if (d_crds) {
+    node_gather_kernel<<<cdiv(3LL * S.n_node, 256), 256, 0, st>>>(S.n_node, S.n_quad, h->node_inc_ptr,
+                                                                 h->node_inc, h->corner_q, h->corner_b, d_crds);
+    CKL("node_gather_kernel");
+  }
+  return JSSO_OK;
+}
+
+// ---------------------------------------------------------------- forward / backward
+int jsso_forward(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, const double* f,
+                 double* u, const jsso_solve_opts* opts, jsso_stats* stats, void* stream) {
+  if (!h || !crds || !f || !u) return JSSO_ERR_ARG;
+  int rc = jsso_assemble(h, crds, prop_q, prop_b, 1, stream);
+  if (rc) return rc;
+  jsso_solve_opts o; default_opts(opts, o);
+  return solve_system(h, f, u, o, stats, (cudaStream_t)stream);
+}
+
+int jsso_backward(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, const double* u,
+                  const double* g, double* d_crds, double* d_prop_q, double* d_prop_b, double* lam,
+                  const jsso_solve_opts* opts, jsso_stats* stats, void* stream) {
+  if (!h || !crds || !u || (!g && !(opts && opts->compliance))) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  jsso_solve_opts o; default_opts(opts, o);
+  double* l = lam ? lam : h->tmp_lam;
+  const long long n = 6LL * h->sym.n_node;
+  if (o.compliance) {
+    // g = f/2 and K symmetric  =>  lam = u/2  (SSO_model.py:297-301)
+    scale_copy_kernel<<<std::max(1, std::min(h->red_blocks, cdiv(n, 256))), 256, 0, st>>>(n, 0.5, u, l);
+    CKL("scale_copy_kernel");
+    if (stats) std::memset(stats, 0, sizeof(*stats)), stats->converged = 1;
+  } else {
+    int rc = solve_system(h, g, l, o, stats, st);   // K symmetric => K^T lam = g is the same operator
+    if (rc) return rc;
+  }
+  return jsso_adjoint(h, crds, prop_q, prop_b, u, l, d_crds, d_prop_q, d_prop_b, stream);
+}
+
+static int ensure_host_staging(jsso_handle* h) {
+  if (h->h_crds) return JSSO_OK;
+  const Symbolic& S = h->sym;
+  CK(cudaMallocHost((void**)&h->h_crds, sizeof(double) * 3 * (size_t)S.n_node));
+  CK(cudaMallocHost((void**)&h->h_pq, sizeof(double) * (5 * (size_t)S.n_quad + 1)));
+  CK(cudaMallocHost((void**)&h->h_pb, sizeof(double) * (6 * (size_t)S.n_beam + 1)));
+  CK(cudaMallocHost((void**)&h->h_f, sizeof(double) * 6 * (size_t)S.n_node));
+  CK(cudaMallocHost((void**)&h->h_u, sizeof(double) * 6 * (size_t)S.n_node));
+  CK(cudaMallocHost((void**)&h->h_dc, sizeof(double) * 3 * (size_t)S.n_node));
+  CK(cudaMallocHost((void**)&h->h_dpq, sizeof(double) * (5 * (size_t)S.n_quad + 1)));
+  CK(cudaMallocHost((void**)&h->h_dpb, sizeof(double) * (6 * (size_t)S.n_beam + 1)));
+  CK(dalloc(&h->s_crds, 3 * (size_t)S.n_node)); CK(dalloc(&h->s_pq, 5 * (size_t)S.n_quad));
+  CK(dalloc(&h->s_pb, 6 * (size_t)S.n_beam)); CK(dalloc(&h->s_f, 6 * (size_t)S.n_node));
+  CK(dalloc(&h->s_u, 6 * (size_t)S.n_node)); CK(dalloc(&h->s_dc, 3 * (size_t)S.n_node));
+  CK(dalloc(&h->s_dpq, 5 * (size_t)S.n_quad)); CK(dalloc(&h->s_dpb, 6 * (size_t)S.n_beam));
+  return JSSO_OK;
+}
+
+int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double* pq_h, const double* pb_h,
+                             const double* f_h, double* value_out, double* u_h, double* dc_h, double* dpq_h,
+                             double* dpb_h, const jsso_solve_opts* opts, jsso_stats* fs, jsso_stats* bs) {
+  if (!h || !crds_h || !f_h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_host_staging(h);
+  if (rc) return rc;
+  const Symbolic& S = h->sym;
+  const size_t nc = 3 * (size_t)S.n_node, nq = 5 * (size_t)S.n_quad, nb = 6 * (size_t)S.n_beam,
+               nd = 6 * (size_t)S.n_node;
+  double *d_crds = h->s_crds, *d_pq = h->s_pq, *d_pb = h->s_pb, *d_f = h->s_f, *d_u = h->s_u, *d_dc = h->s_dc,
+         *d_dpq = h->s_dpq, *d_dpb = h->s_dpb;
+  cudaStream_t st = 0;
+  std::memcpy(h->h_crds, crds_h, nc * sizeof(double));
+  if (nq) std::memcpy(h->h_pq, pq_h, nq * sizeof(double));
+  if (nb) std::memcpy(h->h_pb, pb_h, nb * sizeof(double));
+  std::memcpy(h->h_f, f_h, nd * sizeof(double));
+  CK(cudaMemcpyAsync(d_crds, h->h_crds, nc * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nq) CK(cudaMemcpyAsync(d_pq, h->h_pq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nb) CK(cudaMemcpyAsync(d_pb, h->h_pb, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_f, h->h_f, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = jsso_forward(h, d_crds, d_pq, d_pb, d_f, d_u, opts, fs, st);
+  if (rc) return rc;
+  jsso_solve_opts o; default_opts(opts, o);
+  o.compliance = 1;
+  const bool want_grad = dc_h || dpq_h || dpb_h;
+  if (want_grad) {
+    rc = jsso_backward(h, d_crds, d_pq, d_pb, d_u, nullptr, dc_h ? d_dc : nullptr, (dpq_h && nq) ? d_dpq : nullptr,
+                       (dpb_h && nb) ? d_dpb : nullptr, nullptr, &o, bs, st);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(h->h_u, d_u, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dc_h) CK(cudaMemcpyAsync(h->h_dc, d_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpq_h && nq) CK(cudaMemcpyAsync(h->h_dpq, d_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpb_h && nb) CK(cudaMemcpyAsync(h->h_dpb, d_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double v = 0.0;
+  for (size_t i = 0; i < nd; ++i) v += h->h_f[i] * h->h_u[i];
+  if (value_out) *value_out = 0.5 * v;
+  if (u_h) std::memcpy(u_h, h->h_u, nd * sizeof(double));
+  if (dc_h) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
+  if (dpq_h && nq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+  if (dpb_h && nb) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  return JSSO_OK;
+}
+
+// ---------------------------------------------------------------- utilities
+int jsso_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA; }
+void* jsso_dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes ? bytes : 8) == cudaSuccess ? p : nullptr; }
+void jsso_dev_free(void* p) { if (p) cudaFree(p); }
+void* jsso_host_alloc_pinned(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 8) == cudaSuccess ? p : nullptr; }
+void jsso_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int jsso_memcpy_h2d(void* d, const void* s, size_t n, void* st) {
+  return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+int jsso_memcpy_d2h(void* d, const void* s, size_t n, void* st) {
+  if (cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st) != cudaSuccess) return JSSO_ERR_CUDA;
+  return cudaStreamSynchronize((cudaStream_t)st) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+int jsso_memset(void* d, int v, size_t n, void* st) {
+  return cudaMemsetAsync(d, v, n, (cudaStream_t)st) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+int jsso_stream_sync(void* st) { return cudaStreamSynchronize((cudaStream_t)st) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA; }
+int jsso_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+void* jsso_event_create(void) { cudaEvent_t e; return cudaEventCreate(&e) == cudaSuccess ? (void*)e : nullptr; }
+int jsso_event_record(void* ev, void* st) {
+  return cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+int jsso_event_elapsed_ms(void* a, void* b, float* ms) {
+  if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess) return JSSO_ERR_CUDA;
+  return cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+void jsso_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int64_t jsso_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

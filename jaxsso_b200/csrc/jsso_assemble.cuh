@@ -1,0 +1,368 @@
+// Element stiffness generation and numeric assembly kernels (sm_100a, FP64).
+//
+//  * stage_quad_geometry : per (quad, Gauss point) thread -> shared memory record
+//  * quad_pair_block     : per (quad, node a, node b) thread -> one 6x6 global block
+//  * quad_ke_kernel / beam_ke_kernel : materialise K_e in the reference's `data`
+//    layout (element.py:1236-1237, 270-271) for tests and for the stand-alone
+//    assembly path
+//  * assemble_fused_kernel : Ke + assembly in one pass; K_e never reaches HBM.
+//    One CTA per chunk of <= 256 pair items (sorted by block slot); duplicates are
+//    summed in a fixed order from a shared-memory staging buffer (no atomics) and
+//    the block-CSR values are written once with fully coalesced stores.
+//  * assemble_from_ke_kernel : stand-alone segmented reduction of materialised K_e.
+#pragma once
+#include "jsso_elem.cuh"
+#include "jsso_symbolic.h"
+
+namespace jsso {
+
+// shared-memory record of one quad (doubles); odd stride => conflict-free across quads
+constexpr int QS = 63;
+constexpr int Q_R = 0;      // 9: dirCos rows x^,y^,z^
+constexpr int Q_GRY = 9;    // 2
+constexpr int Q_GRX = 11;   // 2
+constexpr int Q_GSY = 13;   // 2
+constexpr int Q_GSX = 15;   // 2
+constexpr int Q_M = 17;     // m11, m12, m22
+constexpr int Q_KRZ = 20;
+constexpr int Q_MAT = 21;   // cm11 cm12 cm21 cm22 cm33 D nu hb ks
+constexpr int Q_GP = 30;    // 4 x {ji0..3, det, prr, prs, pss}
+
+constexpr int FLAG_BADJAC = 1, FLAG_DEGBEAM = 2, FLAG_UNSYM = 4;
+
+// Stage the geometry of `n_el` quads (ids from `els`, or first_el + i when els is
+// null) into `sm`.  Called by all threads of the CTA; (quad, gp) tasks are dealt to
+// consecutive threads so the four Gauss points of a quad sit in adjacent lanes and
+// the drilling-stiffness minimum (element.py:978) is reduced with two shuffles.
+__device__ inline void stage_quad_geometry(double* sm, int n_el, const int32_t* els, int first_el,
+                                           const double* __restrict__ crds,
+                                           const int32_t* __restrict__ cnct,
+                                           const double* __restrict__ prop, int* flags) {
+  const int n_task = 4 * n_el;
+  for (int base = (threadIdx.x & ~31); base < n_task; base += blockDim.x) {
+    int task = base + (threadIdx.x & 31);
+    const bool live = task < n_task;
+    if (!live) task = n_task - 1;
+    const int le = task >> 2, q = task & 3;
+    const int e = els ? els[le] : first_el + le;
+    double P[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nd = cnct[4 * e + k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
+    }
+    QuadFrame<double> f;
+    quad_frame(P, f);
+    QuadShear<double> sh;
+    quad_shear(f, sh);
+    QuadGp<double> g;
+    quad_gp(f, q, g);
+    QuadMat m;
+    quad_mat(prop + 5 * (size_t)e, m);
+    double dg[8];
+    quad_diag_gp(sh, g, q, m, dg);
+    double krz = 1e300;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dg[i] += __shfl_xor_sync(0xffffffffu, dg[i], 1);
+      dg[i] += __shfl_xor_sync(0xffffffffu, dg[i], 2);
+      krz = fmin(krz, fabs(dg[i]));
+    }
+    if (live) {
+      double* s = sm + le * QS;
+      double* sg = s + Q_GP + 8 * q;
+      sg[0] = g.ji[0]; sg[1] = g.ji[1]; sg[2] = g.ji[2]; sg[3] = g.ji[3];
+      sg[4] = g.det; sg[5] = g.prr; sg[6] = g.prs; sg[7] = g.pss;
+      if (!(g.det > 0.0)) atomicOr(flags, FLAG_BADJAC);
+      if (q == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) s[Q_R + 3 * i + j] = f.R[i][j];
+        s[Q_GRY] = sh.gry[0]; s[Q_GRY + 1] = sh.gry[1];
+        s[Q_GRX] = sh.grx[0]; s[Q_GRX + 1] = sh.grx[1];
+        s[Q_GSY] = sh.gsy[0]; s[Q_GSY + 1] = sh.gsy[1];
+        s[Q_GSX] = sh.gsx[0]; s[Q_GSX + 1] = sh.gsx[1];
+        s[Q_M] = sh.m11; s[Q_M + 1] = sh.m12; s[Q_M + 2] = sh.m22;
+        s[Q_KRZ] = krz / 1000.0;
+        s[Q_MAT] = m.cm11; s[Q_MAT + 1] = m.cm12; s[Q_MAT + 2] = m.cm21; s[Q_MAT + 3] = m.cm22;
+        s[Q_MAT + 4] = m.cm33; s[Q_MAT + 5] = m.D; s[Q_MAT + 6] = m.nu; s[Q_MAT + 7] = m.hb;
+        s[Q_MAT + 8] = m.ks;
+        if (prop[5 * (size_t)e + 3] != prop[5 * (size_t)e + 4]) atomicOr(flags, FLAG_UNSYM);
+      }
+    }
+  }
+}
+
+// G = R^T S R for S = [[s00,s01,0],[s10,s11,0],[0,0,s22]], written into the 6x6
+// column-major block `out` at sub-block (br, bc).
+__device__ inline void rtsr_diag(const double* R, double s00, double s01, double s10, double s11,
+                                 double s22, double* out, int br, int bc) {
+  double u[3], v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    u[i] = s00 * R[i] + s10 * R[3 + i];      // sum_p R[p][i] S[p][0]
+    v[i] = s01 * R[i] + s11 * R[3 + i];      // sum_p R[p][i] S[p][1]
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      out[(3 * bc + j) * 6 + 3 * br + i] = u[i] * R[j] + v[i] * R[3 + j] + (s22 * R[6 + i]) * R[6 + j];
+}
+
+// 6x6 global block (a,b) of a quad from its staged record `s`; column-major out[6*j+i].
+__device__ inline void quad_pair_block(const double* s, int a, int b, double* out) {
+  const double ra = node_r(a), sa = node_s(a), rb = node_r(b), sb = node_s(b);
+  double pxx = 0, pxy = 0, pyx = 0, pyy = 0, crr = 0, crs = 0, csr = 0, css = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double* g = s + Q_GP + 8 * q;
+    const double r = JSSO_GP * node_r(q), t = JSSO_GP * node_s(q);
+    const double far = 1.0 + t * sa, fas = 1.0 + r * ra, fbr = 1.0 + t * sb, fbs = 1.0 + r * rb;
+    const double dra = 0.25 * ra * far, dsa = 0.25 * sa * fas;
+    const double drb = 0.25 * rb * fbr, dsb = 0.25 * sb * fbs;
+    const double ha0 = g[0] * dra + g[1] * dsa, ha1 = g[2] * dra + g[3] * dsa;
+    const double hb0 = g[0] * drb + g[1] * dsb, hb1 = g[2] * drb + g[3] * dsb;
+    const double d0 = g[4] * ha0, d1 = g[4] * ha1;
+    pxx += d0 * hb0; pxy += d0 * hb1; pyx += d1 * hb0; pyy += d1 * hb1;
+    crr += g[5] * (far * fbr); crs += g[6] * (far * fbs);
+    csr += g[6] * (fas * fbr); css += g[7] * (fas * fbs);
+  }
+  const double* mt = s + Q_MAT;
+  const double D = mt[5], nu = mt[6], hb = mt[7], ks = mt[8];
+  // membrane 2x2 (u,v)
+  const double muu = mt[0] * pxx + mt[4] * pyy, muv = mt[1] * pxy + mt[4] * pyx;
+  const double mvu = mt[2] * pyx + mt[4] * pxy, mvv = mt[3] * pyy + mt[4] * pxx;
+  // plate 3x3 (w, theta_x, theta_y): bending + MITC4 shear
+  const int ira = (a < 2) ? 0 : 1, isa = (a == 0 || a == 3) ? 0 : 1;
+  const int irb = (b < 2) ? 0 : 1, isb = (b == 0 || b == 3) ? 0 : 1;
+  const double gra[3] = {0.5 * ra, s[Q_GRY + ira], s[Q_GRX + ira]};
+  const double gsa[3] = {0.5 * sa, s[Q_GSY + isa], s[Q_GSX + isa]};
+  const double grb[3] = {0.5 * rb, s[Q_GRY + irb], s[Q_GRX + irb]};
+  const double gsb[3] = {0.5 * sb, s[Q_GSY + isb], s[Q_GSX + isb]};
+  const double m11 = s[Q_M], m12 = s[Q_M + 1], m22 = s[Q_M + 2];
+  double P[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double va = ks * (m11 * crr * gra[i] + m12 * csr * gsa[i]);
+    const double wa = ks * (m12 * crs * gra[i] + m22 * css * gsa[i]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) P[i][j] = va * grb[j] + wa * gsb[j];
+  }
+  P[1][1] += D * (pyy + hb * pxx);
+  P[1][2] -= D * (nu * pyx + hb * pxy);
+  P[2][1] -= D * (nu * pxy + hb * pyx);
+  P[2][2] += D * (pxx + hb * pyy);
+  const double drill = (a == b) ? s[Q_KRZ] : 0.0;
+  const double* R = s + Q_R;
+  // translational-translational and rotational-rotational sub-blocks
+  rtsr_diag(R, muu, muv, mvu, mvv, P[0][0], out, 0, 0);
+  rtsr_diag(R, P[1][1], P[1][2], P[2][1], P[2][2], drill, out, 1, 1);
+  // TR: S = e_z (P_w,thx  P_w,thy  0);  RT: S = (P_thx,w  P_thy,w  0)^T e_z^T
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double cj = P[0][1] * R[j] + P[0][2] * R[3 + j];
+    const double rj = P[1][0] * R[j] + P[2][0] * R[3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      out[(3 + j) * 6 + i] = R[6 + i] * cj;       // rows: translations, cols: rotations
+      out[i * 6 + 3 + j] = rj * R[6 + i];         // rows: rotations (j), cols: translations (i)
+    }
+  }
+}
+
+// 6x6 global block (a,b) of a beam-column, K_e = T^-1 K_local T (element.py:107-139).
+__device__ inline void beam_pair_block(const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+                                       const double* __restrict__ prop, int e, int a, int b, double* out,
+                                       int* flags) {
+  double P[2][3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int nd = cnct[2 * e + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
+  }
+  double R[3][3], L;
+  const bool deg = beam_dircos(P, R, L);
+  double Ri[3][3];  // T^-1 block: R^T when orthonormal, explicit inverse on the Cxz == 0 branch
+  if (deg) {
+    atomicOr(flags, FLAG_DEGBEAM);
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) -
+                       R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    const double id = 1.0 / det;
+    Ri[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) * id;
+    Ri[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) * id;
+    Ri[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) * id;
+    Ri[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) * id;
+    Ri[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) * id;
+    Ri[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) * id;
+    Ri[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) * id;
+    Ri[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) * id;
+    Ri[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) * id;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Ri[i][j] = R[j][i];
+  }
+  const double* pr = prop + 6 * (size_t)e;
+  const double E = pr[0], G = pr[1], Iy = pr[2], Iz = pr[3], J = pr[4], A = pr[5];
+  const double L2 = L * L, L3 = L2 * L;
+  const double ax = A * E / L, tz = G * J / L;
+  const double bz12 = 12 * E * Iz / L3, bz6 = 6 * E * Iz / L2, bz4 = 4 * E * Iz / L, bz2 = 2 * E * Iz / L;
+  const double by12 = 12 * E * Iy / L3, by6 = 6 * E * Iy / L2, by4 = 4 * E * Iy / L, by2 = 2 * E * Iy / L;
+  const double sg = (a == b) ? 1.0 : -1.0;  // off-diagonal node blocks flip TT and RR(0,0)
+  // local 6x6 block in 3x3 pieces (rows node a, cols node b), literal from element.py:115-126
+  double TT[3] = {sg * ax, sg * bz12, sg * by12};                // diagonal
+  double RR[3] = {sg * tz, (a == b) ? by4 : by2, (a == b) ? bz4 : bz2};
+  // TR: (v, thz) and (w, thy);  RT: (thy, w) and (thz, v)
+  const double s_a = (a == 0) ? 1.0 : -1.0;  // row node sign for TR
+  const double s_b = (b == 0) ? 1.0 : -1.0;  // col node sign for RT
+  const double tr_v_thz = s_a * bz6, tr_w_thy = -s_a * by6;
+  const double rt_thy_w = -s_b * by6, rt_thz_v = s_b * bz6;
+  // G_xy = Ri * S * R  for each 3x3 piece
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double tt = 0, rr = 0;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        tt += Ri[i][p] * TT[p] * R[p][j];
+        rr += Ri[i][p] * RR[p] * R[p][j];
+      }
+      const double tr = Ri[i][1] * tr_v_thz * R[2][j] + Ri[i][2] * tr_w_thy * R[1][j];
+      const double rt = Ri[i][1] * rt_thy_w * R[2][j] + Ri[i][2] * rt_thz_v * R[1][j];
+      out[j * 6 + i] = tt;
+      out[(3 + j) * 6 + 3 + i] = rr;
+      out[(3 + j) * 6 + i] = tr;
+      out[j * 6 + 3 + i] = rt;
+    }
+}
+
+// Materialise quad K_e: 16 threads per quad (one per node pair), 16 quads per CTA.
+__global__ void __launch_bounds__(256)
+quad_ke_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+               const double* __restrict__ prop, double* __restrict__ ke, int* flags) {
+  __shared__ double sm[16 * QS];
+  const int first = blockIdx.x * 16;
+  const int n_el = min(16, n_quad - first);
+  stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
+  __syncthreads();
+  const int le = threadIdx.x >> 4, a = (threadIdx.x >> 2) & 3, b = threadIdx.x & 3;
+  if (le >= n_el) return;
+  double out[36];
+  quad_pair_block(sm + le * QS, a, b, out);
+  double* dst = ke + (size_t)(first + le) * 576 + (6 * a) * 24 + 6 * b;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dst[i * 24 + j] = out[j * 6 + i];
+}
+
+__global__ void __launch_bounds__(256)
+beam_ke_kernel(int n_beam, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+               const double* __restrict__ prop, double* __restrict__ ke, int* flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, a = (t >> 1) & 1, b = t & 1;
+  if (e >= n_beam) return;
+  double out[36];
+  beam_pair_block(crds, cnct, prop, e, a, b, out, flags);
+  double* dst = ke + (size_t)e * 144 + (6 * a) * 12 + 6 * b;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dst[i * 12 + j] = out[j * 6 + i];
+}
+
+// Boundary conditions on one block entry: prescribed rows/cols -> identity
+// (equivalent to the reference's Lagrange rows with zero prescribed displacement,
+// assemblemodel.py:145-163, 192).
+__device__ inline double bc_entry(double v, unsigned rmask, unsigned cmask, int i, int j, bool diag_blk) {
+  const bool rk = (rmask >> i) & 1u, ck = (cmask >> j) & 1u;
+  if (rk || ck) return (diag_blk && i == j) ? 1.0 : 0.0;
+  return v;
+}
+
+constexpr int STAGE_LD = kChunkItems + 1;  // odd => conflict-free column reads
+constexpr int FUSED_SMEM_DOUBLES =
+    (36 * STAGE_LD > kChunkQuads * QS) ? 36 * STAGE_LD : kChunkQuads * QS;
+
+struct AsmArgs {
+  const double* crds; const int32_t* cnct_q; const double* prop_q;
+  const int32_t* cnct_b; const double* prop_b;
+  const int32_t* chunk_blk; const int32_t* chunk_el_ptr; const int32_t* chunk_els;
+  const int32_t* blk_item_ptr; const int32_t* item_code; const uint8_t* item_lel;
+  const int32_t* blk_row; const int32_t* colidx; const uint8_t* node_mask;
+  double* vals; int* flags; int n_quad; int apply_bc;
+};
+
+__global__ void __launch_bounds__(kChunkItems)
+assemble_fused_kernel(AsmArgs A) {
+  extern __shared__ double sm[];
+  const int c = blockIdx.x;
+  const int blk0 = A.chunk_blk[c], blk1 = A.chunk_blk[c + 1];
+  const int it0 = A.blk_item_ptr[blk0], it1 = A.blk_item_ptr[blk1];
+  const int el0 = A.chunk_el_ptr[c], n_el = A.chunk_el_ptr[c + 1] - el0;
+  if (n_el > 0)
+    stage_quad_geometry(sm, n_el, A.chunk_els + el0, 0, A.crds, A.cnct_q, A.prop_q, A.flags);
+  __syncthreads();
+  const int it = it0 + threadIdx.x;
+  double out[36];
+  if (it < it1) {
+    const int code = A.item_code[it];
+    const int el = code >> 4, a = (code >> 2) & 3, b = code & 3;
+    if (el < A.n_quad) quad_pair_block(sm + A.item_lel[it] * QS, a, b, out);
+    else beam_pair_block(A.crds, A.cnct_b, A.prop_b, el - A.n_quad, a, b, out, A.flags);
+  }
+  __syncthreads();  // geometry records are dead; the staging buffer aliases them
+  if (it < it1) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) sm[k * STAGE_LD + threadIdx.x] = out[k];
+  }
+  __syncthreads();
+  const int n_out = (blk1 - blk0) * 36;
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    const int bl = o / 36, k = o - bl * 36;
+    const int blk = blk0 + bl;
+    const int i0 = A.blk_item_ptr[blk] - it0, i1 = A.blk_item_ptr[blk + 1] - it0;
+    double s = 0.0;
+    for (int i = i0; i < i1; ++i) s += sm[k * STAGE_LD + i];
+    if (A.apply_bc) {
+      const int r = A.blk_row[blk], cc = A.colidx[blk];
+      s = bc_entry(s, A.node_mask[r], A.node_mask[cc], k % 6, k / 6, r == cc);
+    }
+    A.vals[(size_t)blk * 36 + k] = s;
+  }
+}
+
+// Stand-alone numeric assembly: one thread per stored entry, contributors summed in
+// list order from the materialised element matrices.
+__global__ void __launch_bounds__(256)
+assemble_from_ke_kernel(long long n_out, int n_quad, const double* __restrict__ ke_q,
+                        const double* __restrict__ ke_b, const int32_t* __restrict__ blk_item_ptr,
+                        const int32_t* __restrict__ item_code, const int32_t* __restrict__ blk_row,
+                        const int32_t* __restrict__ colidx, const uint8_t* __restrict__ node_mask,
+                        double* __restrict__ vals, int apply_bc) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const int blk = (int)(o / 36), k = (int)(o - (long long)blk * 36);
+  const int i = k % 6, j = k / 6;
+  double s = 0.0;
+  for (int it = blk_item_ptr[blk]; it < blk_item_ptr[blk + 1]; ++it) {
+    const int code = item_code[it];
+    const int el = code >> 4, a = (code >> 2) & 3, b = code & 3;
+    if (el < n_quad) s += ke_q[(size_t)el * 576 + (6 * a + i) * 24 + 6 * b + j];
+    else s += ke_b[(size_t)(el - n_quad) * 144 + (6 * a + i) * 12 + 6 * b + j];
+  }
+  if (apply_bc) {
+    const int r = blk_row[blk], c = colidx[blk];
+    s = bc_entry(s, node_mask[r], node_mask[c], i, j, r == c);
+  }
+  vals[o] = s;
+}
+
+}  // namespace jsso

@@ -1,0 +1,146 @@
+#include "jsso_symbolic.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace jsso {
+
+namespace {
+struct Entry {
+  int32_t col;
+  int32_t code;
+};
+}  // namespace
+
+std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cq, int n_beam,
+                           const int32_t* cb, int n_known, const int32_t* known, Symbolic& S) {
+  if (n_node <= 0 || n_row < 0 || n_row > n_node) return "bad node counts";
+  if ((int64_t)n_quad + n_beam >= (1 << 27)) return "too many elements for 27-bit item codes";
+  S = Symbolic();
+  S.n_node = n_node; S.n_row = n_row; S.n_quad = n_quad; S.n_beam = n_beam;
+  for (int64_t i = 0; i < 4LL * n_quad; ++i)
+    if (cq[i] < 0 || cq[i] >= n_node) return "quad connectivity out of range";
+  for (int64_t i = 0; i < 2LL * n_beam; ++i)
+    if (cb[i] < 0 || cb[i] >= n_node) return "beam connectivity out of range";
+
+  // ---- boundary mask (duplicates in `known` are harmless here; the reference's
+  // Lagrange system would become singular, model.py:286)
+  S.node_mask.assign(n_node, 0);
+  for (int i = 0; i < n_known; ++i) {
+    if (known[i] < 0 || known[i] >= 6 * n_node) return "known dof out of range";
+    S.node_mask[known[i] / 6] |= (uint8_t)(1u << (known[i] % 6));
+  }
+
+  // ---- corners per node (gradient gather lists)
+  S.node_inc_ptr.assign(n_node + 1, 0);
+  for (int e = 0; e < n_beam; ++e)
+    for (int a = 0; a < 2; ++a) S.node_inc_ptr[cb[2 * e + a] + 1]++;
+  for (int e = 0; e < n_quad; ++e)
+    for (int a = 0; a < 4; ++a) S.node_inc_ptr[cq[4 * e + a] + 1]++;
+  std::partial_sum(S.node_inc_ptr.begin(), S.node_inc_ptr.end(), S.node_inc_ptr.begin());
+  S.node_inc.resize(S.node_inc_ptr[n_node]);
+  {
+    std::vector<int32_t> pos(S.node_inc_ptr.begin(), S.node_inc_ptr.end() - 1);
+    for (int e = 0; e < n_beam; ++e)
+      for (int a = 0; a < 2; ++a) S.node_inc[pos[cb[2 * e + a]]++] = ((n_quad + e) << 2) | a;
+    for (int e = 0; e < n_quad; ++e)
+      for (int a = 0; a < 4; ++a) S.node_inc[pos[cq[4 * e + a]]++] = (e << 2) | a;
+  }
+
+  // ---- raw pair items bucketed by block row, in the reference's raw order
+  // (diagonal placeholder first so that every row owns its diagonal block)
+  std::vector<int64_t> rptr(n_row + 1, 0);
+  for (int r = 0; r < n_row; ++r) rptr[r + 1] = 1;
+  for (int e = 0; e < n_beam; ++e)
+    for (int a = 0; a < 2; ++a)
+      if (cb[2 * e + a] < n_row) rptr[cb[2 * e + a] + 1] += 2;
+  for (int e = 0; e < n_quad; ++e)
+    for (int a = 0; a < 4; ++a)
+      if (cq[4 * e + a] < n_row) rptr[cq[4 * e + a] + 1] += 4;
+  std::partial_sum(rptr.begin(), rptr.end(), rptr.begin());
+  std::vector<Entry> ent(rptr[n_row]);
+  {
+    std::vector<int64_t> pos(rptr.begin(), rptr.end() - 1);
+    for (int r = 0; r < n_row; ++r) ent[pos[r]++] = Entry{r, -1};
+    for (int e = 0; e < n_beam; ++e)
+      for (int a = 0; a < 2; ++a) {
+        const int r = cb[2 * e + a];
+        if (r >= n_row) continue;
+        for (int b = 0; b < 2; ++b)
+          ent[pos[r]++] = Entry{cb[2 * e + b], ((n_quad + e) << 4) | (a << 2) | b};
+      }
+    for (int e = 0; e < n_quad; ++e)
+      for (int a = 0; a < 4; ++a) {
+        const int r = cq[4 * e + a];
+        if (r >= n_row) continue;
+        for (int b = 0; b < 4; ++b) ent[pos[r]++] = Entry{cq[4 * e + b], (e << 4) | (a << 2) | b};
+      }
+  }
+
+  // ---- per row: stable sort by column -> blocks; contributors keep raw order
+  S.rowptr.assign(n_row + 1, 0);
+  S.diag_slot.assign(n_row, -1);
+  S.colidx.reserve(ent.size() / 2);
+  S.blk_row.reserve(ent.size() / 2);
+  S.blk_item_ptr.reserve(ent.size() / 2 + 1);
+  S.item_code.reserve(ent.size());
+  S.blk_item_ptr.push_back(0);
+  for (int r = 0; r < n_row; ++r) {
+    Entry* b = ent.data() + rptr[r];
+    Entry* e = ent.data() + rptr[r + 1];
+    std::stable_sort(b, e, [](const Entry& x, const Entry& y) { return x.col < y.col; });
+    for (Entry* p = b; p < e;) {
+      const int32_t c = p->col;
+      if (c == r) S.diag_slot[r] = (int32_t)S.colidx.size();
+      S.colidx.push_back(c);
+      S.blk_row.push_back(r);
+      for (; p < e && p->col == c; ++p)
+        if (p->code >= 0) S.item_code.push_back(p->code);
+      S.blk_item_ptr.push_back((int32_t)S.item_code.size());
+    }
+    S.rowptr[r + 1] = (int32_t)S.colidx.size();
+  }
+  if (S.item_code.size() >= (size_t)INT32_MAX) return "too many pair items";
+
+  // ---- chunks: consecutive blocks with <= kChunkItems items and <= kChunkQuads quads
+  const int64_t nnzb = S.nnzb();
+  S.item_lel.assign(S.item_code.size(), 0);
+  std::vector<int32_t> seen(n_quad, -1), lidx(n_quad, 0);
+  S.chunk_blk.push_back(0);
+  S.chunk_el_ptr.push_back(0);
+  int items = 0, quads = 0, chunk = 0;
+  std::vector<int32_t> fresh;
+  for (int64_t blk = 0; blk < nnzb; ++blk) {
+    const int i0 = S.blk_item_ptr[blk], i1 = S.blk_item_ptr[blk + 1];
+    if (i1 - i0 > kChunkItems) return "a block has more contributors than a chunk can hold";
+    fresh.clear();
+    for (int i = i0; i < i1; ++i) {
+      const int el = S.item_code[i] >> 4;
+      if (el < n_quad && seen[el] != chunk &&
+          std::find(fresh.begin(), fresh.end(), el) == fresh.end())
+        fresh.push_back(el);
+    }
+    if ((int)fresh.size() > kChunkQuads) return "a block touches more quads than a chunk can stage";
+    if (items + (i1 - i0) > kChunkItems || quads + (int)fresh.size() > kChunkQuads) {
+      S.chunk_blk.push_back((int32_t)blk);
+      S.chunk_el_ptr.push_back((int32_t)S.chunk_els.size());
+      ++chunk; items = 0; quads = 0;
+    }
+    for (int i = i0; i < i1; ++i) {
+      const int el = S.item_code[i] >> 4;
+      if (el >= n_quad) continue;
+      if (seen[el] != chunk) {
+        seen[el] = chunk;
+        lidx[el] = quads++;
+        S.chunk_els.push_back(el);
+      }
+      S.item_lel[i] = (uint8_t)lidx[el];
+    }
+    items += i1 - i0;
+  }
+  S.chunk_blk.push_back((int32_t)nnzb);
+  S.chunk_el_ptr.push_back((int32_t)S.chunk_els.size());
+  return "";
+}
+
+}  // namespace jsso

@@ -1,0 +1,47 @@
+// Symbolic pass (host, once per model): everything that is a pure function of
+// the connectivity and the boundary conditions.
+//
+// The reference recomputes COO indices per call (JaxSSO/element.py:141-149,
+// 1097-1106) and lexicographically sorts + segment-sums all 144 n_b + 576 n_q raw
+// entries on every evaluation (JaxSSO/assemblemodel.py:156-162).  Its
+// sorted-unique (row, col) set is exactly the 6x6 block expansion of the node
+// adjacency graph, which is what this pass builds once as block-CSR, together
+// with the contributor lists that let the numeric assembly sum duplicates in a
+// fixed order without atomics.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace jsso {
+
+constexpr int kChunkItems = 256;  // pair items per assembly chunk (= CTA size)
+constexpr int kChunkQuads = 48;   // distinct quads whose geometry a chunk stages in shared memory
+
+struct Symbolic {
+  int n_node = 0, n_row = 0, n_quad = 0, n_beam = 0;
+  // block-CSR over nodes; rows = owned nodes [0, n_row), columns = all local nodes
+  std::vector<int32_t> rowptr, colidx, blk_row, diag_slot;
+  // pair items (element, a, b) sorted by block slot, beams before quads, then by
+  // element id (the reference's concatenation order, assemblemodel.py:202-211)
+  std::vector<int32_t> blk_item_ptr;  // nnzb + 1
+  std::vector<int32_t> item_code;     // (elem << 4) | (a << 2) | b; beams use elem = n_quad + id
+  std::vector<uint8_t> item_lel;      // quad items: index into the chunk's staged-geometry list
+  std::vector<int32_t> chunk_blk;     // n_chunk + 1 block boundaries
+  std::vector<int32_t> chunk_el_ptr;  // n_chunk + 1
+  std::vector<int32_t> chunk_els;     // quads staged per chunk
+  // per node: incident (element, local node) corners, for the gradient gather
+  std::vector<int32_t> node_inc_ptr;  // n_node + 1
+  std::vector<int32_t> node_inc;      // (elem << 2) | a; beams use elem = n_quad + id
+  std::vector<uint8_t> node_mask;     // bit k set <=> dof 6*node+k is prescribed (zero)
+  int64_t nnzb() const { return (int64_t)colidx.size(); }
+  int64_t n_items() const { return (int64_t)item_code.size(); }
+  int n_chunk() const { return (int)chunk_blk.size() - 1; }
+};
+
+// Returns an empty string on success, else an error message.
+std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cnct_quads, int n_beam,
+                           const int32_t* cnct_beams, int n_known, const int32_t* known,
+                           Symbolic& out);
+
+}  // namespace jsso
