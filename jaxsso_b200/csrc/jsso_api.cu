@@ -431,9 +431,13 @@ static int cg_iteration(jsso_handle* h, int cur, cudaStream_t st) {
   if ((rc = allreduce_scalar(h, &h->sc->pq, 1, st))) return rc;
   const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
   cg_update_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vp, h->vq, h->vx, h->vr, h->sc, h->partials,
-                                                  h->counters + 1);
+                                                  h->counters + 1, h->n_rank <= 1);
   CKL("cg_update_kernel");
-  if ((rc = allreduce_scalar(h, &h->sc->rr[cur ^ 1], 1, st))) return rc;
+  if (h->n_rank > 1) {
+    if ((rc = allreduce_scalar(h, &h->sc->rr[cur ^ 1], 1, st))) return rc;
+    cg_latch_kernel<<<1, 1, 0, st>>>(cur, h->sc);
+    CKL("cg_latch_kernel");
+  }
   cg_direction_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vr, h->vp, h->sc);
   CKL("cg_direction_kernel");
   return JSSO_OK;
@@ -446,7 +450,7 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
   const long long n = 6LL * n_row;
   const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
   int restarts = 0, total_iter = 0;
-  double relres_true = 0.0, relres_rec = 0.0;
+  double relres_true = 0.0, relres_rec = 0.0, prev_true = 1e300;
   bool first = true, converged = false;
   int rc;
   for (;;) {
@@ -507,14 +511,24 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
     CK(cudaStreamSynchronize(st));
     relres_true = (h->sc_host->bb > 0) ? std::sqrt(h->sc_host->aux / h->sc_host->bb) : 0.0;
     if (relres_true <= o.rtol * 1.5 || h->sc_host->bb == 0.0) { converged = true; break; }
-    if (total_iter >= o.maxiter || restarts >= 20) break;
-    ++restarts;   // residual replacement: restart from the current iterate
+    // the recurrence residual has drifted from the true one: residual replacement, i.e.
+    // restart from the current iterate -- unless the last restart no longer gained a
+    // factor 2 (attainable accuracy reached)
+    if (total_iter >= o.maxiter || restarts >= 20 || relres_true > 0.5 * prev_true) break;
+    prev_true = relres_true;
+    ++restarts;
   }
   if (stats) {
     stats->iterations = total_iter; stats->restarts = restarts; stats->converged = converged ? 1 : 0;
     stats->relres = relres_true; stats->relres_recur = relres_rec;
   }
-  if (!converged) return fail(h, JSSO_ERR_NOCONV, "PCG did not reach rtol within maxiter");
+  if (!converged) {
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "PCG did not reach rtol=%.3g: true relres %.3g after %d iterations, %d restarts%s",
+                  o.rtol, relres_true, total_iter, restarts,
+                  total_iter >= o.maxiter ? " (maxiter)" : " (stagnated: attainable accuracy)");
+    return fail(h, JSSO_ERR_NOCONV, buf);
+  }
   return JSSO_OK;
 }
 

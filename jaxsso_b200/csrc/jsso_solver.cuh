@@ -271,7 +271,7 @@ cg_init_kernel(long long n, const double* __restrict__ b, const double* __restri
 __global__ void __launch_bounds__(RED_BLOCK)
 cg_update_kernel(long long n, int cur, const double* __restrict__ p, const double* __restrict__ q,
                  double* __restrict__ x, double* __restrict__ r, CgScalars* sc, double* partials,
-                 unsigned* counter) {
+                 unsigned* counter, int single_gpu) {
   if (cg_stop(sc, cur)) return;
   const double rr = sc->rr[cur], pq = sc->pq;
   const double alpha = rr / pq;
@@ -285,9 +285,18 @@ cg_update_kernel(long long n, int cur, const double* __restrict__ p, const doubl
   double total;
   if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
     // non-positive curvature => not SPD: poison the state so that everything stops
-    sc->rr[cur ^ 1] = (pq > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
+    const double nrr = (pq > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
+    sc->rr[cur ^ 1] = nrr;
     sc->iter += 1;
+    // On stop, latch BOTH parity slots: later launches of the batch test rr[cur] with
+    // alternating cur.  Safe here: every block read rr[cur] before contributing its partial.
+    if (single_gpu && !(nrr > sc->tol2 * sc->bb)) sc->rr[cur] = nrr;
   }
+}
+
+// multi-GPU: after the all-reduce of rr[cur^1], latch the stop state in both slots
+__global__ void cg_latch_kernel(int cur, CgScalars* sc) {
+  if (!(sc->rr[cur ^ 1] > sc->tol2 * sc->bb)) sc->rr[cur] = sc->rr[cur ^ 1];
 }
 
 // p = r + beta p

@@ -42,8 +42,9 @@ class Dev:
         return nat.bsr_to_scipy(rp, ci, self.h.values_host()).tocsr()
 
 
-def relmax(a, b):
-    return np.abs(a - b).max() / np.abs(b).max()
+def relmax(a, b, floor=0.0):
+    """inf-norm relative error; `floor` guards reference arrays that are identically 0."""
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor)
 
 
 def warped_quads(n, seed=0):
@@ -162,10 +163,13 @@ def test_forward_displacements(case, mannheim_data, golden):
           'plate32': lambda: meshes.plate(32)}[case]()
     d = Dev(md)
     u_d = nat.DeviceArray((md.ndof,))
-    st = d.h.forward(d.crds, d.pq, d.pb, d.f, u_d, opts=nat.make_opts(rtol=1e-12))
+    # rtol is the TRUE relative residual of the block-Jacobi-scaled system; Mannheim's
+    # attainable accuracy in FP64 is ~1e-10 (kappa ~ 1e6), the others reach 1e-12
+    rtol = 1e-10 if case == 'mannheim' else 1e-12
+    st = d.h.forward(d.crds, d.pq, d.pb, d.f, u_d, opts=nat.make_opts(rtol=rtol))
     u = u_d.download()
     uref = orc.solve_refined(to_oracle_mesh(md))
-    assert st.converged and st.relres <= 2e-12
+    assert st.converged and st.relres <= 1.5 * rtol
     assert np.linalg.norm(u - uref) / np.linalg.norm(uref) <= U_TOL
     c, cref = 0.5 * md.loads @ u, 0.5 * md.loads @ uref
     assert abs(c - cref) / abs(cref) <= U_TOL
@@ -175,6 +179,14 @@ def test_forward_displacements(case, mannheim_data, golden):
         assert abs(u[6 * md.design_nodes + 2].min() - golden['shell_arch_min_uz']['dense']) / 25.0 <= 1e-9
     if case == 'beam_arch':
         assert abs(c - golden['beam_arch']['dense_strain_energy']) / c <= 5e-8
+
+
+def test_pcg_unattainable_tolerance_is_reported(mannheim_data):
+    md = meshes.mannheim_quad(mannheim_data)
+    d = Dev(md)
+    with pytest.raises(nat.JssoError) as ei:
+        d.h.forward(d.crds, d.pq, d.pb, d.f, nat.DeviceArray((md.ndof,)), opts=nat.make_opts(rtol=1e-13))
+    assert ei.value.code == 3 and 'stagnated' in str(ei.value)
 
 
 def test_pcg_reports_nonconvergence():
@@ -234,7 +246,7 @@ def test_value_and_grad_end_to_end(case, mannheim_data, golden):
           'frames10': lambda: meshes.frames(10, 100), 'beam_arch': meshes.beam_arch}[case]()
     h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
     val, u, dc, dq, db, fs, bs = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads,
-                                                       opts=nat.make_opts(rtol=1e-12))
+                                                       opts=nat.make_opts(rtol=1e-10 if case == 'mannheim' else 1e-12))
     rv, ru, rl, rdc, rdq, rdb = orc.value_and_grad(to_oracle_mesh(md))
     assert abs(val - rv) / abs(rv) <= U_TOL
     assert np.linalg.norm(u - ru) / np.linalg.norm(ru) <= U_TOL
@@ -243,8 +255,11 @@ def test_value_and_grad_end_to_end(case, mannheim_data, golden):
         for k in (0, 1, 2):
             assert relmax(dq[:, k], rdq[:, k]) <= G_TOL
     if md.n_beam:
+        # columns whose reference gradient is identically zero (e.g. torsion of a plane arch)
+        # are compared against the scale of the E-column
         for k in range(6):
-            assert relmax(db[:, k], rdb[:, k]) <= G_TOL
+            scale = np.abs(rdb[:, 0] * md.prop_beams[:, 0]).max() / np.abs(md.prop_beams[:, k]).max()
+            assert relmax(db[:, k], rdb[:, k], floor=scale) <= G_TOL
     if case == 'beam_arch':
         g = golden['beam_arch_grad_node49']
         assert abs(dc[g['design_i'], 2] - g['dense']) / abs(g['dense']) <= 1e-5
