@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see DESIGN.md section "Measurement").
+
+Workload (N = 1): BASELINE.json configs[2], the synthetic 1024 x 1024 MITC4 shell
+(1 048 576 quads, 6 303 750 dof), jittered as SURVEY.md 8(d).
+One "step" = fused Ke + numeric assembly (BC imposed) + fused adjoint sensitivity
+reduction over all quads, with coordinates, properties, u and lam resident in HBM:
+metric M1 "MITC4 Ke+assembly+adjoint elements/s" (solve excluded by definition).
+The full shape-gradient evaluation including the PCG solve (metric M2) is measured
+once per run and reported under "grad_eval".
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from jaxsso_b200 import meshes  # noqa: E402
+
+METRIC = 'MITC4 Ke+assembly+adjoint elements/s'
+UNIT = 'elements/s'
+
+
+# ------------------------------------------------------------------------------ helpers
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def synthetic_state(md):
+    """A smooth displacement-like field u (zero at prescribed dofs) and lam = u/2."""
+    rng = np.random.default_rng(7)
+    x, y = md.crds[:, 0], md.crds[:, 1]
+    sx, sy = x / max(x.max(), 1.0), y / max(y.max(), 1.0)
+    u = np.zeros((md.n_node, 6))
+    bump = np.sin(np.pi * sx) * np.sin(np.pi * sy)
+    u[:, 2] = -1e-3 * bump
+    u[:, 0] = 1e-5 * np.cos(np.pi * sx) * bump
+    u[:, 1] = 1e-5 * np.cos(np.pi * sy) * bump
+    u[:, 3] = 1e-4 * np.sin(np.pi * sx) * np.cos(np.pi * sy)
+    u[:, 4] = -1e-4 * np.cos(np.pi * sx) * np.sin(np.pi * sy)
+    u += 1e-7 * rng.standard_normal(u.shape)
+    u = u.reshape(-1)
+    u[md.known] = 0.0
+    return u, 0.5 * u
+
+
+# ------------------------------------------------------------------------------ reference arm
+def _oracle_chunk(args):
+    """Ke + adjoint element sensitivities of one chunk of quads (worker process)."""
+    from oracle import jaxsso_oracle as orc
+    crds, cnct, prop, u, lam = args
+    n = cnct.shape[0]
+    e = crds[cnct].reshape(n, 12)
+    K = orc.element_K_quad(e, prop)
+    dof = (6 * cnct.astype(np.int64)[:, :, None] + np.arange(6)[None, None, :]).reshape(n, 24)
+    W = -lam[dof][:, :, None] * u[dof][:, None, :]
+    dx = np.zeros((n, 12))
+    dp = np.zeros((n, 5))
+    h = 1e-30
+    for k in range(12):
+        ec = e.astype(complex); ec[:, k] += 1j * h
+        dx[:, k] = np.sum(W * (orc.element_K_quad(ec, prop).imag / h), axis=(1, 2))
+    for k in range(5):
+        pc = prop.astype(complex); pc[:, k] += 1j * h
+        dp[:, k] = np.sum(W * (orc.element_K_quad(e, pc).imag / h), axis=(1, 2))
+    return K, dx, dp
+
+
+def reference_step(md, u, lam, pool, n_workers):
+    """The reference's algorithm for the path on host cores: vmap(element_K_quad) ->
+    raw COO -> sort/sum_duplicates (scipy tocsr) -> element-wise adjoint reduction."""
+    import scipy.sparse as sp
+    from oracle import jaxsso_oracle as orc
+    parts = np.array_split(np.arange(md.n_quad), n_workers)
+    jobs = [(md.crds, md.cnct_quads[p], md.prop_quads[p], u, lam) for p in parts if p.size]
+    res = list(pool.map(_oracle_chunk, jobs)) if pool else [_oracle_chunk(j) for j in jobs]
+    K = np.concatenate([r[0] for r in res])
+    r, c = orc.quad_indices(md.cnct_quads)
+    Kg = sp.coo_matrix((K.reshape(-1), (r, c)), shape=(md.ndof, md.ndof)).tocsr()
+    d_crds = np.zeros((md.n_node, 3))
+    dx = np.concatenate([r_[1] for r_ in res]).reshape(-1, 4, 3)
+    np.add.at(d_crds, md.cnct_quads, dx)
+    return Kg, d_crds
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    n_workers = max(1, min(cores, 32))
+    size = args.ref_size
+    md = meshes.plate(size)
+    u, lam = synthetic_state(md)
+    pool = ProcessPoolExecutor(n_workers) if n_workers > 1 else None
+    try:
+        for _ in range(args.warmup):
+            reference_step(md, u, lam, pool, n_workers)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            reference_step(md, u, lam, pool, n_workers)
+        dt = (time.perf_counter() - t0) / args.steps
+    finally:
+        if pool:
+            pool.shutdown()
+    v = md.n_quad / dt
+    sample = (f'{size}x{size} jittered plate ({md.n_quad} quads) per step: NumPy/SciPy restatement of '
+              f'vmap(element_K_quad) + COO->CSR sum_duplicates + complex-step adjoint reduction, '
+              f'{n_workers} worker processes')
+    out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+           'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': f'synthetic {args.size}x{args.size} MITC4 shell plate (BASELINE configs[2]); '
+                                  f'reference arm timed on a bounded {size}x{size} sample of it'},
+           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': n_workers, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------ own arm
+def run_b200(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local_rank)
+        dist_.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist = dist_
+    from jaxsso_b200 import _native as nat
+    from jaxsso_b200 import build as jbuild
+    from jaxsso_b200 import partition
+    if rank == 0:
+        jbuild.build()
+    if dist:
+        dist.barrier()
+    L = nat.lib()
+    L.jsso_set_device(local_rank)
+
+    def barrier():
+        L.jsso_stream_sync(None)
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N = args.size
+    t_setup = time.perf_counter()
+    if args.scaling == 'weak' and world > 1:
+        gmd = meshes.plate(N, M=N * world)
+    else:
+        gmd = meshes.plate(N)
+    n_quad_total = gmd.n_quad
+    if world > 1:
+        owner = partition.rcb_owner(gmd.crds[:, :2], world)
+        lm = partition.local_mesh(gmd, owner, rank, world)
+        md, n_row = lm.md, lm.n_owned
+        ug, lg = synthetic_state(gmd)
+        u = ug.reshape(-1, 6)[lm.l2g].reshape(-1)
+        lam = lg.reshape(-1, 6)[lm.l2g].reshape(-1)
+    else:
+        md, n_row = gmd, gmd.n_node
+        u, lam = synthetic_state(md)
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=local_rank, n_row=n_row)
+    if world > 1:
+        idbuf = [nat.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(idbuf, src=0)
+        h.set_halo(idbuf[0], rank, world, lm.peer_rank, lm.send_ptr, lm.send_idx, lm.recv_start, lm.recv_count)
+    D = nat.DeviceArray
+    crds_d, pq_d, pb_d = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams)
+    u_d, lam_d, f_d = D.from_host(u), D.from_host(lam), D.from_host(md.loads)
+    dc_d, dq_d = D((md.n_node, 3)), D((md.n_quad, 5))
+    t_setup = time.perf_counter() - t_setup
+
+    def step():
+        h.assemble(crds_d, pq_d, pb_d, apply_bc=True)
+        h.adjoint(crds_d, pq_d, pb_d, u_d, lam_d, dc_d, dq_d, None)
+
+    ev = [L.jsso_event_create() for _ in range(4)]
+
+    def timed(fn, reps):
+        """CUDA events on the launching stream (the default stream of this process)."""
+        L.jsso_event_record(ev[0], None)
+        for _ in range(reps):
+            fn()
+        L.jsso_event_record(ev[1], None)
+        import ctypes
+        ms = ctypes.c_float()
+        L.jsso_event_elapsed_ms(ev[0], ev[1], ctypes.byref(ms))
+        return ms.value / reps
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = L.jsso_launch_count()
+    ms_step = max_over_ranks(timed(step, args.steps))
+    launches = L.jsso_launch_count() - l0
+    barrier()
+    # the two kernels on their own (roofline of each)
+    ms_asm = max_over_ranks(timed(lambda: h.assemble(crds_d, pq_d, pb_d, apply_bc=True), args.steps))
+    ms_adj = max_over_ranks(timed(lambda: h.adjoint(crds_d, pq_d, pb_d, u_d, lam_d, dc_d, dq_d, None), args.steps))
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the C ABI with host buffers (H2D + kernels + D2H inside the timed region)
+    out_bufs = (np.empty((md.n_node, 3)), np.empty((md.n_quad, 5)), None)
+    for _ in range(2):
+        h.assemble_adjoint_host(md.crds, md.prop_quads, md.prop_beams, u, lam, out_bufs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.assemble_adjoint_host(md.crds, md.prop_quads, md.prop_beams, u, lam, out_bufs)
+    barrier()
+    s_e2e = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    h2d = 8 * (md.crds.size + md.prop_quads.size + md.prop_beams.size + 2 * u.size)
+    d2h = 8 * (out_bufs[0].size + out_bufs[1].size)
+
+    # full shape-gradient evaluation incl. the solve (metric M2), once
+    grad_eval = None
+    if args.solve:
+        opts = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, check_every=100, compliance=True)
+        uu_d = D((md.ndof,))
+        barrier()
+        t0 = time.perf_counter()
+        try:
+            fs = h.forward(crds_d, pq_d, pb_d, f_d, uu_d, opts=opts)
+            h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=opts)
+            L.jsso_stream_sync(None)
+            ok = True
+        except nat.JssoError as e:
+            fs, ok = None, str(e)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if fs is not None:
+            grad_eval = {'seconds': dt, 'evals_per_s': 1.0 / dt, 'pcg_iterations': fs.iterations,
+                         'pcg_restarts': fs.restarts, 'true_relres': fs.relres, 'rtol': args.rtol,
+                         'ms_per_pcg_iteration': 1e3 * dt / max(fs.iterations, 1),
+                         'note': 'Ke+assembly, block-Jacobi PCG for u, lam = u/2 (compliance), adjoint'}
+        else:
+            grad_eval = {'error': ok, 'seconds': dt}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    hbm, peak_src = peaks()
+    s = h.sizes
+    # algorithmic bytes of the fused Ke+assembly kernel: connectivity + properties +
+    # coordinates read once, every stored block written once
+    asm_bytes = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
+    roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9,
+            'peak': hbm, 'unit': 'GB/s', 'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
+            'peak_source': peak_src, 'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm}
+    adj_flops = 14000.0 * s.n_quad
+    roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
+                'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
+                'peak_source': 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)', 'ms': ms_adj,
+                'algorithmic_flops_per_launch': adj_flops}
+    value = n_quad_total / (ms_step * 1e-3)
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+           'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
+                                  f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
+                                  f'{6 * gmd.n_node} dof; step = fused Ke+assembly + adjoint reduction',
+                      'parallelism': f'rcb{world}' if world > 1 else 'single',
+                      'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
+                      'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
+           'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                   'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
+           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_adjoint': roof_adj,
+           'kernel_ms': {'assemble_fused': ms_asm, 'adjoint': ms_adj}, 'setup_s': t_setup,
+           'grad_eval': grad_eval}
+    if world == 1 and args.cpu_baseline:
+        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+               '--ref-size', str(args.ref_size), '--ref-serial']
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            out['cpu_baseline'] = ref['cpu_baseline']
+        except Exception as e:  # the baseline is a report, never a reason to lose the bench line
+            out['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': f'failed: {e}'}
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--size', type=int, default=1024, help='plate is size x size quads')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--no-solve', dest='solve', action='store_false')
+    ap.add_argument('--rtol', type=float, default=1e-8)
+    ap.add_argument('--maxiter', type=int, default=400000)
+    ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    ap.add_argument('--ref-size', type=int, default=64, help='plate size of the bounded CPU sample')
+    ap.add_argument('--ref-serial', action='store_true', help='reference arm on one core (cpu_baseline leg)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        if args.ref_serial:
+            os.cpu_count = lambda: 1
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

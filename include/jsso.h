@@ -165,6 +165,12 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
                              double* d_crds_h, double* d_prop_q_h, double* d_prop_b_h,
                              const jsso_solve_opts* opts, jsso_stats* fwd_stats, jsso_stats* bwd_stats);
 
+/* Solve-free part of a gradient evaluation with HOST buffers: H2D (crds, props, u, lam),
+ * fused Ke + assembly, adjoint reduction, D2H (gradients).  Outputs may be NULL. */
+int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const double* prop_q_h,
+                               const double* prop_b_h, const double* u_h, const double* lam_h,
+                               double* d_crds_h, double* d_prop_q_h, double* d_prop_b_h);
+
 /* ---- multi-GPU: halo exchange plan + NCCL communicator (one process per GPU) ------- */
 /* 128-byte NCCL unique id, generated by rank 0 and distributed by the caller. */
 int jsso_nccl_unique_id(uint8_t id_out[128]);

@@ -54,7 +54,7 @@ class SolveOpts(C.Structure):
 SYMBOLS = ['jsso_create', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_adjoint',
-           'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_nccl_unique_id',
+           'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
            'jsso_memset', 'jsso_stream_sync', 'jsso_device_count', 'jsso_event_create',
@@ -94,6 +94,7 @@ def lib():
     L.jsso_backward.argtypes = [vp] + [vp] * 9 + [C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_value_and_grad_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(dbl), vp, vp, vp, vp,
                                            C.POINTER(SolveOpts), C.POINTER(Stats), C.POINTER(Stats)]
+    L.jsso_assemble_adjoint_host.argtypes = [vp] * 9
     L.jsso_nccl_unique_id.argtypes = [vp]
     L.jsso_set_halo.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.jsso_halo_exchange.argtypes = [vp, vp, vp]
@@ -316,6 +317,15 @@ class Handle:
                                                 C.byref(val), _ptr(u), _ptr(dc), _ptr(dq), _ptr(db),
                                                 C.byref(o), C.byref(fs), C.byref(bs)))
         return val.value, u, dc, dq, db, fs, bs
+
+    def assemble_adjoint_host(self, crds, prop_q, prop_b, u, lam, out=None):
+        """Ke+assembly+adjoint with HOST buffers; `out` = (d_crds, d_prop_q, d_prop_b) to reuse."""
+        if out is None:
+            out = (np.empty((self.n_node, 3)), np.empty((self.n_quad, 5)) if self.n_quad else None,
+                   np.empty((self.n_beam, 6)) if self.n_beam else None)
+        self._ck(lib().jsso_assemble_adjoint_host(self.h, _ptr(crds), _ptr(prop_q), _ptr(prop_b), _ptr(u),
+                                                  _ptr(lam), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
 
     # ---- multi-GPU
     def set_halo(self, nccl_id, rank, n_rank, peer_rank, send_ptr, send_idx, recv_start, recv_count):

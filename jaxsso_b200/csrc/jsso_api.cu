@@ -697,6 +697,46 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
   return JSSO_OK;
 }
 
+// Host-buffer entry point for the solve-free part of a gradient evaluation: H2D of
+// coordinates, properties, u and lam; fused Ke + assembly (BC imposed); adjoint
+// reduction; D2H of the gradients.  This is the end-to-end leg bench.py times.
+int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const double* pq_h, const double* pb_h,
+                               const double* u_h, const double* lam_h, double* dc_h, double* dpq_h,
+                               double* dpb_h) {
+  if (!h || !crds_h || !u_h || !lam_h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_host_staging(h);
+  if (rc) return rc;
+  const Symbolic& S = h->sym;
+  const size_t nc = 3 * (size_t)S.n_node, nq = 5 * (size_t)S.n_quad, nb = 6 * (size_t)S.n_beam,
+               nd = 6 * (size_t)S.n_node;
+  cudaStream_t st = 0;
+  // the caller's buffers may be pageable: stage through pinned memory so the copies are true DMA
+  std::memcpy(h->h_crds, crds_h, nc * sizeof(double));
+  if (nq) std::memcpy(h->h_pq, pq_h, nq * sizeof(double));
+  if (nb) std::memcpy(h->h_pb, pb_h, nb * sizeof(double));
+  std::memcpy(h->h_f, u_h, nd * sizeof(double));
+  std::memcpy(h->h_u, lam_h, nd * sizeof(double));
+  CK(cudaMemcpyAsync(h->s_crds, h->h_crds, nc * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nq) CK(cudaMemcpyAsync(h->s_pq, h->h_pq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nb) CK(cudaMemcpyAsync(h->s_pb, h->h_pb, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->s_f, h->h_f, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->s_u, h->h_u, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
+  if ((rc = jsso_adjoint(h, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, dc_h ? h->s_dc : nullptr,
+                         (dpq_h && nq) ? h->s_dpq : nullptr, (dpb_h && nb) ? h->s_dpb : nullptr, st)))
+    return rc;
+  if (dc_h) CK(cudaMemcpyAsync(h->h_dc, h->s_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpq_h && nq) CK(cudaMemcpyAsync(h->h_dpq, h->s_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpb_h && nb) CK(cudaMemcpyAsync(h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (dc_h) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
+  if (dpq_h && nq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+  if (dpb_h && nb) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  return JSSO_OK;
+}
+
 // ---------------------------------------------------------------- utilities
 int jsso_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA; }
 void* jsso_dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes ? bytes : 8) == cudaSuccess ? p : nullptr; }
