@@ -37,7 +37,7 @@ struct jsso_handle {
   int32_t *rowptr = nullptr, *colidx = nullptr, *blk_row = nullptr, *diag_slot = nullptr;
   int32_t *blk_item_ptr = nullptr, *item_code = nullptr;
   uint8_t *item_lel = nullptr, *node_mask = nullptr;
-  int32_t *chunk_blk = nullptr, *chunk_el_ptr = nullptr, *chunk_els = nullptr;
+  int32_t *chunk_blk = nullptr, *chunk_el_ptr = nullptr, *chunk_els = nullptr, *blk_perm = nullptr;
   int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
   // numeric state
   double* vals = nullptr;   // nnzb*36, column-major blocks
@@ -144,7 +144,7 @@ int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
   CK(upload(&h->blk_item_ptr, S.blk_item_ptr)); CK(upload(&h->item_code, S.item_code));
   CK(upload(&h->item_lel, S.item_lel)); CK(upload(&h->node_mask, S.node_mask));
   CK(upload(&h->chunk_blk, S.chunk_blk)); CK(upload(&h->chunk_el_ptr, S.chunk_el_ptr));
-  CK(upload(&h->chunk_els, S.chunk_els));
+  CK(upload(&h->chunk_els, S.chunk_els)); CK(upload(&h->blk_perm, S.blk_perm));
   CK(upload(&h->node_inc_ptr, S.node_inc_ptr)); CK(upload(&h->node_inc, S.node_inc));
   const size_t nd = 6 * (size_t)S.n_node;
   CK(dalloc(&h->vals, (size_t)S.nnzb() * 36));
@@ -176,7 +176,7 @@ void jsso_destroy(jsso_handle* h) {
   if (h->device == JSSO_DEVICE_NONE) { delete h; return; }
   cudaSetDevice(h->device);
   void* dev[] = {h->cnct_q, h->cnct_b, h->rowptr, h->colidx, h->blk_row, h->diag_slot, h->blk_item_ptr,
-                 h->item_code, h->item_lel, h->node_mask, h->chunk_blk, h->chunk_el_ptr, h->chunk_els,
+                 h->item_code, h->item_lel, h->node_mask, h->chunk_blk, h->chunk_el_ptr, h->chunk_els, h->blk_perm,
                  h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
                  h->corner_q, h->corner_b, h->tmp_lam, h->tmp_g, h->sc, h->partials, h->counters, h->flags,
                  h->send_idx, h->send_buf, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
@@ -235,11 +235,11 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
   AsmArgs A;
   A.crds = crds; A.cnct_q = h->cnct_q; A.prop_q = prop_q; A.cnct_b = h->cnct_b; A.prop_b = prop_b;
   A.chunk_blk = h->chunk_blk; A.chunk_el_ptr = h->chunk_el_ptr; A.chunk_els = h->chunk_els;
-  A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
+  A.blk_perm = h->blk_perm; A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
   A.blk_row = h->blk_row; A.colidx = h->colidx; A.node_mask = h->node_mask;
   A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
   if (h->sym.nnzb() > 0) {
-    assemble_fused_kernel<<<h->sym.n_chunk(), kChunkItems, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
+    assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
     CKL("assemble_fused_kernel");
   }
   h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false;

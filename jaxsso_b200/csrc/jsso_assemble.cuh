@@ -6,9 +6,9 @@
 //    layout (element.py:1236-1237, 270-271) for tests and for the stand-alone
 //    assembly path
 //  * assemble_fused_kernel : Ke + assembly in one pass; K_e never reaches HBM.
-//    One CTA per chunk of <= 256 pair items (sorted by block slot); duplicates are
-//    summed in a fixed order from a shared-memory staging buffer (no atomics) and
-//    the block-CSR values are written once with fully coalesced stores.
+//    One CTA per chunk of <= 256 block slots; one thread owns one 6x6 block and sums
+//    its contributors in a fixed order in registers (no atomics), then writes the
+//    block once.
 //  * assemble_from_ke_kernel : stand-alone segmented reduction of materialised K_e.
 #pragma once
 #include "jsso_elem.cuh"
@@ -17,7 +17,7 @@
 namespace jsso {
 
 // shared-memory record of one quad (doubles); odd stride => conflict-free across quads
-constexpr int QS = 63;
+constexpr int QS = 71;
 constexpr int Q_R = 0;      // 9: dirCos rows x^,y^,z^
 constexpr int Q_GRY = 9;    // 2
 constexpr int Q_GRX = 11;   // 2
@@ -27,23 +27,21 @@ constexpr int Q_M = 17;     // m11, m12, m22
 constexpr int Q_KRZ = 20;
 constexpr int Q_MAT = 21;   // cm11 cm12 cm21 cm22 cm33 D nu hb ks
 constexpr int Q_GP = 30;    // 4 x {ji0..3, det, prr, prs, pss}
+constexpr int Q_XY = 62;    // x0,y0,x1,y1,x3,y3 local coordinates (node 3 is the origin) -> 68
 
 constexpr int FLAG_BADJAC = 1, FLAG_DEGBEAM = 2, FLAG_UNSYM = 4;
 
-// Stage the geometry of `n_el` quads (ids from `els`, or first_el + i when els is
-// null) into `sm`.  Called by all threads of the CTA; (quad, gp) tasks are dealt to
-// consecutive threads so the four Gauss points of a quad sit in adjacent lanes and
-// the drilling-stiffness minimum (element.py:978) is reduced with two shuffles.
+// Stage the geometry of `n_el` quads (ids from `els`, or first_el + i when els is null) into
+// `sm`.  Called by all threads of the CTA.  Phase A: one thread per quad (frame, projected
+// coordinates, gp-independent shear data, material).  Phase B: one thread per (quad, Gauss point)
+// (inverse Jacobian, detJ, shear scale factors); the four Gauss points of a quad sit in adjacent
+// lanes, so the drilling-stiffness minimum over the summed diagonal (element.py:978) is reduced
+// with two shuffles.
 __device__ inline void stage_quad_geometry(double* sm, int n_el, const int32_t* els, int first_el,
                                            const double* __restrict__ crds,
                                            const int32_t* __restrict__ cnct,
                                            const double* __restrict__ prop, int* flags) {
-  const int n_task = 4 * n_el;
-  for (int base = (threadIdx.x & ~31); base < n_task; base += blockDim.x) {
-    int task = base + (threadIdx.x & 31);
-    const bool live = task < n_task;
-    if (!live) task = n_task - 1;
-    const int le = task >> 2, q = task & 3;
+  for (int le = threadIdx.x; le < n_el; le += blockDim.x) {
     const int e = els ? els[le] : first_el + le;
     double P[4][3];
 #pragma unroll
@@ -56,10 +54,44 @@ __device__ inline void stage_quad_geometry(double* sm, int n_el, const int32_t* 
     quad_frame(P, f);
     QuadShear<double> sh;
     quad_shear(f, sh);
-    QuadGp<double> g;
-    quad_gp(f, q, g);
     QuadMat m;
     quad_mat(prop + 5 * (size_t)e, m);
+    double* s = sm + le * QS;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s[Q_R + 3 * i + j] = f.R[i][j];
+    s[Q_GRY] = sh.gry[0]; s[Q_GRY + 1] = sh.gry[1];
+    s[Q_GRX] = sh.grx[0]; s[Q_GRX + 1] = sh.grx[1];
+    s[Q_GSY] = sh.gsy[0]; s[Q_GSY + 1] = sh.gsy[1];
+    s[Q_GSX] = sh.gsx[0]; s[Q_GSX + 1] = sh.gsx[1];
+    s[Q_M] = sh.m11; s[Q_M + 1] = sh.m12; s[Q_M + 2] = sh.m22;
+    s[Q_MAT] = m.cm11; s[Q_MAT + 1] = m.cm12; s[Q_MAT + 2] = m.cm21; s[Q_MAT + 3] = m.cm22;
+    s[Q_MAT + 4] = m.cm33; s[Q_MAT + 5] = m.D; s[Q_MAT + 6] = m.nu; s[Q_MAT + 7] = m.hb;
+    s[Q_MAT + 8] = m.ks;
+    s[Q_XY] = f.x[0]; s[Q_XY + 1] = f.y[0]; s[Q_XY + 2] = f.x[1]; s[Q_XY + 3] = f.y[1];
+    s[Q_XY + 4] = f.x[3]; s[Q_XY + 5] = f.y[3];
+    if (prop[5 * (size_t)e + 3] != prop[5 * (size_t)e + 4]) atomicOr(flags, FLAG_UNSYM);
+  }
+  __syncthreads();
+  const int n_task = 4 * n_el;
+  for (int base = (threadIdx.x & ~31); base < n_task; base += blockDim.x) {
+    int task = base + (threadIdx.x & 31);
+    const bool live = task < n_task;
+    if (!live) task = n_task - 1;
+    const int le = task >> 2, q = task & 3;
+    double* s = sm + le * QS;
+    QuadFrame<double> f;
+    f.x[0] = s[Q_XY]; f.y[0] = s[Q_XY + 1]; f.x[1] = s[Q_XY + 2]; f.y[1] = s[Q_XY + 3];
+    f.x[2] = 0.0; f.y[2] = 0.0; f.x[3] = s[Q_XY + 4]; f.y[3] = s[Q_XY + 5];
+    QuadShear<double> sh;
+    sh.gry[0] = s[Q_GRY]; sh.gry[1] = s[Q_GRY + 1]; sh.grx[0] = s[Q_GRX]; sh.grx[1] = s[Q_GRX + 1];
+    sh.gsy[0] = s[Q_GSY]; sh.gsy[1] = s[Q_GSY + 1]; sh.gsx[0] = s[Q_GSX]; sh.gsx[1] = s[Q_GSX + 1];
+    sh.m11 = s[Q_M]; sh.m12 = s[Q_M + 1]; sh.m22 = s[Q_M + 2];
+    QuadMat m;
+    m.D = s[Q_MAT + 5]; m.nu = s[Q_MAT + 6]; m.hb = s[Q_MAT + 7]; m.ks = s[Q_MAT + 8];
+    QuadGp<double> g;
+    quad_gp(f, q, g);
     double dg[8];
     quad_diag_gp(sh, g, q, m, dg);
     double krz = 1e300;
@@ -70,32 +102,16 @@ __device__ inline void stage_quad_geometry(double* sm, int n_el, const int32_t* 
       krz = fmin(krz, fabs(dg[i]));
     }
     if (live) {
-      double* s = sm + le * QS;
       double* sg = s + Q_GP + 8 * q;
       sg[0] = g.ji[0]; sg[1] = g.ji[1]; sg[2] = g.ji[2]; sg[3] = g.ji[3];
       sg[4] = g.det; sg[5] = g.prr; sg[6] = g.prs; sg[7] = g.pss;
       if (!(g.det > 0.0)) atomicOr(flags, FLAG_BADJAC);
-      if (q == 0) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) s[Q_R + 3 * i + j] = f.R[i][j];
-        s[Q_GRY] = sh.gry[0]; s[Q_GRY + 1] = sh.gry[1];
-        s[Q_GRX] = sh.grx[0]; s[Q_GRX + 1] = sh.grx[1];
-        s[Q_GSY] = sh.gsy[0]; s[Q_GSY + 1] = sh.gsy[1];
-        s[Q_GSX] = sh.gsx[0]; s[Q_GSX + 1] = sh.gsx[1];
-        s[Q_M] = sh.m11; s[Q_M + 1] = sh.m12; s[Q_M + 2] = sh.m22;
-        s[Q_KRZ] = krz / 1000.0;
-        s[Q_MAT] = m.cm11; s[Q_MAT + 1] = m.cm12; s[Q_MAT + 2] = m.cm21; s[Q_MAT + 3] = m.cm22;
-        s[Q_MAT + 4] = m.cm33; s[Q_MAT + 5] = m.D; s[Q_MAT + 6] = m.nu; s[Q_MAT + 7] = m.hb;
-        s[Q_MAT + 8] = m.ks;
-        if (prop[5 * (size_t)e + 3] != prop[5 * (size_t)e + 4]) atomicOr(flags, FLAG_UNSYM);
-      }
+      if (q == 0) s[Q_KRZ] = krz / 1000.0;
     }
   }
 }
 
-// G = R^T S R for S = [[s00,s01,0],[s10,s11,0],[0,0,s22]], written into the 6x6
+// G = R^T S R for S = [[s00,s01,0],[s10,s11,0],[0,0,s22]], ADDED into the 6x6
 // column-major block `out` at sub-block (br, bc).
 __device__ inline void rtsr_diag(const double* R, double s00, double s01, double s10, double s11,
                                  double s22, double* out, int br, int bc) {
@@ -109,10 +125,11 @@ __device__ inline void rtsr_diag(const double* R, double s00, double s01, double
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-      out[(3 * bc + j) * 6 + 3 * br + i] = u[i] * R[j] + v[i] * R[3 + j] + (s22 * R[6 + i]) * R[6 + j];
+      out[(3 * bc + j) * 6 + 3 * br + i] += u[i] * R[j] + v[i] * R[3 + j] + (s22 * R[6 + i]) * R[6 + j];
 }
 
-// 6x6 global block (a,b) of a quad from its staged record `s`; column-major out[6*j+i].
+// 6x6 global block (a,b) of a quad from its staged record `s`, ADDED into the column-major
+// accumulator out[6*j+i].
 __device__ inline void quad_pair_block(const double* s, int a, int b, double* out) {
   const double ra = node_r(a), sa = node_s(a), rb = node_r(b), sb = node_s(b);
   double pxx = 0, pxy = 0, pyx = 0, pyy = 0, crr = 0, crs = 0, csr = 0, css = 0;
@@ -167,13 +184,13 @@ __device__ inline void quad_pair_block(const double* s, int a, int b, double* ou
     const double rj = P[1][0] * R[j] + P[2][0] * R[3 + j];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      out[(3 + j) * 6 + i] = R[6 + i] * cj;       // rows: translations, cols: rotations
-      out[i * 6 + 3 + j] = rj * R[6 + i];         // rows: rotations (j), cols: translations (i)
+      out[(3 + j) * 6 + i] += R[6 + i] * cj;      // rows: translations, cols: rotations
+      out[i * 6 + 3 + j] += rj * R[6 + i];        // rows: rotations (j), cols: translations (i)
     }
   }
 }
 
-// 6x6 global block (a,b) of a beam-column, K_e = T^-1 K_local T (element.py:107-139).
+// 6x6 global block (a,b) of a beam-column, K_e = T^-1 K_local T (element.py:107-139), ADDED into out.
 __device__ inline void beam_pair_block(const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                                        const double* __restrict__ prop, int e, int a, int b, double* out,
                                        int* flags) {
@@ -236,10 +253,10 @@ __device__ inline void beam_pair_block(const double* __restrict__ crds, const in
       }
       const double tr = Ri[i][1] * tr_v_thz * R[2][j] + Ri[i][2] * tr_w_thy * R[1][j];
       const double rt = Ri[i][1] * rt_thy_w * R[2][j] + Ri[i][2] * rt_thz_v * R[1][j];
-      out[j * 6 + i] = tt;
-      out[(3 + j) * 6 + 3 + i] = rr;
-      out[(3 + j) * 6 + i] = tr;
-      out[j * 6 + 3 + i] = rt;
+      out[j * 6 + i] += tt;
+      out[(3 + j) * 6 + 3 + i] += rr;
+      out[(3 + j) * 6 + i] += tr;
+      out[j * 6 + 3 + i] += rt;
     }
 }
 
@@ -255,6 +272,8 @@ quad_ke_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __res
   const int le = threadIdx.x >> 4, a = (threadIdx.x >> 2) & 3, b = threadIdx.x & 3;
   if (le >= n_el) return;
   double out[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) out[k] = 0.0;
   quad_pair_block(sm + le * QS, a, b, out);
   double* dst = ke + (size_t)(first + le) * 576 + (6 * a) * 24 + 6 * b;
 #pragma unroll
@@ -270,6 +289,8 @@ beam_ke_kernel(int n_beam, const double* __restrict__ crds, const int32_t* __res
   const int e = t >> 2, a = (t >> 1) & 1, b = t & 1;
   if (e >= n_beam) return;
   double out[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) out[k] = 0.0;
   beam_pair_block(crds, cnct, prop, e, a, b, out, flags);
   double* dst = ke + (size_t)e * 144 + (6 * a) * 12 + 6 * b;
 #pragma unroll
@@ -287,56 +308,55 @@ __device__ inline double bc_entry(double v, unsigned rmask, unsigned cmask, int 
   return v;
 }
 
-constexpr int STAGE_LD = kChunkItems + 1;  // odd => conflict-free column reads
-constexpr int FUSED_SMEM_DOUBLES =
-    (36 * STAGE_LD > kChunkQuads * QS) ? 36 * STAGE_LD : kChunkQuads * QS;
+constexpr int FUSED_SMEM_DOUBLES = kChunkQuads * QS;
 
 struct AsmArgs {
   const double* crds; const int32_t* cnct_q; const double* prop_q;
   const int32_t* cnct_b; const double* prop_b;
   const int32_t* chunk_blk; const int32_t* chunk_el_ptr; const int32_t* chunk_els;
-  const int32_t* blk_item_ptr; const int32_t* item_code; const uint8_t* item_lel;
+  const int32_t* blk_perm; const int32_t* blk_item_ptr; const int32_t* item_code; const uint8_t* item_lel;
   const int32_t* blk_row; const int32_t* colidx; const uint8_t* node_mask;
   double* vals; int* flags; int n_quad; int apply_bc;
 };
 
-__global__ void __launch_bounds__(kChunkItems)
+// One CTA per chunk of consecutive block slots.  After the chunk's quads are staged in shared
+// memory, ONE THREAD OWNS ONE 6x6 BLOCK: it loops over the block's contributors (element, a, b)
+// in list order, accumulates in registers and writes its 288 contiguous bytes once -- no atomics,
+// no staging buffer, a fixed summation order.  Blocks are dealt to threads by decreasing
+// contributor count (blk_perm), so the lanes of a warp loop the same number of times.
+__global__ void __launch_bounds__(kChunkBlocks, 2)
 assemble_fused_kernel(AsmArgs A) {
   extern __shared__ double sm[];
   const int c = blockIdx.x;
   const int blk0 = A.chunk_blk[c], blk1 = A.chunk_blk[c + 1];
-  const int it0 = A.blk_item_ptr[blk0], it1 = A.blk_item_ptr[blk1];
   const int el0 = A.chunk_el_ptr[c], n_el = A.chunk_el_ptr[c + 1] - el0;
-  if (n_el > 0)
-    stage_quad_geometry(sm, n_el, A.chunk_els + el0, 0, A.crds, A.cnct_q, A.prop_q, A.flags);
+  stage_quad_geometry(sm, n_el, A.chunk_els + el0, 0, A.crds, A.cnct_q, A.prop_q, A.flags);
   __syncthreads();
-  const int it = it0 + threadIdx.x;
-  double out[36];
-  if (it < it1) {
+  if ((int)threadIdx.x >= blk1 - blk0) return;
+  const int blk = A.blk_perm[blk0 + threadIdx.x];
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  const int i1 = A.blk_item_ptr[blk + 1];
+  for (int it = A.blk_item_ptr[blk]; it < i1; ++it) {
     const int code = A.item_code[it];
     const int el = code >> 4, a = (code >> 2) & 3, b = code & 3;
-    if (el < A.n_quad) quad_pair_block(sm + A.item_lel[it] * QS, a, b, out);
-    else beam_pair_block(A.crds, A.cnct_b, A.prop_b, el - A.n_quad, a, b, out, A.flags);
+    if (el < A.n_quad) quad_pair_block(sm + A.item_lel[it] * QS, a, b, acc);
+    else beam_pair_block(A.crds, A.cnct_b, A.prop_b, el - A.n_quad, a, b, acc, A.flags);
   }
-  __syncthreads();  // geometry records are dead; the staging buffer aliases them
-  if (it < it1) {
+  if (A.apply_bc) {
+    const int r = A.blk_row[blk], cc = A.colidx[blk];
+    const unsigned rm = A.node_mask[r], cm = A.node_mask[cc];
+    if (rm | cm) {
 #pragma unroll
-    for (int k = 0; k < 36; ++k) sm[k * STAGE_LD + threadIdx.x] = out[k];
-  }
-  __syncthreads();
-  const int n_out = (blk1 - blk0) * 36;
-  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-    const int bl = o / 36, k = o - bl * 36;
-    const int blk = blk0 + bl;
-    const int i0 = A.blk_item_ptr[blk] - it0, i1 = A.blk_item_ptr[blk + 1] - it0;
-    double s = 0.0;
-    for (int i = i0; i < i1; ++i) s += sm[k * STAGE_LD + i];
-    if (A.apply_bc) {
-      const int r = A.blk_row[blk], cc = A.colidx[blk];
-      s = bc_entry(s, A.node_mask[r], A.node_mask[cc], k % 6, k / 6, r == cc);
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[j * 6 + i] = bc_entry(acc[j * 6 + i], rm, cm, i, j, r == cc);
     }
-    A.vals[(size_t)blk * 36 + k] = s;
   }
+  double2* dst = (double2*)(A.vals + (size_t)blk * 36);
+#pragma unroll
+  for (int k = 0; k < 18; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
 }
 
 // Stand-alone numeric assembly: one thread per stored entry, contributors summed in

@@ -121,7 +121,8 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cq,
         fresh.push_back(el);
     }
     if ((int)fresh.size() > kChunkQuads) return "a block touches more quads than a chunk can stage";
-    if (items + (i1 - i0) > kChunkItems || quads + (int)fresh.size() > kChunkQuads) {
+    if (items + (i1 - i0) > kChunkItems || quads + (int)fresh.size() > kChunkQuads ||
+        blk - S.chunk_blk.back() >= kChunkBlocks) {
       S.chunk_blk.push_back((int32_t)blk);
       S.chunk_el_ptr.push_back((int32_t)S.chunk_els.size());
       ++chunk; items = 0; quads = 0;
@@ -140,6 +141,14 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cq,
   }
   S.chunk_blk.push_back((int32_t)nnzb);
   S.chunk_el_ptr.push_back((int32_t)S.chunk_els.size());
+  // per chunk: blocks by decreasing contributor count (stable => ascending id within a count)
+  S.blk_perm.resize(nnzb);
+  std::iota(S.blk_perm.begin(), S.blk_perm.end(), 0);
+  for (int c = 0; c + 1 < (int)S.chunk_blk.size(); ++c)
+    std::stable_sort(S.blk_perm.begin() + S.chunk_blk[c], S.blk_perm.begin() + S.chunk_blk[c + 1],
+                     [&](int32_t x, int32_t y) {
+                       return S.blk_item_ptr[x + 1] - S.blk_item_ptr[x] > S.blk_item_ptr[y + 1] - S.blk_item_ptr[y];
+                     });
   return "";
 }
 

@@ -15,8 +15,9 @@
 
 namespace jsso {
 
-constexpr int kChunkItems = 256;  // pair items per assembly chunk (= CTA size)
-constexpr int kChunkQuads = 48;   // distinct quads whose geometry a chunk stages in shared memory
+constexpr int kChunkBlocks = 256; // block slots per assembly chunk (= CTA size: one thread per block)
+constexpr int kChunkItems = 448;  // pair items per assembly chunk
+constexpr int kChunkQuads = 64;   // distinct quads whose geometry a chunk stages in shared memory
 
 struct Symbolic {
   int n_node = 0, n_row = 0, n_quad = 0, n_beam = 0;
@@ -28,6 +29,8 @@ struct Symbolic {
   std::vector<int32_t> item_code;     // (elem << 4) | (a << 2) | b; beams use elem = n_quad + id
   std::vector<uint8_t> item_lel;      // quad items: index into the chunk's staged-geometry list
   std::vector<int32_t> chunk_blk;     // n_chunk + 1 block boundaries
+  std::vector<int32_t> blk_perm;      // nnzb: within each chunk, its block ids ordered by decreasing
+                                      // contributor count (warps then loop a uniform number of times)
   std::vector<int32_t> chunk_el_ptr;  // n_chunk + 1
   std::vector<int32_t> chunk_els;     // quads staged per chunk
   // per node: incident (element, local node) corners, for the gradient gather
