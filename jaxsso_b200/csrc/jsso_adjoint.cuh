@@ -6,13 +6,13 @@
 // sum_duplicates / sort / concatenate and vmap(element_K_*) including its batched LU
 // solves.  Mathematically that is
 //     dL/dx = - d/dx [ lam_e^T K_e(x) u_e ]   summed over elements,
-// so these kernels never form K_e, dK_e or the nse-long cotangent: each thread
-// evaluates the scalar bilinear form e(x) = lam_e^T K_e(x) u_e through the element's
-// strains with forward-mode duals seeded on the three coordinates of ONE node of the
-// element (thread = (element, node)), using the same templated geometry code as the
-// stiffness kernels.  Property derivatives are closed-form from the split energies.
-// Nodal gradients are then gathered per node from the per-corner partials in a fixed
-// order (no atomics).
+// so these kernels never form K_e, dK_e or the nse-long cotangent: they differentiate the
+// scalar bilinear form e(x) = lam_e^T K_e(x) u_e evaluated through the element's strains.
+//   * quads: hand-derived reverse mode, thread = (quad, Gauss point) (below);
+//   * beam-columns: forward-mode duals seeded on the three coordinates of one node,
+//     thread = (beam, node), on the same templated geometry code as the stiffness kernel.
+// Property derivatives are closed-form from the split energies.  Nodal gradients are then
+// gathered per node from the per-corner partials in a fixed order (no atomics).
 #pragma once
 #include "jsso_elem.cuh"
 
@@ -20,198 +20,381 @@ namespace jsso {
 
 using D3 = Dual<3>;
 
-struct QuadEnergyParts {      // value parts needed for the closed-form property derivatives
-  double Mxx, Mxy, Myx, Myy, Mss;   // membrane contractions (sum_gp detJ ...)
-  double Bsum, Bnu, Bss;            // bending: kxx+kyy terms, nu cross terms, twist term
-  double Sh;                        // shear contraction
-  double theta;                     // sum_k lam_thz,k u_thz,k (local)
-  double kb_a, kb_b, ks_c;          // arg-min diagonal: |D (kb_a + hb kb_b) + ks ks_c|
-  double sign;                      // sign of that diagonal entry
-};
+// ---------------------------------------------------------------------------------------
+// Hand-derived reverse mode of e(X) = lam_e^T K_e(X) u_e for the MITC4 quad.
+//
+// thread = (quad, Gauss point); the 4 lanes of a quad cooperate through shuffles.  With
+// h_k = J^-1 dN_k (physical shape-function gradients), fields phi in {u, v, theta_x, theta_y}
+// of both vectors, Phi the membrane+bending energy density and S_phi = dPhi/d(grad phi):
+//   d(detJ Phi)/dx_m = detJ (h_m,x Phi - h_m . T_x),   T = sum_phi S_phi (x) grad phi
+//   d(detJ Phi)/dphi_k = detJ S_phi . h_k
+// (the classic shape derivative: d grad phi = -h_m (grad phi)_x dx_m, d detJ = detJ h_m,x dx_m).
+// The MITC4 shear energy is  ks [m11 Prr al au + m12 Prs (al bu + bl au) + m22 Pss bl bu]
+// with a(s) = (1+s) A0 + (1-s) A1, b(r) = (1+r) B0 + (1-r) B1 the covariant edge strains and
+// Prr = |J row 1|^2/(4 detJ), Pss = |J row 0|^2/(4 detJ), Prs = sqrt(Prr Pss); its adjoint goes
+// through (Prr, Prs, Pss) -> J -> local coordinates, through m12 and through the edge vectors.
+// The drilling spring min|diag|/1000 * sum_k lam_thz,k u_thz,k differentiates the arg-min
+// diagonal entry only (first arg-min, element.py:978).  Local-coordinate and frame adjoints are
+// finally pulled back through the normalised cross-product frame (element.py:502-539).
+// ---------------------------------------------------------------------------------------
+constexpr int ADJ_QUADS = 32;        // quads per CTA (128 threads)
+constexpr int ADJ_LD = 97;           // doubles per quad in shared memory (odd stride)
+constexpr int A_UG = 0, A_LG = 24, A_UL = 48, A_LL = 72;   // global u, global lam, local u, local lam
 
-// e = lam_e^T K_e u_e for one quad.  P: nodal coordinates (S), prop: t,E,nu,kx,ky,
-// ue/le: the 24 global dofs of u and lam.
-template <class S>
-__device__ inline S quad_bilinear(const S P[4][3], const double* prop, const double* ue, const double* le,
-                                  QuadEnergyParts* parts) {
-  QuadFrame<S> f;
-  quad_frame(P, f);
-  QuadShear<S> sh;
-  quad_shear(f, sh);
-  QuadMat m;
-  quad_mat(prop, m);
-  // local vectors  (T u)_k = (R u_k[0:3], R u_k[3:6])
-  S ut[4][3], ur[4][3], lt[4][3], lr[4][3];
+__device__ inline double quad4_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+template <bool WANT_PROP>
+__global__ void __launch_bounds__(4 * ADJ_QUADS)
+quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+                    const double* __restrict__ prop, const double* __restrict__ u,
+                    const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
+  __shared__ double sv[ADJ_QUADS * ADJ_LD];
+  const int le = threadIdx.x >> 2, q = threadIdx.x & 3;
+  int e = blockIdx.x * ADJ_QUADS + le;
+  const bool valid = e < n_quad;
+  if (!valid) e = n_quad - 1;
+  double* sm = sv + le * ADJ_LD;
+  // ---- gather: every lane needs the four nodes' coordinates; lane q stages node q's vectors
+  double P[4][3];
+  int nq = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 4; ++k) {
+    const int nd = cnct[4 * e + k];
+    if (k == q) nq = nd;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
+  }
+  QuadFrame<double> f;
+  quad_frame(P, f);
+  {
+    double ug[6], lg[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { ug[d] = u[6 * (size_t)nq + d]; lg[d] = lam[6 * (size_t)nq + d]; }
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { sm[A_UG + 6 * q + d] = ug[d]; sm[A_LG + 6 * q + d] = lg[d]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      ut[k][i] = f.R[i][0] * ue[6 * k] + f.R[i][1] * ue[6 * k + 1] + f.R[i][2] * ue[6 * k + 2];
-      ur[k][i] = f.R[i][0] * ue[6 * k + 3] + f.R[i][1] * ue[6 * k + 4] + f.R[i][2] * ue[6 * k + 5];
-      lt[k][i] = f.R[i][0] * le[6 * k] + f.R[i][1] * le[6 * k + 1] + f.R[i][2] * le[6 * k + 2];
-      lr[k][i] = f.R[i][0] * le[6 * k + 3] + f.R[i][1] * le[6 * k + 4] + f.R[i][2] * le[6 * k + 5];
+      sm[A_UL + 6 * q + i] = f.R[i][0] * ug[0] + f.R[i][1] * ug[1] + f.R[i][2] * ug[2];
+      sm[A_UL + 6 * q + 3 + i] = f.R[i][0] * ug[3] + f.R[i][1] * ug[4] + f.R[i][2] * ug[5];
+      sm[A_LL + 6 * q + i] = f.R[i][0] * lg[0] + f.R[i][1] * lg[1] + f.R[i][2] * lg[2];
+      sm[A_LL + 6 * q + 3 + i] = f.R[i][0] * lg[3] + f.R[i][1] * lg[4] + f.R[i][2] * lg[5];
     }
-  // covariant edge shear strains (gp independent): A+/A- along r on edges 1-2 / 4-3,
-  // B+/B- along s on edges 1-4 / 2-3
-  S Au[2], Al[2], Bu[2], Bl[2];
-  Au[0] = (ut[0][2] - ut[1][2]) * 0.5 + sh.gry[0] * (ur[0][0] + ur[1][0]) + sh.grx[0] * (ur[0][1] + ur[1][1]);
-  Au[1] = (ut[3][2] - ut[2][2]) * 0.5 + sh.gry[1] * (ur[2][0] + ur[3][0]) + sh.grx[1] * (ur[2][1] + ur[3][1]);
-  Bu[0] = (ut[0][2] - ut[3][2]) * 0.5 + sh.gsy[0] * (ur[0][0] + ur[3][0]) + sh.gsx[0] * (ur[0][1] + ur[3][1]);
-  Bu[1] = (ut[1][2] - ut[2][2]) * 0.5 + sh.gsy[1] * (ur[1][0] + ur[2][0]) + sh.gsx[1] * (ur[1][1] + ur[2][1]);
-  Al[0] = (lt[0][2] - lt[1][2]) * 0.5 + sh.gry[0] * (lr[0][0] + lr[1][0]) + sh.grx[0] * (lr[0][1] + lr[1][1]);
-  Al[1] = (lt[3][2] - lt[2][2]) * 0.5 + sh.gry[1] * (lr[2][0] + lr[3][0]) + sh.grx[1] * (lr[2][1] + lr[3][1]);
-  Bl[0] = (lt[0][2] - lt[3][2]) * 0.5 + sh.gsy[0] * (lr[0][0] + lr[3][0]) + sh.gsx[0] * (lr[0][1] + lr[3][1]);
-  Bl[1] = (lt[1][2] - lt[2][2]) * 0.5 + sh.gsy[1] * (lr[1][0] + lr[2][0]) + sh.gsx[1] * (lr[1][1] + lr[2][1]);
+  }
+  __syncwarp();
+  const double* UL = sm + A_UL;   // local u: per node [u, v, w, thx, thy, thz]
+  const double* LL = sm + A_LL;
+  const double* pr = prop + 5 * (size_t)e;
+  QuadMat m;
+  quad_mat(pr, m);
+  QuadShear<double> sh;
+  quad_shear(f, sh);
+  QuadGp<double> g;
+  quad_gp(f, q, g);
+  const double r = JSSO_GP * node_r(q), s = JSSO_GP * node_s(q);
 
-  const S zero = Lift<S>::from(0.0);
-  S Mxx = zero, Mxy = zero, Myx = zero, Myy = zero, Mss = zero;
-  S Bsum = zero, Bnu = zero, Bss = zero, Sh = zero;
-  S diag[8];
+  // ---- pass 1: drilling stiffness = min |sum_gp diag| / 1000, first arg-min
+  int im = 0;
+  double dsel;
+  {
+    double dg[8];
+    quad_diag_gp(sh, g, q, m, dg);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) diag[i] = zero;
+    for (int i = 0; i < 8; ++i) dg[i] = quad4_sum(dg[i]);
+    double best = fabs(dg[0]);
+    dsel = dg[0];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    QuadGp<S> g;
-    quad_gp(f, q, g);
-    const double r = JSSO_GP * node_r(q), s = JSSO_GP * node_s(q);
-    S exu = zero, eyu = zero, gxu = zero, exl = zero, eyl = zero, gxl = zero;     // membrane
-    S kxu = zero, kyu = zero, kzu = zero, kxl = zero, kyl = zero, kzl = zero;     // curvatures
+    for (int i = 1; i < 8; ++i) {
+      const double a = fabs(dg[i]);
+      if (a < best) { best = a; im = i; dsel = dg[i]; }
+    }
+  }
+  const double sgn = (dsel < 0.0) ? -1.0 : 1.0;
+  const double krz = fabs(dsel) * 1e-3;
+  double theta = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) theta += LL[6 * k + 5] * UL[6 * k + 5];
+  const double dbar = sgn * theta * 1e-3;   // adjoint of the selected (summed) diagonal entry
+
+  // ---- pass 2: this Gauss point
+  double h0[4], h1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double dr = 0.25 * node_r(k) * (1.0 + s * node_s(k));
+    const double ds = 0.25 * node_s(k) * (1.0 + r * node_r(k));
+    h0[k] = g.ji[0] * dr + g.ji[1] * ds;
+    h1[k] = g.ji[2] * dr + g.ji[3] * ds;
+  }
+  // gradients of the eight fields: a = u, b = v, c = theta_x, d = theta_y (lower: u, upper: lam)
+  double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+  double A0 = 0, A1 = 0, B0 = 0, B1 = 0, C0 = 0, C1 = 0, D0 = 0, D1 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double uu = UL[6 * k], uv = UL[6 * k + 1], ux = UL[6 * k + 3], uy = UL[6 * k + 4];
+    const double lu = LL[6 * k], lv = LL[6 * k + 1], lx = LL[6 * k + 3], ly = LL[6 * k + 4];
+    a0 += h0[k] * uu; a1 += h1[k] * uu; b0 += h0[k] * uv; b1 += h1[k] * uv;
+    c0 += h0[k] * ux; c1 += h1[k] * ux; d0 += h0[k] * uy; d1 += h1[k] * uy;
+    A0 += h0[k] * lu; A1 += h1[k] * lu; B0 += h0[k] * lv; B1 += h1[k] * lv;
+    C0 += h0[k] * lx; C1 += h1[k] * lx; D0 += h0[k] * ly; D1 += h1[k] * ly;
+  }
+  const double exu = a0, eyu = b1, gxu = a1 + b0, kxu = -d0, kyu = c1, kzu = c0 - d1;
+  const double exl = A0, eyl = B1, gxl = A1 + B0, kxl = -D0, kyl = C1, kzl = C0 - D1;
+  // stresses: dPhi/d(strain of u) and dPhi/d(strain of lam)
+  const double Nxu = m.cm11 * exl + m.cm21 * eyl, Nyu = m.cm12 * exl + m.cm22 * eyl, Nsu = m.cm33 * gxl;
+  const double Nxl = m.cm11 * exu + m.cm12 * eyu, Nyl = m.cm21 * exu + m.cm22 * eyu, Nsl = m.cm33 * gxu;
+  const double Mxu = m.D * (kxl + m.nu * kyl), Myu = m.D * (kyl + m.nu * kxl), Mzu = m.D * m.hb * kzl;
+  const double Mxl = m.D * (kxu + m.nu * kyu), Myl = m.D * (kyu + m.nu * kxu), Mzl = m.D * m.hb * kzu;
+  const double Phi = exl * Nxl + eyl * Nyl + gxl * Nsl + kxl * Mxl + kyl * Myl + kzl * Mzl;
+  // S_phi = dPhi/d(grad phi) for the eight fields
+  //   u: (Nx, Ns)  v: (Ns, Ny)  thx: (Mz, My)  thy: (-Mx, -Mz)
+  const double Tx0 = Nxu * a0 + Nsu * b0 + Mzu * c0 - Mxu * d0 + Nxl * A0 + Nsl * B0 + Mzl * C0 - Mxl * D0;
+  const double Tx1 = Nsu * a0 + Nyu * b0 + Myu * c0 - Mzu * d0 + Nsl * A0 + Nyl * B0 + Myl * C0 - Mzl * D0;
+  const double Ty0 = Nxu * a1 + Nsu * b1 + Mzu * c1 - Mxu * d1 + Nxl * A1 + Nsl * B1 + Mzl * C1 - Mxl * D1;
+  const double Ty1 = Nsu * a1 + Nyu * b1 + Myu * c1 - Mzu * d1 + Nsl * A1 + Nyl * B1 + Myl * C1 - Mzl * D1;
+  double xb[4] = {0, 0, 0, 0}, yb[4] = {0, 0, 0, 0};   // adjoints of the local coordinates
+  double Rb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // adjoint of dirCos
+  const double* UG = sm + A_UG;
+  const double* LG = sm + A_LG;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xb[k] += g.det * (h0[k] * Phi - (h0[k] * Tx0 + h1[k] * Tx1));
+    yb[k] += g.det * (h1[k] * Phi - (h0[k] * Ty0 + h1[k] * Ty1));
+    // nodal adjoints of the local components (u, v, thx, thy) of both vectors -> dirCos rows 0, 1
+    const double ub = g.det * (Nxu * h0[k] + Nsu * h1[k]), vb = g.det * (Nsu * h0[k] + Nyu * h1[k]);
+    const double txb = g.det * (Mzu * h0[k] + Myu * h1[k]), tyb = -g.det * (Mxu * h0[k] + Mzu * h1[k]);
+    const double Ub = g.det * (Nxl * h0[k] + Nsl * h1[k]), Vb = g.det * (Nsl * h0[k] + Nyl * h1[k]);
+    const double Txb = g.det * (Mzl * h0[k] + Myl * h1[k]), Tyb = -g.det * (Mxl * h0[k] + Mzl * h1[k]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Rb[0][c] += ub * UG[6 * k + c] + txb * UG[6 * k + 3 + c] + Ub * LG[6 * k + c] + Txb * LG[6 * k + 3 + c];
+      Rb[1][c] += vb * UG[6 * k + c] + tyb * UG[6 * k + 3 + c] + Vb * LG[6 * k + c] + Tyb * LG[6 * k + 3 + c];
+    }
+  }
+  // ---- MITC4 shear
+  // covariant edge strains of u and lam: index 0: A0 (edge 1-2), 1: A1 (edge 4-3), 2: B0 (1-4), 3: B1 (2-3)
+  // edge e: nodes (n1, n2), w-coefficient +1/2 on n1 and -1/2 on n2, theta sums weighted by gy/gx
+  double Eu[4], El[4];
+  {
+    const int n1[4] = {0, 3, 0, 1}, n2[4] = {1, 2, 3, 2};
+    const double gy[4] = {sh.gry[0], sh.gry[1], sh.gsy[0], sh.gsy[1]};
+    const double gx[4] = {sh.grx[0], sh.grx[1], sh.gsx[0], sh.gsx[1]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Eu[i] = 0.5 * (UL[6 * n1[i] + 2] - UL[6 * n2[i] + 2]) + gy[i] * (UL[6 * n1[i] + 3] + UL[6 * n2[i] + 3]) +
+              gx[i] * (UL[6 * n1[i] + 4] + UL[6 * n2[i] + 4]);
+      El[i] = 0.5 * (LL[6 * n1[i] + 2] - LL[6 * n2[i] + 2]) + gy[i] * (LL[6 * n1[i] + 3] + LL[6 * n2[i] + 3]) +
+              gx[i] * (LL[6 * n1[i] + 4] + LL[6 * n2[i] + 4]);
+    }
+  }
+  const double au = Eu[0] * (1.0 + s) + Eu[1] * (1.0 - s), al = El[0] * (1.0 + s) + El[1] * (1.0 - s);
+  const double bu = Eu[2] * (1.0 + r) + Eu[3] * (1.0 - r), bl = El[2] * (1.0 + r) + El[3] * (1.0 - r);
+  const double Crr = al * au, Crs = al * bu + bl * au, Css = bl * bu;
+  double m12b = m.ks * g.prs * Crs;
+  double Prrb = m.ks * sh.m11 * Crr, Prsb = m.ks * sh.m12 * Crs, Pssb = m.ks * sh.m22 * Css;
+  const double aub = m.ks * (sh.m11 * g.prr * al + sh.m12 * g.prs * bl);
+  const double alb = m.ks * (sh.m11 * g.prr * au + sh.m12 * g.prs * bu);
+  const double bub = m.ks * (sh.m12 * g.prs * al + sh.m22 * g.pss * bl);
+  const double blb = m.ks * (sh.m12 * g.prs * au + sh.m22 * g.pss * bu);
+  double Eub[4] = {(1.0 + s) * aub, (1.0 - s) * aub, (1.0 + r) * bub, (1.0 - r) * bub};
+  double Elb[4] = {(1.0 + s) * alb, (1.0 - s) * alb, (1.0 + r) * blb, (1.0 - r) * blb};
+  double gyb[4] = {0, 0, 0, 0}, gxb[4] = {0, 0, 0, 0};   // adjoints of (gry0, gry1, gsy0, gsy1), (grx.., gsx..)
+
+  // ---- drilling: derivative of the selected diagonal entry (this Gauss point's share)
+  double kb_a = 0, kb_b = 0, ks_c = 0;
+  {
+    const int kd = im >> 1, comp = im & 1;
+    double hk0 = h0[0], hk1 = h1[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (k == kd) { hk0 = h0[k]; hk1 = h1[k]; }
+    const double pxx = g.det * hk0 * hk0, pyy = g.det * hk1 * hk1;
+    // bending part D (pa + hb pb): comp 0 (theta_x): pa = pyy, pb = pxx; comp 1: pa = pxx, pb = pyy
+    const double wxx = dbar * m.D * (comp ? 1.0 : m.hb), wyy = dbar * m.D * (comp ? m.hb : 1.0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // d pxx/dx_m = -det hk0^2 h_m0 ; d pxx/dy_m = det hk0 (h_m1 hk0 - 2 h_m0 hk1)
+      // d pyy/dx_m = det hk1 (h_m0 hk1 - 2 h_m1 hk0) ; d pyy/dy_m = -det hk1^2 h_m1
+      xb[k] += wxx * (-pxx * h0[k]) + wyy * (g.det * hk1 * (h0[k] * hk1 - 2.0 * h1[k] * hk0));
+      yb[k] += wxx * (g.det * hk0 * (h1[k] * hk0 - 2.0 * h0[k] * hk1)) + wyy * (-pyy * h1[k]);
+    }
+    kb_a = comp ? pxx : pyy; kb_b = comp ? pyy : pxx;
+    // shear part ks (m11 crr ax^2 + 2 m12 crs ax bx + m22 css bx^2)
+    const double fr = 1.0 + s * node_s(kd), fs = 1.0 + r * node_r(kd);
+    const int ir = (kd < 2) ? 0 : 1, is = (kd == 0 || kd == 3) ? 0 : 1;
+    const double ax = comp ? sh.grx[ir] : sh.gry[ir], bx = comp ? sh.gsx[is] : sh.gsy[is];
+    const double crr = g.prr * fr * fr, crs = g.prs * fr * fs, css = g.pss * fs * fs;
+    ks_c = sh.m11 * crr * ax * ax + 2.0 * sh.m12 * crs * ax * bx + sh.m22 * css * bx * bx;
+    const double w = dbar * m.ks;
+    Prrb += w * sh.m11 * fr * fr * ax * ax;
+    Prsb += w * sh.m12 * 2.0 * fr * fs * ax * bx;
+    Pssb += w * sh.m22 * fs * fs * bx * bx;
+    m12b += w * 2.0 * crs * ax * bx;
+    const double axb = w * 2.0 * (sh.m11 * crr * ax + sh.m12 * crs * bx);
+    const double bxb = w * 2.0 * (sh.m12 * crs * ax + sh.m22 * css * bx);
+    // ax is gr?[ir] (edge index ir), bx is gs?[is] (edge index 2 + is)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (comp == 0) { if (i == ir) gyb[i] += axb; if (i == is) gyb[2 + i] += bxb; }
+      else           { if (i == ir) gxb[i] += axb; if (i == is) gxb[2 + i] += bxb; }
+    }
+  }
+  // ---- (Prr, Prs, Pss) -> J -> local coordinates
+  {
+    // recover J from J^-1: J = det * [[ji3, -ji1], [-ji2, ji0]]
+    const double j00 = g.det * g.ji[3], j01 = -g.det * g.ji[1], j10 = -g.det * g.ji[2], j11 = g.det * g.ji[0];
+    const double n1 = j10 * j10 + j11 * j11, n0 = j00 * j00 + j01 * j01;
+    const double qq = 0.25 / g.det, w = sqrt(n1 * n0);
+    double n1b = Prrb * qq, n0b = Pssb * qq;
+    double qb = Prrb * n1 + Pssb * n0 + Prsb * w;
+    const double wb = Prsb * qq;
+    n1b += wb * n0 / (2.0 * w);
+    n0b += wb * n1 / (2.0 * w);
+    const double detb = -qb * qq / g.det;
+    const double j00b = 2.0 * j00 * n0b + detb * j11, j01b = 2.0 * j01 * n0b - detb * j10;
+    const double j10b = 2.0 * j10 * n1b - detb * j01, j11b = 2.0 * j11 * n1b + detb * j00;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double dr = 0.25 * node_r(k) * (1.0 + s * node_s(k));
       const double ds = 0.25 * node_s(k) * (1.0 + r * node_r(k));
-      const S h0 = g.ji[0] * dr + g.ji[1] * ds, h1 = g.ji[2] * dr + g.ji[3] * ds;
-      exu = exu + h0 * ut[k][0]; eyu = eyu + h1 * ut[k][1]; gxu = gxu + h1 * ut[k][0] + h0 * ut[k][1];
-      exl = exl + h0 * lt[k][0]; eyl = eyl + h1 * lt[k][1]; gxl = gxl + h1 * lt[k][0] + h0 * lt[k][1];
-      kxu = kxu - h0 * ur[k][1]; kyu = kyu + h1 * ur[k][0]; kzu = kzu + h0 * ur[k][0] - h1 * ur[k][1];
-      kxl = kxl - h0 * lr[k][1]; kyl = kyl + h1 * lr[k][0]; kzl = kzl + h0 * lr[k][0] - h1 * lr[k][1];
+      xb[k] += dr * j00b + ds * j10b;
+      yb[k] += dr * j01b + ds * j11b;
     }
-    Mxx = Mxx + g.det * exl * exu; Mxy = Mxy + g.det * exl * eyu;
-    Myx = Myx + g.det * eyl * exu; Myy = Myy + g.det * eyl * eyu;
-    Mss = Mss + g.det * gxl * gxu;
-    Bsum = Bsum + g.det * (kxl * kxu + kyl * kyu);
-    Bnu = Bnu + g.det * (kxl * kyu + kyl * kxu);
-    Bss = Bss + g.det * kzl * kzu;
-    const S au = Au[0] * (1.0 + s) + Au[1] * (1.0 - s), al = Al[0] * (1.0 + s) + Al[1] * (1.0 - s);
-    const S bu = Bu[0] * (1.0 + r) + Bu[1] * (1.0 - r), bl = Bl[0] * (1.0 + r) + Bl[1] * (1.0 - r);
-    Sh = Sh + sh.m11 * g.prr * al * au + sh.m12 * g.prs * (al * bu + bl * au) + sh.m22 * g.pss * bl * bu;
-    S dq[8];
-    quad_diag_gp(sh, g, q, m, dq);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) diag[i] = diag[i] + dq[i];
   }
-  // drilling stiffness: first arg-min of |diag| (element.py:978; XLA's min VJP sends the
-  // cotangent to the arg-min, and to the first one unless two entries are bitwise equal)
-  int im = 0;
-  double best = fabs(val(diag[0]));
+  // ---- edge strains -> local vectors (dirCos rows 2, 0, 1) and edge geometry
+  {
+    const int n1[4] = {0, 3, 0, 1}, n2[4] = {1, 2, 3, 2};
+    const double gy[4] = {sh.gry[0], sh.gry[1], sh.gsy[0], sh.gsy[1]};
+    const double gx[4] = {sh.grx[0], sh.grx[1], sh.gsx[0], sh.gsx[1]};
 #pragma unroll
-  for (int i = 1; i < 8; ++i) {
-    const double a = fabs(val(diag[i]));
-    if (a < best) { best = a; im = i; }
-  }
-  S dsel = diag[0];
+    for (int i = 0; i < 4; ++i) {
+      const int p = n1[i], t = n2[i];
+      gyb[i] += Eub[i] * (UL[6 * p + 3] + UL[6 * t + 3]) + Elb[i] * (LL[6 * p + 3] + LL[6 * t + 3]);
+      gxb[i] += Eub[i] * (UL[6 * p + 4] + UL[6 * t + 4]) + Elb[i] * (LL[6 * p + 4] + LL[6 * t + 4]);
 #pragma unroll
-  for (int i = 1; i < 8; ++i) if (i == im) dsel = diag[i];
-  const S krz = sabs(dsel) * 1e-3;
-  S theta = zero;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) theta = theta + lr[k][2] * ur[k][2];
-
-  const S e_m = Mxx * m.cm11 + Mxy * m.cm12 + Myx * m.cm21 + Myy * m.cm22 + Mss * m.cm33;
-  const S e_b = (Bsum + Bnu * m.nu + Bss * m.hb) * m.D;
-  const S e_s = Sh * m.ks;
-  const S e_d = krz * theta;
-  if (parts) {
-    parts->Mxx = val(Mxx); parts->Mxy = val(Mxy); parts->Myx = val(Myx); parts->Myy = val(Myy);
-    parts->Mss = val(Mss); parts->Bsum = val(Bsum); parts->Bnu = val(Bnu); parts->Bss = val(Bss);
-    parts->Sh = val(Sh); parts->theta = val(theta);
-    parts->sign = (val(dsel) < 0.0) ? -1.0 : 1.0;
-    // split the selected diagonal value into its D- and ks-proportional parts: recompute
-    // with unit material constants (cheap, value-only)
-    QuadMat mb = m; mb.D = 1.0; mb.ks = 0.0;
-    QuadMat mh = m; mh.D = 1.0; mh.ks = 0.0; mh.hb = 0.0;
-    QuadMat msh = m; msh.D = 0.0; msh.ks = 1.0;
-    double db = 0, dh = 0, dsv = 0;
-    QuadFrame<double> fv; QuadShear<double> shv;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { fv.x[k] = val(f.x[k]); fv.y[k] = val(f.y[k]); }
-    quad_shear(fv, shv);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      QuadGp<double> gv; quad_gp(fv, q, gv);
-      double t1[8], t2[8], t3[8];
-      quad_diag_gp(shv, gv, q, mb, t1); quad_diag_gp(shv, gv, q, mh, t2); quad_diag_gp(shv, gv, q, msh, t3);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (i == im) { db += t1[i]; dh += t2[i]; dsv += t3[i]; }
+      for (int c = 0; c < 3; ++c) {
+        // w = e_z . ut  (row 2), theta_x = e_x . ur (row 0), theta_y = e_y . ur (row 1)
+        Rb[2][c] += 0.5 * (Eub[i] * (UG[6 * p + c] - UG[6 * t + c]) + Elb[i] * (LG[6 * p + c] - LG[6 * t + c]));
+        Rb[0][c] += gy[i] * (Eub[i] * (UG[6 * p + 3 + c] + UG[6 * t + 3 + c]) + Elb[i] * (LG[6 * p + 3 + c] + LG[6 * t + 3 + c]));
+        Rb[1][c] += gx[i] * (Eub[i] * (UG[6 * p + 3 + c] + UG[6 * t + 3 + c]) + Elb[i] * (LG[6 * p + 3 + c] + LG[6 * t + 3 + c]));
+      }
+      // gy = -(y_p - y_t)/4, gx = (x_p - x_t)/4
+      yb[p] -= 0.25 * gyb[i]; yb[t] += 0.25 * gyb[i];
+      xb[p] += 0.25 * gxb[i]; xb[t] -= 0.25 * gxb[i];
     }
-    // diag = D (kb_a + hb kb_b) + ks ks_c  with kb_a = dh, kb_b = (db - dh)/hb
-    parts->kb_a = dh; parts->kb_b = (m.hb != 0.0) ? (db - dh) / m.hb : 0.0; parts->ks_c = dsv;
   }
-  return e_m + e_b + e_s + e_d;
-}
-
-// thread = (quad, node a): writes the three coordinate partials of corner (e,a) and,
-// from a == 0, the five property partials.
-__global__ void __launch_bounds__(128)
-quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
-                    const double* __restrict__ prop, const double* __restrict__ u,
-                    const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = t >> 2, a = t & 3;
-  if (e >= n_quad) return;
-  D3 P[4][3];
-  double ue[24], le[24];
+  // ---- m12 = (|ry||sy| - rx sx)/(nr ns) -> local coordinates
+  {
+    const double* x = f.x; const double* y = f.y;
+    const double rx = ((x[0] + x[3]) - (x[1] + x[2])) * 0.5, ry = ((y[0] + y[3]) - (y[1] + y[2])) * 0.5;
+    const double sx = ((x[0] + x[1]) - (x[2] + x[3])) * 0.5, sy = ((y[0] + y[1]) - (y[2] + y[3])) * 0.5;
+    const double nr = sqrt(rx * rx + ry * ry), ns = sqrt(sx * sx + sy * sy);
+    const double sig = ((ry < 0.0) != (sy < 0.0)) ? -1.0 : 1.0;
+    const double Nb = m12b / (nr * ns), nrb = -m12b * sh.m12 / nr, nsb = -m12b * sh.m12 / ns;
+    const double rxb = -Nb * sx + nrb * rx / nr, ryb = Nb * sig * sy + nrb * ry / nr;
+    const double sxb = -Nb * rx + nsb * sx / ns, syb = Nb * sig * ry + nsb * sy / ns;
+    xb[0] += 0.5 * (rxb + sxb); xb[1] += 0.5 * (sxb - rxb); xb[3] += 0.5 * (rxb - sxb);
+    yb[0] += 0.5 * (ryb + syb); yb[1] += 0.5 * (syb - ryb); yb[3] += 0.5 * (ryb - syb);
+  }
+  // ---- drilling: theta_z = e_z . ur  (row 2), shared by the four lanes -> count it once (lane 0)
+  if (q == 0) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int nd = cnct[4 * e + k];
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        Rb[2][c] += krz * (LL[6 * k + 5] * UG[6 * k + 3 + c] + UL[6 * k + 5] * LG[6 * k + 3 + c]);
+  }
+  // ---- sum the four Gauss points
+  xb[0] = quad4_sum(xb[0]); xb[1] = quad4_sum(xb[1]); xb[3] = quad4_sum(xb[3]);
+  yb[0] = quad4_sum(yb[0]); yb[1] = quad4_sum(yb[1]); yb[3] = quad4_sum(yb[3]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Rb[i][c] = quad4_sum(Rb[i][c]);
+  // ---- local coordinates x_k = v3k . e_x, y_k = v3k . e_y  (k = 0, 1, 3; node 3 is the origin)
+  double v31[3], v32[3], v34[3], v42[3], vb31[3], vb32[3], vb34[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    v31[c] = P[0][c] - P[2][c]; v32[c] = P[1][c] - P[2][c];
+    v34[c] = P[3][c] - P[2][c]; v42[c] = P[1][c] - P[3][c];
+    Rb[0][c] += xb[0] * v31[c] + xb[1] * v32[c] + xb[3] * v34[c];
+    Rb[1][c] += yb[0] * v31[c] + yb[1] * v32[c] + yb[3] * v34[c];
+    vb31[c] = xb[0] * f.R[0][c] + yb[0] * f.R[1][c];
+    vb32[c] = xb[1] * f.R[0][c] + yb[1] * f.R[1][c];
+    vb34[c] = xb[3] * f.R[0][c] + yb[3] * f.R[1][c];
+  }
+  // ---- frame: e_x = v31/|v31|, z_r = v31 x v42, y_r = z_r x v31, e_y = y_r/|y_r|, e_z = z_r/|z_r|
+  double zr[3] = {v31[1] * v42[2] - v31[2] * v42[1], v31[2] * v42[0] - v31[0] * v42[2],
+                  v31[0] * v42[1] - v31[1] * v42[0]};
+  double yr[3] = {zr[1] * v31[2] - zr[2] * v31[1], zr[2] * v31[0] - zr[0] * v31[2],
+                  zr[0] * v31[1] - zr[1] * v31[0]};
+  const double inx = 1.0 / sqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
+  const double iny = 1.0 / sqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
+  const double inz = 1.0 / sqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
+  const double dx = f.R[0][0] * Rb[0][0] + f.R[0][1] * Rb[0][1] + f.R[0][2] * Rb[0][2];
+  const double dy = f.R[1][0] * Rb[1][0] + f.R[1][1] * Rb[1][1] + f.R[1][2] * Rb[1][2];
+  const double dz = f.R[2][0] * Rb[2][0] + f.R[2][1] * Rb[2][1] + f.R[2][2] * Rb[2][2];
+  double yrb[3], zrb[3], vb42[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    vb31[c] += (Rb[0][c] - f.R[0][c] * dx) * inx;
+    yrb[c] = (Rb[1][c] - f.R[1][c] * dy) * iny;
+    zrb[c] = (Rb[2][c] - f.R[2][c] * dz) * inz;
+  }
+  // y_r = z_r x v31:  z_r_bar += v31 x y_r_bar,  v31_bar += y_r_bar x z_r
+  zrb[0] += v31[1] * yrb[2] - v31[2] * yrb[1];
+  zrb[1] += v31[2] * yrb[0] - v31[0] * yrb[2];
+  zrb[2] += v31[0] * yrb[1] - v31[1] * yrb[0];
+  vb31[0] += yrb[1] * zr[2] - yrb[2] * zr[1];
+  vb31[1] += yrb[2] * zr[0] - yrb[0] * zr[2];
+  vb31[2] += yrb[0] * zr[1] - yrb[1] * zr[0];
+  // z_r = v31 x v42:  v31_bar += v42 x z_r_bar,  v42_bar = z_r_bar x v31
+  vb31[0] += v42[1] * zrb[2] - v42[2] * zrb[1];
+  vb31[1] += v42[2] * zrb[0] - v42[0] * zrb[2];
+  vb31[2] += v42[0] * zrb[1] - v42[1] * zrb[0];
+  vb42[0] = zrb[1] * v31[2] - zrb[2] * v31[1];
+  vb42[1] = zrb[2] * v31[0] - zrb[0] * v31[2];
+  vb42[2] = zrb[0] * v31[1] - zrb[1] * v31[0];
+  if (valid && corner) {
+    // node 0: v31; node 1: v32 + v42; node 2: -(v31 + v32 + v34); node 3: v34 - v42.  dL = -de.
+    double* cdst = corner + 3 * ((size_t)e * 4 + q);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      P[k][c] = mk<3>(crds[3 * (size_t)nd + c]);
-      if (k == a) P[k][c].d[c] = 1.0;
-    }
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-      ue[6 * k + d] = u[6 * (size_t)nd + d];
-      le[6 * k + d] = lam[6 * (size_t)nd + d];
+      const double p0 = vb31[c], p1 = vb32[c] + vb42[c], p3 = vb34[c] - vb42[c];
+      const double p2 = -(vb31[c] + vb32[c] + vb34[c]);
+      cdst[c] = -((q == 0) ? p0 : (q == 1) ? p1 : (q == 2) ? p2 : p3);
     }
   }
-  const double* pr = prop + 5 * (size_t)e;
-  QuadEnergyParts parts;
-  const D3 en = quad_bilinear<D3>(P, pr, ue, le, (a == 0 && d_prop) ? &parts : nullptr);
-  if (corner) {
-    double* c = corner + 3 * (size_t)t;
-    c[0] = -en.d[0]; c[1] = -en.d[1]; c[2] = -en.d[2];
-  }
-  if (a == 0 && d_prop) {
-    const double th = pr[0], E = pr[1], nu = pr[2], kx = pr[3], ky = pr[4];
-    QuadMat m; quad_mat(pr, m);
-    const double e_m = parts.Mxx * m.cm11 + parts.Mxy * m.cm12 + parts.Myx * m.cm21 + parts.Myy * m.cm22 +
-                       parts.Mss * m.cm33;
-    const double bcon = parts.Bsum + parts.Bnu * nu + parts.Bss * m.hb;
-    const double e_b = bcon * m.D, e_s = parts.Sh * m.ks;
-    const double dsel = m.D * (parts.kb_a + m.hb * parts.kb_b) + m.ks * parts.ks_c;   // signed diagonal
-    const double sg = parts.sign * 1e-3 * parts.theta;                                 // e_d = sg * dsel
-    const double one_m_nu2 = 1.0 - nu * nu;
-    // d/dt: membrane ~ t, bending ~ t^3, shear ~ t
-    const double de_dt = (e_m + 3.0 * e_b + e_s) / th +
-                         sg * (3.0 * m.D * (parts.kb_a + m.hb * parts.kb_b) + m.ks * parts.ks_c) / th;
-    const double de_dE = (e_m + e_b + e_s + sg * dsel) / E;
-    // d/dnu of the prefactors
-    const double pre = 1.0 / one_m_nu2, dpre = 2.0 * nu * pre * pre;
-    const double tE = th * E;
-    const double dem = tE * (dpre * (kx * (parts.Mxx + nu * parts.Mxy) + ky * (nu * parts.Myx + parts.Myy)) +
-                             pre * (kx * parts.Mxy + ky * parts.Myx)) -
-                       tE * parts.Mss / (2.0 * (1.0 + nu) * (1.0 + nu));
-    const double dD = m.D * 2.0 * nu / one_m_nu2;
-    const double deb = dD * bcon + m.D * (parts.Bnu - 0.5 * parts.Bss);
-    const double dks = -m.ks / (1.0 + nu);
-    const double des = dks * parts.Sh;
-    const double ddsel = dD * (parts.kb_a + m.hb * parts.kb_b) - 0.5 * m.D * parts.kb_b + dks * parts.ks_c;
-    const double de_dnu = dem + deb + des + sg * ddsel;
-    const double de_dkx = tE * pre * (parts.Mxx + nu * parts.Mxy);
-    const double de_dky = tE * pre * (nu * parts.Myx + parts.Myy);
-    double* o = d_prop + 5 * (size_t)e;
-    o[0] = -de_dt; o[1] = -de_dE; o[2] = -de_dnu; o[3] = -de_dkx; o[4] = -de_dky;
+  if (WANT_PROP) {
+    // value accumulators for the closed-form property derivatives (summed over Gauss points)
+    const double Mxx = quad4_sum(g.det * exl * exu), Mxy = quad4_sum(g.det * exl * eyu);
+    const double Myx = quad4_sum(g.det * eyl * exu), Myy = quad4_sum(g.det * eyl * eyu);
+    const double Mss = quad4_sum(g.det * gxl * gxu);
+    const double Bsum = quad4_sum(g.det * (kxl * kxu + kyl * kyu));
+    const double Bnu = quad4_sum(g.det * (kxl * kyu + kyl * kxu));
+    const double Bss = quad4_sum(g.det * kzl * kzu);
+    const double Sh = quad4_sum(sh.m11 * g.prr * Crr + sh.m12 * g.prs * Crs + sh.m22 * g.pss * Css);
+    const double kba = quad4_sum(kb_a), kbb = quad4_sum(kb_b), ksc = quad4_sum(ks_c);
+    if (valid && q == 0 && d_prop) {
+      const double th = pr[0], E = pr[1], nu = pr[2], kx = pr[3], ky = pr[4];
+      const double e_m = Mxx * m.cm11 + Mxy * m.cm12 + Myx * m.cm21 + Myy * m.cm22 + Mss * m.cm33;
+      const double bcon = Bsum + Bnu * nu + Bss * m.hb;
+      const double e_b = bcon * m.D, e_s = Sh * m.ks;
+      const double dsv = m.D * (kba + m.hb * kbb) + m.ks * ksc;   // the selected diagonal entry
+      const double sg = sgn * 1e-3 * theta;                       // e_d = sg * dsv
+      const double omn = 1.0 - nu * nu, pre = 1.0 / omn, dpre = 2.0 * nu * pre * pre, tE = th * E;
+      const double de_dt = (e_m + 3.0 * e_b + e_s) / th + sg * (3.0 * m.D * (kba + m.hb * kbb) + m.ks * ksc) / th;
+      const double de_dE = (e_m + e_b + e_s + sg * dsv) / E;
+      const double dem = tE * (dpre * (kx * (Mxx + nu * Mxy) + ky * (nu * Myx + Myy)) + pre * (kx * Mxy + ky * Myx)) -
+                         tE * Mss / (2.0 * (1.0 + nu) * (1.0 + nu));
+      const double dD = m.D * 2.0 * nu / omn, dks = -m.ks / (1.0 + nu);
+      const double deb = dD * bcon + m.D * (Bnu - 0.5 * Bss);
+      const double ddsel = dD * (kba + m.hb * kbb) - 0.5 * m.D * kbb + dks * ksc;
+      double* o = d_prop + 5 * (size_t)e;
+      o[0] = -de_dt; o[1] = -de_dE; o[2] = -(dem + deb + dks * Sh + sg * ddsel);
+      o[3] = -(tE * pre * (Mxx + nu * Mxy)); o[4] = -(tE * pre * (nu * Myx + Myy));
+    }
   }
 }
 

@@ -582,8 +582,13 @@ int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const
   cudaStream_t st = (cudaStream_t)stream;
   const Symbolic& S = h->sym;
   if (S.n_quad > 0) {
-    quad_adjoint_kernel<<<cdiv(4LL * S.n_quad, 128), 128, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
-                                                                  d_crds ? h->corner_q : nullptr, d_prop_q);
+    const int blocks = cdiv(S.n_quad, ADJ_QUADS);
+    if (d_prop_q)
+      quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
+                                                                 d_crds ? h->corner_q : nullptr, d_prop_q);
+    else
+      quad_adjoint_kernel<false><<<blocks, 4 * ADJ_QUADS, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
+                                                                  d_crds ? h->corner_q : nullptr, nullptr);
     CKL("quad_adjoint_kernel");
   }
   if (S.n_beam > 0) {
