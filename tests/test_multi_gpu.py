@@ -1,0 +1,27 @@
+"""Multi-GPU parity (needs >= 2 GPUs; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`):
+the partitioned forward + backward equals the single-GPU result."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from jaxsso_b200 import _native as nat
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_partitioned_equals_single(world):
+    if nat.lib().jsso_device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
+           '--master-addr', '127.0.0.1', '--master-port', str(29510 + world),
+           os.path.join(ROOT, 'scripts', 'dist_check.py'), '48']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith('DIST_CHECK')]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads(line[0].split(' ', 1)[1])
+    assert res['u_err'] < 1e-8 and res['grad_err'] < 1e-7 and res['dprop_err'] < 1e-7
