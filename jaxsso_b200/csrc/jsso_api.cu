@@ -352,9 +352,10 @@ int jsso_halo_exchange(jsso_handle* h, double* vec_d, void* stream) {
   return halo_exchange_w(h, vec_d, 6, (cudaStream_t)stream);
 }
 
-static int allreduce_scalar(jsso_handle* h, double* p, int count, cudaStream_t st) {
+// global = sum over ranks of this rank's partial (out of place, so repeating it is harmless)
+static int allreduce_scalar(jsso_handle* h, const double* local, double* global, cudaStream_t st) {
   if (h->n_rank <= 1) return JSSO_OK;
-  CKN(ncclAllReduce(p, p, count, ncclDouble, ncclSum, h->comm, st));
+  CKN(ncclAllReduce(local, global, 1, ncclDouble, ncclSum, h->comm, st));
   return JSSO_OK;
 }
 
@@ -364,7 +365,7 @@ static int spmv_plain(jsso_handle* h, const double* x, double* y, cudaStream_t s
   if (n_row == 0) return JSSO_OK;
   const int blocks = std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32));
   bsr_spmv_kernel<0><<<blocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, x, y, h->sc, 0,
-                                                   h->partials, h->counters);
+                                                   h->partials, h->counters, 1);
   CKL("bsr_spmv_kernel<0>");
   return JSSO_OK;
 }
@@ -422,19 +423,20 @@ static void default_opts(const jsso_solve_opts* in, jsso_solve_opts& o) {
 static int cg_iteration(jsso_handle* h, int cur, cudaStream_t st) {
   const int n_row = h->sym.n_row;
   const long long n = 6LL * n_row;
+  const int single = h->n_rank <= 1;
   int rc = halo_exchange_w(h, h->vp, 6, st);
   if (rc) return rc;
   const int sblocks = std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
   bsr_spmv_kernel<1><<<sblocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, h->vp, h->vq, h->sc,
-                                                   cur, h->partials, h->counters);
+                                                   cur, h->partials, h->counters, single);
   CKL("bsr_spmv_kernel<1>");
-  if ((rc = allreduce_scalar(h, &h->sc->pq, 1, st))) return rc;
+  if ((rc = allreduce_scalar(h, &h->sc->loc[0], &h->sc->pq, st))) return rc;
   const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
   cg_update_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vp, h->vq, h->vx, h->vr, h->sc, h->partials,
-                                                  h->counters + 1, h->n_rank <= 1);
+                                                  h->counters + 1, single);
   CKL("cg_update_kernel");
-  if (h->n_rank > 1) {
-    if ((rc = allreduce_scalar(h, &h->sc->rr[cur ^ 1], 1, st))) return rc;
+  if (!single) {
+    if ((rc = allreduce_scalar(h, &h->sc->loc[1], &h->sc->rr[cur ^ 1], st))) return rc;
     cg_latch_kernel<<<1, 1, 0, st>>>(cur, h->sc);
     CKL("cg_latch_kernel");
   }
@@ -463,19 +465,21 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
     } else {
       CK(cudaMemsetAsync(h->vx, 0, 6 * (size_t)h->sym.n_node * sizeof(double), st));
     }
+    const int single = h->n_rank <= 1;
     if (first) {
       cg_init_kernel<1><<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, q, h->vr, h->vp, h->sc, h->partials,
-                                                       h->counters + 2, o.rtol);
+                                                       h->counters + 2, o.rtol, single);
       CKL("cg_init_kernel<1>");
-      if ((rc = allreduce_scalar(h, &h->sc->bb, 1, st))) return rc;
+      if ((rc = allreduce_scalar(h, &h->sc->loc[2], &h->sc->bb, st))) return rc;
     } else {
       cg_init_kernel<0><<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, q, h->vr, h->vp, h->sc, h->partials,
-                                                       h->counters + 2, o.rtol);
+                                                       h->counters + 2, o.rtol, single);
       CKL("cg_init_kernel<0>");
     }
-    if (h->n_rank > 1) {
-      // rr[0] and rr[1] hold the same local value; reduce both
-      if ((rc = allreduce_scalar(h, &h->sc->rr[0], 2, st))) return rc;
+    if (!single) {
+      if ((rc = allreduce_scalar(h, &h->sc->loc[1], &h->sc->rr[0], st))) return rc;
+      cg_copy_rr_kernel<<<1, 1, 0, st>>>(h->sc);
+      CKL("cg_copy_rr_kernel");
     }
     first = false;
     int cur = 0, it_local = 0;
@@ -504,9 +508,10 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
     // true residual
     if ((rc = halo_exchange_w(h, h->vx, 6, st))) return rc;
     if ((rc = spmv_plain(h, h->vx, h->vq, st))) return rc;
-    residual_norm_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, h->vq, h->sc, h->partials, h->counters + 2);
+    residual_norm_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, h->vb, h->vq, h->sc, h->partials, h->counters + 2,
+                                                        h->n_rank <= 1);
     CKL("residual_norm_kernel");
-    if ((rc = allreduce_scalar(h, &h->sc->aux, 1, st))) return rc;
+    if ((rc = allreduce_scalar(h, &h->sc->loc[3], &h->sc->aux, st))) return rc;
     CK(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     relres_true = (h->sc_host->bb > 0) ? std::sqrt(h->sc_host->aux / h->sc_host->bb) : 0.0;

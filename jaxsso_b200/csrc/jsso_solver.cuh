@@ -30,6 +30,10 @@ struct CgScalars {
   double bb;        // |b^|^2
   double tol2;      // rtol^2
   double aux;       // scratch dot (true residual)
+  // this rank's partial sums [p.Ap, r.r, |b|^2, aux]: on several GPUs the kernels write here and an
+  // out-of-place ncclAllReduce(loc -> target) fills the globals, which keeps the reduction
+  // idempotent when later launches of a batch are no-ops after convergence
+  double loc[4];
   int iter;
   int pad;
 };
@@ -88,7 +92,7 @@ template <int MODE>
 __global__ void __launch_bounds__(RED_BLOCK)
 bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                CgScalars* sc, int cur, double* partials, unsigned* counter) {
+                CgScalars* sc, int cur, double* partials, unsigned* counter, int single_gpu) {
   if (MODE == 1 && cg_stop(sc, cur)) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -135,7 +139,10 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   }
   if (MODE == 1) {
     double total;
-    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) sc->pq = total;
+    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) {
+      sc->loc[0] = total;
+      if (single_gpu) sc->pq = total;
+    }
   }
 }
 
@@ -248,7 +255,8 @@ block_apply_kernel(int n_row, const double* __restrict__ W, const double* __rest
 template <int SETBB>
 __global__ void __launch_bounds__(RED_BLOCK)
 cg_init_kernel(long long n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
-               double* __restrict__ p, CgScalars* sc, double* partials, unsigned* counter, double rtol) {
+               double* __restrict__ p, CgScalars* sc, double* partials, unsigned* counter, double rtol,
+               int single_gpu) {
   double acc = 0.0, accb = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double bi = b[i];
@@ -258,12 +266,16 @@ cg_init_kernel(long long n, const double* __restrict__ b, const double* __restri
   }
   double total;
   if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
-    sc->rr[0] = total; sc->rr[1] = total; sc->iter = 0; sc->tol2 = rtol * rtol;
+    sc->loc[1] = total; sc->iter = 0; sc->tol2 = rtol * rtol;
+    if (single_gpu) { sc->rr[0] = total; sc->rr[1] = total; }
   }
   if (SETBB) {
     __syncthreads();
     double tb;
-    if (grid_sum(accb, partials + RED_MAX_BLOCKS, counter + 1, tb) && threadIdx.x == 0) sc->bb = tb;
+    if (grid_sum(accb, partials + RED_MAX_BLOCKS, counter + 1, tb) && threadIdx.x == 0) {
+      sc->loc[2] = tb;
+      if (single_gpu) sc->bb = tb;
+    }
   }
 }
 
@@ -286,11 +298,14 @@ cg_update_kernel(long long n, int cur, const double* __restrict__ p, const doubl
   if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
     // non-positive curvature => not SPD: poison the state so that everything stops
     const double nrr = (pq > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
-    sc->rr[cur ^ 1] = nrr;
+    sc->loc[1] = nrr;
     sc->iter += 1;
-    // On stop, latch BOTH parity slots: later launches of the batch test rr[cur] with
-    // alternating cur.  Safe here: every block read rr[cur] before contributing its partial.
-    if (single_gpu && !(nrr > sc->tol2 * sc->bb)) sc->rr[cur] = nrr;
+    if (single_gpu) {
+      sc->rr[cur ^ 1] = nrr;
+      // On stop, latch BOTH parity slots: later launches of the batch test rr[cur] with
+      // alternating cur.  Safe here: every block read rr[cur] before contributing its partial.
+      if (!(nrr > sc->tol2 * sc->bb)) sc->rr[cur] = nrr;
+    }
   }
 }
 
@@ -298,6 +313,7 @@ cg_update_kernel(long long n, int cur, const double* __restrict__ p, const doubl
 __global__ void cg_latch_kernel(int cur, CgScalars* sc) {
   if (!(sc->rr[cur ^ 1] > sc->tol2 * sc->bb)) sc->rr[cur] = sc->rr[cur ^ 1];
 }
+__global__ void cg_copy_rr_kernel(CgScalars* sc) { sc->rr[1] = sc->rr[0]; }
 
 // p = r + beta p
 __global__ void __launch_bounds__(RED_BLOCK)
@@ -312,14 +328,17 @@ cg_direction_kernel(long long n, int cur, const double* __restrict__ r, double* 
 // aux = |b - q|^2 (true residual check)
 __global__ void __launch_bounds__(RED_BLOCK)
 residual_norm_kernel(long long n, const double* __restrict__ b, const double* __restrict__ q, CgScalars* sc,
-                     double* partials, unsigned* counter) {
+                     double* partials, unsigned* counter, int single_gpu) {
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double d = b[i] - q[i];
     acc += d * d;
   }
   double total;
-  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) sc->aux = total;
+  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
+    sc->loc[3] = total;
+    if (single_gpu) sc->aux = total;
+  }
 }
 
 // out = s * in  (owned part)
