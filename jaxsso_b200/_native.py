@@ -178,6 +178,30 @@ class DeviceArray:
             pass
 
 
+class PinnedArray(np.ndarray):
+    """NumPy array backed by page-locked host memory (cudaHostAlloc) so that the library's
+    host-buffer entry points can DMA straight from / into it."""
+    _keep = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    ptr = lib().jsso_host_alloc_pinned(max(nbytes, 8))
+    if not ptr:
+        raise MemoryError('cudaHostAlloc failed')
+    buf = (C.c_char * max(nbytes, 8)).from_address(ptr)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape).view(PinnedArray)
+    a._keep = (buf, ptr)   # freed when the process exits; benchmark buffers live that long
+    return a
+
+
+def pinned_copy(a):
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 def _dp(a):
     """Device pointer of a DeviceArray / raw int / None."""
     if a is None:

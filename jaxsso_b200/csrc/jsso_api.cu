@@ -722,28 +722,35 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   const size_t nc = 3 * (size_t)S.n_node, nq = 5 * (size_t)S.n_quad, nb = 6 * (size_t)S.n_beam,
                nd = 6 * (size_t)S.n_node;
   cudaStream_t st = 0;
-  // the caller's buffers may be pageable: stage through pinned memory so the copies are true DMA
-  std::memcpy(h->h_crds, crds_h, nc * sizeof(double));
-  if (nq) std::memcpy(h->h_pq, pq_h, nq * sizeof(double));
-  if (nb) std::memcpy(h->h_pb, pb_h, nb * sizeof(double));
-  std::memcpy(h->h_f, u_h, nd * sizeof(double));
-  std::memcpy(h->h_u, lam_h, nd * sizeof(double));
-  CK(cudaMemcpyAsync(h->s_crds, h->h_crds, nc * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (nq) CK(cudaMemcpyAsync(h->s_pq, h->h_pq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (nb) CK(cudaMemcpyAsync(h->s_pb, h->h_pb, nb * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->s_f, h->h_f, nd * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->s_u, h->h_u, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  // DMA straight from / to the caller's buffers when they are pinned (cudaHostAlloc / registered);
+  // pageable buffers are staged through the handle's pinned scratch so the copies stay asynchronous
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  auto h2d = [&](double* dst, const double* src, double* stage, size_t n) -> cudaError_t {
+    if (!n) return cudaSuccess;
+    if (!pinned(src)) { std::memcpy(stage, src, n * sizeof(double)); src = stage; }
+    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+  };
+  CK(h2d(h->s_crds, crds_h, h->h_crds, nc));
+  CK(h2d(h->s_pq, pq_h, h->h_pq, nq));
+  CK(h2d(h->s_pb, pb_h, h->h_pb, nb));
+  CK(h2d(h->s_f, u_h, h->h_f, nd));
+  CK(h2d(h->s_u, lam_h, h->h_u, nd));
   if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
   if ((rc = jsso_adjoint(h, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, dc_h ? h->s_dc : nullptr,
                          (dpq_h && nq) ? h->s_dpq : nullptr, (dpb_h && nb) ? h->s_dpb : nullptr, st)))
     return rc;
-  if (dc_h) CK(cudaMemcpyAsync(h->h_dc, h->s_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (dpq_h && nq) CK(cudaMemcpyAsync(h->h_dpq, h->s_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (dpb_h && nb) CK(cudaMemcpyAsync(h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  const bool p_dc = dc_h && pinned(dc_h), p_dq = dpq_h && pinned(dpq_h), p_db = dpb_h && pinned(dpb_h);
+  if (dc_h) CK(cudaMemcpyAsync(p_dc ? dc_h : h->h_dc, h->s_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpq_h && nq) CK(cudaMemcpyAsync(p_dq ? dpq_h : h->h_dpq, h->s_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dpb_h && nb) CK(cudaMemcpyAsync(p_db ? dpb_h : h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (dc_h) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
-  if (dpq_h && nq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
-  if (dpb_h && nb) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  if (dc_h && !p_dc) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
+  if (dpq_h && nq && !p_dq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+  if (dpb_h && nb && !p_db) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
   return JSSO_OK;
 }
 
