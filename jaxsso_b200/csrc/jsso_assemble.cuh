@@ -32,7 +32,7 @@ constexpr int Q_XY = 62;    // x0,y0,x1,y1,x3,y3 local coordinates (node 3 is th
 constexpr int FLAG_BADJAC = 1, FLAG_DEGBEAM = 2, FLAG_UNSYM = 4;
 
 // Stage the geometry of `n_el` quads (ids from `els`, or first_el + i when els is null) into
-// `sm`.  Called by all threads of the CTA.  Phase A: one thread per quad (frame, projected
+// `sm`.  Called by all threads of the CTA.  Phase 0: coordinate gather.  Phase A: one thread per quad (frame, projected
 // coordinates, gp-independent shear data, material).  Phase B: one thread per (quad, Gauss point)
 // (inverse Jacobian, detJ, shear scale factors); the four Gauss points of a quad sit in adjacent
 // lanes, so the drilling-stiffness minimum over the summed diagonal (element.py:978) is reduced
@@ -41,15 +41,23 @@ __device__ inline void stage_quad_geometry(double* sm, int n_el, const int32_t* 
                                            const double* __restrict__ crds,
                                            const int32_t* __restrict__ cnct,
                                            const double* __restrict__ prop, int* flags) {
+  // phase 0: one thread per (quad, node) gathers the coordinates (all global-load chains in
+  // parallel); they are parked in the record's Gauss-point area, which phase B overwrites later
+  for (int t = threadIdx.x; t < 4 * n_el; t += blockDim.x) {
+    const int le = t >> 2, k = t & 3;
+    const int e = els ? els[le] : first_el + le;
+    const int nd = cnct[4 * e + k];
+    double* s = sm + le * QS + Q_GP + 3 * k;
+    s[0] = crds[3 * (size_t)nd]; s[1] = crds[3 * (size_t)nd + 1]; s[2] = crds[3 * (size_t)nd + 2];
+  }
+  __syncthreads();
   for (int le = threadIdx.x; le < n_el; le += blockDim.x) {
     const int e = els ? els[le] : first_el + le;
     double P[4][3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int nd = cnct[4 * e + k];
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
-    }
+      for (int c = 0; c < 3; ++c) P[k][c] = sm[le * QS + Q_GP + 3 * k + c];
     QuadFrame<double> f;
     quad_frame(P, f);
     QuadShear<double> sh;
@@ -308,7 +316,9 @@ __device__ inline double bc_entry(double v, unsigned rmask, unsigned cmask, int 
   return v;
 }
 
-constexpr int FUSED_SMEM_DOUBLES = kChunkQuads * QS;
+constexpr int OUT_LD = 37;  // padded block stride of the output transposition buffer (odd => few conflicts)
+constexpr int FUSED_SMEM_DOUBLES =
+    (kChunkQuads * QS > kChunkBlocks * OUT_LD) ? kChunkQuads * QS : kChunkBlocks * OUT_LD;
 
 struct AsmArgs {
   const double* crds; const int32_t* cnct_q; const double* prop_q;
@@ -321,30 +331,32 @@ struct AsmArgs {
 
 // One CTA per chunk of consecutive block slots.  After the chunk's quads are staged in shared
 // memory, ONE THREAD OWNS ONE 6x6 BLOCK: it loops over the block's contributors (element, a, b)
-// in list order, accumulates in registers and writes its 288 contiguous bytes once -- no atomics,
-// no staging buffer, a fixed summation order.  Blocks are dealt to threads by decreasing
+// in list order and accumulates in registers -- no atomics, a fixed summation order; the chunk's
+// blocks are then transposed through shared memory and written with coalesced stores.  Blocks are dealt to threads by decreasing
 // contributor count (blk_perm), so the lanes of a warp loop the same number of times.
-__global__ void __launch_bounds__(kChunkBlocks, 2)
+__global__ void __launch_bounds__(kChunkBlocks, 4)
 assemble_fused_kernel(AsmArgs A) {
   extern __shared__ double sm[];
   const int c = blockIdx.x;
   const int blk0 = A.chunk_blk[c], blk1 = A.chunk_blk[c + 1];
   const int el0 = A.chunk_el_ptr[c], n_el = A.chunk_el_ptr[c + 1] - el0;
+  // this thread's block and contributor range: loaded before the staging phases so that the
+  // dependent global-load chain (perm -> item ptr) is hidden behind them
+  const bool has_blk = (int)threadIdx.x < blk1 - blk0;
+  const int blk = has_blk ? A.blk_perm[blk0 + threadIdx.x] : blk0;
+  const int i0 = A.blk_item_ptr[blk], i1 = has_blk ? A.blk_item_ptr[blk + 1] : i0;
   stage_quad_geometry(sm, n_el, A.chunk_els + el0, 0, A.crds, A.cnct_q, A.prop_q, A.flags);
   __syncthreads();
-  if ((int)threadIdx.x >= blk1 - blk0) return;
-  const int blk = A.blk_perm[blk0 + threadIdx.x];
   double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-  const int i1 = A.blk_item_ptr[blk + 1];
-  for (int it = A.blk_item_ptr[blk]; it < i1; ++it) {
+  for (int it = i0; it < i1; ++it) {
     const int code = A.item_code[it];
     const int el = code >> 4, a = (code >> 2) & 3, b = code & 3;
     if (el < A.n_quad) quad_pair_block(sm + A.item_lel[it] * QS, a, b, acc);
     else beam_pair_block(A.crds, A.cnct_b, A.prop_b, el - A.n_quad, a, b, acc, A.flags);
   }
-  if (A.apply_bc) {
+  if (has_blk && A.apply_bc) {
     const int r = A.blk_row[blk], cc = A.colidx[blk];
     const unsigned rm = A.node_mask[r], cm = A.node_mask[cc];
     if (rm | cm) {
@@ -354,9 +366,23 @@ assemble_fused_kernel(AsmArgs A) {
         for (int i = 0; i < 6; ++i) acc[j * 6 + i] = bc_entry(acc[j * 6 + i], rm, cm, i, j, r == cc);
     }
   }
-  double2* dst = (double2*)(A.vals + (size_t)blk * 36);
+  // Transpose through shared memory (the geometry records are dead now) so that the chunk's
+  // contiguous range of vals is written with fully coalesced 16-byte stores: thread-private
+  // 288-byte segments would touch 32 different sectors per store instruction.
+  __syncthreads();
+  if (has_blk) {
+    double* dstb = sm + (blk - blk0) * OUT_LD;
 #pragma unroll
-  for (int k = 0; k < 18; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+    for (int k = 0; k < 36; ++k) dstb[k] = acc[k];
+  }
+  __syncthreads();
+  const int n_pair = (blk1 - blk0) * 18;   // 16-byte pairs in this chunk's slice of vals
+  double2* out2 = (double2*)(A.vals + (size_t)blk0 * 36);
+  for (int o = threadIdx.x; o < n_pair; o += blockDim.x) {
+    const int bl = o / 18, k2 = o - bl * 18;
+    const double* src = sm + bl * OUT_LD + 2 * k2;
+    out2[o] = make_double2(src[0], src[1]);
+  }
 }
 
 // Stand-alone numeric assembly: one thread per stored entry, contributors summed in

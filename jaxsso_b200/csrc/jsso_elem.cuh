@@ -89,6 +89,15 @@ template <int N> __host__ __device__ inline Dual<N> ssqrt(const Dual<N>& a) {
   for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * h;
   return r;
 }
+// 1/sqrt(a): one MUFU + Newton step for doubles instead of a sqrt followed by divisions
+__host__ __device__ inline double srsqrt(double a) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(a);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+template <int N> __host__ __device__ inline Dual<N> srsqrt(const Dual<N>& a) { return 1.0 / ssqrt(a); }
 __host__ __device__ inline double sabs(double a) { return fabs(a); }
 template <int N> __host__ __device__ inline Dual<N> sabs(const Dual<N>& a) { return a.v < 0.0 ? -a : a; }
 __host__ __device__ inline double val(double a) { return a; }
@@ -128,14 +137,14 @@ __host__ __device__ inline void quad_frame(const S P[4][3], QuadFrame<S>& f) {
              v31[0] * v42[1] - v31[1] * v42[0]};
   S yr[3] = {zr[1] * v31[2] - zr[2] * v31[1], zr[2] * v31[0] - zr[0] * v31[2],
              zr[0] * v31[1] - zr[1] * v31[0]};
-  const S nx = ssqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
-  const S ny = ssqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
-  const S nz = ssqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
+  const S inx = srsqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
+  const S iny = srsqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
+  const S inz = srsqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    f.R[0][c] = v31[c] / nx;
-    f.R[1][c] = yr[c] / ny;
-    f.R[2][c] = zr[c] / nz;
+    f.R[0][c] = v31[c] * inx;
+    f.R[1][c] = yr[c] * iny;
+    f.R[2][c] = zr[c] * inz;
   }
   f.x[0] = v31[0] * f.R[0][0] + v31[1] * f.R[0][1] + v31[2] * f.R[0][2];
   f.y[0] = v31[0] * f.R[1][0] + v31[1] * f.R[1][1] + v31[2] * f.R[1][2];
@@ -165,10 +174,10 @@ __host__ __device__ inline void quad_shear(const QuadFrame<S>& f, QuadShear<S>& 
   // r-axis ~ (x1+x4-x2-x3, y1+y4-y2-y3)/2, s-axis ~ (x1+x2-x3-x4, ...)/2, normalised
   S rx = ((x[0] + x[3]) - (x[1] + x[2])) * 0.5, ry = ((y[0] + y[3]) - (y[1] + y[2])) * 0.5;
   S sx = ((x[0] + x[1]) - (x[2] + x[3])) * 0.5, sy = ((y[0] + y[1]) - (y[2] + y[3])) * 0.5;
-  const S nr = ssqrt(rx * rx + ry * ry), ns = ssqrt(sx * sx + sy * sy);
-  const S ca = rx / nr, cb = sx / ns;
-  const S sa = -sabs(ry / nr);   // element.py:795: sin_alpha = -|r^ x e_x|
-  const S sb = sabs(sy / ns);    // element.py:796
+  const S inr = srsqrt(rx * rx + ry * ry), ins = srsqrt(sx * sx + sy * sy);
+  const S ca = rx * inr, cb = sx * ins;
+  const S sa = -sabs(ry * inr);   // element.py:795: sin_alpha = -|r^ x e_x|
+  const S sb = sabs(sy * ins);    // element.py:796
   q.m11 = sb * sb + cb * cb;
   q.m12 = -(sa * sb + ca * cb);
   q.m22 = sa * sa + ca * ca;
@@ -203,7 +212,7 @@ __host__ __device__ inline void quad_gp(const QuadFrame<S>& f, int q, QuadGp<S>&
   const S q4 = id * 0.25;
   g.prr = n1 * q4;                      // detJ gr^2, gr = sqrt(16 n1)/(8 detJ)
   g.pss = n0 * q4;
-  g.prs = ssqrt(n1) * ssqrt(n0) * q4;
+  g.prs = ssqrt(n1 * n0) * q4;
 }
 
 // material constants of one quad (element.py:820-875); cm* already include t
@@ -215,16 +224,18 @@ struct QuadMat {
 
 __host__ __device__ inline void quad_mat(const double* prop, QuadMat& m) {
   const double t = prop[0], E = prop[1], nu = prop[2], kx = prop[3], ky = prop[4];
-  const double pre = 1.0 / (1.0 - nu * nu);
-  m.cm11 = t * (pre * (E * kx));
-  m.cm12 = t * (pre * (nu * (E * kx)));
-  m.cm21 = t * (pre * (nu * (E * ky)));
-  m.cm22 = t * (pre * (E * ky));
-  m.cm33 = t * (E / (2.0 * (1.0 + nu)));   // pre * (1-nu^2) * G
-  m.D = E * t * t * t / (12.0 * (1.0 - nu * nu));
+  const double ip = 1.0 / (1.0 + nu);          // two divisions in total
+  const double pre = ip / (1.0 - nu);          // 1 / (1 - nu^2)
+  const double tE = t * E;
+  m.cm11 = pre * (tE * kx);
+  m.cm12 = pre * (nu * (tE * kx));
+  m.cm21 = pre * (nu * (tE * ky));
+  m.cm22 = pre * (tE * ky);
+  m.cm33 = 0.5 * tE * ip;                      // pre * (1-nu^2) * G, G = E / (2 (1+nu))
+  m.D = tE * t * t * pre * (1.0 / 12.0);
   m.nu = nu;
   m.hb = 0.5 * (1.0 - nu);
-  m.ks = E * t * (5.0 / 6.0) / (2.0 * (1.0 + nu));
+  m.ks = tE * (5.0 / 12.0) * ip;
 }
 
 // Contribution of Gauss point q to the eight diagonal entries

@@ -15,9 +15,9 @@
 
 namespace jsso {
 
-constexpr int kChunkBlocks = 256; // block slots per assembly chunk (= CTA size: one thread per block)
-constexpr int kChunkItems = 448;  // pair items per assembly chunk
-constexpr int kChunkQuads = 64;   // distinct quads whose geometry a chunk stages in shared memory
+constexpr int kChunkBlocks = 128; // block slots per assembly chunk (= CTA size: one thread per block)
+constexpr int kChunkItems = 224;  // pair items per assembly chunk
+constexpr int kChunkQuads = 36;   // distinct quads whose geometry a chunk stages in shared memory
 
 struct Symbolic {
   int n_node = 0, n_row = 0, n_quad = 0, n_beam = 0;
