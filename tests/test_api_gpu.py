@@ -1,0 +1,132 @@
+"""The host-side mirror of the reference API (jaxsso_b200.Model / SSO_model) on the GPU path,
+written the way the reference's own notebooks use it (Test/shells_ad_validation.ipynb,
+Test/beamcols_ad_validation.ipynb, Examples/shells_topo_shape.ipynb)."""
+import numpy as np
+import pytest
+
+import jaxsso_b200 as jb
+from jaxsso_b200 import meshes
+from oracle import jaxsso_oracle as orc
+from tests.conftest import to_oracle_mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(md):
+    model = jb.Model()
+    for i in range(md.n_node):
+        model.add_node(i, *md.crds[i])
+    act = np.zeros((md.n_node, 6), int)
+    act.reshape(-1)[md.known] = 1
+    for i in np.flatnonzero(act.any(1)):
+        model.add_support(int(i), act[i].tolist())
+    for i in np.flatnonzero(np.abs(md.loads.reshape(-1, 6)).sum(1)):
+        model.add_nodal_load(int(i), md.loads.reshape(-1, 6)[i].tolist())
+    for e in range(md.n_quad):
+        model.add_quad(e, *[int(x) for x in md.cnct_quads[e]], *md.prop_quads[e])
+    for e in range(md.n_beam):
+        model.add_beamcol(e, *[int(x) for x in md.cnct_beams[e]], *md.prop_beams[e])
+    return model
+
+
+def test_model_solve_shell_arch(golden):
+    md = meshes.barrel_arch()
+    model = build_model(md)
+    model.model_ready()
+    model.solve(which_solver='sparse', enforce_scipy_sparse=True)   # reference call signature
+    uz = model.u[md.design_nodes * 6 + 2]
+    assert abs(uz.min() - golden['shell_arch_min_uz']['dense']) / 25.0 < 1e-8
+    assert abs(model.strain_energy() - golden['shell_arch_strain_energy']['value']) / 1.2e6 < 1e-8
+
+
+def test_sso_shape_gradient_shell_arch(golden):
+    md = meshes.barrel_arch()
+    model = build_model(md)
+    sso = jb.SSO_model(model)
+    for node in md.design_nodes:
+        sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+    sso.initialize_parameters_values()
+    sso.set_objective(objective='strain energy', func=None, func_args=None)
+    C, sens = sso.value_grad_params(which_solver='sparse', enforce_scipy_sparse=True)
+    g = golden['shell_arch_grad_node201']
+    k = int(np.where(md.design_nodes == g['design_i'])[0][0])
+    assert abs(sens[k] - g['dense']) / abs(g['dense']) < 1e-6
+    assert abs(C - golden['shell_arch_strain_energy']['value']) / C < 1e-8
+    assert sens.shape == (md.design_nodes.shape[0],)
+    assert abs(sso.params_to_objective() - C) / C < 1e-10
+    assert np.allclose(sso.grad_params(), sens, rtol=1e-9)
+
+
+def test_sso_beam_gradient(golden):
+    md = meshes.beam_arch()
+    model = build_model(md)
+    sso = jb.SSO_model(model)
+    for node in md.design_nodes:
+        sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+    sso.initialize_parameters_values()
+    sso.set_objective('strain energy')
+    sso.rtol = 1e-12
+    C, sens = sso.value_grad_params()
+    g = golden['beam_arch_grad_node49']
+    k = int(np.where(md.design_nodes == g['design_i'])[0][0])
+    assert abs(sens[k] - g['dense']) / abs(g['dense']) < 1e-5
+    assert abs(C - golden['beam_arch']['dense_strain_energy']) / C < 5e-8
+
+
+def test_sso_mixed_parameters_and_update():
+    """Node z + quad E (topology) + quad t (size) parameters in one vector, in add order
+    (SSO_model.py:125-173), and update_*parameter between evaluations."""
+    md = meshes.plate(12)
+    model = build_model(md)
+    sso = jb.SSO_model(model)
+    for node in md.design_nodes[::3]:
+        sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+    for e in range(0, md.n_quad, 2):
+        sso.add_eleparameter(jb.ElementParameter(e, ele_type=1, prop_type=1))
+    for e in range(1, md.n_quad, 2):
+        sso.add_eleparameter(jb.ElementParameter(e, ele_type=1, prop_type=0))
+    sso.initialize_parameters_values()
+    sso.set_objective('strain energy')
+    sso.rtol = 1e-12
+    z = sso.nodeparameters_values + 0.03
+    ep = sso.eleparameters_values * 1.1
+    sso.update_nodeparameter(z)
+    sso.update_eleparameter(ep)
+    C, sens = sso.value_grad_params()
+    crds = md.crds.copy()
+    crds[md.design_nodes[::3], 2] = z
+    pq = md.prop_quads.copy()
+    pq[0::2, 1] *= 1.1
+    pq[1::2, 0] *= 1.1
+    m = to_oracle_mesh(md)
+    rv, ru, rl, rdc, rdq, _ = orc.value_and_grad(m, crds=crds, prop_quads=pq)
+    ref = np.concatenate([rdc[md.design_nodes[::3], 2], rdq[0::2, 1], rdq[1::2, 0]])
+    assert abs(C - rv) / rv < 1e-8
+    nn = md.design_nodes[::3].shape[0]
+    assert np.abs(sens[:nn] - ref[:nn]).max() / np.abs(ref[:nn]).max() < 1e-6
+    assert np.abs(sens[nn:] - ref[nn:]).max() / np.abs(ref[nn:]).max() < 1e-6
+
+
+def test_user_objective():
+    """A user objective L(u) with its own dL/du (the adjoint right-hand side is arbitrary,
+    Examples/Shells_Mannheim_Multihalle_Size.ipynb uses a displacement penalty)."""
+    md = meshes.plate(10)
+    model = build_model(md)
+    sso = jb.SSO_model(model)
+    for node in md.design_nodes:
+        sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+    sso.initialize_parameters_values()
+    w = np.random.default_rng(0).uniform(0.5, 1.5, md.ndof)
+    w[md.known] = 0
+
+    def penalty(sso_model, u, weight):
+        return float(0.5 * np.sum(weight * u * u)), weight * u
+
+    sso.set_objective('user', func=penalty, func_args=(w,))
+    sso.rtol = 1e-12
+    L, sens = sso.value_grad_params()
+    m = to_oracle_mesh(md)
+    rv, ru, rl, rdc, _, _ = orc.value_and_grad(m, g_fn=lambda u: (0.5 * np.sum(w * u * u), w * u))
+    assert abs(L - rv) / rv < 1e-8
+    ref = rdc[md.design_nodes, 2]
+    assert np.abs(sens - ref).max() / np.abs(ref).max() < 1e-6
