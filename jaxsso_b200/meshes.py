@@ -184,10 +184,13 @@ def gridshell(n=224, k=0):
     a_k = 5 + 0.25 * k
     z = a_k * (1 - xi ** 2) * (1 - eta ** 2) + rng.uniform(-0.01, 0.01, size=n * n)
     boundary = (i == 0) | (i == n - 1) | (j == 0) | (j == n - 1)
-    z[boundary] = 0.0
     nid = np.arange(n * n).reshape(n, n)
     cnct = np.concatenate([np.stack([nid[:, :-1].ravel(), nid[:, 1:].ravel()], 1),
                            np.stack([nid[:-1, :].ravel(), nid[1:, :].ravel()], 1)])
+    # the z perturbation (kept on the boundary too) guarantees that no member is exactly parallel
+    # to global Y, where the reference's transformation degenerates (element.py:92-94)
+    d = np.stack([i, j, z], 1)[cnct[:, 1]] - np.stack([i, j, z], 1)[cnct[:, 0]]
+    assert (np.hypot(d[:, 0], d[:, 2]) / np.linalg.norm(d, axis=1)).min() > 1e-9
     b, h, E = 0.1, 0.2, 3.79e9
     Iy, Iz = b * h ** 3 / 12, h * b ** 3 / 12
     sec = dict(E=E, G=E / 2.6, Iy=Iy, Iz=Iz, J=Iy + Iz, A=b * h)
