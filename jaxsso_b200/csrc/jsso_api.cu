@@ -54,6 +54,7 @@ struct jsso_handle {
   bool assembled = false, assembled_bc = false, scaled = false;
   int red_blocks = 148 * 4;
   int spmv_blocks = 148 * 8;
+  int coop_blocks = 0;          // max co-resident blocks of cg_persistent_kernel (0: unsupported)
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, n_rank = 1;
@@ -165,6 +166,12 @@ int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
   CK(cudaGetDeviceProperties(&prop, h->device));
   h->red_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 4);
   h->spmv_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 8);
+  {
+    int occ = 0, coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_persistent_kernel, RED_BLOCK, 0));
+    h->coop_blocks = coop ? std::min(RED_MAX_BLOCKS, occ * prop.multiProcessorCount) : 0;
+  }
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
   *out = h;
@@ -487,9 +494,25 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
     while (!stop) {
       const int batch = std::min(o.check_every, o.maxiter - total_iter - it_local);
       if (batch <= 0) break;
-      for (int k = 0; k < batch; ++k) {
-        if ((rc = cg_iteration(h, cur, st))) return rc;
-        cur ^= 1;
+      // single GPU and a matrix that stays L2-resident (latency / launch bound regime): the whole
+      // batch in one cooperative launch.  HBM-bound systems keep the 3-kernel loop, whose 64
+      // warps/SM stream faster than the 24 warps/SM a co-resident grid allows (0.71 vs 0.97 ms
+      // per iteration at 1M quads).
+      if (h->n_rank <= 1 && h->coop_blocks > 0 && (size_t)h->sym.nnzb() * 288 <= ((size_t)96 << 20)) {
+        int n_row_ = n_row, batch_ = batch;
+        // ~2 block rows per warp, at most what fits co-resident: small systems use few blocks
+        // so that the grid barriers stay cheap
+        const int grid = std::max(1, std::min(h->coop_blocks, cdiv(n_row, 2 * (RED_BLOCK / 32))));
+        void* args[] = {&n_row_, &h->rowptr, &h->colidx, &h->vals, &h->vx, &h->vr, &h->vp, &h->vq, &h->sc,
+                        &h->partials, &batch_};
+        CK(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel, dim3(grid), dim3(RED_BLOCK), args, 0, st));
+        LAUNCHED();
+        cur = 0;
+      } else {
+        for (int k = 0; k < batch; ++k) {
+          if ((rc = cg_iteration(h, cur, st))) return rc;
+          cur ^= 1;
+        }
       }
       it_local += batch;
       CK(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
