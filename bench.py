@@ -266,6 +266,12 @@ def run_b200(args):
     # the two kernels on their own (roofline of each)
     ms_asm = max_over_ranks(timed(lambda: h.assemble(crds_d, pq_d, pb_d, apply_bc=True), args.steps))
     ms_adj = max_over_ranks(timed(lambda: h.adjoint(crds_d, pq_d, pb_d, u_d, lam_d, dc_d, dq_d, None), args.steps))
+    # the PCG's dominant kernel: block-CSR SpMV on the assembled (BC-imposed) matrix
+    y_d = D((6 * n_row,))
+    h.assemble(crds_d, pq_d, pb_d, apply_bc=True)
+    for _ in range(3):
+        h.spmv(u_d, y_d)
+    ms_spmv = max_over_ranks(timed(lambda: h.spmv(u_d, y_d), max(args.steps, 20)))
     barrier()
     clocks = sampler.stop() if sampler else None
 
@@ -319,6 +325,15 @@ def run_b200(args):
     roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9,
             'peak': hbm, 'unit': 'GB/s', 'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
             'peak_source': peak_src, 'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm}
+    # DRAM traffic of one launch from the committed ncu capture (profiles/r1_ncu_elem_1024.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum), only valid for that exact workload
+    if world == 1 and N == 1024:
+        roof['traffic'] = 329.856512e6 + 2.757134e9
+    spmv_bytes = s.nnzb * 292 + s.n_row * 100
+    roof_spmv = {'kernel': 'bsr_spmv_kernel', 'bound': 'hbm', 'achieved': spmv_bytes / (ms_spmv * 1e-3) / 1e9,
+                 'peak': hbm, 'unit': 'GB/s', 'frac': spmv_bytes / (ms_spmv * 1e-3) / 1e9 / hbm,
+                 'traffic': (2.821973e9 + 52.820736e6) if (world == 1 and N == 1024) else None,
+                 'algorithmic_bytes_per_launch': spmv_bytes, 'ms': ms_spmv, 'peak_source': peak_src}
     adj_flops = 14000.0 * s.n_quad
     roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
                 'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
@@ -337,7 +352,8 @@ def run_b200(args):
            'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                    'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_adjoint': roof_adj,
-           'kernel_ms': {'assemble_fused': ms_asm, 'adjoint': ms_adj}, 'setup_s': t_setup,
+           'roofline_spmv': roof_spmv,
+           'kernel_ms': {'assemble_fused': ms_asm, 'adjoint': ms_adj, 'spmv': ms_spmv}, 'setup_s': t_setup,
            'grad_eval': grad_eval}
     if world == 1 and args.cpu_baseline:
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
