@@ -232,6 +232,11 @@ def run_b200(args):
         idbuf = [nat.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(idbuf, src=0)
         h.set_halo(idbuf[0], rank, world, lm.peer_rank, lm.send_ptr, lm.send_idx, lm.recv_start, lm.recv_count)
+        if args.p2p:
+            # NVLink peer-memory path: halo pushes and scalar all-reduces inside the CG kernels
+            hs = [None] * world
+            dist.all_gather_object(hs, h.p2p_export())
+            h.p2p_connect(hs, lm.remote_start)
     D = nat.DeviceArray
     crds_d, pq_d, pb_d = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams)
     u_d, lam_d, f_d = D.from_host(u), D.from_host(lam), D.from_host(md.loads)
@@ -346,7 +351,7 @@ def run_b200(args):
            'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
                                   f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
                                   f'{6 * gmd.n_node} dof; step = fused Ke+assembly + adjoint reduction',
-                      'parallelism': f'rcb{world}' if world > 1 else 'single',
+                      'parallelism': (f'rcb{world}+' + ('p2p' if args.p2p else 'nccl')) if world > 1 else 'single',
                       'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
                       'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
            'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -378,6 +383,8 @@ def main():
     ap.add_argument('--size', type=int, default=1024, help='plate is size x size quads')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--no-solve', dest='solve', action='store_false')
+    ap.add_argument('--no-p2p', dest='p2p', action='store_false',
+                    help='distributed CG over NCCL send/recv + all-reduce instead of peer-memory kernels')
     ap.add_argument('--rtol', type=float, default=1e-8)
     ap.add_argument('--maxiter', type=int, default=400000)
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')

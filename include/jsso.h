@@ -179,6 +179,12 @@ int jsso_nccl_unique_id(uint8_t id_out[128]);
 int jsso_set_halo(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_peer,
                   const int32_t* peer_rank, const int32_t* send_ptr, const int32_t* send_idx,
                   const int32_t* recv_start, const int32_t* recv_count);
+/* Optional NVLink peer-memory path (CUDA IPC, one node): after jsso_set_halo every rank exports
+ * 128 bytes, the caller all-gathers them (n_rank x 128, rank order) and every rank connects.
+ * remote_start[p] = first ghost slot of my nodes in peer p's local numbering.  The CG then does
+ * its halo exchange and scalar all-reduces with stores/loads on peer memory inside its kernels. */
+int jsso_p2p_export(jsso_handle* h, uint8_t out[128]);
+int jsso_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* remote_start);
 /* Fill the ghost entries of a 6-dof-per-node vector from their owners. */
 int jsso_halo_exchange(jsso_handle* h, double* vec_d, void* stream);
 

@@ -55,7 +55,7 @@ SYMBOLS = ['jsso_create', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', '
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
-           'jsso_set_halo', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
+           'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
            'jsso_memset', 'jsso_stream_sync', 'jsso_device_count', 'jsso_event_create',
            'jsso_event_record', 'jsso_event_elapsed_ms', 'jsso_event_destroy', 'jsso_launch_count']
@@ -98,6 +98,8 @@ def lib():
     L.jsso_nccl_unique_id.argtypes = [vp]
     L.jsso_set_halo.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.jsso_halo_exchange.argtypes = [vp, vp, vp]
+    L.jsso_p2p_export.argtypes = [vp, vp]
+    L.jsso_p2p_connect.argtypes = [vp, vp, vp]
     L.jsso_set_device.argtypes = [C.c_int]
     L.jsso_dev_alloc.argtypes = [C.c_size_t]
     L.jsso_dev_alloc.restype = vp
@@ -356,6 +358,16 @@ class Handle:
         a = [np.ascontiguousarray(x, np.int32) for x in (peer_rank, send_ptr, send_idx, recv_start, recv_count)]
         idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
         self._ck(lib().jsso_set_halo(self.h, _ptr(idb), rank, n_rank, len(a[0]), *[_ptr(x) for x in a]))
+
+    def p2p_export(self):
+        buf = np.zeros(128, np.uint8)
+        self._ck(lib().jsso_p2p_export(self.h, _ptr(buf)))
+        return buf.tobytes()
+
+    def p2p_connect(self, all_handles, remote_start):
+        blob = np.frombuffer(b''.join(all_handles), dtype=np.uint8).copy()
+        rs = np.ascontiguousarray(remote_start, np.int32)
+        self._ck(lib().jsso_p2p_connect(self.h, _ptr(blob), _ptr(rs)))
 
     def halo_exchange(self, vec, stream=None):
         self._ck(lib().jsso_halo_exchange(self.h, _dp(vec), stream))

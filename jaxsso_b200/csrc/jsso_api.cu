@@ -62,6 +62,11 @@ struct jsso_handle {
   int32_t* send_idx = nullptr;
   double *send_buf = nullptr;
   int n_send_nodes = 0;
+  // NVLink peer-memory path (CUDA IPC): mailbox + peers' p vectors
+  Mailbox* mbox = nullptr;
+  P2PCtx* p2p = nullptr;            // device copy of the context; null = NCCL path
+  std::vector<void*> ipc_opened;
+  unsigned long long halo_seq = 0, red_seq_a = 0, red_seq_b = 0;
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
@@ -186,12 +191,13 @@ void jsso_destroy(jsso_handle* h) {
                  h->item_code, h->item_lel, h->node_mask, h->chunk_blk, h->chunk_el_ptr, h->chunk_els, h->blk_perm,
                  h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
                  h->corner_q, h->corner_b, h->tmp_lam, h->tmp_g, h->sc, h->partials, h->counters, h->flags,
-                 h->send_idx, h->send_buf, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
+                 h->send_idx, h->send_buf, h->mbox, h->p2p, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
                  h->s_dpb};
   for (void* p : dev) if (p) cudaFree(p);
   void* hst[] = {h->sc_host, h->flags_host, h->h_crds, h->h_pq, h->h_pb, h->h_f, h->h_u, h->h_dc, h->h_dpq,
                  h->h_dpb};
   for (void* p : hst) if (p) cudaFreeHost(p);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm) ncclCommDestroy(h->comm);
   delete h;
 }
@@ -360,6 +366,57 @@ int jsso_halo_exchange(jsso_handle* h, double* vec_d, void* stream) {
 }
 
 // global = sum over ranks of this rank's partial (out of place, so repeating it is harmless)
+// ---- peer-memory (CUDA IPC) setup: export my handles, import everybody's
+int jsso_p2p_export(jsso_handle* h, uint8_t out[128]) {
+  if (!h || !out) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  if (!h->mbox) {
+    CK(dalloc(&h->mbox, 1));
+    CK(cudaMemset(h->mbox, 0, sizeof(Mailbox)));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t a, b;
+  CK(cudaIpcGetMemHandle(&a, h->vp));
+  CK(cudaIpcGetMemHandle(&b, h->mbox));
+  std::memcpy(out, &a, 64);
+  std::memcpy(out + 64, &b, 64);
+  return JSSO_OK;
+}
+
+int jsso_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* remote_start) {
+  if (!h || !all_handles || !remote_start) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  if (h->n_rank <= 1 || h->n_rank > P2P_MAX_RANKS || (int)h->peers.size() > P2P_MAX_RANKS || !h->mbox)
+    return fail(h, JSSO_ERR_STATE, "p2p_connect needs set_halo + p2p_export first and <= 16 ranks");
+  P2PCtx c;
+  std::memset(&c, 0, sizeof c);
+  c.rank = h->rank; c.n_rank = h->n_rank; c.n_peer = (int)h->peers.size();
+  for (int r = 0; r < h->n_rank; ++r) {
+    if (r == h->rank) { c.mbox[r] = h->mbox; continue; }
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, all_handles + 128 * (size_t)r + 64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    c.mbox[r] = (Mailbox*)p;
+  }
+  for (int i = 0; i < c.n_peer; ++i) {
+    const HaloPeer& hp = h->peers[i];
+    cudaIpcMemHandle_t vh;
+    std::memcpy(&vh, all_handles + 128 * (size_t)hp.rank, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, vh, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    c.peer_rank[i] = hp.rank; c.peer_vec[i] = (double*)p;
+    c.send_off[i] = hp.send_off; c.send_cnt[i] = hp.send_cnt; c.remote_start[i] = remote_start[i];
+  }
+  CK(dalloc(&h->p2p, 1));
+  CK(cudaMemcpy(h->p2p, &c, sizeof c, cudaMemcpyHostToDevice));
+  return JSSO_OK;
+}
+
 static int allreduce_scalar(jsso_handle* h, const double* local, double* global, cudaStream_t st) {
   if (h->n_rank <= 1) return JSSO_OK;
   CKN(ncclAllReduce(local, global, 1, ncclDouble, ncclSum, h->comm, st));
@@ -372,7 +429,7 @@ static int spmv_plain(jsso_handle* h, const double* x, double* y, cudaStream_t s
   if (n_row == 0) return JSSO_OK;
   const int blocks = std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32));
   bsr_spmv_kernel<0><<<blocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, x, y, h->sc, 0,
-                                                   h->partials, h->counters, 1);
+                                                   h->partials, h->counters, 1, nullptr, 0, 0);
   CKL("bsr_spmv_kernel<0>");
   return JSSO_OK;
 }
@@ -431,23 +488,39 @@ static int cg_iteration(jsso_handle* h, int cur, cudaStream_t st) {
   const int n_row = h->sym.n_row;
   const long long n = 6LL * n_row;
   const int single = h->n_rank <= 1;
-  int rc = halo_exchange_w(h, h->vp, 6, st);
-  if (rc) return rc;
   const int sblocks = std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
+  const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
+  int rc;
+  if (h->p2p) {
+    // peer-memory path: 4 launches, no NCCL call; the collectives live inside the kernels
+    const unsigned long long hs = ++h->halo_seq, sa = ++h->red_seq_a, sb = ++h->red_seq_b;
+    const int pblocks = std::max(1, std::min(64, cdiv(6LL * h->n_send_nodes, RED_BLOCK)));
+    p2p_halo_push_kernel<<<pblocks, RED_BLOCK, 0, st>>>(h->p2p, h->send_idx, h->vp, h->counters + 3, hs);
+    CKL("p2p_halo_push_kernel");
+    bsr_spmv_kernel<1><<<sblocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, h->vp, h->vq, h->sc,
+                                                     cur, h->partials, h->counters, 0, h->p2p, hs, sa);
+    CKL("bsr_spmv_kernel<1>");
+    cg_update_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vp, h->vq, h->vx, h->vr, h->sc, h->partials,
+                                                    h->counters + 1, 0, h->p2p, sa, sb);
+    CKL("cg_update_kernel");
+    cg_direction_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vr, h->vp, h->sc, h->p2p, sb);
+    CKL("cg_direction_kernel");
+    return JSSO_OK;
+  }
+  if ((rc = halo_exchange_w(h, h->vp, 6, st))) return rc;
   bsr_spmv_kernel<1><<<sblocks, RED_BLOCK, 0, st>>>(n_row, h->rowptr, h->colidx, h->vals, h->vp, h->vq, h->sc,
-                                                   cur, h->partials, h->counters, single);
+                                                   cur, h->partials, h->counters, single, nullptr, 0, 0);
   CKL("bsr_spmv_kernel<1>");
   if ((rc = allreduce_scalar(h, &h->sc->loc[0], &h->sc->pq, st))) return rc;
-  const int vblocks = std::max(1, std::min(h->red_blocks, cdiv(n, RED_BLOCK)));
   cg_update_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vp, h->vq, h->vx, h->vr, h->sc, h->partials,
-                                                  h->counters + 1, single);
+                                                  h->counters + 1, single, nullptr, 0, 0);
   CKL("cg_update_kernel");
   if (!single) {
     if ((rc = allreduce_scalar(h, &h->sc->loc[1], &h->sc->rr[cur ^ 1], st))) return rc;
     cg_latch_kernel<<<1, 1, 0, st>>>(cur, h->sc);
     CKL("cg_latch_kernel");
   }
-  cg_direction_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vr, h->vp, h->sc);
+  cg_direction_kernel<<<vblocks, RED_BLOCK, 0, st>>>(n, cur, h->vr, h->vp, h->sc, nullptr, 0);
   CKL("cg_direction_kernel");
   return JSSO_OK;
 }

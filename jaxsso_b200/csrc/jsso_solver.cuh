@@ -43,6 +43,65 @@ __device__ inline bool cg_stop(const CgScalars* sc, int cur) {
   return !(sc->rr[cur] > sc->tol2 * sc->bb);   // also true for NaN
 }
 
+// ---- NVLink peer-memory collectives for the distributed CG ---------------------------------
+// One process per GPU; every rank maps its peers' `p` vector and mailbox through CUDA IPC.
+// The halo exchange and the two scalar all-reduces of a CG iteration are then done by the CG
+// kernels themselves with plain stores / loads on peer pointers (no NCCL call, no extra launch
+// on the critical path except the push kernel):
+//   * halo: the owner writes its interface entries of p straight into the ghost slots of the
+//     neighbours' p vectors, fences system-wide and raises halo[rank] = seq in their mailboxes;
+//     the neighbour's SpMV spins on its own mailbox before touching ghost columns;
+//   * all-reduce: the block that finalises a dot product stores (value, tag = seq) into slot
+//     [channel][rank] of EVERY rank's mailbox; the consumer kernel's blocks spin until all
+//     n_rank tags equal seq and sum the values in rank order (bitwise identical on all ranks).
+// Tags only grow, so no reset or barrier is needed; see DESIGN.md section 5 for the ordering
+// argument (a rank cannot reach reduction k+1 before every rank has read reduction k).
+constexpr int P2P_MAX_RANKS = 16;
+struct Mailbox {
+  double val[2][P2P_MAX_RANKS];
+  unsigned long long tag[2][P2P_MAX_RANKS];
+  unsigned long long halo[P2P_MAX_RANKS];
+};
+struct P2PCtx {
+  int rank, n_rank, n_peer;
+  Mailbox* mbox[P2P_MAX_RANKS];      // by rank (own entry = local mailbox)
+  int peer_rank[P2P_MAX_RANKS];      // by peer index
+  double* peer_vec[P2P_MAX_RANKS];   // peer's p vector
+  int send_off[P2P_MAX_RANKS], send_cnt[P2P_MAX_RANKS], remote_start[P2P_MAX_RANKS];
+};
+
+// called by ONE thread: publish this rank's partial of reduction `seq` on channel ch
+__device__ inline void p2p_publish(const P2PCtx* c, int ch, unsigned long long seq, double v) {
+  for (int r = 0; r < c->n_rank; ++r) ((volatile double*)c->mbox[r]->val[ch])[c->rank] = v;
+  __threadfence_system();
+  for (int r = 0; r < c->n_rank; ++r) ((volatile unsigned long long*)c->mbox[r]->tag[ch])[c->rank] = seq;
+}
+// called by ALL threads of a block: wait for reduction `seq` and return the sum (rank order)
+__device__ inline double p2p_reduce(const P2PCtx* c, int ch, unsigned long long seq) {
+  __shared__ double total;
+  if (threadIdx.x == 0) {
+    const Mailbox* m = c->mbox[c->rank];
+    double s = 0.0;
+    for (int r = 0; r < c->n_rank; ++r) {
+      while (((volatile unsigned long long*)m->tag[ch])[r] < seq) { }
+      __threadfence_system();
+      s += ((volatile double*)m->val[ch])[r];
+    }
+    total = s;
+  }
+  __syncthreads();
+  return total;
+}
+// called by ALL threads of a block: wait until every neighbour has pushed halo `seq`
+__device__ inline void p2p_wait_halo(const P2PCtx* c, unsigned long long seq) {
+  if ((int)threadIdx.x < c->n_peer) {
+    const Mailbox* m = c->mbox[c->rank];
+    while (((volatile unsigned long long*)m->halo)[c->peer_rank[threadIdx.x]] < seq) { }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 constexpr int RED_BLOCK = 256;
 constexpr int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8
 
@@ -129,8 +188,14 @@ template <int MODE>
 __global__ void __launch_bounds__(RED_BLOCK)
 bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                CgScalars* sc, int cur, double* partials, unsigned* counter, int single_gpu) {
-  if (MODE == 1 && cg_stop(sc, cur)) return;
+                CgScalars* sc, int cur, double* partials, unsigned* counter, int single_gpu,
+                const P2PCtx* p2p, unsigned long long halo_seq, unsigned long long red_seq) {
+  if (MODE == 1 && cg_stop(sc, cur)) {
+    // latch the stop state into the other parity slot (nobody reads it in this kernel)
+    if (p2p && blockIdx.x == 0 && threadIdx.x == 0) sc->rr[cur ^ 1] = sc->rr[cur];
+    return;
+  }
+  if (p2p) p2p_wait_halo(p2p, halo_seq);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warp = (gridDim.x * blockDim.x) >> 5;
@@ -151,7 +216,30 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
     if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) {
       sc->loc[0] = total;
       if (single_gpu) sc->pq = total;
+      if (p2p) p2p_publish(p2p, 0, red_seq, total);
     }
+  }
+}
+
+// push this rank's interface entries of `v` into the neighbours' ghost slots, then raise the flags
+__global__ void __launch_bounds__(RED_BLOCK)
+p2p_halo_push_kernel(const P2PCtx* c, const int32_t* __restrict__ send_idx, const double* __restrict__ v,
+                     unsigned* counter, unsigned long long seq) {
+  __shared__ bool last;
+  for (int pi = 0; pi < c->n_peer; ++pi) {
+    double* dst = c->peer_vec[pi] + 6 * (size_t)c->remote_start[pi];
+    const int32_t* idx = send_idx + c->send_off[pi];
+    const int n = 6 * c->send_cnt[pi];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+      dst[t] = v[6 * (size_t)idx[t / 6] + t % 6];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (last && (int)threadIdx.x < c->n_peer) {
+    __threadfence_system();
+    ((volatile unsigned long long*)c->mbox[c->peer_rank[threadIdx.x]]->halo)[c->rank] = seq;
   }
 }
 
@@ -375,9 +463,11 @@ cg_init_kernel(long long n, const double* __restrict__ b, const double* __restri
 __global__ void __launch_bounds__(RED_BLOCK)
 cg_update_kernel(long long n, int cur, const double* __restrict__ p, const double* __restrict__ q,
                  double* __restrict__ x, double* __restrict__ r, CgScalars* sc, double* partials,
-                 unsigned* counter, int single_gpu) {
+                 unsigned* counter, int single_gpu, const P2PCtx* p2p, unsigned long long seq_a,
+                 unsigned long long seq_b) {
   if (cg_stop(sc, cur)) return;
-  const double rr = sc->rr[cur], pq = sc->pq;
+  const double rr = sc->rr[cur];
+  const double pq = p2p ? p2p_reduce(p2p, 0, seq_a) : sc->pq;
   const double alpha = rr / pq;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -392,6 +482,7 @@ cg_update_kernel(long long n, int cur, const double* __restrict__ p, const doubl
     const double nrr = (pq > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
     sc->loc[1] = nrr;
     sc->iter += 1;
+    if (p2p) { sc->pq = pq; p2p_publish(p2p, 1, seq_b, nrr); }
     if (single_gpu) {
       sc->rr[cur ^ 1] = nrr;
       // On stop, latch BOTH parity slots: later launches of the batch test rr[cur] with
@@ -410,9 +501,19 @@ __global__ void cg_copy_rr_kernel(CgScalars* sc) { sc->rr[1] = sc->rr[0]; }
 // p = r + beta p
 __global__ void __launch_bounds__(RED_BLOCK)
 cg_direction_kernel(long long n, int cur, const double* __restrict__ r, double* __restrict__ p,
-                    const CgScalars* sc) {
-  if (cg_stop(sc, cur) || cg_stop(sc, cur ^ 1)) return;
-  const double beta = sc->rr[cur ^ 1] / sc->rr[cur];
+                    CgScalars* sc, const P2PCtx* p2p, unsigned long long seq_b) {
+  double beta;
+  if (p2p) {
+    if (cg_stop(sc, cur)) return;
+    const double rr_new = p2p_reduce(p2p, 1, seq_b);
+    // rr[cur^1] is not read by any block of this kernel in p2p mode
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->rr[cur ^ 1] = rr_new;
+    if (!(rr_new > sc->tol2 * sc->bb)) return;
+    beta = rr_new / sc->rr[cur];
+  } else {
+    if (cg_stop(sc, cur) || cg_stop(sc, cur ^ 1)) return;
+    beta = sc->rr[cur ^ 1] / sc->rr[cur];
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = fma(beta, p[i], r[i]);
 }

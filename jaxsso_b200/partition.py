@@ -41,11 +41,13 @@ class LocalMesh:
     ghosts grouped by owner), plus the halo plan for jsso_set_halo."""
 
     def __init__(self, md, n_owned, l2g, peer_rank, send_ptr, send_idx, recv_start, recv_count,
-                 quad_ids, beam_ids):
+                 quad_ids, beam_ids, remote_start):
         self.md, self.n_owned, self.l2g = md, n_owned, l2g
         self.peer_rank, self.send_ptr, self.send_idx = peer_rank, send_ptr, send_idx
         self.recv_start, self.recv_count = recv_start, recv_count
         self.quad_ids, self.beam_ids = quad_ids, beam_ids
+        # where my interface nodes sit in each peer's local numbering (for direct peer-memory pushes)
+        self.remote_start = remote_start
 
 
 def _ghost_groups(md, owner, rank):
@@ -73,7 +75,7 @@ def local_mesh(md: MeshData, owner, rank, n_rank):
         pos += groups[p].shape[0]
     # what each peer needs from me = its ghost group owned by me (same deterministic order)
     send_ptr, send_idx = [0], []
-    send_peers = []
+    send_peers, remote_start = [], []
     for p in range(n_rank):
         if p == rank:
             continue
@@ -82,6 +84,8 @@ def local_mesh(md: MeshData, owner, rank, n_rank):
             send_peers.append(p)
             send_idx.append(g2l[gp[rank]])
             send_ptr.append(send_ptr[-1] + gp[rank].shape[0])
+            remote_start.append(int(np.count_nonzero(owner == p)) +
+                                sum(gp[q].shape[0] for q in gp if q < rank))
     # symmetric adjacency is guaranteed (an element touching nodes of r and p makes each a ghost of the other)
     assert send_peers == peers, (send_peers, peers)
     known_g = md.known.astype(np.int64)
@@ -93,4 +97,5 @@ def local_mesh(md: MeshData, owner, rank, n_rank):
                    loads=loads, design_nodes=np.zeros(0, np.int64))
     return LocalMesh(sub, owned.shape[0], l2g, np.array(peers, np.int32), np.array(send_ptr, np.int32),
                      (np.concatenate(send_idx) if send_idx else np.zeros(0)).astype(np.int32),
-                     np.array(recv_start, np.int32), np.array(recv_count, np.int32), qsel, bsel)
+                     np.array(recv_start, np.int32), np.array(recv_count, np.int32), qsel, bsel,
+                     np.array(remote_start, np.int32))

@@ -28,6 +28,11 @@ h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, de
 ids = [nat.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 h.set_halo(ids[0], rank, world, lm.peer_rank, lm.send_ptr, lm.send_idx, lm.recv_start, lm.recv_count)
+use_p2p = os.environ.get('JSSO_P2P', '1') != '0'
+if use_p2p:
+    hs = [None] * world
+    dist.all_gather_object(hs, h.p2p_export())
+    h.p2p_connect(hs, lm.remote_start)
 D = nat.DeviceArray
 crds, pq, pb, f = D.from_host(lm.md.crds), D.from_host(lm.md.prop_quads), D.from_host(lm.md.prop_beams), D.from_host(lm.md.loads)
 u = D((lm.md.ndof,))
@@ -51,7 +56,7 @@ if rank == 0:
     eu = np.linalg.norm(U.ravel() - u1) / np.linalg.norm(u1)
     eg = np.abs(G - dc1).max() / np.abs(dc1).max()
     eq = np.abs(Q - dq1).max() / np.abs(dq1).max()
-    res = {'world': world, 'size': size, 'u_err': eu, 'grad_err': eg, 'dprop_err': eq,
+    res = {'world': world, 'size': size, 'p2p': use_p2p, 'u_err': eu, 'grad_err': eg, 'dprop_err': eq,
            'iters_dist': gu[0][5], 'iters_single': fs1.iterations, 'relres_dist': gu[0][6]}
     print('DIST_CHECK', json.dumps(res))
     ok = eu < 1e-8 and eg < 1e-7 and eq < 1e-7

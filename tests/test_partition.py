@@ -42,6 +42,8 @@ def test_local_meshes_cover_the_mesh(n_rank):
             sent = lm.l2g[lm.send_idx[lm.send_ptr[i]:lm.send_ptr[i + 1]]]
             recv = other.l2g[other.recv_start[j]:other.recv_start[j] + other.recv_count[j]]
             assert np.array_equal(sent, recv)
+            # direct peer-memory pushes land where the peer expects my nodes
+            assert lm.remote_start[i] == other.recv_start[j]
         # prescribed dofs restricted to local nodes
         g = (6 * lm.l2g[lm.md.known // 6] + lm.md.known % 6)
         assert set(g.tolist()) <= set(md.known.tolist())
