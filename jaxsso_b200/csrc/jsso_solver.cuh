@@ -70,11 +70,29 @@ struct P2PCtx {
   int send_off[P2P_MAX_RANKS], send_cnt[P2P_MAX_RANKS], remote_start[P2P_MAX_RANKS];
 };
 
+// system-scope release store / acquire load (PTX memory model): the release orders every write
+// this thread has performed or observed (through CTA barriers / gpu-scope atomics) before the
+// flag; the acquire makes them visible to the loads that follow the successful poll.
+__device__ inline void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ inline double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // called by ONE thread: publish this rank's partial of reduction `seq` on channel ch
 __device__ inline void p2p_publish(const P2PCtx* c, int ch, unsigned long long seq, double v) {
-  for (int r = 0; r < c->n_rank; ++r) ((volatile double*)c->mbox[r]->val[ch])[c->rank] = v;
-  __threadfence_system();
-  for (int r = 0; r < c->n_rank; ++r) ((volatile unsigned long long*)c->mbox[r]->tag[ch])[c->rank] = seq;
+  for (int r = 0; r < c->n_rank; ++r) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&c->mbox[r]->val[ch][c->rank]), "d"(v) : "memory");
+  }
+  for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->tag[ch][c->rank], seq);
 }
 // called by ALL threads of a block: wait for reduction `seq` and return the sum (rank order)
 __device__ inline double p2p_reduce(const P2PCtx* c, int ch, unsigned long long seq) {
@@ -83,9 +101,8 @@ __device__ inline double p2p_reduce(const P2PCtx* c, int ch, unsigned long long 
     const Mailbox* m = c->mbox[c->rank];
     double s = 0.0;
     for (int r = 0; r < c->n_rank; ++r) {
-      while (((volatile unsigned long long*)m->tag[ch])[r] < seq) { }
-      __threadfence_system();
-      s += ((volatile double*)m->val[ch])[r];
+      while (ld_acquire_sys(&m->tag[ch][r]) < seq) { }
+      s += ld_relaxed_sys_f64(&m->val[ch][r]);
     }
     total = s;
   }
@@ -96,8 +113,7 @@ __device__ inline double p2p_reduce(const P2PCtx* c, int ch, unsigned long long 
 __device__ inline void p2p_wait_halo(const P2PCtx* c, unsigned long long seq) {
   if ((int)threadIdx.x < c->n_peer) {
     const Mailbox* m = c->mbox[c->rank];
-    while (((volatile unsigned long long*)m->halo)[c->peer_rank[threadIdx.x]] < seq) { }
-    __threadfence_system();
+    while (ld_acquire_sys(&m->halo[c->peer_rank[threadIdx.x]]) < seq) { }
   }
   __syncthreads();
 }
@@ -233,13 +249,17 @@ p2p_halo_push_kernel(const P2PCtx* c, const int32_t* __restrict__ send_idx, cons
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
       dst[t] = v[6 * (size_t)idx[t / 6] + t % 6];
   }
-  __threadfence_system();
+  // block barrier, then a gpu-scope release by thread 0 (fence + atomic): the last block to
+  // arrive has observed every block's stores and releases them system-wide with the flags
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  }
   __syncthreads();
   if (last && (int)threadIdx.x < c->n_peer) {
-    __threadfence_system();
-    ((volatile unsigned long long*)c->mbox[c->peer_rank[threadIdx.x]]->halo)[c->rank] = seq;
+    __threadfence();
+    st_release_sys(&c->mbox[c->peer_rank[threadIdx.x]]->halo[c->rank], seq);
   }
 }
 
