@@ -48,6 +48,8 @@ class SSO_model:
         self.objective = None
         self.objective_args = None
         self.rtol = 1e-10
+        self.warm_start = False   # start each solve from the previous design's u (optimiser loops)
+        self._u_prev = None
         self.last_stats = None
 
     # ---- parameters (SSO_model.py:125-196) -------------------------------------------
@@ -180,7 +182,10 @@ class SSO_model:
         h = self.model.handle
         opts = nat.make_opts(rtol=self.rtol)
         if self.objective == 'strain energy':
-            val, u, dc, dq, db, fs, bs = h.value_and_grad_host(crds, pq, pb, self.model.nodal_loads, opts=opts)
+            u0 = self._u_prev if (self.warm_start and self._u_prev is not None) else None
+            val, u, dc, dq, db, fs, bs = h.value_and_grad_host(crds, pq, pb, self.model.nodal_loads, opts=opts,
+                                                               u0=u0)
+            self._u_prev = u
             self.last_stats = {'forward': fs.as_dict(), 'backward': bs.as_dict()}
             self.model.u = u
             return val, self._gather_grad(dc, dq, db)

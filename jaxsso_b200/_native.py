@@ -326,19 +326,22 @@ class Handle:
                                      C.byref(o), C.byref(st), stream))
         return st
 
-    def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None):
-        """End-to-end strain-energy value + gradient with HOST (NumPy) buffers."""
+    def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None, u0=None):
+        """End-to-end strain-energy value + gradient with HOST (NumPy) buffers.  ``u0``: initial
+        guess for the solve (e.g. the previous design's u); needs opts.use_x0."""
         crds = np.ascontiguousarray(crds, np.float64)
         prop_q = np.ascontiguousarray(prop_q, np.float64)
         prop_b = np.ascontiguousarray(prop_b, np.float64)
         f = np.ascontiguousarray(f, np.float64)
-        u = np.empty(6 * self.n_node)
+        u = np.empty(6 * self.n_node) if u0 is None else np.array(u0, dtype=np.float64).ravel()
         dc = np.empty((self.n_node, 3)) if 'crds' in want else None
         dq = np.empty((self.n_quad, 5)) if ('prop_q' in want and self.n_quad) else None
         db = np.empty((self.n_beam, 6)) if ('prop_b' in want and self.n_beam) else None
         val = C.c_double()
         fs, bs = Stats(), Stats()
         o = opts or make_opts()
+        if u0 is not None:
+            o.use_x0 = 1
         self._ck(lib().jsso_value_and_grad_host(self.h, _ptr(crds), _ptr(prop_q), _ptr(prop_b), _ptr(f),
                                                 C.byref(val), _ptr(u), _ptr(dc), _ptr(dq), _ptr(db),
                                                 C.byref(o), C.byref(fs), C.byref(bs)))

@@ -650,12 +650,14 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
   if (fl & 8) return fail(h, JSSO_ERR_NOT_SPD, "a diagonal 6x6 block is not positive definite");
   const int n_row = h->sym.n_row;
   if (n_row == 0) return JSSO_OK;
-  // b^ = W b (prescribed dofs zeroed), x0^ = W^-T x0 is not needed: we iterate on y = W^-T x, so
-  // an initial guess x0 must be mapped with y0 = L^T x0; keep it simple: y0 = 0 unless use_x0, then
-  // solve for the correction instead (b <- b - K x0 is done in scaled space via the restart path).
+  // b^ = W b (prescribed dofs zeroed); an initial guess x0 maps to y0 = W^-T x0 (x = W^T y)
   block_apply_kernel<0><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, b, h->node_mask, h->vb);
   CKL("block_apply_kernel<0>");
-  rc = cg_solve_scaled(h, o, false, stats, st);
+  if (o.use_x0) {
+    block_solve_wt_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, x, h->node_mask, h->vx);
+    CKL("block_solve_wt_kernel");
+  }
+  rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
   if (rc && rc != JSSO_ERR_NOCONV) return rc;
   block_apply_kernel<1><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->vx, nullptr, x);
@@ -778,10 +780,16 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
   if (nq) CK(cudaMemcpyAsync(d_pq, h->h_pq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
   if (nb) CK(cudaMemcpyAsync(d_pb, h->h_pb, nb * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_f, h->h_f, nd * sizeof(double), cudaMemcpyHostToDevice, st));
-  rc = jsso_forward(h, d_crds, d_pq, d_pb, d_f, d_u, opts, fs, st);
-  if (rc) return rc;
   jsso_solve_opts o; default_opts(opts, o);
-  o.compliance = 1;
+  if (o.use_x0 && u_h) {   // warm start: u_h holds the previous design's displacements
+    std::memcpy(h->h_u, u_h, nd * sizeof(double));
+    CK(cudaMemcpyAsync(d_u, h->h_u, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    o.use_x0 = 0;
+  }
+  rc = jsso_forward(h, d_crds, d_pq, d_pb, d_f, d_u, &o, fs, st);
+  if (rc) return rc;
+  o.compliance = 1; o.use_x0 = 0;
   const bool want_grad = dc_h || dpq_h || dpb_h;
   if (want_grad) {
     rc = jsso_backward(h, d_crds, d_pq, d_pb, d_u, nullptr, dc_h ? d_dc : nullptr, (dpq_h && nq) ? d_dpq : nullptr,

@@ -450,6 +450,30 @@ block_apply_kernel(int n_row, const double* __restrict__ W, const double* __rest
   }
 }
 
+// y_r = W_r^-T x_r  (back substitution with the upper-triangular W_r^T): maps an initial guess
+// of the unscaled system into the scaled one (x = W^T y).
+__global__ void __launch_bounds__(128)
+block_solve_wt_kernel(int n_row, const double* __restrict__ W, const double* __restrict__ x,
+                      const uint8_t* __restrict__ mask, double* __restrict__ y) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_row) return;
+  const double* w = W + (size_t)r * 36;
+  const unsigned m = mask ? mask[r] : 0u;
+  double v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = ((m >> i) & 1u) ? 0.0 : x[6 * (size_t)r + i];
+  // sum_k W[k][i] y[k] = v[i], W lower triangular => solve from i = 5 down
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double t = v[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) t -= w[k * 6 + i] * v[k];
+    v[i] = t / w[i * 6 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[6 * (size_t)r + i] = v[i];
+}
+
 // ---- CG vector kernels ---------------------------------------------------------------
 // r = b - q (q = A x0 or 0), p = r, rr[0] = bb-candidate.  SETBB: also bb = |b|^2.
 template <int SETBB>

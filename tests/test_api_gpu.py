@@ -130,3 +130,27 @@ def test_user_objective():
     assert abs(L - rv) / rv < 1e-8
     ref = rdc[md.design_nodes, 2]
     assert np.abs(sens - ref).max() / np.abs(ref).max() < 1e-6
+
+
+def test_warm_started_optimiser_steps():
+    """Three projected-gradient steps with sso.warm_start: fewer PCG iterations after the first,
+    same objective as cold starts."""
+    md = meshes.plate(16)
+    vals = {}
+    for warm in (False, True):
+        model = build_model(md)
+        sso = jb.SSO_model(model)
+        for node in md.design_nodes:
+            sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+        sso.initialize_parameters_values()
+        sso.set_objective('strain energy')
+        sso.warm_start = warm
+        its, cs = [], []
+        for step in range(3):
+            C, g = sso.value_grad_params()
+            its.append(sso.last_stats['forward']['iterations'])
+            cs.append(C)
+            sso.update_nodeparameter(sso.nodeparameters_values - 1e-3 * g / np.abs(g).max())
+        vals[warm] = (its, cs)
+    assert np.allclose(vals[True][1], vals[False][1], rtol=1e-8)
+    assert vals[True][0][1] < vals[False][0][1] and vals[True][0][2] < vals[False][0][2]

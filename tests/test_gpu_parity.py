@@ -181,6 +181,26 @@ def test_forward_displacements(case, mannheim_data, golden):
         assert abs(c - golden['beam_arch']['dense_strain_energy']) / c <= 5e-8
 
 
+def test_warm_start_from_previous_design():
+    """use_x0: the previous design's u as initial guess (what an optimiser loop does)."""
+    md = meshes.plate(24)
+    d = Dev(md)
+    u_d = nat.DeviceArray((md.ndof,))
+    st0 = d.h.forward(d.crds, d.pq, d.pb, d.f, u_d, opts=nat.make_opts(rtol=1e-10))
+    # same system again from its own solution: converged before the first iteration batch ends
+    st1 = d.h.forward(d.crds, d.pq, d.pb, d.f, u_d, opts=nat.make_opts(rtol=1e-10, use_x0=True, check_every=5))
+    assert st1.converged and st1.iterations <= 5
+    # slightly changed design
+    crds2 = md.crds.copy()
+    crds2[md.design_nodes, 2] += 1e-4 * np.sin(md.crds[md.design_nodes, 0])
+    c2 = nat.DeviceArray.from_host(crds2)
+    st2 = d.h.forward(c2, d.pq, d.pb, d.f, u_d, opts=nat.make_opts(rtol=1e-10, use_x0=True))
+    m = to_oracle_mesh(md)
+    uref = orc.solve_refined(m, crds=crds2)
+    assert st2.converged and st2.iterations < st0.iterations
+    assert np.linalg.norm(u_d.download() - uref) / np.linalg.norm(uref) <= U_TOL
+
+
 def test_pcg_unattainable_tolerance_is_reported(mannheim_data):
     md = meshes.mannheim_quad(mannheim_data)
     d = Dev(md)
