@@ -97,7 +97,19 @@ typedef struct {
   int32_t check_every;   /* iterations per convergence poll; default 50 */
   int32_t use_x0;        /* 1: `u`/`x` holds an initial guess */
   int32_t compliance;    /* jsso_backward only: 1 => g == f/2, take lam = u/2 (K symmetric) */
+  int32_t precond;       /* 0 auto, 1 block-Jacobi CG, 2 smoothed-aggregation multigrid PCG */
+  int32_t cheb_degree;   /* Chebyshev smoother degree of the multigrid V-cycle; default 2 */
 } jsso_solve_opts;
+
+/* One coarsening step of the multigrid hierarchy: connectivity-only gather lists built on the
+ * host (jaxsso_b200/multigrid.py: build_level).  All arrays are host int32. */
+typedef struct {
+  int32_t n_f, n_c, nnz_p, nnz_ap, nnz_c;
+  const int32_t *agg, *p_rowptr, *p_col, *p_own, *ps_ptr, *ps_a, *ps_j;
+  const int32_t *apl_ptr, *apl_a, *apl_p;
+  const int32_t *c_rowptr, *c_col, *c_diag, *cl_ptr, *cl_p, *cl_ap;
+  const int32_t *pt_rowptr, *pt_col, *pt_src, *mem_ptr, *mem;
+} jsso_mg_level_desc;
 
 /* ---- lifetime ---------------------------------------------------------------- */
 int jsso_create(const jsso_mesh_desc* desc, jsso_handle** out);
@@ -136,6 +148,11 @@ int jsso_spmv(jsso_handle* h, const double* x_d, double* y_d, void* stream);
  * K x = b with b zeroed at prescribed dofs.  Synchronises `stream`. */
 int jsso_pcg(jsso_handle* h, const double* b_d, double* x_d, const jsso_solve_opts* opts,
              jsso_stats* stats, void* stream);
+
+/* Optional smoothed-aggregation multigrid preconditioner (single GPU): upload
+ * the symbolic hierarchy once; the numeric hierarchy (rigid-body prolongators, Galerkin operators)
+ * is rebuilt inside the first solve after each assembly. */
+int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_level_desc* levels);
 
 /* ---- adjoint sensitivity reduction ---------------------------------------------- */
 /* d_crds[n,c] = sum_e sum_ab (-lam_e[a] u_e[b]) dK_e[a,b]/dcrds[n,c], same for the

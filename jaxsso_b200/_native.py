@@ -47,13 +47,26 @@ class Stats(C.Structure):
 
 class SolveOpts(C.Structure):
     _fields_ = [('rtol', C.c_double), ('maxiter', C.c_int32), ('check_every', C.c_int32),
-                ('use_x0', C.c_int32), ('compliance', C.c_int32)]
+                ('use_x0', C.c_int32), ('compliance', C.c_int32), ('precond', C.c_int32),
+                ('cheb_degree', C.c_int32)]
+
+
+_MG_INT_FIELDS = ['n_f', 'n_c', 'nnz_p', 'nnz_ap', 'nnz_c']
+_MG_PTR_FIELDS = ['agg', 'p_rowptr', 'p_col', 'p_own', 'ps_ptr', 'ps_a', 'ps_j', 'apl_ptr', 'apl_a', 'apl_p',
+                  'c_rowptr', 'c_col', 'c_diag', 'cl_ptr', 'cl_p', 'cl_ap', 'pt_rowptr', 'pt_col', 'pt_src',
+                  'mem_ptr', 'mem']
+
+
+class MgLevelDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in _MG_INT_FIELDS] + [(k, C.c_void_p) for k in _MG_PTR_FIELDS]
+
+PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
-           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_adjoint',
+           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
@@ -89,6 +102,7 @@ def lib():
     L.jsso_get_flags.argtypes = [vp, C.POINTER(i32)]
     L.jsso_spmv.argtypes = [vp, vp, vp, vp]
     L.jsso_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
+    L.jsso_mg_setup.argtypes = [vp, i32, C.POINTER(MgLevelDesc)]
     L.jsso_adjoint.argtypes = [vp] + [vp] * 8 + [vp]
     L.jsso_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_backward.argtypes = [vp] + [vp] * 9 + [C.POINTER(SolveOpts), C.POINTER(Stats), vp]
@@ -213,8 +227,10 @@ def _dp(a):
     return C.c_void_p(int(a))
 
 
-def make_opts(rtol=1e-10, maxiter=200000, check_every=50, use_x0=False, compliance=False):
-    return SolveOpts(float(rtol), int(maxiter), int(check_every), int(bool(use_x0)), int(bool(compliance)))
+def make_opts(rtol=1e-10, maxiter=200000, check_every=50, use_x0=False, compliance=False, precond='auto',
+              cheb_degree=2):
+    return SolveOpts(float(rtol), int(maxiter), int(check_every), int(bool(use_x0)), int(bool(compliance)),
+                     PRECOND[precond] if isinstance(precond, str) else int(precond), int(cheb_degree))
 
 
 class Handle:
@@ -303,6 +319,25 @@ class Handle:
         self._ck(lib().jsso_pcg(self.h, _dp(b), _dp(x), C.byref(o), C.byref(st), stream),
                  allow=(JSSO_ERR_NOCONV,) if allow_noconv else ())
         return st
+
+    def mg_setup(self, levels=None, max_coarse_nodes=400):
+        """Build (or take) the symbolic smoothed-aggregation hierarchy and upload it."""
+        from . import multigrid
+        if levels is None:
+            rp, ci = self.pattern()
+            levels = multigrid.build_hierarchy(rp, ci, max_coarse_nodes=max_coarse_nodes)
+        descs = (MgLevelDesc * max(len(levels), 1))()
+        keep = []
+        for d, lv in zip(descs, levels):
+            for k in _MG_INT_FIELDS:
+                setattr(d, k, int(lv[k]))
+            for k in _MG_PTR_FIELDS:
+                a = np.ascontiguousarray(lv[k], dtype=np.int32)
+                keep.append(a)
+                setattr(d, k, a.ctypes.data)
+        self._ck(lib().jsso_mg_setup(self.h, len(levels), descs))
+        self.mg_levels = [(lv['n_f'], lv['n_c']) for lv in levels]
+        return levels
 
     # ---- adjoint
     def adjoint(self, crds, prop_q, prop_b, u, lam, d_crds=None, d_prop_q=None, d_prop_b=None, stream=None):

@@ -14,6 +14,7 @@
 #include "jsso_adjoint.cuh"
 #include "jsso_assemble.cuh"
 #include "jsso_solver.cuh"
+#include "jsso_multigrid.cuh"
 #include "jsso_symbolic.h"
 
 using namespace jsso;
@@ -67,6 +68,27 @@ struct jsso_handle {
   P2PCtx* p2p = nullptr;            // device copy of the context; null = NCCL path
   std::vector<void*> ipc_opened;
   unsigned long long halo_seq = 0, red_seq_a = 0, red_seq_b = 0;
+  // smoothed-aggregation multigrid (single GPU): symbolic data per coarsening step + numeric state
+  struct MgLevel {
+    int n_f = 0, n_c = 0, nnz_p = 0, nnz_ap = 0, nnz_c = 0;
+    int32_t *agg = nullptr, *p_row = nullptr, *p_rowptr = nullptr, *p_col = nullptr, *p_own = nullptr;
+    int32_t *ps_ptr = nullptr, *ps_a = nullptr, *ps_j = nullptr;
+    int32_t *apl_ptr = nullptr, *apl_a = nullptr, *apl_p = nullptr;
+    int32_t *c_rowptr = nullptr, *c_col = nullptr, *c_diag = nullptr, *cl_ptr = nullptr, *cl_p = nullptr,
+            *cl_ap = nullptr;
+    int32_t *pt_rowptr = nullptr, *pt_col = nullptr, *pt_src = nullptr, *mem_ptr = nullptr, *mem = nullptr;
+    double *P = nullptr, *Pt = nullptr, *AP = nullptr, *Ac = nullptr, *Xc = nullptr, *Dinv = nullptr;
+    double *b = nullptr, *x = nullptr, *r = nullptr, *d = nullptr;   // level vectors (b, x unused at level 0)
+    double lam = 0.0;
+  };
+  std::vector<MgLevel> mg;
+  double* Lfac = nullptr;          // L_i (row-major) of the fine diagonal blocks
+  double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
+  double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
+  double* mg_scal = nullptr;       // device scalars of the host-driven PCG
+  double* mg_scal_host = nullptr;  // pinned
+  bool mg_ready = false;           // numeric hierarchy matches the current matrix
+  const double* last_crds = nullptr;
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
@@ -255,7 +277,8 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
     CKL("assemble_fused_kernel");
   }
-  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false;
+  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
+  h->last_crds = crds;
   return JSSO_OK;
 }
 
@@ -270,7 +293,7 @@ int jsso_assemble_from_ke(jsso_handle* h, const double* ke_q, const double* ke_b
         h->vals, apply_bc);
     CKL("assemble_from_ke_kernel");
   }
-  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false;
+  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
   return JSSO_OK;
 }
 
@@ -447,7 +470,7 @@ static int ensure_scaled(jsso_handle* h, cudaStream_t st) {
   if (h->scaled) return JSSO_OK;
   const int n_row = h->sym.n_row;
   if (n_row > 0) {
-    diag_factor_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->diag_slot, h->vals, h->W, h->flags);
+    diag_factor_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->diag_slot, h->vals, h->W, h->Lfac, h->flags);
     CKL("diag_factor_kernel");
   }
   if (h->n_rank > 1) {
@@ -474,11 +497,14 @@ static int ensure_scaled(jsso_handle* h, cudaStream_t st) {
 
 static void default_opts(const jsso_solve_opts* in, jsso_solve_opts& o) {
   o.rtol = 1e-10; o.maxiter = 200000; o.check_every = 50; o.use_x0 = 0; o.compliance = 0;
+  o.precond = 0; o.cheb_degree = 2;
   if (in) {
     if (in->rtol > 0) o.rtol = in->rtol;
     if (in->maxiter > 0) o.maxiter = in->maxiter;
     if (in->check_every > 0) o.check_every = in->check_every;
     o.use_x0 = in->use_x0; o.compliance = in->compliance;
+    o.precond = in->precond;
+    if (in->cheb_degree > 0) o.cheb_degree = in->cheb_degree;
   }
 }
 
@@ -633,6 +659,270 @@ static int cg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
   return JSSO_OK;
 }
 
+}  // extern "C" (templates below)
+
+// ---------------------------------------------------------------- multigrid (single GPU)
+extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_level_desc* L) {
+  if (!h || (n_levels > 0 && !L)) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  if (!h->mg.empty()) return fail(h, JSSO_ERR_STATE, "multigrid hierarchy already set");
+  if (h->sym.n_row != h->sym.n_node) return fail(h, JSSO_ERR_STATE, "multigrid: single-GPU handles only");
+  int n_prev = h->sym.n_row;
+  for (int l = 0; l < n_levels; ++l) {
+    const jsso_mg_level_desc& d = L[l];
+    if (d.n_f != n_prev) return fail(h, JSSO_ERR_ARG, "multigrid level sizes do not chain");
+    jsso_handle::MgLevel m;
+    m.n_f = d.n_f; m.n_c = d.n_c; m.nnz_p = d.nnz_p; m.nnz_ap = d.nnz_ap; m.nnz_c = d.nnz_c;
+    auto up = [&](int32_t** dst, const int32_t* src, size_t n) -> cudaError_t {
+      std::vector<int32_t> v(src, src + n);
+      return upload(dst, v);
+    };
+    std::vector<int32_t> prow(d.nnz_p);
+    for (int i = 0; i < d.n_f; ++i)
+      for (int s = d.p_rowptr[i]; s < d.p_rowptr[i + 1]; ++s) prow[s] = i;
+    CK(upload(&m.p_row, prow));
+    CK(up(&m.agg, d.agg, d.n_f)); CK(up(&m.p_rowptr, d.p_rowptr, d.n_f + 1)); CK(up(&m.p_col, d.p_col, d.nnz_p));
+    CK(up(&m.p_own, d.p_own, d.nnz_p)); CK(up(&m.ps_ptr, d.ps_ptr, d.nnz_p + 1));
+    const size_t n_ps = d.ps_ptr[d.nnz_p], n_apl = d.apl_ptr[d.nnz_ap], n_cl = d.cl_ptr[d.nnz_c];
+    CK(up(&m.ps_a, d.ps_a, n_ps)); CK(up(&m.ps_j, d.ps_j, n_ps));
+    CK(up(&m.apl_ptr, d.apl_ptr, d.nnz_ap + 1)); CK(up(&m.apl_a, d.apl_a, n_apl)); CK(up(&m.apl_p, d.apl_p, n_apl));
+    CK(up(&m.c_rowptr, d.c_rowptr, d.n_c + 1)); CK(up(&m.c_col, d.c_col, d.nnz_c)); CK(up(&m.c_diag, d.c_diag, d.n_c));
+    CK(up(&m.cl_ptr, d.cl_ptr, d.nnz_c + 1)); CK(up(&m.cl_p, d.cl_p, n_cl)); CK(up(&m.cl_ap, d.cl_ap, n_cl));
+    CK(up(&m.pt_rowptr, d.pt_rowptr, d.n_c + 1)); CK(up(&m.pt_col, d.pt_col, d.nnz_p)); CK(up(&m.pt_src, d.pt_src, d.nnz_p));
+    CK(up(&m.mem_ptr, d.mem_ptr, d.n_c + 1)); CK(up(&m.mem, d.mem, d.n_f));
+    CK(dalloc(&m.P, 36 * (size_t)d.nnz_p)); CK(dalloc(&m.Pt, 36 * (size_t)d.nnz_p));
+    CK(dalloc(&m.AP, 36 * (size_t)d.nnz_ap)); CK(dalloc(&m.Ac, 36 * (size_t)d.nnz_c));
+    CK(dalloc(&m.Xc, 3 * (size_t)d.n_c));
+    if (l > 0) { CK(dalloc(&m.Dinv, 36 * (size_t)d.n_f)); CK(dalloc(&m.b, 6 * (size_t)d.n_f)); CK(dalloc(&m.x, 6 * (size_t)d.n_f)); }
+    CK(dalloc(&m.r, 6 * (size_t)d.n_f)); CK(dalloc(&m.d, 6 * (size_t)d.n_f));
+    h->mg.push_back(m);
+    n_prev = d.n_c;
+  }
+  if (n_levels > 0) {
+    const size_t nc = 6 * (size_t)n_prev;
+    if (nc > 6000) return fail(h, JSSO_ERR_ARG, "multigrid: coarsest level too large for the dense solve");
+    CK(dalloc(&h->mg_dense, 2 * nc * nc)); CK(dalloc(&h->mg_cb, nc)); CK(dalloc(&h->mg_cx, nc));
+    CK(dalloc(&h->Lfac, 36 * (size_t)h->sym.n_node));
+    CK(dalloc(&h->mg_scal, 8));
+    CK(cudaMallocHost((void**)&h->mg_scal_host, 8 * sizeof(double)));
+  }
+  h->mg_ready = false;
+  h->assembled = false;   // the fine factor L is produced by the scaling of the NEXT assembly
+  h->scaled = false;
+  return JSSO_OK;
+}
+
+struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; };
+static MgMat mg_matrix(jsso_handle* h, int l) {
+  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row};
+  const jsso_handle::MgLevel& p = h->mg[l - 1];
+  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c};
+}
+static inline int mg_blocks(jsso_handle* h, int n_row) {
+  return std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
+}
+template <int MODE>
+static int mg_spmv(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, int n_row,
+                   const double* x, double* y, const double* b, cudaStream_t st) {
+  if (n_row == 0) return JSSO_OK;
+  bsr_spmv_axpby_kernel<MODE><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v, x, y, b);
+  CKL("bsr_spmv_axpby_kernel");
+  return JSSO_OK;
+}
+static int mg_dot(jsso_handle* h, long long n, const double* a, const double* b, int slot, cudaStream_t st) {
+  const int blocks = std::max(1, std::min(h->red_blocks, cdiv(n, 256)));
+  mg_dot_kernel<<<blocks, 256, 0, st>>>(n, a, b, h->partials, h->counters + 2, h->mg_scal + slot);
+  CKL("mg_dot_kernel");
+  return JSSO_OK;
+}
+static int mg_read_scalars(jsso_handle* h, cudaStream_t st) {
+  CK(cudaMemcpyAsync(h->mg_scal_host, h->mg_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return JSSO_OK;
+}
+
+// numeric hierarchy for the current (block-Jacobi-scaled) matrix
+static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
+  if (h->mg_ready) return JSSO_OK;
+  if (!h->last_crds) return fail(h, JSSO_ERR_STATE, "multigrid needs the coordinates of the last jsso_assemble");
+  const int nl = (int)h->mg.size();
+  const double* X = h->last_crds;
+  int rc;
+  for (int l = 0; l < nl; ++l) {
+    jsso_handle::MgLevel& m = h->mg[l];
+    const MgMat A = mg_matrix(h, l);
+    const int n = m.n_f;
+    if (l > 0) {
+      mg_diag_inverse_kernel<<<cdiv(n, 128), 128, 0, st>>>(n, h->mg[l - 1].c_diag, A.v, m.Dinv);
+      CKL("mg_diag_inverse_kernel");
+    }
+    // lambda_max(D^-1 A) by power iteration from the constant vector (12 steps, x1.1 safety)
+    const long long nd = 6LL * n;
+    const int vb = std::max(1, std::min(h->red_blocks, cdiv(nd, 256)));
+    mg_fill_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / std::sqrt((double)nd), m.r);
+    CKL("mg_fill_kernel");
+    double lam = 1.0;
+    for (int it = 0; it < 12; ++it) {
+      if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n, m.r, m.d, nullptr, st))) return rc;
+      if (m.Dinv) {
+        block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
+        CKL("block_apply_kernel<0>");
+      }
+      if ((rc = mg_dot(h, nd, m.d, m.d, 0, st))) return rc;
+      if ((rc = mg_read_scalars(h, st))) return rc;
+      lam = std::sqrt(h->mg_scal_host[0]);
+      if (!(lam > 0.0) || !(lam == lam)) return fail(h, JSSO_ERR_NAN, "multigrid: power iteration broke down");
+      mg_axpby_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / lam, m.d, 0.0, m.r);
+      CKL("mg_axpby_kernel");
+    }
+    m.lam = 1.1 * lam;
+    mg_centroid_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.mem_ptr, m.mem, X, m.Xc);
+    CKL("mg_centroid_kernel");
+    mg_smooth_prolongator_kernel<<<cdiv(m.nnz_p, 128), 128, 0, st>>>(
+        m.nnz_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, m.Dinv, l == 0 ? h->Lfac : nullptr,
+        l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P);
+    CKL("mg_smooth_prolongator_kernel");
+    mg_transpose_blocks_kernel<<<cdiv(36LL * m.nnz_p, 256), 256, 0, st>>>(m.nnz_p, m.pt_src, m.P, m.Pt);
+    CKL("mg_transpose_blocks_kernel");
+    mg_block_product_kernel<0><<<cdiv(m.nnz_ap, 128), 128, 0, st>>>(m.nnz_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP);
+    CKL("mg_block_product_kernel<0>");
+    mg_block_product_kernel<1><<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
+    CKL("mg_block_product_kernel<1>");
+    X = m.Xc;
+  }
+  // coarsest level: dense inverse
+  const MgMat C = mg_matrix(h, nl);
+  const int nc = 6 * C.n;
+  mg_dense_from_bsr_kernel<<<std::max(1, std::min(1184, cdiv(2LL * nc * nc, 256))), 256, 0, st>>>(C.n, C.rp, C.ci, C.v, h->mg_dense);
+  CKL("mg_dense_from_bsr_kernel");
+  mg_dense_fill_kernel<<<C.n, 64, 0, st>>>(C.n, C.rp, C.ci, C.v, h->mg_dense);
+  CKL("mg_dense_fill_kernel");
+  mg_dense_invert_kernel<<<1, 1024, 0, st>>>(nc, h->mg_dense);
+  CKL("mg_dense_invert_kernel");
+  h->mg_ready = true;
+  return JSSO_OK;
+}
+
+// Chebyshev(deg) on D^-1 A with eigenvalues in [lam/4, lam]; x updated in place
+static int mg_smooth(jsso_handle* h, int l, const double* b, double* x, bool zero_guess, int deg, cudaStream_t st) {
+  jsso_handle::MgLevel& m = h->mg[l];
+  const MgMat A = mg_matrix(h, l);
+  const int n = m.n_f, nb = cdiv(n, 128);
+  const double lmax = m.lam, lmin = m.lam / 4.0;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  int rc;
+  if (zero_guess) {
+    mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, b, m.d, x, 0.0, 1.0 / theta, 1);
+  } else {
+    if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n, x, m.r, b, st))) return rc;
+    mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, 0.0, 1.0 / theta, 0);
+  }
+  CKL("mg_cheb_kernel<1>");
+  for (int k = 1; k < deg; ++k) {
+    if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n, x, m.r, b, st))) return rc;
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, rho_new * rho, 2.0 * rho_new / delta, 0);
+    CKL("mg_cheb_kernel<0>");
+    rho = rho_new;
+  }
+  return JSSO_OK;
+}
+
+static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg, cudaStream_t st) {
+  const int nl = (int)h->mg.size();
+  int rc;
+  if (l == nl) {
+    const int nc = 6 * mg_matrix(h, nl).n;
+    mg_dense_matvec_kernel<<<cdiv(32LL * nc, 256), 256, 0, st>>>(nc, h->mg_dense, b, x);
+    CKL("mg_dense_matvec_kernel");
+    return JSSO_OK;
+  }
+  jsso_handle::MgLevel& m = h->mg[l];
+  const MgMat A = mg_matrix(h, l);
+  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
+  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
+  if ((rc = mg_smooth(h, l, b, x, true, deg, st))) return rc;
+  if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, m.n_f, x, m.r, b, st))) return rc;          // r = b - A x
+  if ((rc = mg_spmv<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
+  if ((rc = mg_vcycle(h, l + 1, bc, xc, deg, st))) return rc;
+  if ((rc = mg_spmv<3>(h, m.p_rowptr, m.p_col, m.P, m.n_f, xc, x, nullptr, st))) return rc;        // x += P x_c
+  return mg_smooth(h, l, b, x, false, deg, st);
+}
+
+// PCG on the scaled system with the V-cycle as preconditioner (host-driven scalars: the count is
+// 30-100 iterations, each several milliseconds at 1M quads, so three host syncs per iteration
+// cost nothing)
+static int mg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, jsso_stats* stats, cudaStream_t st) {
+  int rc = mg_numeric_setup(h, st);
+  if (rc) return rc;
+  const int n_row = h->sym.n_row;
+  const long long n = 6LL * n_row;
+  const int vb = std::max(1, std::min(h->red_blocks, cdiv(n, 256)));
+  double *b = h->vb, *x = h->vx, *r = h->vr, *p = h->vp, *q = h->vq, *z = h->tmp_g;
+  const MgMat A = mg_matrix(h, 0);
+  if (use_x0) {
+    if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n_row, x, r, b, st))) return rc;
+  } else {
+    CK(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+    CK(cudaMemcpyAsync(r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  if ((rc = mg_dot(h, n, b, b, 1, st))) return rc;
+  if ((rc = mg_dot(h, n, r, r, 2, st))) return rc;
+  if ((rc = mg_read_scalars(h, st))) return rc;
+  const double bb = h->mg_scal_host[1];
+  double rr = h->mg_scal_host[2], rz = 0.0;
+  int it = 0;
+  bool converged = (bb == 0.0) || std::sqrt(rr / bb) <= o.rtol;
+  while (!converged && it < o.maxiter) {
+    if ((rc = mg_vcycle(h, 0, r, z, o.cheb_degree, st))) return rc;
+    if ((rc = mg_dot(h, n, r, z, 3, st))) return rc;
+    if ((rc = mg_read_scalars(h, st))) return rc;
+    const double rz_new = h->mg_scal_host[3];
+    if (!(rz_new > 0.0)) return fail(h, JSSO_ERR_NAN, "multigrid PCG breakdown: r.z <= 0 (preconditioner not SPD?)");
+    if (it == 0) { CK(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st)); }
+    else { mg_axpby_kernel<<<vb, 256, 0, st>>>(n, 1.0, z, rz_new / rz, p); CKL("mg_axpby_kernel"); }
+    rz = rz_new;
+    if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n_row, p, q, nullptr, st))) return rc;
+    if ((rc = mg_dot(h, n, p, q, 4, st))) return rc;
+    if ((rc = mg_read_scalars(h, st))) return rc;
+    const double pq = h->mg_scal_host[4];
+    if (!(pq > 0.0)) return fail(h, JSSO_ERR_NAN, "multigrid PCG breakdown: non-positive curvature");
+    const double alpha = rz / pq;
+    mg_axpby_kernel<<<vb, 256, 0, st>>>(n, alpha, p, 1.0, x); CKL("mg_axpby_kernel");
+    mg_axpby_kernel<<<vb, 256, 0, st>>>(n, -alpha, q, 1.0, r); CKL("mg_axpby_kernel");
+    if ((rc = mg_dot(h, n, r, r, 2, st))) return rc;
+    if ((rc = mg_read_scalars(h, st))) return rc;
+    rr = h->mg_scal_host[2];
+    ++it;
+    if (!(rr == rr)) return fail(h, JSSO_ERR_NAN, "multigrid PCG: NaN residual");
+    if (std::sqrt(rr / bb) <= o.rtol) {
+      // confirm on the true residual; if the recurrence drifted keep iterating from it
+      if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n_row, x, r, b, st))) return rc;
+      if ((rc = mg_dot(h, n, r, r, 2, st))) return rc;
+      if ((rc = mg_read_scalars(h, st))) return rc;
+      rr = h->mg_scal_host[2];
+      if (std::sqrt(rr / bb) <= 1.5 * o.rtol) converged = true;
+      else if (stats) stats->restarts += 1;
+      if (stats && stats->restarts > 20) break;
+    }
+  }
+  if (stats) {
+    stats->iterations = it; stats->converged = converged ? 1 : 0;
+    stats->relres = bb > 0 ? std::sqrt(rr / bb) : 0.0; stats->relres_recur = stats->relres;
+  }
+  if (!converged) {
+    char buf[200];
+    std::snprintf(buf, sizeof buf, "multigrid PCG did not reach rtol=%.3g: relres %.3g after %d iterations", o.rtol,
+                  bb > 0 ? std::sqrt(rr / bb) : 0.0, it);
+    return fail(h, JSSO_ERR_NOCONV, buf);
+  }
+  return JSSO_OK;
+}
+
+extern "C" {
+
 // K x = b on the assembled BC-imposed matrix: scale, solve, unscale.
 static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_solve_opts& o, jsso_stats* stats,
                         cudaStream_t st) {
@@ -657,7 +947,13 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
     block_solve_wt_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, x, h->node_mask, h->vx);
     CKL("block_solve_wt_kernel");
   }
-  rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
+  // preconditioner: 0 auto (multigrid when a hierarchy is set, the system is not tiny and the
+  // handle is single-GPU), 1 block-Jacobi CG, 2 smoothed-aggregation multigrid
+  const bool have_mg = !h->mg.empty() && h->n_rank <= 1;
+  const bool use_mg = (o.precond == 2) || (o.precond == 0 && have_mg && h->sym.n_row >= 20000);
+  if (use_mg && !have_mg) return fail(h, JSSO_ERR_STATE, "precond = multigrid but no hierarchy (jsso_mg_setup)");
+  if (stats) stats->flags = fl;
+  rc = use_mg ? mg_solve_scaled(h, o, o.use_x0 != 0, stats, st) : cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
   if (rc && rc != JSSO_ERR_NOCONV) return rc;
   block_apply_kernel<1><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->vx, nullptr, x);

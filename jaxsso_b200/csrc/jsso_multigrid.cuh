@@ -1,0 +1,348 @@
+// Smoothed-aggregation multigrid preconditioner on 6x6 block-CSR (numeric kernels).
+//
+// Not part of the reference (which solves with SuperLU, JaxSSO/solver.py:195-197): it only
+// changes how fast the same u is reached.  The symbolic part (aggregates, patterns, gather
+// lists) is built once per model by jaxsso_b200/multigrid.py; everything here is numeric and
+// re-run after each assembly.  All sparse products are gathers over precomputed
+// (left slot, right slot) lists: no atomics, fixed summation order.  Blocks are column-major
+// (entry (i,j) at 6 j + i) like the stiffness values.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jsso {
+
+// rigid-body block T = [[I, -[r]x], [0, I]] (column-major), rows of prescribed dofs zeroed,
+// optionally left-multiplied by Lt (row-major 6x6: the transposed Cholesky factor of the node's
+// diagonal block, when the level matrix is the block-Jacobi-scaled one)
+__device__ inline void rigid_block(const double* X, const double* Xc, int i, int a, unsigned mask,
+                                   const double* LtRow /* L row-major = Lt column-major, or null */,
+                                   double* T /* 36, column-major */) {
+  const double rx = X[3 * (size_t)i] - Xc[3 * (size_t)a], ry = X[3 * (size_t)i + 1] - Xc[3 * (size_t)a + 1],
+               rz = X[3 * (size_t)i + 2] - Xc[3 * (size_t)a + 2];
+  double B[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) B[k] = 0.0;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) B[6 * d + d] = 1.0;
+  // translation rows vs rotation columns: -[r]x = [[0, rz, -ry], [-rz, 0, rx], [ry, -rx, 0]]
+  B[6 * 4 + 0] = rz;  B[6 * 5 + 0] = -ry;
+  B[6 * 3 + 1] = -rz; B[6 * 5 + 1] = rx;
+  B[6 * 3 + 2] = ry;  B[6 * 4 + 2] = -rx;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    if ((mask >> r) & 1u) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) B[6 * c + r] = 0.0;
+    }
+  if (!LtRow) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) T[k] = B[k];
+    return;
+  }
+  // T = L^T B : T[r][c] = sum_k L[k][r] B[k][c], L lower triangular (row-major LtRow[k*6+r])
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = r; k < 6; ++k) s += LtRow[k * 6 + r] * B[6 * c + k];
+      T[6 * c + r] = s;
+    }
+}
+
+// acc (col-major) += A (col-major) * B (col-major)
+__device__ inline void blk_mma(const double* __restrict__ A, const double* B, double* acc) {
+  double a[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) a[k] = A[k];
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double b = B[6 * c + k];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[6 * c + r] = fma(a[6 * k + r], b, acc[6 * c + r]);
+    }
+}
+// acc += A^T * B
+__device__ inline void blk_mma_t(const double* __restrict__ A, const double* __restrict__ B, double* acc) {
+  double a[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) a[k] = A[k];
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double b = B[6 * c + k];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[6 * c + r] = fma(a[6 * r + k], b, acc[6 * c + r]);
+    }
+}
+
+// centroid of every aggregate (members listed in ascending node order)
+__global__ void mg_centroid_kernel(int n_c, const int32_t* __restrict__ mem_ptr, const int32_t* __restrict__ mem,
+                                   const double* __restrict__ X, double* __restrict__ Xc) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_c) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  const int m0 = mem_ptr[a], m1 = mem_ptr[a + 1];
+  for (int k = m0; k < m1; ++k) {
+    const int i = mem[k];
+    s0 += X[3 * (size_t)i]; s1 += X[3 * (size_t)i + 1]; s2 += X[3 * (size_t)i + 2];
+  }
+  const double inv = 1.0 / (double)(m1 - m0);
+  Xc[3 * (size_t)a] = s0 * inv; Xc[3 * (size_t)a + 1] = s1 * inv; Xc[3 * (size_t)a + 2] = s2 * inv;
+}
+
+// inverse of the diagonal blocks (row-major out, like W); a (near) zero block -> identity
+// (aggregates made of fully prescribed nodes give an empty coarse row/column)
+__global__ void __launch_bounds__(128)
+mg_diag_inverse_kernel(int n, const int32_t* __restrict__ diag_slot, const double* __restrict__ vals,
+                       double* __restrict__ Dinv) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double* d = vals + (size_t)diag_slot[r] * 36;
+  double M[6][12];
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(d[6 * i + i]));
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      M[i][j] = 0.5 * (d[6 * j + i] + d[6 * i + j]);
+      M[i][6 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  // Gauss-Jordan without pivoting (SPD blocks); tiny pivots -> that row/col becomes identity
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double p = M[k][k];
+    if (!(fabs(p) > 1e-14 * scale) || scale == 0.0) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) M[k][j] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) M[i][k] = 0.0;
+      M[k][k] = 1.0; M[k][6 + k] = 1.0;
+      p = 1.0;
+    }
+    const double ip = 1.0 / p;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) M[k][j] *= ip;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i == k) continue;
+      const double f = M[i][k];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) M[i][j] = fma(-f, M[k][j], M[i][j]);
+    }
+  }
+  double* o = Dinv + (size_t)r * 36;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[i * 6 + j] = M[i][6 + j];
+}
+
+// P[s] = own(s) T~_i - omega * Dinv_i * sum_k A[a_k] T~_{j_k},  T~ = (Lt) T;  thread per P block
+__global__ void __launch_bounds__(128)
+mg_smooth_prolongator_kernel(int nnz_p, const int32_t* __restrict__ p_row, const int32_t* __restrict__ p_col,
+                             const int32_t* __restrict__ p_own, const int32_t* __restrict__ ps_ptr,
+                             const int32_t* __restrict__ ps_a, const int32_t* __restrict__ ps_j,
+                             const int32_t* __restrict__ agg, const double* __restrict__ A,
+                             const double* __restrict__ Dinv /* row-major or null */,
+                             const double* __restrict__ Lfac /* row-major L per node or null */,
+                             const uint8_t* __restrict__ mask, const double* __restrict__ X,
+                             const double* __restrict__ Xc, double omega, double* __restrict__ P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz_p) return;
+  const int i = p_row[s];
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  for (int k = ps_ptr[s]; k < ps_ptr[s + 1]; ++k) {
+    const int j = ps_j[k];
+    double T[36];
+    rigid_block(X, Xc, j, agg[j], mask ? mask[j] : 0u, Lfac ? Lfac + (size_t)j * 36 : nullptr, T);
+    blk_mma(A + (size_t)ps_a[k] * 36, T, acc);
+  }
+  double out[36];
+  if (p_own[s]) rigid_block(X, Xc, i, agg[i], mask ? mask[i] : 0u, Lfac ? Lfac + (size_t)i * 36 : nullptr, out);
+  else {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) out[k] = 0.0;
+  }
+  if (Dinv) {
+    const double* di = Dinv + (size_t)i * 36;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t += di[r * 6 + k] * acc[6 * c + k];
+        out[6 * c + r] -= omega * t;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) out[k] -= omega * acc[k];
+  }
+  double* o = P + (size_t)s * 36;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) o[k] = out[k];
+}
+
+// out[s] = sum_k op(L[l_k]) * R[r_k]   (TRANS: op = transpose); thread per output block
+template <int TRANS>
+__global__ void __launch_bounds__(128)
+mg_block_product_kernel(int nnz_out, const int32_t* __restrict__ ptr, const int32_t* __restrict__ li,
+                        const int32_t* __restrict__ ri, const double* __restrict__ Lv,
+                        const double* __restrict__ Rv, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz_out) return;
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  for (int k = ptr[s]; k < ptr[s + 1]; ++k) {
+    if (TRANS) blk_mma_t(Lv + (size_t)li[k] * 36, Rv + (size_t)ri[k] * 36, acc);
+    else blk_mma(Lv + (size_t)li[k] * 36, Rv + (size_t)ri[k] * 36, acc);
+  }
+  double* o = out + (size_t)s * 36;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) o[k] = acc[k];
+}
+
+// Pt[s] = P[src[s]]^T
+__global__ void mg_transpose_blocks_kernel(int nnz, const int32_t* __restrict__ src, const double* __restrict__ P,
+                                           double* __restrict__ Pt) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 36LL * nnz) return;
+  const int s = (int)(t / 36), k = (int)(t % 36);
+  const int r = k % 6, c = k / 6;
+  Pt[t] = P[(size_t)src[s] * 36 + 6 * r + c];
+}
+
+// Chebyshev smoother step on D^-1 A, thread per node:
+//   r <- Dinv r (if Dinv);  FIRST: d = r / theta, x = zero_guess ? d : x + d
+//                           else : d = c1 d + c2 r, x += d
+template <int FIRST>
+__global__ void __launch_bounds__(128)
+mg_cheb_kernel(int n, const double* __restrict__ Dinv, const double* __restrict__ r, double* __restrict__ d,
+               double* __restrict__ x, double c1, double c2, int zero_guess) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rv[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) rv[k] = r[6 * (size_t)i + k];
+  if (Dinv) {
+    const double* di = Dinv + (size_t)i * 36;
+    double t[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += di[a * 6 + k] * rv[k];
+      t[a] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rv[k] = t[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const size_t o = 6 * (size_t)i + k;
+    double dv;
+    if (FIRST) dv = rv[k] * c2;   // c2 = 1 / theta
+    else dv = c1 * d[o] + c2 * rv[k];
+    d[o] = dv;
+    x[o] = (FIRST && zero_guess) ? dv : x[o] + dv;
+  }
+}
+
+// ---- coarsest level: dense inverse (n <= a few hundred), one CTA, matrix in global memory
+__global__ void mg_dense_from_bsr_kernel(int n_node, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                                         double* __restrict__ M /* (6n) x (12n) row-major: [A | I] */) {
+  const int n = 6 * n_node;
+  const long long total = (long long)n * 2 * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / (2 * n)), c = (int)(t % (2 * n));
+    M[t] = (c >= n && c - n == r) ? 1.0 : 0.0;
+  }
+}
+__global__ void mg_dense_fill_kernel(int n_node, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                     const double* __restrict__ vals, double* __restrict__ M) {
+  const int n = 6 * n_node;
+  const int br = blockIdx.x;
+  for (int s = rowptr[br]; s < rowptr[br + 1]; ++s) {
+    const int bc = colidx[s];
+    for (int k = threadIdx.x; k < 36; k += blockDim.x) {
+      const int i = k % 6, j = k / 6;
+      M[(size_t)(6 * br + i) * 2 * n + 6 * bc + j] = vals[(size_t)s * 36 + k];
+    }
+  }
+}
+// Gauss-Jordan on [A | I] without pivoting (A SPD; empty rows -> identity); one CTA
+__global__ void __launch_bounds__(1024)
+mg_dense_invert_kernel(int n, double* __restrict__ M) {
+  __shared__ double piv;
+  const int w = 2 * n;
+  for (int k = 0; k < n; ++k) {
+    if (threadIdx.x == 0) {
+      double p = M[(size_t)k * w + k];
+      if (!(fabs(p) > 1e-300)) { p = 1.0; M[(size_t)k * w + k] = 1.0; }
+      piv = 1.0 / p;
+    }
+    __syncthreads();
+    const double ip = piv;
+    for (int j = threadIdx.x; j < w; j += blockDim.x) M[(size_t)k * w + j] *= ip;
+    __syncthreads();
+    // eliminate column k from all other rows: thread handles (row i, column chunk)
+    for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5) {
+      if (i == k) continue;
+      const double f = M[(size_t)i * w + k];
+      if (f == 0.0) continue;
+      for (int j = (threadIdx.x & 31); j < w; j += 32)
+        if (j != k) M[(size_t)i * w + j] = fma(-f, M[(size_t)k * w + j], M[(size_t)i * w + j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (i != k) M[(size_t)i * w + k] = 0.0;
+    __syncthreads();
+  }
+}
+// x = Ainv b with Ainv = right half of M; one warp per row
+__global__ void mg_dense_matvec_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
+                                       double* __restrict__ x) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* a = M + (size_t)row * 2 * n + n;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s = fma(a[j], b[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) x[row] = s;
+}
+
+// ---- small vector kernels of the host-driven outer PCG
+// out[0] = a.b (deterministic two-stage); n entries
+__global__ void __launch_bounds__(256)
+mg_dot_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b, double* partials,
+              unsigned* counter, double* out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fma(a[i], b[i], acc);
+  double total;
+  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) *out = total;
+}
+// y = a*x + b*y
+__global__ void mg_axpby_kernel(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + b * y[i];
+}
+__global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = v;
+}
+
+}  // namespace jsso

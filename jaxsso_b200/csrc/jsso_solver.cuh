@@ -237,6 +237,33 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   }
 }
 
+// MODE 0: y = A x;  2: y = b - A x;  3: y += A x   (any 6x6 block-CSR, also rectangular)
+template <int MODE>
+__global__ void __launch_bounds__(RED_BLOCK)
+bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                      const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                      const double* __restrict__ bvec) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warp = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_row; r += n_warp) {
+    double u0, u1;
+    bsr_row_product(r, lane, rowptr, colidx, vals, x, u0, u1);
+    if (lane < 3) {
+      double2* yp = (double2*)(y + 6 * (size_t)r + 2 * lane);
+      if (MODE == 2) {
+        const double2 bv = *(const double2*)(bvec + 6 * (size_t)r + 2 * lane);
+        *yp = make_double2(bv.x - u0, bv.y - u1);
+      } else if (MODE == 3) {
+        const double2 yv = *yp;
+        *yp = make_double2(yv.x + u0, yv.y + u1);
+      } else {
+        *yp = make_double2(u0, u1);
+      }
+    }
+  }
+}
+
 // push this rank's interface entries of `v` into the neighbours' ghost slots, then raise the flags
 __global__ void __launch_bounds__(RED_BLOCK)
 p2p_halo_push_kernel(const P2PCtx* c, const int32_t* __restrict__ send_idx, const double* __restrict__ v,
@@ -350,7 +377,7 @@ cg_persistent_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_
 // W_r = L_r^-1 (lower triangular, stored dense row-major 6x6) from the diagonal blocks.
 __global__ void __launch_bounds__(128)
 diag_factor_kernel(int n_row, const int32_t* __restrict__ diag_slot, const double* __restrict__ vals,
-                   double* __restrict__ W, int* flags) {
+                   double* __restrict__ W, double* __restrict__ Lout /* optional: L row-major */, int* flags) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_row) return;
   const double* d = vals + (size_t)diag_slot[r] * 36;
@@ -373,6 +400,13 @@ diag_factor_kernel(int n_row, const int32_t* __restrict__ diag_slot, const doubl
     }
   }
   if (!ok) atomicOr(flags, 8);
+  if (Lout) {
+    double* lo = Lout + (size_t)r * 36;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) lo[i * 6 + j] = (j <= i) ? L[i][j] : 0.0;
+  }
   // invert L (forward substitution on identity)
   double Wl[6][6];
 #pragma unroll

@@ -1,0 +1,148 @@
+"""Smoothed-aggregation multigrid: (CPU) the symbolic gather lists reproduce SciPy's sparse
+products; (GPU) the multigrid-preconditioned solve returns the same u as the oracle in a
+mesh-independent number of iterations."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from jaxsso_b200 import meshes, multigrid as mg
+from oracle import jaxsso_oracle as orc
+from tests.conftest import to_oracle_mesh
+
+
+def scaled_system(md):
+    """Block-Jacobi-scaled BC-imposed matrix A^ = W K W^T (what the GPU multigrid sees)."""
+    K = orc.K_global(to_oracle_mesh(md)).tocsr()
+    mask = np.zeros(md.ndof, bool)
+    mask[md.known] = True
+    Dm = sp.diags((~mask).astype(float))
+    K = (Dm @ K @ Dm + sp.diags(mask.astype(float))).tocsr()
+    n = md.n_node
+    Kb = K.tobsr((6, 6))
+    Kb.sort_indices()
+    D = np.zeros((n, 6, 6))
+    for i in range(n):
+        for k in range(Kb.indptr[i], Kb.indptr[i + 1]):
+            if Kb.indices[k] == i:
+                D[i] = Kb.data[k]
+    L = np.linalg.cholesky(0.5 * (D + D.transpose(0, 2, 1)))
+    W = sp.bsr_matrix((np.linalg.inv(L), np.arange(n), np.arange(n + 1)), shape=K.shape)
+    Ah = (W @ K @ W.T).tobsr((6, 6))
+    Ah.sort_indices()
+    return Ah, L, mask.reshape(-1, 6)
+
+
+def test_aggregation_covers_all_nodes():
+    md = meshes.plate(12)
+    Ah, _, _ = scaled_system(md)
+    agg, na = mg.aggregate(Ah.indptr, Ah.indices)
+    assert agg.min() == 0 and agg.max() == na - 1 and np.unique(agg).shape[0] == na
+    assert na < md.n_node / 4
+
+
+@pytest.mark.parametrize('case', ['plate', 'gridshell'])
+def test_gather_lists_reproduce_sparse_products(case):
+    md = meshes.plate(10) if case == 'plate' else meshes.gridshell(12, 0)
+    Ah, L, mask = scaled_system(md)
+    levels = mg.build_hierarchy(Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32), max_coarse_nodes=8)
+    assert len(levels) >= 2
+    ref, Ac_last = mg.reference_setup(Ah.data, Ah.indptr, Ah.indices, md.crds, mask, levels, Lt0=L.transpose(0, 2, 1))
+    A_blocks = Ah.data                       # (nnzb, 6, 6) [row, col]
+    X, mk, Lt = md.crds, mask, L.transpose(0, 2, 1)
+    for l, lv in enumerate(levels):
+        R = ref[l]
+        n = lv['n_f']
+        cent = mg.centroids(X, lv)
+        T = mg.rigid_blocks(X, cent, lv['agg'], mk)
+        if Lt is not None:
+            T = np.einsum('nij,njk->nik', Lt, T)
+        omega = 4.0 / (3.0 * R.lam)
+        prow = np.repeat(np.arange(n), np.diff(lv['p_rowptr']))
+        # smoothing lists
+        P = np.zeros((lv['nnz_p'], 6, 6))
+        for s in range(lv['nnz_p']):
+            acc = np.zeros((6, 6))
+            for k in range(lv['ps_ptr'][s], lv['ps_ptr'][s + 1]):
+                acc += A_blocks[lv['ps_a'][k]] @ T[lv['ps_j'][k]]
+            P[s] = (T[prow[s]] if lv['p_own'][s] else 0.0) - omega * R.Dinv[prow[s]] @ acc
+        Pref = R.P.tobsr((6, 6))
+        Pl = sp.bsr_matrix((P, lv['p_col'], lv['p_rowptr']), shape=Pref.shape)
+        assert abs(Pl - Pref).max() <= 1e-12 * abs(Pref).max()
+        # AP and Ac lists
+        AP = np.zeros((lv['nnz_ap'], 6, 6))
+        for s in range(lv['nnz_ap']):
+            for k in range(lv['apl_ptr'][s], lv['apl_ptr'][s + 1]):
+                AP[s] += A_blocks[lv['apl_a'][k]] @ P[lv['apl_p'][k]]
+        APl = sp.bsr_matrix((AP, lv['ap_col'], lv['ap_rowptr']), shape=Pref.shape)
+        APref = R.A @ R.P
+        assert abs(APl - APref).max() <= 1e-12 * abs(APref).max()
+        Ac = np.zeros((lv['nnz_c'], 6, 6))
+        for s in range(lv['nnz_c']):
+            for k in range(lv['cl_ptr'][s], lv['cl_ptr'][s + 1]):
+                Ac[s] += P[lv['cl_p'][k]].T @ AP[lv['cl_ap'][k]]
+        Acl = sp.bsr_matrix((Ac, lv['c_col'], lv['c_rowptr']), shape=(6 * lv['n_c'],) * 2)
+        Acref = ref[l + 1].A if l + 1 < len(levels) else Ac_last
+        assert abs(Acl - Acref).max() <= 1e-11 * abs(Acref).max()
+        # transpose map and diagonal slots
+        Pt = P[lv['pt_src']].transpose(0, 2, 1)
+        Ptl = sp.bsr_matrix((Pt, lv['pt_col'], lv['pt_rowptr']), shape=(Pref.shape[1], Pref.shape[0]))
+        assert abs(Ptl - Pref.T).max() <= 1e-12 * abs(Pref).max()
+        crow = np.repeat(np.arange(lv['n_c']), np.diff(lv['c_rowptr']))
+        assert np.array_equal(lv['c_col'][lv['c_diag']], np.arange(lv['n_c']))
+        assert np.array_equal(crow[lv['c_diag']], np.arange(lv['n_c']))
+        A_blocks, X, mk, Lt = Ac, cent, None, None
+
+
+def test_reference_vcycle_is_a_good_preconditioner():
+    md = meshes.plate(24)
+    Ah, L, mask = scaled_system(md)
+    levels = mg.build_hierarchy(Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32), max_coarse_nodes=100)
+    ref, Ac = mg.reference_setup(Ah.data, Ah.indptr, Ah.indices, md.crds, mask, levels, Lt0=L.transpose(0, 2, 1))
+    Ainv = np.linalg.inv(Ac.toarray())
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(Ah.shape[0])
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = mg.reference_vcycle(ref, Ainv, r)
+    p = z.copy()
+    rz = r @ z
+    for it in range(200):
+        q = Ah @ p
+        a = rz / (p @ q)
+        x += a * p
+        r -= a * q
+        if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b):
+            break
+        z = mg.reference_vcycle(ref, Ainv, r)
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+    assert it < 60
+
+
+# ------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['plate48', 'gridshell40', 'mannheim', 'mixed'])
+def test_multigrid_solve_matches_oracle(case, mannheim_data):
+    from jaxsso_b200 import _native as nat
+    if case == 'mixed':
+        md = meshes.plate(24)
+        nid = np.arange(md.n_node).reshape(25, 25)
+        md.cnct_beams = np.stack([nid[12, :-1], nid[12, 1:]], 1).astype(np.int32)
+        md.prop_beams = np.tile([3.79e9, 3.79e9 / 2.6, 6.7e-5, 1.7e-5, 8.4e-5, 0.02], (24, 1))
+    else:
+        md = {'plate48': lambda: meshes.plate(48), 'gridshell40': lambda: meshes.gridshell(40, 0),
+              'mannheim': lambda: meshes.mannheim_quad(mannheim_data)}[case]()
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    h.mg_setup(max_coarse_nodes=100)
+    D = nat.DeviceArray
+    crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
+    u = D((md.ndof,))
+    rtol = 1e-10
+    st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond='multigrid'))
+    uref = orc.solve_refined(to_oracle_mesh(md))
+    assert st.converged and st.relres <= 1.5 * rtol
+    assert np.linalg.norm(u.download() - uref) / np.linalg.norm(uref) <= 1e-8
+    st_bj = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond='block_jacobi'))
+    assert st.iterations < st_bj.iterations / 4
+    if case == 'plate48':
+        assert st.iterations <= 70
