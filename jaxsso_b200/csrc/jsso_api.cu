@@ -757,26 +757,28 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       mg_diag_inverse_kernel<<<cdiv(n, 128), 128, 0, st>>>(n, h->mg[l - 1].c_diag, A.v, m.Dinv);
       CKL("mg_diag_inverse_kernel");
     }
-    // lambda_max(D^-1 A) by power iteration from the constant vector (12 steps, x1.1 safety)
+    // lambda_max(D^-1 A): power iteration from a pseudo-random vector (30 steps, x1.15 safety); an
+    // underestimate would make the Chebyshev smoother amplify the top modes and the V-cycle indefinite
     const long long nd = 6LL * n;
     const int vb = std::max(1, std::min(h->red_blocks, cdiv(nd, 256)));
-    mg_fill_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / std::sqrt((double)nd), m.r);
-    CKL("mg_fill_kernel");
+    mg_hash_fill_kernel<<<vb, 256, 0, st>>>(nd, m.r);
+    CKL("mg_hash_fill_kernel");
     double lam = 1.0;
-    for (int it = 0; it < 12; ++it) {
+    for (int it = 0; it < 30; ++it) {
       if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n, m.r, m.d, nullptr, st))) return rc;
       if (m.Dinv) {
         block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
         CKL("block_apply_kernel<0>");
       }
       if ((rc = mg_dot(h, nd, m.d, m.d, 0, st))) return rc;
+      if ((rc = mg_dot(h, nd, m.r, m.r, 5, st))) return rc;
       if ((rc = mg_read_scalars(h, st))) return rc;
-      lam = std::sqrt(h->mg_scal_host[0]);
+      lam = std::sqrt(h->mg_scal_host[0] / h->mg_scal_host[5]);
       if (!(lam > 0.0) || !(lam == lam)) return fail(h, JSSO_ERR_NAN, "multigrid: power iteration broke down");
-      mg_axpby_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / lam, m.d, 0.0, m.r);
+      mg_axpby_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / std::sqrt(h->mg_scal_host[0]), m.d, 0.0, m.r);
       CKL("mg_axpby_kernel");
     }
-    m.lam = 1.1 * lam;
+    m.lam = 1.15 * lam;
     mg_centroid_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.mem_ptr, m.mem, X, m.Xc);
     CKL("mg_centroid_kernel");
     mg_smooth_prolongator_kernel<<<cdiv(m.nnz_p, 128), 128, 0, st>>>(
@@ -880,7 +882,12 @@ static int mg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
     if ((rc = mg_dot(h, n, r, z, 3, st))) return rc;
     if ((rc = mg_read_scalars(h, st))) return rc;
     const double rz_new = h->mg_scal_host[3];
-    if (!(rz_new > 0.0)) return fail(h, JSSO_ERR_NAN, "multigrid PCG breakdown: r.z <= 0 (preconditioner not SPD?)");
+    if (!(rz_new > 0.0)) {
+      char buf[200];
+      std::snprintf(buf, sizeof buf, "multigrid PCG breakdown at iteration %d: r.z = %.3e (lam0 = %.3f)", it, rz_new,
+                    h->mg.empty() ? 0.0 : h->mg[0].lam);
+      return fail(h, JSSO_ERR_NAN, buf);
+    }
     if (it == 0) { CK(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st)); }
     else { mg_axpby_kernel<<<vb, 256, 0, st>>>(n, 1.0, z, rz_new / rz, p); CKL("mg_axpby_kernel"); }
     rz = rz_new;

@@ -344,5 +344,16 @@ __global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = v;
 }
+// deterministic pseudo-random start vector in (-1, 1) (integer hash of the index): a constant vector
+// is nearly orthogonal to the top of the spectrum on large meshes and the power iteration stalls
+__global__ void mg_hash_fill_kernel(long long n, double* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = (unsigned long long)i + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    y[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+  }
+}
 
 }  // namespace jsso

@@ -162,7 +162,7 @@ class RefLevel:
     pass
 
 
-def reference_setup(A0_bsr_blocks, rowptr, colidx, X0, mask_nodes, levels, Lt0=None, n_power=12):
+def reference_setup(A0_bsr_blocks, rowptr, colidx, X0, mask_nodes, levels, Lt0=None, n_power=30):
     """SciPy reference of the numeric setup.  A0 blocks are (nnzb,6,6) [row, col]-oriented.
     ``Lt0``: optional (n,6,6) left factors applied to T at level 0 (L_i^T when the fine matrix is
     the block-Jacobi-scaled one).  Returns a list of RefLevel (A, Dinv, lam, P) + coarsest A."""
@@ -183,13 +183,14 @@ def reference_setup(A0_bsr_blocks, rowptr, colidx, X0, mask_nodes, levels, Lt0=N
         D[bad] = np.eye(6)
         R.Dinv = np.linalg.inv(D)
         Dinv_sp = sp.bsr_matrix((R.Dinv, np.arange(n), np.arange(n + 1)), shape=A.shape)
-        v = np.ones(6 * n) / np.sqrt(6 * n)     # same deterministic start vector as the GPU path
+        v = np.random.default_rng(0).uniform(-1, 1, 6 * n)
+        v /= np.linalg.norm(v)
         lam = 1.0
         for _ in range(n_power):
             w = Dinv_sp @ (A @ v)
             lam = np.linalg.norm(w)
             v = w / lam
-        R.lam = 1.1 * lam
+        R.lam = 1.15 * lam
         cent = centroids(X, lv)
         T = rigid_blocks(X, cent, lv['agg'], mk)
         if Lt is not None:
