@@ -29,6 +29,7 @@ class Model:
         self.device = device
         self._handle = None
         self._topology_key = None
+        self.multigrid_min_nodes = 20000
         self.last_stats = None
 
     # ---- building (reference: model.py:56-214) ------------------------------------
@@ -80,6 +81,10 @@ class Model:
                 self._handle.close()
             self._handle = nat.Handle(self.crds.shape[0], self.cnct_quads, self.cnct_beamcols,
                                       np.unique(self.known_id), device=self.device)
+            # larger models get the smoothed-aggregation multigrid hierarchy (symbolic, once); the
+            # solver picks it automatically from 20 000 nodes on, block-Jacobi CG below
+            if self.crds.shape[0] >= self.multigrid_min_nodes:
+                self._handle.mg_setup()
             self._topology_key = key
 
     @property

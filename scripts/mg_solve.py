@@ -17,3 +17,10 @@ for rep in range(2):
         print('rep', rep, 'forward %.3fs' % (time.perf_counter() - t0), st.as_dict(), flush=True)
     except Exception as e:
         print('ERR', e); break
+# setup cost: one iteration only
+t0 = time.perf_counter()
+try:
+    h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=1e-8, precond='multigrid', cheb_degree=deg, maxiter=1))
+except Exception as e:
+    pass
+print('assemble + scaling + numeric mg setup + 1 iteration: %.3fs' % (time.perf_counter() - t0), flush=True)
