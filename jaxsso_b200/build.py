@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ['-Xptxas', '-v']
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ['-o', LIB, '-lnccl', '-lcudart']
+    cmd += ['-o', LIB, '-lcudart', '-ldl']   # NCCL is bound lazily with dlopen (see jsso_api.cu)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

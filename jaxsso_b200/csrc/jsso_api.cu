@@ -2,6 +2,7 @@
 #include "../../include/jsso.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <atomic>
@@ -18,6 +19,46 @@
 #include "jsso_symbolic.h"
 
 using namespace jsso;
+
+// NCCL is bound lazily with dlopen/dlsym instead of a link-time dependency: a process that also
+// imports PyTorch must end up with ONE libnccl.so.2 (PyTorch bundles a newer one than the system's;
+// whichever is loaded first wins, and a link-time dependency here would break `import torch`
+// after this library).  RTLD_NOLOAD first => reuse the copy that is already in the process.
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+  if (g_nccl.ok) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return false;
+  auto sym = [&](const char* n) { return dlsym(lib, n); };
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+  g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.GroupStart &&
+              g_nccl.GroupEnd && g_nccl.Send && g_nccl.Recv && g_nccl.AllReduce && g_nccl.GetErrorString;
+  return g_nccl.ok;
+}
+}  // namespace
 
 static std::atomic<long long> g_launches{0};
 static thread_local std::string g_create_error;
@@ -118,7 +159,7 @@ static int fail(jsso_handle* h, int code, const std::string& msg) {
   do {                                                                                        \
     ncclResult_t r_ = (call);                                                                 \
     if (r_ != ncclSuccess)                                                                    \
-      return fail(h, JSSO_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));      \
+      return fail(h, JSSO_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));  \
   } while (0)
 
 template <class T>
@@ -220,7 +261,7 @@ void jsso_destroy(jsso_handle* h) {
                  h->h_dpb};
   for (void* p : hst) if (p) cudaFreeHost(p);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-  if (h->comm) ncclCommDestroy(h->comm);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   delete h;
 }
 
@@ -331,7 +372,8 @@ int jsso_nccl_unique_id(uint8_t id_out[128]) {
   jsso_handle* h = nullptr;
   ncclUniqueId id;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
-  CKN(ncclGetUniqueId(&id));
+  if (!nccl_load()) return fail(h, JSSO_ERR_NCCL, "libnccl.so.2 not found");
+  CKN(g_nccl.GetUniqueId(&id));
   std::memcpy(id_out, &id, 128);
   return JSSO_OK;
 }
@@ -353,9 +395,10 @@ int jsso_set_halo(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int3
   CK(upload(&h->send_idx, si));
   CK(dalloc(&h->send_buf, (size_t)h->n_send_nodes * 36));
   if (n_rank > 1) {
+    if (!nccl_load()) return fail(h, JSSO_ERR_NCCL, "libnccl.so.2 not found");
     ncclUniqueId id;
     std::memcpy(&id, nccl_id, 128);
-    CKN(ncclCommInitRank(&h->comm, n_rank, id, rank));
+    CKN(g_nccl.CommInitRank(&h->comm, n_rank, id, rank));
   }
   return JSSO_OK;
 }
@@ -370,14 +413,14 @@ static int halo_exchange_w(jsso_handle* h, double* vec, int width, cudaStream_t 
                                                                       h->send_buf);
     CKL("halo_pack_kernel");
   }
-  CKN(ncclGroupStart());
+  CKN(g_nccl.GroupStart());
   for (const HaloPeer& p : h->peers) {
     if (p.send_cnt)
-      CKN(ncclSend(h->send_buf + 6 * (size_t)p.send_off, 6 * (size_t)p.send_cnt, ncclDouble, p.rank, h->comm, st));
+      CKN(g_nccl.Send(h->send_buf + 6 * (size_t)p.send_off, 6 * (size_t)p.send_cnt, ncclDouble, p.rank, h->comm, st));
     if (p.recv_cnt)
-      CKN(ncclRecv(vec + 6 * (size_t)p.recv_start, 6 * (size_t)p.recv_cnt, ncclDouble, p.rank, h->comm, st));
+      CKN(g_nccl.Recv(vec + 6 * (size_t)p.recv_start, 6 * (size_t)p.recv_cnt, ncclDouble, p.rank, h->comm, st));
   }
-  CKN(ncclGroupEnd());
+  CKN(g_nccl.GroupEnd());
   return JSSO_OK;
 }
 
@@ -442,7 +485,7 @@ int jsso_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* 
 
 static int allreduce_scalar(jsso_handle* h, const double* local, double* global, cudaStream_t st) {
   if (h->n_rank <= 1) return JSSO_OK;
-  CKN(ncclAllReduce(local, global, 1, ncclDouble, ncclSum, h->comm, st));
+  CKN(g_nccl.AllReduce(local, global, 1, ncclDouble, ncclSum, h->comm, st));
   return JSSO_OK;
 }
 
