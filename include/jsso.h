@@ -113,6 +113,13 @@ typedef struct {
 
 /* ---- lifetime ---------------------------------------------------------------- */
 int jsso_create(const jsso_mesh_desc* desc, jsso_handle** out);
+/* Solver-plugin compatibility mode: the reference's solver callables take an assembled matrix
+ * (model.py:340-356, solver.py:75/103/177).  Create a handle over a given 6x6 block-CSR pattern
+ * (sorted columns, diagonal blocks present), then supply values (blocks column-major, no BCs yet)
+ * and use jsso_pcg / jsso_spmv as usual.  No element kernels on such a handle. */
+int jsso_create_from_bsr(int32_t n_node, const int32_t* rowptr_h, const int32_t* colidx_h, int32_t n_known,
+                         const int32_t* known_h, int32_t device, jsso_handle** out);
+int jsso_set_values_host(jsso_handle* h, const double* vals_h, int apply_bc);
 void jsso_destroy(jsso_handle* h);
 const char* jsso_last_error(const jsso_handle* h); /* h may be NULL: last create error */
 int jsso_get_sizes(const jsso_handle* h, jsso_sizes* out);

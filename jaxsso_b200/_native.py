@@ -64,7 +64,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['jsso_create', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
+SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
@@ -87,6 +87,8 @@ def lib():
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.jsso_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(vp)]
+    L.jsso_create_from_bsr.argtypes = [i32, vp, vp, i32, vp, i32, C.POINTER(vp)]
+    L.jsso_set_values_host.argtypes = [vp, vp, C.c_int]
     L.jsso_destroy.argtypes = [vp]
     L.jsso_destroy.restype = None
     L.jsso_last_error.argtypes = [vp]
@@ -255,6 +257,33 @@ class Handle:
         self.n_node, self.n_row, self.n_quad, self.n_beam = s.n_node, s.n_row, s.n_quad, s.n_beam
         self.nnzb, self.n_items, self.n_chunk = s.nnzb, s.n_items, s.n_chunk
         self.device = device
+
+    @classmethod
+    def from_bsr(cls, rowptr, colidx, known=None, device=0):
+        """Pattern-only handle (solver-plugin compatibility mode): values come from set_values."""
+        L = lib()
+        self = cls.__new__(cls)
+        rp = np.ascontiguousarray(rowptr, np.int32)
+        ci = np.ascontiguousarray(colidx, np.int32)
+        kn = np.ascontiguousarray(np.zeros(0) if known is None else known, dtype=np.int32).ravel()
+        h = C.c_void_p()
+        rc = L.jsso_create_from_bsr(rp.shape[0] - 1, _ptr(rp), _ptr(ci), kn.shape[0], _ptr(kn), int(device), C.byref(h))
+        if rc:
+            raise JssoError(rc, L.jsso_last_error(None).decode())
+        self.h = h
+        s = Sizes()
+        L.jsso_get_sizes(self.h, C.byref(s))
+        self.sizes = s
+        self.n_node, self.n_row, self.n_quad, self.n_beam = s.n_node, s.n_row, s.n_quad, s.n_beam
+        self.nnzb, self.n_items, self.n_chunk = s.nnzb, s.n_items, s.n_chunk
+        self.device = device
+        return self
+
+    def set_values(self, blocks, apply_bc=True):
+        """blocks: (nnzb, 6, 6) in [row, col] orientation, without boundary conditions."""
+        v = np.ascontiguousarray(np.asarray(blocks, np.float64).transpose(0, 2, 1))   # -> column-major blocks
+        assert v.shape == (self.nnzb, 6, 6)
+        self._ck(lib().jsso_set_values_host(self.h, _ptr(v), int(apply_bc)))
 
     def _ck(self, rc, allow=()):
         if rc and rc not in allow:

@@ -94,6 +94,7 @@ struct jsso_handle {
   int* flags = nullptr;
   int* flags_host = nullptr;     // pinned
   bool assembled = false, assembled_bc = false, scaled = false;
+  bool pattern_only = false;     // created by jsso_create_from_bsr: no element kernels
   int red_blocks = 148 * 4;
   int spmv_blocks = 148 * 8;
   int coop_blocks = 0;          // max co-resident blocks of cg_persistent_kernel (0: unsupported)
@@ -182,31 +183,9 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
       return fail(h, JSSO_ERR_STATE, "symbolic-only handle (device = JSSO_DEVICE_NONE): no compute"); \
   } while (0)
 
-extern "C" {
-
-const char* jsso_last_error(const jsso_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
-
-int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
-  jsso_handle* h = nullptr;
-  if (!d || !out) return fail(h, JSSO_ERR_ARG, "null argument");
-  *out = nullptr;
-  int ndev = 0;
-  if (d->device != JSSO_DEVICE_NONE) {
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-      return fail(h, JSSO_ERR_CUDA, "no CUDA device: the jaxsso_b200 hot path has no CPU fallback");
-    if (d->device < 0 || d->device >= ndev) return fail(h, JSSO_ERR_ARG, "bad device ordinal");
-  }
-  jsso_handle* nh = new jsso_handle();
-  nh->device = d->device;
-  std::string msg = build_symbolic(d->n_node, d->n_row, d->n_quad, d->cnct_quads, d->n_beam, d->cnct_beams,
-                                   d->n_known, d->known, nh->sym);
-  if (!msg.empty()) { delete nh; return fail(h, JSSO_ERR_ARG, msg); }
-  h = nh;
-  if (d->device == JSSO_DEVICE_NONE) { *out = h; return JSSO_OK; }   // symbolic-only handle
+static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const std::vector<int32_t>& cb) {
   const Symbolic& S = h->sym;
   CK(cudaSetDevice(h->device));
-  std::vector<int32_t> cq(d->cnct_quads, d->cnct_quads + 4 * (size_t)d->n_quad);
-  std::vector<int32_t> cb(d->cnct_beams, d->cnct_beams + 2 * (size_t)d->n_beam);
   CK(upload(&h->cnct_q, cq)); CK(upload(&h->cnct_b, cb));
   CK(upload(&h->rowptr, S.rowptr)); CK(upload(&h->colidx, S.colidx));
   CK(upload(&h->blk_row, S.blk_row)); CK(upload(&h->diag_slot, S.diag_slot));
@@ -242,7 +221,72 @@ int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
   }
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
+  return JSSO_OK;
+}
+
+extern "C" {
+
+const char* jsso_last_error(const jsso_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int jsso_create(const jsso_mesh_desc* d, jsso_handle** out) {
+  jsso_handle* h = nullptr;
+  if (!d || !out) return fail(h, JSSO_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (d->device != JSSO_DEVICE_NONE) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(h, JSSO_ERR_CUDA, "no CUDA device: the jaxsso_b200 hot path has no CPU fallback");
+    if (d->device < 0 || d->device >= ndev) return fail(h, JSSO_ERR_ARG, "bad device ordinal");
+  }
+  jsso_handle* nh = new jsso_handle();
+  nh->device = d->device;
+  std::string msg = build_symbolic(d->n_node, d->n_row, d->n_quad, d->cnct_quads, d->n_beam, d->cnct_beams,
+                                   d->n_known, d->known, nh->sym);
+  if (!msg.empty()) { delete nh; return fail(h, JSSO_ERR_ARG, msg); }
+  h = nh;
+  if (d->device == JSSO_DEVICE_NONE) { *out = h; return JSSO_OK; }   // symbolic-only handle
+  std::vector<int32_t> cq(d->cnct_quads, d->cnct_quads + 4 * (size_t)d->n_quad);
+  std::vector<int32_t> cb(d->cnct_beams, d->cnct_beams + 2 * (size_t)d->n_beam);
+  { int rc_ = handle_upload(h, cq, cb); if (rc_) return rc_; }
   *out = h;
+  return JSSO_OK;
+}
+
+// Solver-plugin compatibility mode: a handle over a GIVEN 6x6 block-CSR pattern,
+// values supplied by the caller (e.g. the reference's own K after sort_indices + sum_duplicates).
+int jsso_create_from_bsr(int32_t n_node, const int32_t* rowptr, const int32_t* colidx, int32_t n_known,
+                         const int32_t* known, int32_t device, jsso_handle** out) {
+  jsso_handle* h = nullptr;
+  if (!rowptr || !colidx || !out) return fail(h, JSSO_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, JSSO_ERR_CUDA, "no CUDA device: the jaxsso_b200 hot path has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(h, JSSO_ERR_ARG, "bad device ordinal");
+  jsso_handle* nh = new jsso_handle();
+  nh->device = device;
+  std::string msg = build_symbolic_from_bsr(n_node, rowptr, colidx, n_known, known, nh->sym);
+  if (!msg.empty()) { delete nh; return fail(h, JSSO_ERR_ARG, msg); }
+  h = nh;
+  h->pattern_only = true;
+  { int rc_ = handle_upload(h, std::vector<int32_t>(), std::vector<int32_t>()); if (rc_) return rc_; }
+  *out = h;
+  return JSSO_OK;
+}
+
+// vals_h: nnzb*36 doubles, blocks column-major, WITHOUT boundary conditions; apply_bc imposes them.
+int jsso_set_values_host(jsso_handle* h, const double* vals_h, int apply_bc) {
+  if (!h || !vals_h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  const long long n_out = (long long)h->sym.nnzb() * 36;
+  CK(cudaMemcpy(h->vals, vals_h, n_out * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemset(h->flags, 0, sizeof(int)));
+  if (apply_bc && n_out > 0) {
+    apply_bc_kernel<<<cdiv(n_out, 256), 256>>>(n_out, h->blk_row, h->colidx, h->node_mask, h->vals);
+    CKL("apply_bc_kernel");
+  }
+  h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
   return JSSO_OK;
 }
 

@@ -385,6 +385,17 @@ assemble_fused_kernel(AsmArgs A) {
   }
 }
 
+// Boundary conditions on an already assembled matrix (values given by the caller)
+__global__ void __launch_bounds__(256)
+apply_bc_kernel(long long n_out, const int32_t* __restrict__ blk_row, const int32_t* __restrict__ colidx,
+                const uint8_t* __restrict__ node_mask, double* __restrict__ vals) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const int blk = (int)(o / 36), k = (int)(o - (long long)blk * 36);
+  const int r = blk_row[blk], c = colidx[blk];
+  vals[o] = bc_entry(vals[o], node_mask[r], node_mask[c], k % 6, k / 6, r == c);
+}
+
 // Stand-alone numeric assembly: one thread per stored entry, contributors summed in
 // list order from the materialised element matrices.
 __global__ void __launch_bounds__(256)

@@ -152,4 +152,39 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cq,
   return "";
 }
 
+std::string build_symbolic_from_bsr(int n_node, const int32_t* rowptr, const int32_t* colidx, int n_known,
+                                    const int32_t* known, Symbolic& S) {
+  if (n_node <= 0 || !rowptr || rowptr[0] != 0) return "bad block-CSR pattern";
+  S = Symbolic();
+  S.n_node = n_node; S.n_row = n_node;
+  S.node_mask.assign(n_node, 0);
+  for (int i = 0; i < n_known; ++i) {
+    if (known[i] < 0 || known[i] >= 6 * n_node) return "known dof out of range";
+    S.node_mask[known[i] / 6] |= (uint8_t)(1u << (known[i] % 6));
+  }
+  S.rowptr.assign(rowptr, rowptr + n_node + 1);
+  const int64_t nnzb = rowptr[n_node];
+  S.colidx.assign(colidx, colidx + nnzb);
+  S.blk_row.resize(nnzb);
+  S.diag_slot.assign(n_node, -1);
+  for (int r = 0; r < n_node; ++r) {
+    if (rowptr[r + 1] < rowptr[r]) return "row pointers not monotone";
+    for (int s = rowptr[r]; s < rowptr[r + 1]; ++s) {
+      const int c = colidx[s];
+      if (c < 0 || c >= n_node) return "column index out of range";
+      if (s > rowptr[r] && colidx[s - 1] >= c) return "columns must be sorted and unique within a row";
+      S.blk_row[s] = r;
+      if (c == r) S.diag_slot[r] = s;
+    }
+    if (S.diag_slot[r] < 0) return "every block row needs its diagonal block";
+  }
+  S.blk_item_ptr.assign(nnzb + 1, 0);
+  S.blk_perm.resize(nnzb);
+  for (int64_t i = 0; i < nnzb; ++i) S.blk_perm[i] = (int32_t)i;
+  S.chunk_blk = {0, (int32_t)nnzb};
+  S.chunk_el_ptr = {0, 0};
+  S.node_inc_ptr.assign(n_node + 1, 0);
+  return "";
+}
+
 }  // namespace jsso

@@ -47,4 +47,9 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cnc
                            const int32_t* cnct_beams, int n_known, const int32_t* known,
                            Symbolic& out);
 
+// Pattern-only symbolic state (solver-plugin compatibility mode): the block-CSR pattern is given,
+// there are no element contributor lists.
+std::string build_symbolic_from_bsr(int n_node, const int32_t* rowptr, const int32_t* colidx, int n_known,
+                                    const int32_t* known, Symbolic& out);
+
 }  // namespace jsso

@@ -154,3 +154,25 @@ def test_warm_started_optimiser_steps():
         vals[warm] = (its, cs)
     assert np.allclose(vals[True][1], vals[False][1], rtol=1e-8)
     assert vals[True][0][1] < vals[False][0][1] and vals[True][0][2] < vals[False][0][2]
+
+
+def test_solver_plugin_on_reference_K_aug(golden):
+    """(K_aug, f_aug) -> u_aug with the reference's solver signature: the oracle's literal
+    augmented matrix (assemblemodel.py:111-163) goes in, u and the Lagrange multipliers come out."""
+    from jaxsso_b200 import solver
+    md = meshes.barrel_arch()
+    m = to_oracle_mesh(md)
+    K_aug = orc.K_aug(m)
+    f_aug = orc.f_aug(m)
+    u_aug = solver.b200_solve(K_aug, f_aug, rtol=1e-12)
+    ref = orc.solve_literal(m)
+    u_ref = orc.solve_refined(m)
+    assert u_aug.shape == ref.shape
+    assert np.linalg.norm(u_aug[:m.ndof] - u_ref) / np.linalg.norm(u_ref) < 1e-8
+    mu_ref = (md.loads - orc.K_global(m) @ u_ref)[md.known]
+    assert np.abs(u_aug[m.ndof:] - mu_ref).max() / np.abs(mu_ref).max() < 1e-7
+    assert abs(0.5 * f_aug[:m.ndof] @ u_aug[:m.ndof] - golden['shell_arch_strain_energy']['value']) / 1.2e6 < 1e-8
+    # CSR triple form, as the reference's pure_callback passes it (solver.py:202-209)
+    A = K_aug.tocsr()
+    u2 = solver.b200_solve((A.data, A.indices, A.indptr, A.shape), f_aug, rtol=1e-12)
+    assert np.allclose(u2, u_aug, rtol=0, atol=1e-9 * np.abs(u_aug).max())
