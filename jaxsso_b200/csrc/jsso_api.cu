@@ -134,6 +134,8 @@ struct jsso_handle {
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
+  cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
+  cudaEvent_t ev_b = nullptr;
   // device scratch of the host-buffer entry point
   double *s_crds = nullptr, *s_pq = nullptr, *s_pb = nullptr, *s_f = nullptr, *s_u = nullptr;
   double *s_dc = nullptr, *s_dpq = nullptr, *s_dpb = nullptr;
@@ -304,6 +306,9 @@ void jsso_destroy(jsso_handle* h) {
   void* hst[] = {h->sc_host, h->flags_host, h->h_crds, h->h_pq, h->h_pb, h->h_f, h->h_u, h->h_dc, h->h_dpq,
                  h->h_dpb};
   for (void* p : hst) if (p) cudaFreeHost(p);
+  if (h->st_a) cudaStreamDestroy(h->st_a);
+  if (h->st_b) cudaStreamDestroy(h->st_b);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   delete h;
@@ -1145,6 +1150,9 @@ static int ensure_host_staging(jsso_handle* h) {
   CK(dalloc(&h->s_pb, 6 * (size_t)S.n_beam)); CK(dalloc(&h->s_f, 6 * (size_t)S.n_node));
   CK(dalloc(&h->s_u, 6 * (size_t)S.n_node)); CK(dalloc(&h->s_dc, 3 * (size_t)S.n_node));
   CK(dalloc(&h->s_dpq, 5 * (size_t)S.n_quad)); CK(dalloc(&h->s_dpb, 6 * (size_t)S.n_beam));
+  CK(cudaStreamCreateWithFlags(&h->st_a, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->st_b, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
   return JSSO_OK;
 }
 
@@ -1215,7 +1223,10 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   const Symbolic& S = h->sym;
   const size_t nc = 3 * (size_t)S.n_node, nq = 5 * (size_t)S.n_quad, nb = 6 * (size_t)S.n_beam,
                nd = 6 * (size_t)S.n_node;
-  cudaStream_t st = 0;
+  // two streams: coordinates/properties + fused assembly on st, the upload of u and lam on st_b
+  // overlaps the assembly; the adjoint waits for both
+  CK(cudaDeviceSynchronize());
+  cudaStream_t st = h->st_a, st2 = h->st_b;
   // DMA straight from / to the caller's buffers when they are pinned (cudaHostAlloc / registered);
   // pageable buffers are staged through the handle's pinned scratch so the copies stay asynchronous
   auto pinned = [](const void* p) {
@@ -1223,17 +1234,19 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
   };
-  auto h2d = [&](double* dst, const double* src, double* stage, size_t n) -> cudaError_t {
+  auto h2d = [&](double* dst, const double* src, double* stage, size_t n, cudaStream_t s_) -> cudaError_t {
     if (!n) return cudaSuccess;
     if (!pinned(src)) { std::memcpy(stage, src, n * sizeof(double)); src = stage; }
-    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s_);
   };
-  CK(h2d(h->s_crds, crds_h, h->h_crds, nc));
-  CK(h2d(h->s_pq, pq_h, h->h_pq, nq));
-  CK(h2d(h->s_pb, pb_h, h->h_pb, nb));
-  CK(h2d(h->s_f, u_h, h->h_f, nd));
-  CK(h2d(h->s_u, lam_h, h->h_u, nd));
+  CK(h2d(h->s_crds, crds_h, h->h_crds, nc, st));
+  CK(h2d(h->s_pq, pq_h, h->h_pq, nq, st));
+  CK(h2d(h->s_pb, pb_h, h->h_pb, nb, st));
   if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
+  CK(h2d(h->s_f, u_h, h->h_f, nd, st2));
+  CK(h2d(h->s_u, lam_h, h->h_u, nd, st2));
+  CK(cudaEventRecord(h->ev_b, st2));
+  CK(cudaStreamWaitEvent(st, h->ev_b, 0));
   if ((rc = jsso_adjoint(h, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, dc_h ? h->s_dc : nullptr,
                          (dpq_h && nq) ? h->s_dpq : nullptr, (dpb_h && nb) ? h->s_dpb : nullptr, st)))
     return rc;

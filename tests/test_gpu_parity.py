@@ -302,3 +302,23 @@ def test_barrel_arch_gradient_golden(golden):
     # ties make the arg-min rounding dependent: up to 3.6e-5 of max|grad|
     assert relmax(dc, rdc) <= 1e-4
     assert abs(np.sum(md.prop_quads[:, 1] * dq[:, 1]) + val) / val <= 1e-8   # sum_e E dC/dE = -C
+
+
+def test_host_buffer_assemble_adjoint_matches_device_path():
+    """jsso_assemble_adjoint_host (bench.py's e2e leg; pageable and pinned buffers) == device path."""
+    md = meshes.plate(20)
+    rng = np.random.default_rng(4)
+    u, lam = rng.standard_normal(md.ndof), rng.standard_normal(md.ndof)
+    d = Dev(md)
+    dc, dq = nat.DeviceArray((md.n_node, 3)), nat.DeviceArray((md.n_quad, 5))
+    d.h.adjoint(d.crds, d.pq, d.pb, nat.DeviceArray.from_host(u), nat.DeviceArray.from_host(lam), dc, dq, None)
+    ref_c, ref_q = dc.download(), dq.download()
+    got = d.h.assemble_adjoint_host(md.crds, md.prop_quads, md.prop_beams, u, lam)
+    assert np.array_equal(got[0], ref_c) and np.array_equal(got[1], ref_q)
+    pin = [nat.pinned_copy(a) for a in (md.crds, md.prop_quads, md.prop_beams, u, lam)]
+    out = (nat.pinned_empty((md.n_node, 3)), nat.pinned_empty((md.n_quad, 5)), None)
+    d.h.assemble_adjoint_host(*pin, out)
+    assert np.array_equal(np.asarray(out[0]), ref_c) and np.array_equal(np.asarray(out[1]), ref_q)
+    K = nat.bsr_to_scipy(*d.h.pattern(), d.h.values_host())
+    Kref = d.K_scipy(apply_bc=True)
+    assert abs(K - Kref).max() == 0.0
