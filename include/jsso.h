@@ -134,6 +134,14 @@ int jsso_quad_ke(jsso_handle* h, const double* crds_d, const double* prop_q_d, d
 /* ke_d: (n_beam,12,12) row-major (element.py:270-271). */
 int jsso_beam_ke(jsso_handle* h, const double* crds_d, const double* prop_b_d, double* ke_d, void* stream);
 
+/* ---- post-processing and the filters either side of the path ------------ */
+/* Surface area of every quad (JaxSSO/element.py:471-487); area_d has n_quad entries. */
+int jsso_quad_area(jsso_handle* h, const double* crds_d, double* area_d, void* stream);
+/* y = A x for a scalar CSR matrix on the current device: the sparse form of the examples' dense
+ * hat-filter matrices B_ij (Examples/Shells_Mannheim_Multihalle_Shape.ipynb cells 10-13). */
+int jsso_csr_spmv(int32_t n_row, const int32_t* rowptr_d, const int32_t* colidx_d, const double* vals_d,
+                  const double* x_d, double* y_d, void* stream);
+
 /* ---- assembly ------------------------------------------------------------------ */
 /* Fused Ke + numeric assembly into the handle-owned block-CSR values (K_e never
  * touches HBM).  apply_bc != 0 imposes the prescribed dofs (rows/cols -> identity). */

@@ -65,7 +65,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
-           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
+           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
@@ -97,6 +97,8 @@ def lib():
     L.jsso_pattern.argtypes = [vp, vp, vp]
     L.jsso_quad_ke.argtypes = [vp, vp, vp, vp, vp]
     L.jsso_beam_ke.argtypes = [vp, vp, vp, vp, vp]
+    L.jsso_quad_area.argtypes = [vp, vp, vp, vp]
+    L.jsso_csr_spmv.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     L.jsso_assemble.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.jsso_assemble_from_ke.argtypes = [vp, vp, vp, C.c_int, vp]
     L.jsso_get_values.argtypes = [vp, vp, vp]
@@ -317,6 +319,11 @@ class Handle:
     def beam_ke(self, crds, prop_b, out=None, stream=None):
         out = DeviceArray((self.n_beam, 12, 12)) if out is None else out
         self._ck(lib().jsso_beam_ke(self.h, _dp(crds), _dp(prop_b), _dp(out), stream))
+        return out
+
+    def quad_area(self, crds, out=None, stream=None):
+        out = DeviceArray((self.n_quad,)) if out is None else out
+        self._ck(lib().jsso_quad_area(self.h, _dp(crds), _dp(out), stream))
         return out
 
     # ---- assembly

@@ -339,6 +339,27 @@ int jsso_quad_ke(jsso_handle* h, const double* crds, const double* prop_q, doubl
   return JSSO_OK;
 }
 
+int jsso_quad_area(jsso_handle* h, const double* crds, double* area, void* stream) {
+  if (!h || !crds || !area) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  const int n = h->sym.n_quad;
+  if (n == 0) return JSSO_OK;
+  quad_area_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, crds, h->cnct_q, area);
+  CKL("quad_area_kernel");
+  return JSSO_OK;
+}
+
+int jsso_csr_spmv(int32_t n_row, const int32_t* rowptr_d, const int32_t* colidx_d, const double* vals_d,
+                  const double* x_d, double* y_d, void* stream) {
+  jsso_handle* h = nullptr;
+  if (n_row < 0 || !rowptr_d || !y_d) return fail(h, JSSO_ERR_ARG, "bad csr_spmv argument");
+  if (n_row == 0) return JSSO_OK;
+  csr_spmv_kernel<<<cdiv(8LL * n_row, 256), 256, 0, (cudaStream_t)stream>>>(n_row, rowptr_d, colidx_d, vals_d, x_d, y_d);
+  CKL("csr_spmv_kernel");
+  return JSSO_OK;
+}
+
 int jsso_beam_ke(jsso_handle* h, const double* crds, const double* prop_b, double* ke, void* stream) {
   if (!h) return JSSO_ERR_ARG;
   NEED_GPU();

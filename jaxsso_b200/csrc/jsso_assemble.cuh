@@ -385,6 +385,48 @@ assemble_fused_kernel(AsmArgs A) {
   }
 }
 
+// Post-processing on the same data: surface area of every quad as the two
+// triangles (1,2,4) and (3,4,2) (JaxSSO/element.py:471-487, used by the size-optimisation example
+// for the material volume sum_e t_e A_e).
+__global__ void __launch_bounds__(256)
+quad_area_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+                 double* __restrict__ area) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_quad) return;
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int nd = cnct[4 * e + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
+  }
+  double a[3], b[3], c[3], d[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[i] = P[1][i] - P[0][i]; b[i] = P[3][i] - P[0][i];
+    c[i] = P[3][i] - P[2][i]; d[i] = P[1][i] - P[2][i];
+  }
+  const double x1 = a[1] * b[2] - a[2] * b[1], y1 = a[2] * b[0] - a[0] * b[2], z1 = a[0] * b[1] - a[1] * b[0];
+  const double x2 = c[1] * d[2] - c[2] * d[1], y2 = c[2] * d[0] - c[0] * d[2], z2 = c[0] * d[1] - c[1] * d[0];
+  area[e] = 0.5 * (sqrt(x1 * x1 + y1 * y1 + z1 * z1) + sqrt(x2 * x2 + y2 * y2 + z2 * z2));
+}
+
+// y = A x for a scalar CSR matrix (the sparse radius filters either side of the path, SURVEY 8(f)
+// rank 3); 8 lanes per row
+__global__ void __launch_bounds__(256)
+csr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = t >> 3, sub = t & 7;
+  double s = 0.0;
+  if (row < n_row)
+    for (int k = rowptr[row] + sub; k < rowptr[row + 1]; k += 8) s = fma(vals[k], x[colidx[k]], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (row < n_row && sub == 0) y[row] = s;
+}
+
 // Boundary conditions on an already assembled matrix (values given by the caller)
 __global__ void __launch_bounds__(256)
 apply_bc_kernel(long long n_out, const int32_t* __restrict__ blk_row, const int32_t* __restrict__ colidx,

@@ -137,6 +137,14 @@ def beam_indices(cnct):
 # ----------------------------------------------------------------------------
 # MITC4 quad (element.py:488-1106)
 # ----------------------------------------------------------------------------
+def quad_area(crds):
+    """Surface area of a quad as two triangles (1,2,4) and (3,4,2); element.py:471-487.  crds (n,12)."""
+    P = np.asarray(crds).reshape(-1, 4, 3)
+    a1 = _norm(_cross(P[:, 1] - P[:, 0], P[:, 3] - P[:, 0])) * 0.5
+    a2 = _norm(_cross(P[:, 3] - P[:, 2], P[:, 1] - P[:, 2])) * 0.5
+    return a1 + a2
+
+
 def quad_frame(crds):
     """Local axes (x^, y^, z^) of a quad; element.py:502-521 and 649-671.
 

@@ -176,3 +176,32 @@ def test_solver_plugin_on_reference_K_aug(golden):
     A = K_aug.tocsr()
     u2 = solver.b200_solve((A.data, A.indices, A.indptr, A.shape), f_aug, rtol=1e-12)
     assert np.allclose(u2, u_aug, rtol=0, atol=1e-9 * np.abs(u_aug).max())
+
+
+def test_quad_area_and_volume(mannheim_data):
+    """Quad.A (element.py:471-487) and the material volume of the size example."""
+    from jaxsso_b200 import _native as nat
+    md = meshes.mannheim_quad(mannheim_data)
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    area = h.quad_area(nat.DeviceArray.from_host(md.crds)).download()
+    ref = orc.quad_area(md.crds[md.cnct_quads].reshape(-1, 12))
+    assert np.abs(area - ref).max() / ref.max() < 1e-14
+    assert abs(area @ md.prop_quads[:, 0] - ref @ md.prop_quads[:, 0]) / (ref @ md.prop_quads[:, 0]) < 1e-14
+
+
+def test_sparse_hat_filter_matches_dense_notebook_filter(mannheim_data):
+    """The examples' dense filter (Examples/Shells_Mannheim_Multihalle_Shape.ipynb cells 10-13) vs the
+    sparse GPU one, forward (B @ z) and transposed (sens @ B)."""
+    from jaxsso_b200.filters import HatFilter
+    xs = mannheim_data['x'] - mannheim_data['x'].min()
+    ys = mannheim_data['y'] - mannheim_data['y'].min()
+    R = 10.0
+    D_ij = (np.subtract.outer(xs, xs) ** 2 + np.subtract.outer(ys, ys) ** 2) ** 0.5
+    B_ini = np.where(D_ij > R, 0, (1 / R) * (R - D_ij))
+    B_dense = B_ini / B_ini.sum(axis=1)[:, None]
+    f = HatFilter(np.stack([xs, ys], 1), R)
+    rng = np.random.default_rng(1)
+    z, g = rng.standard_normal(xs.shape[0]), rng.standard_normal(xs.shape[0])
+    assert np.abs(f.apply(z) - B_dense @ z).max() < 1e-13
+    assert np.abs(f.apply_T(g) - g @ B_dense).max() < 1e-13
+    assert f.B.nnz < 0.2 * B_dense.size
