@@ -44,50 +44,101 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region: NVML from a sampling thread
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`
+    prints); falls back to an `nvidia-smi -lms` child writing to a file when NVML cannot be loaded."""
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_s=0.05):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.period, self.stop_flag, self.source = period_s, threading.Event(), None
+        self.proc = self.path = self.nv = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = 'nvml'
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        if not self.rows:   # one synchronous query rather than an empty record
+            self.nv = None
             try:
-                r = subprocess.run(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                   capture_output=True, text=True, timeout=20)
-                self.rows = [l.strip() for l in r.stdout.splitlines() if l.strip()][:1]
+                self.path = os.path.join(ROOT, 'gpurun_out', f'clocks_{os.getpid()}.csv')
+                os.makedirs(os.path.dirname(self.path), exist_ok=True)
+                self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                              '--format=csv,noheader,nounits', '-lms', '100', '-f', self.path],
+                                             stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                self.source = 'nvidia-smi'
+            except Exception:
+                self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = [(getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8), 'hw_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40), 'hw_thermal_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), 'sw_thermal_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4), 'sw_power_cap')]
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(self.max_mhz)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, n in bits:
+                    if r & b:
+                        self.reasons.add(n)
             except Exception:
                 pass
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            f = [x.strip() for x in r.split(',')]
+            self.stop_flag.wait(self.period)
+
+    @property
+    def n_samples(self):
+        return len(self.sm)
+
+    def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2.0)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+            try:
+                with open(self.path) as f:
+                    rows = [l.strip() for l in f if l.strip()]
+                os.remove(self.path)
+            except Exception:
+                rows = []
+            for r in rows:
+                f = [x.strip() for x in r.split(',')]
+                try:
+                    self.sm.append(float(f[0])); self.mx.append(float(f[1]))
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(self.NAMES, f[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+        else:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'samples': 0, 'reasons': ['nvml and nvidia-smi unavailable']}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None,
+                'sm_max_mhz': max(self.mx) if self.mx else None, 'samples': len(self.sm),
+                'reasons': sorted(self.reasons), 'source': self.source}
 
 
 def synthetic_state(md):
@@ -305,9 +356,9 @@ def run_b200(args):
         h.assemble_adjoint_host(hc, hq, hb, hu, hl, out_bufs)
     barrier()
     s_e2e = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    if sampler and len(sampler.rows) < 3:      # very short runs: keep the GPU busy until a few samples exist
+    if sampler and sampler.n_samples < 3:      # very short runs: keep the GPU busy until a few samples exist
         t_end = time.perf_counter() + 1.5
-        while time.perf_counter() < t_end and len(sampler.rows) < 3:
+        while time.perf_counter() < t_end and sampler.n_samples < 3:
             step()
             L.jsso_stream_sync(None)
     clocks = sampler.stop() if sampler else None

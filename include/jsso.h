@@ -127,6 +127,14 @@ int jsso_get_sizes(const jsso_handle* h, jsso_sizes* out);
 /* ---- symbolic pass results (host copies) -------------------------------------- */
 /* rowptr[n_row+1], colidx[nnzb] (sorted within each row): the bit-exact pattern. */
 int jsso_pattern(const jsso_handle* h, int32_t* rowptr_h, int32_t* colidx_h);
+/* Warp-task lists of the two-kernel numeric assembly (host copies, for tests): counts[3] =
+ * {n_task, n_task_els, tasks_ok}; every other pointer may be NULL.  task_meta: 4 ints per task
+ * {blk0, item0, el0, n_blk | n_item<<8 | n_el<<16}; item_desc per pair item: local block (bits 0-4),
+ * b (5-6), a (7-8), local quad (9-11), beam (12), first item of its block (13); blk_bc per block: row
+ * mask | col mask<<6 | diagonal<<12; blk_item_ptr[nnzb+1] / item_code[n_items] = (elem<<4)|(a<<2)|b are
+ * the contributor lists in the reference's concatenation order (assemblemodel.py:202-211). */
+int jsso_assembly_tasks(const jsso_handle* h, int32_t* counts, int32_t* task_meta_h, int32_t* task_els_h,
+                        uint16_t* item_desc_h, uint16_t* blk_bc_h, int32_t* blk_item_ptr_h, int32_t* item_code_h);
 
 /* ---- element stiffness, materialised (tests / ncu) ----------------------------- */
 /* ke_d: (n_quad,24,24) row-major, the reference's `data` layout (element.py:1236-1237). */

@@ -64,7 +64,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern',
+SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_assembly_tasks',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
@@ -95,6 +95,7 @@ def lib():
     L.jsso_last_error.restype = C.c_char_p
     L.jsso_get_sizes.argtypes = [vp, C.POINTER(Sizes)]
     L.jsso_pattern.argtypes = [vp, vp, vp]
+    L.jsso_assembly_tasks.argtypes = [vp] * 8
     L.jsso_quad_ke.argtypes = [vp, vp, vp, vp, vp]
     L.jsso_beam_ke.argtypes = [vp, vp, vp, vp, vp]
     L.jsso_quad_area.argtypes = [vp, vp, vp, vp]
@@ -309,6 +310,19 @@ class Handle:
         colidx = np.empty(self.nnzb, np.int32)
         self._ck(lib().jsso_pattern(self.h, _ptr(rowptr), _ptr(colidx)))
         return rowptr, colidx
+
+    def assembly_tasks(self):
+        """Host copies of the warp-task lists of the two-kernel assembly (dict of arrays)."""
+        cnt = np.zeros(3, np.int32)
+        self._ck(lib().jsso_assembly_tasks(self.h, _ptr(cnt), None, None, None, None, None, None))
+        out = {'n_task': int(cnt[0]), 'tasks_ok': bool(cnt[2]),
+               'task_meta': np.empty((int(cnt[0]), 4), np.int32), 'task_els': np.empty(int(cnt[1]), np.int32),
+               'item_desc': np.empty(self.n_items, np.uint16), 'blk_bc': np.empty(self.nnzb, np.uint16),
+               'blk_item_ptr': np.empty(self.nnzb + 1, np.int32), 'item_code': np.empty(self.n_items, np.int32)}
+        self._ck(lib().jsso_assembly_tasks(self.h, _ptr(cnt), _ptr(out['task_meta']), _ptr(out['task_els']),
+                                           _ptr(out['item_desc']), _ptr(out['blk_bc']), _ptr(out['blk_item_ptr']),
+                                           _ptr(out['item_code'])))
+        return out
 
     # ---- element matrices
     def quad_ke(self, crds, prop_q, out=None, stream=None):

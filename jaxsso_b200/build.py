@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libjsso.so')
 SOURCES = ['jsso_api.cu', 'jsso_symbolic.cpp']
-HEADERS = ['jsso_elem.cuh', 'jsso_assemble.cuh', 'jsso_solver.cuh', 'jsso_adjoint.cuh', 'jsso_symbolic.h',
+HEADERS = ['jsso_elem.cuh', 'jsso_assemble.cuh', 'jsso_solver.cuh', 'jsso_adjoint.cuh', 'jsso_multigrid.cuh',
+           'jsso_symbolic.h',
            os.path.join('..', '..', 'include', 'jsso.h')]
 
 

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,6 +81,11 @@ struct jsso_handle {
   int32_t *blk_item_ptr = nullptr, *item_code = nullptr;
   uint8_t *item_lel = nullptr, *node_mask = nullptr;
   int32_t *chunk_blk = nullptr, *chunk_el_ptr = nullptr, *chunk_els = nullptr, *blk_perm = nullptr;
+  // two-kernel assembly (geometry records + warp tasks); asm_tasks = false: chunked single-kernel path
+  int32_t *task_meta = nullptr, *task_els = nullptr;
+  uint16_t *item_desc = nullptr, *blk_bc = nullptr;
+  double* quad_rec = nullptr;    // n_quad x REC geometry records
+  bool asm_tasks = false;
   int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
   // numeric state
   double* vals = nullptr;   // nnzb*36, column-major blocks
@@ -120,11 +126,14 @@ struct jsso_handle {
             *cl_ap = nullptr;
     int32_t *pt_rowptr = nullptr, *pt_col = nullptr, *pt_src = nullptr, *mem_ptr = nullptr, *mem = nullptr;
     double *P = nullptr, *Pt = nullptr, *AP = nullptr, *Ac = nullptr, *Xc = nullptr, *Dinv = nullptr;
+    float *P32 = nullptr, *Pt32 = nullptr, *Ac32 = nullptr;   // single-precision copies used by the V-cycle
     double *b = nullptr, *x = nullptr, *r = nullptr, *d = nullptr;   // level vectors (b, x unused at level 0)
     double lam = 0.0;
   };
   std::vector<MgLevel> mg;
   double* Lfac = nullptr;          // L_i (row-major) of the fine diagonal blocks
+  float* vals32 = nullptr;         // single-precision copy of the scaled fine matrix (V-cycle only)
+  bool mg_fp32 = true;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -195,6 +204,15 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
   CK(upload(&h->item_lel, S.item_lel)); CK(upload(&h->node_mask, S.node_mask));
   CK(upload(&h->chunk_blk, S.chunk_blk)); CK(upload(&h->chunk_el_ptr, S.chunk_el_ptr));
   CK(upload(&h->chunk_els, S.chunk_els)); CK(upload(&h->blk_perm, S.blk_perm));
+  {
+    const char* e = std::getenv("JSSO_ASM_CHUNKED");   // A/B switch: force the chunked single-kernel assembly
+    h->asm_tasks = S.tasks_ok && !(e && e[0] == '1');
+  }
+  if (h->asm_tasks) {
+    CK(upload(&h->task_meta, S.task_meta)); CK(upload(&h->task_els, S.task_els));
+    CK(upload(&h->item_desc, S.item_desc)); CK(upload(&h->blk_bc, S.blk_bc));
+    CK(dalloc(&h->quad_rec, (size_t)S.n_quad * REC));
+  }
   CK(upload(&h->node_inc_ptr, S.node_inc_ptr)); CK(upload(&h->node_inc, S.node_inc));
   const size_t nd = 6 * (size_t)S.n_node;
   CK(dalloc(&h->vals, (size_t)S.nnzb() * 36));
@@ -223,6 +241,8 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
   }
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
+  CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          TASK_WARPS * TASK_SMEM_DOUBLES * (int)sizeof(double)));
   return JSSO_OK;
 }
 
@@ -298,7 +318,7 @@ void jsso_destroy(jsso_handle* h) {
   cudaSetDevice(h->device);
   void* dev[] = {h->cnct_q, h->cnct_b, h->rowptr, h->colidx, h->blk_row, h->diag_slot, h->blk_item_ptr,
                  h->item_code, h->item_lel, h->node_mask, h->chunk_blk, h->chunk_el_ptr, h->chunk_els, h->blk_perm,
-                 h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
+                 h->task_meta, h->task_els, h->item_desc, h->blk_bc, h->quad_rec, h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
                  h->corner_q, h->corner_b, h->tmp_lam, h->tmp_g, h->sc, h->partials, h->counters, h->flags,
                  h->send_idx, h->send_buf, h->mbox, h->p2p, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
                  h->s_dpb};
@@ -325,6 +345,20 @@ int jsso_pattern(const jsso_handle* h, int32_t* rowptr, int32_t* colidx) {
   if (!h || !rowptr || !colidx) return JSSO_ERR_ARG;
   std::memcpy(rowptr, h->sym.rowptr.data(), h->sym.rowptr.size() * sizeof(int32_t));
   std::memcpy(colidx, h->sym.colidx.data(), h->sym.colidx.size() * sizeof(int32_t));
+  return JSSO_OK;
+}
+
+int jsso_assembly_tasks(const jsso_handle* h, int32_t* counts, int32_t* task_meta, int32_t* task_els,
+                        uint16_t* item_desc, uint16_t* blk_bc, int32_t* blk_item_ptr, int32_t* item_code) {
+  if (!h || !counts) return JSSO_ERR_ARG;
+  const Symbolic& S = h->sym;
+  counts[0] = S.n_task(); counts[1] = (int32_t)S.task_els.size(); counts[2] = S.tasks_ok ? 1 : 0;
+  if (task_meta) std::memcpy(task_meta, S.task_meta.data(), S.task_meta.size() * sizeof(int32_t));
+  if (task_els) std::memcpy(task_els, S.task_els.data(), S.task_els.size() * sizeof(int32_t));
+  if (item_desc) std::memcpy(item_desc, S.item_desc.data(), S.item_desc.size() * sizeof(uint16_t));
+  if (blk_bc) std::memcpy(blk_bc, S.blk_bc.data(), S.blk_bc.size() * sizeof(uint16_t));
+  if (blk_item_ptr) std::memcpy(blk_item_ptr, S.blk_item_ptr.data(), S.blk_item_ptr.size() * sizeof(int32_t));
+  if (item_code) std::memcpy(item_code, S.item_code.data(), S.item_code.size() * sizeof(int32_t));
   return JSSO_OK;
 }
 
@@ -384,7 +418,21 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
   A.blk_perm = h->blk_perm; A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
   A.blk_row = h->blk_row; A.colidx = h->colidx; A.node_mask = h->node_mask;
   A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
-  if (h->sym.nnzb() > 0) {
+  if (h->sym.nnzb() > 0 && h->asm_tasks) {
+    const int nq = h->sym.n_quad;
+    if (nq > 0) {
+      quad_geometry_kernel<<<cdiv(nq, 32), 128, 0, st>>>(nq, crds, h->cnct_q, prop_q, h->quad_rec, h->flags);
+      CKL("quad_geometry_kernel");
+    }
+    TaskArgs T;
+    T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta; T.task_els = h->task_els;
+    T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
+    T.crds = crds; T.cnct_b = h->cnct_b; T.prop_b = prop_b;
+    T.vals = h->vals; T.flags = h->flags; T.n_quad = nq; T.n_task = h->sym.n_task(); T.apply_bc = apply_bc;
+    assemble_tasks_kernel<<<cdiv(T.n_task, TASK_WARPS), 32 * TASK_WARPS,
+                            TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
+    CKL("assemble_tasks_kernel");
+  } else if (h->sym.nnzb() > 0) {
     assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
     CKL("assemble_fused_kernel");
   }
@@ -807,6 +855,8 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     CK(dalloc(&m.P, 36 * (size_t)d.nnz_p)); CK(dalloc(&m.Pt, 36 * (size_t)d.nnz_p));
     CK(dalloc(&m.AP, 36 * (size_t)d.nnz_ap)); CK(dalloc(&m.Ac, 36 * (size_t)d.nnz_c));
     CK(dalloc(&m.Xc, 3 * (size_t)d.n_c));
+    CK(dalloc(&m.P32, 36 * (size_t)d.nnz_p)); CK(dalloc(&m.Pt32, 36 * (size_t)d.nnz_p));
+    CK(dalloc(&m.Ac32, 36 * (size_t)d.nnz_c));
     if (l > 0) { CK(dalloc(&m.Dinv, 36 * (size_t)d.n_f)); CK(dalloc(&m.b, 6 * (size_t)d.n_f)); CK(dalloc(&m.x, 6 * (size_t)d.n_f)); }
     CK(dalloc(&m.r, 6 * (size_t)d.n_f)); CK(dalloc(&m.d, 6 * (size_t)d.n_f));
     h->mg.push_back(m);
@@ -817,8 +867,13 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     if (nc > 6000) return fail(h, JSSO_ERR_ARG, "multigrid: coarsest level too large for the dense solve");
     CK(dalloc(&h->mg_dense, 2 * nc * nc)); CK(dalloc(&h->mg_cb, nc)); CK(dalloc(&h->mg_cx, nc));
     CK(dalloc(&h->Lfac, 36 * (size_t)h->sym.n_node));
+    CK(dalloc(&h->vals32, 36 * (size_t)h->sym.nnzb()));
     CK(dalloc(&h->mg_scal, 8));
     CK(cudaMallocHost((void**)&h->mg_scal_host, 8 * sizeof(double)));
+  }
+  {
+    const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
+    h->mg_fp32 = !(e && e[0] == '1');
   }
   h->mg_ready = false;
   h->assembled = false;   // the fine factor L is produced by the scaling of the NEXT assembly
@@ -826,11 +881,11 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
   return JSSO_OK;
 }
 
-struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; };
+struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; };
 static MgMat mg_matrix(jsso_handle* h, int l) {
-  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row};
+  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32};
   const jsso_handle::MgLevel& p = h->mg[l - 1];
-  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c};
+  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c, p.Ac32};
 }
 static inline int mg_blocks(jsso_handle* h, int n_row) {
   return std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
@@ -839,8 +894,24 @@ template <int MODE>
 static int mg_spmv(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, int n_row,
                    const double* x, double* y, const double* b, cudaStream_t st) {
   if (n_row == 0) return JSSO_OK;
-  bsr_spmv_axpby_kernel<MODE><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v, x, y, b);
+  bsr_spmv_axpby_kernel<MODE, double><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v, x, y, b);
   CKL("bsr_spmv_axpby_kernel");
+  return JSSO_OK;
+}
+// same with single-precision block storage (falls back to the FP64 values when fp32 is off)
+template <int MODE>
+static int mg_spmv_p(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, const float* v32,
+                     int n_row, const double* x, double* y, const double* b, cudaStream_t st) {
+  if (!h->mg_fp32 || !v32) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
+  if (n_row == 0) return JSSO_OK;
+  bsr_spmv_axpby_kernel<MODE, float><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v32, x, y, b);
+  CKL("bsr_spmv_axpby_kernel<float>");
+  return JSSO_OK;
+}
+static int mg_to_float(jsso_handle* h, long long n, const double* a, float* b, cudaStream_t st) {
+  if (n == 0) return JSSO_OK;
+  mg_to_float_kernel<<<std::max(1, std::min(1184, cdiv(n, 256))), 256, 0, st>>>(n, a, b);
+  CKL("mg_to_float_kernel");
   return JSSO_OK;
 }
 static int mg_dot(jsso_handle* h, long long n, const double* a, const double* b, int slot, cudaStream_t st) {
@@ -904,7 +975,15 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     CKL("mg_block_product_kernel<0>");
     mg_block_product_kernel<1><<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
     CKL("mg_block_product_kernel<1>");
+    if (h->mg_fp32) {
+      if ((rc = mg_to_float(h, 36LL * m.nnz_p, m.P, m.P32, st))) return rc;
+      if ((rc = mg_to_float(h, 36LL * m.nnz_p, m.Pt, m.Pt32, st))) return rc;
+      if ((rc = mg_to_float(h, 36LL * m.nnz_c, m.Ac, m.Ac32, st))) return rc;
+    }
     X = m.Xc;
+  }
+  if (h->mg_fp32 && nl > 0) {
+    if ((rc = mg_to_float(h, 36LL * h->sym.nnzb(), h->vals, h->vals32, st))) return rc;
   }
   // coarsest level: dense inverse
   const MgMat C = mg_matrix(h, nl);
@@ -931,12 +1010,12 @@ static int mg_smooth(jsso_handle* h, int l, const double* b, double* x, bool zer
   if (zero_guess) {
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, b, m.d, x, 0.0, 1.0 / theta, 1);
   } else {
-    if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n, x, m.r, b, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st))) return rc;
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, 0.0, 1.0 / theta, 0);
   }
   CKL("mg_cheb_kernel<1>");
   for (int k = 1; k < deg; ++k) {
-    if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, n, x, m.r, b, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st))) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, rho_new * rho, 2.0 * rho_new / delta, 0);
     CKL("mg_cheb_kernel<0>");
@@ -959,10 +1038,10 @@ static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg,
   double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
   if ((rc = mg_smooth(h, l, b, x, true, deg, st))) return rc;
-  if ((rc = mg_spmv<2>(h, A.rp, A.ci, A.v, m.n_f, x, m.r, b, st))) return rc;          // r = b - A x
-  if ((rc = mg_spmv<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
+  if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st))) return rc;          // r = b - A x
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.Pt32, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
   if ((rc = mg_vcycle(h, l + 1, bc, xc, deg, st))) return rc;
-  if ((rc = mg_spmv<3>(h, m.p_rowptr, m.p_col, m.P, m.n_f, xc, x, nullptr, st))) return rc;        // x += P x_c
+  if ((rc = mg_spmv_p<3>(h, m.p_rowptr, m.p_col, m.P, m.P32, m.n_f, xc, x, nullptr, st))) return rc;        // x += P x_c
   return mg_smooth(h, l, b, x, false, deg, st);
 }
 

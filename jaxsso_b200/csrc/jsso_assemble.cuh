@@ -385,6 +385,116 @@ assemble_fused_kernel(AsmArgs A) {
   }
 }
 
+// ---- two-kernel assembly: per-quad geometry records + warp tasks ------------------------------------
+// (1) quad_geometry_kernel evaluates the staged record of EVERY quad once (no redundancy between
+//     neighbouring chunks, full occupancy) and writes its first REC doubles (everything
+//     quad_pair_block reads) to a global buffer, 496 bytes per quad.
+// (2) assemble_tasks_kernel: one WARP owns a run of consecutive block slots with <= 32 pair items
+//     (symbolic pass, `task_meta`), copies the <= kTaskQuads records it needs from global/L2 into its
+//     private slice of shared memory, evaluates ONE pair item per lane (uniform work, no loop, no
+//     dependent loads), parks the 36 values of every item in shared memory and then writes the run's
+//     contiguous slice of `vals` with coalesced 16-byte stores, each entry summing its contributors
+//     in list order (fixed order, no atomics).  Warps never synchronise with each other.
+constexpr int REC = 62;        // doubles of the record that quad_pair_block reads (Q_R .. Q_GP + 31)
+constexpr int REC_LD = 63;     // odd shared-memory stride: distinct quads -> distinct banks
+constexpr int ITEM_LD = 38;    // even stride (16-byte aligned rows), 19 x 16 B: conflict-free 16-byte accesses
+constexpr int TASK_SMEM_DOUBLES = kTaskQuads * REC_LD + kTaskItems * ITEM_LD;   // 1720 doubles = 13 760 B per warp
+constexpr int TASK_WARPS = 4;  // warps (= tasks) per CTA
+static_assert((kTaskQuads * REC_LD) % 2 == 0 && TASK_SMEM_DOUBLES % 2 == 0, "16-byte alignment of the item rows");
+
+__global__ void __launch_bounds__(128)
+quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
+                     const double* __restrict__ prop, double* __restrict__ rec, int* flags) {
+  __shared__ double sm[32 * QS];
+  const int first = blockIdx.x * 32;
+  const int n_el = min(32, n_quad - first);
+  stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
+  __syncthreads();
+  double* dst = rec + (size_t)first * REC;
+  for (int idx = threadIdx.x; idx < n_el * REC; idx += blockDim.x) {
+    const int le = idx / REC, w = idx - le * REC;
+    dst[idx] = sm[le * QS + w];
+  }
+}
+
+struct TaskArgs {
+  const double* rec;            // n_quad x REC
+  const int4* task_meta; const int32_t* task_els; const uint16_t* item_desc; const uint16_t* blk_bc;
+  const int32_t* item_code;     // beams: global element id
+  const double* crds; const int32_t* cnct_b; const double* prop_b;
+  double* vals; int* flags; int n_quad; int n_task; int apply_bc;
+};
+
+__global__ void __launch_bounds__(32 * TASK_WARPS, 4)
+assemble_tasks_kernel(TaskArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int task = blockIdx.x * TASK_WARPS + w;
+  if (task >= A.n_task) return;                       // whole warp; no CTA-wide barrier anywhere
+  double* rec = sm + w * TASK_SMEM_DOUBLES;
+  double* buf = rec + kTaskQuads * REC_LD;
+  const int4 m = A.task_meta[task];
+  const int blk0 = m.x, item0 = m.y, el0 = m.z;
+  const int n_blk = m.w & 255, n_item = (m.w >> 8) & 255, n_el = (m.w >> 16) & 255;
+  // independent loads first: item descriptor, boundary word of block `lane`, quad id of record `lane`
+  const unsigned desc = (lane < n_item) ? A.item_desc[item0 + lane] : 0u;
+  const unsigned my_bc = (A.apply_bc && lane < n_blk) ? A.blk_bc[blk0 + lane] : 0u;
+  const int my_el = (lane < n_el) ? A.task_els[el0 + lane] : 0;
+  const bool is_beam = (desc & kDescBeam) != 0;
+  const int beam_el = (is_beam && lane < n_item) ? (A.item_code[item0 + lane] >> 4) - A.n_quad : 0;
+  // records -> shared memory (coalesced 8-byte loads, REC consecutive doubles per quad)
+  const int n_rec = n_el * REC;
+  for (int base = 0; base < n_rec; base += 32) {      // warp-uniform trip count (shuffle inside)
+    const int idx = base + lane;
+    const bool ok = idx < n_rec;
+    const int le = ok ? idx / REC : 0, wd = idx - le * REC;
+    const int e = __shfl_sync(FULL, my_el, le);
+    if (ok) rec[le * REC_LD + wd] = __ldg(A.rec + (size_t)e * REC + wd);
+  }
+  // item starts per local block: lane l holds the lane index of the first item of block l
+  const unsigned firsts = __ballot_sync(FULL, (lane < n_item) && (desc & kDescFirst));
+  const int st = (lane < n_blk) ? (int)__fns(firsts, 0, lane + 1) : n_item;
+  __syncwarp();
+  if (lane < n_item) {
+    double out[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) out[k] = 0.0;
+    const int b = (desc >> 5) & 3, a = (desc >> 7) & 3, lq = (desc >> 9) & 7;
+    if (is_beam) beam_pair_block(A.crds, A.cnct_b, A.prop_b, beam_el, a, b, out, A.flags);
+    else quad_pair_block(rec + lq * REC_LD, a, b, out);
+    double2* dst = (double2*)(buf + lane * ITEM_LD);
+#pragma unroll
+    for (int k2 = 0; k2 < 18; ++k2) dst[k2] = make_double2(out[2 * k2], out[2 * k2 + 1]);
+  }
+  __syncwarp();
+  const int n_out = n_blk * 18;                       // 16-byte pairs of this run's slice of vals
+  double2* out2 = (double2*)(A.vals + (size_t)blk0 * 36);
+  for (int o0 = 0; o0 < n_out; o0 += 32) {
+    const int o = o0 + lane;
+    const bool live = o < n_out;
+    const int bl = live ? o / 18 : 0, k2 = o - bl * 18;
+    const int s0 = __shfl_sync(FULL, st, bl);
+    int s1 = __shfl_sync(FULL, st, (bl + 1) & 31);
+    if (bl + 1 >= n_blk) s1 = n_item;
+    const unsigned bc = __shfl_sync(FULL, my_bc, bl);
+    if (live) {
+      double2 v = *(const double2*)(buf + s0 * ITEM_LD + 2 * k2);
+      for (int it = s0 + 1; it < s1; ++it) {
+        const double2 t = *(const double2*)(buf + it * ITEM_LD + 2 * k2);
+        v.x += t.x; v.y += t.y;
+      }
+      if (bc & 0xfffu) {                              // prescribed rows/cols -> identity
+        const int j = k2 / 3, i = 2 * (k2 - 3 * j);   // entries (i, j) and (i + 1, j), column-major
+        const bool diag = (bc >> 12) & 1u;
+        v.x = bc_entry(v.x, bc & 63u, (bc >> 6) & 63u, i, j, diag);
+        v.y = bc_entry(v.y, bc & 63u, (bc >> 6) & 63u, i + 1, j, diag);
+      }
+      out2[o] = v;
+    }
+  }
+}
+
 // Post-processing on the same data: surface area of every quad as the two
 // triangles (1,2,4) and (3,4,2) (JaxSSO/element.py:471-487, used by the size-optimisation example
 // for the material volume sum_e t_e A_e).

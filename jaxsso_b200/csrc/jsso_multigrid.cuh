@@ -344,6 +344,10 @@ __global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = v;
 }
+__global__ void mg_to_float_kernel(long long n, const double* __restrict__ a, float* __restrict__ b) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    b[i] = (float)a[i];
+}
 // deterministic pseudo-random start vector in (-1, 1) (integer hash of the index): a constant vector
 // is nearly orthogonal to the top of the spectrum on large meshes and the power iteration stalls
 __global__ void mg_hash_fill_kernel(long long n, double* __restrict__ y) {

@@ -163,13 +163,23 @@ __device__ inline bool grid_sum(double v, double* partials, unsigned* counter, d
 
 // ---- SpMV ------------------------------------------------------------------------
 // One block row times x by one warp: lanes 0..2 return rows (2 lane, 2 lane + 1) in (u0, u1).
+// two consecutive block entries as doubles; the FP32 overload serves the multigrid preconditioner,
+// whose level matrices are stored in single precision (half the HBM traffic; accumulation, vectors
+// and the outer PCG stay FP64)
+__device__ inline double2 load_pair(const double* p) { return __ldg((const double2*)p); }
+__device__ inline double2 load_pair(const float* p) {
+  const float2 v = __ldg((const float2*)p);
+  return make_double2((double)v.x, (double)v.y);
+}
+
+template <class VT>
 __device__ inline void bsr_row_product(int r, int lane, const int32_t* __restrict__ rowptr,
-                                       const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                                       const int32_t* __restrict__ colidx, const VT* __restrict__ vals,
                                        const double* __restrict__ x, double& u0, double& u1) {
   const int sub = lane % 3, cg = lane / 3;   // rows (2 sub, 2 sub + 1), column group 0..9 (10 = idle)
   const int b0 = rowptr[r], b1 = rowptr[r + 1];
   const int ncol = 6 * (b1 - b0);
-  const double* base = vals + (size_t)b0 * 36 + 2 * sub;
+  const VT* base = vals + (size_t)b0 * 36 + 2 * sub;
   double acc0 = 0.0, acc1 = 0.0;
   for (int c0 = 0; c0 < ncol; c0 += 60) {
     double2 a[6];
@@ -178,7 +188,7 @@ __device__ inline void bsr_row_product(int r, int lane, const int32_t* __restric
     for (int u = 0; u < 6; ++u) {
       const int c = c0 + 10 * u + cg;
       const bool ok = (cg < 10) && (c < ncol);
-      a[u] = ok ? __ldg((const double2*)(base + (size_t)c * 6)) : make_double2(0.0, 0.0);
+      a[u] = ok ? load_pair(base + (size_t)c * 6) : make_double2(0.0, 0.0);
       xv[u] = ok ? x[6 * (size_t)colidx[b0 + c / 6] + c % 6] : 0.0;
     }
 #pragma unroll
@@ -238,10 +248,10 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
 }
 
 // MODE 0: y = A x;  2: y = b - A x;  3: y += A x   (any 6x6 block-CSR, also rectangular)
-template <int MODE>
+template <int MODE, class VT>
 __global__ void __launch_bounds__(RED_BLOCK)
 bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                      const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                      const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                       const double* __restrict__ bvec) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

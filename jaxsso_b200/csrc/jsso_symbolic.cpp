@@ -149,6 +149,71 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cq,
                      [&](int32_t x, int32_t y) {
                        return S.blk_item_ptr[x + 1] - S.blk_item_ptr[x] > S.blk_item_ptr[y + 1] - S.blk_item_ptr[y];
                      });
+  // ---- per-block boundary word
+  S.blk_bc.resize(nnzb);
+  for (int64_t blk = 0; blk < nnzb; ++blk) {
+    const int r = S.blk_row[blk], c = S.colidx[blk];
+    S.blk_bc[blk] = (uint16_t)(S.node_mask[r] | (S.node_mask[c] << 6) | ((r == c) ? (1u << 12) : 0u));
+  }
+
+  // ---- warp tasks: runs of consecutive blocks with <= 32 items and <= kTaskQuads distinct quads
+  S.item_desc.assign(S.item_code.size(), 0);
+  S.tasks_ok = true;
+  {
+    std::fill(seen.begin(), seen.end(), -1);
+    int task = 0, t_items = 0, t_quads = 0, t_blks = 0;
+    int32_t t_blk0 = 0, t_item0 = 0, t_el0 = 0;
+    auto close_task = [&](int64_t blk_end) {
+      if (blk_end > t_blk0) {
+        S.task_meta.push_back(t_blk0); S.task_meta.push_back(t_item0); S.task_meta.push_back(t_el0);
+        S.task_meta.push_back(t_blks | (t_items << 8) | (t_quads << 16));
+        ++task;
+      }
+      t_blk0 = (int32_t)blk_end; t_item0 = S.blk_item_ptr[blk_end]; t_el0 = (int32_t)S.task_els.size();
+      t_items = t_quads = t_blks = 0;
+    };
+    for (int64_t blk = 0; blk < nnzb && S.tasks_ok; ++blk) {
+      const int i0 = S.blk_item_ptr[blk], i1 = S.blk_item_ptr[blk + 1];
+      fresh.clear();
+      for (int i = i0; i < i1; ++i) {
+        const int el = S.item_code[i] >> 4;
+        if (el < n_quad && seen[el] != task && std::find(fresh.begin(), fresh.end(), el) == fresh.end())
+          fresh.push_back(el);
+      }
+      if (t_items + (i1 - i0) > kTaskItems || t_quads + (int)fresh.size() > kTaskQuads || t_blks >= 32) {
+        close_task(blk);
+        // the quads seen by the closed task are fresh again for the new one
+        fresh.clear();
+        for (int i = i0; i < i1; ++i) {
+          const int el = S.item_code[i] >> 4;
+          if (el < n_quad && std::find(fresh.begin(), fresh.end(), el) == fresh.end()) fresh.push_back(el);
+        }
+      }
+      // a block one warp cannot hold, or an empty block (a node without elements): chunked path
+      if (i1 == i0 || i1 - i0 > kTaskItems || (int)fresh.size() > kTaskQuads) { S.tasks_ok = false; break; }
+      for (int i = i0; i < i1; ++i) {
+        const int code = S.item_code[i];
+        const int el = code >> 4;
+        unsigned d = (unsigned)t_blks | ((unsigned)(code & 15) << 5);   // (a<<2|b) -> bits 5..8: b in 5-6, a in 7-8
+        if (el >= n_quad) {
+          d |= kDescBeam;
+        } else {
+          if (seen[el] != task) {
+            seen[el] = task;
+            lidx[el] = t_quads++;
+            S.task_els.push_back(el);
+          }
+          d |= (unsigned)lidx[el] << 9;
+        }
+        if (i == i0) d |= kDescFirst;
+        S.item_desc[i] = (uint16_t)d;
+      }
+      t_items += i1 - i0;
+      ++t_blks;
+    }
+    if (S.tasks_ok) close_task(nnzb);
+    if (!S.tasks_ok) { S.task_meta.clear(); S.task_els.clear(); }
+  }
   return "";
 }
 

@@ -18,6 +18,12 @@ namespace jsso {
 constexpr int kChunkBlocks = 128; // block slots per assembly chunk (= CTA size: one thread per block)
 constexpr int kChunkItems = 224;  // pair items per assembly chunk
 constexpr int kChunkQuads = 36;   // distinct quads whose geometry a chunk stages in shared memory
+// warp tasks of the two-kernel assembly (quad_geometry_kernel + assemble_tasks_kernel): one warp sums
+// <= 32 pair items (one per lane) of a run of consecutive block slots
+constexpr int kTaskItems = 32;    // = warp size
+constexpr int kTaskQuads = 8;     // distinct quads whose records one warp stages
+// item descriptor bits (uint16)
+constexpr unsigned kDescBeam = 1u << 12, kDescFirst = 1u << 13;   // lb:0-4  b:5-6  a:7-8  lq:9-11
 
 struct Symbolic {
   int n_node = 0, n_row = 0, n_quad = 0, n_beam = 0;
@@ -33,6 +39,15 @@ struct Symbolic {
                                       // contributor count (warps then loop a uniform number of times)
   std::vector<int32_t> chunk_el_ptr;  // n_chunk + 1
   std::vector<int32_t> chunk_els;     // quads staged per chunk
+  // warp tasks (see kTaskItems): task_meta = 4 ints per task {blk0, item0, el0, n_blk | n_item<<8 | n_el<<16};
+  // task_els = quads staged per task; item_desc per pair item (same order as item_code): local block,
+  // node pair, local quad, beam flag, first-item-of-block flag; blk_bc per block = row mask | col mask<<6 |
+  // diagonal<<12.  tasks_ok is false when some block cannot be handled by one warp (> 32 contributors or
+  // > kTaskQuads quads): the chunked single-kernel path is used instead.
+  std::vector<int32_t> task_meta, task_els;
+  std::vector<uint16_t> item_desc, blk_bc;
+  bool tasks_ok = false;
+  int n_task() const { return (int)(task_meta.size() / 4); }
   // per node: incident (element, local node) corners, for the gradient gather
   std::vector<int32_t> node_inc_ptr;  // n_node + 1
   std::vector<int32_t> node_inc;      // (elem << 2) | a; beams use elem = n_quad + id
