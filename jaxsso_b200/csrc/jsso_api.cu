@@ -86,6 +86,7 @@ struct jsso_handle {
   uint16_t *item_desc = nullptr, *blk_bc = nullptr;
   double* quad_rec = nullptr;    // n_quad x REC geometry records
   bool asm_tasks = false;
+  int task_ctas = 148 * 4;       // persistent grid of assemble_tasks_kernel (resident CTAs)
   int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
   // numeric state
   double* vals = nullptr;   // nnzb*36, column-major blocks
@@ -243,6 +244,16 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           TASK_WARPS * TASK_SMEM_DOUBLES * (int)sizeof(double)));
+  // 4 CTAs x 55 KB per SM need the largest shared-memory carve-out
+  CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          (int)cudaSharedmemCarveoutMaxShared));
+  {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_tasks_kernel, 32 * TASK_WARPS,
+                                                     TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double)));
+    h->task_ctas = std::max(1, occ) * prop.multiProcessorCount;
+    if (const char* e = std::getenv("JSSO_TASK_CTAS")) h->task_ctas = std::max(1, std::atoi(e));
+  }
   return JSSO_OK;
 }
 
@@ -427,9 +438,10 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     TaskArgs T;
     T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta; T.task_els = h->task_els;
     T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
+    T.blk_item_ptr = h->blk_item_ptr;
     T.crds = crds; T.cnct_b = h->cnct_b; T.prop_b = prop_b;
     T.vals = h->vals; T.flags = h->flags; T.n_quad = nq; T.n_task = h->sym.n_task(); T.apply_bc = apply_bc;
-    assemble_tasks_kernel<<<cdiv(T.n_task, TASK_WARPS), 32 * TASK_WARPS,
+    assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
                             TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
     CKL("assemble_tasks_kernel");
   } else if (h->sym.nnzb() > 0) {

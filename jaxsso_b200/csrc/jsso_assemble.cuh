@@ -395,11 +395,11 @@ assemble_fused_kernel(AsmArgs A) {
 //     dependent loads), parks the 36 values of every item in shared memory and then writes the run's
 //     contiguous slice of `vals` with coalesced 16-byte stores, each entry summing its contributors
 //     in list order (fixed order, no atomics).  Warps never synchronise with each other.
-constexpr int REC = 62;        // doubles of the record that quad_pair_block reads (Q_R .. Q_GP + 31)
-constexpr int REC_LD = 63;     // odd shared-memory stride: distinct quads -> distinct banks
+constexpr int REC = 62;        // doubles of the record that quad_pair_block reads (Q_R .. Q_GP + 31), 31 x 16 B
+constexpr int REC_LD = 66;     // shared-memory stride: 16-byte aligned rows; 2*lq + c distinct mod 16 for 8 quads
 constexpr int ITEM_LD = 38;    // even stride (16-byte aligned rows), 19 x 16 B: conflict-free 16-byte accesses
-constexpr int TASK_SMEM_DOUBLES = kTaskQuads * REC_LD + kTaskItems * ITEM_LD;   // 1720 doubles = 13 760 B per warp
-constexpr int TASK_WARPS = 4;  // warps (= tasks) per CTA
+constexpr int TASK_SMEM_DOUBLES = kTaskQuads * REC_LD + kTaskItems * ITEM_LD;   // 1744 doubles = 13 952 B per warp
+constexpr int TASK_WARPS = 4;  // warps per CTA
 static_assert((kTaskQuads * REC_LD) % 2 == 0 && TASK_SMEM_DOUBLES % 2 == 0, "16-byte alignment of the item rows");
 
 __global__ void __launch_bounds__(128)
@@ -420,78 +420,124 @@ quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t*
 struct TaskArgs {
   const double* rec;            // n_quad x REC
   const int4* task_meta; const int32_t* task_els; const uint16_t* item_desc; const uint16_t* blk_bc;
+  const int32_t* blk_item_ptr;  // item start of every block
   const int32_t* item_code;     // beams: global element id
   const double* crds; const int32_t* cnct_b; const double* prop_b;
   double* vals; int* flags; int n_quad; int n_task; int apply_bc;
 };
 
+__device__ inline void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// per-lane data of one task that is loaded ahead of time (registers)
+struct TaskRegs {
+  int blk0, cnt;      // first block slot; n_blk | n_item<<8 | n_el<<16
+  unsigned desc;      // item descriptor of item `lane`
+  unsigned bc;        // boundary word of local block `lane`
+  int st;             // lane index of the first item of local block `lane` (n_item beyond the last block)
+  int el;             // quad id of record `lane`
+  int beam_el;        // beam id of item `lane` (beam items only)
+};
+
+__device__ inline void task_load(const TaskArgs& A, const int4 m, int lane, TaskRegs& t) {
+  const int n_blk = m.w & 255, n_item = (m.w >> 8) & 255, n_el = (m.w >> 16) & 255;
+  t.blk0 = m.x; t.cnt = m.w;
+  t.desc = (lane < n_item) ? A.item_desc[m.y + lane] : 0u;
+  t.bc = (A.apply_bc && lane < n_blk) ? A.blk_bc[m.x + lane] : 0u;
+  t.st = (lane < n_blk) ? A.blk_item_ptr[m.x + lane] - m.y : n_item;
+  t.el = (lane < n_el) ? A.task_els[m.z + lane] : 0;
+  t.beam_el = ((t.desc & kDescBeam) && lane < n_item) ? (A.item_code[m.y + lane] >> 4) - A.n_quad : 0;
+}
+
+// records of the task's quads -> this warp's record buffer, 16-byte asynchronous copies
+__device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, int lane, double* rec) {
+  const int n_el = (t.cnt >> 16) & 255;
+  for (int le = 0; le < n_el; ++le) {
+    const int e = __shfl_sync(0xffffffffu, t.el, le);
+    if (lane < REC / 2) cp_async16(rec + le * REC_LD + 2 * lane, A.rec + (size_t)e * REC + 2 * lane);
+  }
+  cp_async_commit();
+}
+
+// Persistent warps: warp gw handles tasks gw, gw + W, gw + 2W, ...  Software pipeline per warp:
+// the meta word of task k+2 and the per-lane descriptors of task k+1 are in registers while task k
+// is computed, and the records of task k+1 stream into shared memory (cp.async) during the output
+// phase of task k, so no global-load latency is exposed after the prologue.
 __global__ void __launch_bounds__(32 * TASK_WARPS, 4)
 assemble_tasks_kernel(TaskArgs A) {
   extern __shared__ __align__(16) double sm[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int task = blockIdx.x * TASK_WARPS + w;
+  const int stride = gridDim.x * TASK_WARPS;
+  int task = blockIdx.x * TASK_WARPS + w;
   if (task >= A.n_task) return;                       // whole warp; no CTA-wide barrier anywhere
   double* rec = sm + w * TASK_SMEM_DOUBLES;
   double* buf = rec + kTaskQuads * REC_LD;
-  const int4 m = A.task_meta[task];
-  const int blk0 = m.x, item0 = m.y, el0 = m.z;
-  const int n_blk = m.w & 255, n_item = (m.w >> 8) & 255, n_el = (m.w >> 16) & 255;
-  // independent loads first: item descriptor, boundary word of block `lane`, quad id of record `lane`
-  const unsigned desc = (lane < n_item) ? A.item_desc[item0 + lane] : 0u;
-  const unsigned my_bc = (A.apply_bc && lane < n_blk) ? A.blk_bc[blk0 + lane] : 0u;
-  const int my_el = (lane < n_el) ? A.task_els[el0 + lane] : 0;
-  const bool is_beam = (desc & kDescBeam) != 0;
-  const int beam_el = (is_beam && lane < n_item) ? (A.item_code[item0 + lane] >> 4) - A.n_quad : 0;
-  // records -> shared memory (coalesced 8-byte loads, REC consecutive doubles per quad)
-  const int n_rec = n_el * REC;
-  for (int base = 0; base < n_rec; base += 32) {      // warp-uniform trip count (shuffle inside)
-    const int idx = base + lane;
-    const bool ok = idx < n_rec;
-    const int le = ok ? idx / REC : 0, wd = idx - le * REC;
-    const int e = __shfl_sync(FULL, my_el, le);
-    if (ok) rec[le * REC_LD + wd] = __ldg(A.rec + (size_t)e * REC + wd);
-  }
-  // item starts per local block: lane l holds the lane index of the first item of block l
-  const unsigned firsts = __ballot_sync(FULL, (lane < n_item) && (desc & kDescFirst));
-  const int st = (lane < n_blk) ? (int)__fns(firsts, 0, lane + 1) : n_item;
-  __syncwarp();
-  if (lane < n_item) {
-    double out[36];
+  // lane -> (block of the triple, 16-byte pieces k and k + 9 of its 18) in the output phase
+  const int c0 = lane / 9, kp = lane - 9 * c0;
+  TaskRegs cur, nxt;
+  task_load(A, A.task_meta[task], lane, cur);
+  task_stage_records(A, cur, lane, rec);
+  int4 m2 = make_int4(0, 0, 0, 0);
+  const bool has1 = task + stride < A.n_task;
+  if (has1) task_load(A, A.task_meta[task + stride], lane, nxt);
+  for (; task < A.n_task; task += stride) {
+    const bool has_next = task + stride < A.n_task, has_next2 = task + 2 * stride < A.n_task;
+    if (has_next2) m2 = A.task_meta[task + 2 * stride];
+    const int n_blk = cur.cnt & 255, n_item = (cur.cnt >> 8) & 255;
+    cp_async_wait_all();
+    __syncwarp();
+    if (lane < n_item) {
+      double out[36];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) out[k] = 0.0;
-    const int b = (desc >> 5) & 3, a = (desc >> 7) & 3, lq = (desc >> 9) & 7;
-    if (is_beam) beam_pair_block(A.crds, A.cnct_b, A.prop_b, beam_el, a, b, out, A.flags);
-    else quad_pair_block(rec + lq * REC_LD, a, b, out);
-    double2* dst = (double2*)(buf + lane * ITEM_LD);
+      for (int k = 0; k < 36; ++k) out[k] = 0.0;
+      const int b = (cur.desc >> 5) & 3, a = (cur.desc >> 7) & 3, lq = (cur.desc >> 9) & 7;
+      if (cur.desc & kDescBeam) beam_pair_block(A.crds, A.cnct_b, A.prop_b, cur.beam_el, a, b, out, A.flags);
+      else quad_pair_block(rec + lq * REC_LD, a, b, out);
+      double2* dst = (double2*)(buf + lane * ITEM_LD);
 #pragma unroll
-    for (int k2 = 0; k2 < 18; ++k2) dst[k2] = make_double2(out[2 * k2], out[2 * k2 + 1]);
-  }
-  __syncwarp();
-  const int n_out = n_blk * 18;                       // 16-byte pairs of this run's slice of vals
-  double2* out2 = (double2*)(A.vals + (size_t)blk0 * 36);
-  for (int o0 = 0; o0 < n_out; o0 += 32) {
-    const int o = o0 + lane;
-    const bool live = o < n_out;
-    const int bl = live ? o / 18 : 0, k2 = o - bl * 18;
-    const int s0 = __shfl_sync(FULL, st, bl);
-    int s1 = __shfl_sync(FULL, st, (bl + 1) & 31);
-    if (bl + 1 >= n_blk) s1 = n_item;
-    const unsigned bc = __shfl_sync(FULL, my_bc, bl);
-    if (live) {
-      double2 v = *(const double2*)(buf + s0 * ITEM_LD + 2 * k2);
-      for (int it = s0 + 1; it < s1; ++it) {
-        const double2 t = *(const double2*)(buf + it * ITEM_LD + 2 * k2);
-        v.x += t.x; v.y += t.y;
-      }
-      if (bc & 0xfffu) {                              // prescribed rows/cols -> identity
-        const int j = k2 / 3, i = 2 * (k2 - 3 * j);   // entries (i, j) and (i + 1, j), column-major
-        const bool diag = (bc >> 12) & 1u;
-        v.x = bc_entry(v.x, bc & 63u, (bc >> 6) & 63u, i, j, diag);
-        v.y = bc_entry(v.y, bc & 63u, (bc >> 6) & 63u, i + 1, j, diag);
-      }
-      out2[o] = v;
+      for (int k2 = 0; k2 < 18; ++k2) dst[k2] = make_double2(out[2 * k2], out[2 * k2 + 1]);
     }
+    __syncwarp();                                     // item rows complete; record buffer free
+    if (has_next) task_stage_records(A, nxt, lane, rec);
+    TaskRegs nn;
+    if (has_next2) task_load(A, m2, lane, nn);
+    // output: three blocks per step, lane (c0, kp) sums pieces kp and kp + 9 of block 3 j + c0 over
+    // the block's items in list order and writes them (27 lanes x 2 x 16 B, contiguous per block)
+    double2* out2 = (double2*)(A.vals + (size_t)cur.blk0 * 36);
+    for (int b3 = 0; b3 < n_blk; b3 += 3) {
+      const int bl = b3 + c0;
+      const bool live = (lane < 27) && (bl < n_blk);
+      const int s0 = __shfl_sync(FULL, cur.st, bl & 31);
+      int s1 = __shfl_sync(FULL, cur.st, (bl + 1) & 31);
+      if (bl + 1 >= n_blk) s1 = n_item;
+      const unsigned bc = __shfl_sync(FULL, cur.bc, bl & 31);
+      if (live) {
+        const double2* src = (const double2*)(buf + s0 * ITEM_LD) + kp;
+        double2 v0 = src[0], v1 = src[9];
+        for (int it = s0 + 1; it < s1; ++it) {
+          src += ITEM_LD / 2;
+          const double2 t0 = src[0], t1 = src[9];
+          v0.x += t0.x; v0.y += t0.y; v1.x += t1.x; v1.y += t1.y;
+        }
+        if (bc & 0xfffu) {                            // prescribed rows/cols -> identity
+          const int j = kp / 3, i = 2 * (kp - 3 * j); // piece kp: entries (i, j), (i+1, j); piece kp+9: column j+3
+          const bool diag = (bc >> 12) & 1u;
+          const unsigned rm = bc & 63u, cm = (bc >> 6) & 63u;
+          v0.x = bc_entry(v0.x, rm, cm, i, j, diag);     v0.y = bc_entry(v0.y, rm, cm, i + 1, j, diag);
+          v1.x = bc_entry(v1.x, rm, cm, i, j + 3, diag); v1.y = bc_entry(v1.y, rm, cm, i + 1, j + 3, diag);
+        }
+        out2[bl * 18 + kp] = v0;
+        out2[bl * 18 + kp + 9] = v1;
+      }
+    }
+    __syncwarp();                                     // item rows read before the next task overwrites them
+    cur = nxt;
+    nxt = nn;
   }
 }
 
