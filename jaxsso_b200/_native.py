@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libjsso.so')
+LIB_PATH = os.environ.get('JSSO_LIB') or os.path.join(_HERE, 'libjsso.so')   # JSSO_LIB: a tuning variant
 
 ERR_NAMES = {0: 'OK', 1: 'ARG', 2: 'CUDA', 3: 'NOCONV', 4: 'NAN', 5: 'BADJAC', 6: 'DEGENERATE_BEAM',
              7: 'NOT_SPD', 8: 'NCCL', 9: 'STATE'}

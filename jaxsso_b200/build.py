@@ -30,22 +30,24 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into jaxsso_b200/libjsso.so."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defs=(), out=None):
+    """Compile every CUDA source for sm_100a into jaxsso_b200/libjsso.so (`defs`/`out`: tuning
+    variants built beside it, selected at run time with JSSO_LIB=<path>)."""
+    if out is None and not force and not needs_build():
         return LIB
     cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
     if verbose:
         cmd += ['-Xptxas', '-v']
+    cmd += ['-D' + d for d in defs]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ['-o', LIB, '-lcudart', '-ldl']   # NCCL is bound lazily with dlopen (see jsso_api.cu)
+    cmd += ['-o', out or LIB, '-lcudart', '-ldl']   # NCCL is bound lazily with dlopen (see jsso_api.cu)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

@@ -37,9 +37,12 @@ using D3 = Dual<3>;
 // diagonal entry only (first arg-min, element.py:978).  Local-coordinate and frame adjoints are
 // finally pulled back through the normalised cross-product frame (element.py:502-539).
 // ---------------------------------------------------------------------------------------
-constexpr int ADJ_QUADS = 32;        // quads per CTA (128 threads)
-constexpr int ADJ_LD = 97;           // doubles per quad in shared memory (odd stride)
-constexpr int A_UG = 0, A_LG = 24, A_UL = 48, A_LL = 72;   // global u, global lam, local u, local lam
+constexpr int ADJ_QUADS = 32;        // quads per batch (128 threads)
+constexpr int ADJ_ST = 66;           // doubles per quad of the gather stage: P 0..11 | u 12..35 | lam 36..59 | prop 60..64
+                                     // (even: 16-byte aligned rows; 66 k mod 16 distinct for the 8 quads of a warp)
+constexpr int ADJ_LD = 49;           // doubles per quad of the local-vector buffer (odd stride)
+constexpr int A_P = 0, A_UG = 12, A_LG = 36, A_PR = 60;   // gather stage: coordinates, global u, global lam, properties
+constexpr int A_UL = 0, A_LL = 24;             // local-vector buffer: local u, local lam
 
 __device__ inline double quad4_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -47,35 +50,75 @@ __device__ inline double quad4_sum(double v) {
   return v;
 }
 
+__device__ inline void adj_cp8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ inline void adj_cp16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+// lane (quad, q) copies node q's coordinates, u and lam rows into the quad's stage record
+__device__ inline void adj_stage(double* rec, int q, int nd, int e, const double* __restrict__ crds,
+                                 const double* __restrict__ prop, const double* __restrict__ u,
+                                 const double* __restrict__ lam) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) adj_cp8(rec + A_P + 3 * q + c, crds + 3 * (size_t)nd + c);
+  adj_cp8(rec + A_PR + q, prop + 5 * (size_t)e + q);
+  if (q == 0) adj_cp8(rec + A_PR + 4, prop + 5 * (size_t)e + 4);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    adj_cp16(rec + A_UG + 6 * q + 2 * j, u + 6 * (size_t)nd + 2 * j);
+    adj_cp16(rec + A_LG + 6 * q + 2 * j, lam + 6 * (size_t)nd + 2 * j);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+// Persistent CTAs: batch b, b + gridDim.x, ... of 32 quads.  The gather of the NEXT batch (node ids one
+// more batch ahead, in a register) streams into the other stage buffer with cp.async while this batch is
+// differentiated, so the two-deep global-load chain cnct -> (crds, u, lam) is exposed only once per CTA.
+// Warps never exchange data with each other (a quad's four lanes share a warp): __syncwarp only.
 template <bool WANT_PROP>
 __global__ void __launch_bounds__(4 * ADJ_QUADS)
 quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                     const double* __restrict__ prop, const double* __restrict__ u,
                     const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
+  __shared__ __align__(16) double stg[2][ADJ_QUADS * ADJ_ST];
   __shared__ double sv[ADJ_QUADS * ADJ_LD];
   const int le = threadIdx.x >> 2, q = threadIdx.x & 3;
-  int e = blockIdx.x * ADJ_QUADS + le;
+  const int n_batch = (n_quad + ADJ_QUADS - 1) / ADJ_QUADS;
+  const int G = gridDim.x;
+  int batch = blockIdx.x;
+  if (batch >= n_batch) return;
+  int nd_next = cnct[4 * min(batch * ADJ_QUADS + le, n_quad - 1) + q];
+  adj_stage(stg[0] + le * ADJ_ST, q, nd_next, min(batch * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
+  nd_next = (batch + G < n_batch) ? cnct[4 * min((batch + G) * ADJ_QUADS + le, n_quad - 1) + q] : 0;
+  for (int it = 0; batch < n_batch; batch += G, ++it) {
+  const bool has_next = batch + G < n_batch;
+  if (has_next)
+    adj_stage(stg[(it + 1) & 1] + le * ADJ_ST, q, nd_next, min((batch + G) * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
+  if (batch + 2 * G < n_batch) nd_next = cnct[4 * min((batch + 2 * G) * ADJ_QUADS + le, n_quad - 1) + q];
+  if (has_next) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+  else asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncwarp();
+  int e = batch * ADJ_QUADS + le;
   const bool valid = e < n_quad;
   if (!valid) e = n_quad - 1;
+  const double* sg = stg[it & 1] + le * ADJ_ST;
   double* sm = sv + le * ADJ_LD;
-  // ---- gather: every lane needs the four nodes' coordinates; lane q stages node q's vectors
-  double P[4][3];
-  int nq = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int nd = cnct[4 * e + k];
-    if (k == q) nq = nd;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) P[k][c] = crds[3 * (size_t)nd + c];
-  }
+  const double* UG = sg + A_UG;
+  const double* LG = sg + A_LG;
   QuadFrame<double> f;
-  quad_frame(P, f);
   {
+    double P[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) P[k][c] = sg[A_P + 3 * k + c];
+    quad_frame(P, f);
     double ug[6], lg[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) { ug[d] = u[6 * (size_t)nq + d]; lg[d] = lam[6 * (size_t)nq + d]; }
-#pragma unroll
-    for (int d = 0; d < 6; ++d) { sm[A_UG + 6 * q + d] = ug[d]; sm[A_LG + 6 * q + d] = lg[d]; }
+    for (int d = 0; d < 6; ++d) { ug[d] = UG[6 * q + d]; lg[d] = LG[6 * q + d]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       sm[A_UL + 6 * q + i] = f.R[i][0] * ug[0] + f.R[i][1] * ug[1] + f.R[i][2] * ug[2];
@@ -87,7 +130,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   __syncwarp();
   const double* UL = sm + A_UL;   // local u: per node [u, v, w, thx, thy, thz]
   const double* LL = sm + A_LL;
-  const double* pr = prop + 5 * (size_t)e;
+  const double* pr = sg + A_PR;   // t, E, nu, kx, ky (staged)
   QuadMat m;
   quad_mat(pr, m);
   QuadShear<double> sh;
@@ -156,8 +199,6 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   const double Ty1 = Nsu * a1 + Nyu * b1 + Myu * c1 - Mzu * d1 + Nsl * A1 + Nyl * B1 + Myl * C1 - Mzl * D1;
   double xb[4] = {0, 0, 0, 0}, yb[4] = {0, 0, 0, 0};   // adjoints of the local coordinates
   double Rb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // adjoint of dirCos
-  const double* UG = sm + A_UG;
-  const double* LG = sm + A_LG;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     xb[k] += g.det * (h0[k] * Phi - (h0[k] * Tx0 + h1[k] * Tx1));
@@ -316,8 +357,10 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   double v31[3], v32[3], v34[3], v42[3], vb31[3], vb32[3], vb34[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    v31[c] = P[0][c] - P[2][c]; v32[c] = P[1][c] - P[2][c];
-    v34[c] = P[3][c] - P[2][c]; v42[c] = P[1][c] - P[3][c];
+    // coordinates re-read from the gather stage (not kept in registers across the kernel)
+    const double p0 = sg[A_P + c], p1 = sg[A_P + 3 + c], p2 = sg[A_P + 6 + c], p3 = sg[A_P + 9 + c];
+    v31[c] = p0 - p2; v32[c] = p1 - p2;
+    v34[c] = p3 - p2; v42[c] = p1 - p3;
     Rb[0][c] += xb[0] * v31[c] + xb[1] * v32[c] + xb[3] * v34[c];
     Rb[1][c] += yb[0] * v31[c] + yb[1] * v32[c] + yb[3] * v34[c];
     vb31[c] = xb[0] * f.R[0][c] + yb[0] * f.R[1][c];
@@ -396,6 +439,8 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
       o[3] = -(tE * pre * (Mxx + nu * Mxy)); o[4] = -(tE * pre * (nu * Myx + Myy));
     }
   }
+  __syncwarp();   // this batch's stage and local vectors are dead: the next iterations may overwrite them
+  }  // batch loop
 }
 
 // e = lam_e^T K_e u_e for a beam-column, K_e = T^T K_local T (orthonormal T).

@@ -87,6 +87,7 @@ struct jsso_handle {
   double* quad_rec = nullptr;    // n_quad x REC geometry records
   bool asm_tasks = false;
   int task_ctas = 148 * 4;       // persistent grid of assemble_tasks_kernel (resident CTAs)
+  int adj_ctas = 148 * 2, adj_ctas_prop = 148 * 2;   // persistent grids of quad_adjoint_kernel<false/true>
   int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
   // numeric state
   double* vals = nullptr;   // nnzb*36, column-major blocks
@@ -212,7 +213,7 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
   if (h->asm_tasks) {
     CK(upload(&h->task_meta, S.task_meta)); CK(upload(&h->task_els, S.task_els));
     CK(upload(&h->item_desc, S.item_desc)); CK(upload(&h->blk_bc, S.blk_bc));
-    CK(dalloc(&h->quad_rec, (size_t)S.n_quad * REC));
+    CK(dalloc(&h->quad_rec, (size_t)S.n_quad * REC_GLD));
   }
   CK(upload(&h->node_inc_ptr, S.node_inc_ptr)); CK(upload(&h->node_inc, S.node_inc));
   const size_t nd = 6 * (size_t)S.n_node;
@@ -253,6 +254,10 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
                                                      TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double)));
     h->task_ctas = std::max(1, occ) * prop.multiProcessorCount;
     if (const char* e = std::getenv("JSSO_TASK_CTAS")) h->task_ctas = std::max(1, std::atoi(e));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<false>, 4 * ADJ_QUADS, 0));
+    h->adj_ctas = std::max(1, occ) * prop.multiProcessorCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<true>, 4 * ADJ_QUADS, 0));
+    h->adj_ctas_prop = std::max(1, occ) * prop.multiProcessorCount;
   }
   return JSSO_OK;
 }
@@ -1192,7 +1197,7 @@ int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const
   cudaStream_t st = (cudaStream_t)stream;
   const Symbolic& S = h->sym;
   if (S.n_quad > 0) {
-    const int blocks = cdiv(S.n_quad, ADJ_QUADS);
+    const int blocks = std::min(cdiv(S.n_quad, ADJ_QUADS), d_prop_q ? h->adj_ctas_prop : h->adj_ctas);
     if (d_prop_q)
       quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
                                                                  d_crds ? h->corner_q : nullptr, d_prop_q);

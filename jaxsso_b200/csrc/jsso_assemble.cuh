@@ -395,11 +395,31 @@ assemble_fused_kernel(AsmArgs A) {
 //     dependent loads), parks the 36 values of every item in shared memory and then writes the run's
 //     contiguous slice of `vals` with coalesced 16-byte stores, each entry summing its contributors
 //     in list order (fixed order, no atomics).  Warps never synchronise with each other.
+// tuning switches (A/B builds: scripts/variants.py)
+#ifndef JSSO_T_DEEP
+#define JSSO_T_DEEP 0      // descriptors loaded two tasks ahead (0: one task ahead)
+#endif
+#ifndef JSSO_T_L2PF
+#define JSSO_T_L2PF 0      // L2 prefetch of the next task's records during the compute phase
+#endif
+#ifndef JSSO_T_UNROLL1
+#define JSSO_T_UNROLL1 1   // item loop of the output phase not unrolled
+#endif
+#ifndef JSSO_T_OUT
+#define JSSO_T_OUT 0       // 0: three blocks per step, coalesced; 1: lane l sums and stores block l
+#endif
+#ifndef JSSO_T_WARPS
+#define JSSO_T_WARPS 4
+#endif
+#ifndef JSSO_T_GLD
+#define JSSO_T_GLD 62
+#endif
 constexpr int REC = 62;        // doubles of the record that quad_pair_block reads (Q_R .. Q_GP + 31), 31 x 16 B
+constexpr int REC_GLD = JSSO_T_GLD;    // global stride of a record: 512 B = four aligned 128-byte lines
 constexpr int REC_LD = 66;     // shared-memory stride: 16-byte aligned rows; 2*lq + c distinct mod 16 for 8 quads
 constexpr int ITEM_LD = 38;    // even stride (16-byte aligned rows), 19 x 16 B: conflict-free 16-byte accesses
 constexpr int TASK_SMEM_DOUBLES = kTaskQuads * REC_LD + kTaskItems * ITEM_LD;   // 1744 doubles = 13 952 B per warp
-constexpr int TASK_WARPS = 4;  // warps per CTA
+constexpr int TASK_WARPS = JSSO_T_WARPS;  // warps per CTA
 static_assert((kTaskQuads * REC_LD) % 2 == 0 && TASK_SMEM_DOUBLES % 2 == 0, "16-byte alignment of the item rows");
 
 __global__ void __launch_bounds__(128)
@@ -410,15 +430,22 @@ quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t*
   const int n_el = min(32, n_quad - first);
   stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
   __syncthreads();
-  double* dst = rec + (size_t)first * REC;
-  for (int idx = threadIdx.x; idx < n_el * REC; idx += blockDim.x) {
-    const int le = idx / REC, w = idx - le * REC;
-    dst[idx] = sm[le * QS + w];
+  double* dst = rec + (size_t)first * REC_GLD;
+  if (REC_GLD == REC) {
+    for (int idx = threadIdx.x; idx < n_el * REC; idx += blockDim.x) {
+      const int le = idx / REC, w = idx - le * REC;
+      dst[idx] = sm[le * QS + w];
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n_el * REC_GLD; idx += blockDim.x) {
+      const int le = idx / REC_GLD, w = idx % REC_GLD;
+      if (w < REC) dst[idx] = sm[le * QS + w];
+    }
   }
 }
 
 struct TaskArgs {
-  const double* rec;            // n_quad x REC
+  const double* rec;            // n_quad x REC_GLD
   const int4* task_meta; const int32_t* task_els; const uint16_t* item_desc; const uint16_t* blk_bc;
   const int32_t* blk_item_ptr;  // item start of every block
   const int32_t* item_code;     // beams: global element id
@@ -430,6 +457,7 @@ __device__ inline void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ inline void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -458,7 +486,7 @@ __device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, 
   const int n_el = (t.cnt >> 16) & 255;
   for (int le = 0; le < n_el; ++le) {
     const int e = __shfl_sync(0xffffffffu, t.el, le);
-    if (lane < REC / 2) cp_async16(rec + le * REC_LD + 2 * lane, A.rec + (size_t)e * REC + 2 * lane);
+    if (lane < REC / 2) cp_async16(rec + le * REC_LD + 2 * lane, A.rec + (size_t)e * REC_GLD + 2 * lane);
   }
   cp_async_commit();
 }
@@ -467,7 +495,7 @@ __device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, 
 // the meta word of task k+2 and the per-lane descriptors of task k+1 are in registers while task k
 // is computed, and the records of task k+1 stream into shared memory (cp.async) during the output
 // phase of task k, so no global-load latency is exposed after the prologue.
-__global__ void __launch_bounds__(32 * TASK_WARPS, 4)
+__global__ void __launch_bounds__(32 * TASK_WARPS, 16 / TASK_WARPS)
 assemble_tasks_kernel(TaskArgs A) {
   extern __shared__ __align__(16) double sm[];
   const unsigned FULL = 0xffffffffu;
@@ -479,16 +507,29 @@ assemble_tasks_kernel(TaskArgs A) {
   double* buf = rec + kTaskQuads * REC_LD;
   // lane -> (block of the triple, 16-byte pieces k and k + 9 of its 18) in the output phase
   const int c0 = lane / 9, kp = lane - 9 * c0;
-  TaskRegs cur, nxt;
+  TaskRegs cur, nxt, nn;
   task_load(A, A.task_meta[task], lane, cur);
   task_stage_records(A, cur, lane, rec);
-  int4 m2 = make_int4(0, 0, 0, 0);
-  const bool has1 = task + stride < A.n_task;
-  if (has1) task_load(A, A.task_meta[task + stride], lane, nxt);
+  nxt = cur; nn = cur;
+  if (task + stride < A.n_task) task_load(A, A.task_meta[task + stride], lane, nxt);
+  int4 m2 = make_int4(0, 0, 0, 0);                    // meta word of task + 2 stride (one iteration ahead of its use)
+  if (task + 2 * stride < A.n_task) m2 = A.task_meta[task + 2 * stride];
   for (; task < A.n_task; task += stride) {
     const bool has_next = task + stride < A.n_task, has_next2 = task + 2 * stride < A.n_task;
+#if JSSO_T_DEEP
+    if (has_next2) task_load(A, m2, lane, nn);        // descriptors two tasks ahead (m2 arrived long ago)
+    if (task + 3 * stride < A.n_task) m2 = A.task_meta[task + 3 * stride];
+#else
     if (has_next2) m2 = A.task_meta[task + 2 * stride];
+#endif
     const int n_blk = cur.cnt & 255, n_item = (cur.cnt >> 8) & 255;
+#if JSSO_T_L2PF
+    {
+      // pull the next task's records (four 128-byte lines each) into L2 while this task computes
+      const int e = __shfl_sync(FULL, nxt.el, lane >> 2);
+      if (has_next && (lane >> 2) < ((nxt.cnt >> 16) & 255)) prefetch_l2(A.rec + (size_t)e * REC_GLD + 16 * (lane & 3));
+    }
+#endif
     cp_async_wait_all();
     __syncwarp();
     if (lane < n_item) {
@@ -504,8 +545,40 @@ assemble_tasks_kernel(TaskArgs A) {
     }
     __syncwarp();                                     // item rows complete; record buffer free
     if (has_next) task_stage_records(A, nxt, lane, rec);
-    TaskRegs nn;
+#if !JSSO_T_DEEP
     if (has_next2) task_load(A, m2, lane, nn);
+#endif
+#if JSSO_T_OUT == 1
+    // output: lane l sums block l over its items in list order (registers) and stores its 288 bytes
+    {
+      int s1 = __shfl_down_sync(FULL, cur.st, 1);
+      if (lane + 1 >= n_blk) s1 = n_item;
+      if (lane < n_blk) {
+        const double2* src = (const double2*)(buf + cur.st * ITEM_LD);
+        double2 v[18];
+#pragma unroll
+        for (int k2 = 0; k2 < 18; ++k2) v[k2] = src[k2];
+#pragma unroll 1
+        for (int it = cur.st + 1; it < s1; ++it) {
+          src += ITEM_LD / 2;
+#pragma unroll
+          for (int k2 = 0; k2 < 18; ++k2) { const double2 t = src[k2]; v[k2].x += t.x; v[k2].y += t.y; }
+        }
+        if (cur.bc & 0xfffu) {
+          const bool diag = (cur.bc >> 12) & 1u;
+          const unsigned rm = cur.bc & 63u, cm = (cur.bc >> 6) & 63u;
+#pragma unroll
+          for (int k2 = 0; k2 < 18; ++k2) {
+            v[k2].x = bc_entry(v[k2].x, rm, cm, 2 * (k2 % 3), k2 / 3, diag);
+            v[k2].y = bc_entry(v[k2].y, rm, cm, 2 * (k2 % 3) + 1, k2 / 3, diag);
+          }
+        }
+        double2* o = (double2*)(A.vals + (size_t)(cur.blk0 + lane) * 36);
+#pragma unroll
+        for (int k2 = 0; k2 < 18; ++k2) o[k2] = v[k2];
+      }
+    }
+#else
     // output: three blocks per step, lane (c0, kp) sums pieces kp and kp + 9 of block 3 j + c0 over
     // the block's items in list order and writes them (27 lanes x 2 x 16 B, contiguous per block)
     double2* out2 = (double2*)(A.vals + (size_t)cur.blk0 * 36);
@@ -519,6 +592,9 @@ assemble_tasks_kernel(TaskArgs A) {
       if (live) {
         const double2* src = (const double2*)(buf + s0 * ITEM_LD) + kp;
         double2 v0 = src[0], v1 = src[9];
+#if JSSO_T_UNROLL1
+#pragma unroll 1
+#endif
         for (int it = s0 + 1; it < s1; ++it) {
           src += ITEM_LD / 2;
           const double2 t0 = src[0], t1 = src[9];
@@ -535,6 +611,7 @@ assemble_tasks_kernel(TaskArgs A) {
         out2[bl * 18 + kp + 9] = v1;
       }
     }
+#endif
     __syncwarp();                                     // item rows read before the next task overwrites them
     cur = nxt;
     nxt = nn;
