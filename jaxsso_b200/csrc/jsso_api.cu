@@ -234,7 +234,16 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->device));
   h->red_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 4);
-  h->spmv_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * 8);
+  {
+    // persistent SpMV grids: exactly the co-resident CTAs (one wave), the smallest over the variants
+    int o1 = 0, o2 = 0, o3 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, bsr_spmv_kernel<1>, RED_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, bsr_spmv_axpby_kernel<2, float>, RED_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, bsr_spmv_axpby_kernel<2, double>, RED_BLOCK, 0));
+    const int occ = std::max(1, std::min(o1, std::min(o2, o3)));
+    h->spmv_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * occ);
+    if (const char* e = std::getenv("JSSO_SPMV_BLOCKS")) h->spmv_blocks = std::max(1, std::min(RED_MAX_BLOCKS, std::atoi(e)));
+  }
   {
     int occ = 0, coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
@@ -918,9 +927,15 @@ static int mg_spmv(jsso_handle* h, const int32_t* rp, const int32_t* ci, const d
 // same with single-precision block storage (falls back to the FP64 values when fp32 is off)
 template <int MODE>
 static int mg_spmv_p(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, const float* v32,
-                     int n_row, const double* x, double* y, const double* b, cudaStream_t st) {
+                     int n_row, const double* x, double* y, const double* b, cudaStream_t st,
+                     bool short_rows = false) {
   if (!h->mg_fp32 || !v32) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
   if (n_row == 0) return JSSO_OK;
+  if (short_rows) {   // prolongators: a thread per (row, row pair)
+    bsr_spmv_short_kernel<MODE><<<cdiv(3LL * n_row, 256), 256, 0, st>>>(n_row, rp, ci, v32, x, y, b);
+    CKL("bsr_spmv_short_kernel");
+    return JSSO_OK;
+  }
   bsr_spmv_axpby_kernel<MODE, float><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v32, x, y, b);
   CKL("bsr_spmv_axpby_kernel<float>");
   return JSSO_OK;
@@ -1058,7 +1073,8 @@ static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg,
   if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st))) return rc;          // r = b - A x
   if ((rc = mg_spmv_p<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.Pt32, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
   if ((rc = mg_vcycle(h, l + 1, bc, xc, deg, st))) return rc;
-  if ((rc = mg_spmv_p<3>(h, m.p_rowptr, m.p_col, m.P, m.P32, m.n_f, xc, x, nullptr, st))) return rc;        // x += P x_c
+  if ((rc = mg_spmv_p<3>(h, m.p_rowptr, m.p_col, m.P, m.P32, m.n_f, xc, x, nullptr, st,
+                         m.nnz_p <= 5LL * m.n_f))) return rc;                                        // x += P x_c
   return mg_smooth(h, l, b, x, false, deg, st);
 }
 

@@ -344,9 +344,14 @@ __global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = v;
 }
+// FP64 column-major blocks a[36 s + 6 j + i] -> FP32 row-pair-major blocks b[36 s + 12 sub + 2 j + r],
+// i = 2 sub + r (the layout bsr_row_product<float> reads with 16-byte loads)
 __global__ void mg_to_float_kernel(long long n, const double* __restrict__ a, float* __restrict__ b) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    b[i] = (float)a[i];
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+    const long long s = o / 36;
+    const int k = (int)(o - 36 * s), sub = k / 12, rem = k - 12 * sub, j = rem >> 1, r = rem & 1;
+    b[o] = (float)a[36 * s + 6 * j + 2 * sub + r];
+  }
 }
 // deterministic pseudo-random start vector in (-1, 1) (integer hash of the index): a constant vector
 // is nearly orthogonal to the top of the spectrum on large meshes and the power iteration stalls

@@ -163,32 +163,63 @@ __device__ inline bool grid_sum(double v, double* partials, unsigned* counter, d
 
 // ---- SpMV ------------------------------------------------------------------------
 // One block row times x by one warp: lanes 0..2 return rows (2 lane, 2 lane + 1) in (u0, u1).
-// two consecutive block entries as doubles; the FP32 overload serves the multigrid preconditioner,
-// whose level matrices are stored in single precision (half the HBM traffic; accumulation, vectors
-// and the outer PCG stay FP64)
-__device__ inline double2 load_pair(const double* p) { return __ldg((const double2*)p); }
-__device__ inline double2 load_pair(const float* p) {
-  const float2 v = __ldg((const float2*)p);
-  return make_double2((double)v.x, (double)v.y);
+// Both row products take the row's block range [b0, b1) and the column indices of its FIRST chunk
+// (RowU<VT>::U per lane, -1 = no work) in registers, so that the kernels can load them one row ahead
+// (software pipeline: rowptr two rows ahead, colidx one row ahead); longer rows continue with direct loads.
+template <class VT> struct RowU;
+template <> struct RowU<double> { static constexpr int U = 6; };   // 10 blocks per chunk: 30 lanes x 6 columns
+template <> struct RowU<float> { static constexpr int U = 3; };    // 9 blocks per chunk: 27 lanes x 3 blocks
+
+__device__ inline void row_colidx(int lane, int b0, int b1, const int32_t* __restrict__ colidx, int (&ci)[6], const double*) {
+  const int cg = lane / 3, ncol = 6 * (b1 - b0);
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const int c = 10 * u + cg;
+    ci[u] = ((cg < 10) && (c < ncol)) ? colidx[b0 + c / 6] : -1;
+  }
+}
+__device__ inline void row_colidx(int lane, int b0, int b1, const int32_t* __restrict__ colidx, int (&ci)[3], const float*) {
+  const int kb = lane / 9;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int k = b0 + 3 * u + kb;
+    ci[u] = ((lane < 27) && (k < b1)) ? colidx[k] : -1;
+  }
 }
 
-template <class VT>
-__device__ inline void bsr_row_product(int r, int lane, const int32_t* __restrict__ rowptr,
-                                       const int32_t* __restrict__ colidx, const VT* __restrict__ vals,
+// FP64 blocks, column-major: lane = 3 cg + sub handles rows (2 sub, 2 sub + 1) of columns 10 u + cg;
+// lanes 0..2 return rows (2 lane, 2 lane + 1) in (u0, u1).
+__device__ inline void bsr_row_product(int b0, int b1, const int (&ci)[6], int lane,
+                                       const int32_t* __restrict__ colidx, const double* __restrict__ vals,
                                        const double* __restrict__ x, double& u0, double& u1) {
   const int sub = lane % 3, cg = lane / 3;   // rows (2 sub, 2 sub + 1), column group 0..9 (10 = idle)
-  const int b0 = rowptr[r], b1 = rowptr[r + 1];
   const int ncol = 6 * (b1 - b0);
-  const VT* base = vals + (size_t)b0 * 36 + 2 * sub;
+  const double* base = vals + (size_t)b0 * 36 + 2 * sub;
   double acc0 = 0.0, acc1 = 0.0;
-  for (int c0 = 0; c0 < ncol; c0 += 60) {
+  {
+    double2 a[6];
+    double xv[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int c = 10 * u + cg;
+      const bool ok = ci[u] >= 0;
+      a[u] = ok ? __ldg((const double2*)(base + (size_t)c * 6)) : make_double2(0.0, 0.0);
+      xv[u] = ok ? x[6 * (size_t)ci[u] + c % 6] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      acc0 = fma(a[u].x, xv[u], acc0);
+      acc1 = fma(a[u].y, xv[u], acc1);
+    }
+  }
+  for (int c0 = 60; c0 < ncol; c0 += 60) {   // rows with more than 10 blocks
     double2 a[6];
     double xv[6];
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
       const int c = c0 + 10 * u + cg;
       const bool ok = (cg < 10) && (c < ncol);
-      a[u] = ok ? load_pair(base + (size_t)c * 6) : make_double2(0.0, 0.0);
+      a[u] = ok ? __ldg((const double2*)(base + (size_t)c * 6)) : make_double2(0.0, 0.0);
       xv[u] = ok ? x[6 * (size_t)colidx[b0 + c / 6] + c % 6] : 0.0;
     }
 #pragma unroll
@@ -206,6 +237,103 @@ __device__ inline void bsr_row_product(int r, int lane, const int32_t* __restric
   u1 = t1 + __shfl_down_sync(0xffffffffu, t1, 3);
   u0 += __shfl_down_sync(0xffffffffu, s0, 12);
   u1 += __shfl_down_sync(0xffffffffu, s1, 12);
+}
+
+// FP32 block storage of the multigrid preconditioner (half the HBM traffic of the V-cycle; accumulation,
+// vectors and the outer PCG stay FP64).  Blocks are stored ROW-PAIR major,
+//   f[12 sub + 2 j + r] = A[2 sub + r][j]   (sub = 0..2, j = 0..5, r = 0..1),
+// so that the 2 x 2 sub-block (rows 2 sub, 2 sub + 1; columns 2 cp, 2 cp + 1) is one aligned 16-byte load.
+// lane = 9 kb + 3 cp + sub handles that sub-block of block kb of the current triple of blocks (27 lanes,
+// three 16-byte loads of A and three of x in flight); lanes 0..2 return rows (2 lane, 2 lane + 1).
+__device__ inline void bsr_row_product(int b0, int b1, const int (&ci)[3], int lane,
+                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                       const double* __restrict__ x, double& u0, double& u1) {
+  const int kb = lane / 9, rem = lane - 9 * kb, cp = rem / 3, sub = rem - 3 * cp;
+  const float4* base = (const float4*)(vals + (size_t)b0 * 36) + 3 * sub + cp + 9 * kb;   // + 27 per step
+  double acc0 = 0.0, acc1 = 0.0;
+  {
+    float4 a[3];
+    double2 xv[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const bool ok = ci[u] >= 0;
+      a[u] = ok ? __ldg(base + 27 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[u] = ok ? *(const double2*)(x + 6 * (size_t)ci[u] + 2 * cp) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      acc0 = fma((double)a[u].x, xv[u].x, acc0); acc0 = fma((double)a[u].z, xv[u].y, acc0);
+      acc1 = fma((double)a[u].y, xv[u].x, acc1); acc1 = fma((double)a[u].w, xv[u].y, acc1);
+    }
+  }
+  for (int k0 = b0 + 9; k0 < b1; k0 += 9) {   // rows with more than 9 blocks
+    float4 a[3];
+    double2 xv[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int k = k0 + 3 * u + kb;
+      const bool ok = (lane < 27) && (k < b1);
+      a[u] = ok ? __ldg(base + 9 * (size_t)(k0 - b0) + 27 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[u] = ok ? *(const double2*)(x + 6 * (size_t)colidx[k] + 2 * cp) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      acc0 = fma((double)a[u].x, xv[u].x, acc0); acc0 = fma((double)a[u].z, xv[u].y, acc0);
+      acc1 = fma((double)a[u].y, xv[u].x, acc1); acc1 = fma((double)a[u].w, xv[u].y, acc1);
+    }
+  }
+  // sum the 9 lanes of every sub: lanes l, l+3, ..., l+24 -> lanes 0..2
+  const double s0 = acc0 + __shfl_down_sync(0xffffffffu, acc0, 12);
+  const double s1 = acc1 + __shfl_down_sync(0xffffffffu, acc1, 12);
+  const double t0 = s0 + __shfl_down_sync(0xffffffffu, s0, 6);
+  const double t1 = s1 + __shfl_down_sync(0xffffffffu, s1, 6);
+  u0 = t0 + __shfl_down_sync(0xffffffffu, t0, 3);
+  u1 = t1 + __shfl_down_sync(0xffffffffu, t1, 3);
+  u0 += __shfl_down_sync(0xffffffffu, acc0, 24);
+  u1 += __shfl_down_sync(0xffffffffu, acc1, 24);
+}
+
+// un-pipelined form (one row, everything loaded here)
+template <class VT>
+__device__ inline void bsr_row_product(int r, int lane, const int32_t* __restrict__ rowptr,
+                                       const int32_t* __restrict__ colidx, const VT* __restrict__ vals,
+                                       const double* __restrict__ x, double& u0, double& u1) {
+  const int b0 = rowptr[r], b1 = rowptr[r + 1];
+  int ci[RowU<VT>::U];
+  row_colidx(lane, b0, b1, colidx, ci, vals);
+  bsr_row_product(b0, b1, ci, lane, colidx, vals, x, u0, u1);
+}
+
+// Software-pipelined row loop of a warp: rows r, r + n_warp, ...; `body(r, u0, u1)` consumes a row's
+// product (lanes 0..2).  rowptr is loaded two rows ahead and colidx one row ahead, so that per row only
+// the matrix / x loads are on the critical path (one memory latency instead of three).
+template <class VT, class Body>
+__device__ inline void bsr_rows_pipelined(int warp, int n_warp, int lane, int n_row,
+                                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                          const VT* __restrict__ vals, const double* __restrict__ x, Body body) {
+  constexpr int U = RowU<VT>::U;
+  int r = warp;
+  if (r >= n_row) return;
+  int b0 = rowptr[r], b1 = rowptr[r + 1];
+  int ci[U];
+  row_colidx(lane, b0, b1, colidx, ci, vals);
+  int nb0 = 0, nb1 = 0;
+  if (r + n_warp < n_row) { nb0 = rowptr[r + n_warp]; nb1 = rowptr[r + n_warp + 1]; }
+  for (; r < n_row; r += n_warp) {
+    const int r1 = r + n_warp, r2 = r + 2 * n_warp;
+    int nci[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) nci[u] = -1;
+    if (r1 < n_row) row_colidx(lane, nb0, nb1, colidx, nci, vals);   // nb0/nb1 were loaded one iteration ago
+    int nnb0 = 0, nnb1 = 0;
+    if (r2 < n_row) { nnb0 = rowptr[r2]; nnb1 = rowptr[r2 + 1]; }
+    double u0, u1;
+    bsr_row_product(b0, b1, ci, lane, colidx, vals, x, u0, u1);
+    body(r, u0, u1);
+    b0 = nb0; b1 = nb1; nb0 = nnb0; nb1 = nnb1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) ci[u] = nci[u];
+  }
 }
 
 // MODE 0: y = A x.            MODE 1: y = A x and sc->pq = x.y (CG step).
@@ -226,9 +354,7 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warp = (gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
-  for (int r = warp; r < n_row; r += n_warp) {
-    double u0, u1;
-    bsr_row_product(r, lane, rowptr, colidx, vals, x, u0, u1);
+  bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, [&](int r, double u0, double u1) {
     if (lane < 3) {
       *(double2*)(y + 6 * (size_t)r + 2 * lane) = make_double2(u0, u1);
       if (MODE == 1) {
@@ -236,7 +362,7 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
         dot += u0 * xr.x + u1 * xr.y;
       }
     }
-  }
+  });
   if (MODE == 1) {
     double total;
     if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) {
@@ -256,9 +382,7 @@ bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warp = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp; r < n_row; r += n_warp) {
-    double u0, u1;
-    bsr_row_product(r, lane, rowptr, colidx, vals, x, u0, u1);
+  bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, [&](int r, double u0, double u1) {
     if (lane < 3) {
       double2* yp = (double2*)(y + 6 * (size_t)r + 2 * lane);
       if (MODE == 2) {
@@ -271,6 +395,43 @@ bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32
         *yp = make_double2(u0, u1);
       }
     }
+  });
+}
+
+// Short rows (prolongators: 1-4 blocks per row) in the FP32 row-pair-major layout: one THREAD per
+// (block row, row pair), no shuffles -- a warp works on ten rows at once instead of one, which is what
+// hides the rowptr -> colidx -> x load chain when rows are this short.  MODE as above.
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+bsr_spmv_short_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                      const float* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                      const double* __restrict__ bvec) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3LL * n_row) return;
+  const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
+  const int b0 = rowptr[r], b1 = rowptr[r + 1];
+  const float4* base = (const float4*)(vals + (size_t)b0 * 36) + 3 * sub;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int k = b0; k < b1; ++k, base += 9) {
+    const double2* xp = (const double2*)(x + 6 * (size_t)colidx[k]);
+    const float4 a0 = __ldg(base), a1 = __ldg(base + 1), a2 = __ldg(base + 2);
+    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
+    acc0 = fma((double)a0.x, x0.x, acc0); acc0 = fma((double)a0.z, x0.y, acc0);
+    acc1 = fma((double)a0.y, x0.x, acc1); acc1 = fma((double)a0.w, x0.y, acc1);
+    acc0 = fma((double)a1.x, x1.x, acc0); acc0 = fma((double)a1.z, x1.y, acc0);
+    acc1 = fma((double)a1.y, x1.x, acc1); acc1 = fma((double)a1.w, x1.y, acc1);
+    acc0 = fma((double)a2.x, x2.x, acc0); acc0 = fma((double)a2.z, x2.y, acc0);
+    acc1 = fma((double)a2.y, x2.x, acc1); acc1 = fma((double)a2.w, x2.y, acc1);
+  }
+  double2* yp = (double2*)(y + 6 * (size_t)r + 2 * sub);
+  if (MODE == 2) {
+    const double2 bv = *(const double2*)(bvec + 6 * (size_t)r + 2 * sub);
+    *yp = make_double2(bv.x - acc0, bv.y - acc1);
+  } else if (MODE == 3) {
+    const double2 yv = *yp;
+    *yp = make_double2(yv.x + acc0, yv.y + acc1);
+  } else {
+    *yp = make_double2(acc0, acc1);
   }
 }
 
