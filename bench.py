@@ -333,8 +333,18 @@ def run_b200(args):
     ms_step = max_over_ranks(timed(step, args.steps))
     launches = L.jsso_launch_count() - l0
     barrier()
-    # the two kernels on their own (roofline of each)
+    # the stages on their own (roofline of each); the assembly's two kernels are timed separately with
+    # CUDA events recorded between them on the launching stream (jsso_profile)
     ms_asm = max_over_ranks(timed(lambda: h.assemble(crds_d, pq_d, pb_d, apply_bc=True), args.steps))
+    h.profile(True)
+    g_ms, t_ms = [], []
+    for _ in range(args.steps):
+        h.assemble(crds_d, pq_d, pb_d, apply_bc=True)
+        a, b = h.profile_read()
+        g_ms.append(a); t_ms.append(b)
+    h.profile(False)
+    ms_geo = max_over_ranks(float(np.mean(g_ms)))
+    ms_tasks = max_over_ranks(float(np.mean(t_ms)))
     ms_adj = max_over_ranks(timed(lambda: h.adjoint(crds_d, pq_d, pb_d, u_d, lam_d, dc_d, dq_d, None), args.steps))
     # the PCG's dominant kernel: block-CSR SpMV on the assembled (BC-imposed) matrix
     y_d = D((6 * n_row,))
@@ -370,7 +380,7 @@ def run_b200(args):
     if args.solve:
         precond = args.precond if world == 1 else 'block_jacobi'   # the multigrid path is single-GPU
         opts = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, check_every=100, compliance=True,
-                             precond=precond)
+                             precond=precond, cheb_degree=args.cheb_degree)
         uu_d = D((md.ndof,))
         barrier()
         t0 = time.perf_counter()
@@ -386,7 +396,7 @@ def run_b200(args):
             grad_eval = {'seconds': dt, 'evals_per_s': 1.0 / dt, 'pcg_iterations': fs.iterations,
                          'pcg_restarts': fs.restarts, 'true_relres': fs.relres, 'rtol': args.rtol,
                          'ms_per_pcg_iteration': 1e3 * dt / max(fs.iterations, 1),
-                         'preconditioner': ('smoothed-aggregation multigrid (V-cycle, Chebyshev-2)'
+                         'preconditioner': (f'smoothed-aggregation multigrid (V-cycle, Chebyshev-{args.cheb_degree}, FP32 level matrices)'
                                             if (world == 1 and precond != 'block_jacobi') else 'block-Jacobi'),
                          'multigrid': mg_info,
                          'note': 'Ke+assembly, PCG for u (numeric multigrid setup included), lam = u/2 '
@@ -400,25 +410,48 @@ def run_b200(args):
         return
     hbm, peak_src = peaks()
     s = h.sizes
-    # algorithmic bytes of the fused Ke+assembly kernel: connectivity + properties +
-    # coordinates read once, every stored block written once
+    # measured DRAM traffic per launch of the committed ncu capture of this exact workload (profiles/)
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic_1024.json')) as f:
+            ncu = json.load(f) if (world == 1 and N == 1024) else {}
+    except Exception:
+        ncu = {}
+    # dominant kernel: assemble_tasks_kernel.  Algorithmic bytes of that launch: every geometry record read
+    # once (496 B per quad), task/item descriptors, every stored block written once
+    REC_BYTES = 496
+    tasks_bytes = s.n_quad * REC_BYTES + s.n_items * 2 + s.nnzb * (288 + 6)
+    if ms_tasks > 0:
+        roof = {'kernel': 'assemble_tasks_kernel', 'bound': 'hbm', 'achieved': tasks_bytes / (ms_tasks * 1e-3) / 1e9,
+                'peak': hbm, 'unit': 'GB/s', 'frac': tasks_bytes / (ms_tasks * 1e-3) / 1e9 / hbm,
+                'traffic': ncu.get('assemble_tasks_kernel'), 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': tasks_bytes, 'ms': ms_tasks,
+                'note': 'second bound: LSU data-pipe wavefronts (shared memory), see profiles/'}
+    else:   # chunked single-kernel path (meshes the warp tasks cannot hold, or JSSO_ASM_CHUNKED=1)
+        b_ = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
+        roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': b_ / (ms_asm * 1e-3) / 1e9,
+                'peak': hbm, 'unit': 'GB/s', 'frac': b_ / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
+                'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_, 'ms': ms_asm}
+    # the whole assembly stage (quad_geometry_kernel + assemble_tasks_kernel) against SURVEY 8(d)'s
+    # algorithmic bytes of a fused Ke+assembly: connectivity + properties + coordinates read once, every
+    # stored block written once (the geometry records are overhead traffic of the two-kernel design)
     asm_bytes = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
-    roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9,
-            'peak': hbm, 'unit': 'GB/s', 'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
-            'peak_source': peak_src, 'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm}
-    # DRAM traffic of one launch from the committed ncu capture (profiles/r1_ncu_elem_1024.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum), only valid for that exact workload
-    if world == 1 and N == 1024:
-        roof['traffic'] = 329.856512e6 + 2.757134e9
+    tr = [ncu.get('quad_geometry_kernel'), ncu.get('assemble_tasks_kernel')]
+    roof_asm = {'kernel': 'quad_geometry_kernel + assemble_tasks_kernel', 'bound': 'hbm',
+                'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm,
+                'traffic': (tr[0] + tr[1]) if all(t is not None for t in tr) else None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm, 'ms_geometry': ms_geo, 'ms_tasks': ms_tasks}
     spmv_bytes = s.nnzb * 292 + s.n_row * 100
     roof_spmv = {'kernel': 'bsr_spmv_kernel', 'bound': 'hbm', 'achieved': spmv_bytes / (ms_spmv * 1e-3) / 1e9,
                  'peak': hbm, 'unit': 'GB/s', 'frac': spmv_bytes / (ms_spmv * 1e-3) / 1e9 / hbm,
-                 'traffic': (2.821973e9 + 52.820736e6) if (world == 1 and N == 1024) else None,
+                 'traffic': ncu.get('bsr_spmv_kernel'),
                  'algorithmic_bytes_per_launch': spmv_bytes, 'ms': ms_spmv, 'peak_source': peak_src}
     adj_flops = 14000.0 * s.n_quad
     roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
                 'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
                 'peak_source': 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)', 'ms': ms_adj,
+                'traffic': ncu.get('quad_adjoint_kernel'),
                 'algorithmic_flops_per_launch': adj_flops}
     value = n_quad_total / (ms_step * 1e-3)
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -426,15 +459,17 @@ def run_b200(args):
            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
            'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
                                   f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
-                                  f'{6 * gmd.n_node} dof; step = fused Ke+assembly + adjoint reduction',
+                                  f'{6 * gmd.n_node} dof; step = Ke+assembly (geometry records + warp tasks) + adjoint reduction',
                       'parallelism': (f'rcb{world}+' + ('p2p' if args.p2p else 'nccl')) if world > 1 else 'single',
                       'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
                       'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
            'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                    'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
-           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_adjoint': roof_adj,
+           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_assembly': roof_asm,
+           'roofline_adjoint': roof_adj,
            'roofline_spmv': roof_spmv,
-           'kernel_ms': {'assemble_fused': ms_asm, 'adjoint': ms_adj, 'spmv': ms_spmv}, 'setup_s': t_setup,
+           'kernel_ms': {'assembly': ms_asm, 'quad_geometry': ms_geo, 'assemble_tasks': ms_tasks, 'adjoint': ms_adj,
+                         'spmv': ms_spmv}, 'setup_s': t_setup,
            'grad_eval': grad_eval}
     if world == 1 and args.cpu_baseline:
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
@@ -464,6 +499,7 @@ def main():
     ap.add_argument('--rtol', type=float, default=1e-8)
     ap.add_argument('--precond', default='auto', choices=['auto', 'block_jacobi', 'multigrid'])
     ap.add_argument('--maxiter', type=int, default=400000)
+    ap.add_argument('--cheb-degree', type=int, default=1, help='Chebyshev smoother degree of the V-cycle')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     ap.add_argument('--ref-size', type=int, default=64, help='plate size of the bounded CPU sample')
     ap.add_argument('--ref-serial', action='store_true', help='reference arm on one core (cpu_baseline leg)')

@@ -156,6 +156,11 @@ int jsso_csr_spmv(int32_t n_row, const int32_t* rowptr_d, const int32_t* colidx_
 int jsso_assemble(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
                   int apply_bc, void* stream);
 /* Stand-alone segmented reduction of materialised element matrices. */
+/* Per-kernel timing of jsso_assemble's two kernels (CUDA events on the caller's stream; measurement aid for
+ * bench.py): jsso_profile(h, 1), then after any jsso_assemble, ms[0] = quad_geometry_kernel, ms[1] =
+ * assemble_tasks_kernel of the last call. */
+int jsso_profile(jsso_handle* h, int enable);
+int jsso_profile_read(jsso_handle* h, float* ms);
 int jsso_assemble_from_ke(jsso_handle* h, const double* ke_q_d, const double* ke_b_d, int apply_bc,
                           void* stream);
 /* Copy the handle's values (nnzb*36, column-major blocks) to a device / host buffer. */

@@ -65,7 +65,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_assembly_tasks',
-           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_assemble_from_ke', 'jsso_get_values',
+           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
@@ -102,6 +102,8 @@ def lib():
     L.jsso_csr_spmv.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     L.jsso_assemble.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.jsso_assemble_from_ke.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.jsso_profile.argtypes = [vp, C.c_int]
+    L.jsso_profile_read.argtypes = [vp, vp]
     L.jsso_get_values.argtypes = [vp, vp, vp]
     L.jsso_get_values_host.argtypes = [vp, vp]
     L.jsso_get_flags.argtypes = [vp, C.POINTER(i32)]
@@ -343,6 +345,15 @@ class Handle:
     # ---- assembly
     def assemble(self, crds, prop_q, prop_b, apply_bc=True, stream=None):
         self._ck(lib().jsso_assemble(self.h, _dp(crds), _dp(prop_q), _dp(prop_b), int(apply_bc), stream))
+
+    def profile(self, enable=True):
+        self._ck(lib().jsso_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """(quad_geometry_kernel ms, assemble_tasks_kernel ms) of the last assemble() under profile()."""
+        ms = np.zeros(2, np.float32)
+        self._ck(lib().jsso_profile_read(self.h, _ptr(ms)))
+        return float(ms[0]), float(ms[1])
 
     def assemble_from_ke(self, ke_q, ke_b, apply_bc=True, stream=None):
         self._ck(lib().jsso_assemble_from_ke(self.h, _dp(ke_q), _dp(ke_b), int(apply_bc), stream))

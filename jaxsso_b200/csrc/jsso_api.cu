@@ -88,6 +88,9 @@ struct jsso_handle {
   bool asm_tasks = false;
   int task_ctas = 148 * 4;       // persistent grid of assemble_tasks_kernel (resident CTAs)
   int adj_ctas = 148 * 2, adj_ctas_prop = 148 * 2;   // persistent grids of quad_adjoint_kernel<false/true>
+  // optional per-kernel timing of jsso_assemble (jsso_profile): events before / between / after its two kernels
+  bool prof = false;
+  cudaEvent_t ev_prof[3] = {nullptr, nullptr, nullptr};
   int32_t *node_inc_ptr = nullptr, *node_inc = nullptr;
   // numeric state
   double* vals = nullptr;   // nnzb*36, column-major blocks
@@ -354,6 +357,7 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_a) cudaStreamDestroy(h->st_a);
   if (h->st_b) cudaStreamDestroy(h->st_b);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
+  for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   delete h;
@@ -445,10 +449,12 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
   A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
   if (h->sym.nnzb() > 0 && h->asm_tasks) {
     const int nq = h->sym.n_quad;
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[0], st));
     if (nq > 0) {
       quad_geometry_kernel<<<cdiv(nq, 32), 128, 0, st>>>(nq, crds, h->cnct_q, prop_q, h->quad_rec, h->flags);
       CKL("quad_geometry_kernel");
     }
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[1], st));
     TaskArgs T;
     T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta; T.task_els = h->task_els;
     T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
@@ -458,12 +464,37 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
                             TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
     CKL("assemble_tasks_kernel");
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[2], st));
   } else if (h->sym.nnzb() > 0) {
     assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
     CKL("assemble_fused_kernel");
   }
   h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
   h->last_crds = crds;
+  return JSSO_OK;
+}
+
+// Per-kernel timing of the two-kernel assembly (bench.py roofline): enable, call jsso_assemble, read.
+int jsso_profile(jsso_handle* h, int enable) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  if (enable && !h->ev_prof[0])
+    for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&h->ev_prof[i]));
+  h->prof = enable != 0;
+  return JSSO_OK;
+}
+
+// ms[0] = quad_geometry_kernel, ms[1] = assemble_tasks_kernel of the LAST jsso_assemble (both 0 on the chunked path)
+int jsso_profile_read(jsso_handle* h, float* ms) {
+  if (!h || !ms) return JSSO_ERR_ARG;
+  NEED_GPU();
+  ms[0] = ms[1] = 0.f;
+  if (!h->prof || !h->asm_tasks || !h->assembled) return JSSO_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev_prof[2]));
+  CK(cudaEventElapsedTime(&ms[0], h->ev_prof[0], h->ev_prof[1]));
+  CK(cudaEventElapsedTime(&ms[1], h->ev_prof[1], h->ev_prof[2]));
   return JSSO_OK;
 }
 
