@@ -296,6 +296,17 @@ def run_b200(args):
             dist.all_gather_object(hs, h.p2p_export())
             h.p2p_connect(hs, lm.remote_start)
     mg_info = None
+    hg = None
+    if world > 1 and args.solve and args.precond != 'block_jacobi':
+        # N > 1: the multigrid tier is single-GPU, and the solve is > 99 % of a gradient evaluation, so every
+        # rank keeps a handle of the WHOLE mesh and runs the multigrid solve redundantly (1.2 ms of redundant
+        # assembly, no communication); Ke+assembly+adjoint of the metric stay partitioned.  --precond
+        # block_jacobi runs the distributed CG (halo pushes over NVLink peer memory) instead.
+        t_mg = time.perf_counter()
+        hg = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=local_rank)
+        hg.mg_setup()
+        mg_info = {'nodes_per_level': [a for a, _ in hg.mg_levels] + [hg.mg_levels[-1][1]],
+                   'symbolic_setup_s': time.perf_counter() - t_mg}
     if world == 1 and args.solve and args.precond != 'block_jacobi':
         # single GPU: smoothed-aggregation multigrid preconditioner (symbolic hierarchy, once per model)
         t_mg = time.perf_counter()
@@ -378,14 +389,22 @@ def run_b200(args):
     # full shape-gradient evaluation incl. the solve (metric M2), once
     grad_eval = None
     if args.solve:
-        precond = args.precond if world == 1 else 'block_jacobi'   # the multigrid path is single-GPU
+        precond = args.precond if (world == 1 or hg is not None) else 'block_jacobi'
         opts = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, check_every=100, compliance=True,
                              precond=precond, cheb_degree=args.cheb_degree)
         uu_d = D((md.ndof,))
+        if hg is not None:   # replicated multigrid solve on the whole mesh, partitioned adjoint
+            gc_d, gq_d, gb_d = D.from_host(gmd.crds), D.from_host(gmd.prop_quads), D.from_host(gmd.prop_beams)
+            gf_d, gu_d = D.from_host(gmd.loads), D((gmd.ndof,))
+            l2g_d = D.from_host(lm.l2g.astype(np.int32))
         barrier()
         t0 = time.perf_counter()
         try:
-            fs = h.forward(crds_d, pq_d, pb_d, f_d, uu_d, opts=opts)
+            if hg is not None:
+                fs = hg.forward(gc_d, gq_d, gb_d, gf_d, gu_d, opts=opts)
+                nat.gather_rows(gu_d, l2g_d, 6, out=uu_d)
+            else:
+                fs = h.forward(crds_d, pq_d, pb_d, f_d, uu_d, opts=opts)
             h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=opts)
             L.jsso_stream_sync(None)
             ok = True
@@ -397,7 +416,10 @@ def run_b200(args):
                          'pcg_restarts': fs.restarts, 'true_relres': fs.relres, 'rtol': args.rtol,
                          'ms_per_pcg_iteration': 1e3 * dt / max(fs.iterations, 1),
                          'preconditioner': (f'smoothed-aggregation multigrid (V-cycle, Chebyshev-{args.cheb_degree}, FP32 level matrices)'
-                                            if (world == 1 and precond != 'block_jacobi') else 'block-Jacobi'),
+                                            if precond != 'block_jacobi' else 'block-Jacobi'),
+                         'solve': ('single GPU' if world == 1 else
+                                   ('replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
+                                    else 'distributed CG over the partition')),
                          'multigrid': mg_info,
                          'note': 'Ke+assembly, PCG for u (numeric multigrid setup included), lam = u/2 '
                                  '(compliance), adjoint'}

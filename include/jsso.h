@@ -156,6 +156,9 @@ int jsso_csr_spmv(int32_t n_row, const int32_t* rowptr_d, const int32_t* colidx_
 int jsso_assemble(jsso_handle* h, const double* crds_d, const double* prop_q_d, const double* prop_b_d,
                   int apply_bc, void* stream);
 /* Stand-alone segmented reduction of materialised element matrices. */
+/* dst_d[i*width + k] = src_d[idx_d[i]*width + k], i < n: node-row gather between numberings on the current
+ * device (the local part of a replicated global vector for a partitioned handle). */
+int jsso_gather_rows(const double* src_d, const int32_t* idx_d, int32_t n, int32_t width, double* dst_d, void* stream);
 /* Per-kernel timing of jsso_assemble's two kernels (CUDA events on the caller's stream; measurement aid for
  * bench.py): jsso_profile(h, 1), then after any jsso_assemble, ms[0] = quad_geometry_kernel, ms[1] =
  * assemble_tasks_kernel of the last call. */

@@ -65,7 +65,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_assembly_tasks',
-           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
+           'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_gather_rows', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
@@ -103,6 +103,7 @@ def lib():
     L.jsso_assemble.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.jsso_assemble_from_ke.argtypes = [vp, vp, vp, C.c_int, vp]
     L.jsso_profile.argtypes = [vp, C.c_int]
+    L.jsso_gather_rows.argtypes = [vp, vp, i32, i32, vp, vp]
     L.jsso_profile_read.argtypes = [vp, vp]
     L.jsso_get_values.argtypes = [vp, vp, vp]
     L.jsso_get_values_host.argtypes = [vp, vp]
@@ -470,6 +471,16 @@ class Handle:
 
     def halo_exchange(self, vec, stream=None):
         self._ck(lib().jsso_halo_exchange(self.h, _dp(vec), stream))
+
+
+def gather_rows(src, idx, width, out=None, stream=None):
+    """out[i, :] = src[idx[i], :] on the device (src, idx, out: DeviceArray; idx int32)."""
+    n = int(np.prod(idx.shape))
+    out = DeviceArray((n * width,)) if out is None else out
+    rc = lib().jsso_gather_rows(src.ptr, idx.ptr, n, width, out.ptr, stream)
+    if rc:
+        raise JssoError(rc, 'jsso_gather_rows')
+    return out
 
 
 def nccl_unique_id():

@@ -474,6 +474,17 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
   return JSSO_OK;
 }
 
+// dst[i*width + k] = src[idx[i]*width + k]: node-row gather between numberings (e.g. the local part
+// u_global[l2g] of a replicated solve for the partitioned adjoint)
+int jsso_gather_rows(const double* src_d, const int32_t* idx_d, int32_t n, int32_t width, double* dst_d, void* stream) {
+  if (n < 0 || width <= 0 || (n > 0 && (!src_d || !idx_d || !dst_d))) return JSSO_ERR_ARG;
+  if (n == 0) return JSSO_OK;
+  const long long total = (long long)n * width;
+  gather_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(total, width, src_d, idx_d, dst_d);
+  LAUNCHED();
+  return cudaGetLastError() == cudaSuccess ? JSSO_OK : JSSO_ERR_CUDA;
+}
+
 // Per-kernel timing of the two-kernel assembly (bench.py roofline): enable, call jsso_assemble, read.
 int jsso_profile(jsso_handle* h, int enable) {
   if (!h) return JSSO_ERR_ARG;

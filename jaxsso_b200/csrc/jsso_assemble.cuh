@@ -660,6 +660,15 @@ csr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   if (row < n_row && sub == 0) y[row] = s;
 }
 
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(long long total, int width, const double* __restrict__ src, const int32_t* __restrict__ idx,
+                   double* __restrict__ dst) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  const long long i = o / width;
+  dst[o] = src[(size_t)idx[i] * width + (o - i * width)];
+}
+
 // Boundary conditions on an already assembled matrix (values given by the caller)
 __global__ void __launch_bounds__(256)
 apply_bc_kernel(long long n_out, const int32_t* __restrict__ blk_row, const int32_t* __restrict__ colidx,
