@@ -78,8 +78,11 @@ __device__ inline void adj_stage(double* rec, int q, int nd, int e, const double
 // more batch ahead, in a register) streams into the other stage buffer with cp.async while this batch is
 // differentiated, so the two-deep global-load chain cnct -> (crds, u, lam) is exposed only once per CTA.
 // Warps never exchange data with each other (a quad's four lanes share a warp): __syncwarp only.
+#ifndef JSSO_ADJ_MINB
+#define JSSO_ADJ_MINB 2   // resident CTAs per SM the register allocation aims at (3 -> 168 registers)
+#endif
 template <bool WANT_PROP>
-__global__ void __launch_bounds__(4 * ADJ_QUADS)
+__global__ void __launch_bounds__(4 * ADJ_QUADS, JSSO_ADJ_MINB)
 quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                     const double* __restrict__ prop, const double* __restrict__ u,
                     const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
@@ -286,13 +289,15 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
     // recover J from J^-1: J = det * [[ji3, -ji1], [-ji2, ji0]]
     const double j00 = g.det * g.ji[3], j01 = -g.det * g.ji[1], j10 = -g.det * g.ji[2], j11 = g.det * g.ji[0];
     const double n1 = j10 * j10 + j11 * j11, n0 = j00 * j00 + j01 * j01;
-    const double qq = 0.25 / g.det, w = sqrt(n1 * n0);
+    // one division and one rsqrt for 1/det, sqrt(n1 n0) and 1/sqrt(n1 n0)
+    const double idet = 1.0 / g.det, iw = rsqrt(n1 * n0);
+    const double qq = 0.25 * idet, w = (n1 * n0) * iw;
     double n1b = Prrb * qq, n0b = Pssb * qq;
     double qb = Prrb * n1 + Pssb * n0 + Prsb * w;
     const double wb = Prsb * qq;
-    n1b += wb * n0 / (2.0 * w);
-    n0b += wb * n1 / (2.0 * w);
-    const double detb = -qb * qq / g.det;
+    n1b += wb * n0 * (0.5 * iw);
+    n0b += wb * n1 * (0.5 * iw);
+    const double detb = -qb * qq * idet;
     const double j00b = 2.0 * j00 * n0b + detb * j11, j01b = 2.0 * j01 * n0b - detb * j10;
     const double j10b = 2.0 * j10 * n1b - detb * j01, j11b = 2.0 * j11 * n1b + detb * j00;
 #pragma unroll
@@ -330,11 +335,11 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
     const double* x = f.x; const double* y = f.y;
     const double rx = ((x[0] + x[3]) - (x[1] + x[2])) * 0.5, ry = ((y[0] + y[3]) - (y[1] + y[2])) * 0.5;
     const double sx = ((x[0] + x[1]) - (x[2] + x[3])) * 0.5, sy = ((y[0] + y[1]) - (y[2] + y[3])) * 0.5;
-    const double nr = sqrt(rx * rx + ry * ry), ns = sqrt(sx * sx + sy * sy);
+    const double inr = rsqrt(rx * rx + ry * ry), ins = rsqrt(sx * sx + sy * sy);   // 1/|r|, 1/|s|
     const double sig = ((ry < 0.0) != (sy < 0.0)) ? -1.0 : 1.0;
-    const double Nb = m12b / (nr * ns), nrb = -m12b * sh.m12 / nr, nsb = -m12b * sh.m12 / ns;
-    const double rxb = -Nb * sx + nrb * rx / nr, ryb = Nb * sig * sy + nrb * ry / nr;
-    const double sxb = -Nb * rx + nsb * sx / ns, syb = Nb * sig * ry + nsb * sy / ns;
+    const double Nb = m12b * (inr * ins), nrb = -m12b * sh.m12 * inr, nsb = -m12b * sh.m12 * ins;
+    const double rxb = -Nb * sx + nrb * rx * inr, ryb = Nb * sig * sy + nrb * ry * inr;
+    const double sxb = -Nb * rx + nsb * sx * ins, syb = Nb * sig * ry + nsb * sy * ins;
     xb[0] += 0.5 * (rxb + sxb); xb[1] += 0.5 * (sxb - rxb); xb[3] += 0.5 * (rxb - sxb);
     yb[0] += 0.5 * (ryb + syb); yb[1] += 0.5 * (syb - ryb); yb[3] += 0.5 * (ryb - syb);
   }
@@ -372,9 +377,9 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
                   v31[0] * v42[1] - v31[1] * v42[0]};
   double yr[3] = {zr[1] * v31[2] - zr[2] * v31[1], zr[2] * v31[0] - zr[0] * v31[2],
                   zr[0] * v31[1] - zr[1] * v31[0]};
-  const double inx = 1.0 / sqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
-  const double iny = 1.0 / sqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
-  const double inz = 1.0 / sqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
+  const double inx = rsqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
+  const double iny = rsqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
+  const double inz = rsqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
   const double dx = f.R[0][0] * Rb[0][0] + f.R[0][1] * Rb[0][1] + f.R[0][2] * Rb[0][2];
   const double dy = f.R[1][0] * Rb[1][0] + f.R[1][1] * Rb[1][1] + f.R[1][2] * Rb[1][2];
   const double dz = f.R[2][0] * Rb[2][0] + f.R[2][1] * Rb[2][1] + f.R[2][2] * Rb[2][2];
@@ -426,12 +431,16 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
       const double e_b = bcon * m.D, e_s = Sh * m.ks;
       const double dsv = m.D * (kba + m.hb * kbb) + m.ks * ksc;   // the selected diagonal entry
       const double sg = sgn * 1e-3 * theta;                       // e_d = sg * dsv
-      const double omn = 1.0 - nu * nu, pre = 1.0 / omn, dpre = 2.0 * nu * pre * pre, tE = th * E;
-      const double de_dt = (e_m + 3.0 * e_b + e_s) / th + sg * (3.0 * m.D * (kba + m.hb * kbb) + m.ks * ksc) / th;
-      const double de_dE = (e_m + e_b + e_s + sg * dsv) / E;
+      // the four reciprocals 1/t, 1/E, 1/(1+nu), 1/(1-nu^2) from ONE division
+      const double tE = th * E, cd = (1.0 + nu) * (1.0 - nu);
+      const double rr = 1.0 / (tE * cd);
+      const double pre = rr * tE, inv_tE = rr * cd, ip = pre * (1.0 - nu), dpre = 2.0 * nu * pre * pre;
+      const double inv_th = inv_tE * E, inv_E = inv_tE * th;
+      const double de_dt = ((e_m + 3.0 * e_b + e_s) + sg * (3.0 * m.D * (kba + m.hb * kbb) + m.ks * ksc)) * inv_th;
+      const double de_dE = (e_m + e_b + e_s + sg * dsv) * inv_E;
       const double dem = tE * (dpre * (kx * (Mxx + nu * Mxy) + ky * (nu * Myx + Myy)) + pre * (kx * Mxy + ky * Myx)) -
-                         tE * Mss / (2.0 * (1.0 + nu) * (1.0 + nu));
-      const double dD = m.D * 2.0 * nu / omn, dks = -m.ks / (1.0 + nu);
+                         tE * Mss * (0.5 * ip * ip);
+      const double dD = m.D * 2.0 * nu * pre, dks = -m.ks * ip;
       const double deb = dD * bcon + m.D * (Bnu - 0.5 * Bss);
       const double ddsel = dD * (kba + m.hb * kbb) - 0.5 * m.D * kbb + dks * ksc;
       double* o = d_prop + 5 * (size_t)e;

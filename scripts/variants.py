@@ -4,16 +4,9 @@ them on the GPU box:   python scripts/variants.py build      (here, no GPU)
 import os, subprocess, sys
 sys.path.insert(0, '.')
 VARIANTS = {
-    'base':      [],
-    'nodeep':    ['JSSO_T_DEEP=0'],
-    'nol2':      ['JSSO_T_L2PF=0'],
-    'nodeep_nol2': ['JSSO_T_DEEP=0', 'JSSO_T_L2PF=0'],
-    'nodeep_nol2_unroll': ['JSSO_T_DEEP=0', 'JSSO_T_L2PF=0', 'JSSO_T_UNROLL1=0'],
-    'nodeep_nol2_g62': ['JSSO_T_DEEP=0', 'JSSO_T_L2PF=0', 'JSSO_T_GLD=62'],
-    'out1':      ['JSSO_T_OUT=1'],
-    'out1_nodeep_nol2': ['JSSO_T_OUT=1', 'JSSO_T_DEEP=0', 'JSSO_T_L2PF=0'],
-    'warps8':    ['JSSO_T_WARPS=8'],
-    'warps2':    ['JSSO_T_WARPS=2'],
+    'base':   [],
+    'adj3':   ['JSSO_ADJ_MINB=3'],
+    'adj4':   ['JSSO_ADJ_MINB=4'],
 }
 VDIR = os.path.join('jaxsso_b200', 'variants')
 
@@ -30,7 +23,7 @@ def build():
 def run(N):
     for name in VARIANTS:
         env = dict(os.environ, JSSO_LIB=os.path.abspath(os.path.join(VDIR, f'libjsso_{name}.so')))
-        r = subprocess.run([sys.executable, 'scripts/asm_time.py', str(N)], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, os.environ.get('JSSO_VARIANT_SCRIPT', 'scripts/asm_time.py'), str(N)], env=env, capture_output=True, text=True)
         print(f'{name:22s}', (r.stdout.strip().splitlines() or ['?'])[-1], r.stderr.strip()[-300:], flush=True)
 
 
