@@ -40,9 +40,10 @@ using D3 = Dual<3>;
 constexpr int ADJ_QUADS = 32;        // quads per batch (128 threads)
 constexpr int ADJ_ST = 66;           // doubles per quad of the gather stage: P 0..11 | u 12..35 | lam 36..59 | prop 60..64
                                      // (even: 16-byte aligned rows; 66 k mod 16 distinct for the 8 quads of a warp)
-constexpr int ADJ_LD = 49;           // doubles per quad of the local-vector buffer (odd stride)
+constexpr int ADJ_LD = 61;           // doubles per quad of the local-vector buffer (odd stride): UL 24 | LL 24 | 12 property sums
 constexpr int A_P = 0, A_UG = 12, A_LG = 36, A_PR = 60;   // gather stage: coordinates, global u, global lam, properties
-constexpr int A_UL = 0, A_LL = 24;             // local-vector buffer: local u, local lam
+constexpr int A_UL = 0, A_LL = 24, A_PS = 48;  // local-vector buffer: local u, local lam, property sums
+constexpr int ADJ_SMEM_DOUBLES = 2 * ADJ_QUADS * ADJ_ST + ADJ_QUADS * ADJ_LD;   // 49 408 B of dynamic shared memory
 
 __device__ inline double quad4_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -86,20 +87,20 @@ __global__ void __launch_bounds__(4 * ADJ_QUADS, JSSO_ADJ_MINB)
 quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                     const double* __restrict__ prop, const double* __restrict__ u,
                     const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
-  __shared__ __align__(16) double stg[2][ADJ_QUADS * ADJ_ST];
-  __shared__ double sv[ADJ_QUADS * ADJ_LD];
+  extern __shared__ __align__(16) double adj_sm[];
+  double* const sv = adj_sm + 2 * ADJ_QUADS * ADJ_ST;
   const int le = threadIdx.x >> 2, q = threadIdx.x & 3;
   const int n_batch = (n_quad + ADJ_QUADS - 1) / ADJ_QUADS;
   const int G = gridDim.x;
   int batch = blockIdx.x;
   if (batch >= n_batch) return;
   int nd_next = cnct[4 * min(batch * ADJ_QUADS + le, n_quad - 1) + q];
-  adj_stage(stg[0] + le * ADJ_ST, q, nd_next, min(batch * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
+  adj_stage(adj_sm + le * ADJ_ST, q, nd_next, min(batch * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
   nd_next = (batch + G < n_batch) ? cnct[4 * min((batch + G) * ADJ_QUADS + le, n_quad - 1) + q] : 0;
   for (int it = 0; batch < n_batch; batch += G, ++it) {
   const bool has_next = batch + G < n_batch;
   if (has_next)
-    adj_stage(stg[(it + 1) & 1] + le * ADJ_ST, q, nd_next, min((batch + G) * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
+    adj_stage(adj_sm + ((it + 1) & 1) * (ADJ_QUADS * ADJ_ST) + le * ADJ_ST, q, nd_next, min((batch + G) * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
   if (batch + 2 * G < n_batch) nd_next = cnct[4 * min((batch + 2 * G) * ADJ_QUADS + le, n_quad - 1) + q];
   if (has_next) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
   else asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -107,7 +108,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   int e = batch * ADJ_QUADS + le;
   const bool valid = e < n_quad;
   if (!valid) e = n_quad - 1;
-  const double* sg = stg[it & 1] + le * ADJ_ST;
+  const double* sg = adj_sm + (it & 1) * (ADJ_QUADS * ADJ_ST) + le * ADJ_ST;
   double* sm = sv + le * ADJ_LD;
   const double* UG = sg + A_UG;
   const double* LG = sg + A_LG;
@@ -194,6 +195,20 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   const double Mxu = m.D * (kxl + m.nu * kyl), Myu = m.D * (kyl + m.nu * kxl), Mzu = m.D * m.hb * kzl;
   const double Mxl = m.D * (kxu + m.nu * kyu), Myl = m.D * (kyu + m.nu * kxu), Mzl = m.D * m.hb * kzu;
   const double Phi = exl * Nxl + eyl * Nyl + gxl * Nsl + kxl * Mxl + kyl * Myl + kzl * Mzl;
+  if (WANT_PROP) {
+    // membrane / bending value sums of the closed-form property derivatives: summed over the Gauss points
+    // now and parked in shared memory, so that the strains do not stay live to the end of the kernel
+    const double Mxx = quad4_sum(g.det * exl * exu), Mxy = quad4_sum(g.det * exl * eyu);
+    const double Myx = quad4_sum(g.det * eyl * exu), Myy = quad4_sum(g.det * eyl * eyu);
+    const double Mss = quad4_sum(g.det * gxl * gxu);
+    const double Bsum = quad4_sum(g.det * (kxl * kxu + kyl * kyu));
+    const double Bnu = quad4_sum(g.det * (kxl * kyu + kyl * kxu));
+    const double Bss = quad4_sum(g.det * kzl * kzu);
+    if (q == 0) {
+      double* ps = sm + A_PS;
+      ps[0] = Mxx; ps[1] = Mxy; ps[2] = Myx; ps[3] = Myy; ps[4] = Mss; ps[5] = Bsum; ps[6] = Bnu; ps[7] = Bss;
+    }
+  }
   // S_phi = dPhi/d(grad phi) for the eight fields
   //   u: (Nx, Ns)  v: (Ns, Ny)  thx: (Mz, My)  thy: (-Mx, -Mz)
   const double Tx0 = Nxu * a0 + Nsu * b0 + Mzu * c0 - Mxu * d0 + Nxl * A0 + Nsl * B0 + Mzl * C0 - Mxl * D0;
@@ -416,15 +431,11 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   }
   if (WANT_PROP) {
     // value accumulators for the closed-form property derivatives (summed over Gauss points)
-    const double Mxx = quad4_sum(g.det * exl * exu), Mxy = quad4_sum(g.det * exl * eyu);
-    const double Myx = quad4_sum(g.det * eyl * exu), Myy = quad4_sum(g.det * eyl * eyu);
-    const double Mss = quad4_sum(g.det * gxl * gxu);
-    const double Bsum = quad4_sum(g.det * (kxl * kxu + kyl * kyu));
-    const double Bnu = quad4_sum(g.det * (kxl * kyu + kyl * kxu));
-    const double Bss = quad4_sum(g.det * kzl * kzu);
     const double Sh = quad4_sum(sh.m11 * g.prr * Crr + sh.m12 * g.prs * Crs + sh.m22 * g.pss * Css);
     const double kba = quad4_sum(kb_a), kbb = quad4_sum(kb_b), ksc = quad4_sum(ks_c);
     if (valid && q == 0 && d_prop) {
+      const double* ps = sm + A_PS;   // written by this same lane above
+      const double Mxx = ps[0], Mxy = ps[1], Myx = ps[2], Myy = ps[3], Mss = ps[4], Bsum = ps[5], Bnu = ps[6], Bss = ps[7];
       const double th = pr[0], E = pr[1], nu = pr[2], kx = pr[3], ky = pr[4];
       const double e_m = Mxx * m.cm11 + Mxy * m.cm12 + Myx * m.cm21 + Myy * m.cm22 + Mss * m.cm33;
       const double bcon = Bsum + Bnu * nu + Bss * m.hb;

@@ -266,9 +266,12 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
                                                      TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double)));
     h->task_ctas = std::max(1, occ) * prop.multiProcessorCount;
     if (const char* e = std::getenv("JSSO_TASK_CTAS")) h->task_ctas = std::max(1, std::atoi(e));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<false>, 4 * ADJ_QUADS, 0));
+    const size_t adj_smem = ADJ_SMEM_DOUBLES * sizeof(double);
+    CK(cudaFuncSetAttribute(quad_adjoint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+    CK(cudaFuncSetAttribute(quad_adjoint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<false>, 4 * ADJ_QUADS, adj_smem));
     h->adj_ctas = std::max(1, occ) * prop.multiProcessorCount;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<true>, 4 * ADJ_QUADS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_adjoint_kernel<true>, 4 * ADJ_QUADS, adj_smem));
     h->adj_ctas_prop = std::max(1, occ) * prop.multiProcessorCount;
   }
   return JSSO_OK;
@@ -1257,10 +1260,10 @@ int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const
   if (S.n_quad > 0) {
     const int blocks = std::min(cdiv(S.n_quad, ADJ_QUADS), d_prop_q ? h->adj_ctas_prop : h->adj_ctas);
     if (d_prop_q)
-      quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
+      quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
                                                                  d_crds ? h->corner_q : nullptr, d_prop_q);
     else
-      quad_adjoint_kernel<false><<<blocks, 4 * ADJ_QUADS, 0, st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
+      quad_adjoint_kernel<false><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
                                                                   d_crds ? h->corner_q : nullptr, nullptr);
     CKL("quad_adjoint_kernel");
   }
