@@ -40,10 +40,10 @@ using D3 = Dual<3>;
 constexpr int ADJ_QUADS = 32;        // quads per batch (128 threads)
 constexpr int ADJ_ST = 66;           // doubles per quad of the gather stage: P 0..11 | u 12..35 | lam 36..59 | prop 60..64
                                      // (even: 16-byte aligned rows; 66 k mod 16 distinct for the 8 quads of a warp)
-constexpr int ADJ_LD = 61;           // doubles per quad of the local-vector buffer (odd stride): UL 24 | LL 24 | 12 property sums
+constexpr int ADJ_LD = 87;           // doubles per quad of the local-vector buffer (odd stride): UL 24 | LL 24 | 12 property sums | 6 local xy | 11 shear data | 9 material
 constexpr int A_P = 0, A_UG = 12, A_LG = 36, A_PR = 60;   // gather stage: coordinates, global u, global lam, properties
-constexpr int A_UL = 0, A_LL = 24, A_PS = 48;  // local-vector buffer: local u, local lam, property sums
-constexpr int ADJ_SMEM_DOUBLES = 2 * ADJ_QUADS * ADJ_ST + ADJ_QUADS * ADJ_LD;   // 49 408 B of dynamic shared memory
+constexpr int A_UL = 0, A_LL = 24, A_PS = 48, A_XY = 60, A_SH = 66, A_MT = 77;  // local-vector buffer: local u, local lam, property sums, local x0 y0 x1 y1 x3 y3
+constexpr int ADJ_SMEM_DOUBLES = 2 * ADJ_QUADS * ADJ_ST + ADJ_QUADS * ADJ_LD;   // 56 064 B of dynamic shared memory
 
 __device__ inline double quad4_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -130,6 +130,12 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
       sm[A_LL + 6 * q + i] = f.R[i][0] * lg[0] + f.R[i][1] * lg[1] + f.R[i][2] * lg[2];
       sm[A_LL + 6 * q + 3 + i] = f.R[i][0] * lg[3] + f.R[i][1] * lg[4] + f.R[i][2] * lg[5];
     }
+    // the frame is NOT kept in registers: the pull-back at the end recomputes dirCos from the staged
+    // coordinates (same expressions), and the m12 section re-reads the local coordinates from here
+    if (q == 0) {
+      sm[A_XY] = f.x[0]; sm[A_XY + 1] = f.y[0]; sm[A_XY + 2] = f.x[1]; sm[A_XY + 3] = f.y[1];
+      sm[A_XY + 4] = f.x[3]; sm[A_XY + 5] = f.y[3];
+    }
   }
   __syncwarp();
   const double* UL = sm + A_UL;   // local u: per node [u, v, w, thx, thy, thz]
@@ -139,6 +145,28 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   quad_mat(pr, m);
   QuadShear<double> sh;
   quad_shear(f, sh);
+  // per-quad constants are parked in shared memory and RE-LOADED at the head of the later sections
+  // (ADJ_RELOAD), so that they do not occupy 40 registers from here to the end of the kernel
+  if (q == 0) {
+    double* p = sm + A_SH;
+    p[0] = sh.gry[0]; p[1] = sh.gry[1]; p[2] = sh.grx[0]; p[3] = sh.grx[1];
+    p[4] = sh.gsy[0]; p[5] = sh.gsy[1]; p[6] = sh.gsx[0]; p[7] = sh.gsx[1];
+    p[8] = sh.m11; p[9] = sh.m12; p[10] = sh.m22;
+    double* t = sm + A_MT;
+    t[0] = m.cm11; t[1] = m.cm12; t[2] = m.cm21; t[3] = m.cm22; t[4] = m.cm33;
+    t[5] = m.D; t[6] = m.nu; t[7] = m.hb; t[8] = m.ks;
+  }
+  __syncwarp();
+#define ADJ_RELOAD()                                                                        \
+  do {                                                                                      \
+    const double* p_ = sm + A_SH;                                                           \
+    sh.gry[0] = p_[0]; sh.gry[1] = p_[1]; sh.grx[0] = p_[2]; sh.grx[1] = p_[3];             \
+    sh.gsy[0] = p_[4]; sh.gsy[1] = p_[5]; sh.gsx[0] = p_[6]; sh.gsx[1] = p_[7];             \
+    sh.m11 = p_[8]; sh.m12 = p_[9]; sh.m22 = p_[10];                                        \
+    const double* t_ = sm + A_MT;                                                           \
+    m.cm11 = t_[0]; m.cm12 = t_[1]; m.cm21 = t_[2]; m.cm22 = t_[3]; m.cm33 = t_[4];         \
+    m.D = t_[5]; m.nu = t_[6]; m.hb = t_[7]; m.ks = t_[8];                                  \
+  } while (0)
   QuadGp<double> g;
   quad_gp(f, q, g);
   const double r = JSSO_GP * node_r(q), s = JSSO_GP * node_s(q);
@@ -232,6 +260,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
       Rb[1][c] += vb * UG[6 * k + c] + tyb * UG[6 * k + 3 + c] + Vb * LG[6 * k + c] + Tyb * LG[6 * k + 3 + c];
     }
   }
+  ADJ_RELOAD();
   // ---- MITC4 shear
   // covariant edge strains of u and lam: index 0: A0 (edge 1-2), 1: A1 (edge 4-3), 2: B0 (1-4), 3: B1 (2-3)
   // edge e: nodes (n1, n2), w-coefficient +1/2 on n1 and -1/2 on n2, theta sums weighted by gy/gx
@@ -323,6 +352,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
       yb[k] += dr * j01b + ds * j11b;
     }
   }
+  ADJ_RELOAD();
   // ---- edge strains -> local vectors (dirCos rows 2, 0, 1) and edge geometry
   {
     const int n1[4] = {0, 3, 0, 1}, n2[4] = {1, 2, 3, 2};
@@ -347,9 +377,9 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   }
   // ---- m12 = (|ry||sy| - rx sx)/(nr ns) -> local coordinates
   {
-    const double* x = f.x; const double* y = f.y;
-    const double rx = ((x[0] + x[3]) - (x[1] + x[2])) * 0.5, ry = ((y[0] + y[3]) - (y[1] + y[2])) * 0.5;
-    const double sx = ((x[0] + x[1]) - (x[2] + x[3])) * 0.5, sy = ((y[0] + y[1]) - (y[2] + y[3])) * 0.5;
+    const double x0 = sm[A_XY], y0 = sm[A_XY + 1], x1 = sm[A_XY + 2], y1 = sm[A_XY + 3], x3 = sm[A_XY + 4], y3 = sm[A_XY + 5];
+    const double rx = ((x0 + x3) - x1) * 0.5, ry = ((y0 + y3) - y1) * 0.5;   // node 3 (index 2) is the origin
+    const double sx = ((x0 + x1) - x3) * 0.5, sy = ((y0 + y1) - y3) * 0.5;
     const double inr = rsqrt(rx * rx + ry * ry), ins = rsqrt(sx * sx + sy * sy);   // 1/|r|, 1/|s|
     const double sig = ((ry < 0.0) != (sy < 0.0)) ? -1.0 : 1.0;
     const double Nb = m12b * (inr * ins), nrb = -m12b * sh.m12 * inr, nsb = -m12b * sh.m12 * ins;
@@ -383,11 +413,9 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
     v34[c] = p3 - p2; v42[c] = p1 - p3;
     Rb[0][c] += xb[0] * v31[c] + xb[1] * v32[c] + xb[3] * v34[c];
     Rb[1][c] += yb[0] * v31[c] + yb[1] * v32[c] + yb[3] * v34[c];
-    vb31[c] = xb[0] * f.R[0][c] + yb[0] * f.R[1][c];
-    vb32[c] = xb[1] * f.R[0][c] + yb[1] * f.R[1][c];
-    vb34[c] = xb[3] * f.R[0][c] + yb[3] * f.R[1][c];
   }
   // ---- frame: e_x = v31/|v31|, z_r = v31 x v42, y_r = z_r x v31, e_y = y_r/|y_r|, e_z = z_r/|z_r|
+  // (dirCos recomputed here exactly as quad_frame does, instead of living in registers since the start)
   double zr[3] = {v31[1] * v42[2] - v31[2] * v42[1], v31[2] * v42[0] - v31[0] * v42[2],
                   v31[0] * v42[1] - v31[1] * v42[0]};
   double yr[3] = {zr[1] * v31[2] - zr[2] * v31[1], zr[2] * v31[0] - zr[0] * v31[2],
@@ -395,15 +423,23 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   const double inx = rsqrt(v31[0] * v31[0] + v31[1] * v31[1] + v31[2] * v31[2]);
   const double iny = rsqrt(yr[0] * yr[0] + yr[1] * yr[1] + yr[2] * yr[2]);
   const double inz = rsqrt(zr[0] * zr[0] + zr[1] * zr[1] + zr[2] * zr[2]);
-  const double dx = f.R[0][0] * Rb[0][0] + f.R[0][1] * Rb[0][1] + f.R[0][2] * Rb[0][2];
-  const double dy = f.R[1][0] * Rb[1][0] + f.R[1][1] * Rb[1][1] + f.R[1][2] * Rb[1][2];
-  const double dz = f.R[2][0] * Rb[2][0] + f.R[2][1] * Rb[2][1] + f.R[2][2] * Rb[2][2];
+  double R0[3], R1[3], R2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    R0[c] = v31[c] * inx; R1[c] = yr[c] * iny; R2[c] = zr[c] * inz;
+    vb31[c] = xb[0] * R0[c] + yb[0] * R1[c];
+    vb32[c] = xb[1] * R0[c] + yb[1] * R1[c];
+    vb34[c] = xb[3] * R0[c] + yb[3] * R1[c];
+  }
+  const double dx = R0[0] * Rb[0][0] + R0[1] * Rb[0][1] + R0[2] * Rb[0][2];
+  const double dy = R1[0] * Rb[1][0] + R1[1] * Rb[1][1] + R1[2] * Rb[1][2];
+  const double dz = R2[0] * Rb[2][0] + R2[1] * Rb[2][1] + R2[2] * Rb[2][2];
   double yrb[3], zrb[3], vb42[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    vb31[c] += (Rb[0][c] - f.R[0][c] * dx) * inx;
-    yrb[c] = (Rb[1][c] - f.R[1][c] * dy) * iny;
-    zrb[c] = (Rb[2][c] - f.R[2][c] * dz) * inz;
+    vb31[c] += (Rb[0][c] - R0[c] * dx) * inx;
+    yrb[c] = (Rb[1][c] - R1[c] * dy) * iny;
+    zrb[c] = (Rb[2][c] - R2[c] * dz) * inz;
   }
   // y_r = z_r x v31:  z_r_bar += v31 x y_r_bar,  v31_bar += y_r_bar x z_r
   zrb[0] += v31[1] * yrb[2] - v31[2] * yrb[1];
@@ -430,6 +466,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
     }
   }
   if (WANT_PROP) {
+    ADJ_RELOAD();
     // value accumulators for the closed-form property derivatives (summed over Gauss points)
     const double Sh = quad4_sum(sh.m11 * g.prr * Crr + sh.m12 * g.prs * Crs + sh.m22 * g.pss * Css);
     const double kba = quad4_sum(kb_a), kbb = quad4_sum(kb_b), ksc = quad4_sum(ks_c);
@@ -461,6 +498,7 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   }
   __syncwarp();   // this batch's stage and local vectors are dead: the next iterations may overwrite them
   }  // batch loop
+#undef ADJ_RELOAD
 }
 
 // e = lam_e^T K_e u_e for a beam-column, K_e = T^T K_local T (orthonormal T).
