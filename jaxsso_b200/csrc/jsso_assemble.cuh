@@ -16,16 +16,19 @@
 
 namespace jsso {
 
-// shared-memory record of one quad (doubles); odd stride => conflict-free across quads
-constexpr int QS = 71;
+// shared-memory record of one quad (doubles).  Every field group starts on an even offset and the stride is
+// even, so that quad_pair_block reads the record with 16-byte loads (lanes working on the same quad read the
+// same address: one broadcast wavefront moves twice the data of an 8-byte load); 70 k mod 16 is distinct for 8
+// consecutive quads (the per-Gauss-point staging phase).
+constexpr int QS = 70;
 constexpr int Q_R = 0;      // 9: dirCos rows x^,y^,z^
-constexpr int Q_GRY = 9;    // 2
-constexpr int Q_GRX = 11;   // 2
-constexpr int Q_GSY = 13;   // 2
-constexpr int Q_GSX = 15;   // 2
-constexpr int Q_M = 17;     // m11, m12, m22
-constexpr int Q_KRZ = 20;
-constexpr int Q_MAT = 21;   // cm11 cm12 cm21 cm22 cm33 D nu hb ks
+constexpr int Q_KRZ = 9;    // drilling stiffness                      -> (R, krz) = 5 pairs
+constexpr int Q_MAT = 10;   // cm11 cm12 cm21 cm22 cm33 D nu hb ks
+constexpr int Q_M = 19;     // m11, m12, m22                           -> (MAT, M) = 6 pairs
+constexpr int Q_GRY = 22;   // 2
+constexpr int Q_GRX = 24;   // 2
+constexpr int Q_GSY = 26;   // 2
+constexpr int Q_GSX = 28;   // 2
 constexpr int Q_GP = 30;    // 4 x {ji0..3, det, prr, prs, pss}
 constexpr int Q_XY = 62;    // x0,y0,x1,y1,x3,y3 local coordinates (node 3 is the origin) -> 68
 
@@ -139,35 +142,44 @@ __device__ inline void rtsr_diag(const double* R, double s00, double s01, double
 // 6x6 global block (a,b) of a quad from its staged record `s`, ADDED into the column-major
 // accumulator out[6*j+i].
 __device__ inline void quad_pair_block(const double* s, int a, int b, double* out) {
+  const double2* s2 = (const double2*)s;   // 16-byte aligned record (even stride, aligned base)
   const double ra = node_r(a), sa = node_s(a), rb = node_r(b), sb = node_s(b);
   double pxx = 0, pxy = 0, pyx = 0, pyy = 0, crr = 0, crs = 0, csr = 0, css = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const double* g = s + Q_GP + 8 * q;
+    const double2 j01 = s2[Q_GP / 2 + 4 * q], j23 = s2[Q_GP / 2 + 4 * q + 1];      // J^-1
+    const double2 dp = s2[Q_GP / 2 + 4 * q + 2], ps = s2[Q_GP / 2 + 4 * q + 3];    // (det, prr), (prs, pss)
     const double r = JSSO_GP * node_r(q), t = JSSO_GP * node_s(q);
     const double far = 1.0 + t * sa, fas = 1.0 + r * ra, fbr = 1.0 + t * sb, fbs = 1.0 + r * rb;
     const double dra = 0.25 * ra * far, dsa = 0.25 * sa * fas;
     const double drb = 0.25 * rb * fbr, dsb = 0.25 * sb * fbs;
-    const double ha0 = g[0] * dra + g[1] * dsa, ha1 = g[2] * dra + g[3] * dsa;
-    const double hb0 = g[0] * drb + g[1] * dsb, hb1 = g[2] * drb + g[3] * dsb;
-    const double d0 = g[4] * ha0, d1 = g[4] * ha1;
+    const double ha0 = j01.x * dra + j01.y * dsa, ha1 = j23.x * dra + j23.y * dsa;
+    const double hb0 = j01.x * drb + j01.y * dsb, hb1 = j23.x * drb + j23.y * dsb;
+    const double d0 = dp.x * ha0, d1 = dp.x * ha1;
     pxx += d0 * hb0; pxy += d0 * hb1; pyx += d1 * hb0; pyy += d1 * hb1;
-    crr += g[5] * (far * fbr); crs += g[6] * (far * fbs);
-    csr += g[6] * (fas * fbr); css += g[7] * (fas * fbs);
+    crr += dp.y * (far * fbr); crs += ps.x * (far * fbs);
+    csr += ps.x * (fas * fbr); css += ps.y * (fas * fbs);
   }
-  const double* mt = s + Q_MAT;
+  // (R, krz): 5 pairs; (MAT, M): 6 pairs; shear edge data: 4 pairs
+  double R[10];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { const double2 v = s2[k]; R[2 * k] = v.x; R[2 * k + 1] = v.y; }
+  double mt[12];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const double2 v = s2[Q_MAT / 2 + k]; mt[2 * k] = v.x; mt[2 * k + 1] = v.y; }
+  const double2 gry = s2[Q_GRY / 2], grx = s2[Q_GRX / 2], gsy = s2[Q_GSY / 2], gsx = s2[Q_GSX / 2];
   const double D = mt[5], nu = mt[6], hb = mt[7], ks = mt[8];
   // membrane 2x2 (u,v)
   const double muu = mt[0] * pxx + mt[4] * pyy, muv = mt[1] * pxy + mt[4] * pyx;
   const double mvu = mt[2] * pyx + mt[4] * pxy, mvv = mt[3] * pyy + mt[4] * pxx;
   // plate 3x3 (w, theta_x, theta_y): bending + MITC4 shear
-  const int ira = (a < 2) ? 0 : 1, isa = (a == 0 || a == 3) ? 0 : 1;
-  const int irb = (b < 2) ? 0 : 1, isb = (b == 0 || b == 3) ? 0 : 1;
-  const double gra[3] = {0.5 * ra, s[Q_GRY + ira], s[Q_GRX + ira]};
-  const double gsa[3] = {0.5 * sa, s[Q_GSY + isa], s[Q_GSX + isa]};
-  const double grb[3] = {0.5 * rb, s[Q_GRY + irb], s[Q_GRX + irb]};
-  const double gsb[3] = {0.5 * sb, s[Q_GSY + isb], s[Q_GSX + isb]};
-  const double m11 = s[Q_M], m12 = s[Q_M + 1], m22 = s[Q_M + 2];
+  const bool ira = a >= 2, isa = !(a == 0 || a == 3);
+  const bool irb = b >= 2, isb = !(b == 0 || b == 3);
+  const double gra[3] = {0.5 * ra, ira ? gry.y : gry.x, ira ? grx.y : grx.x};
+  const double gsa[3] = {0.5 * sa, isa ? gsy.y : gsy.x, isa ? gsx.y : gsx.x};
+  const double grb[3] = {0.5 * rb, irb ? gry.y : gry.x, irb ? grx.y : grx.x};
+  const double gsb[3] = {0.5 * sb, isb ? gsy.y : gsy.x, isb ? gsx.y : gsx.x};
+  const double m11 = mt[9], m12 = mt[10], m22 = mt[11];
   double P[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -180,8 +192,7 @@ __device__ inline void quad_pair_block(const double* s, int a, int b, double* ou
   P[1][2] -= D * (nu * pyx + hb * pxy);
   P[2][1] -= D * (nu * pxy + hb * pyx);
   P[2][2] += D * (pxx + hb * pyy);
-  const double drill = (a == b) ? s[Q_KRZ] : 0.0;
-  const double* R = s + Q_R;
+  const double drill = (a == b) ? R[9] : 0.0;
   // translational-translational and rotational-rotational sub-blocks
   rtsr_diag(R, muu, muv, mvu, mvv, P[0][0], out, 0, 0);
   rtsr_diag(R, P[1][1], P[1][2], P[2][1], P[2][2], drill, out, 1, 1);
@@ -272,7 +283,7 @@ __device__ inline void beam_pair_block(const double* __restrict__ crds, const in
 __global__ void __launch_bounds__(256)
 quad_ke_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                const double* __restrict__ prop, double* __restrict__ ke, int* flags) {
-  __shared__ double sm[16 * QS];
+  __shared__ __align__(16) double sm[16 * QS];
   const int first = blockIdx.x * 16;
   const int n_el = min(16, n_quad - first);
   stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
@@ -336,7 +347,7 @@ struct AsmArgs {
 // contributor count (blk_perm), so the lanes of a warp loop the same number of times.
 __global__ void __launch_bounds__(kChunkBlocks, 4)
 assemble_fused_kernel(AsmArgs A) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int c = blockIdx.x;
   const int blk0 = A.chunk_blk[c], blk1 = A.chunk_blk[c + 1];
   const int el0 = A.chunk_el_ptr[c], n_el = A.chunk_el_ptr[c + 1] - el0;
@@ -425,7 +436,7 @@ static_assert((kTaskQuads * REC_LD) % 2 == 0 && TASK_SMEM_DOUBLES % 2 == 0, "16-
 __global__ void __launch_bounds__(128)
 quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                      const double* __restrict__ prop, double* __restrict__ rec, int* flags) {
-  __shared__ double sm[32 * QS];
+  __shared__ __align__(16) double sm[32 * QS];
   const int first = blockIdx.x * 32;
   const int n_el = min(32, n_quad - first);
   stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
