@@ -220,6 +220,17 @@ def run_reference(args):
         if pool:
             pool.shutdown()
     v = md.n_quad / dt
+    # metric M2 on the host: one full gradient evaluation of the same bounded sample in the reference's
+    # LITERAL formulation (raw COO -> CSR, augmented Lagrange system, SuperLU twice, element derivatives)
+    ge = None
+    if args.ref_grad:
+        from oracle import jaxsso_oracle as orc
+        m = orc.Mesh(md.crds, md.cnct_quads, md.prop_quads, md.cnct_beams, md.prop_beams, md.known, md.loads)
+        t0 = time.perf_counter()
+        orc.value_and_grad(m, literal=True)
+        ge = {'seconds': time.perf_counter() - t0, 'quads': int(md.n_quad),
+              'what': 'oracle value_and_grad(literal=True): augmented SuperLU solve x2 + complex-step element '
+                      'derivatives, one process'}
     sample = (f'{size}x{size} jittered plate ({md.n_quad} quads) per step: NumPy/SciPy restatement of '
               f'vmap(element_K_quad) + COO->CSR sum_duplicates + complex-step adjoint reduction, '
               f'{n_workers} worker processes')
@@ -228,7 +239,8 @@ def run_reference(args):
            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
            'config': {'workload': f'synthetic {args.size}x{args.size} MITC4 shell plate (BASELINE configs[2]); '
                                   f'reference arm timed on a bounded {size}x{size} sample of it'},
-           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': n_workers, 'kind': 'port', 'sample': sample},
+           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': n_workers, 'kind': 'port', 'sample': sample,
+                            'grad_eval': ge},
            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
 
@@ -495,7 +507,7 @@ def run_b200(args):
            'grad_eval': grad_eval}
     if world == 1 and args.cpu_baseline:
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
-               '--ref-size', str(args.ref_size), '--ref-serial']
+               '--ref-size', str(args.ref_size), '--ref-serial', '--ref-grad']
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
             ref = json.loads(r.stdout.strip().splitlines()[-1])
@@ -525,6 +537,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     ap.add_argument('--ref-size', type=int, default=64, help='plate size of the bounded CPU sample')
     ap.add_argument('--ref-serial', action='store_true', help='reference arm on one core (cpu_baseline leg)')
+    ap.add_argument('--ref-grad', action='store_true', help='also time one literal gradient evaluation of the sample')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.ref_serial:

@@ -11,7 +11,7 @@ D = nat.DeviceArray
 crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
 u = D((md.ndof,))
 try:
-    st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=1e-8, precond='multigrid', maxiter=iters))
+    st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=1e-8, precond='multigrid', maxiter=iters, cheb_degree=int(sys.argv[3]) if len(sys.argv) > 3 else 1))
     print(st.as_dict())
 except Exception as e:
     print('stopped:', e)

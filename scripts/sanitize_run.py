@@ -20,3 +20,13 @@ for pre in ('block_jacobi', 'multigrid'):
     print(pre, st.as_dict())
 val = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads)[0]
 print('ok', val)
+# both assembly paths (warp tasks by default above, chunked single kernel here) and the 3-kernel CG
+import os
+os.environ['JSSO_ASM_CHUNKED'] = '1'
+h2 = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+del os.environ['JSSO_ASM_CHUNKED']
+h2.assemble(crds, pq, pb, apply_bc=True)
+y = D((md.ndof,))
+h.assemble(crds, pq, pb, apply_bc=True)
+h.spmv(u, y)
+print('chunked vs tasks', float(np.abs(h.values_host() - h2.values_host()).max()))

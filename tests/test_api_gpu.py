@@ -205,3 +205,33 @@ def test_sparse_hat_filter_matches_dense_notebook_filter(mannheim_data):
     assert np.abs(f.apply(z) - B_dense @ z).max() < 1e-13
     assert np.abs(f.apply_T(g) - g @ B_dense).max() < 1e-13
     assert f.B.nnz < 0.2 * B_dense.size
+
+
+def test_gather_rows_and_assembly_profile():
+    """jsso_gather_rows (local part of a replicated vector) and the per-kernel timing hooks of
+    jsso_assemble; the two assembly paths (warp tasks / chunked) give the same matrix."""
+    import os
+    from jaxsso_b200 import _native as nat
+    rng = np.random.default_rng(3)
+    src = rng.standard_normal((50, 6))
+    idx = rng.permutation(50)[:31].astype(np.int32)
+    out = nat.gather_rows(nat.DeviceArray.from_host(src), nat.DeviceArray.from_host(idx), 6).download()
+    assert np.array_equal(out.reshape(-1, 6), src[idx])
+    md = meshes.plate(24)
+    D = nat.DeviceArray
+    crds, pq, pb = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams)
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    h.profile(True)
+    h.assemble(crds, pq, pb, apply_bc=True)
+    g_ms, t_ms = h.profile_read()
+    assert g_ms > 0.0 and t_ms > 0.0
+    v_tasks = h.values_host()
+    os.environ['JSSO_ASM_CHUNKED'] = '1'
+    try:
+        h2 = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    finally:
+        del os.environ['JSSO_ASM_CHUNKED']
+    h2.assemble(crds, pq, pb, apply_bc=True)
+    assert h2.profile_read() == (0.0, 0.0)
+    v_chunk = h2.values_host()
+    assert np.abs(v_tasks - v_chunk).max() <= 1e-13 * np.abs(v_chunk).max()
