@@ -257,6 +257,8 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           TASK_WARPS * TASK_SMEM_DOUBLES * (int)sizeof(double)));
+  CK(cudaFuncSetAttribute(quad_geometry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          G_QUADS * QS * (int)sizeof(double)));
   // 4 CTAs x 55 KB per SM need the largest shared-memory carve-out
   CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                           (int)cudaSharedmemCarveoutMaxShared));
@@ -454,7 +456,8 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     const int nq = h->sym.n_quad;
     if (h->prof) CK(cudaEventRecord(h->ev_prof[0], st));
     if (nq > 0) {
-      quad_geometry_kernel<<<cdiv(nq, 32), 128, 0, st>>>(nq, crds, h->cnct_q, prop_q, h->quad_rec, h->flags);
+      quad_geometry_kernel<<<cdiv(nq, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
+          nq, crds, h->cnct_q, prop_q, h->quad_rec, h->flags);
       CKL("quad_geometry_kernel");
     }
     if (h->prof) CK(cudaEventRecord(h->ev_prof[1], st));

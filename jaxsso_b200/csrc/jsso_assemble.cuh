@@ -433,12 +433,20 @@ constexpr int TASK_SMEM_DOUBLES = kTaskQuads * REC_LD + kTaskItems * ITEM_LD;   
 constexpr int TASK_WARPS = JSSO_T_WARPS;  // warps per CTA
 static_assert((kTaskQuads * REC_LD) % 2 == 0 && TASK_SMEM_DOUBLES % 2 == 0, "16-byte alignment of the item rows");
 
-__global__ void __launch_bounds__(128)
+#ifndef JSSO_G_QUADS
+#define JSSO_G_QUADS 64      // quads per CTA of quad_geometry_kernel (variant sweep: 32 -> 0.223 ms, 64 -> 0.200 ms, 128 -> 0.255 ms)
+#endif
+#ifndef JSSO_G_THREADS
+#define JSSO_G_THREADS 128
+#endif
+constexpr int G_QUADS = JSSO_G_QUADS, G_THREADS = JSSO_G_THREADS;
+
+__global__ void __launch_bounds__(G_THREADS)
 quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                      const double* __restrict__ prop, double* __restrict__ rec, int* flags) {
-  __shared__ __align__(16) double sm[32 * QS];
-  const int first = blockIdx.x * 32;
-  const int n_el = min(32, n_quad - first);
+  extern __shared__ __align__(16) double sm[];   // G_QUADS * QS doubles
+  const int first = blockIdx.x * G_QUADS;
+  const int n_el = min(G_QUADS, n_quad - first);
   stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
   __syncthreads();
   double* dst = rec + (size_t)first * REC_GLD;

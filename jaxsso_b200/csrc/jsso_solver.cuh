@@ -374,8 +374,11 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
 }
 
 // MODE 0: y = A x;  2: y = b - A x;  3: y += A x   (any 6x6 block-CSR, also rectangular)
+#ifndef JSSO_SPMV_MINB
+#define JSSO_SPMV_MINB 4   // resident CTAs per SM the register allocation of the level SpMV aims at
+#endif
 template <int MODE, class VT>
-__global__ void __launch_bounds__(RED_BLOCK)
+__global__ void __launch_bounds__(RED_BLOCK, JSSO_SPMV_MINB)
 bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                       const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                       const double* __restrict__ bvec) {

@@ -5,8 +5,12 @@ import os, subprocess, sys
 sys.path.insert(0, '.')
 VARIANTS = {
     'base':   [],
-    'adj3':   ['JSSO_ADJ_MINB=3'],
-    'adj4':   ['JSSO_ADJ_MINB=4'],
+    'g64':    ['JSSO_G_QUADS=64'],
+    'g128':   ['JSSO_G_QUADS=128'],
+    'g64t256': ['JSSO_G_QUADS=64', 'JSSO_G_THREADS=256'],
+    'g128t256': ['JSSO_G_QUADS=128', 'JSSO_G_THREADS=256'],
+    'spmv5':  ['JSSO_SPMV_MINB=5'],
+    'spmv6':  ['JSSO_SPMV_MINB=6'],
 }
 VDIR = os.path.join('jaxsso_b200', 'variants')
 
