@@ -127,6 +127,9 @@ int jsso_get_sizes(const jsso_handle* h, jsso_sizes* out);
 /* ---- symbolic pass results (host copies) -------------------------------------- */
 /* rowptr[n_row+1], colidx[nnzb] (sorted within each row): the bit-exact pattern. */
 int jsso_pattern(const jsso_handle* h, int32_t* rowptr_h, int32_t* colidx_h);
+/* Greedy aggregation step of the multigrid symbolic setup on the host (no device): agg_h[n] receives the
+ * aggregate of every node of the block-CSR graph (rowptr_h, colidx_h), *n_agg the number of aggregates. */
+int jsso_mg_aggregate(int32_t n, const int32_t* rowptr_h, const int32_t* colidx_h, int32_t* agg_h, int32_t* n_agg);
 /* Warp-task lists of the two-kernel numeric assembly (host copies, for tests): counts[3] =
  * {n_task, n_task_els, tasks_ok}; every other pointer may be NULL.  task_meta: 4 ints per task
  * {blk0, item0, el0, n_blk | n_item<<8 | n_el<<16}; item_desc per pair item: local block (bits 0-4),

@@ -382,6 +382,13 @@ int jsso_pattern(const jsso_handle* h, int32_t* rowptr, int32_t* colidx) {
   return JSSO_OK;
 }
 
+// host-only helper of the multigrid symbolic setup (no handle, no device)
+int jsso_mg_aggregate(int32_t n, const int32_t* rowptr, const int32_t* colidx, int32_t* agg, int32_t* n_agg) {
+  if (n < 0 || !rowptr || !agg || !n_agg || (rowptr[n] > 0 && !colidx)) return JSSO_ERR_ARG;
+  *n_agg = mg_aggregate(n, rowptr, colidx, agg);
+  return JSSO_OK;
+}
+
 int jsso_assembly_tasks(const jsso_handle* h, int32_t* counts, int32_t* task_meta, int32_t* task_els,
                         uint16_t* item_desc, uint16_t* blk_bc, int32_t* blk_item_ptr, int32_t* item_code) {
   if (!h || !counts) return JSSO_ERR_ARG;

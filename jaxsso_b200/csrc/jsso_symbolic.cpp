@@ -252,4 +252,27 @@ std::string build_symbolic_from_bsr(int n_node, const int32_t* rowptr, const int
   return "";
 }
 
+int mg_aggregate(int n, const int32_t* rowptr, const int32_t* colidx, int32_t* agg) {
+  std::fill(agg, agg + n, -1);
+  int na = 0;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    bool all_free = true;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; ++s)
+      if (agg[colidx[s]] >= 0) { all_free = false; break; }
+    if (!all_free) continue;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) agg[colidx[s]] = na;
+    agg[i] = na;
+    ++na;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    int got = -1;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; ++s)
+      if (agg[colidx[s]] >= 0) { got = agg[colidx[s]]; break; }
+    agg[i] = (got >= 0) ? got : na++;
+  }
+  return na;
+}
+
 }  // namespace jsso

@@ -67,4 +67,10 @@ std::string build_symbolic(int n_node, int n_row, int n_quad, const int32_t* cnc
 std::string build_symbolic_from_bsr(int n_node, const int32_t* rowptr, const int32_t* colidx, int n_known,
                                     const int32_t* known, Symbolic& out);
 
+// Greedy aggregation of the smoothed-aggregation multigrid (Vanek et al.), the host loop of
+// jaxsso_b200/multigrid.py::aggregate_py restated in C++ (identical, deterministic result): a node whose whole
+// neighbourhood is free roots an aggregate of itself + neighbours; leftovers join the aggregate of their first
+// aggregated neighbour (column order) or become singletons.  Returns the number of aggregates.
+int mg_aggregate(int n, const int32_t* rowptr, const int32_t* colidx, int32_t* agg);
+
 }  // namespace jsso

@@ -119,6 +119,20 @@ def test_reference_vcycle_is_a_good_preconditioner():
     assert it < 60
 
 
+@pytest.mark.parametrize('case', ['plate20', 'gridshell12', 'frames', 'mannheim'])
+def test_native_aggregation_equals_python(case, mannheim_data):
+    """jsso_mg_aggregate (C++ host routine) reproduces the Python greedy aggregation exactly."""
+    from jaxsso_b200 import _native as nat
+    md = {'plate20': lambda: meshes.plate(20), 'gridshell12': lambda: meshes.gridshell(12, 0),
+          'frames': lambda: meshes.frames(4, 20), 'mannheim': lambda: meshes.mannheim_quad(mannheim_data)}[case]()
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=-1)
+    rp, ci = h.pattern()
+    a1, n1 = mg.aggregate(rp, ci)
+    a2, n2 = mg.aggregate_py(rp, ci)
+    assert n1 == n2 and np.array_equal(a1, a2)
+    h.close()
+
+
 # ------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', ['plate48', 'gridshell40', 'mannheim', 'mixed'])
