@@ -1,14 +1,15 @@
 // Element stiffness generation and numeric assembly kernels (sm_100a, FP64).
 //
-//  * stage_quad_geometry : per (quad, Gauss point) thread -> shared memory record
-//  * quad_pair_block     : per (quad, node a, node b) thread -> one 6x6 global block
+//  * stage_quad_geometry : per (quad, Gauss point) thread -> shared memory record of the quad
+//  * quad_pair_block     : one (quad, node a, node b) pair item -> one 6x6 global block, from the record
 //  * quad_ke_kernel / beam_ke_kernel : materialise K_e in the reference's `data`
 //    layout (element.py:1236-1237, 270-271) for tests and for the stand-alone
 //    assembly path
-//  * assemble_fused_kernel : Ke + assembly in one pass; K_e never reaches HBM.
-//    One CTA per chunk of <= 256 block slots; one thread owns one 6x6 block and sums
-//    its contributors in a fixed order in registers (no atomics), then writes the
-//    block once.
+//  * quad_geometry_kernel + assemble_tasks_kernel : the production assembly.  The geometry record of
+//    every quad is written once (496 B); persistent warps then own runs of block slots ("tasks"),
+//    one pair item per lane, sums in list order, coalesced stores -- K_e never reaches HBM, no atomics.
+//  * assemble_fused_kernel : the chunked single-kernel variant (one CTA per chunk of <= 128 block
+//    slots, one thread owns one 6x6 block): fallback for meshes the warp tasks cannot hold, A/B reference.
 //  * assemble_from_ke_kernel : stand-alone segmented reduction of materialised K_e.
 #pragma once
 #include "jsso_elem.cuh"

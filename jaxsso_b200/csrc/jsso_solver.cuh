@@ -13,7 +13,9 @@
 //
 // All kernels are HBM-bound streaming kernels; the SpMV moves 288 B per block with
 // 16-byte loads, 30 of 32 lanes active (3 lanes x 2 rows per block column, 10 block
-// columns per warp-load), all loads of a block row issued before the first FMA.
+// columns per warp-load), all loads of a block row issued before the first FMA, and the
+// row loop is software-pipelined (rowptr two rows ahead, colidx one row ahead) so that one
+// memory latency per row is exposed instead of three: 0.96 of the measured HBM bandwidth.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
