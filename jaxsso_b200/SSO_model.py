@@ -101,6 +101,14 @@ class SSO_model:
     def update_parameter(self, params_values):
         self.parameter_values = np.array(params_values, dtype=float)
 
+    def update_model_parameter(self):
+        """Write the current node-parameter values back into the model's nodes and re-freeze it
+        (reference: SSO_model.py:198-202; the symbolic state is kept, the topology did not change)."""
+        for tag, xyz, val in zip(self.nodeparameters_tags, self.nodeparameters_xyzs,
+                                 np.asarray(self.parameter_values[:self.n_node_params], dtype=float).tolist()):
+            self.model.update_node(tag, xyz, val)
+        self.model.model_ready()
+
     # ---- parameters -> arrays (SSO_model.py:207-222) -----------------------------------
     def node_params_crds(self, nodeparameter_values):
         crds = self.model.crds.copy()
@@ -147,6 +155,13 @@ class SSO_model:
 
     def params_c(self, parameter_values, which_solver='b200', enforce_scipy_sparse=True):
         return 0.5 * self.model.nodal_loads @ self.params_u(parameter_values, which_solver, enforce_scipy_sparse)
+
+    def node_params_c(self, nodeparameter_values, which_solver='b200', enforce_scipy_sparse=True):
+        """Strain energy as a function of the node parameters only, element parameters at their current
+        values (reference: SSO_model.py:262-271)."""
+        pv = np.array(self.parameter_values, dtype=float)
+        pv[:self.n_node_params] = nodeparameter_values
+        return self.params_c(pv, which_solver, enforce_scipy_sparse)
 
     # ---- objective (SSO_model.py:275-306) ------------------------------------------------
     def set_objective(self, objective='strain energy', func=None, func_args=None):

@@ -16,6 +16,14 @@ import numpy as np
 from . import _native as nat
 
 
+class Node:
+    """A node (reference: model.py:15-32): tag and global coordinates."""
+
+    def __init__(self, nodeTag, X, Y, Z):
+        self.nodeTag = nodeTag
+        self.X, self.Y, self.Z = X, Y, Z
+
+
 class Model:
     """The FE model to be analysed (reference: model.py:34-383)."""
 
