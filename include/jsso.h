@@ -19,6 +19,15 @@
  *                                                       JaxSSO/solver.py:157-166, 239-248
  *   jsso_forward        body of SSO_model.params_u      JaxSSO/SSO_model.py:243-248
  *   jsso_backward       *_sparse_solve_bwd + transposes JaxSSO/solver.py:138-166, 221-248
+ *   jsso_quad_area      Quad.A                          JaxSSO/element.py:471-487
+ *   jsso_csr_spmv       the examples' dense hat-filter mat-vec B @ z / sens @ B
+ *                                                       Examples/Shells_Mannheim_Multihalle_Shape.ipynb cells 10-13
+ *   jsso_create_from_bsr / jsso_set_values_host          the (K_aug, f_aug) -> u_aug solver plugin of
+ *                                                       Model.select_solver, JaxSSO/model.py:340-356
+ * Without a counterpart in the reference (it has no multi-GPU path, no iterative solver and no profiler
+ * hooks): jsso_mg_setup / jsso_mg_aggregate (multigrid preconditioner), jsso_set_halo / jsso_p2p_* /
+ * jsso_halo_exchange / jsso_nccl_unique_id (partitioned meshes), jsso_gather_rows, jsso_assembly_tasks,
+ * jsso_profile* (tests and measurement), and the memory / stream / event helpers at the end of this file.
  *
  * Conventions
  *   - all floating point is FP64, all indices int32 (model.py:284-313).
