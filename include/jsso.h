@@ -25,7 +25,7 @@
  *   jsso_create_from_bsr / jsso_set_values_host          the (K_aug, f_aug) -> u_aug solver plugin of
  *                                                       Model.select_solver, JaxSSO/model.py:340-356
  * Without a counterpart in the reference (it has no multi-GPU path, no iterative solver and no profiler
- * hooks): jsso_mg_setup / jsso_mg_aggregate (multigrid preconditioner), jsso_set_halo / jsso_p2p_* /
+ * hooks): jsso_mg_setup / jsso_mg_aggregate / jsso_mg_pattern_lists (multigrid preconditioner), jsso_set_halo / jsso_p2p_* /
  * jsso_halo_exchange / jsso_nccl_unique_id (partitioned meshes), jsso_gather_rows, jsso_assembly_tasks,
  * jsso_profile* (tests and measurement), and the memory / stream / event helpers at the end of this file.
  *
@@ -139,6 +139,12 @@ int jsso_pattern(const jsso_handle* h, int32_t* rowptr_h, int32_t* colidx_h);
 /* Greedy aggregation step of the multigrid symbolic setup on the host (no device): agg_h[n] receives the
  * aggregate of every node of the block-CSR graph (rowptr_h, colidx_h), *n_agg the number of aggregates. */
 int jsso_mg_aggregate(int32_t n, const int32_t* rowptr_h, const int32_t* colidx_h, int32_t* agg_h, int32_t* n_agg);
+/* Gather-list construction of the multigrid symbolic setup on the host: m triples (row, col, left, right),
+ * emitted in (left, right) order, -> block pattern sorted by (row, col) and per block its (left, right) pairs in
+ * input order; output arrays sized for n_blk = m (ptr: m + 1), *n_blk receives the number of blocks. */
+int jsso_mg_pattern_lists(int64_t m, const int32_t* row_h, const int32_t* col_h, const int32_t* left_h,
+                          const int32_t* right_h, int32_t n_row, int32_t* rowptr_h, int32_t* ocol_h, int32_t* ptr_h,
+                          int32_t* left_out_h, int32_t* right_out_h, int64_t* n_blk);
 /* Warp-task lists of the two-kernel numeric assembly (host copies, for tests): counts[3] =
  * {n_task, n_task_els, tasks_ok}; every other pointer may be NULL.  task_meta: 4 ints per task
  * {blk0, item0, el0, n_blk | n_item<<8 | n_el<<16}; item_desc per pair item: local block (bits 0-4),

@@ -64,7 +64,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_mg_aggregate', 'jsso_assembly_tasks',
+SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_mg_aggregate', 'jsso_mg_pattern_lists', 'jsso_assembly_tasks',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_gather_rows', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
            'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
@@ -97,6 +97,7 @@ def lib():
     L.jsso_pattern.argtypes = [vp, vp, vp]
     L.jsso_assembly_tasks.argtypes = [vp] * 8
     L.jsso_mg_aggregate.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
+    L.jsso_mg_pattern_lists.argtypes = [i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, C.POINTER(i64)]
     L.jsso_quad_ke.argtypes = [vp, vp, vp, vp, vp]
     L.jsso_beam_ke.argtypes = [vp, vp, vp, vp, vp]
     L.jsso_quad_area.argtypes = [vp, vp, vp, vp]

@@ -389,6 +389,18 @@ int jsso_mg_aggregate(int32_t n, const int32_t* rowptr, const int32_t* colidx, i
   return JSSO_OK;
 }
 
+int jsso_mg_pattern_lists(int64_t m, const int32_t* row, const int32_t* col, const int32_t* left,
+                          const int32_t* right, int32_t n_row, int32_t* rowptr, int32_t* ocol, int32_t* ptr,
+                          int32_t* left_o, int32_t* right_o, int64_t* n_blk) {
+  if (m < 0 || m >= INT32_MAX || n_row < 0 || !rowptr || !ptr || !n_blk ||
+      (m > 0 && (!row || !col || !left || !right || !ocol || !left_o || !right_o)))
+    return JSSO_ERR_ARG;
+  for (int64_t t = 0; t < m; ++t)
+    if (row[t] < 0 || row[t] >= n_row) return JSSO_ERR_ARG;
+  *n_blk = mg_pattern_lists(m, row, col, left, right, n_row, rowptr, ocol, ptr, left_o, right_o);
+  return JSSO_OK;
+}
+
 int jsso_assembly_tasks(const jsso_handle* h, int32_t* counts, int32_t* task_meta, int32_t* task_els,
                         uint16_t* item_desc, uint16_t* blk_bc, int32_t* blk_item_ptr, int32_t* item_code) {
   if (!h || !counts) return JSSO_ERR_ARG;

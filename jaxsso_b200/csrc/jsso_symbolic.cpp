@@ -275,4 +275,37 @@ int mg_aggregate(int n, const int32_t* rowptr, const int32_t* colidx, int32_t* a
   return na;
 }
 
+int64_t mg_pattern_lists(int64_t m, const int32_t* row, const int32_t* col, const int32_t* left,
+                         const int32_t* right, int n_row, int32_t* rowptr, int32_t* ocol, int32_t* ptr,
+                         int32_t* left_o, int32_t* right_o) {
+  std::vector<int64_t> start(n_row + 1, 0);
+  for (int64_t t = 0; t < m; ++t) start[row[t] + 1]++;
+  for (int r = 0; r < n_row; ++r) start[r + 1] += start[r];
+  std::vector<int64_t> order(m);
+  {
+    std::vector<int64_t> pos(start.begin(), start.end() - 1);
+    for (int64_t t = 0; t < m; ++t) order[pos[row[t]]++] = t;      // stable by row
+  }
+  int64_t nb = 0;
+  rowptr[0] = 0;
+  for (int r = 0; r < n_row; ++r) {
+    int64_t* b = order.data() + start[r];
+    int64_t* e = order.data() + start[r + 1];
+    std::stable_sort(b, e, [&](int64_t x, int64_t y) { return col[x] < col[y]; });
+    for (int64_t* p = b; p < e; ++p) {
+      const int64_t o = p - order.data();
+      if (p == b || col[*p] != col[*(p - 1)]) {
+        ocol[nb] = col[*p];
+        ptr[nb] = (int32_t)o;
+        ++nb;
+      }
+      left_o[o] = left[*p];
+      right_o[o] = right[*p];
+    }
+    rowptr[r + 1] = (int32_t)nb;
+  }
+  ptr[nb] = (int32_t)m;
+  return nb;
+}
+
 }  // namespace jsso

@@ -73,4 +73,12 @@ std::string build_symbolic_from_bsr(int n_node, const int32_t* rowptr, const int
 // aggregated neighbour (column order) or become singletons.  Returns the number of aggregates.
 int mg_aggregate(int n, const int32_t* rowptr, const int32_t* colidx, int32_t* agg);
 
+// Gather-list construction of the multigrid symbolic setup: m triples (row, col, left slot, right slot) ->
+// block pattern sorted by (row, col) (rowptr[n_row+1], ocol[n_blk]) and, per output block, its (left, right)
+// pairs IN INPUT ORDER (ptr[n_blk+1], left_o[m], right_o[m]).  Stable two-level sort (counting sort by row,
+// stable sort by column inside a row).  Output arrays are sized for the worst case n_blk = m.  Returns n_blk.
+int64_t mg_pattern_lists(int64_t m, const int32_t* row, const int32_t* col, const int32_t* left,
+                         const int32_t* right, int n_row, int32_t* rowptr, int32_t* ocol, int32_t* ptr,
+                         int32_t* left_o, int32_t* right_o);
+
 }  // namespace jsso

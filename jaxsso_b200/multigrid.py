@@ -48,17 +48,34 @@ def _csr_lists(keys_major, payload_cols, n_major):
     return np.cumsum(ptr).astype(np.int32), payload_cols
 
 
+def _pattern_and_lists_native(row, col, left, right, n_row):
+    """The same through the native host routine (stable two-level sort; input already in (left, right) order)."""
+    import ctypes
+    from . import _native as nat
+    arrs = [np.ascontiguousarray(a, np.int32) for a in (row, col, left, right)]
+    m = arrs[0].shape[0]
+    rowptr = np.empty(n_row + 1, np.int32)
+    ocol, ptr = np.empty(max(m, 1), np.int32), np.empty(m + 1, np.int32)
+    lo, ro = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
+    nb = ctypes.c_int64()
+    rc = nat.lib().jsso_mg_pattern_lists(m, *(nat._ptr(a) for a in arrs), n_row, nat._ptr(rowptr), nat._ptr(ocol),
+                                         nat._ptr(ptr), nat._ptr(lo), nat._ptr(ro), ctypes.byref(nb))
+    if rc:
+        raise nat.JssoError(rc, 'jsso_mg_pattern_lists')
+    nb = int(nb.value)
+    return rowptr, ocol[:nb].copy(), ptr[:nb + 1].copy(), lo[:m], ro[:m]
+
+
 def _pattern_and_lists(row, col, left, right, n_row, n_col):
     """Triples (row, col, left slot, right slot) -> sorted block pattern (rowptr, colidx) and, per
     output block, its (left, right) list in a deterministic order."""
+    # every caller emits its triples in (left, right) order already, so a STABLE sort by (row, col) alone is
+    # the lexicographic (row, col, left, right) order: native routine; the three-key sort is kept for other input
+    dl = np.diff(left)
+    if np.all((dl > 0) | ((dl == 0) & (np.diff(right) >= 0))):
+        return _pattern_and_lists_native(row, col, left, right, n_row)
     key = row.astype(np.int64) * n_col + col
-    # every caller emits its triples in (left, right) order already, so a STABLE sort by the block key alone
-    # is the lexicographic (key, left, right) order; the three-key sort is kept for any other input
-    dl = np.diff(left.astype(np.int64))
-    if np.all((dl > 0) | ((dl == 0) & (np.diff(right.astype(np.int64)) >= 0))):
-        order = np.argsort(key, kind='stable')
-    else:
-        order = np.lexsort((right, left, key))
+    order = np.lexsort((right, left, key))
     key, left, right = key[order], left[order], right[order]
     uniq, start = np.unique(key, return_index=True)
     ptr = np.append(start, key.shape[0]).astype(np.int32)

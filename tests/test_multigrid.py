@@ -134,6 +134,33 @@ def test_native_aggregation_equals_python(case, mannheim_data):
     h.close()
 
 
+def test_native_pattern_lists_equal_three_key_sort():
+    """jsso_mg_pattern_lists (stable two-level sort) == np.lexsort((right, left, row*n_col+col)) on triples
+    emitted in (left, right) order, including empty rows and repeated (row, col) keys."""
+    rng = np.random.default_rng(5)
+    n_row, n_col, m = 37, 11, 4000
+    left = np.sort(rng.integers(0, 900, m)).astype(np.int32)
+    right = np.zeros(m, np.int32)
+    for v in np.unique(left):                       # ascending `right` inside equal `left`
+        sel = np.flatnonzero(left == v)
+        right[sel] = np.sort(rng.integers(0, 50, sel.size))
+    row = rng.integers(0, n_row - 3, m).astype(np.int32)      # the last rows stay empty
+    col = rng.integers(0, n_col, m).astype(np.int32)
+    rp, oc, ptr, lo, ro = mg._pattern_and_lists(row, col, left, right, n_row, n_col)
+    key = row.astype(np.int64) * n_col + col
+    order = np.lexsort((right, left, key))
+    uniq, start = np.unique(key[order], return_index=True)
+    assert np.array_equal(oc, (uniq % n_col).astype(np.int32))
+    assert np.array_equal(ptr, np.append(start, m).astype(np.int32))
+    assert np.array_equal(lo, left[order]) and np.array_equal(ro, right[order])
+    assert np.array_equal(np.diff(rp), np.bincount(uniq // n_col, minlength=n_row))
+    # input that is NOT in (left, right) order takes the NumPy path and gives the same kind of result
+    perm = rng.permutation(m)
+    rp2, oc2, ptr2, lo2, ro2 = mg._pattern_and_lists(row[perm], col[perm], left[perm], right[perm], n_row, n_col)
+    assert np.array_equal(rp2, rp) and np.array_equal(oc2, oc) and np.array_equal(ptr2, ptr)
+    assert np.array_equal(lo2, lo) and np.array_equal(ro2, ro)
+
+
 # ------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', ['plate48', 'gridshell40', 'mannheim', 'mixed'])
