@@ -131,3 +131,169 @@ def reference_vcycle(ref_levels, A_coarse_dense_inv, b, deg=2, ratio=4.0):
         return cheb(R, rhs, x, False)
 
     return rec(0, b)
+
+
+# ----------------------------------------------------------------------------- distributed replay
+def _dofs(ids):
+    return (6 * np.asarray(ids, np.int64)[:, None] + np.arange(6)[None, :]).ravel()
+
+
+class _EmulatedRanks:
+    """N simulated ranks, each with its OWN full-length copy of every level vector, initialised to NaN.  A rank
+    only ever writes its row range; everything else arrives through `exchange` / `allgather`, exactly the calls
+    `mg_solve_dist` (csrc/jsso_api.cu) makes.  A product that reads an entry nobody delivered turns NaN, so a
+    missing ghost in the plan (jaxsso_b200/dist_multigrid.py) fails the comparison with the global V-cycle."""
+
+    def __init__(self, ref_levels, A_coarse_inv, plan, deg):
+        self.ref, self.Ainv, self.plan, self.deg = ref_levels, A_coarse_inv, plan, deg
+        self.n_rank, self.n_dist = plan['n_rank'], plan['n_dist']
+        self.v = [dict() for _ in range(self.n_rank)]
+        self.sizes = [R.A.shape[0] for R in ref_levels] + [A_coarse_inv.shape[0]]
+        self.n_exchange = 0
+
+    def vec(self, r, l, name):
+        key = (l, name)
+        if key not in self.v[r]:
+            self.v[r][key] = np.full(self.sizes[l], np.nan)
+        return self.v[r][key]
+
+    def rng(self, l, r):
+        b = self.plan['bounds'][l]
+        return 6 * int(b[r]), 6 * int(b[r + 1])
+
+    def exchange(self, l, name):
+        need = self.plan['need'][l]
+        for r in range(self.n_rank):
+            for s in range(self.n_rank):
+                if s != r and need[r][s].size:
+                    d = _dofs(need[r][s])
+                    self.vec(r, l, name)[d] = self.vec(s, l, name)[d]
+        self.n_exchange += 1
+
+    def allgather(self, l, name):
+        for r in range(self.n_rank):
+            for s in range(self.n_rank):
+                a, b = self.rng(l, s)
+                self.vec(r, l, name)[a:b] = self.vec(s, l, name)[a:b]
+
+    def rows(self, M, l_rows, r, x):
+        """rows [range of rank r at level l_rows] of M @ x"""
+        a, b = self.rng(l_rows, r)
+        return M[a:b] @ x
+
+    def dot(self, l, n1, n2):
+        tot = 0.0
+        for r in range(self.n_rank):
+            a, b = self.rng(l, r)
+            tot += float(self.vec(r, l, n1)[a:b] @ self.vec(r, l, n2)[a:b])
+        return tot
+
+    # ---- V-cycle, mirroring mg_smooth_dist / mg_vcycle_dist
+    def _dinv(self, l, r, v):
+        a, b = self.rng(l, r)
+        D = self.ref[l].Dinv[a // 6:b // 6]
+        return np.einsum('nij,nj->ni', D, v.reshape(-1, 6)).ravel()
+
+    def smooth(self, l, bname, xname, zero_guess):
+        R = self.ref[l]
+        lmax, lmin = R.lam, R.lam / 4.0
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        sigma = theta / delta
+        rho = 1.0 / sigma
+        if not zero_guess:
+            self.exchange(l, xname)
+        for r in range(self.n_rank):
+            a, b = self.rng(l, r)
+            bv, x = self.vec(r, l, bname), self.vec(r, l, xname)
+            res = bv[a:b] if zero_guess else bv[a:b] - self.rows(R.A, l, r, x)
+            d = self._dinv(l, r, res) / theta
+            self.vec(r, l, 'd')[a:b] = d
+            x[a:b] = d if zero_guess else x[a:b] + d
+        for _ in range(1, self.deg):
+            self.exchange(l, xname)
+            rho_new = 1.0 / (2.0 * sigma - rho)
+            for r in range(self.n_rank):
+                a, b = self.rng(l, r)
+                bv, x, d = self.vec(r, l, bname), self.vec(r, l, xname), self.vec(r, l, 'd')
+                res = self._dinv(l, r, bv[a:b] - self.rows(R.A, l, r, x))
+                d[a:b] = rho_new * rho * d[a:b] + (2.0 * rho_new / delta) * res
+                x[a:b] += d[a:b]
+            rho = rho_new
+
+    def vcycle(self, l, bname, xname):
+        if l >= self.n_dist:       # replicated levels: every rank runs the plain V-cycle on its full copy
+            for r in range(self.n_rank):
+                b = self.vec(r, l, bname)
+                self.vec(r, l, xname)[:] = reference_vcycle(self.ref[l:], self.Ainv, b, deg=self.deg)
+            return
+        R = self.ref[l]
+        Pt = R.P.T.tocsr()
+        self.smooth(l, bname, xname, True)
+        self.exchange(l, xname)
+        for r in range(self.n_rank):
+            a, b = self.rng(l, r)
+            self.vec(r, l, 'r')[a:b] = self.vec(r, l, bname)[a:b] - self.rows(R.A, l, r, self.vec(r, l, xname))
+        self.exchange(l, 'r')
+        for r in range(self.n_rank):
+            a, b = self.rng(l + 1, r)
+            self.vec(r, l + 1, 'b')[a:b] = self.rows(Pt, l + 1, r, self.vec(r, l, 'r'))
+        if l + 1 == self.n_dist:
+            self.allgather(l + 1, 'b')
+        self.vcycle(l + 1, 'b', 'x')
+        if l + 1 < self.n_dist:
+            self.exchange(l + 1, 'x')
+        for r in range(self.n_rank):
+            a, b = self.rng(l, r)
+            self.vec(r, l, xname)[a:b] += self.rows(R.P, l, r, self.vec(r, l + 1, 'x'))
+        self.smooth(l, bname, xname, False)
+
+
+def emulate_distributed_vcycle(ref_levels, A_coarse_inv, plan, b, deg=2):
+    """z = V-cycle(b) computed by row ranges; returns (z assembled from the owners, number of exchanges)."""
+    E = _EmulatedRanks(ref_levels, A_coarse_inv, plan, deg)
+    for r in range(E.n_rank):
+        a, e = E.rng(0, r)
+        E.vec(r, 0, 'pr')[a:e] = b[a:e]
+    E.vcycle(0, 'pr', 'pz')
+    z = np.empty_like(b)
+    for r in range(E.n_rank):
+        a, e = E.rng(0, r)
+        z[a:e] = E.vec(r, 0, 'pz')[a:e]
+    return z, E.n_exchange
+
+
+def emulate_distributed_pcg(ref_levels, A_coarse_inv, plan, b, deg=2, rtol=1e-8, maxiter=200):
+    """The outer PCG of mg_solve_dist: range updates, one exchange of p per iteration, three summed dots."""
+    E = _EmulatedRanks(ref_levels, A_coarse_inv, plan, deg)
+    A = ref_levels[0].A
+    for r in range(E.n_rank):
+        a, e = E.rng(0, r)
+        E.vec(r, 0, 'b')[a:e] = b[a:e]
+        E.vec(r, 0, 'pr')[a:e] = b[a:e]
+        E.vec(r, 0, 'px')[a:e] = 0.0
+    bb = E.dot(0, 'b', 'b')
+    rr, rz, it = E.dot(0, 'pr', 'pr'), 0.0, 0
+    while np.sqrt(rr / bb) > rtol and it < maxiter:
+        E.vcycle(0, 'pr', 'pz')
+        rz_new = E.dot(0, 'pr', 'pz')
+        for r in range(E.n_rank):
+            a, e = E.rng(0, r)
+            p = E.vec(r, 0, 'pp')
+            p[a:e] = E.vec(r, 0, 'pz')[a:e] if it == 0 else E.vec(r, 0, 'pz')[a:e] + (rz_new / rz) * p[a:e]
+        rz = rz_new
+        E.exchange(0, 'pp')
+        for r in range(E.n_rank):
+            a, e = E.rng(0, r)
+            E.vec(r, 0, 'pq')[a:e] = E.rows(A, 0, r, E.vec(r, 0, 'pp'))
+        alpha = rz / E.dot(0, 'pp', 'pq')
+        for r in range(E.n_rank):
+            a, e = E.rng(0, r)
+            E.vec(r, 0, 'px')[a:e] += alpha * E.vec(r, 0, 'pp')[a:e]
+            E.vec(r, 0, 'pr')[a:e] -= alpha * E.vec(r, 0, 'pq')[a:e]
+        rr = E.dot(0, 'pr', 'pr')
+        it += 1
+    E.allgather(0, 'px')
+    xs = [E.vec(r, 0, 'px') for r in range(E.n_rank)]
+    for x in xs[1:]:
+        assert np.array_equal(x, xs[0])
+    return xs[0].copy(), it

@@ -1,0 +1,210 @@
+"""Distributed multigrid solve, host side (CPU): ownership renumbering, per-level row ranges and halo plans
+(jaxsso_b200/dist_multigrid.py).  The sequence of range products and exchanges that `mg_solve_dist` runs on
+the GPUs is replayed on simulated ranks with NaN-poisoned ghosts (oracle/multigrid_ref.py) and must
+reproduce the global V-cycle / PCG; the packed per-rank lists are exchanged for real over `gloo`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from jaxsso_b200 import dist_multigrid as dmg
+from jaxsso_b200 import meshes, multigrid as mg, partition
+from oracle import jaxsso_oracle as orc
+from oracle import multigrid_ref as mgref
+from tests.conftest import to_oracle_mesh
+from tests.test_multigrid import scaled_system
+
+
+def _setup(n, n_rank, min_dist_nodes, max_coarse_nodes=8):
+    md0 = meshes.plate(n)
+    owner = partition.rcb_owner(md0.crds[:, :2], n_rank)
+    perm, bounds = dmg.owner_permutation(owner, n_rank)
+    md = dmg.renumber_mesh(md0, perm)
+    Ah, L, mask = scaled_system(md)
+    rp, ci = Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32)
+    levels = mg.build_hierarchy(rp, ci, max_coarse_nodes=max_coarse_nodes)
+    ref, Ac = mgref.reference_setup(Ah.data, Ah.indptr, Ah.indices, md.crds, mask, levels, Lt0=L.transpose(0, 2, 1))
+    plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist_nodes)
+    return md0, md, perm, Ah, levels, ref, np.linalg.inv(Ac.toarray()), plan
+
+
+def test_renumbering_is_a_symmetric_permutation_of_K():
+    md0 = meshes.plate(8)
+    owner = partition.rcb_owner(md0.crds[:, :2], 4)
+    perm, bounds = dmg.owner_permutation(owner, 4)
+    assert np.array_equal(np.diff(bounds), np.bincount(owner, minlength=4))
+    for r in range(4):
+        assert np.all(owner[perm[bounds[r]:bounds[r + 1]]] == r)
+    md = dmg.renumber_mesh(md0, perm)
+    K0 = orc.K_global(to_oracle_mesh(md0)).tocsr()
+    K1 = orc.K_global(to_oracle_mesh(md)).tocsr()
+    d = (6 * perm[:, None] + np.arange(6)[None, :]).ravel()
+    assert abs(K1 - K0[d][:, d]).max() <= 1e-12 * abs(K0).max()
+    assert np.array_equal(np.sort(d[md.known]), np.sort(md0.known))
+    assert np.array_equal(md.loads, md0.loads[d])
+
+
+@pytest.mark.parametrize('n_rank', [2, 4])
+def test_coarse_ranges_and_plans_are_consistent(n_rank):
+    _, md, _, Ah, levels, _, _, plan = _setup(24, n_rank, min_dist_nodes=40)
+    assert plan['n_dist'] == 2 and len(plan['bounds']) == 3
+    for l, b in enumerate(plan['bounds']):
+        n_l = levels[l]['n_f'] if l < len(levels) else levels[-1]['n_c']
+        assert b[0] == 0 and b[-1] == n_l and np.all(np.diff(b) >= 0)
+    # most aggregates live where their members live
+    lv = levels[0]
+    own_f = np.searchsorted(plan['bounds'][0], np.arange(lv['n_f']), side='right') - 1
+    own_c = np.searchsorted(plan['bounds'][1], lv['agg'], side='right') - 1
+    assert np.mean(own_f == own_c) > 0.8
+    rps = [dmg.rank_plan(plan, r) for r in range(n_rank)]
+    for l in range(plan['n_dist']):
+        for r in range(n_rank):
+            me = rps[r][l]
+            lo, hi = plan['bounds'][l][r], plan['bounds'][l][r + 1]
+            assert np.all((me['send_idx'] >= lo) & (me['send_idx'] < hi))          # I only send what I own
+            assert not np.any((me['recv_idx'] >= lo) & (me['recv_idx'] < hi))
+            for i, p in enumerate(me['peer_rank']):
+                other = rps[p][l]
+                j = list(other['peer_rank']).index(r)
+                sent = me['send_idx'][me['send_ptr'][i]:me['send_ptr'][i + 1]]
+                recv = other['recv_idx'][other['recv_ptr'][j]:other['recv_ptr'][j + 1]]
+                assert np.array_equal(sent, recv)
+    s = dmg.plan_summary(plan)
+    assert s['n_dist'] == 2 and sum(s['rows_per_rank'][0]) == md.n_node
+
+
+@pytest.mark.parametrize('n_rank,min_dist,deg', [(2, 40, 1), (2, 40, 2), (4, 40, 1), (4, 200, 2), (4, 5, 1)])
+def test_replayed_distributed_vcycle_equals_global(n_rank, min_dist, deg):
+    _, md, _, Ah, levels, ref, Ainv, plan = _setup(24, n_rank, min_dist_nodes=min_dist)
+    assert plan['n_dist'] == {40: 2, 200: 1, 5: len(levels)}[min_dist]
+    b = np.random.default_rng(3).standard_normal(Ah.shape[0])
+    z_ref = mgref.reference_vcycle(ref, Ainv, b, deg=deg)
+    z, n_ex = mgref.emulate_distributed_vcycle(ref, Ainv, plan, b, deg=deg)
+    assert not np.isnan(z).any()
+    assert np.linalg.norm(z - z_ref) <= 1e-12 * np.linalg.norm(z_ref)
+    # exchanges per V-cycle: per distributed level 2 (residual, restriction) + deg (post-smoother) + (deg - 1)
+    # (pre-smoother) + 1 for the correction of every distributed coarse level
+    nd = plan['n_dist']
+    assert n_ex == nd * (2 + deg + deg - 1) + (nd - 1)
+
+
+def test_a_missing_ghost_is_detected():
+    """The NaN poisoning works: dropping one received node from the plan breaks the replay."""
+    _, md, _, Ah, levels, ref, Ainv, plan = _setup(24, 2, min_dist_nodes=200)
+    b = np.random.default_rng(3).standard_normal(Ah.shape[0])
+    plan['need'][0][1][0] = plan['need'][0][1][0][1:]
+    z, _ = mgref.emulate_distributed_vcycle(ref, Ainv, plan, b, deg=1)
+    assert np.isnan(z).any()
+
+
+@pytest.mark.parametrize('n_rank', [2, 4])
+def test_replayed_distributed_pcg_solves_the_original_system(n_rank):
+    md0, md, perm, Ah, levels, ref, Ainv, plan = _setup(24, n_rank, min_dist_nodes=40)
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(Ah.shape[0])
+    # global PCG with the plain V-cycle
+    x = np.zeros_like(b); r = b.copy()
+    z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+    p = z.copy(); rz = r @ z
+    for it in range(1, 200):
+        q = Ah @ p
+        a = rz / (p @ q)
+        x += a * p; r -= a * q
+        if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b):
+            break
+        z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+    xd, itd = mgref.emulate_distributed_pcg(ref, Ainv, plan, b, deg=1, rtol=1e-8)
+    assert itd == it and itd < 100
+    assert np.linalg.norm(xd - x) <= 1e-9 * np.linalg.norm(x)
+
+
+def test_block_ordering_keeps_the_iteration_count():
+    """Renumbering by owner changes the greedy aggregates; the preconditioner stays as good."""
+    def iters(md):
+        Ah, L, mask = scaled_system(md)
+        levels = mg.build_hierarchy(Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32), max_coarse_nodes=30)
+        ref, Ac = mgref.reference_setup(Ah.data, Ah.indptr, Ah.indices, md.crds, mask, levels, Lt0=L.transpose(0, 2, 1))
+        Ainv = np.linalg.inv(Ac.toarray())
+        b = np.random.default_rng(1).standard_normal(Ah.shape[0])
+        x = np.zeros_like(b); r = b.copy()
+        z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+        p = z.copy(); rz = r @ z
+        for it in range(1, 300):
+            q = Ah @ p
+            a = rz / (p @ q)
+            x += a * p; r -= a * q
+            if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b):
+                return it
+            z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+            rz, rz_old = r @ z, rz
+            p = z + (rz / rz_old) * p
+        return 300
+    md0 = meshes.plate(32)
+    base = iters(md0)
+    for n_rank in (2, 8):
+        perm, _ = dmg.owner_permutation(partition.rcb_owner(md0.crds[:, :2], n_rank), n_rank)
+        assert iters(dmg.renumber_mesh(md0, perm)) <= base * 1.25 + 2
+
+
+# ------------------------------------------------------------------------------- gloo, world_size 2
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    md0, md, perm, Ah, levels, ref, Ainv, plan = _setup(16, world, min_dist_nodes=30)
+    mine = dmg.rank_plan(plan, rank)
+    ok = True
+    for l in range(plan['n_dist']):
+        A = ref[l].A
+        n = A.shape[0]
+        xg = np.random.default_rng(10 + l).standard_normal(n)
+        lo, hi = 6 * plan['bounds'][l][rank], 6 * plan['bounds'][l][rank + 1]
+        x = np.full(n, np.nan)
+        x[lo:hi] = xg[lo:hi]
+        me = mine[l]
+        reqs, recvs = [], []
+        for i, p in enumerate(me['peer_rank']):
+            s_ids = me['send_idx'][me['send_ptr'][i]:me['send_ptr'][i + 1]]
+            r_ids = me['recv_idx'][me['recv_ptr'][i]:me['recv_ptr'][i + 1]]
+            if s_ids.size:     # pack -> send
+                reqs.append(dist.isend(torch.from_numpy(x.reshape(-1, 6)[s_ids].copy()), int(p)))
+            if r_ids.size:
+                rb = torch.zeros((r_ids.size, 6), dtype=torch.float64)
+                reqs.append(dist.irecv(rb, int(p)))
+                recvs.append((r_ids, rb))
+        for rq in reqs:
+            rq.wait()
+        for r_ids, rb in recvs:   # unpack
+            x.reshape(-1, 6)[r_ids] = rb.numpy()
+        y = A[lo:hi] @ x
+        ok = ok and bool(np.allclose(y, (A @ xg)[lo:hi], rtol=1e-13, atol=1e-13 * abs(A @ xg).max()))
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_rank_plans_over_gloo():
+    import torch.multiprocessing as tmp
+    world = 2
+    ctx = tmp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(ret[r] for r in range(world))
