@@ -315,10 +315,27 @@ def run_b200(args):
         # assembly, no communication); Ke+assembly+adjoint of the metric stay partitioned.  --precond
         # block_jacobi runs the distributed CG (halo pushes over NVLink peer memory) instead.
         t_mg = time.perf_counter()
-        hg = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=local_rank)
-        hg.mg_setup()
+        smd, inv_perm = gmd, None     # the mesh the solve handle sees
+        if args.dist_mg:
+            # row-range distributed V-cycle PCG (jsso_mg_set_dist): the whole mesh renumbered so that every rank's
+            # nodes are one range; assembly + numeric multigrid setup stay replicated, the iteration is distributed
+            from jaxsso_b200 import dist_multigrid as dmg
+            perm, bounds = dmg.owner_permutation(owner, world)
+            smd = dmg.renumber_mesh(gmd, perm)
+            inv_perm = np.empty(gmd.n_node, np.int64)
+            inv_perm[perm] = np.arange(gmd.n_node)
+        hg = nat.Handle(smd.n_node, smd.cnct_quads, smd.cnct_beams, smd.known, device=local_rank)
+        levels = hg.mg_setup()
         mg_info = {'nodes_per_level': [a for a, _ in hg.mg_levels] + [hg.mg_levels[-1][1]],
                    'symbolic_setup_s': time.perf_counter() - t_mg}
+        if args.dist_mg:
+            rp_, ci_ = hg.pattern()
+            plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=args.min_dist_nodes)
+            idbuf2 = [nat.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(idbuf2, src=0)
+            hg.mg_set_dist(idbuf2[0], rank, world, plan)
+            mg_info['distributed'] = dmg.plan_summary(plan)
+        del levels
     if world == 1 and args.solve and args.precond != 'block_jacobi':
         # single GPU: smoothed-aggregation multigrid preconditioner (symbolic hierarchy, once per model)
         t_mg = time.perf_counter()
@@ -406,9 +423,9 @@ def run_b200(args):
                              precond=precond, cheb_degree=args.cheb_degree)
         uu_d = D((md.ndof,))
         if hg is not None:   # replicated multigrid solve on the whole mesh, partitioned adjoint
-            gc_d, gq_d, gb_d = D.from_host(gmd.crds), D.from_host(gmd.prop_quads), D.from_host(gmd.prop_beams)
-            gf_d, gu_d = D.from_host(gmd.loads), D((gmd.ndof,))
-            l2g_d = D.from_host(lm.l2g.astype(np.int32))
+            gc_d, gq_d, gb_d = D.from_host(smd.crds), D.from_host(smd.prop_quads), D.from_host(smd.prop_beams)
+            gf_d, gu_d = D.from_host(smd.loads), D((smd.ndof,))
+            l2g_d = D.from_host((lm.l2g if inv_perm is None else inv_perm[lm.l2g]).astype(np.int32))
         barrier()
         t0 = time.perf_counter()
         try:
@@ -430,11 +447,15 @@ def run_b200(args):
                          'preconditioner': (f'smoothed-aggregation multigrid (V-cycle, Chebyshev-{args.cheb_degree}, FP32 level matrices)'
                                             if precond != 'block_jacobi' else 'block-Jacobi'),
                          'solve': ('single GPU' if world == 1 else
-                                   ('replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
+                                   (('V-cycle PCG distributed by row ranges (replicated assembly + numeric setup), '
+                                     'adjoint partitioned') if (hg is not None and args.dist_mg) else
+                                    'replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
                                     else 'distributed CG over the partition')),
                          'multigrid': mg_info,
                          'note': 'Ke+assembly, PCG for u (numeric multigrid setup included), lam = u/2 '
                                  '(compliance), adjoint'}
+            if hg is not None and args.dist_mg:
+                grad_eval['halo_exchanges'], grad_eval['scalar_allreduces'] = hg.mg_dist_counters()
         else:
             grad_eval = {'error': ok, 'seconds': dt}
 
@@ -530,6 +551,11 @@ def main():
     ap.add_argument('--no-solve', dest='solve', action='store_false')
     ap.add_argument('--no-p2p', dest='p2p', action='store_false',
                     help='distributed CG over NCCL send/recv + all-reduce instead of peer-memory kernels')
+    ap.add_argument('--dist-mg', action='store_true',
+                    help='N > 1: distribute the multigrid V-cycle PCG by row ranges (jsso_mg_set_dist) instead of '
+                         'solving redundantly on every rank')
+    ap.add_argument('--min-dist-nodes', type=int, default=20000,
+                    help='multigrid levels with fewer nodes run replicated under --dist-mg')
     ap.add_argument('--rtol', type=float, default=1e-8)
     ap.add_argument('--precond', default='auto', choices=['auto', 'block_jacobi', 'multigrid'])
     ap.add_argument('--maxiter', type=int, default=400000)

@@ -203,6 +203,24 @@ int jsso_pcg(jsso_handle* h, const double* b_d, double* x_d, const jsso_solve_op
  * is rebuilt inside the first solve after each assembly. */
 int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_level_desc* levels);
 
+/* Row-range distribution of the multigrid-preconditioned solve over N GPUs (one process per GPU; SURVEY 8(e):
+ * "PCG per iteration: halo exchange ... overlapped", 8(f) rank 1).  The handle holds the WHOLE mesh, renumbered
+ * so that every rank's nodes are one contiguous range (jaxsso_b200/dist_multigrid.py), with the hierarchy already
+ * uploaded; assembly and the numeric multigrid setup stay replicated, the V-cycle and PCG products are computed
+ * by row ranges with the halo exchanges described per level below, levels >= n_dist run replicated.  Collective
+ * over the communicator of `nccl_id` (jsso_nccl_unique_id on rank 0, distributed by the caller).
+ * bounds_h: (n_dist + 1) x (n_rank + 1) int32, row-range bounds of levels 0..n_dist. */
+typedef struct {
+  int32_t n_peer;
+  const int32_t *peer_rank;          /* [n_peer] */
+  const int32_t *send_ptr, *send_idx; /* [n_peer + 1], node ids of this level this rank owns and the peer reads */
+  const int32_t *recv_ptr, *recv_idx; /* [n_peer + 1], node ids the peer owns and this rank's rows read */
+} jsso_mg_halo_desc;
+int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
+                     const int32_t* bounds_h, const jsso_mg_halo_desc* halo);
+/* out[0] = halo exchanges, out[1] = scalar all-reduces issued by the distributed solve so far. */
+int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out);
+
 /* ---- adjoint sensitivity reduction ---------------------------------------------- */
 /* d_crds[n,c] = sum_e sum_ab (-lam_e[a] u_e[b]) dK_e[a,b]/dcrds[n,c], same for the
  * element properties.  Any of the three outputs may be NULL. */

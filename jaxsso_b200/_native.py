@@ -60,13 +60,19 @@ _MG_PTR_FIELDS = ['agg', 'p_rowptr', 'p_col', 'p_own', 'ps_ptr', 'ps_a', 'ps_j',
 class MgLevelDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in _MG_INT_FIELDS] + [(k, C.c_void_p) for k in _MG_PTR_FIELDS]
 
+
+
+class MgHaloDesc(C.Structure):
+    _fields_ = [('n_peer', C.c_int32)] + [(k, C.c_void_p) for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr',
+                                                                      'recv_idx')]
+
 PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_mg_aggregate', 'jsso_mg_pattern_lists', 'jsso_assembly_tasks',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_gather_rows', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
-           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_adjoint',
+           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_mg_set_dist', 'jsso_mg_dist_counters', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
@@ -113,6 +119,8 @@ def lib():
     L.jsso_spmv.argtypes = [vp, vp, vp, vp]
     L.jsso_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_mg_setup.argtypes = [vp, i32, C.POINTER(MgLevelDesc)]
+    L.jsso_mg_set_dist.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(MgHaloDesc)]
+    L.jsso_mg_dist_counters.argtypes = [vp, vp]
     L.jsso_adjoint.argtypes = [vp] + [vp] * 8 + [vp]
     L.jsso_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_backward.argtypes = [vp] + [vp] * 9 + [C.POINTER(SolveOpts), C.POINTER(Stats), vp]
@@ -402,6 +410,29 @@ class Handle:
         self._ck(lib().jsso_mg_setup(self.h, len(levels), descs))
         self.mg_levels = [(lv['n_f'], lv['n_c']) for lv in levels]
         return levels
+
+    def mg_set_dist(self, nccl_id, rank, n_rank, plan):
+        """Distribute the multigrid solve of this whole-mesh handle by row ranges (collective; `plan` from
+        jaxsso_b200.dist_multigrid.build_plan, computed identically on every rank)."""
+        from . import dist_multigrid
+        mine = dist_multigrid.rank_plan(plan, rank)
+        n_dist = plan['n_dist']
+        bounds = np.ascontiguousarray(np.stack(plan['bounds'][:n_dist + 1]), np.int32)
+        descs = (MgHaloDesc * max(n_dist, 1))()
+        keep = []
+        for d, lv in zip(descs, mine):
+            d.n_peer = int(lv['peer_rank'].shape[0])
+            for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr', 'recv_idx'):
+                a = np.ascontiguousarray(lv[k], dtype=np.int32)
+                keep.append(a)
+                setattr(d, k, a.ctypes.data)
+        idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
+        self._ck(lib().jsso_mg_set_dist(self.h, _ptr(idb), int(rank), int(n_rank), int(n_dist), _ptr(bounds), descs))
+
+    def mg_dist_counters(self):
+        out = np.zeros(2, np.int64)
+        self._ck(lib().jsso_mg_dist_counters(self.h, _ptr(out)))
+        return int(out[0]), int(out[1])
 
     # ---- adjoint
     def adjoint(self, crds, prop_q, prop_b, u, lam, d_crds=None, d_prop_q=None, d_prop_b=None, stream=None):

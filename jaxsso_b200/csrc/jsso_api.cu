@@ -145,6 +145,22 @@ struct jsso_handle {
   double* mg_scal_host = nullptr;  // pinned
   bool mg_ready = false;           // numeric hierarchy matches the current matrix
   const double* last_crds = nullptr;
+  // row-range distributed multigrid solve (jsso_mg_set_dist): the hierarchy above stays replicated on every
+  // rank, the V-cycle / PCG products are computed by row ranges with halo exchanges between the ranks
+  struct MgDistPeer { int rank, send_off, send_cnt, recv_off, recv_cnt; };   // node counts
+  struct MgDistLevel {
+    std::vector<MgDistPeer> peers;
+    int32_t *send_idx = nullptr, *recv_idx = nullptr;   // device: node ids of this level
+    int n_send = 0, n_recv = 0;
+  };
+  struct MgDist {
+    int rank = 0, n_rank = 1, n_dist = 0;
+    ncclComm_t comm = nullptr;
+    std::vector<std::vector<int32_t>> bounds;   // [n_dist + 1][n_rank + 1] row ranges per level
+    std::vector<MgDistLevel> lv;                // [n_dist]
+    double *send_buf = nullptr, *recv_buf = nullptr;
+    long long n_exchange = 0, n_allreduce = 0;
+  } mgd;
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
@@ -365,6 +381,10 @@ void jsso_destroy(jsso_handle* h) {
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); }
+  if (h->mgd.send_buf) cudaFree(h->mgd.send_buf);
+  if (h->mgd.recv_buf) cudaFree(h->mgd.recv_buf);
+  if (h->mgd.comm && g_nccl.ok) g_nccl.CommDestroy(h->mgd.comm);
   delete h;
 }
 
@@ -974,6 +994,71 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
   return JSSO_OK;
 }
 
+// Row-range distribution of the multigrid solve over the ranks of one NCCL communicator (see mg_solve_dist).
+// The handle must hold the WHOLE mesh, renumbered so that every rank's nodes are one range
+// (jaxsso_b200/dist_multigrid.py), with the hierarchy already uploaded by jsso_mg_setup.  Collective: every rank
+// calls it (ncclCommInitRank).  bounds: (n_dist + 1) x (n_rank + 1) row-range bounds per level; halo: n_dist entries.
+extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
+                                const int32_t* bounds, const jsso_mg_halo_desc* halo) {
+  if (!h || !nccl_id || !bounds || (n_dist > 0 && !halo)) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  if (h->mg.empty()) return fail(h, JSSO_ERR_STATE, "jsso_mg_set_dist needs the hierarchy (jsso_mg_setup) first");
+  if (h->n_rank > 1 || h->sym.n_row != h->sym.n_node)
+    return fail(h, JSSO_ERR_STATE, "jsso_mg_set_dist: whole-mesh handles only (the partition is by row ranges)");
+  if (h->mgd.comm) return fail(h, JSSO_ERR_STATE, "distributed multigrid already set");
+  const int nl = (int)h->mg.size();
+  if (n_rank < 2 || rank < 0 || rank >= n_rank || n_dist < 1 || n_dist > nl)
+    return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: need n_rank >= 2, 0 <= rank < n_rank, 1 <= n_dist <= levels");
+  jsso_handle::MgDist D;
+  D.rank = rank; D.n_rank = n_rank; D.n_dist = n_dist;
+  size_t max_send = 0, max_recv = 0;
+  for (int l = 0; l <= n_dist; ++l) {
+    const int n_l = (l == 0) ? h->sym.n_row : h->mg[l - 1].n_c;
+    const int32_t* b = bounds + (size_t)l * (n_rank + 1);
+    if (b[0] != 0 || b[n_rank] != n_l) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bounds do not cover a level");
+    for (int r = 0; r < n_rank; ++r)
+      if (b[r + 1] < b[r]) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bounds not monotone");
+    D.bounds.emplace_back(b, b + n_rank + 1);
+  }
+  for (int l = 0; l < n_dist; ++l) {
+    const jsso_mg_halo_desc& d = halo[l];
+    const int n_l = (l == 0) ? h->sym.n_row : h->mg[l - 1].n_c;
+    const int lo = D.bounds[l][rank], hi = D.bounds[l][rank + 1];
+    jsso_handle::MgDistLevel L;
+    if (d.n_peer < 0 || (d.n_peer > 0 && (!d.peer_rank || !d.send_ptr || !d.recv_ptr)))
+      return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad halo description");
+    for (int i = 0; i < d.n_peer; ++i) {
+      if (d.peer_rank[i] < 0 || d.peer_rank[i] >= n_rank || d.peer_rank[i] == rank)
+        return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad peer rank");
+      L.peers.push_back(jsso_handle::MgDistPeer{d.peer_rank[i], d.send_ptr[i], d.send_ptr[i + 1] - d.send_ptr[i],
+                                                d.recv_ptr[i], d.recv_ptr[i + 1] - d.recv_ptr[i]});
+    }
+    L.n_send = d.n_peer ? d.send_ptr[d.n_peer] : 0;
+    L.n_recv = d.n_peer ? d.recv_ptr[d.n_peer] : 0;
+    std::vector<int32_t> si(d.send_idx, d.send_idx + L.n_send), ri(d.recv_idx, d.recv_idx + L.n_recv);
+    for (int v : si) if (v < lo || v >= hi) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: send index not owned");
+    for (int v : ri) if (v < 0 || v >= n_l || (v >= lo && v < hi)) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad receive index");
+    CK(upload(&L.send_idx, si)); CK(upload(&L.recv_idx, ri));
+    max_send = std::max(max_send, (size_t)L.n_send); max_recv = std::max(max_recv, (size_t)L.n_recv);
+    D.lv.push_back(L);
+  }
+  CK(dalloc(&D.send_buf, 6 * max_send)); CK(dalloc(&D.recv_buf, 6 * max_recv));
+  if (!nccl_load()) return fail(h, JSSO_ERR_NCCL, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  std::memcpy(&id, nccl_id, 128);
+  CKN(g_nccl.CommInitRank(&D.comm, n_rank, id, rank));
+  h->mgd = D;
+  return JSSO_OK;
+}
+
+// statistics of the distributed solve since jsso_mg_set_dist: out[0] = halo exchanges, out[1] = scalar all-reduces
+extern "C" int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out) {
+  if (!h || !out) return JSSO_ERR_ARG;
+  out[0] = h->mgd.n_exchange; out[1] = h->mgd.n_allreduce;
+  return JSSO_OK;
+}
+
 struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; };
 static MgMat mg_matrix(jsso_handle* h, int l) {
   if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32};
@@ -1220,6 +1305,210 @@ static int mg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
   return JSSO_OK;
 }
 
+// ---------------------------------------------------------------- multigrid, row-range distributed solve
+// The hierarchy is replicated (every rank assembled the whole renumbered mesh and ran mg_numeric_setup); rank r
+// computes rows [bounds[l][r], bounds[l][r+1]) of every product at the distributed levels l < n_dist with the
+// same kernels (offset pointers: `rowptr + s`, `y + 6 s`; x stays full length in global numbering).  Before a
+// product the entries of x that its rows read and other ranks own are delivered by mgd_exchange (pack ->
+// grouped ncclSend/ncclRecv -> unpack at the global positions).  Levels >= n_dist run replicated on the
+// all-gathered right-hand side.  The same sequence of range products and exchanges is replayed on the CPU with
+// NaN-poisoned ghosts by oracle/multigrid_ref.py::emulate_distributed_pcg (tests/test_dist_multigrid.py).
+static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n) {
+  const std::vector<int32_t>& b = h->mgd.bounds[l];
+  s = b[h->mgd.rank];
+  n = b[h->mgd.rank + 1] - s;
+}
+
+static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st) {
+  jsso_handle::MgDistLevel& d = h->mgd.lv[l];
+  if (d.peers.empty()) return JSSO_OK;
+  if (d.n_send > 0) {
+    halo_pack_kernel<<<cdiv(6LL * d.n_send, 256), 256, 0, st>>>(d.n_send, d.send_idx, v, h->mgd.send_buf);
+    CKL("halo_pack_kernel");
+  }
+  CKN(g_nccl.GroupStart());
+  for (const jsso_handle::MgDistPeer& p : d.peers) {
+    if (p.send_cnt)
+      CKN(g_nccl.Send(h->mgd.send_buf + 6 * (size_t)p.send_off, 6 * (size_t)p.send_cnt, ncclDouble, p.rank, h->mgd.comm, st));
+    if (p.recv_cnt)
+      CKN(g_nccl.Recv(h->mgd.recv_buf + 6 * (size_t)p.recv_off, 6 * (size_t)p.recv_cnt, ncclDouble, p.rank, h->mgd.comm, st));
+  }
+  CKN(g_nccl.GroupEnd());
+  if (d.n_recv > 0) {
+    halo_unpack_kernel<<<cdiv(6LL * d.n_recv, 256), 256, 0, st>>>(d.n_recv, d.recv_idx, h->mgd.recv_buf, v);
+    CKL("halo_unpack_kernel");
+  }
+  ++h->mgd.n_exchange;
+  return JSSO_OK;
+}
+
+// every rank's row range of a level-l vector to every other rank (ranges are contiguous: no packing)
+static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st) {
+  const std::vector<int32_t>& b = h->mgd.bounds[l];
+  const int me = h->mgd.rank;
+  const size_t mine = 6 * (size_t)(b[me + 1] - b[me]);
+  CKN(g_nccl.GroupStart());
+  for (int r = 0; r < h->mgd.n_rank; ++r) {
+    if (r == me) continue;
+    const size_t theirs = 6 * (size_t)(b[r + 1] - b[r]);
+    if (mine) CKN(g_nccl.Send(v + 6 * (size_t)b[me], mine, ncclDouble, r, h->mgd.comm, st));
+    if (theirs) CKN(g_nccl.Recv(v + 6 * (size_t)b[r], theirs, ncclDouble, r, h->mgd.comm, st));
+  }
+  CKN(g_nccl.GroupEnd());
+  return JSSO_OK;
+}
+
+// sum over the ranks of `count` device scalars starting at slot (in place), then read all scalars back
+static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st) {
+  CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
+  ++h->mgd.n_allreduce;
+  return mg_read_scalars(h, st);
+}
+
+static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, bool zero_guess, int deg, cudaStream_t st) {
+  jsso_handle::MgLevel& m = h->mg[l];
+  const MgMat A = mg_matrix(h, l);
+  int s, n;
+  mgd_range(h, l, s, n);
+  const size_t off = 6 * (size_t)s;
+  const int nb = cdiv(n, 128);
+  const double* Dinv = m.Dinv ? m.Dinv + 36 * (size_t)s : nullptr;
+  const double lmax = m.lam, lmin = m.lam / 4.0;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  int rc;
+  if (zero_guess) {
+    if (n > 0) {
+      mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, Dinv, b + off, m.d + off, x + off, 0.0, 1.0 / theta, 1);
+      CKL("mg_cheb_kernel<1>");
+    }
+  } else {
+    if ((rc = mgd_exchange(h, l, x, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;
+    if (n > 0) {
+      mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, 0.0, 1.0 / theta, 0);
+      CKL("mg_cheb_kernel<1>");
+    }
+  }
+  for (int k = 1; k < deg; ++k) {
+    if ((rc = mgd_exchange(h, l, x, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    if (n > 0) {
+      mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, rho_new * rho, 2.0 * rho_new / delta, 0);
+      CKL("mg_cheb_kernel<0>");
+    }
+    rho = rho_new;
+  }
+  return JSSO_OK;
+}
+
+// b, x: full-length level-l vectors; on entry b is valid on this rank's range (everywhere at replicated levels),
+// on exit x is valid on this rank's range (everywhere at replicated levels)
+static int mg_vcycle_dist(jsso_handle* h, int l, double* b, double* x, int deg, cudaStream_t st) {
+  const int nl = (int)h->mg.size();
+  if (l >= h->mgd.n_dist) return mg_vcycle(h, l, b, x, deg, st);
+  int rc;
+  jsso_handle::MgLevel& m = h->mg[l];
+  const MgMat A = mg_matrix(h, l);
+  int s, n, s1, n1;
+  mgd_range(h, l, s, n);
+  mgd_range(h, l + 1, s1, n1);
+  const size_t off = 6 * (size_t)s, off1 = 6 * (size_t)s1;
+  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
+  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
+  if ((rc = mg_smooth_dist(h, l, b, x, true, deg, st))) return rc;
+  if ((rc = mgd_exchange(h, l, x, st))) return rc;
+  if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;        // r = b - A x
+  if ((rc = mgd_exchange(h, l, m.r, st))) return rc;
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st))) return rc;   // b_c = P^T r
+  if (l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; }
+  if ((rc = mg_vcycle_dist(h, l + 1, bc, xc, deg, st))) return rc;
+  if (l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; }
+  if ((rc = mg_spmv_p<3>(h, m.p_rowptr + s, m.p_col, m.P, m.P32, n, xc, x + off, nullptr, st,
+                         m.nnz_p <= 5LL * m.n_f))) return rc;                                            // x += P x_c
+  return mg_smooth_dist(h, l, b, x, false, deg, st);
+}
+
+// PCG on the scaled system, V-cycle preconditioner, rows of this rank only; the solution is all-gathered at the
+// end so that the caller's unscaling / adjoint see the whole vector on every rank
+static int mg_solve_dist(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, jsso_stats* stats, cudaStream_t st) {
+  int rc = mg_numeric_setup(h, st);
+  if (rc) return rc;
+  int s, n_row;
+  mgd_range(h, 0, s, n_row);
+  const size_t off = 6 * (size_t)s;
+  const long long n = 6LL * n_row;
+  const int vb = std::max(1, std::min(h->red_blocks, cdiv(n, 256)));
+  double *b = h->vb, *x = h->vx, *r = h->vr, *p = h->vp, *q = h->vq, *z = h->tmp_g;
+  const MgMat A = mg_matrix(h, 0);
+  if (use_x0) {
+    if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;   // x is whole on every rank
+  } else {
+    CK(cudaMemsetAsync(x + off, 0, n * sizeof(double), st));
+    CK(cudaMemcpyAsync(r + off, b + off, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  if ((rc = mg_dot(h, n, b + off, b + off, 1, st))) return rc;
+  if ((rc = mg_dot(h, n, r + off, r + off, 2, st))) return rc;
+  if ((rc = mgd_reduce_read(h, 1, 2, st))) return rc;
+  const double bb = h->mg_scal_host[1];
+  double rr = h->mg_scal_host[2], rz = 0.0;
+  int it = 0;
+  bool converged = (bb == 0.0) || std::sqrt(rr / bb) <= o.rtol;
+  while (!converged && it < o.maxiter) {
+    if ((rc = mg_vcycle_dist(h, 0, r, z, o.cheb_degree, st))) return rc;
+    if ((rc = mg_dot(h, n, r + off, z + off, 3, st))) return rc;
+    if ((rc = mgd_reduce_read(h, 3, 1, st))) return rc;
+    const double rz_new = h->mg_scal_host[3];
+    if (!(rz_new > 0.0)) {
+      char buf[200];
+      std::snprintf(buf, sizeof buf, "distributed multigrid PCG breakdown at iteration %d: r.z = %.3e (lam0 = %.3f)", it,
+                    rz_new, h->mg.empty() ? 0.0 : h->mg[0].lam);
+      return fail(h, JSSO_ERR_NAN, buf);
+    }
+    if (it == 0) { CK(cudaMemcpyAsync(p + off, z + off, n * sizeof(double), cudaMemcpyDeviceToDevice, st)); }
+    else { mg_axpby_kernel<<<vb, 256, 0, st>>>(n, 1.0, z + off, rz_new / rz, p + off); CKL("mg_axpby_kernel"); }
+    rz = rz_new;
+    if ((rc = mgd_exchange(h, 0, p, st))) return rc;
+    if ((rc = mg_spmv<0>(h, A.rp + s, A.ci, A.v, n_row, p, q + off, nullptr, st))) return rc;
+    if ((rc = mg_dot(h, n, p + off, q + off, 4, st))) return rc;
+    if ((rc = mgd_reduce_read(h, 4, 1, st))) return rc;
+    const double pq = h->mg_scal_host[4];
+    if (!(pq > 0.0)) return fail(h, JSSO_ERR_NAN, "distributed multigrid PCG breakdown: non-positive curvature");
+    const double alpha = rz / pq;
+    mg_axpby_kernel<<<vb, 256, 0, st>>>(n, alpha, p + off, 1.0, x + off); CKL("mg_axpby_kernel");
+    mg_axpby_kernel<<<vb, 256, 0, st>>>(n, -alpha, q + off, 1.0, r + off); CKL("mg_axpby_kernel");
+    if ((rc = mg_dot(h, n, r + off, r + off, 2, st))) return rc;
+    if ((rc = mgd_reduce_read(h, 2, 1, st))) return rc;
+    rr = h->mg_scal_host[2];
+    ++it;
+    if (!(rr == rr)) return fail(h, JSSO_ERR_NAN, "distributed multigrid PCG: NaN residual");
+    if (std::sqrt(rr / bb) <= o.rtol) {
+      // confirm on the true residual; if the recurrence drifted keep iterating from it
+      if ((rc = mgd_exchange(h, 0, x, st))) return rc;
+      if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;
+      if ((rc = mg_dot(h, n, r + off, r + off, 2, st))) return rc;
+      if ((rc = mgd_reduce_read(h, 2, 1, st))) return rc;
+      rr = h->mg_scal_host[2];
+      if (std::sqrt(rr / bb) <= 1.5 * o.rtol) converged = true;
+      else if (stats) stats->restarts += 1;
+      if (stats && stats->restarts > 20) break;
+    }
+  }
+  if ((rc = mgd_allgather(h, 0, x, st))) return rc;
+  if (stats) {
+    stats->iterations = it; stats->converged = converged ? 1 : 0;
+    stats->relres = bb > 0 ? std::sqrt(rr / bb) : 0.0; stats->relres_recur = stats->relres;
+  }
+  if (!converged) {
+    char buf[200];
+    std::snprintf(buf, sizeof buf, "distributed multigrid PCG did not reach rtol=%.3g: relres %.3g after %d iterations",
+                  o.rtol, bb > 0 ? std::sqrt(rr / bb) : 0.0, it);
+    return fail(h, JSSO_ERR_NOCONV, buf);
+  }
+  return JSSO_OK;
+}
+
 extern "C" {
 
 // K x = b on the assembled BC-imposed matrix: scale, solve, unscale.
@@ -1252,7 +1541,8 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
   const bool use_mg = (o.precond == 2) || (o.precond == 0 && have_mg && h->sym.n_row >= 20000);
   if (use_mg && !have_mg) return fail(h, JSSO_ERR_STATE, "precond = multigrid but no hierarchy (jsso_mg_setup)");
   if (stats) stats->flags = fl;
-  rc = use_mg ? mg_solve_scaled(h, o, o.use_x0 != 0, stats, st) : cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
+  if (use_mg) rc = (h->mgd.n_rank > 1) ? mg_solve_dist(h, o, o.use_x0 != 0, stats, st) : mg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
+  else rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
   if (rc && rc != JSSO_ERR_NOCONV) return rc;
   block_apply_kernel<1><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->vx, nullptr, x);

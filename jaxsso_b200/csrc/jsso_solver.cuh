@@ -801,5 +801,13 @@ __global__ void halo_pack_kernel(int n, const int32_t* __restrict__ idx, const d
   if (t >= 6 * n) return;
   buf[t] = v[6 * (size_t)idx[t / 6] + t % 6];
 }
+// halo unpack: v[6*idx[k]+d] = buf[k*6+d]  (receive side of the row-range distributed multigrid solve, where
+// ghosts keep their global position instead of sitting in a contiguous tail)
+__global__ void halo_unpack_kernel(int n, const int32_t* __restrict__ idx, const double* __restrict__ buf,
+                                   double* __restrict__ v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * n) return;
+  v[6 * (size_t)idx[t / 6] + t % 6] = buf[t];
+}
 
 }  // namespace jsso
