@@ -139,6 +139,8 @@ struct jsso_handle {
   double* Lfac = nullptr;          // L_i (row-major) of the fine diagonal blocks
   float* vals32 = nullptr;         // single-precision copy of the scaled fine matrix (V-cycle only)
   bool mg_fp32 = true;
+  __half* vals16 = nullptr;        // binary16 copy of the scaled fine matrix (V-cycle only; JSSO_MG_FP16=1)
+  bool mg_fp16 = false;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -381,6 +383,17 @@ void jsso_destroy(jsso_handle* h) {
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  for (auto& m : h->mg) {
+    void* lv[] = {m.agg, m.p_row, m.p_rowptr, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.apl_ptr, m.apl_a, m.apl_p,
+                  m.c_rowptr, m.c_col, m.c_diag, m.cl_ptr, m.cl_p, m.cl_ap, m.pt_rowptr, m.pt_col, m.pt_src, m.mem_ptr,
+                  m.mem, m.P, m.Pt, m.AP, m.Ac, m.Xc, m.Dinv, m.P32, m.Pt32, m.Ac32, m.b, m.x, m.r, m.d};
+    for (void* p : lv) if (p) cudaFree(p);
+  }
+  {
+    void* mgp[] = {h->Lfac, h->vals32, h->vals16, h->mg_dense, h->mg_cb, h->mg_cx, h->mg_scal};
+    for (void* p : mgp) if (p) cudaFree(p);
+    if (h->mg_scal_host) cudaFreeHost(h->mg_scal_host);
+  }
   for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); }
   if (h->mgd.send_buf) cudaFree(h->mgd.send_buf);
   if (h->mgd.recv_buf) cudaFree(h->mgd.recv_buf);
@@ -987,6 +1000,9 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
   {
     const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
     h->mg_fp32 = !(e && e[0] == '1');
+    const char* e16 = std::getenv("JSSO_MG_FP16");   // opt-in: binary16 storage of the fine-level V-cycle matrix
+    h->mg_fp16 = h->mg_fp32 && n_levels > 0 && e16 && e16[0] == '1';
+    if (h->mg_fp16) CK(dalloc(&h->vals16, 36 * (size_t)h->sym.nnzb()));
   }
   h->mg_ready = false;
   h->assembled = false;   // the fine factor L is produced by the scaling of the NEXT assembly
@@ -1059,11 +1075,11 @@ extern "C" int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out) {
   return JSSO_OK;
 }
 
-struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; };
+struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; const __half* v16; };
 static MgMat mg_matrix(jsso_handle* h, int l) {
-  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32};
+  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32, h->mg_fp16 ? h->vals16 : nullptr};
   const jsso_handle::MgLevel& p = h->mg[l - 1];
-  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c, p.Ac32};
+  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c, p.Ac32, nullptr};
 }
 static inline int mg_blocks(jsso_handle* h, int n_row) {
   return std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
@@ -1080,9 +1096,14 @@ static int mg_spmv(jsso_handle* h, const int32_t* rp, const int32_t* ci, const d
 template <int MODE>
 static int mg_spmv_p(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, const float* v32,
                      int n_row, const double* x, double* y, const double* b, cudaStream_t st,
-                     bool short_rows = false) {
+                     bool short_rows = false, const __half* v16 = nullptr) {
   if (!h->mg_fp32 || !v32) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
   if (n_row == 0) return JSSO_OK;
+  if (v16 && !short_rows) {   // fine level, binary16 blocks (JSSO_MG_FP16=1)
+    bsr_spmv_axpby_kernel<MODE, __half><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v16, x, y, b);
+    CKL("bsr_spmv_axpby_kernel<half>");
+    return JSSO_OK;
+  }
   if (short_rows) {   // prolongators: a thread per (row, row pair)
     bsr_spmv_short_kernel<MODE><<<cdiv(3LL * n_row, 256), 256, 0, st>>>(n_row, rp, ci, v32, x, y, b);
     CKL("bsr_spmv_short_kernel");
@@ -1169,6 +1190,11 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_fp32 && nl > 0) {
     if ((rc = mg_to_float(h, 36LL * h->sym.nnzb(), h->vals, h->vals32, st))) return rc;
   }
+  if (h->mg_fp16 && nl > 0 && h->sym.nnzb() > 0) {
+    const long long n16 = 36LL * h->sym.nnzb();
+    mg_to_half_kernel<<<std::max(1, std::min(1184, cdiv(n16, 256))), 256, 0, st>>>(n16, h->vals, h->vals16);
+    CKL("mg_to_half_kernel");
+  }
   // coarsest level: dense inverse
   const MgMat C = mg_matrix(h, nl);
   const int nc = 6 * C.n;
@@ -1194,12 +1220,12 @@ static int mg_smooth(jsso_handle* h, int l, const double* b, double* x, bool zer
   if (zero_guess) {
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, b, m.d, x, 0.0, 1.0 / theta, 1);
   } else {
-    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16))) return rc;
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, 0.0, 1.0 / theta, 0);
   }
   CKL("mg_cheb_kernel<1>");
   for (int k = 1; k < deg; ++k) {
-    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16))) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, rho_new * rho, 2.0 * rho_new / delta, 0);
     CKL("mg_cheb_kernel<0>");
@@ -1222,7 +1248,7 @@ static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg,
   double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
   if ((rc = mg_smooth(h, l, b, x, true, deg, st))) return rc;
-  if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st))) return rc;          // r = b - A x
+  if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st, false, A.v16))) return rc;          // r = b - A x
   if ((rc = mg_spmv_p<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.Pt32, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
   if ((rc = mg_vcycle(h, l + 1, bc, xc, deg, st))) return rc;
   if ((rc = mg_spmv_p<3>(h, m.p_rowptr, m.p_col, m.P, m.P32, m.n_f, xc, x, nullptr, st,
@@ -1384,7 +1410,7 @@ static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, boo
     }
   } else {
     if ((rc = mgd_exchange(h, l, x, st))) return rc;
-    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;
     if (n > 0) {
       mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, 0.0, 1.0 / theta, 0);
       CKL("mg_cheb_kernel<1>");
@@ -1392,7 +1418,7 @@ static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, boo
   }
   for (int k = 1; k < deg; ++k) {
     if ((rc = mgd_exchange(h, l, x, st))) return rc;
-    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     if (n > 0) {
       mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, rho_new * rho, 2.0 * rho_new / delta, 0);
@@ -1419,7 +1445,7 @@ static int mg_vcycle_dist(jsso_handle* h, int l, double* b, double* x, int deg, 
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
   if ((rc = mg_smooth_dist(h, l, b, x, true, deg, st))) return rc;
   if ((rc = mgd_exchange(h, l, x, st))) return rc;
-  if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st))) return rc;        // r = b - A x
+  if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;        // r = b - A x
   if ((rc = mgd_exchange(h, l, m.r, st))) return rc;
   if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st))) return rc;   // b_c = P^T r
   if (l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; }

@@ -7,6 +7,7 @@
 // (left slot, right slot) lists: no atomics, fixed summation order.  Blocks are column-major
 // (entry (i,j) at 6 j + i) like the stiffness values.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -351,6 +352,14 @@ __global__ void mg_to_float_kernel(long long n, const double* __restrict__ a, fl
     const long long s = o / 36;
     const int k = (int)(o - 36 * s), sub = k / 12, rem = k - 12 * sub, j = rem >> 1, r = rem & 1;
     b[o] = (float)a[36 * s + 6 * j + 2 * sub + r];
+  }
+}
+// the same layout in binary16 (fine level only: the block-Jacobi-scaled matrix has |entries| <= 1)
+__global__ void mg_to_half_kernel(long long n, const double* __restrict__ a, __half* __restrict__ b) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+    const long long s = o / 36;
+    const int k = (int)(o - 36 * s), sub = k / 12, rem = k - 12 * sub, j = rem >> 1, r = rem & 1;
+    b[o] = __double2half(a[36 * s + 6 * j + 2 * sub + r]);
   }
 }
 // deterministic pseudo-random start vector in (-1, 1) (integer hash of the index): a constant vector

@@ -14,6 +14,19 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box via gpurun)')
+    config.addinivalue_line('markers', 'unverified: GPU path written after the round\'s GPU budget was spent; it '
+                                       'compiles but has not run on hardware yet (JSSO_RUN_UNVERIFIED=1 runs it)')
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests of GPU code that has never run on hardware are opt-in, so that a first failure there cannot
+    mask the verified parity tests under `-x`; they run with JSSO_RUN_UNVERIFIED=1."""
+    if os.environ.get('JSSO_RUN_UNVERIFIED', '0') == '1':
+        return
+    skip = pytest.mark.skip(reason='not yet run on hardware; set JSSO_RUN_UNVERIFIED=1')
+    for it in items:
+        if 'unverified' in it.keywords:
+            it.add_marker(skip)
 
 
 @pytest.fixture(scope='session')
