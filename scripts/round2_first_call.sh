@@ -1,0 +1,31 @@
+#!/bin/bash
+# First GPU call of round 2 (needs >= 2 GPUs for the distributed part; on 1 GPU those tests skip):
+#   gpurun --gpus 2 --timeout 1500 -- bash scripts/round2_first_call.sh
+# 1. the verified GPU tests (must stay green), 2. the tests of code written after round 1's GPU budget
+# (row-range distributed multigrid, binary16 fine level), 3. bench lines with / without the new switches.
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -q -m gpu -x > gpurun_out/r2_tests_verified.log 2>&1
+echo "verified tests rc=$?"
+JSSO_RUN_UNVERIFIED=1 timeout 1200 python -m pytest tests -q -m gpu -k "fp16 or distributed_multigrid" > gpurun_out/r2_tests_unverified.log 2>&1
+echo "unverified tests rc=$?"
+tail -5 gpurun_out/r2_tests_verified.log gpurun_out/r2_tests_unverified.log
+python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1.json 2> gpurun_out/r2_b1.err
+JSSO_MG_FP16=1 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1_fp16.json 2> gpurun_out/r2_b1_fp16.err
+python - <<'PY'
+import json
+for f in ('gpurun_out/r2_b1.json', 'gpurun_out/r2_b1_fp16.json'):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, d['ms_per_step'], d['grad_eval'])
+    except Exception as e:
+        print(f, 'failed', e)
+PY
+NG=$(python -c "from jaxsso_b200 import _native as n; print(n.lib().jsso_device_count())")
+if [ "$NG" -ge 2 ]; then
+  for extra in "" "--dist-mg"; do
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 \
+      bench.py --gpus 2 --steps 10 $extra > "gpurun_out/r2_b2${extra}.json" 2> "gpurun_out/r2_b2${extra}.err"
+    tail -c 1500 "gpurun_out/r2_b2${extra}.json"
+  done
+fi
