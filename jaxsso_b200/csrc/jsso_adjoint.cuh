@@ -51,6 +51,13 @@ __device__ inline double quad4_sum(double v) {
   return v;
 }
 
+#ifdef JSSO_EMU   // CPU test harness: synchronous copies
+__device__ inline void adj_cp8(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 8); }
+__device__ inline void adj_cp16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ inline void adj_cp_commit() {}
+__device__ inline void adj_cp_wait_1() {}
+__device__ inline void adj_cp_wait_all() {}
+#else
 __device__ inline void adj_cp8(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -59,6 +66,10 @@ __device__ inline void adj_cp16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ inline void adj_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ inline void adj_cp_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ inline void adj_cp_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
 // lane (quad, q) copies node q's coordinates, u and lam rows into the quad's stage record
 __device__ inline void adj_stage(double* rec, int q, int nd, int e, const double* __restrict__ crds,
                                  const double* __restrict__ prop, const double* __restrict__ u,
@@ -72,7 +83,7 @@ __device__ inline void adj_stage(double* rec, int q, int nd, int e, const double
     adj_cp16(rec + A_UG + 6 * q + 2 * j, u + 6 * (size_t)nd + 2 * j);
     adj_cp16(rec + A_LG + 6 * q + 2 * j, lam + 6 * (size_t)nd + 2 * j);
   }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  adj_cp_commit();
 }
 
 // Persistent CTAs: batch b, b + gridDim.x, ... of 32 quads.  The gather of the NEXT batch (node ids one
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(4 * ADJ_QUADS, JSSO_ADJ_MINB)
 quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                     const double* __restrict__ prop, const double* __restrict__ u,
                     const double* __restrict__ lam, double* __restrict__ corner, double* __restrict__ d_prop) {
-  extern __shared__ __align__(16) double adj_sm[];
+  JSSO_DYN_SMEM(adj_sm);
   double* const sv = adj_sm + 2 * ADJ_QUADS * ADJ_ST;
   const int le = threadIdx.x >> 2, q = threadIdx.x & 3;
   const int n_batch = (n_quad + ADJ_QUADS - 1) / ADJ_QUADS;
@@ -102,8 +113,8 @@ quad_adjoint_kernel(int n_quad, const double* __restrict__ crds, const int32_t* 
   if (has_next)
     adj_stage(adj_sm + ((it + 1) & 1) * (ADJ_QUADS * ADJ_ST) + le * ADJ_ST, q, nd_next, min((batch + G) * ADJ_QUADS + le, n_quad - 1), crds, prop, u, lam);
   if (batch + 2 * G < n_batch) nd_next = cnct[4 * min((batch + 2 * G) * ADJ_QUADS + le, n_quad - 1) + q];
-  if (has_next) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-  else asm volatile("cp.async.wait_all;\n" ::: "memory");
+  if (has_next) adj_cp_wait_1();
+  else adj_cp_wait_all();
   __syncwarp();
   int e = batch * ADJ_QUADS + le;
   const bool valid = e < n_quad;

@@ -348,7 +348,7 @@ struct AsmArgs {
 // contributor count (blk_perm), so the lanes of a warp loop the same number of times.
 __global__ void __launch_bounds__(kChunkBlocks, 4)
 assemble_fused_kernel(AsmArgs A) {
-  extern __shared__ __align__(16) double sm[];
+  JSSO_DYN_SMEM(sm);
   const int c = blockIdx.x;
   const int blk0 = A.chunk_blk[c], blk1 = A.chunk_blk[c + 1];
   const int el0 = A.chunk_el_ptr[c], n_el = A.chunk_el_ptr[c + 1] - el0;
@@ -445,7 +445,7 @@ constexpr int G_QUADS = JSSO_G_QUADS, G_THREADS = JSSO_G_THREADS;
 __global__ void __launch_bounds__(G_THREADS)
 quad_geometry_kernel(int n_quad, const double* __restrict__ crds, const int32_t* __restrict__ cnct,
                      const double* __restrict__ prop, double* __restrict__ rec, int* flags) {
-  extern __shared__ __align__(16) double sm[];   // G_QUADS * QS doubles
+  JSSO_DYN_SMEM(sm);   // G_QUADS * QS doubles
   const int first = blockIdx.x * G_QUADS;
   const int n_el = min(G_QUADS, n_quad - first);
   stage_quad_geometry(sm, n_el, nullptr, first, crds, cnct, prop, flags);
@@ -473,6 +473,12 @@ struct TaskArgs {
   double* vals; int* flags; int n_quad; int n_task; int apply_bc;
 };
 
+#ifdef JSSO_EMU   // CPU test harness: a synchronous copy (a missing wait is not detected there)
+__device__ inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ inline void prefetch_l2(const void*) {}
+__device__ inline void cp_async_commit() {}
+__device__ inline void cp_async_wait_all() {}
+#else
 __device__ inline void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -480,6 +486,7 @@ __device__ inline void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ inline void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
 
 // per-lane data of one task that is loaded ahead of time (registers)
 struct TaskRegs {
@@ -517,7 +524,7 @@ __device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, 
 // phase of task k, so no global-load latency is exposed after the prologue.
 __global__ void __launch_bounds__(32 * TASK_WARPS, 16 / TASK_WARPS)
 assemble_tasks_kernel(TaskArgs A) {
-  extern __shared__ __align__(16) double sm[];
+  JSSO_DYN_SMEM(sm);
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int stride = gridDim.x * TASK_WARPS;

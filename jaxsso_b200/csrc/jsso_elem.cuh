@@ -22,6 +22,14 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// JSSO_EMU is defined only by the CPU test harness (tests/emu: the kernels compiled by g++ against a SIMT
+// emulator to check their logic without a GPU).  The product build (nvcc) never defines it.
+#ifdef JSSO_EMU
+#define JSSO_DYN_SMEM(name) double* name = (double*)emu::dyn_smem()
+#else
+#define JSSO_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#endif
+
 namespace jsso {
 
 // ------------------------------------------------------------------ duals

@@ -76,6 +76,12 @@ struct P2PCtx {
 // system-scope release store / acquire load (PTX memory model): the release orders every write
 // this thread has performed or observed (through CTA barriers / gpu-scope atomics) before the
 // flag; the acquire makes them visible to the loads that follow the successful poll.
+#ifdef JSSO_EMU   // CPU test harness (single process: the peer-memory kernels are not exercised there)
+__device__ inline void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ inline unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ inline double ld_relaxed_sys_f64(const double* p) { return *(const volatile double*)p; }
+__device__ inline void st_relaxed_sys_f64(double* p, double v) { *(volatile double*)p = v; }
+#else
 __device__ inline void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -89,11 +95,15 @@ __device__ inline double ld_relaxed_sys_f64(const double* p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ inline void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#endif
 
 // called by ONE thread: publish this rank's partial of reduction `seq` on channel ch
 __device__ inline void p2p_publish(const P2PCtx* c, int ch, unsigned long long seq, double v) {
   for (int r = 0; r < c->n_rank; ++r) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&c->mbox[r]->val[ch][c->rank]), "d"(v) : "memory");
+    st_relaxed_sys_f64(&c->mbox[r]->val[ch][c->rank], v);
   }
   for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->tag[ch][c->rank], seq);
 }
