@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, '_build', 'libjsso_emu.so')
-SRC = [os.path.join(HERE, 'emu_kernels.cpp')]
+SRC = [os.path.join(HERE, 'emu_kernels.cpp'), os.path.join(ROOT, 'jaxsso_b200', 'csrc', 'jsso_symbolic.cpp')]
 DEPS = SRC + [os.path.join(HERE, 'cuda_emu.h')] + \
     [os.path.join(ROOT, 'jaxsso_b200', 'csrc', f) for f in os.listdir(os.path.join(ROOT, 'jaxsso_b200', 'csrc'))]
 

@@ -37,7 +37,7 @@
 #define __shared__ static
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 namespace emu {
 
