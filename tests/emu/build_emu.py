@@ -23,6 +23,9 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ['g++', '-std=c++20', '-O1', '-g', '-fPIC', '-shared', '-pthread', '-DJSSO_EMU', '-w',
+           # libjsso.so (loaded RTLD_GLOBAL by other tests) exports host stubs with the SAME mangled kernel names:
+           # keep every reference inside this library
+           '-fvisibility=hidden', '-fvisibility-inlines-hidden', '-Wl,-Bsymbolic',
            '-I' + cuda_include()] + SRC + ['-o', OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

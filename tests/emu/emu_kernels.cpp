@@ -28,6 +28,7 @@ int run_axpby_mode(int mode, int n_row, const int32_t* rp, const int32_t* ci, co
 }
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 // y (op)= A x over n_row rows; vt: 0 double (column-major blocks), 1 float, 2 binary16 (row-pair-major blocks)
@@ -166,3 +167,4 @@ int emu_pattern(int n_node, int n_quad, const int32_t* cq, int n_beam, const int
 }
 
 }  // extern "C"
+#pragma GCC visibility pop
