@@ -4,23 +4,24 @@
 // against the oracle in the CPU test suite, where there is no GPU.  It says nothing about performance and is not a
 // fallback: the product library (libjsso.so) is built by nvcc only and refuses to run without a device.
 //
-// Model: CTAs run one after another; inside a CTA every CUDA thread is a std::thread.  __syncthreads /
-// __syncwarp are std::barrier phases; a warp shuffle is "publish my value, barrier, read the source lane,
-// barrier".  A thread that returns from the kernel drops out of its barriers (arrive_and_drop), like an exited
-// lane.  Limits: full-mask warp primitives only; no inter-CTA waiting (grid.sync only with one CTA; the
+// Model: CTAs run one after another; inside a CTA every CUDA thread is a cooperative fiber.
+// __syncthreads / __syncwarp are barrier phases; a warp shuffle is "publish my value, barrier, read the source
+// lane, barrier".  A thread that returns from the kernel drops out of its barriers, like an exited lane.  Limits: full-mask warp primitives only; no inter-CTA waiting (grid.sync only with one CTA; the
 // peer-memory spin loops are not emulated); cp.async is a synchronous copy, so a missing wait is NOT detected.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -39,101 +40,195 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 
+// stack switch without a system call (swapcontext saves the signal mask with one): callee-saved registers only
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+
 namespace emu {
 
+// ---- cooperative fibers: every CUDA thread of the running CTA is a fiber (own stack, hand-written switch) on the launching OS thread.
+// A barrier is "arrive; if not last, yield until the generation changes"; the scheduler resumes fibers round-robin,
+// warp by warp, so a warp-level barrier completes after one pass over its 32 lanes.  Deterministic, no OS threads,
+// no futexes (an OS-thread version spent milliseconds per CTA waking 256 threads).
+struct Barrier {
+  int expected = 0, arrived = 0;
+  unsigned long long gen = 0;
+};
+struct Fiber;
 struct WarpCtx {
-  std::barrier<> bar;
+  Barrier bar;
   alignas(64) unsigned char slot[32][16];
-  explicit WarpCtx(int n) : bar(n) {}
 };
 struct CtaCtx {
-  std::barrier<> bar;
+  Barrier bar;
   std::vector<unsigned char> dyn;
-  CtaCtx(int n, size_t smem) : bar(n), dyn(smem + 64) {}
 };
-struct Tls {
+struct Fiber {
+  void* sp = nullptr;
   uint3 tid{0, 0, 0}, bid{0, 0, 0};
   dim3 bdim{1, 1, 1}, gdim{1, 1, 1};
   int lane = 0;
   WarpCtx* w = nullptr;
   CtaCtx* c = nullptr;
+  bool done = false;
+  const std::function<void()>* body = nullptr;
 };
-inline thread_local Tls tls;
+struct Sched {
+  void* main_sp = nullptr;
+  std::vector<Fiber> fibers;
+  std::vector<unsigned char*> stacks;
+  Fiber* cur = nullptr;
+};
+inline Sched& sched() { static thread_local Sched s; return s; }
+constexpr size_t kStack = 512 * 1024;
+
+// `tls` is the running fiber (one launch at a time per process: launch_mutex)
+#define EMU_CUR (*emu::sched().cur)
+
+inline void yield() {
+  Sched& S = sched();
+  emu_switch(&S.cur->sp, S.main_sp);
+}
+inline void barrier_wait(Barrier& b) {
+  if (++b.arrived >= b.expected) { b.arrived = 0; ++b.gen; return; }
+  const unsigned long long g = b.gen;
+  while (b.gen == g) yield();
+}
+inline void barrier_drop(Barrier& b) {
+  --b.expected;
+  if (b.expected > 0 && b.arrived >= b.expected) { b.arrived = 0; ++b.gen; }
+}
+inline void fiber_entry() {
+  Fiber& f = *sched().cur;
+  (*f.body)();
+  barrier_drop(f.w->bar);
+  barrier_drop(f.c->bar);
+  f.done = true;
+  emu_switch(&f.sp, sched().main_sp);
+  std::abort();   // a finished fiber is never resumed
+}
 
 inline void* dyn_smem() {
-  uintptr_t p = (uintptr_t)tls.c->dyn.data();
+  uintptr_t p = (uintptr_t)EMU_CUR.c->dyn.data();
   return (void*)((p + 63) & ~(uintptr_t)63);
 }
 
+inline unsigned dimx(unsigned v) { return v; }
+inline unsigned dimx(int v) { return (unsigned)v; }
+inline unsigned dimx(long long v) { return (unsigned)v; }
+inline unsigned dimx(size_t v) { return (unsigned)v; }
+inline unsigned dimx(const dim3& v) { return v.x; }
+// kernels keep `__shared__` data in function-local statics: one emulated launch at a time, process-wide
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+
 // launch(grid, block, dynamic shared bytes, [&] { kernel(args...); })
-template <class F>
-void launch(unsigned grid, unsigned block, size_t smem, F&& body) {
+template <class G, class B, class F>
+void launch(G grid_, B block_, size_t smem, F&& body_) {
+  std::lock_guard<std::mutex> serial(launch_mutex());
+  const unsigned grid = dimx(grid_), block = dimx(block_);
   const unsigned n_warp = (block + 31) / 32;
+  const std::function<void()> body = body_;
+  Sched& S = sched();
+  if (S.fibers.size() < block) S.fibers.resize(block);
+  while (S.stacks.size() < block) S.stacks.push_back((unsigned char*)std::malloc(kStack));
   for (unsigned b = 0; b < grid; ++b) {
-    CtaCtx cta((int)block, smem);
-    std::vector<std::unique_ptr<WarpCtx>> warps;
-    for (unsigned w = 0; w < n_warp; ++w)
-      warps.emplace_back(new WarpCtx((int)std::min(32u, block - 32 * w)));
-    std::vector<std::thread> th;
-    th.reserve(block);
+    CtaCtx cta;
+    cta.bar.expected = (int)block;
+    cta.dyn.resize(smem + 64);
+    std::vector<WarpCtx> warps(n_warp);
+    for (unsigned w = 0; w < n_warp; ++w) warps[w].bar.expected = (int)std::min(32u, block - 32 * w);
     for (unsigned t = 0; t < block; ++t) {
-      th.emplace_back([&, t, b] {
-        tls.tid = uint3{t, 0, 0};
-        tls.bid = uint3{b, 0, 0};
-        tls.bdim = dim3(block, 1, 1);
-        tls.gdim = dim3(grid, 1, 1);
-        tls.lane = (int)(t & 31);
-        tls.w = warps[t >> 5].get();
-        tls.c = &cta;
-        body();
-        tls.w->bar.arrive_and_drop();
-        tls.c->bar.arrive_and_drop();
-      });
+      Fiber& f = S.fibers[t];
+      f.tid = uint3{t, 0, 0}; f.bid = uint3{b, 0, 0};
+      f.bdim = dim3(block, 1, 1); f.gdim = dim3(grid, 1, 1);
+      f.lane = (int)(t & 31); f.w = &warps[t >> 5]; f.c = &cta; f.done = false; f.body = &body;
+      // initial frame: six zeroed callee-saved registers, then the entry address for `ret`; after the ret
+      // rsp = top - 8, the alignment a function sees on entry
+      void** top = (void**)(((uintptr_t)S.stacks[t] + kStack) & ~(uintptr_t)15);
+      void** sp0 = top - 8;
+      for (int k = 0; k < 6; ++k) sp0[k] = nullptr;
+      sp0[6] = (void*)&fiber_entry;
+      sp0[7] = nullptr;
+      f.sp = sp0;
     }
-    for (auto& x : th) x.join();
+    unsigned live = block;
+    while (live > 0) {
+      unsigned progressed = 0;
+      for (unsigned t = 0; t < block; ++t) {
+        Fiber& f = S.fibers[t];
+        if (f.done) continue;
+        S.cur = &f;
+        emu_switch(&S.main_sp, f.sp);
+        if (f.done) { --live; }
+        ++progressed;
+      }
+      if (!progressed) break;
+    }
+    S.cur = nullptr;
   }
 }
 
 template <class T>
 inline T shfl_from(T v, int src) {
   static_assert(sizeof(T) <= 16, "shuffle payload");
-  WarpCtx& w = *tls.w;
-  std::memcpy(w.slot[tls.lane], &v, sizeof(T));
-  w.bar.arrive_and_wait();
+  Fiber& f = EMU_CUR;
+  WarpCtx& w = *f.w;
+  std::memcpy(w.slot[f.lane], &v, sizeof(T));
+  barrier_wait(w.bar);
   T r;
   std::memcpy(&r, w.slot[src], sizeof(T));
-  w.bar.arrive_and_wait();
+  barrier_wait(w.bar);
   return r;
 }
 
 }  // namespace emu
 
-#define threadIdx (emu::tls.tid)
-#define blockIdx (emu::tls.bid)
-#define blockDim (emu::tls.bdim)
-#define gridDim (emu::tls.gdim)
+#define threadIdx (EMU_CUR.tid)
+#define blockIdx (EMU_CUR.bid)
+#define blockDim (EMU_CUR.bdim)
+#define gridDim (EMU_CUR.gdim)
 
-inline void __syncthreads() { emu::tls.c->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::tls.w->bar.arrive_and_wait(); }
+inline void __syncthreads() { emu::barrier_wait(EMU_CUR.c->bar); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_wait(EMU_CUR.w->bar); }
 
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
-  const int lane = emu::tls.lane, base = lane & ~(width - 1);
+  const int lane = EMU_CUR.lane, base = lane & ~(width - 1);
   return emu::shfl_from(v, base + (src & (width - 1)));
 }
 template <class T>
 inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
-  const int lane = emu::tls.lane, base = lane & ~(width - 1), s = lane + (int)d;
+  const int lane = EMU_CUR.lane, base = lane & ~(width - 1), s = lane + (int)d;
   return emu::shfl_from(v, s < base + width ? s : lane);
 }
 template <class T>
 inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
-  const int lane = emu::tls.lane, base = lane & ~(width - 1), s = lane - (int)d;
+  const int lane = EMU_CUR.lane, base = lane & ~(width - 1), s = lane - (int)d;
   return emu::shfl_from(v, s >= base ? s : lane);
 }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
-  const int lane = emu::tls.lane, base = lane & ~(width - 1), s = lane ^ m;
+  const int lane = EMU_CUR.lane, base = lane & ~(width - 1), s = lane ^ m;
   return emu::shfl_from(v, s < base + width ? s : lane);
 }
 
@@ -172,7 +267,7 @@ inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
 namespace cooperative_groups {
 struct grid_group {
   void sync() const {
-    if (emu::tls.gdim.x != 1) { std::fprintf(stderr, "emu: grid.sync() needs a one-CTA grid\n"); std::abort(); }
+    if (EMU_CUR.gdim.x != 1) { std::fprintf(stderr, "emu: grid.sync() needs a one-CTA grid\n"); std::abort(); }
     __syncthreads();
   }
 };

@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE: runs the package's normal Python -> C ABI path against the EMULATED library
+(JSSO_LIB=tests/emu/_build/libjsso_emuapi.so: the product's host driver + kernels compiled by g++ on the SIMT
+emulator).  Launched as a subprocess by tests/test_emu_driver.py; prints one JSON line.
+
+  driver_check.py grad  SIZE                         value + gradient of a mixed quad/beam plate vs the oracle
+  driver_check.py mg    SIZE DEG                     multigrid PCG vs block-Jacobi CG vs the oracle
+  driver_check.py dist  WORLD SIZE MIN_DIST DEG      row-range distributed multigrid solve on WORLD rank THREADS
+                                                     (fake NCCL between them) vs the undistributed solve
+"""
+import json
+import os
+import sys
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from jaxsso_b200 import _native as nat                       # noqa: E402
+from jaxsso_b200 import dist_multigrid as dmg               # noqa: E402
+from jaxsso_b200 import meshes, partition                    # noqa: E402
+from oracle import jaxsso_oracle as orc                      # noqa: E402
+
+assert 'emuapi' in nat.LIB_PATH, 'this script is for the emulated library only'
+D = nat.DeviceArray
+
+
+def omesh(md):
+    return orc.Mesh(md.crds, md.cnct_quads, md.prop_quads, md.cnct_beams, md.prop_beams, md.known, md.loads)
+
+
+def mixed(n):
+    md = meshes.plate(n)
+    nid = np.arange(md.n_node).reshape(n + 1, n + 1)
+    md.cnct_beams = np.stack([nid[n // 2, :-1], nid[n // 2, 1:]], 1).astype(np.int32)
+    md.prop_beams = np.tile([3.79e9, 3.79e9 / 2.6, 6.7e-5, 1.7e-5, 8.4e-5, 0.02], (n, 1))
+    return md
+
+
+def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=8):
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    info, cnt = None, (0, 0)
+    if precond == 'multigrid':
+        levels = h.mg_setup(max_coarse_nodes=max_coarse)
+        if dist is not None:
+            nid, rank, world, bounds, min_dist = dist
+            rp, ci = h.pattern()
+            plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist)
+            h.mg_set_dist(nid, rank, world, plan)
+            info = dmg.plan_summary(plan)
+    crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
+    u = D((md.ndof,))
+    st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond=precond, cheb_degree=deg))
+    out = u.download()
+    if dist is not None:
+        cnt = h.mg_dist_counters()
+    h.close()
+    return out, st.iterations, bool(st.converged), st.relres, info, cnt
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == 'grad':
+        md = mixed(int(sys.argv[2]))
+        h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+        val, u, dc, dq, db, fs, bs = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads,
+                                                           opts=nat.make_opts(rtol=1e-11))
+        rv, ru, rl, rdc, rdq, rdb = orc.value_and_grad(omesh(md))
+        res = {'u_err': float(np.linalg.norm(u - ru) / np.linalg.norm(ru)), 'c_err': float(abs(val - rv) / abs(rv)),
+               'g_err': float(np.abs(dc - rdc).max() / np.abs(rdc).max()),
+               'dq_err': float(np.abs(dq - rdq).max() / np.abs(rdq).max()),
+               'db_err': float(np.abs(db - rdb).max() / np.abs(rdb).max()),
+               'iterations': fs.iterations, 'launches': int(nat.lib().jsso_launch_count())}
+    elif mode == 'mg':
+        md, deg = meshes.plate(int(sys.argv[2])), int(sys.argv[3])
+        um, itm, cm, rm, _, _ = solve(md, 'multigrid', deg)
+        ub, itb, cb, rb, _, _ = solve(md, 'block_jacobi')
+        uref = orc.solve_refined(omesh(md))
+        res = {'mg_err': float(np.linalg.norm(um - uref) / np.linalg.norm(uref)),
+               'bj_err': float(np.linalg.norm(ub - uref) / np.linalg.norm(uref)),
+               'mg_iters': itm, 'bj_iters': itb, 'mg_converged': cm, 'bj_converged': cb, 'fp16': os.environ.get('JSSO_MG_FP16', '0')}
+    elif mode == 'dist':
+        world, size, min_dist, deg = (int(a) for a in sys.argv[2:6])
+        md0 = meshes.plate(size)
+        owner = partition.rcb_owner(md0.crds[:, :2], world)
+        perm, bounds = dmg.owner_permutation(owner, world)
+        md = dmg.renumber_mesh(md0, perm)
+        nid = nat.nccl_unique_id()
+        out = [None] * world
+
+        def worker(rank):
+            out[rank] = solve(md, 'multigrid', deg, dist=(nid, rank, world, bounds, min_dist))
+
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        us, its, cs, rs, _, _ = solve(md, 'multigrid', deg)
+        uref = orc.solve_refined(omesh(md0))
+        res = {'world': world, 'iters_dist': [o[1] for o in out], 'iters_single': its,
+               'converged': all(o[2] for o in out),
+               'err_vs_single': float(max(np.linalg.norm(o[0] - us) for o in out) / np.linalg.norm(us)),
+               'identical_on_all_ranks': all(np.array_equal(o[0], out[0][0]) for o in out),
+               'err_vs_oracle': float(np.linalg.norm(out[0][0].reshape(-1, 6) - uref.reshape(-1, 6)[perm]) / np.linalg.norm(uref)),
+               'plan': out[0][4], 'exchanges': out[0][5][0], 'allreduces': out[0][5][1]}
+    else:
+        raise SystemExit('unknown mode')
+    print('EMU_RESULT ' + json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()

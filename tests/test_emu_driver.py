@@ -1,0 +1,69 @@
+"""The product's HOST DRIVER on the CPU: csrc/jsso_api.cu (handle management, assembly, scaled PCG, multigrid setup
+and V-cycle PCG, the row-range distributed multigrid solve, adjoint) compiled by g++ on the SIMT emulator
+(tests/emu), kernel launches rewritten into emulator launches, CUDA runtime = heap, NCCL = queues between rank
+THREADS.  The package's own Python binding runs against it in a subprocess (JSSO_LIB=...).  This is test
+infrastructure, not a fallback: libjsso.so is untouched and still refuses to run without a GPU
+(tests/test_abi.py).  It verifies LOGIC (indexing, ordering, which exchange is needed where); speed and the
+real memory model are the GPU tests' business."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+
+
+@pytest.fixture(scope='module')
+def emu_api():
+    import build_emu
+    return build_emu.build_api()
+
+
+def run(emu_api, *args, env=None):
+    e = dict(os.environ, JSSO_LIB=emu_api, **(env or {}))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'emu', 'driver_check.py'), *map(str, args)],
+                       capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith('EMU_RESULT ')]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-4000:]
+    return json.loads(line[0].split(' ', 1)[1])
+
+
+def test_value_and_gradient_through_the_emulated_driver(emu_api):
+    """jsso_value_and_grad_host end to end: Ke + assembly (warp tasks), BC, block-Jacobi scaling, 3-kernel CG with
+    device-side stop flag, adjoint kernels, node gather -- against the oracle at the GPU tests' tolerances."""
+    res = run(emu_api, 'grad', 6)
+    assert res['u_err'] <= 1e-8 and res['c_err'] <= 1e-8
+    assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6 and res['db_err'] <= 1e-6
+    assert res['launches'] > 100
+
+
+@pytest.mark.parametrize('fp16', ['0', '1'])
+def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
+    """mg_numeric_setup (power iteration, smoothed prolongator, Galerkin products, dense coarse inverse) + V-cycle
+    PCG; with JSSO_MG_FP16=1 the fine-level V-cycle matrix is stored in binary16 (the path that has not run on
+    hardware yet): same solution, iteration count within 2."""
+    res = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_FP16': fp16})
+    assert res['mg_converged'] and res['bj_converged']
+    assert res['mg_err'] <= 1e-8 and res['bj_err'] <= 1e-8
+    assert res['mg_iters'] < res['bj_iters'] / 2
+    if fp16 == '1':
+        base = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_FP16': '0'})
+        assert abs(res['mg_iters'] - base['mg_iters']) <= 2
+
+
+@pytest.mark.parametrize('world,size,min_dist,deg', [(2, 12, 10, 1), (2, 12, 1000, 2), (4, 16, 10, 2)])
+def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size, min_dist, deg):
+    """jsso_mg_set_dist + mg_solve_dist (the REAL C++ driver, not its Python replay) on `world` rank threads with
+    the fake NCCL: same iteration count as the undistributed solve, bitwise identical u on every rank, u equal to
+    the undistributed solve to rounding and to the oracle within 1e-8.  min_dist 10 distributes two levels (with an
+    EMPTY row range on some ranks at the first replicated level), 1000 only the fine one."""
+    res = run(emu_api, 'dist', world, size, min_dist, deg)
+    assert res['converged'] and res['identical_on_all_ranks']
+    assert all(abs(i - res['iters_single']) <= 1 for i in res['iters_dist'])
+    assert res['err_vs_single'] <= 1e-10 and res['err_vs_oracle'] <= 1e-8
+    assert res['plan']['n_dist'] == (2 if min_dist == 10 else 1)
+    assert res['exchanges'] > 0 and res['allreduces'] >= 3 * res['iters_single']
