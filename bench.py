@@ -459,82 +459,145 @@ def run_b200(args):
         else:
             grad_eval = {'error': ok, 'seconds': dt}
 
+    def build_out():
+        hbm, peak_src = peaks()
+        s = h.sizes
+        # measured DRAM traffic per launch of the committed ncu capture of this exact workload (profiles/)
+        ncu = {}
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic_1024.json')) as f:
+                ncu = json.load(f) if (world == 1 and N == 1024) else {}
+        except Exception:
+            ncu = {}
+        # dominant kernel: assemble_tasks_kernel.  Algorithmic bytes of that launch: every geometry record read
+        # once (496 B per quad), task/item descriptors, every stored block written once
+        REC_BYTES = 496
+        tasks_bytes = s.n_quad * REC_BYTES + s.n_items * 2 + s.nnzb * (288 + 6)
+        if ms_tasks > 0:
+            roof = {'kernel': 'assemble_tasks_kernel', 'bound': 'hbm', 'achieved': tasks_bytes / (ms_tasks * 1e-3) / 1e9,
+                    'peak': hbm, 'unit': 'GB/s', 'frac': tasks_bytes / (ms_tasks * 1e-3) / 1e9 / hbm,
+                    'traffic': ncu.get('assemble_tasks_kernel'), 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': tasks_bytes, 'ms': ms_tasks,
+                    'note': 'second bound: LSU data-pipe wavefronts (shared memory), see profiles/'}
+        else:   # chunked single-kernel path (meshes the warp tasks cannot hold, or JSSO_ASM_CHUNKED=1)
+            b_ = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
+            roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': b_ / (ms_asm * 1e-3) / 1e9,
+                    'peak': hbm, 'unit': 'GB/s', 'frac': b_ / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
+                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_, 'ms': ms_asm}
+        # the whole assembly stage (quad_geometry_kernel + assemble_tasks_kernel) against SURVEY 8(d)'s
+        # algorithmic bytes of a fused Ke+assembly: connectivity + properties + coordinates read once, every
+        # stored block written once (the geometry records are overhead traffic of the two-kernel design)
+        asm_bytes = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
+        tr = [ncu.get('quad_geometry_kernel'), ncu.get('assemble_tasks_kernel')]
+        roof_asm = {'kernel': 'quad_geometry_kernel + assemble_tasks_kernel', 'bound': 'hbm',
+                    'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                    'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm,
+                    'traffic': (tr[0] + tr[1]) if all(t is not None for t in tr) else None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm, 'ms_geometry': ms_geo, 'ms_tasks': ms_tasks}
+        spmv_bytes = s.nnzb * 292 + s.n_row * 100
+        roof_spmv = {'kernel': 'bsr_spmv_kernel', 'bound': 'hbm', 'achieved': spmv_bytes / (ms_spmv * 1e-3) / 1e9,
+                     'peak': hbm, 'unit': 'GB/s', 'frac': spmv_bytes / (ms_spmv * 1e-3) / 1e9 / hbm,
+                     'traffic': ncu.get('bsr_spmv_kernel'),
+                     'algorithmic_bytes_per_launch': spmv_bytes, 'ms': ms_spmv, 'peak_source': peak_src}
+        adj_flops = 14000.0 * s.n_quad
+        roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
+                    'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
+                    'peak_source': 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)', 'ms': ms_adj,
+                    'traffic': ncu.get('quad_adjoint_kernel'),
+                    'algorithmic_flops_per_launch': adj_flops}
+        value = n_quad_total / (ms_step * 1e-3)
+        out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+               'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+               'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+               'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
+                                      f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
+                                      f'{6 * gmd.n_node} dof; step = Ke+assembly (geometry records + warp tasks) + adjoint reduction',
+                          'parallelism': (f'rcb{world}+' + ('p2p' if args.p2p else 'nccl')) if world > 1 else 'single',
+                          'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
+                          'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
+               'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                       'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
+               'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_assembly': roof_asm,
+               'roofline_adjoint': roof_adj,
+               'roofline_spmv': roof_spmv,
+               'kernel_ms': {'assembly': ms_asm, 'quad_geometry': ms_geo, 'assemble_tasks': ms_tasks, 'adjoint': ms_adj,
+                             'spmv': ms_spmv}, 'setup_s': t_setup,
+               'grad_eval': grad_eval}
+        if world == 1 and args.cpu_baseline:
+            cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                   '--ref-size', str(args.ref_size), '--ref-serial', '--ref-grad']
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                out['cpu_baseline'] = ref['cpu_baseline']
+            except Exception as e:  # the baseline is a report, never a reason to lose the bench line
+                out['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': f'failed: {e}'}
+        return out
+
+    out = build_out() if rank == 0 else None
+
+    # N > 1, extra leg: the same gradient evaluation with the V-cycle PCG DISTRIBUTED by row ranges
+    # (jsso_mg_set_dist).  That path was written after round 1's GPU budget was spent: its logic is verified on the
+    # CPU (emulated driver, rank threads), it had not run on hardware when this was committed.  So it runs LAST,
+    # after the bench line is complete, under a watchdog: if it hangs, rank 0 prints the line without it and every
+    # rank exits; its u is compared with the replicated solve of the same run.
+    if world > 1 and hg is not None and not args.dist_mg and args.dist_leg and grad_eval and 'error' not in grad_eval:
+        import threading
+
+        def on_timeout():
+            if rank == 0:
+                out['grad_eval_dist'] = {'error': f'timeout after {args.dist_leg_timeout} s (watchdog)'}
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+
+        wd = threading.Timer(args.dist_leg_timeout, on_timeout)
+        wd.daemon = True
+        wd.start()
+        try:
+            from jaxsso_b200 import dist_multigrid as dmg
+            t_s = time.perf_counter()
+            perm, bounds = dmg.owner_permutation(owner, world)
+            rmd = dmg.renumber_mesh(gmd, perm)
+            inv_perm = np.empty(gmd.n_node, np.int64)
+            inv_perm[perm] = np.arange(gmd.n_node)
+            hd = nat.Handle(rmd.n_node, rmd.cnct_quads, rmd.cnct_beams, rmd.known, device=local_rank)
+            levels = hd.mg_setup()
+            rp_, ci_ = hd.pattern()
+            plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=args.min_dist_nodes)
+            del levels
+            idb = [nat.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(idb, src=0)
+            hd.mg_set_dist(idb[0], rank, world, plan)
+            rc_d, rq_d, rb_d = D.from_host(rmd.crds), D.from_host(rmd.prop_quads), D.from_host(rmd.prop_beams)
+            rf_d, ru_d = D.from_host(rmd.loads), D((rmd.ndof,))
+            rl2g_d = D.from_host(inv_perm[lm.l2g].astype(np.int32))
+            u_rep = uu_d.download()                      # local part of the replicated solve
+            t_s = time.perf_counter() - t_s
+            barrier()
+            t0 = time.perf_counter()
+            fsd = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
+            nat.gather_rows(ru_d, rl2g_d, 6, out=uu_d)
+            h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=opts)
+            L.jsso_stream_sync(None)
+            dtd = max_over_ranks(time.perf_counter() - t0)
+            u_dst = uu_d.download()
+            diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
+            ex, ar = hd.mg_dist_counters()
+            leg = {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
+                   'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
+                   'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
+                   'setup_s': t_s, 'plan': dmg.plan_summary(plan),
+                   'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
+                            'multigrid setup), adjoint partitioned'}
+        except Exception as e:   # an error on one rank only would leave the others in a collective: the watchdog ends them
+            leg = {'error': f'{type(e).__name__}: {e}'}
+        wd.cancel()
+        if rank == 0:
+            out['grad_eval_dist'] = leg
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
-    hbm, peak_src = peaks()
-    s = h.sizes
-    # measured DRAM traffic per launch of the committed ncu capture of this exact workload (profiles/)
-    ncu = {}
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic_1024.json')) as f:
-            ncu = json.load(f) if (world == 1 and N == 1024) else {}
-    except Exception:
-        ncu = {}
-    # dominant kernel: assemble_tasks_kernel.  Algorithmic bytes of that launch: every geometry record read
-    # once (496 B per quad), task/item descriptors, every stored block written once
-    REC_BYTES = 496
-    tasks_bytes = s.n_quad * REC_BYTES + s.n_items * 2 + s.nnzb * (288 + 6)
-    if ms_tasks > 0:
-        roof = {'kernel': 'assemble_tasks_kernel', 'bound': 'hbm', 'achieved': tasks_bytes / (ms_tasks * 1e-3) / 1e9,
-                'peak': hbm, 'unit': 'GB/s', 'frac': tasks_bytes / (ms_tasks * 1e-3) / 1e9 / hbm,
-                'traffic': ncu.get('assemble_tasks_kernel'), 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': tasks_bytes, 'ms': ms_tasks,
-                'note': 'second bound: LSU data-pipe wavefronts (shared memory), see profiles/'}
-    else:   # chunked single-kernel path (meshes the warp tasks cannot hold, or JSSO_ASM_CHUNKED=1)
-        b_ = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
-        roof = {'kernel': 'assemble_fused_kernel', 'bound': 'hbm', 'achieved': b_ / (ms_asm * 1e-3) / 1e9,
-                'peak': hbm, 'unit': 'GB/s', 'frac': b_ / (ms_asm * 1e-3) / 1e9 / hbm, 'traffic': None,
-                'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_, 'ms': ms_asm}
-    # the whole assembly stage (quad_geometry_kernel + assemble_tasks_kernel) against SURVEY 8(d)'s
-    # algorithmic bytes of a fused Ke+assembly: connectivity + properties + coordinates read once, every
-    # stored block written once (the geometry records are overhead traffic of the two-kernel design)
-    asm_bytes = s.n_quad * (16 + 40) + s.n_node * 24 + s.nnzb * 288
-    tr = [ncu.get('quad_geometry_kernel'), ncu.get('assemble_tasks_kernel')]
-    roof_asm = {'kernel': 'quad_geometry_kernel + assemble_tasks_kernel', 'bound': 'hbm',
-                'achieved': asm_bytes / (ms_asm * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
-                'frac': asm_bytes / (ms_asm * 1e-3) / 1e9 / hbm,
-                'traffic': (tr[0] + tr[1]) if all(t is not None for t in tr) else None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': asm_bytes, 'ms': ms_asm, 'ms_geometry': ms_geo, 'ms_tasks': ms_tasks}
-    spmv_bytes = s.nnzb * 292 + s.n_row * 100
-    roof_spmv = {'kernel': 'bsr_spmv_kernel', 'bound': 'hbm', 'achieved': spmv_bytes / (ms_spmv * 1e-3) / 1e9,
-                 'peak': hbm, 'unit': 'GB/s', 'frac': spmv_bytes / (ms_spmv * 1e-3) / 1e9 / hbm,
-                 'traffic': ncu.get('bsr_spmv_kernel'),
-                 'algorithmic_bytes_per_launch': spmv_bytes, 'ms': ms_spmv, 'peak_source': peak_src}
-    adj_flops = 14000.0 * s.n_quad
-    roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
-                'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
-                'peak_source': 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)', 'ms': ms_adj,
-                'traffic': ncu.get('quad_adjoint_kernel'),
-                'algorithmic_flops_per_launch': adj_flops}
-    value = n_quad_total / (ms_step * 1e-3)
-    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-           'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
-           'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
-                                  f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
-                                  f'{6 * gmd.n_node} dof; step = Ke+assembly (geometry records + warp tasks) + adjoint reduction',
-                      'parallelism': (f'rcb{world}+' + ('p2p' if args.p2p else 'nccl')) if world > 1 else 'single',
-                      'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
-                      'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
-           'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                   'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
-           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_assembly': roof_asm,
-           'roofline_adjoint': roof_adj,
-           'roofline_spmv': roof_spmv,
-           'kernel_ms': {'assembly': ms_asm, 'quad_geometry': ms_geo, 'assemble_tasks': ms_tasks, 'adjoint': ms_adj,
-                         'spmv': ms_spmv}, 'setup_s': t_setup,
-           'grad_eval': grad_eval}
-    if world == 1 and args.cpu_baseline:
-        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
-               '--ref-size', str(args.ref_size), '--ref-serial', '--ref-grad']
-        try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-            ref = json.loads(r.stdout.strip().splitlines()[-1])
-            out['cpu_baseline'] = ref['cpu_baseline']
-        except Exception as e:  # the baseline is a report, never a reason to lose the bench line
-            out['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': f'failed: {e}'}
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
@@ -554,6 +617,9 @@ def main():
     ap.add_argument('--dist-mg', action='store_true',
                     help='N > 1: distribute the multigrid V-cycle PCG by row ranges (jsso_mg_set_dist) instead of '
                          'solving redundantly on every rank')
+    ap.add_argument('--no-dist-leg', dest='dist_leg', action='store_false',
+                    help='N > 1: skip the extra distributed-multigrid gradient evaluation at the end')
+    ap.add_argument('--dist-leg-timeout', type=float, default=150.0, help='watchdog of that leg, seconds')
     ap.add_argument('--min-dist-nodes', type=int, default=20000,
                     help='multigrid levels with fewer nodes run replicated under --dist-mg')
     ap.add_argument('--rtol', type=float, default=1e-8)

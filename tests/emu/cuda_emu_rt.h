@@ -9,6 +9,7 @@
 
 #include <nccl.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -41,11 +42,12 @@ inline cudaError_t StreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t StreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t StreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t StreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
-inline cudaError_t EventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline cudaError_t EventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::calloc(1, 8); return cudaSuccess; }
 inline cudaError_t EventCreateWithFlags(cudaEvent_t* e, unsigned) { return EventCreate(e); }
-inline cudaError_t EventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t EventRecord(cudaEvent_t e, cudaStream_t = nullptr) { *(double*)e = now_ms(); return cudaSuccess; }   // launches are synchronous
 inline cudaError_t EventSynchronize(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t EventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+inline cudaError_t EventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(*(double*)b - *(double*)a); return cudaSuccess; }
 inline cudaError_t EventDestroy(cudaEvent_t e) { std::free((void*)e); return cudaSuccess; }
 inline cudaError_t GetLastError() { return cudaSuccess; }
 inline const char* GetErrorString(cudaError_t) { return "emulated CUDA runtime"; }
