@@ -64,6 +64,13 @@ emu_switch:
 .size emu_switch,.-emu_switch
 )");
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define EMU_ASAN 1
+#else
+#define EMU_ASAN 0
+#endif
+
 namespace emu {
 
 // ---- cooperative fibers: every CUDA thread of the running CTA is a fiber (own stack, hand-written switch) on the launching OS thread.
@@ -81,10 +88,11 @@ struct WarpCtx {
 };
 struct CtaCtx {
   Barrier bar;
-  std::vector<unsigned char> dyn;
+  unsigned char* dyn = nullptr;   // dynamic shared memory of the running CTA (buffer owned by the scheduler)
 };
 struct Fiber {
   void* sp = nullptr;
+  void* stack_lo = nullptr;   // AddressSanitizer needs the bounds of the stack it switches to
   uint3 tid{0, 0, 0}, bid{0, 0, 0};
   dim3 bdim{1, 1, 1}, gdim{1, 1, 1};
   int lane = 0;
@@ -95,8 +103,11 @@ struct Fiber {
 };
 struct Sched {
   void* main_sp = nullptr;
+  const void* main_lo = nullptr; size_t main_size = 0;
   std::vector<Fiber> fibers;
   std::vector<unsigned char*> stacks;
+  std::vector<unsigned char> dyn;   // reused by every CTA; refilled with 0xFF (NaN doubles) so that a read of
+                                    // shared memory nobody wrote shows up in the results
   Fiber* cur = nullptr;
 };
 inline Sched& sched() { static thread_local Sched s; return s; }
@@ -107,7 +118,14 @@ constexpr size_t kStack = 512 * 1024;
 
 inline void yield() {
   Sched& S = sched();
+#if EMU_ASAN
+  void* fake = nullptr;
+  __sanitizer_start_switch_fiber(&fake, S.main_lo, S.main_size);
+#endif
   emu_switch(&S.cur->sp, S.main_sp);
+#if EMU_ASAN
+  __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
 }
 inline void barrier_wait(Barrier& b) {
   if (++b.arrived >= b.expected) { b.arrived = 0; ++b.gen; return; }
@@ -119,17 +137,23 @@ inline void barrier_drop(Barrier& b) {
   if (b.expected > 0 && b.arrived >= b.expected) { b.arrived = 0; ++b.gen; }
 }
 inline void fiber_entry() {
+#if EMU_ASAN
+  __sanitizer_finish_switch_fiber(nullptr, &sched().main_lo, &sched().main_size);
+#endif
   Fiber& f = *sched().cur;
   (*f.body)();
   barrier_drop(f.w->bar);
   barrier_drop(f.c->bar);
   f.done = true;
+#if EMU_ASAN
+  __sanitizer_start_switch_fiber(nullptr, sched().main_lo, sched().main_size);   // this fiber never comes back
+#endif
   emu_switch(&f.sp, sched().main_sp);
   std::abort();   // a finished fiber is never resumed
 }
 
 inline void* dyn_smem() {
-  uintptr_t p = (uintptr_t)EMU_CUR.c->dyn.data();
+  uintptr_t p = (uintptr_t)EMU_CUR.c->dyn;
   return (void*)((p + 63) & ~(uintptr_t)63);
 }
 
@@ -154,7 +178,9 @@ void launch(G grid_, B block_, size_t smem, F&& body_) {
   for (unsigned b = 0; b < grid; ++b) {
     CtaCtx cta;
     cta.bar.expected = (int)block;
-    cta.dyn.resize(smem + 64);
+    if (S.dyn.size() < smem + 64) S.dyn.resize(smem + 64);
+    std::memset(S.dyn.data(), 0xFF, smem + 64);
+    cta.dyn = S.dyn.data();
     std::vector<WarpCtx> warps(n_warp);
     for (unsigned w = 0; w < n_warp; ++w) warps[w].bar.expected = (int)std::min(32u, block - 32 * w);
     for (unsigned t = 0; t < block; ++t) {
@@ -170,6 +196,7 @@ void launch(G grid_, B block_, size_t smem, F&& body_) {
       sp0[6] = (void*)&fiber_entry;
       sp0[7] = nullptr;
       f.sp = sp0;
+      f.stack_lo = S.stacks[t];
     }
     unsigned live = block;
     while (live > 0) {
@@ -178,7 +205,14 @@ void launch(G grid_, B block_, size_t smem, F&& body_) {
         Fiber& f = S.fibers[t];
         if (f.done) continue;
         S.cur = &f;
+#if EMU_ASAN
+        void* fake = nullptr;
+        __sanitizer_start_switch_fiber(&fake, f.stack_lo, kStack);
+#endif
         emu_switch(&S.main_sp, f.sp);
+#if EMU_ASAN
+        __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
         if (f.done) { --live; }
         ++progressed;
       }

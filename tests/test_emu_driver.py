@@ -67,3 +67,29 @@ def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size,
     assert res['err_vs_single'] <= 1e-10 and res['err_vs_oracle'] <= 1e-8
     assert res['plan']['n_dist'] == (2 if min_dist == 10 else 1)
     assert res['exchanges'] > 0 and res['allreduces'] >= 3 * res['iters_single']
+
+
+@pytest.mark.parametrize('args,env', [(('grad', 4), {}), (('dist', 2, 8, 10, 1), {'JSSO_MG_FP16': '1'})])
+def test_memcheck_under_address_sanitizer(args, env):
+    """The emulated driver built with -fsanitize=address: every "device" buffer is a heap block, so an out-of-bounds
+    access of a kernel (or of the host driver) aborts with a report naming the .cuh line -- compute-sanitizer
+    memcheck for a box without a GPU.  Runs the gradient flow and the distributed multigrid solve with the binary16
+    fine level (small meshes: the sanitizer costs 3-5x); a negative control (a gather index one row past the end)
+    must be reported."""
+    import build_emu
+    rt = build_emu.asan_runtime()
+    if rt is None:
+        pytest.skip('libasan not available')
+    lib = build_emu.build_api(asan=True)
+    e = dict(os.environ, JSSO_LIB=lib, LD_PRELOAD=rt, ASAN_OPTIONS='detect_leaks=0:halt_on_error=1', **env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'emu', 'driver_check.py'), *map(str, args)],
+                       capture_output=True, text=True, timeout=1200, env=e, cwd=ROOT)
+    assert r.returncode == 0 and 'AddressSanitizer' not in r.stderr, r.stderr[-4000:]
+    assert 'EMU_RESULT ' in r.stdout
+    if args[0] == 'grad':
+        neg = ("import sys; sys.path.insert(0, %r)\n"
+               "import numpy as np\nfrom jaxsso_b200 import _native as nat\n"
+               "s = nat.DeviceArray.from_host(np.arange(60.0)); i = nat.DeviceArray.from_host(np.array([0, 10], np.int32))\n"
+               "nat.gather_rows(s, i, 6)\n" % ROOT)
+        r2 = subprocess.run([sys.executable, '-c', neg], capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
+        assert r2.returncode != 0 and 'heap-buffer-overflow' in r2.stderr and 'gather_rows_kernel' in r2.stderr
