@@ -176,6 +176,13 @@ struct jsso_handle {
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
   cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
   cudaEvent_t ev_b = nullptr;
+  // opt-in chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K > 1): u / lam arrive in K node
+  // ranges, the quad adjoint runs in K quad ranges as soon as the rows a range reads have arrived, and every
+  // range's d_prop_q goes back to the host while the next range is differentiated
+  int e2e_chunks = 1;
+  cudaStream_t st_c = nullptr;
+  std::vector<cudaEvent_t> ev_up, ev_adj;
+  std::vector<int> e2e_qb, e2e_nb, e2e_wait;   // quad bounds, node bounds, upload range each quad range waits for
   // device scratch of the host-buffer entry point
   double *s_crds = nullptr, *s_pq = nullptr, *s_pb = nullptr, *s_f = nullptr, *s_u = nullptr;
   double *s_dc = nullptr, *s_dpq = nullptr, *s_dpb = nullptr;
@@ -388,6 +395,9 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_a) cudaStreamDestroy(h->st_a);
   if (h->st_b) cudaStreamDestroy(h->st_b);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->st_c) cudaStreamDestroy(h->st_c);
+  for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_adj) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
@@ -1596,6 +1606,23 @@ int jsso_pcg(jsso_handle* h, const double* b, double* x, const jsso_solve_opts* 
 }
 
 // ---------------------------------------------------------------- adjoint
+// quad adjoint of the quad range [q0, q0 + nq): per-corner partials into corner_q (want_corner), d_prop_q rows of the range
+static int adjoint_quad_range(jsso_handle* h, int q0, int nq, const double* crds, const double* prop_q, const double* u,
+                              const double* lam, bool want_corner, double* d_prop_q, cudaStream_t st) {
+  if (nq <= 0) return JSSO_OK;
+  const int blocks = std::min(cdiv(nq, ADJ_QUADS), d_prop_q ? h->adj_ctas_prop : h->adj_ctas);
+  const int32_t* cq = h->cnct_q + 4 * (size_t)q0;
+  const double* pq = prop_q + 5 * (size_t)q0;
+  double* corner = want_corner ? h->corner_q + 12 * (size_t)q0 : nullptr;
+  if (d_prop_q)
+    quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(nq, crds, cq, pq, u, lam, corner,
+                                                               d_prop_q + 5 * (size_t)q0);
+  else
+    quad_adjoint_kernel<false><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(nq, crds, cq, pq, u, lam, corner, nullptr);
+  CKL("quad_adjoint_kernel");
+  return JSSO_OK;
+}
+
 int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, const double* u,
                  const double* lam, double* d_crds, double* d_prop_q, double* d_prop_b, void* stream) {
   if (!h || !u || !lam) return JSSO_ERR_ARG;
@@ -1604,14 +1631,8 @@ int jsso_adjoint(jsso_handle* h, const double* crds, const double* prop_q, const
   cudaStream_t st = (cudaStream_t)stream;
   const Symbolic& S = h->sym;
   if (S.n_quad > 0) {
-    const int blocks = std::min(cdiv(S.n_quad, ADJ_QUADS), d_prop_q ? h->adj_ctas_prop : h->adj_ctas);
-    if (d_prop_q)
-      quad_adjoint_kernel<true><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
-                                                                 d_crds ? h->corner_q : nullptr, d_prop_q);
-    else
-      quad_adjoint_kernel<false><<<blocks, 4 * ADJ_QUADS, ADJ_SMEM_DOUBLES * sizeof(double), st>>>(S.n_quad, crds, h->cnct_q, prop_q, u, lam,
-                                                                  d_crds ? h->corner_q : nullptr, nullptr);
-    CKL("quad_adjoint_kernel");
+    int rc = adjoint_quad_range(h, 0, S.n_quad, crds, prop_q, u, lam, d_crds != nullptr, d_prop_q, st);
+    if (rc) return rc;
   }
   if (S.n_beam > 0) {
     beam_adjoint_kernel<<<cdiv(2LL * S.n_beam, 128), 128, 0, st>>>(S.n_beam, crds, h->cnct_b, prop_b, u, lam,
@@ -1677,6 +1698,35 @@ static int ensure_host_staging(jsso_handle* h) {
   CK(cudaStreamCreateWithFlags(&h->st_a, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->st_b, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+  if (const char* e = std::getenv("JSSO_E2E_CHUNKS")) h->e2e_chunks = std::max(1, std::min(64, std::atoi(e)));
+  if (h->e2e_chunks > 1 && S.n_quad >= h->e2e_chunks && S.n_node >= h->e2e_chunks) {
+    const int K = h->e2e_chunks;
+    CK(cudaStreamCreateWithFlags(&h->st_c, cudaStreamNonBlocking));
+    h->ev_up.assign(K, nullptr); h->ev_adj.assign(K, nullptr);
+    for (int c = 0; c < K; ++c) {
+      CK(cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_adj[c], cudaEventDisableTiming));
+    }
+    h->e2e_qb.resize(K + 1); h->e2e_nb.resize(K + 1); h->e2e_wait.resize(K);
+    for (int c = 0; c <= K; ++c) {
+      h->e2e_qb[c] = (int)((long long)S.n_quad * c / K);
+      h->e2e_nb[c] = (int)((long long)S.n_node * c / K);
+    }
+    // a quad range may start once the upload range holding its HIGHEST node has arrived (uploads complete in
+    // order); on a mesh whose element order is unrelated to the node order every range waits for the last one
+    // and the pipeline degenerates to the unchunked schedule, still correct
+    std::vector<int32_t> cq(4 * (size_t)S.n_quad);
+    CK(cudaMemcpy(cq.data(), h->cnct_q, cq.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < K; ++c) {
+      int hi = 0;
+      for (size_t k = 4 * (size_t)h->e2e_qb[c]; k < 4 * (size_t)h->e2e_qb[c + 1]; ++k) hi = std::max(hi, cq[k]);
+      int w = 0;
+      while (w + 1 < K && hi >= h->e2e_nb[w + 1]) ++w;
+      h->e2e_wait[c] = w;
+    }
+  } else {
+    h->e2e_chunks = 1;
+  }
   return JSSO_OK;
 }
 
@@ -1767,6 +1817,55 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   CK(h2d(h->s_pq, pq_h, h->h_pq, nq, st));
   CK(h2d(h->s_pb, pb_h, h->h_pb, nb, st));
   if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
+  if (h->e2e_chunks > 1) {
+    // chunked pipeline (opt-in, JSSO_E2E_CHUNKS): see the handle fields
+    const int K = h->e2e_chunks;
+    const bool want_dq = dpq_h && nq;
+    if (!pinned(u_h)) { std::memcpy(h->h_f, u_h, nd * sizeof(double)); u_h = h->h_f; }
+    if (!pinned(lam_h)) { std::memcpy(h->h_u, lam_h, nd * sizeof(double)); lam_h = h->h_u; }
+    for (int c = 0; c < K; ++c) {
+      const size_t o = 6 * (size_t)h->e2e_nb[c], cnt = 6 * (size_t)(h->e2e_nb[c + 1] - h->e2e_nb[c]);
+      CK(cudaMemcpyAsync(h->s_f + o, u_h + o, cnt * sizeof(double), cudaMemcpyHostToDevice, st2));
+      CK(cudaMemcpyAsync(h->s_u + o, lam_h + o, cnt * sizeof(double), cudaMemcpyHostToDevice, st2));
+      CK(cudaEventRecord(h->ev_up[c], st2));
+    }
+    const bool p_dq = want_dq && pinned(dpq_h);
+    double* dq_dst = want_dq ? (p_dq ? dpq_h : h->h_dpq) : nullptr;
+    int waited = -1;
+    for (int c = 0; c < K; ++c) {
+      if (h->e2e_wait[c] > waited) { waited = h->e2e_wait[c]; CK(cudaStreamWaitEvent(st, h->ev_up[waited], 0)); }
+      const int q0 = h->e2e_qb[c], nqc = h->e2e_qb[c + 1] - q0;
+      if ((rc = adjoint_quad_range(h, q0, nqc, h->s_crds, h->s_pq, h->s_f, h->s_u, dc_h != nullptr,
+                                   want_dq ? h->s_dpq : nullptr, st))) return rc;
+      if (want_dq) {
+        CK(cudaEventRecord(h->ev_adj[c], st));
+        CK(cudaStreamWaitEvent(h->st_c, h->ev_adj[c], 0));
+        CK(cudaMemcpyAsync(dq_dst + 5 * (size_t)q0, h->s_dpq + 5 * (size_t)q0, 5 * (size_t)nqc * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->st_c));
+      }
+    }
+    if (waited < K - 1) CK(cudaStreamWaitEvent(st, h->ev_up[K - 1], 0));   // beams and the node gather read every row
+    if (S.n_beam > 0) {
+      beam_adjoint_kernel<<<cdiv(2LL * S.n_beam, 128), 128, 0, st>>>(S.n_beam, h->s_crds, h->cnct_b, h->s_pb, h->s_f, h->s_u,
+                                                                    dc_h ? h->corner_b : nullptr,
+                                                                    (dpb_h && nb) ? h->s_dpb : nullptr, h->flags);
+      CKL("beam_adjoint_kernel");
+    }
+    if (dc_h) {
+      node_gather_kernel<<<cdiv(3LL * S.n_node, 256), 256, 0, st>>>(S.n_node, S.n_quad, h->node_inc_ptr, h->node_inc,
+                                                                   h->corner_q, h->corner_b, h->s_dc);
+      CKL("node_gather_kernel");
+    }
+    const bool p_dc = dc_h && pinned(dc_h), p_db = dpb_h && pinned(dpb_h);
+    if (dc_h) CK(cudaMemcpyAsync(p_dc ? dc_h : h->h_dc, h->s_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dpb_h && nb) CK(cudaMemcpyAsync(p_db ? dpb_h : h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(h->st_c));
+    if (dc_h && !p_dc) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
+    if (want_dq && !p_dq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+    if (dpb_h && nb && !p_db) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+    return JSSO_OK;
+  }
   CK(h2d(h->s_f, u_h, h->h_f, nd, st2));
   CK(h2d(h->s_u, lam_h, h->h_u, nd, st2));
   CK(cudaEventRecord(h->ev_b, st2));

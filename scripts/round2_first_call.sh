@@ -12,6 +12,10 @@ echo "unverified tests rc=$?"
 tail -5 gpurun_out/r2_tests_verified.log gpurun_out/r2_tests_unverified.log
 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1.json 2> gpurun_out/r2_b1.err
 JSSO_MG_FP16=1 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1_fp16.json 2> gpurun_out/r2_b1_fp16.err
+for K in 2 4 8; do   # chunked host pipeline of the e2e leg (opt-in): compare e2e.ms_per_step
+  JSSO_E2E_CHUNKS=$K python bench.py --steps 10 --no-cpu-baseline --no-solve > gpurun_out/r2_b1_e2e$K.json 2> gpurun_out/r2_b1_e2e$K.err
+  python -c "import json,sys; d=json.loads(open('gpurun_out/r2_b1_e2e$K.json').read().strip().splitlines()[-1]); print('e2e chunks $K', d['e2e'])"
+done
 python - <<'PY'
 import json
 for f in ('gpurun_out/r2_b1.json', 'gpurun_out/r2_b1_fp16.json'):

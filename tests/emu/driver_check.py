@@ -3,6 +3,7 @@
 emulator).  Launched as a subprocess by tests/test_emu_driver.py; prints one JSON line.
 
   driver_check.py grad  SIZE                         value + gradient of a mixed quad/beam plate vs the oracle
+  driver_check.py e2e   SIZE                         jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS from the environment)
   driver_check.py mg    SIZE DEG                     multigrid PCG vs block-Jacobi CG vs the oracle
   driver_check.py dist  WORLD SIZE MIN_DIST DEG      row-range distributed multigrid solve on WORLD rank THREADS
                                                      (fake NCCL between them) vs the undistributed solve
@@ -71,6 +72,20 @@ def main():
                'dq_err': float(np.abs(dq - rdq).max() / np.abs(rdq).max()),
                'db_err': float(np.abs(db - rdb).max() / np.abs(rdb).max()),
                'iterations': fs.iterations, 'launches': int(nat.lib().jsso_launch_count())}
+    elif mode == 'e2e':
+        md = mixed(int(sys.argv[2]))
+        rng = np.random.default_rng(5)
+        u, lam = rng.standard_normal(md.ndof), rng.standard_normal(md.ndof)
+        h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+        dc, dq, db = h.assemble_adjoint_host(md.crds, md.prop_quads, md.prop_beams, u, lam)
+        K = h.values_host()
+        rdc, rdq, rdb = orc.element_sensitivity(omesh(md), u, lam)
+        res = {'chunks': os.environ.get('JSSO_E2E_CHUNKS', '1'),
+               'g_err': float(np.abs(dc - rdc).max() / np.abs(rdc).max()),
+               'dq_err': float(np.abs(dq - rdq).max() / np.abs(rdq).max()),
+               'db_err': float(np.abs(db - rdb).max() / np.abs(rdb).max()),
+               'sum': [float(dc.sum()), float(dq.sum()), float(db.sum()), float(np.abs(K).sum())],
+               'hash': [hash(dc.tobytes()), hash(dq.tobytes()), hash(db.tobytes())]}
     elif mode == 'mg':
         md, deg = meshes.plate(int(sys.argv[2])), int(sys.argv[3])
         um, itm, cm, rm, _, _ = solve(md, 'multigrid', deg)

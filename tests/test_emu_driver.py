@@ -41,6 +41,18 @@ def test_value_and_gradient_through_the_emulated_driver(emu_api):
     assert res['launches'] > 100
 
 
+def test_chunked_host_pipeline_equals_unchunked(emu_api):
+    """JSSO_E2E_CHUNKS=K (opt-in): u / lam uploaded in K node ranges, the quad adjoint in K quad ranges with offset
+    pointers, d_prop_q returned range by range -- bitwise the same gradients as the single-launch path, and within
+    1e-6 of the complex-step oracle.  (The emulator checks the range arithmetic; stream ordering is the GPU's.)"""
+    import hashlib  # noqa: F401
+    base = run(emu_api, 'e2e', 7, env={'JSSO_E2E_CHUNKS': '1', 'PYTHONHASHSEED': '0'})
+    for k in ('3', '4'):
+        res = run(emu_api, 'e2e', 7, env={'JSSO_E2E_CHUNKS': k, 'PYTHONHASHSEED': '0'})
+        assert res['hash'] == base['hash'] and res['sum'] == base['sum']
+        assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6 and res['db_err'] <= 1e-6
+
+
 @pytest.mark.parametrize('fp16', ['0', '1'])
 def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
     """mg_numeric_setup (power iteration, smoothed prolongator, Galerkin products, dense coarse inverse) + V-cycle
