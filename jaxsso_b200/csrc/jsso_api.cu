@@ -1149,6 +1149,10 @@ static int mg_read_scalars(jsso_handle* h, cudaStream_t st) {
   return JSSO_OK;
 }
 
+static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n);
+static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st);
+static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st);
+
 // numeric hierarchy for the current (block-Jacobi-scaled) matrix
 static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_ready) return JSSO_OK;
@@ -1171,7 +1175,33 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     mg_hash_fill_kernel<<<vb, 256, 0, st>>>(nd, m.r);
     CKL("mg_hash_fill_kernel");
     double lam = 1.0;
-    for (int it = 0; it < 30; ++it) {
+    const bool dist_pow = h->mgd.n_rank > 1 && l < h->mgd.n_dist;
+    if (dist_pow) {
+      // distributed levels: the power iteration (30 SpMVs, 18 of the 42 ms of this setup at 1M quads) by row
+      // ranges; the start vector is a function of the index, so it is whole on every rank and only the
+      // normalised iterates are exchanged.  The all-reduced norms make lambda bitwise identical on all ranks.
+      int rs, rn;
+      mgd_range(h, l, rs, rn);
+      const size_t off = 6 * (size_t)rs;
+      const long long ndl = 6LL * rn;
+      const int vbl = std::max(1, std::min(h->red_blocks, cdiv(ndl, 256)));
+      for (int it = 0; it < 30; ++it) {
+        if (it > 0) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
+        if ((rc = mg_spmv<0>(h, A.rp + rs, A.ci, A.v, rn, m.r, m.d + off, nullptr, st))) return rc;
+        if (m.Dinv && rn > 0) {
+          block_apply_kernel<0><<<cdiv(rn, 128), 128, 0, st>>>(rn, m.Dinv + 36 * (size_t)rs, m.d + off, nullptr, m.d + off);
+          CKL("block_apply_kernel<0>");
+        }
+        if ((rc = mg_dot(h, ndl, m.d + off, m.d + off, 0, st))) return rc;
+        if ((rc = mg_dot(h, ndl, m.r + off, m.r + off, 1, st))) return rc;
+        if ((rc = mgd_reduce_read(h, 0, 2, st))) return rc;
+        lam = std::sqrt(h->mg_scal_host[0] / h->mg_scal_host[1]);
+        if (!(lam > 0.0) || !(lam == lam)) return fail(h, JSSO_ERR_NAN, "multigrid: power iteration broke down");
+        mg_axpby_kernel<<<vbl, 256, 0, st>>>(ndl, 1.0 / std::sqrt(h->mg_scal_host[0]), m.d + off, 0.0, m.r + off);
+        CKL("mg_axpby_kernel");
+      }
+    }
+    for (int it = 0; it < 30 && !dist_pow; ++it) {
       if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n, m.r, m.d, nullptr, st))) return rc;
       if (m.Dinv) {
         block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
