@@ -245,6 +245,54 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+
+def distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, device, opts, min_dist_nodes, dev, barrier,
+                          max_over_ranks, bcast):
+    """One gradient evaluation with the V-cycle PCG distributed by row ranges (jsso_mg_set_dist): every rank
+    assembles the whole mesh renumbered by owner and solves collectively, then the partitioned handle `h` runs the
+    adjoint on its part.  `dev`: the rank's device arrays (crds, pq, pb of the local mesh; uu = local part of an
+    earlier solve of the same system, overwritten; dc, dq outputs).  `bcast(obj)`: rank 0's object on every rank.
+    Collective; returns the report dict.  (A function so that the CPU suite can run it on rank threads against
+    the emulated library, tests/emu/driver_check.py.)"""
+    from jaxsso_b200 import dist_multigrid as dmg
+    D = nat.DeviceArray
+    L = nat.lib()
+    t_s = time.perf_counter()
+    perm, bounds = dmg.owner_permutation(owner, world)
+    rmd = dmg.renumber_mesh(gmd, perm)
+    inv_perm = np.empty(gmd.n_node, np.int64)
+    inv_perm[perm] = np.arange(gmd.n_node)
+    hd = nat.Handle(rmd.n_node, rmd.cnct_quads, rmd.cnct_beams, rmd.known, device=device)
+    levels = hd.mg_setup()
+    rp_, ci_ = hd.pattern()
+    plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=min_dist_nodes)
+    del levels
+    nid = bcast(nat.nccl_unique_id() if rank == 0 else None)
+    hd.mg_set_dist(nid, rank, world, plan)
+    rc_d, rq_d, rb_d = D.from_host(rmd.crds), D.from_host(rmd.prop_quads), D.from_host(rmd.prop_beams)
+    rf_d, ru_d = D.from_host(rmd.loads), D((rmd.ndof,))
+    rl2g_d = D.from_host(inv_perm[lm.l2g].astype(np.int32))
+    u_rep = dev['uu'].download()                      # local part of the earlier (replicated) solve
+    t_s = time.perf_counter() - t_s
+    barrier()
+    t0 = time.perf_counter()
+    fsd = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
+    nat.gather_rows(ru_d, rl2g_d, 6, out=dev['uu'])
+    h.backward(dev['crds'], dev['pq'], dev['pb'], dev['uu'], None, dev['dc'], dev['dq'], None, opts=opts)
+    L.jsso_stream_sync(None)
+    dtd = max_over_ranks(time.perf_counter() - t0)
+    u_dst = dev['uu'].download()
+    diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
+    ex, ar = hd.mg_dist_counters()
+    hd.close()
+    return {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
+            'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
+            'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
+            'setup_s': t_s, 'plan': dmg.plan_summary(plan),
+            'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
+                     'multigrid setup), adjoint partitioned'}
+
+
 # ------------------------------------------------------------------------------ own arm
 def run_b200(args):
     rank = int(os.environ.get('RANK', '0'))
@@ -553,42 +601,15 @@ def run_b200(args):
         wd = threading.Timer(args.dist_leg_timeout, on_timeout)
         wd.daemon = True
         wd.start()
+        def bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
         try:
-            from jaxsso_b200 import dist_multigrid as dmg
-            t_s = time.perf_counter()
-            perm, bounds = dmg.owner_permutation(owner, world)
-            rmd = dmg.renumber_mesh(gmd, perm)
-            inv_perm = np.empty(gmd.n_node, np.int64)
-            inv_perm[perm] = np.arange(gmd.n_node)
-            hd = nat.Handle(rmd.n_node, rmd.cnct_quads, rmd.cnct_beams, rmd.known, device=local_rank)
-            levels = hd.mg_setup()
-            rp_, ci_ = hd.pattern()
-            plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=args.min_dist_nodes)
-            del levels
-            idb = [nat.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(idb, src=0)
-            hd.mg_set_dist(idb[0], rank, world, plan)
-            rc_d, rq_d, rb_d = D.from_host(rmd.crds), D.from_host(rmd.prop_quads), D.from_host(rmd.prop_beams)
-            rf_d, ru_d = D.from_host(rmd.loads), D((rmd.ndof,))
-            rl2g_d = D.from_host(inv_perm[lm.l2g].astype(np.int32))
-            u_rep = uu_d.download()                      # local part of the replicated solve
-            t_s = time.perf_counter() - t_s
-            barrier()
-            t0 = time.perf_counter()
-            fsd = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
-            nat.gather_rows(ru_d, rl2g_d, 6, out=uu_d)
-            h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=opts)
-            L.jsso_stream_sync(None)
-            dtd = max_over_ranks(time.perf_counter() - t0)
-            u_dst = uu_d.download()
-            diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
-            ex, ar = hd.mg_dist_counters()
-            leg = {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
-                   'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
-                   'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
-                   'setup_s': t_s, 'plan': dmg.plan_summary(plan),
-                   'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
-                            'multigrid setup), adjoint partitioned'}
+            leg = distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, local_rank, opts, args.min_dist_nodes,
+                                        dict(crds=crds_d, pq=pq_d, pb=pb_d, uu=uu_d, dc=dc_d, dq=dq_d),
+                                        barrier, max_over_ranks, bcast)
         except Exception as e:   # an error on one rank only would leave the others in a collective: the watchdog ends them
             leg = {'error': f'{type(e).__name__}: {e}'}
         wd.cancel()

@@ -5,6 +5,7 @@ emulator).  Launched as a subprocess by tests/test_emu_driver.py; prints one JSO
   driver_check.py grad  SIZE                         value + gradient of a mixed quad/beam plate vs the oracle
   driver_check.py e2e   SIZE                         jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS from the environment)
   driver_check.py mg    SIZE DEG                     multigrid PCG vs block-Jacobi CG vs the oracle
+  driver_check.py benchleg WORLD SIZE MIN_DIST       bench.py's distributed_grad_eval on rank threads vs the oracle
   driver_check.py dist  WORLD SIZE MIN_DIST DEG      row-range distributed multigrid solve on WORLD rank THREADS
                                                      (fake NCCL between them) vs the undistributed solve
 """
@@ -119,6 +120,62 @@ def main():
                'identical_on_all_ranks': all(np.array_equal(o[0], out[0][0]) for o in out),
                'err_vs_oracle': float(np.linalg.norm(out[0][0].reshape(-1, 6) - uref.reshape(-1, 6)[perm]) / np.linalg.norm(uref)),
                'plan': out[0][4], 'exchanges': out[0][5][0], 'allreduces': out[0][5][1]}
+    elif mode == 'benchleg':
+        # bench.py's extra leg (distributed_grad_eval) on rank threads: partitioned handles for the adjoint, a
+        # replicated solve first, then the distributed one; gradients against the oracle
+        import bench
+        world, size, min_dist = (int(a) for a in sys.argv[2:5])
+        gmd = meshes.plate(size)
+        owner = partition.rcb_owner(gmd.crds[:, :2], world)
+        bar = threading.Barrier(world)
+        shared = {'id': None, 'vals': [None] * world}
+        out = [None] * world
+        opts = nat.make_opts(rtol=1e-10, compliance=True, precond='multigrid', cheb_degree=1)
+
+        def worker(rank):
+            lm = partition.local_mesh(gmd, owner, rank, world)
+            h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, device=0, n_row=lm.n_owned)
+            hg = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=0)
+            hg.mg_setup(max_coarse_nodes=8)
+            gu = D((gmd.ndof,))
+            hg.forward(D.from_host(gmd.crds), D.from_host(gmd.prop_quads), D.from_host(gmd.prop_beams),
+                       D.from_host(gmd.loads), gu, opts=opts)
+            dev = dict(crds=D.from_host(lm.md.crds), pq=D.from_host(lm.md.prop_quads), pb=D.from_host(lm.md.prop_beams),
+                       uu=D((lm.md.ndof,)), dc=D((lm.md.n_node, 3)), dq=D((lm.md.n_quad, 5)))
+            nat.gather_rows(gu, D.from_host(lm.l2g.astype(np.int32)), 6, out=dev['uu'])
+
+            def max_over_ranks(x):
+                shared['vals'][rank] = x
+                bar.wait()
+                m = max(shared['vals'])
+                bar.wait()
+                return m
+
+            def bcast(obj):
+                if rank == 0:
+                    shared['id'] = obj
+                bar.wait()
+                return shared['id']
+
+            leg = bench.distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, 0, opts, min_dist, dev, bar.wait,
+                                              max_over_ranks, bcast)
+            out[rank] = (leg, lm.l2g[:lm.n_owned], dev['dc'].download()[:lm.n_owned], lm.quad_ids, dev['dq'].download())
+
+        import jaxsso_b200.multigrid as mgmod
+        _bh = mgmod.build_hierarchy
+        mgmod.build_hierarchy = lambda rp, ci, max_coarse_nodes=64, **kw: _bh(rp, ci, max_coarse_nodes=8, **kw)  # small meshes
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        G, Q = np.zeros((gmd.n_node, 3)), np.zeros((gmd.n_quad, 5))
+        for leg, ids, g, qi, q in out:
+            G[ids] = g
+            Q[qi] = q
+        rv, ru, rl, rdc, rdq, rdb = orc.value_and_grad(omesh(gmd))
+        res = {'leg': out[0][0], 'g_err': float(np.abs(G - rdc).max() / np.abs(rdc).max()),
+               'dq_err': float(np.abs(Q - rdq).max() / np.abs(rdq).max())}
     else:
         raise SystemExit('unknown mode')
     print('EMU_RESULT ' + json.dumps(res))

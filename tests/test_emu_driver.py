@@ -105,3 +105,15 @@ def test_memcheck_under_address_sanitizer(args, env):
                "nat.gather_rows(s, i, 6)\n" % ROOT)
         r2 = subprocess.run([sys.executable, '-c', neg], capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
         assert r2.returncode != 0 and 'heap-buffer-overflow' in r2.stderr and 'gather_rows_kernel' in r2.stderr
+
+
+def test_bench_distributed_leg_on_rank_threads(emu_api):
+    """bench.py's `distributed_grad_eval` (the extra N > 1 leg: whole renumbered mesh per rank, distributed
+    V-cycle PCG, gather to the partitioned handle, partitioned adjoint) on two rank threads: u equals the replicated
+    solve, the gathered gradients equal the oracle's."""
+    res = run(emu_api, 'benchleg', 2, 12, 10)
+    leg = res['leg']
+    assert 'error' not in leg and leg['pcg_iterations'] > 0
+    assert leg['u_rel_diff_vs_replicated_solve'] <= 1e-8
+    assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
+    assert leg['plan']['n_dist'] == 2 and leg['halo_exchanges'] > 0
