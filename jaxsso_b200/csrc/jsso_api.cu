@@ -149,6 +149,7 @@ struct jsso_handle {
   bool mg_fp32 = true;
   __half* vals16 = nullptr;        // binary16 copy of the scaled fine matrix (V-cycle only; JSSO_MG_FP16=1)
   bool mg_fp16 = false;
+  int mg_async = 0;                // > 0: PCG scalars stay on the device, one host poll every mg_async iterations
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -1018,6 +1019,7 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
   {
     const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
     h->mg_fp32 = !(e && e[0] == '1');
+    if (const char* ea = std::getenv("JSSO_MG_ASYNC")) h->mg_async = std::max(0, std::min(64, std::atoi(ea)));
     const char* e16 = std::getenv("JSSO_MG_FP16");   // opt-in: binary16 storage of the fine-level V-cycle matrix
     h->mg_fp16 = h->mg_fp32 && n_levels > 0 && e16 && e16[0] == '1';
     if (h->mg_fp16) CK(dalloc(&h->vals16, 36 * (size_t)h->sym.nnzb()));
@@ -1583,6 +1585,99 @@ static int mg_solve_dist(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, 
   return JSSO_OK;
 }
 
+// ---------------------------------------------------------------- multigrid PCG, scalars on the device (opt-in)
+// JSSO_MG_ASYNC = k: alpha and beta are formed inside the update kernels from device-resident dot products (all-
+// reduced in place on several GPUs), so an iteration needs no host round trip and the host polls the residual
+// every k iterations (at most k - 1 iterations past convergence).  The synchronous drivers above pay three stream
+// synchronisations per iteration, which is what bounds the iteration once the kernels get short (8 GPUs).  Works
+// for the single-GPU and the row-range distributed solve.
+static int mg_solve_async(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, jsso_stats* stats, cudaStream_t st) {
+  int rc = mg_numeric_setup(h, st);
+  if (rc) return rc;
+  const bool dist = h->mgd.n_rank > 1;
+  int s = 0, n_row = h->sym.n_row;
+  if (dist) mgd_range(h, 0, s, n_row);
+  const size_t off = 6 * (size_t)s;
+  const long long n = 6LL * n_row;
+  const int vb = std::max(1, std::min(h->red_blocks, cdiv(n, 256)));
+  double *b = h->vb, *x = h->vx, *r = h->vr, *p = h->vp, *q = h->vq, *z = h->tmp_g;
+  const MgMat A = mg_matrix(h, 0);
+  auto reduce = [&](int slot, int count) -> int {
+    if (!dist) return JSSO_OK;
+    CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
+    ++h->mgd.n_allreduce;
+    return JSSO_OK;
+  };
+  if (use_x0) {
+    if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;
+  } else {
+    CK(cudaMemsetAsync(x + off, 0, n * sizeof(double), st));
+    CK(cudaMemcpyAsync(r + off, b + off, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  if ((rc = mg_dot(h, n, b + off, b + off, MGS_BB, st))) return rc;
+  if ((rc = mg_dot(h, n, r + off, r + off, MGS_RR, st))) return rc;
+  if ((rc = reduce(MGS_BB, 2))) return rc;
+  if ((rc = mg_read_scalars(h, st))) return rc;
+  const double bb = h->mg_scal_host[MGS_BB];
+  double rr = h->mg_scal_host[MGS_RR];
+  int it = 0, restarts = 0;
+  bool converged = (bb == 0.0) || std::sqrt(rr / bb) <= o.rtol;
+  bool first = true;
+  while (!converged && it < o.maxiter) {
+    const int batch = std::min(h->mg_async, o.maxiter - it);
+    for (int k = 0; k < batch; ++k) {
+      if (dist) rc = mg_vcycle_dist(h, 0, r, z, o.cheb_degree, st);
+      else rc = mg_vcycle(h, 0, r, z, o.cheb_degree, st);
+      if (rc) return rc;
+      if ((rc = mg_dot(h, n, r + off, z + off, MGS_RZ, st))) return rc;
+      if ((rc = reduce(MGS_RZ, 1))) return rc;
+      mg_pcg_dir_kernel<<<vb, 256, 0, st>>>(n, z + off, p + off, h->mg_scal, first ? 1 : 0);
+      CKL("mg_pcg_dir_kernel");
+      first = false;
+      if (dist) { if ((rc = mgd_exchange(h, 0, p, st))) return rc; }
+      if ((rc = mg_spmv<0>(h, A.rp + s, A.ci, A.v, n_row, p, q + off, nullptr, st))) return rc;
+      if ((rc = mg_dot(h, n, p + off, q + off, MGS_PQ, st))) return rc;
+      if ((rc = reduce(MGS_PQ, 1))) return rc;
+      mg_pcg_update_kernel<<<vb, 256, 0, st>>>(n, p + off, q + off, x + off, r + off, h->mg_scal);
+      CKL("mg_pcg_update_kernel");
+      if ((rc = mg_dot(h, n, r + off, r + off, MGS_RR, st))) return rc;
+      if ((rc = reduce(MGS_RR, 1))) return rc;
+    }
+    it += batch;
+    if ((rc = mg_read_scalars(h, st))) return rc;
+    rr = h->mg_scal_host[MGS_RR];
+    const double rz = h->mg_scal_host[MGS_RZ], pq = h->mg_scal_host[MGS_PQ];
+    if (!(rr == rr) || !(rz > 0.0) || !(pq > 0.0)) {
+      char buf[200];
+      std::snprintf(buf, sizeof buf, "multigrid PCG (async) breakdown by iteration %d: r.r = %.3e, r.z = %.3e, p.Ap = %.3e", it, rr, rz, pq);
+      return fail(h, JSSO_ERR_NAN, buf);
+    }
+    if (std::sqrt(rr / bb) <= o.rtol) {
+      // confirm on the true residual; if the recurrence drifted keep iterating from it
+      if (dist) { if ((rc = mgd_exchange(h, 0, x, st))) return rc; }
+      if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;
+      if ((rc = mg_dot(h, n, r + off, r + off, MGS_RR, st))) return rc;
+      if ((rc = reduce(MGS_RR, 1))) return rc;
+      if ((rc = mg_read_scalars(h, st))) return rc;
+      rr = h->mg_scal_host[MGS_RR];
+      if (std::sqrt(rr / bb) <= 1.5 * o.rtol) converged = true;
+      else if (++restarts > 20) break;
+    }
+  }
+  if (dist) { if ((rc = mgd_allgather(h, 0, x, st))) return rc; }
+  if (stats) {
+    stats->iterations = it; stats->restarts = restarts; stats->converged = converged ? 1 : 0;
+    stats->relres = bb > 0 ? std::sqrt(rr / bb) : 0.0; stats->relres_recur = stats->relres;
+  }
+  if (!converged) {
+    char buf[200];
+    std::snprintf(buf, sizeof buf, "multigrid PCG (async) did not reach rtol=%.3g: relres %.3g after %d iterations", o.rtol,
+                  bb > 0 ? std::sqrt(rr / bb) : 0.0, it);
+    return fail(h, JSSO_ERR_NOCONV, buf);
+  }
+  return JSSO_OK;
+}
+
 extern "C" {
 
 // K x = b on the assembled BC-imposed matrix: scale, solve, unscale.
@@ -1615,7 +1710,8 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
   const bool use_mg = (o.precond == 2) || (o.precond == 0 && have_mg && h->sym.n_row >= 20000);
   if (use_mg && !have_mg) return fail(h, JSSO_ERR_STATE, "precond = multigrid but no hierarchy (jsso_mg_setup)");
   if (stats) stats->flags = fl;
-  if (use_mg) rc = (h->mgd.n_rank > 1) ? mg_solve_dist(h, o, o.use_x0 != 0, stats, st) : mg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
+  if (use_mg && h->mg_async > 0) rc = mg_solve_async(h, o, o.use_x0 != 0, stats, st);
+  else if (use_mg) rc = (h->mgd.n_rank > 1) ? mg_solve_dist(h, o, o.use_x0 != 0, stats, st) : mg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   else rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
   if (rc && rc != JSSO_ERR_NOCONV) return rc;

@@ -345,6 +345,25 @@ __global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = v;
 }
+// ---- PCG with the scalars kept on the device (opt-in asynchronous driver, JSSO_MG_ASYNC): slots of `scal`
+constexpr int MGS_BB = 1, MGS_RR = 2, MGS_RZ = 3, MGS_PQ = 4, MGS_RZ_OLD = 6;
+// p = z + (rz / rz_old) p   (first: p = z)
+__global__ void mg_pcg_dir_kernel(long long n, const double* __restrict__ z, double* __restrict__ p,
+                                  const double* __restrict__ scal, int first) {
+  const double beta = first ? 0.0 : scal[MGS_RZ] / scal[MGS_RZ_OLD];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+// alpha = rz / pq;  x += alpha p;  r -= alpha q;  then rz_old = rz (nobody reads rz_old in this kernel)
+__global__ void mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __restrict__ q,
+                                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ scal) {
+  const double alpha = scal[MGS_RZ] / scal[MGS_PQ];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    r[i] = fma(-alpha, q[i], r[i]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[MGS_RZ_OLD] = scal[MGS_RZ];
+}
 // FP64 column-major blocks a[36 s + 6 j + i] -> FP32 row-pair-major blocks b[36 s + 12 sub + 2 j + r],
 // i = 2 sub + r (the layout bsr_row_product<float> reads with 16-byte loads)
 __global__ void mg_to_float_kernel(long long n, const double* __restrict__ a, float* __restrict__ b) {

@@ -117,3 +117,15 @@ def test_bench_distributed_leg_on_rank_threads(emu_api):
     assert leg['u_rel_diff_vs_replicated_solve'] <= 1e-8
     assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
     assert leg['plan']['n_dist'] == 2 and leg['halo_exchanges'] > 0
+
+
+def test_device_scalar_pcg_single_and_distributed(emu_api):
+    """JSSO_MG_ASYNC=k (opt-in): alpha / beta formed on the device, one host poll every k iterations -- same
+    solution, at most k - 1 extra iterations, on one GPU and on two rank threads."""
+    base = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_ASYNC': '0'})
+    res = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_ASYNC': '4'})
+    assert res['mg_converged'] and res['mg_err'] <= 1e-8
+    assert base['mg_iters'] <= res['mg_iters'] <= base['mg_iters'] + 3 and res['mg_iters'] % 4 == 0
+    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_ASYNC': '3'})
+    assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
+    assert all(d['iters_single'] <= i <= d['iters_single'] + 2 for i in d['iters_dist'])
