@@ -5,6 +5,7 @@ emulator).  Launched as a subprocess by tests/test_emu_driver.py; prints one JSO
   driver_check.py grad  SIZE                         value + gradient of a mixed quad/beam plate vs the oracle
   driver_check.py e2e   SIZE                         jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS from the environment)
   driver_check.py mg    SIZE DEG                     multigrid PCG vs block-Jacobi CG vs the oracle
+  driver_check.py part  WORLD SIZE                   partitioned handles + distributed block-Jacobi CG (hardware-measured path)
   driver_check.py benchleg WORLD SIZE MIN_DIST       bench.py's distributed_grad_eval on rank threads vs the oracle
   driver_check.py dist  WORLD SIZE MIN_DIST DEG      row-range distributed multigrid solve on WORLD rank THREADS
                                                      (fake NCCL between them) vs the undistributed solve
@@ -120,6 +121,39 @@ def main():
                'identical_on_all_ranks': all(np.array_equal(o[0], out[0][0]) for o in out),
                'err_vs_oracle': float(np.linalg.norm(out[0][0].reshape(-1, 6) - uref.reshape(-1, 6)[perm]) / np.linalg.norm(uref)),
                'plan': out[0][4], 'exchanges': out[0][5][0], 'allreduces': out[0][5][1]}
+    elif mode == 'part':
+        # the partitioned path that IS measured on hardware (scripts/dist_check.py: set_halo + distributed block-Jacobi
+        # CG over NCCL send/recv, partitioned adjoint) on rank threads: calibrates the fake NCCL against a known-good path
+        world, size = int(sys.argv[2]), int(sys.argv[3])
+        gmd = meshes.plate(size)
+        owner = partition.rcb_owner(gmd.crds[:, :2], world)
+        nid = nat.nccl_unique_id()
+        out = [None] * world
+        opts = nat.make_opts(rtol=1e-11, compliance=True, precond='block_jacobi')
+
+        def worker(rank):
+            lm = partition.local_mesh(gmd, owner, rank, world)
+            h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, device=0, n_row=lm.n_owned)
+            h.set_halo(nid, rank, world, lm.peer_rank, lm.send_ptr, lm.send_idx, lm.recv_start, lm.recv_count)
+            crds, pq, pb, f = (D.from_host(a) for a in (lm.md.crds, lm.md.prop_quads, lm.md.prop_beams, lm.md.loads))
+            u, dc, dq = D((lm.md.ndof,)), D((lm.md.n_node, 3)), D((lm.md.n_quad, 5))
+            fs = h.forward(crds, pq, pb, f, u, opts=opts)
+            h.backward(crds, pq, pb, u, None, dc, dq, None, opts=opts)
+            out[rank] = (lm.l2g[:lm.n_owned], u.download().reshape(-1, 6)[:lm.n_owned], dc.download()[:lm.n_owned],
+                         lm.quad_ids, dq.download(), fs.iterations)
+
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        U, G, Q = np.zeros((gmd.n_node, 6)), np.zeros((gmd.n_node, 3)), np.zeros((gmd.n_quad, 5))
+        for ids, u_, g_, qi, q_, it in out:
+            U[ids] = u_; G[ids] = g_; Q[qi] = q_
+        rv, ru, rl, rdc, rdq, rdb = orc.value_and_grad(omesh(gmd))
+        res = {'u_err': float(np.linalg.norm(U.ravel() - ru) / np.linalg.norm(ru)),
+               'g_err': float(np.abs(G - rdc).max() / np.abs(rdc).max()),
+               'dq_err': float(np.abs(Q - rdq).max() / np.abs(rdq).max()), 'iterations': [o[5] for o in out]}
     elif mode == 'benchleg':
         # bench.py's extra leg (distributed_grad_eval) on rank threads: partitioned handles for the adjoint, a
         # replicated solve first, then the distributed one; gradients against the oracle

@@ -81,7 +81,7 @@ def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size,
     assert res['exchanges'] > 0 and res['allreduces'] >= 3 * res['iters_single']
 
 
-@pytest.mark.parametrize('args,env', [(('grad', 4), {}), (('dist', 2, 8, 10, 1), {'JSSO_MG_FP16': '1'})])
+@pytest.mark.parametrize('args,env', [(('grad', 4), {}), (('dist', 2, 6, 5, 1), {'JSSO_MG_FP16': '1'})])
 def test_memcheck_under_address_sanitizer(args, env):
     """The emulated driver built with -fsanitize=address: every "device" buffer is a heap block, so an out-of-bounds
     access of a kernel (or of the host driver) aborts with a report naming the .cuh line -- compute-sanitizer
@@ -129,3 +129,14 @@ def test_device_scalar_pcg_single_and_distributed(emu_api):
     d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_ASYNC': '3'})
     assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
     assert all(d['iters_single'] <= i <= d['iters_single'] + 2 for i in d['iters_dist'])
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_partitioned_path_on_rank_threads(emu_api, world):
+    """Calibration of the rank-thread emulation against a path that IS verified on hardware (tests/test_multi_gpu.py,
+    scripts/dist_check.py): partitioned handles, `jsso_set_halo`, distributed block-Jacobi CG with NCCL halo
+    exchanges and scalar all-reduces, partitioned adjoint -- u and gradients equal the oracle's, every rank
+    takes the same number of iterations."""
+    res = run(emu_api, 'part', world, 8)
+    assert res['u_err'] <= 1e-8 and res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
+    assert len(set(res['iterations'])) == 1
