@@ -140,3 +140,12 @@ def test_partitioned_path_on_rank_threads(emu_api, world):
     res = run(emu_api, 'part', world, 8)
     assert res['u_err'] <= 1e-8 and res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
     assert len(set(res['iterations'])) == 1
+
+
+def test_full_size_property_tests_run_on_the_emulator(emu_api):
+    """tests/test_zz_full_size_properties.py (GPU marker, 1024^2 on the B200) at size 10 against the emulated library:
+    keeps the logic of those tests checked where there is no GPU."""
+    e = dict(os.environ, JSSO_LIB=emu_api, JSSO_FULL_SIZE='10')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_zz_full_size_properties.py'), '-q',
+                        '-x', '-p', 'no:cacheprovider'], capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
+    assert r.returncode == 0 and '2 passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
