@@ -73,7 +73,9 @@ def test_assembly_is_deterministic_linear_in_E_symmetric_and_translation_free(pl
     pq2 = md.prop_quads.copy(); pq2[:, 1] *= 2.0
     pq2_d = D.from_host(pq2)
     h.assemble(dev['crds'], pq2_d, dev['pb'], apply_bc=False)
-    assert np.array_equal(values(h), 2.0 * v1)                              # K(2E) == 2 K(E), bit for bit
+    v2 = values(h)
+    v2 *= 0.5                                                              # exact; keeps the host footprint at two arrays
+    assert np.array_equal(v2, v1)                                          # K(2E) == 2 K(E), bit for bit
     pq2_d.free()
 
 
