@@ -150,6 +150,15 @@ struct jsso_handle {
   __half* vals16 = nullptr;        // binary16 copy of the scaled fine matrix (V-cycle only; JSSO_MG_FP16=1)
   bool mg_fp16 = false;
   int mg_async = 0;                // > 0: PCG scalars stay on the device, one host poll every mg_async iterations
+  // opt-in CUDA graph of the V-cycle's launch-bound part (JSSO_MG_GRAPH=1): the whole V-cycle on one GPU, the
+  // replicated coarse levels of the distributed solve.  Captured once per numeric setup (the smoother
+  // coefficients are kernel arguments) on a private stream, replayed into the caller's stream.
+  bool mg_graph = false;
+  cudaStream_t st_cap = nullptr;
+  cudaGraphExec_t mg_graph_exec = nullptr;
+  int mg_graph_level = -1, mg_graph_deg = 0;
+  const double* mg_graph_b = nullptr;
+  double* mg_graph_x = nullptr;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -397,6 +406,8 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_b) cudaStreamDestroy(h->st_b);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->st_c) cudaStreamDestroy(h->st_c);
+  if (h->mg_graph_exec) cudaGraphExecDestroy(h->mg_graph_exec);
+  if (h->st_cap) cudaStreamDestroy(h->st_cap);
   for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_adj) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
@@ -1020,6 +1031,7 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
     h->mg_fp32 = !(e && e[0] == '1');
     if (const char* ea = std::getenv("JSSO_MG_ASYNC")) h->mg_async = std::max(0, std::min(64, std::atoi(ea)));
+    if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] == '1';
     const char* e16 = std::getenv("JSSO_MG_FP16");   // opt-in: binary16 storage of the fine-level V-cycle matrix
     h->mg_fp16 = h->mg_fp32 && n_levels > 0 && e16 && e16[0] == '1';
     if (h->mg_fp16) CK(dalloc(&h->vals16, 36 * (size_t)h->sym.nnzb()));
@@ -1158,6 +1170,7 @@ static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st)
 // numeric hierarchy for the current (block-Jacobi-scaled) matrix
 static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_ready) return JSSO_OK;
+  if (h->mg_graph_exec) { cudaGraphExecDestroy(h->mg_graph_exec); h->mg_graph_exec = nullptr; }   // coefficients change
   if (!h->last_crds) return fail(h, JSSO_ERR_STATE, "multigrid needs the coordinates of the last jsso_assemble");
   const int nl = (int)h->mg.size();
   const double* X = h->last_crds;
@@ -1306,6 +1319,35 @@ static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg,
   return mg_smooth(h, l, b, x, false, deg, st);
 }
 
+// The V-cycle from level l as ONE graph launch (JSSO_MG_GRAPH=1): its ~8 kernels per level are a few microseconds
+// each on the coarse levels, i.e. bound by launch latency; a graph replays them back to back.  Nothing in
+// mg_vcycle synchronises, allocates or copies, so it can be captured as it is.
+static int mg_vcycle_graphed(jsso_handle* h, int l, const double* b, double* x, int deg, cudaStream_t st) {
+  if (!h->mg_graph) return mg_vcycle(h, l, b, x, deg, st);
+  if (h->mg_graph_exec && (h->mg_graph_level != l || h->mg_graph_b != b || h->mg_graph_x != x || h->mg_graph_deg != deg)) {
+    cudaGraphExecDestroy(h->mg_graph_exec);
+    h->mg_graph_exec = nullptr;
+  }
+  if (!h->mg_graph_exec) {
+    if (!h->st_cap) CK(cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(h->st_cap, cudaStreamCaptureModeThreadLocal));
+    const long long launched = g_launches.load();
+    const int rc = mg_vcycle(h, l, b, x, deg, h->st_cap);
+    g_launches.store(launched);                       // captured, not launched
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->st_cap, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(h, JSSO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&h->mg_graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { h->mg_graph_exec = nullptr; return fail(h, JSSO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2)); }
+    h->mg_graph_level = l; h->mg_graph_b = b; h->mg_graph_x = x; h->mg_graph_deg = deg;
+  }
+  CK(cudaGraphLaunch(h->mg_graph_exec, st));
+  LAUNCHED();
+  return JSSO_OK;
+}
+
 // PCG on the scaled system with the V-cycle as preconditioner (host-driven scalars: the count is
 // 30-100 iterations, each several milliseconds at 1M quads, so three host syncs per iteration
 // cost nothing)
@@ -1331,7 +1373,7 @@ static int mg_solve_scaled(jsso_handle* h, const jsso_solve_opts& o, bool use_x0
   int it = 0;
   bool converged = (bb == 0.0) || std::sqrt(rr / bb) <= o.rtol;
   while (!converged && it < o.maxiter) {
-    if ((rc = mg_vcycle(h, 0, r, z, o.cheb_degree, st))) return rc;
+    if ((rc = mg_vcycle_graphed(h, 0, r, z, o.cheb_degree, st))) return rc;
     if ((rc = mg_dot(h, n, r, z, 3, st))) return rc;
     if ((rc = mg_read_scalars(h, st))) return rc;
     const double rz_new = h->mg_scal_host[3];
@@ -1483,7 +1525,7 @@ static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, boo
 // on exit x is valid on this rank's range (everywhere at replicated levels)
 static int mg_vcycle_dist(jsso_handle* h, int l, double* b, double* x, int deg, cudaStream_t st) {
   const int nl = (int)h->mg.size();
-  if (l >= h->mgd.n_dist) return mg_vcycle(h, l, b, x, deg, st);
+  if (l >= h->mgd.n_dist) return mg_vcycle_graphed(h, l, b, x, deg, st);
   int rc;
   jsso_handle::MgLevel& m = h->mg[l];
   const MgMat A = mg_matrix(h, l);
@@ -1627,7 +1669,7 @@ static int mg_solve_async(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
     const int batch = std::min(h->mg_async, o.maxiter - it);
     for (int k = 0; k < batch; ++k) {
       if (dist) rc = mg_vcycle_dist(h, 0, r, z, o.cheb_degree, st);
-      else rc = mg_vcycle(h, 0, r, z, o.cheb_degree, st);
+      else rc = mg_vcycle_graphed(h, 0, r, z, o.cheb_degree, st);
       if (rc) return rc;
       if ((rc = mg_dot(h, n, r + off, z + off, MGS_RZ, st))) return rc;
       if ((rc = reduce(MGS_RZ, 1))) return rc;

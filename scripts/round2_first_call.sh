@@ -14,6 +14,10 @@ python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1.json 2> gpurun_o
 JSSO_MG_FP16=1 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r2_b1_fp16.json 2> gpurun_out/r2_b1_fp16.err
 JSSO_MG_ASYNC=4 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/r2_b1_async.json 2> gpurun_out/r2_b1_async.err
 python -c "import json; d=json.loads(open('gpurun_out/r2_b1_async.json').read().strip().splitlines()[-1]); print('async', d['grad_eval'])"
+JSSO_MG_GRAPH=1 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/r2_b1_graph.json 2> gpurun_out/r2_b1_graph.err
+python -c "import json; d=json.loads(open('gpurun_out/r2_b1_graph.json').read().strip().splitlines()[-1]); print('graph', d['grad_eval'])"
+JSSO_MG_GRAPH=1 JSSO_MG_ASYNC=4 JSSO_MG_FP16=1 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/r2_b1_all.json 2> gpurun_out/r2_b1_all.err
+python -c "import json; d=json.loads(open('gpurun_out/r2_b1_all.json').read().strip().splitlines()[-1]); print('graph+async+fp16', d['grad_eval'])"
 for K in 2 4 8; do   # chunked host pipeline of the e2e leg (opt-in): compare e2e.ms_per_step
   JSSO_E2E_CHUNKS=$K python bench.py --steps 10 --no-cpu-baseline --no-solve > gpurun_out/r2_b1_e2e$K.json 2> gpurun_out/r2_b1_e2e$K.err
   python -c "import json,sys; d=json.loads(open('gpurun_out/r2_b1_e2e$K.json').read().strip().splitlines()[-1]); print('e2e chunks $K', d['e2e'])"

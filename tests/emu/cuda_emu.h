@@ -165,9 +165,19 @@ inline unsigned dimx(const dim3& v) { return v.x; }
 // kernels keep `__shared__` data in function-local statics: one emulated launch at a time, process-wide
 inline std::mutex& launch_mutex() { static std::mutex m; return m; }
 
-// launch(grid, block, dynamic shared bytes, [&] { kernel(args...); })
+// stream capture (CUDA graphs): while a thread captures, launches are recorded (closures hold their arguments BY
+// VALUE, like a real launch) instead of executed; replay runs them in order
+struct GraphNode { unsigned grid, block; size_t smem; std::function<void()> body; };
+struct Graph { std::vector<GraphNode> nodes; };
+inline thread_local Graph* capturing = nullptr;
+
+// launch(grid, block, dynamic shared bytes, [=] { kernel(args...); })
 template <class G, class B, class F>
 void launch(G grid_, B block_, size_t smem, F&& body_) {
+  if (capturing) {
+    capturing->nodes.push_back(GraphNode{dimx(grid_), dimx(block_), smem, std::function<void()>(body_)});
+    return;
+  }
   std::lock_guard<std::mutex> serial(launch_mutex());
   const unsigned grid = dimx(grid_), block = dimx(block_);
   const unsigned n_warp = (block + 31) / 32;

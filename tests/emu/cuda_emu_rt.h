@@ -28,7 +28,11 @@ template <class T> inline cudaError_t MallocHost(T** p, size_t n) { return Mallo
 inline cudaError_t HostAlloc(void** p, size_t n, unsigned) { return Malloc(p, n); }
 inline cudaError_t FreeHost(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t Memcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
-inline cudaError_t MemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t MemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
+  if (emu::capturing) { std::fprintf(stderr, "emu: memcpy inside a stream capture is not emulated\n"); std::abort(); }
+  if (n) std::memmove(d, s, n);
+  return cudaSuccess;
+}
 inline cudaError_t Memcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
   for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
   return cudaSuccess;
@@ -60,6 +64,29 @@ inline cudaError_t IpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErro
 inline cudaError_t IpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 inline cudaError_t IpcCloseMemHandle(void*) { return cudaSuccess; }
 inline cudaError_t LaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+
+// CUDA graphs: capture = record the launches of this thread, launch = replay them
+inline cudaError_t StreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+  if (emu::capturing) return cudaErrorIllegalState;
+  emu::capturing = new emu::Graph;
+  return cudaSuccess;
+}
+inline cudaError_t StreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+  if (!emu::capturing) return cudaErrorIllegalState;
+  *g = (cudaGraph_t)emu::capturing;
+  emu::capturing = nullptr;
+  return cudaSuccess;
+}
+inline cudaError_t GraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long = 0) {
+  *e = (cudaGraphExec_t) new emu::Graph(*(emu::Graph*)g);
+  return cudaSuccess;
+}
+inline cudaError_t GraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+  for (const emu::GraphNode& nd : ((emu::Graph*)e)->nodes) emu::launch(nd.grid, nd.block, nd.smem, nd.body);
+  return cudaSuccess;
+}
+inline cudaError_t GraphDestroy(cudaGraph_t g) { delete (emu::Graph*)g; return cudaSuccess; }
+inline cudaError_t GraphExecDestroy(cudaGraphExec_t e) { delete (emu::Graph*)e; return cudaSuccess; }
 
 // ---------------------------------------------------------------- fake NCCL between rank threads
 struct Shared {
@@ -188,3 +215,9 @@ inline const char* NGetErrorString(ncclResult_t) { return "emulated NCCL"; }
 #define cudaIpcOpenMemHandle emurt::IpcOpenMemHandle
 #define cudaIpcCloseMemHandle emurt::IpcCloseMemHandle
 #define cudaLaunchCooperativeKernel emurt::LaunchCooperativeKernel
+#define cudaStreamBeginCapture emurt::StreamBeginCapture
+#define cudaStreamEndCapture emurt::StreamEndCapture
+#define cudaGraphInstantiate emurt::GraphInstantiate
+#define cudaGraphLaunch emurt::GraphLaunch
+#define cudaGraphDestroy emurt::GraphDestroy
+#define cudaGraphExecDestroy emurt::GraphExecDestroy

@@ -90,12 +90,15 @@ def main():
                'hash': [hash(dc.tobytes()), hash(dq.tobytes()), hash(db.tobytes())]}
     elif mode == 'mg':
         md, deg = meshes.plate(int(sys.argv[2])), int(sys.argv[3])
+        l0 = int(nat.lib().jsso_launch_count())
         um, itm, cm, rm, _, _ = solve(md, 'multigrid', deg)
+        mg_launches = int(nat.lib().jsso_launch_count()) - l0
         ub, itb, cb, rb, _, _ = solve(md, 'block_jacobi')
         uref = orc.solve_refined(omesh(md))
         res = {'mg_err': float(np.linalg.norm(um - uref) / np.linalg.norm(uref)),
                'bj_err': float(np.linalg.norm(ub - uref) / np.linalg.norm(uref)),
-               'mg_iters': itm, 'bj_iters': itb, 'mg_converged': cm, 'bj_converged': cb, 'fp16': os.environ.get('JSSO_MG_FP16', '0')}
+               'mg_iters': itm, 'bj_iters': itb, 'mg_converged': cm, 'bj_converged': cb, 'fp16': os.environ.get('JSSO_MG_FP16', '0'),
+               'mg_launches': mg_launches}
     elif mode == 'dist':
         world, size, min_dist, deg = (int(a) for a in sys.argv[2:6])
         md0 = meshes.plate(size)

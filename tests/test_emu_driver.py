@@ -149,3 +149,19 @@ def test_full_size_property_tests_run_on_the_emulator(emu_api):
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_zz_full_size_properties.py'), '-q',
                         '-x', '-p', 'no:cacheprovider'], capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
     assert r.returncode == 0 and '2 passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_graph_captured_vcycle(emu_api):
+    """JSSO_MG_GRAPH=1 (opt-in): the V-cycle is captured once per numeric setup and replayed as one graph launch
+    (the emulator records the launches with their arguments by value and replays them): same iterations and
+    solution with far fewer launches, alone and combined with the device-scalar PCG and binary16 storage; on rank
+    threads the replicated coarse levels are the captured part."""
+    base = run(emu_api, 'mg', 12, 1)
+    g = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_GRAPH': '1'})
+    assert g['mg_converged'] and g['mg_iters'] == base['mg_iters'] and g['mg_err'] <= 1e-8
+    assert g['mg_launches'] <= base['mg_launches'] - 10 * g['mg_iters']      # every V-cycle became one launch
+    c = run(emu_api, 'mg', 12, 2, env={'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '4', 'JSSO_MG_FP16': '1'})
+    assert c['mg_converged'] and c['mg_err'] <= 1e-8
+    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_GRAPH': '1'})
+    assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
+    assert all(i == d['iters_single'] for i in d['iters_dist'])
