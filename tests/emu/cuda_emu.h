@@ -35,7 +35,7 @@
 #define __global__
 #define __device__
 #define __host__
-#define __shared__ static
+#define __shared__ static thread_local   /* one copy per rank thread: CTAs of different ranks run concurrently */
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
@@ -113,7 +113,7 @@ struct Sched {
 inline Sched& sched() { static thread_local Sched s; return s; }
 constexpr size_t kStack = 512 * 1024;
 
-// `tls` is the running fiber (one launch at a time per process: launch_mutex)
+// the running fiber of this OS thread
 #define EMU_CUR (*emu::sched().cur)
 
 inline void yield() {
@@ -162,8 +162,9 @@ inline unsigned dimx(int v) { return (unsigned)v; }
 inline unsigned dimx(long long v) { return (unsigned)v; }
 inline unsigned dimx(size_t v) { return (unsigned)v; }
 inline unsigned dimx(const dim3& v) { return v.x; }
-// kernels keep `__shared__` data in function-local statics: one emulated launch at a time, process-wide
-inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+// Launches of different OS threads (rank threads) run CONCURRENTLY -- the peer-memory kernels spin on flags that
+// another rank's kernel sets -- so everything a launch touches is per thread: the scheduler, the fiber stacks and
+// the `__shared__` statics (thread_local).
 
 // stream capture (CUDA graphs): while a thread captures, launches are recorded (closures hold their arguments BY
 // VALUE, like a real launch) instead of executed; replay runs them in order
@@ -178,7 +179,6 @@ void launch(G grid_, B block_, size_t smem, F&& body_) {
     capturing->nodes.push_back(GraphNode{dimx(grid_), dimx(block_), smem, std::function<void()>(body_)});
     return;
   }
-  std::lock_guard<std::mutex> serial(launch_mutex());
   const unsigned grid = dimx(grid_), block = dimx(block_);
   const unsigned n_warp = (block + 31) / 32;
   const std::function<void()> body = body_;

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE: CUDA runtime API and NCCL stand-ins for running the product's HOST driver
 // (csrc/jsso_api.cu, kernel launches rewritten by tests/emu/build_emu.py) on top of the SIMT emulator.
-// "Device memory" is the heap; streams and events are no-ops (every emulated launch is synchronous);
+// "Device memory" is the heap; streams are no-ops (every emulated launch is synchronous within its thread);
 // the device reports 2 SMs and occupancy 1, so persistent grids stay tiny.  The fake NCCL connects RANK THREADS of
 // one process (each thread drives its own handle): buffered sends, blocking receives, rank-ordered all-reduce.
 // Not part of the product; nothing here is reachable from libjsso.so.
@@ -60,8 +60,9 @@ inline cudaError_t DeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 0; ret
 template <class F> inline cudaError_t OccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 template <class F> inline cudaError_t FuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t PointerGetAttributes(cudaPointerAttributes* a, const void*) { std::memset(a, 0, sizeof *a); a->type = cudaMemoryTypeHost; return cudaSuccess; }
-inline cudaError_t IpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t IpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "IPC" between rank threads of one process: the handle carries the pointer
+inline cudaError_t IpcGetMemHandle(cudaIpcMemHandle_t* hd, void* p) { std::memset(hd, 0, sizeof *hd); std::memcpy(hd, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t IpcOpenMemHandle(void** p, cudaIpcMemHandle_t hd, unsigned) { std::memcpy(p, &hd, sizeof *p); return cudaSuccess; }
 inline cudaError_t IpcCloseMemHandle(void*) { return cudaSuccess; }
 inline cudaError_t LaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
 

@@ -128,16 +128,24 @@ def main():
         # the partitioned path that IS measured on hardware (scripts/dist_check.py: set_halo + distributed block-Jacobi
         # CG over NCCL send/recv, partitioned adjoint) on rank threads: calibrates the fake NCCL against a known-good path
         world, size = int(sys.argv[2]), int(sys.argv[3])
+        use_p2p = len(sys.argv) > 4 and sys.argv[4] == 'p2p'
         gmd = meshes.plate(size)
         owner = partition.rcb_owner(gmd.crds[:, :2], world)
         nid = nat.nccl_unique_id()
         out = [None] * world
+        handles = [None] * world
+        bar = threading.Barrier(world)
         opts = nat.make_opts(rtol=1e-11, compliance=True, precond='block_jacobi')
 
         def worker(rank):
             lm = partition.local_mesh(gmd, owner, rank, world)
             h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, device=0, n_row=lm.n_owned)
             h.set_halo(nid, rank, world, lm.peer_rank, lm.send_ptr, lm.send_idx, lm.recv_start, lm.recv_count)
+            if use_p2p:      # peer-memory path: halo pushes and mailbox all-reduces inside the CG kernels
+                handles[rank] = h.p2p_export()
+                bar.wait()
+                h.p2p_connect(list(handles), lm.remote_start)
+                bar.wait()
             crds, pq, pb, f = (D.from_host(a) for a in (lm.md.crds, lm.md.prop_quads, lm.md.prop_beams, lm.md.loads))
             u, dc, dq = D((lm.md.ndof,)), D((lm.md.n_node, 3)), D((lm.md.n_quad, 5))
             fs = h.forward(crds, pq, pb, f, u, opts=opts)

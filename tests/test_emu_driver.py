@@ -131,13 +131,16 @@ def test_device_scalar_pcg_single_and_distributed(emu_api):
     assert all(d['iters_single'] <= i <= d['iters_single'] + 2 for i in d['iters_dist'])
 
 
+@pytest.mark.parametrize('p2p', ['', 'p2p'])
 @pytest.mark.parametrize('world', [2, 4])
-def test_partitioned_path_on_rank_threads(emu_api, world):
+def test_partitioned_path_on_rank_threads(emu_api, world, p2p):
     """Calibration of the rank-thread emulation against a path that IS verified on hardware (tests/test_multi_gpu.py,
     scripts/dist_check.py): partitioned handles, `jsso_set_halo`, distributed block-Jacobi CG with NCCL halo
     exchanges and scalar all-reduces, partitioned adjoint -- u and gradients equal the oracle's, every rank
-    takes the same number of iterations."""
-    res = run(emu_api, 'part', world, 8)
+    takes the same number of iterations.  'p2p': the peer-memory variant (halo pushes into the neighbours' vectors,
+    mailbox all-reduces, kernels spinning on flags another rank's kernel sets) -- the rank threads' launches run
+    concurrently, "IPC" handles carry plain pointers."""
+    res = run(emu_api, 'part', world, 8, p2p)
     assert res['u_err'] <= 1e-8 and res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
     assert len(set(res['iterations'])) == 1
 
