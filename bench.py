@@ -247,7 +247,7 @@ def run_reference(args):
 
 
 def distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, device, opts, min_dist_nodes, dev, barrier,
-                          max_over_ranks, bcast):
+                          max_over_ranks, bcast, allgather=None, on_partial=None):
     """One gradient evaluation with the V-cycle PCG distributed by row ranges (jsso_mg_set_dist): every rank
     assembles the whole mesh renumbered by owner and solves collectively, then the partitioned handle `h` runs the
     adjoint on its part.  `dev`: the rank's device arrays (crds, pq, pb of the local mesh; uu = local part of an
@@ -284,13 +284,36 @@ def distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, device, opts, min
     u_dst = dev['uu'].download()
     diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
     ex, ar = hd.mg_dist_counters()
+    res = {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
+           'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
+           'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
+           'setup_s': t_s, 'plan': dmg.plan_summary(plan),
+           'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
+                    'multigrid setup), adjoint partitioned'}
+    if on_partial:
+        on_partial(dict(res))
+    if allgather is not None:
+        # the same solve again with the exchanges over peer memory (jsso_mg_p2p_connect): push + wait/unpack kernels
+        # and mailbox all-reduces instead of NCCL calls
+        try:
+            hd.mg_p2p_connect(plan, allgather)
+            barrier()
+            t0 = time.perf_counter()
+            fsp = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
+            nat.gather_rows(ru_d, rl2g_d, 6, out=dev['uu'])
+            h.backward(dev['crds'], dev['pq'], dev['pb'], dev['uu'], None, dev['dc'], dev['dq'], None, opts=opts)
+            L.jsso_stream_sync(None)
+            dtp = max_over_ranks(time.perf_counter() - t0)
+            u_p2p = dev['uu'].download()
+            dfp = max_over_ranks(float(np.linalg.norm(u_p2p - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
+            hd.mg_dist_counters()
+            res['peer_memory'] = {'seconds': dtp, 'evals_per_s': 1.0 / dtp, 'pcg_iterations': fsp.iterations,
+                                  'ms_per_pcg_iteration': 1e3 * dtp / max(fsp.iterations, 1),
+                                  'u_rel_diff_vs_replicated_solve': dfp, 'active': bool(hd.mg_dist_p2p)}
+        except nat.JssoError as e:
+            res['peer_memory'] = {'error': str(e)}
     hd.close()
-    return {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
-            'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
-            'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
-            'setup_s': t_s, 'plan': dmg.plan_summary(plan),
-            'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
-                     'multigrid setup), adjoint partitioned'}
+    return res
 
 
 # ------------------------------------------------------------------------------ own arm
@@ -592,9 +615,14 @@ def run_b200(args):
     if world > 1 and hg is not None and not args.dist_mg and args.dist_leg and grad_eval and 'error' not in grad_eval:
         import threading
 
+        partial = {}
+
         def on_timeout():
             if rank == 0:
-                out['grad_eval_dist'] = {'error': f'timeout after {args.dist_leg_timeout} s (watchdog)'}
+                leg_ = dict(partial) if partial else {}
+                leg_['error'] = f'timeout after {args.dist_leg_timeout} s (watchdog)' + \
+                                (' in the peer-memory part' if partial else '')
+                out['grad_eval_dist'] = leg_
                 print(json.dumps(out), flush=True)
             os._exit(0)
 
@@ -606,10 +634,17 @@ def run_b200(args):
             dist.broadcast_object_list(box, src=0)
             return box[0]
 
+        def allgather_obj(obj):
+            box = [None] * world
+            dist.all_gather_object(box, obj)
+            return box
+
         try:
             leg = distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, local_rank, opts, args.min_dist_nodes,
                                         dict(crds=crds_d, pq=pq_d, pb=pb_d, uu=uu_d, dc=dc_d, dq=dq_d),
-                                        barrier, max_over_ranks, bcast)
+                                        barrier, max_over_ranks, bcast,
+                                        allgather=(allgather_obj if args.dist_leg_p2p else None),
+                                        on_partial=partial.update)
         except Exception as e:   # an error on one rank only would leave the others in a collective: the watchdog ends them
             leg = {'error': f'{type(e).__name__}: {e}'}
         wd.cancel()
@@ -640,6 +675,8 @@ def main():
                          'solving redundantly on every rank')
     ap.add_argument('--no-dist-leg', dest='dist_leg', action='store_false',
                     help='N > 1: skip the extra distributed-multigrid gradient evaluation at the end')
+    ap.add_argument('--no-dist-leg-p2p', dest='dist_leg_p2p', action='store_false',
+                    help='that leg: skip the second solve with the exchanges over peer memory')
     ap.add_argument('--dist-leg-timeout', type=float, default=150.0, help='watchdog of that leg, seconds')
     ap.add_argument('--min-dist-nodes', type=int, default=20000,
                     help='multigrid levels with fewer nodes run replicated under --dist-mg')

@@ -215,10 +215,22 @@ typedef struct {
   const int32_t *peer_rank;          /* [n_peer] */
   const int32_t *send_ptr, *send_idx; /* [n_peer + 1], node ids of this level this rank owns and the peer reads */
   const int32_t *recv_ptr, *recv_idx; /* [n_peer + 1], node ids the peer owns and this rank's rows read */
+  const int32_t *remote_off;          /* [n_peer] or NULL: start of this rank's block in the peer's receive list
+                                       * (needed by the peer-memory path only) */
 } jsso_mg_halo_desc;
 int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
                      const int32_t* bounds_h, const jsso_mg_halo_desc* halo);
-/* out[0] = halo exchanges, out[1] = scalar all-reduces issued by the distributed solve so far. */
+/* Optional peer-memory path of the distributed solve (NVLink, CUDA IPC; the distributed CG's counterpart is
+ * jsso_p2p_export / jsso_p2p_connect): halo exchanges become a push kernel storing straight into the peers'
+ * receive arenas + a wait/unpack kernel, scalar all-reduces a mailbox kernel -- no library call on the iteration
+ * path (the two all-gathers per solve / iteration stay on NCCL).  Collective sequence after jsso_mg_set_dist:
+ * jsso_mg_p2p_reserve(max over ranks of the largest per-level receive count), jsso_mg_p2p_export (128 bytes per
+ * rank), exchange the bytes, jsso_mg_p2p_connect(all bytes, every rank's reserve value). */
+int jsso_mg_p2p_reserve(jsso_handle* h, int32_t max_recv_common);
+int jsso_mg_p2p_export(jsso_handle* h, uint8_t out[128]);
+int jsso_mg_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* max_recv_all);
+/* out[3]: halo exchanges and scalar all-reduces issued by the distributed solve so far, and whether they run over
+ * peer memory (1) or NCCL (0). */
 int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out);
 
 /* ---- adjoint sensitivity reduction ---------------------------------------------- */

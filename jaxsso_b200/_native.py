@@ -64,7 +64,7 @@ class MgLevelDesc(C.Structure):
 
 class MgHaloDesc(C.Structure):
     _fields_ = [('n_peer', C.c_int32)] + [(k, C.c_void_p) for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr',
-                                                                      'recv_idx')]
+                                                                      'recv_idx', 'remote_off')]
 
 PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
@@ -72,7 +72,7 @@ PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_mg_aggregate', 'jsso_mg_pattern_lists', 'jsso_assembly_tasks',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_gather_rows', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
-           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_mg_set_dist', 'jsso_mg_dist_counters', 'jsso_adjoint',
+           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_mg_set_dist', 'jsso_mg_p2p_reserve', 'jsso_mg_p2p_export', 'jsso_mg_p2p_connect', 'jsso_mg_dist_counters', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
@@ -121,6 +121,9 @@ def lib():
     L.jsso_mg_setup.argtypes = [vp, i32, C.POINTER(MgLevelDesc)]
     L.jsso_mg_set_dist.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(MgHaloDesc)]
     L.jsso_mg_dist_counters.argtypes = [vp, vp]
+    L.jsso_mg_p2p_reserve.argtypes = [vp, i32]
+    L.jsso_mg_p2p_export.argtypes = [vp, vp]
+    L.jsso_mg_p2p_connect.argtypes = [vp, vp, vp]
     L.jsso_adjoint.argtypes = [vp] + [vp] * 8 + [vp]
     L.jsso_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_backward.argtypes = [vp] + [vp] * 9 + [C.POINTER(SolveOpts), C.POINTER(Stats), vp]
@@ -422,16 +425,30 @@ class Handle:
         keep = []
         for d, lv in zip(descs, mine):
             d.n_peer = int(lv['peer_rank'].shape[0])
-            for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr', 'recv_idx'):
+            for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr', 'recv_idx', 'remote_off'):
                 a = np.ascontiguousarray(lv[k], dtype=np.int32)
                 keep.append(a)
                 setattr(d, k, a.ctypes.data)
         idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
         self._ck(lib().jsso_mg_set_dist(self.h, _ptr(idb), int(rank), int(n_rank), int(n_dist), _ptr(bounds), descs))
 
+    def mg_p2p_connect(self, plan, allgather):
+        """Switch the distributed multigrid solve to the peer-memory exchange (collective).  `allgather(bytes)` returns
+        the list of every rank's bytes in rank order (e.g. torch.distributed.all_gather_object)."""
+        from . import dist_multigrid
+        common = dist_multigrid.common_max_recv(plan)
+        self._ck(lib().jsso_mg_p2p_reserve(self.h, common))
+        buf = np.zeros(128, np.uint8)
+        self._ck(lib().jsso_mg_p2p_export(self.h, _ptr(buf)))
+        blobs = allgather(buf.tobytes())
+        blob = np.frombuffer(b''.join(blobs), dtype=np.uint8).copy()
+        mr = np.full(plan['n_rank'], common, np.int32)
+        self._ck(lib().jsso_mg_p2p_connect(self.h, _ptr(blob), _ptr(mr)))
+
     def mg_dist_counters(self):
-        out = np.zeros(2, np.int64)
+        out = np.zeros(3, np.int64)
         self._ck(lib().jsso_mg_dist_counters(self.h, _ptr(out)))
+        self.mg_dist_p2p = bool(out[2])
         return int(out[0]), int(out[1])
 
     # ---- adjoint

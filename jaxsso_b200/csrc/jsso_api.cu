@@ -172,6 +172,9 @@ struct jsso_handle {
     std::vector<MgDistPeer> peers;
     int32_t *send_idx = nullptr, *recv_idx = nullptr;   // device: node ids of this level
     int n_send = 0, n_recv = 0;
+    std::vector<int32_t> remote_off;                    // where my block starts in each peer's receive list (nodes)
+    MgdLevelDev* dev = nullptr;                         // device copy for the peer-memory kernels
+    unsigned long long seq = 0;                         // exchange counter of this level
   };
   struct MgDist {
     int rank = 0, n_rank = 1, n_dist = 0;
@@ -180,6 +183,14 @@ struct jsso_handle {
     std::vector<MgDistLevel> lv;                // [n_dist]
     double *send_buf = nullptr, *recv_buf = nullptr;
     long long n_exchange = 0, n_allreduce = 0;
+    // peer-memory path (jsso_mg_p2p_export / jsso_mg_p2p_connect): mailbox + receive arena mapped into every peer
+    MgdMailbox* mbox = nullptr;
+    double* arena = nullptr;
+    size_t max_recv = 0;
+    MgdCtx* ctx = nullptr;              // device copy; null = NCCL send/recv path
+    unsigned* push_counter = nullptr;
+    unsigned long long red_seq = 0;
+    std::vector<void*> ipc_opened;
   } mgd;
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
@@ -425,6 +436,9 @@ void jsso_destroy(jsso_handle* h) {
     if (h->mg_scal_host) cudaFreeHost(h->mg_scal_host);
   }
   for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); }
+  for (auto& dl : h->mgd.lv) if (dl.dev) cudaFree(dl.dev);
+  for (void* p : h->mgd.ipc_opened) cudaIpcCloseMemHandle(p);
+  { void* pp[] = {h->mgd.mbox, h->mgd.arena, h->mgd.ctx, h->mgd.push_counter}; for (void* p : pp) if (p) cudaFree(p); }
   if (h->mgd.send_buf) cudaFree(h->mgd.send_buf);
   if (h->mgd.recv_buf) cudaFree(h->mgd.recv_buf);
   if (h->mgd.comm && g_nccl.ok) g_nccl.CommDestroy(h->mgd.comm);
@@ -1084,6 +1098,7 @@ extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int3
     }
     L.n_send = d.n_peer ? d.send_ptr[d.n_peer] : 0;
     L.n_recv = d.n_peer ? d.recv_ptr[d.n_peer] : 0;
+    if (d.remote_off) L.remote_off.assign(d.remote_off, d.remote_off + d.n_peer);
     std::vector<int32_t> si(d.send_idx, d.send_idx + L.n_send), ri(d.recv_idx, d.recv_idx + L.n_recv);
     for (int v : si) if (v < lo || v >= hi) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: send index not owned");
     for (int v : ri) if (v < 0 || v >= n_l || (v >= lo && v < hi)) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad receive index");
@@ -1092,6 +1107,7 @@ extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int3
     D.lv.push_back(L);
   }
   CK(dalloc(&D.send_buf, 6 * max_send)); CK(dalloc(&D.recv_buf, 6 * max_recv));
+  D.max_recv = max_recv;
   if (!nccl_load()) return fail(h, JSSO_ERR_NCCL, "libnccl.so.2 not found");
   ncclUniqueId id;
   std::memcpy(&id, nccl_id, 128);
@@ -1100,10 +1116,92 @@ extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int3
   return JSSO_OK;
 }
 
-// statistics of the distributed solve since jsso_mg_set_dist: out[0] = halo exchanges, out[1] = scalar all-reduces
+// Peer-memory halo exchange / all-reduce of the distributed multigrid solve (optional; after jsso_mg_set_dist).
+// export: 128 bytes = CUDA IPC handles of this rank's mailbox and receive arena; connect: everybody's 128 bytes.
+extern "C" int jsso_mg_p2p_export(jsso_handle* h, uint8_t out[128]) {
+  if (!h || !out) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  jsso_handle::MgDist& D = h->mgd;
+  if (D.n_rank < 2 || !D.comm) return fail(h, JSSO_ERR_STATE, "jsso_mg_p2p_export needs jsso_mg_set_dist first");
+  if (D.n_rank > P2P_MAX_RANKS || D.n_dist > MGD_MAX_LEVELS)
+    return fail(h, JSSO_ERR_STATE, "peer-memory multigrid: at most 16 ranks and 4 distributed levels");
+  for (const auto& L : D.lv)
+    if (L.remote_off.size() != L.peers.size() || L.peers.size() > (size_t)P2P_MAX_RANKS)
+      return fail(h, JSSO_ERR_STATE, "peer-memory multigrid: the plan has no remote offsets");
+  if (!D.mbox) {
+    CK(dalloc(&D.mbox, 1));
+    CK(cudaMemset(D.mbox, 0, sizeof(MgdMailbox)));
+    CK(dalloc(&D.arena, (size_t)MGD_MAX_LEVELS * 2 * 6 * std::max<size_t>(D.max_recv, 1)));
+    CK(dalloc(&D.push_counter, 1));
+    CK(cudaMemset(D.push_counter, 0, sizeof(unsigned)));
+  }
+  cudaIpcMemHandle_t a, b;
+  CK(cudaIpcGetMemHandle(&a, D.mbox));
+  CK(cudaIpcGetMemHandle(&b, D.arena));
+  std::memcpy(out, &a, 64);
+  std::memcpy(out + 64, &b, 64);
+  return JSSO_OK;
+}
+
+extern "C" int jsso_mg_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* max_recv_all) {
+  if (!h || !all_handles || !max_recv_all) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  jsso_handle::MgDist& D = h->mgd;
+  if (!D.mbox) return fail(h, JSSO_ERR_STATE, "jsso_mg_p2p_connect needs jsso_mg_p2p_export first");
+  // every rank sizes its arena by its own max_recv; the strides a pusher uses are the RECEIVER's, so all ranks
+  // agree on one stride: the maximum over the ranks
+  size_t mr = 0;
+  for (int r = 0; r < D.n_rank; ++r) mr = std::max(mr, (size_t)max_recv_all[r]);
+  if (mr > D.max_recv) {   // re-size my arena to the common stride (before anybody maps it: connect is collective)
+    return fail(h, JSSO_ERR_ARG, "jsso_mg_p2p_connect: export with the common max_recv (jsso_mg_p2p_reserve) first");
+  }
+  MgdCtx c;
+  std::memset(&c, 0, sizeof c);
+  c.rank = D.rank; c.n_rank = D.n_rank;
+  c.arena_slot_stride = 6LL * (long long)D.max_recv;
+  c.arena_level_stride = 2 * c.arena_slot_stride;
+  for (int r = 0; r < D.n_rank; ++r) {
+    if (r == D.rank) { c.mbox[r] = D.mbox; c.arena[r] = D.arena; continue; }
+    cudaIpcMemHandle_t mh, ah;
+    std::memcpy(&mh, all_handles + 128 * (size_t)r, 64);
+    std::memcpy(&ah, all_handles + 128 * (size_t)r + 64, 64);
+    void *pm = nullptr, *pa = nullptr;
+    CK(cudaIpcOpenMemHandle(&pm, mh, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&pa, ah, cudaIpcMemLazyEnablePeerAccess));
+    D.ipc_opened.push_back(pm); D.ipc_opened.push_back(pa);
+    c.mbox[r] = (MgdMailbox*)pm; c.arena[r] = (double*)pa;
+  }
+  for (auto& L : D.lv) {
+    MgdLevelDev ld;
+    std::memset(&ld, 0, sizeof ld);
+    ld.n_peer = (int)L.peers.size(); ld.n_send = L.n_send; ld.n_recv = L.n_recv;
+    for (int i = 0; i < ld.n_peer; ++i) {
+      ld.peer_rank[i] = L.peers[i].rank; ld.send_off[i] = L.peers[i].send_off; ld.send_cnt[i] = L.peers[i].send_cnt;
+      ld.remote_off[i] = L.remote_off[i];
+    }
+    CK(dalloc(&L.dev, 1));
+    CK(cudaMemcpy(L.dev, &ld, sizeof ld, cudaMemcpyHostToDevice));
+  }
+  CK(dalloc(&D.ctx, 1));
+  CK(cudaMemcpy(D.ctx, &c, sizeof c, cudaMemcpyHostToDevice));
+  return JSSO_OK;
+}
+
+// the arena stride must be the same on every rank: call with the maximum of max_recv over the ranks BEFORE export
+extern "C" int jsso_mg_p2p_reserve(jsso_handle* h, int32_t max_recv_common) {
+  if (!h || max_recv_common < 0) return JSSO_ERR_ARG;
+  if (h->mgd.mbox) return fail(h, JSSO_ERR_STATE, "jsso_mg_p2p_reserve after export");
+  h->mgd.max_recv = std::max(h->mgd.max_recv, (size_t)max_recv_common);
+  return JSSO_OK;
+}
+
+// statistics of the distributed solve since jsso_mg_set_dist: out[0] = halo exchanges, out[1] = scalar all-reduces,
+// out[2] = 1 if they run over peer memory (jsso_mg_p2p_connect), 0 over NCCL
 extern "C" int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out) {
   if (!h || !out) return JSSO_ERR_ARG;
-  out[0] = h->mgd.n_exchange; out[1] = h->mgd.n_allreduce;
+  out[0] = h->mgd.n_exchange; out[1] = h->mgd.n_allreduce; out[2] = h->mgd.ctx ? 1 : 0;
   return JSSO_OK;
 }
 
@@ -1440,6 +1538,17 @@ static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n) {
 static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st) {
   jsso_handle::MgDistLevel& d = h->mgd.lv[l];
   if (d.peers.empty()) return JSSO_OK;
+  if (h->mgd.ctx) {   // peer-memory path: two kernels, no library call
+    const unsigned long long seq = ++d.seq;
+    const int pb = std::max(1, std::min(32, cdiv(6LL * d.n_send, RED_BLOCK)));
+    mgd_push_kernel<<<pb, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.send_idx, v, h->mgd.push_counter, seq);
+    CKL("mgd_push_kernel");
+    const int ub = std::max(1, std::min(32, cdiv(6LL * d.n_recv, RED_BLOCK)));
+    mgd_wait_unpack_kernel<<<ub, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.recv_idx, v, seq);
+    CKL("mgd_wait_unpack_kernel");
+    ++h->mgd.n_exchange;
+    return JSSO_OK;
+  }
   if (d.n_send > 0) {
     halo_pack_kernel<<<cdiv(6LL * d.n_send, 256), 256, 0, st>>>(d.n_send, d.send_idx, v, h->mgd.send_buf);
     CKL("halo_pack_kernel");
@@ -1477,10 +1586,20 @@ static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st) {
 }
 
 // sum over the ranks of `count` device scalars starting at slot (in place), then read all scalars back
-static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st) {
-  CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
+static int mgd_reduce(jsso_handle* h, int slot, int count, cudaStream_t st) {
+  if (h->mgd.ctx) {
+    if (count > 2) return fail(h, JSSO_ERR_ARG, "peer-memory all-reduce: at most 2 scalars");
+    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + slot, count, ++h->mgd.red_seq);
+    CKL("mgd_allreduce_kernel");
+  } else {
+    CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
+  }
   ++h->mgd.n_allreduce;
-  return mg_read_scalars(h, st);
+  return JSSO_OK;
+}
+static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st) {
+  const int rc = mgd_reduce(h, slot, count, st);
+  return rc ? rc : mg_read_scalars(h, st);
 }
 
 static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, bool zero_guess, int deg, cudaStream_t st) {
@@ -1644,12 +1763,7 @@ static int mg_solve_async(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
   const int vb = std::max(1, std::min(h->red_blocks, cdiv(n, 256)));
   double *b = h->vb, *x = h->vx, *r = h->vr, *p = h->vp, *q = h->vq, *z = h->tmp_g;
   const MgMat A = mg_matrix(h, 0);
-  auto reduce = [&](int slot, int count) -> int {
-    if (!dist) return JSSO_OK;
-    CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
-    ++h->mgd.n_allreduce;
-    return JSSO_OK;
-  };
+  auto reduce = [&](int slot, int count) -> int { return dist ? mgd_reduce(h, slot, count, st) : JSSO_OK; };
   if (use_x0) {
     if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;
   } else {

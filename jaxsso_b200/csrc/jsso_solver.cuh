@@ -543,6 +543,89 @@ p2p_halo_push_kernel(const P2PCtx* c, const int32_t* __restrict__ send_idx, cons
   }
 }
 
+// ---- peer-memory halo exchange and scalar all-reduce of the row-range distributed multigrid solve ----------
+// (jsso_mg_p2p_connect; the NCCL send/recv path stays as the reference.)  An exchange of level l is two kernels
+// and no library call: mgd_push_kernel gathers this rank's entries and stores them straight into the peers'
+// receive arenas over NVLink, then raises halo[l][me] = seq in their mailboxes (release); mgd_wait_unpack_kernel
+// spins on its own mailbox (acquire) and scatters the arena into the vector's ghost positions.  The arena is
+// double-buffered per level by the parity of the level's exchange counter.  Why that suffices: a rank pushes
+// exchange k+2 of a level only after its wait of exchange k+1 saw every peer's flag k+1, and a peer raises flag k+1
+// (in its push kernel) only after its unpack of exchange k has finished (stream order) -- peers are symmetric and
+// raise the flag even when they have nothing to send.  The all-reduce follows the same pattern all-to-all.
+constexpr int MGD_MAX_LEVELS = 4;
+struct MgdMailbox {
+  unsigned long long halo[MGD_MAX_LEVELS][P2P_MAX_RANKS];
+  unsigned long long red_tag[2][P2P_MAX_RANKS];
+  double red_val[2][P2P_MAX_RANKS][2];
+};
+struct MgdCtx {
+  int rank, n_rank;
+  MgdMailbox* mbox[P2P_MAX_RANKS];     // by rank (own entry = local mailbox)
+  double* arena[P2P_MAX_RANKS];        // by rank: receive arena, [level][parity][6 * max_recv]
+  long long arena_level_stride, arena_slot_stride;   // doubles
+};
+struct MgdLevelDev {                   // one distributed level, device copy
+  int n_peer, n_send, n_recv;
+  int peer_rank[P2P_MAX_RANKS], send_off[P2P_MAX_RANKS], send_cnt[P2P_MAX_RANKS], remote_off[P2P_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(RED_BLOCK)
+mgd_push_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const int32_t* __restrict__ send_idx,
+                const double* __restrict__ v, unsigned* counter, unsigned long long seq) {
+  __shared__ bool last;
+  const long long slot = (long long)level * c->arena_level_stride + (long long)(seq & 1ull) * c->arena_slot_stride;
+  for (int pi = 0; pi < L->n_peer; ++pi) {
+    double* dst = c->arena[L->peer_rank[pi]] + slot + 6 * (long long)L->remote_off[pi];
+    const int32_t* idx = send_idx + L->send_off[pi];
+    const int n = 6 * L->send_cnt[pi];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+      dst[t] = v[6 * (size_t)idx[t / 6] + t % 6];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < L->n_peer) {
+    __threadfence();
+    st_release_sys(&c->mbox[L->peer_rank[threadIdx.x]]->halo[level][c->rank], seq);
+  }
+}
+
+__global__ void __launch_bounds__(RED_BLOCK)
+mgd_wait_unpack_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const int32_t* __restrict__ recv_idx,
+                       double* __restrict__ v, unsigned long long seq) {
+  if ((int)threadIdx.x < L->n_peer) {
+    const MgdMailbox* m = c->mbox[c->rank];
+    while (ld_acquire_sys(&m->halo[level][L->peer_rank[threadIdx.x]]) < seq) { }
+  }
+  __syncthreads();
+  const double* src = c->arena[c->rank] + (long long)level * c->arena_level_stride +
+                      (long long)(seq & 1ull) * c->arena_slot_stride;
+  const int n = 6 * L->n_recv;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    v[6 * (size_t)recv_idx[t / 6] + t % 6] = ld_relaxed_sys_f64(src + t);
+}
+
+// scal[0..count) <- sum over the ranks (rank order: bitwise identical everywhere); one block, count <= 2
+__global__ void mgd_allreduce_kernel(const MgdCtx* c, double* scal, int count, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < c->n_rank; ++r)
+      for (int k = 0; k < count; ++k) st_relaxed_sys_f64(&c->mbox[r]->red_val[par][c->rank][k], scal[k]);
+    __threadfence_system();
+    for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->red_tag[par][c->rank], seq);
+    const MgdMailbox* m = c->mbox[c->rank];
+    double acc[2] = {0.0, 0.0};
+    for (int r = 0; r < c->n_rank; ++r) {
+      while (ld_acquire_sys(&m->red_tag[par][r]) < seq) { }
+      for (int k = 0; k < count; ++k) acc[k] += ld_relaxed_sys_f64(&m->red_val[par][r][k]);
+    }
+    for (int k = 0; k < count; ++k) scal[k] = acc[k];
+  }
+}
+
 // ---- persistent CG (single GPU) ------------------------------------------------------
 // All iterations of a batch in ONE cooperative launch: the three phases of an iteration are
 // separated by grid-wide barriers instead of kernel boundaries (the 3-kernel loop is launch

@@ -116,9 +116,17 @@ def rank_plan(plan, rank):
         recv = [need[rank][s] for s in peers]
         cat = lambda xs: (np.concatenate(xs) if xs else np.zeros(0)).astype(np.int32)
         ptr = lambda xs: np.concatenate([[0], np.cumsum([x.size for x in xs])]).astype(np.int32)
+        # peer-memory path: where my block starts in each peer's receive list (its peers in ascending rank order)
+        remote_off = [int(sum(need[s][q].size for q in range(rank) if q != s)) for s in peers]
         out.append(dict(peer_rank=np.array(peers, np.int32), send_ptr=ptr(send), send_idx=cat(send),
-                        recv_ptr=ptr(recv), recv_idx=cat(recv)))
+                        recv_ptr=ptr(recv), recv_idx=cat(recv), remote_off=np.array(remote_off, np.int32)))
     return out
+
+
+def common_max_recv(plan):
+    """Largest number of nodes any rank receives in one exchange of any level (the stride of the peer-memory
+    receive arenas, which must be the same on every rank)."""
+    return int(max([sum(x.size for x in need[r]) for need in plan['need'] for r in range(plan['n_rank'])] + [1]))
 
 
 def plan_summary(plan):

@@ -1,7 +1,7 @@
 """Row-range distributed multigrid solve (jsso_mg_set_dist) on N GPUs against the single-GPU multigrid solve of
 the same system.  Launch:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      scripts/dist_mg_check.py [SIZE] [MIN_DIST_NODES] [CHEB_DEGREE]
+      scripts/dist_mg_check.py [SIZE] [MIN_DIST_NODES] [CHEB_DEGREE] [p2p]
 Every rank builds the whole renumbered mesh, assembles it, and solves K u = f with the V-cycle PCG distributed by
 row ranges; rank 0 then repeats the solve on an undistributed handle.  Prints `DIST_MG_CHECK {...json...}` on
 rank 0 and exits non-zero on mismatch."""
@@ -26,6 +26,7 @@ dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 min_dist = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 deg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+use_p2p = len(sys.argv) > 4 and sys.argv[4] == 'p2p'    # exchanges over peer memory (jsso_mg_p2p_connect) instead of NCCL
 rtol = 1e-10
 nat.lib().jsso_set_device(local)
 md0 = meshes.plate(size)
@@ -45,6 +46,12 @@ def solve(distributed):
         ids = [nat.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         h.mg_set_dist(ids[0], rank, world, plan)
+        if use_p2p:
+            def allgather(obj):
+                box = [None] * world
+                dist.all_gather_object(box, obj)
+                return box
+            h.mg_p2p_connect(plan, allgather)
         info = dmg.plan_summary(plan)
     crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
     u = D((md.ndof,))
@@ -79,7 +86,7 @@ if rank == 0:
     _, u0, *_ = h0.value_and_grad_host(md0.crds, md0.prop_quads, md0.prop_beams, md0.loads,
                                        opts=nat.make_opts(rtol=1e-11, precond='block_jacobi'))
     e0 = np.linalg.norm(ud.reshape(-1, 6) - u0.reshape(-1, 6)[perm]) / np.linalg.norm(u0)
-    res = {'world': world, 'size': size, 'cheb_degree': deg, 'u_err_vs_single_mg': eu, 'u_err_vs_block_jacobi': e0,
+    res = {'world': world, 'size': size, 'cheb_degree': deg, 'peer_memory': use_p2p, 'u_err_vs_single_mg': eu, 'u_err_vs_block_jacobi': e0,
            'iters_dist': std.iterations, 'iters_single': sts.iterations, 'relres_dist': std.relres,
            'seconds_dist': dtd, 'seconds_single': dts, 'same_on_all_ranks': same, 'plan': info,
            'exchanges': cnt[0], 'allreduces': cnt[1]}

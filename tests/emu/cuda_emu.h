@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -178,6 +179,16 @@ void launch(G grid_, B block_, size_t smem, F&& body_) {
   if (capturing) {
     capturing->nodes.push_back(GraphNode{dimx(grid_), dimx(block_), smem, std::function<void()>(body_)});
     return;
+  }
+  {
+    // EMU_JITTER=<max microseconds>: a random pause before every launch, different per rank thread, so that the
+    // peer-memory protocols (flags, double-buffered arenas) are exercised with ranks running far ahead of each other
+    static const int jitter = [] { const char* e = std::getenv("EMU_JITTER"); return e ? std::atoi(e) : 0; }();
+    if (jitter > 0) {
+      static thread_local unsigned long long rs = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&rs;
+      rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17;
+      if ((rs & 7) == 0) std::this_thread::sleep_for(std::chrono::microseconds(rs % (unsigned)jitter));
+    }
   }
   const unsigned grid = dimx(grid_), block = dimx(block_);
   const unsigned n_warp = (block + 31) / 32;

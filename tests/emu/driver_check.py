@@ -46,17 +46,27 @@ def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=8):
     if precond == 'multigrid':
         levels = h.mg_setup(max_coarse_nodes=max_coarse)
         if dist is not None:
-            nid, rank, world, bounds, min_dist = dist
+            nid, rank, world, bounds, min_dist = dist[:5]
             rp, ci = h.pattern()
             plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist)
             h.mg_set_dist(nid, rank, world, plan)
+            if len(dist) > 5 and dist[5] is not None:      # peer-memory exchange: gather the IPC bytes between the threads
+                box, bar = dist[5]
+
+                def allgather(b):
+                    box[rank] = b
+                    bar.wait()
+                    out_ = list(box)
+                    bar.wait()
+                    return out_
+                h.mg_p2p_connect(plan, allgather)
             info = dmg.plan_summary(plan)
     crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
     u = D((md.ndof,))
     st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond=precond, cheb_degree=deg))
     out = u.download()
     if dist is not None:
-        cnt = h.mg_dist_counters()
+        cnt = h.mg_dist_counters() + (h.mg_dist_p2p,)
     h.close()
     return out, st.iterations, bool(st.converged), st.relres, info, cnt
 
@@ -101,6 +111,7 @@ def main():
                'mg_launches': mg_launches}
     elif mode == 'dist':
         world, size, min_dist, deg = (int(a) for a in sys.argv[2:6])
+        p2p = (([None] * world, threading.Barrier(world)) if (len(sys.argv) > 6 and sys.argv[6] == 'p2p') else None)
         md0 = meshes.plate(size)
         owner = partition.rcb_owner(md0.crds[:, :2], world)
         perm, bounds = dmg.owner_permutation(owner, world)
@@ -109,7 +120,7 @@ def main():
         out = [None] * world
 
         def worker(rank):
-            out[rank] = solve(md, 'multigrid', deg, dist=(nid, rank, world, bounds, min_dist))
+            out[rank] = solve(md, 'multigrid', deg, dist=(nid, rank, world, bounds, min_dist, p2p))
 
         th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
         for t in th:
@@ -123,7 +134,7 @@ def main():
                'err_vs_single': float(max(np.linalg.norm(o[0] - us) for o in out) / np.linalg.norm(us)),
                'identical_on_all_ranks': all(np.array_equal(o[0], out[0][0]) for o in out),
                'err_vs_oracle': float(np.linalg.norm(out[0][0].reshape(-1, 6) - uref.reshape(-1, 6)[perm]) / np.linalg.norm(uref)),
-               'plan': out[0][4], 'exchanges': out[0][5][0], 'allreduces': out[0][5][1]}
+               'plan': out[0][4], 'exchanges': out[0][5][0], 'allreduces': out[0][5][1], 'peer_memory': bool(out[0][5][2])}
     elif mode == 'part':
         # the partitioned path that IS measured on hardware (scripts/dist_check.py: set_halo + distributed block-Jacobi
         # CG over NCCL send/recv, partitioned adjoint) on rank threads: calibrates the fake NCCL against a known-good path
@@ -202,8 +213,15 @@ def main():
                 bar.wait()
                 return shared['id']
 
+            def allgather(obj):
+                shared.setdefault('box', [None] * world)[rank] = obj
+                bar.wait()
+                got = list(shared['box'])
+                bar.wait()
+                return got
+
             leg = bench.distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, 0, opts, min_dist, dev, bar.wait,
-                                              max_over_ranks, bcast)
+                                              max_over_ranks, bcast, allgather=allgather)
             out[rank] = (leg, lm.l2g[:lm.n_owned], dev['dc'].download()[:lm.n_owned], lm.quad_ids, dev['dq'].download())
 
         import jaxsso_b200.multigrid as mgmod

@@ -117,6 +117,9 @@ def test_bench_distributed_leg_on_rank_threads(emu_api):
     assert leg['u_rel_diff_vs_replicated_solve'] <= 1e-8
     assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
     assert leg['plan']['n_dist'] == 2 and leg['halo_exchanges'] > 0
+    pm = leg['peer_memory']
+    assert 'error' not in pm and pm['active'] and pm['pcg_iterations'] == leg['pcg_iterations']
+    assert pm['u_rel_diff_vs_replicated_solve'] <= 1e-8
 
 
 def test_device_scalar_pcg_single_and_distributed(emu_api):
@@ -168,3 +171,20 @@ def test_graph_captured_vcycle(emu_api):
     d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_GRAPH': '1'})
     assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
     assert all(i == d['iters_single'] for i in d['iters_dist'])
+
+
+@pytest.mark.parametrize('world,size,min_dist,deg,env', [
+    (2, 12, 10, 1, {}), (4, 12, 10, 1, {'EMU_JITTER': '3000'}),
+    (4, 16, 10, 2, {'JSSO_MG_ASYNC': '3', 'JSSO_MG_GRAPH': '1', 'EMU_JITTER': '1000'})])
+def test_peer_memory_distributed_multigrid(emu_api, world, size, min_dist, deg, env):
+    """jsso_mg_p2p_connect: halo exchanges as push + wait/unpack kernels over "peer memory" (stores into the peers'
+    double-buffered receive arenas, release/acquire flags) and mailbox all-reduces, no NCCL on the iteration path.
+    The rank threads' launches run concurrently, so the kernels really spin on flags set by another rank's kernel;
+    EMU_JITTER pauses every rank at random before launches so that ranks run far ahead of each other (with a
+    SINGLE-buffered arena this stress makes the solve fail -- checked by hand -- with the double buffer it stays
+    bit-identical).  Same iterations as the undistributed solve, identical u on every rank."""
+    res = run(emu_api, 'dist', world, size, min_dist, deg, 'p2p', env=env)
+    assert res['peer_memory'] and res['converged'] and res['identical_on_all_ranks']
+    k = int(env.get('JSSO_MG_ASYNC', '1'))
+    assert all(res['iters_single'] <= i <= res['iters_single'] + k - 1 + 1 for i in res['iters_dist'])
+    assert res['err_vs_single'] <= 1e-10 and res['err_vs_oracle'] <= 1e-8

@@ -28,15 +28,16 @@ def test_partitioned_equals_single(world):
 
 
 @pytest.mark.unverified
+@pytest.mark.parametrize('p2p', ['', 'p2p'])
 @pytest.mark.parametrize('world,min_dist', [(2, 500), (2, 100000), (4, 500), (8, 500)])
-def test_distributed_multigrid_equals_single(world, min_dist):
+def test_distributed_multigrid_equals_single(world, min_dist, p2p):
     """Row-range distributed V-cycle PCG (jsso_mg_set_dist): same u and iteration count as the single-GPU
     multigrid solve; min_dist 500 distributes two levels at 96^2, 100000 only the fine one."""
     if nat.lib().jsso_device_count() < world:
         pytest.skip(f'needs {world} GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
            '--master-addr', '127.0.0.1', '--master-port', str(29530 + world),
-           os.path.join(ROOT, 'scripts', 'dist_mg_check.py'), '96', str(min_dist), '1']
+           os.path.join(ROOT, 'scripts', 'dist_mg_check.py'), '96', str(min_dist), '1'] + ([p2p] if p2p else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith('DIST_MG_CHECK')]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
