@@ -1589,7 +1589,8 @@ static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st) {
 static int mgd_reduce(jsso_handle* h, int slot, int count, cudaStream_t st) {
   if (h->mgd.ctx) {
     if (count > 2) return fail(h, JSSO_ERR_ARG, "peer-memory all-reduce: at most 2 scalars");
-    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + slot, count, ++h->mgd.red_seq);
+    const unsigned long long seq = ++h->mgd.red_seq;
+    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + slot, count, seq);
     CKL("mgd_allreduce_kernel");
   } else {
     CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));

@@ -79,7 +79,10 @@ def rewrite_launches(src):
         assert src[e + 1] == ';', src[e:e + 20]
         smem = cfg[2] if len(cfg) > 2 else '0'
         out.append(src[pos:start])
-        out.append(f'emu::launch({cfg[0]}, {cfg[1]}, {smem}, [=] {{ {name}({args}); }});')   # by value, like a launch
+        # the arguments are evaluated ONCE, at launch, and copied (CUDA semantics): an argument expression with a side
+        # effect inside the per-thread closure would run once per emulated thread
+        out.append(f'{{ auto emu_args_ = std::make_tuple({args}); emu::launch({cfg[0]}, {cfg[1]}, {smem}, '
+                   f'[=] {{ std::apply([](auto... a_) {{ {name}(a_...); }}, emu_args_); }}); }}')
         pos = e + 2
         n += 1
     out.append(src[pos:])

@@ -73,6 +73,9 @@ def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=8):
 
 def main():
     mode = sys.argv[1]
+    if os.environ.get('EMU_DEBUG_HANG'):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['EMU_DEBUG_HANG']), exit=True)
     if mode == 'grad':
         md = mixed(int(sys.argv[2]))
         h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
@@ -120,7 +123,13 @@ def main():
         out = [None] * world
 
         def worker(rank):
-            out[rank] = solve(md, 'multigrid', deg, dist=(nid, rank, world, bounds, min_dist, p2p))
+            try:
+                out[rank] = solve(md, 'multigrid', deg, dist=(nid, rank, world, bounds, min_dist, p2p))
+            except BaseException as e:      # the other ranks would wait for this one forever
+                import traceback
+                print(f'EMU_RANK_ERROR rank {rank}: {e}', flush=True)
+                traceback.print_exc()
+                os._exit(3)
 
         th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
         for t in th:
