@@ -31,7 +31,14 @@ for f in ('gpurun_out/r2_b1.json', 'gpurun_out/r2_b1_fp16.json'):
     except Exception as e:
         print(f, 'failed', e)
 PY
+# peer-memory variant of the distributed multigrid exchanges + the partitioned checks (2 GPUs)
 NG=$(python -c "from jaxsso_b200 import _native as n; print(n.lib().jsso_device_count())")
+if [ "$NG" -ge 2 ]; then
+  for extra in "" "p2p"; do
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 \
+      scripts/dist_mg_check.py 96 500 1 $extra 2>&1 | grep DIST_MG_CHECK
+  done
+fi
 if [ "$NG" -ge 2 ]; then
   for extra in "" "--dist-mg"; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 \
