@@ -677,7 +677,7 @@ def main():
                     help='N > 1: skip the extra distributed-multigrid gradient evaluation at the end')
     ap.add_argument('--no-dist-leg-p2p', dest='dist_leg_p2p', action='store_false',
                     help='that leg: skip the second solve with the exchanges over peer memory')
-    ap.add_argument('--dist-leg-timeout', type=float, default=150.0, help='watchdog of that leg, seconds')
+    ap.add_argument('--dist-leg-timeout', type=float, default=240.0, help='watchdog of that leg, seconds')
     ap.add_argument('--min-dist-nodes', type=int, default=20000,
                     help='multigrid levels with fewer nodes run replicated under --dist-mg')
     ap.add_argument('--rtol', type=float, default=1e-8)
