@@ -381,7 +381,7 @@ def run_b200(args):
     mg_info = None
     hg = None
     if world > 1 and args.solve and args.precond != 'block_jacobi':
-        # N > 1: the multigrid tier is single-GPU, and the solve is > 99 % of a gradient evaluation, so every
+        # N > 1 (measured default): the solve is > 99 % of a gradient evaluation, so every
         # rank keeps a handle of the WHOLE mesh and runs the multigrid solve redundantly (1.2 ms of redundant
         # assembly, no communication); Ke+assembly+adjoint of the metric stay partitioned.  --precond
         # block_jacobi runs the distributed CG (halo pushes over NVLink peer memory) instead.
