@@ -203,7 +203,9 @@ int jsso_pcg(jsso_handle* h, const double* b_d, double* x_d, const jsso_solve_op
  * is rebuilt inside the first solve after each assembly. */
 int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_level_desc* levels);
 
-/* Row-range distribution of the multigrid-preconditioned solve over N GPUs (one process per GPU; SURVEY 8(e):
+/* (No counterpart in the reference: it solves K_aug u_aug = f_aug with one SuperLU factorisation on the host,
+ * JaxSSO/solver.py:176-210, selected in model.py:340-356; this is how the same u is reached on several GPUs.)
+ * Row-range distribution of the multigrid-preconditioned solve over N GPUs (one process per GPU; SURVEY 8(e):
  * "PCG per iteration: halo exchange ... overlapped", 8(f) rank 1).  The handle holds the WHOLE mesh, renumbered
  * so that every rank's nodes are one contiguous range (jaxsso_b200/dist_multigrid.py), with the hierarchy already
  * uploaded; assembly and the numeric multigrid setup stay replicated, the V-cycle and PCG products are computed
