@@ -302,6 +302,12 @@ void* jsso_event_create(void);
 int jsso_event_record(void* ev, void* stream);
 int jsso_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out); /* syncs on ev_stop */
 void jsso_event_destroy(void* ev);
+/* Measured FP64 peak of the device (DFMA chains, 8 per thread, 4 x 256 threads per SM) sustained for about
+ * `seconds`: the denominator of the FP64-bound rooflines (quad adjoint, K_e) in bench.py.  No reference
+ * counterpart (measurement infrastructure, SURVEY 8(d) "measure the FP64 DFMA peak yourself"). */
+int jsso_fp64_peak(int32_t device, double seconds, double* tflops_out, double* seconds_out);
+/* cudaProfilerStart (1) / cudaProfilerStop (0): range markers for `ncu --profile-from-start off`. */
+int jsso_profiler_range(int start);
 /* Number of kernels this library has launched since load (bench `gpu_launches`). */
 int64_t jsso_launch_count(void);
 

@@ -77,7 +77,7 @@ SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
            'jsso_memset', 'jsso_stream_sync', 'jsso_device_count', 'jsso_event_create',
-           'jsso_event_record', 'jsso_event_elapsed_ms', 'jsso_event_destroy', 'jsso_launch_count']
+           'jsso_event_record', 'jsso_event_elapsed_ms', 'jsso_event_destroy', 'jsso_launch_count', 'jsso_fp64_peak', 'jsso_profiler_range']
 
 _lib = None
 
@@ -156,6 +156,8 @@ def lib():
     L.jsso_event_destroy.argtypes = [vp]
     L.jsso_event_destroy.restype = None
     L.jsso_launch_count.argtypes = []
+    L.jsso_profiler_range.argtypes = [C.c_int]
+    L.jsso_fp64_peak.argtypes = [i32, dbl, C.POINTER(dbl), C.POINTER(dbl)]
     L.jsso_launch_count.restype = i64
     _lib = L
     return L
@@ -531,6 +533,15 @@ def gather_rows(src, idx, width, out=None, stream=None):
     if rc:
         raise JssoError(rc, 'jsso_gather_rows')
     return out
+
+
+def fp64_peak(device=0, seconds=1.0):
+    """Measured FP64 DFMA peak in TFLOP/s (jsso_fp64_peak)."""
+    tf, sec = C.c_double(), C.c_double()
+    rc = lib().jsso_fp64_peak(device, seconds, C.byref(tf), C.byref(sec))
+    if rc:
+        raise JssoError(rc, 'jsso_fp64_peak')
+    return float(tf.value), float(sec.value)
 
 
 def nccl_unique_id():

@@ -345,24 +345,43 @@ __global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = v;
 }
-// ---- PCG with the scalars kept on the device (opt-in asynchronous driver, JSSO_MG_ASYNC): slots of `scal`
-constexpr int MGS_BB = 1, MGS_RR = 2, MGS_RZ = 3, MGS_PQ = 4, MGS_RZ_OLD = 6;
+// ---- outer PCG with the scalars kept on the device (slots: MGS_* in jsso_solver.cuh)
 // p = z + (rz / rz_old) p   (first: p = z)
 __global__ void mg_pcg_dir_kernel(long long n, const double* __restrict__ z, double* __restrict__ p,
                                   const double* __restrict__ scal, int first) {
+  if (mgs_stopped(scal)) return;
   const double beta = first ? 0.0 : scal[MGS_RZ] / scal[MGS_RZ_OLD];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = first ? z[i] : z[i] + beta * p[i];
 }
-// alpha = rz / pq;  x += alpha p;  r -= alpha q;  then rz_old = rz (nobody reads rz_old in this kernel)
-__global__ void mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __restrict__ q,
-                                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ scal) {
-  const double alpha = scal[MGS_RZ] / scal[MGS_PQ];
+// alpha = rz / pq;  x += alpha p;  r -= alpha q;  *rr_out = r.r;  the block that finalises the sum also latches
+// rz_old = rz and counts the iteration (it runs after every block has read alpha and passed the stop test).
+// Non-positive curvature or r.z (matrix or preconditioner not SPD) poisons r.r with NaN, which stops everything.
+__global__ void __launch_bounds__(256)
+mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __restrict__ q,
+                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ scal,
+                     double* partials, unsigned* counter, double* rr_out) {
+  if (mgs_stopped(scal)) return;
+  const double rz = scal[MGS_RZ], pq = scal[MGS_PQ];
+  const double alpha = rz / pq;
+  double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     x[i] = fma(alpha, p[i], x[i]);
-    r[i] = fma(-alpha, q[i], r[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    acc = fma(ri, ri, acc);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal[MGS_RZ_OLD] = scal[MGS_RZ];
+  double total;
+  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
+    *rr_out = (pq > 0.0 && rz > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
+    scal[MGS_RZ_OLD] = rz;
+    scal[MGS_ITER] += 1.0;
+  }
+}
+// scal[MGS_TOL] = rtol^2 |b|^2 and the iteration counter (start of a solve; one thread)
+__global__ void mg_pcg_begin_kernel(double* scal, double rtol2, int reset_iter) {
+  scal[MGS_TOL] = rtol2 * scal[MGS_BB];
+  if (reset_iter) scal[MGS_ITER] = 0.0;
 }
 // FP64 column-major blocks a[36 s + 6 j + i] -> FP32 row-pair-major blocks b[36 s + 12 sub + 2 j + r],
 // i = 2 sub + r (the layout bsr_row_product<float> reads with 16-byte loads)

@@ -22,6 +22,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
+#ifndef JSSO_SPMV_PAIRED
+#define JSSO_SPMV_PAIRED 1   // FP32 / binary16 level SpMVs: two rows per warp iteration (bsr_rows_paired)
+#endif
+
 namespace jsso {
 
 // Device-resident CG state.  There is no stored "done" flag: every kernel derives
@@ -386,13 +392,15 @@ __device__ inline void bsr_row_product(int r, int lane, const int32_t* __restric
 // Software-pipelined row loop of a warp: rows r, r + n_warp, ...; `body(r, u0, u1)` consumes a row's
 // product (lanes 0..2).  rowptr is loaded two rows ahead and colidx one row ahead, so that per row only
 // the matrix / x loads are on the critical path (one memory latency instead of three).
+// A body that returns double has its values summed per lane and returned (dot products fused into an epilogue).
 template <class VT, class Body>
-__device__ inline void bsr_rows_pipelined(int warp, int n_warp, int lane, int n_row,
+__device__ inline double bsr_rows_pipelined(int warp, int n_warp, int lane, int n_row,
                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                           const VT* __restrict__ vals, const double* __restrict__ x, Body body) {
   constexpr int U = RowU<VT>::U;
   int r = warp;
-  if (r >= n_row) return;
+  double acc = 0.0;
+  if (r >= n_row) return acc;
   int b0 = rowptr[r], b1 = rowptr[r + 1];
   int ci[U];
   row_colidx(lane, b0, b1, colidx, ci, vals);
@@ -408,11 +416,122 @@ __device__ inline void bsr_rows_pipelined(int warp, int n_warp, int lane, int n_
     if (r2 < n_row) { nnb0 = rowptr[r2]; nnb1 = rowptr[r2 + 1]; }
     double u0, u1;
     bsr_row_product(b0, b1, ci, lane, colidx, vals, x, u0, u1);
-    body(r, u0, u1);
+    if constexpr (std::is_void<decltype(body(r, u0, u1))>::value) body(r, u0, u1);
+    else acc += body(r, u0, u1);
     b0 = nb0; b1 = nb1; nb0 = nnb0; nb1 = nnb1;
 #pragma unroll
     for (int u = 0; u < U; ++u) ci[u] = nci[u];
   }
+  return acc;
+}
+
+// ---- two rows per warp iteration (FP32 / binary16 block storage) --------------------------------------------
+// With half or a quarter of the bytes per row the one-row pipeline above is bound by memory latency, not bandwidth
+// (ncu, 1M quads: long-scoreboard stalls 12 warps per issue, 4.4 TB/s): the loads of TWO rows (r and r + n_warp)
+// are issued before the first FMA, which doubles the bytes in flight per warp at the same occupancy.
+template <class VT> struct RowRaw;
+template <> struct RowRaw<float> { float4 a[3]; double2 xv[3]; };
+template <> struct RowRaw<__half> { uint2 a[3]; double2 xv[3]; };
+__device__ inline void row_issue(int b0, const int (&ci)[3], int lane, const float* __restrict__ vals,
+                                 const double* __restrict__ x, RowRaw<float>& q) {
+  const int kb = lane / 9, rem = lane - 9 * kb, cp = rem / 3, sub = rem - 3 * cp;
+  const float4* base = (const float4*)(vals + (size_t)b0 * 36) + 3 * sub + cp + 9 * kb;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const bool ok = ci[u] >= 0;
+    q.a[u] = ok ? __ldg(base + 27 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    q.xv[u] = ok ? *(const double2*)(x + 6 * (size_t)ci[u] + 2 * cp) : make_double2(0.0, 0.0);
+  }
+}
+__device__ inline void row_issue(int b0, const int (&ci)[3], int lane, const __half* __restrict__ vals,
+                                 const double* __restrict__ x, RowRaw<__half>& q) {
+  const int kb = lane / 9, rem = lane - 9 * kb, cp = rem / 3, sub = rem - 3 * cp;
+  const uint2* base = (const uint2*)(vals + (size_t)b0 * 36) + 3 * sub + cp + 9 * kb;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const bool ok = ci[u] >= 0;
+    q.a[u] = ok ? __ldg(base + 27 * u) : make_uint2(0u, 0u);
+    q.xv[u] = ok ? *(const double2*)(x + 6 * (size_t)ci[u] + 2 * cp) : make_double2(0.0, 0.0);
+  }
+}
+__device__ inline float4 row_block_f32(const float4 v) { return v; }
+__device__ inline float4 row_block_f32(const uint2 v) {
+  float4 f;
+  half4_to_float(v, f.x, f.y, f.z, f.w);
+  return f;
+}
+template <class VT>
+__device__ inline void row_finish(const RowRaw<VT>& q, double& u0, double& u1) {
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const float4 a = row_block_f32(q.a[u]);
+    acc0 = fma((double)a.x, q.xv[u].x, acc0); acc0 = fma((double)a.z, q.xv[u].y, acc0);
+    acc1 = fma((double)a.y, q.xv[u].x, acc1); acc1 = fma((double)a.w, q.xv[u].y, acc1);
+  }
+  const double s0 = acc0 + __shfl_down_sync(0xffffffffu, acc0, 12);
+  const double s1 = acc1 + __shfl_down_sync(0xffffffffu, acc1, 12);
+  const double t0 = s0 + __shfl_down_sync(0xffffffffu, s0, 6);
+  const double t1 = s1 + __shfl_down_sync(0xffffffffu, s1, 6);
+  u0 = t0 + __shfl_down_sync(0xffffffffu, t0, 3);
+  u1 = t1 + __shfl_down_sync(0xffffffffu, t1, 3);
+  u0 += __shfl_down_sync(0xffffffffu, acc0, 24);
+  u1 += __shfl_down_sync(0xffffffffu, acc1, 24);
+}
+template <class VT> struct RowPair { static constexpr bool value = false; static constexpr int minb = 4; };
+// FP32 blocks: two rows in flight need ~100 registers (144 bytes of spills at 80); the coarse levels that use them are
+// 1/9 of the work, so they keep the one-row pipeline.  binary16 (the fine level) fits in 64 registers.
+template <> struct RowPair<float> { static constexpr bool value = false; static constexpr int minb = 4; };
+template <> struct RowPair<__half> { static constexpr bool value = true; static constexpr int minb = 4; };
+
+// rows r, r + n_warp of a warp per iteration (rows with more than 9 blocks fall back to the one-row product)
+template <class VT, class Body>
+__device__ inline double bsr_rows_paired(int warp, int n_warp, int lane, int n_row, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ colidx, const VT* __restrict__ vals,
+                                         const double* __restrict__ x, Body body) {
+  double acc = 0.0;
+  const int step = 2 * n_warp;
+  int r = warp;
+  if (r >= n_row) return acc;
+  int a0 = rowptr[r], a1 = rowptr[r + 1], b0 = 0, b1 = 0;
+  if (r + n_warp < n_row) { b0 = rowptr[r + n_warp]; b1 = rowptr[r + n_warp + 1]; }
+  int ciA[3], ciB[3];
+  row_colidx(lane, a0, a1, colidx, ciA, vals);
+  row_colidx(lane, b0, b1, colidx, ciB, vals);
+  int na0 = 0, na1 = 0, nb0 = 0, nb1 = 0;
+  if (r + step < n_row) { na0 = rowptr[r + step]; na1 = rowptr[r + step + 1]; }
+  if (r + step + n_warp < n_row) { nb0 = rowptr[r + step + n_warp]; nb1 = rowptr[r + step + n_warp + 1]; }
+  for (; r < n_row; r += step) {
+    RowRaw<VT> qa, qb;
+    row_issue(a0, ciA, lane, vals, x, qa);
+    row_issue(b0, ciB, lane, vals, x, qb);
+    int nciA[3], nciB[3];
+    row_colidx(lane, na0, na1, colidx, nciA, vals);   // empty range (past the end) gives -1 everywhere
+    row_colidx(lane, nb0, nb1, colidx, nciB, vals);
+    int nna0 = 0, nna1 = 0, nnb0 = 0, nnb1 = 0;
+    const int r2 = r + 2 * step;
+    if (r2 < n_row) { nna0 = rowptr[r2]; nna1 = rowptr[r2 + 1]; }
+    if (r2 + n_warp < n_row) { nnb0 = rowptr[r2 + n_warp]; nnb1 = rowptr[r2 + n_warp + 1]; }
+    double ua0, ua1, ub0, ub1;
+    if (a1 - a0 <= 9 && b1 - b0 <= 9) {
+      row_finish(qa, ua0, ua1);
+      row_finish(qb, ub0, ub1);
+    } else {   // long rows (coarse levels): the one-row product re-reads its first chunk
+      bsr_row_product(a0, a1, ciA, lane, colidx, vals, x, ua0, ua1);
+      bsr_row_product(b0, b1, ciB, lane, colidx, vals, x, ub0, ub1);
+    }
+    if constexpr (std::is_void<decltype(body(r, ua0, ua1))>::value) {
+      body(r, ua0, ua1);
+      if (r + n_warp < n_row) body(r + n_warp, ub0, ub1);
+    } else {
+      acc += body(r, ua0, ua1);
+      if (r + n_warp < n_row) acc += body(r + n_warp, ub0, ub1);
+    }
+    a0 = na0; a1 = na1; b0 = nb0; b1 = nb1; na0 = nna0; na1 = nna1; nb0 = nnb0; nb1 = nnb1;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { ciA[u] = nciA[u]; ciB[u] = nciB[u]; }
+  }
+  return acc;
 }
 
 // MODE 0: y = A x.            MODE 1: y = A x and sc->pq = x.y (CG step).
@@ -452,19 +571,21 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   }
 }
 
-// MODE 0: y = A x;  2: y = b - A x;  3: y += A x   (any 6x6 block-CSR, also rectangular)
+// MODE 0: y = A x;  2: y = b - A x;  3: y += A x;  5 (short-row kernel only): y = s b + A x
+// (any 6x6 block-CSR, also rectangular)
 #ifndef JSSO_SPMV_MINB
 #define JSSO_SPMV_MINB 4   // resident CTAs per SM the register allocation of the level SpMV aims at
 #endif
+
 template <int MODE, class VT>
-__global__ void __launch_bounds__(RED_BLOCK, JSSO_SPMV_MINB)
+__global__ void __launch_bounds__(RED_BLOCK, (JSSO_SPMV_PAIRED ? RowPair<VT>::minb : JSSO_SPMV_MINB))
 bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                       const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                       const double* __restrict__ bvec) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warp = (gridDim.x * blockDim.x) >> 5;
-  bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, [&](int r, double u0, double u1) {
+  auto epilogue = [=](int r, double u0, double u1) {
     if (lane < 3) {
       double2* yp = (double2*)(y + 6 * (size_t)r + 2 * lane);
       if (MODE == 2) {
@@ -477,7 +598,61 @@ bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32
         *yp = make_double2(u0, u1);
       }
     }
-  });
+  };
+  if constexpr (RowPair<VT>::value && JSSO_SPMV_PAIRED) bsr_rows_paired(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
+  else bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
+}
+
+// ---- fused multigrid-PCG iteration (device-resident scalars) -------------------------------------------
+// Slots of the scalar block `scal` (doubles): the outer PCG keeps every scalar on the device, so an iteration
+// needs no host round trip.  A kernel that gets a `stop` pointer (= scal) returns at once when the recurrence
+// residual has reached the tolerance (r.r <= tol2 |b|^2, also true for NaN), so the launches the host enqueued
+// past convergence (it polls every few iterations) are no-ops.  On several GPUs every dot product is written to
+// its MGS_LOC + slot partial and summed over the ranks OUT OF PLACE into the slot itself (idempotent when the
+// producing kernel was a no-op).
+constexpr int MGS_BB = 1, MGS_RR = 2, MGS_RZ = 3, MGS_PQ = 4, MGS_RZ_OLD = 6, MGS_TOL = 7, MGS_ITER = 8,
+              MGS_LOC = 16, MGS_COUNT = 32;
+__device__ inline bool mgs_stopped(const double* stop) {
+  return stop && !(stop[MGS_RR] > stop[MGS_TOL]);
+}
+
+// y_r = ca * bvec_r + cb * xrow_r + cc * (A x)_r  for the block rows [0, n_row) of (rowptr, y, bvec, xrow);
+// x is the full-length gather vector.  bvec / xrow may be null when their coefficient is 0.
+// DOT 1: *dot_out = sum_r bvec_r . y_r;  DOT 2: *dot_out = sum_r xrow_r . (A x)_r   (deterministic grid sum).
+// Covers the fused V-cycle steps of the fine level -- r0 = b - (1/theta) A b (pre-smoother from a zero guess
+// folded into the residual), z = x + (1/theta)(b - A x) with r.z (post-smoother + the PCG's dot) -- and the outer
+// q = A p with p.q.
+template <class VT, int DOT>
+__global__ void __launch_bounds__(RED_BLOCK, (JSSO_SPMV_PAIRED ? RowPair<VT>::minb : JSSO_SPMV_MINB))
+bsr_spmv_lin_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                    const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                    const double* __restrict__ bvec, const double* __restrict__ xrow, double ca, double cb, double cc,
+                    const double* stop, double* partials, unsigned* counter, double* dot_out) {
+  if (mgs_stopped(stop)) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warp = (gridDim.x * blockDim.x) >> 5;
+  auto epilogue = [=](int r, double u0, double u1) -> double {
+    double d = 0.0;
+    if (lane < 3) {
+      const size_t o = 6 * (size_t)r + 2 * lane;
+      double2 v = make_double2(cc * u0, cc * u1);
+      double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+      if (bvec) { bv = *(const double2*)(bvec + o); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
+      if (xrow) { xv = *(const double2*)(xrow + o); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
+      *(double2*)(y + o) = v;
+      if (DOT == 1) d = bv.x * v.x + bv.y * v.y;
+      if (DOT == 2) d = xv.x * u0 + xv.y * u1;
+    }
+    return d;
+  };
+  double dot;
+  if constexpr (RowPair<VT>::value && JSSO_SPMV_PAIRED) dot = bsr_rows_paired(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
+  else dot = bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
+  if (DOT != 0) {
+    double total;
+    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+  }
 }
 
 // Short rows (prolongators: 1-4 blocks per row) in the FP32 row-pair-major layout: one THREAD per
@@ -487,7 +662,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 bsr_spmv_short_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                       const float* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                      const double* __restrict__ bvec) {
+                      const double* __restrict__ bvec, double s = 1.0, const double* stop = nullptr) {
+  if (mgs_stopped(stop)) return;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 3LL * n_row) return;
   const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
@@ -512,6 +688,9 @@ bsr_spmv_short_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32
   } else if (MODE == 3) {
     const double2 yv = *yp;
     *yp = make_double2(yv.x + acc0, yv.y + acc1);
+  } else if (MODE == 5) {   // y = s * bvec + A x  (prolongation onto the lazily formed pre-smoothed iterate b / theta)
+    const double2 bv = *(const double2*)(bvec + 6 * (size_t)r + 2 * sub);
+    *yp = make_double2(fma(s, bv.x, acc0), fma(s, bv.y, acc1));
   } else {
     *yp = make_double2(acc0, acc1);
   }
@@ -608,12 +787,13 @@ mgd_wait_unpack_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const i
     v[6 * (size_t)recv_idx[t / 6] + t % 6] = ld_relaxed_sys_f64(src + t);
 }
 
-// scal[0..count) <- sum over the ranks (rank order: bitwise identical everywhere); one block, count <= 2
-__global__ void mgd_allreduce_kernel(const MgdCtx* c, double* scal, int count, unsigned long long seq) {
+// dst[0..count) <- sum over the ranks of src[0..count) (rank order: bitwise identical everywhere); one block,
+// count <= 2.  dst may be src (in place) or another slot (out of place: idempotent when repeated).
+__global__ void mgd_allreduce_kernel(const MgdCtx* c, const double* src, double* dst, int count, unsigned long long seq) {
   const int par = (int)(seq & 1ull);
   if (threadIdx.x == 0) {
     for (int r = 0; r < c->n_rank; ++r)
-      for (int k = 0; k < count; ++k) st_relaxed_sys_f64(&c->mbox[r]->red_val[par][c->rank][k], scal[k]);
+      for (int k = 0; k < count; ++k) st_relaxed_sys_f64(&c->mbox[r]->red_val[par][c->rank][k], src[k]);
     __threadfence_system();
     for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->red_tag[par][c->rank], seq);
     const MgdMailbox* m = c->mbox[c->rank];
@@ -622,7 +802,7 @@ __global__ void mgd_allreduce_kernel(const MgdCtx* c, double* scal, int count, u
       while (ld_acquire_sys(&m->red_tag[par][r]) < seq) { }
       for (int k = 0; k < count; ++k) acc[k] += ld_relaxed_sys_f64(&m->red_val[par][r][k]);
     }
-    for (int k = 0; k < count; ++k) scal[k] = acc[k];
+    for (int k = 0; k < count; ++k) dst[k] = acc[k];
   }
 }
 

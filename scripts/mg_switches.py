@@ -1,0 +1,54 @@
+"""A/B of the multigrid-PCG opt-in switches on one mesh, one process: the symbolic hierarchy is built once and
+re-uploaded into a fresh handle per configuration (the switches are read by jsso_mg_setup).
+  python scripts/mg_switches.py [N] [rtol]"""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jaxsso_b200 import _native as nat, meshes, multigrid
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+rtol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-8
+md = meshes.plate(N)
+D = nat.DeviceArray
+crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
+u = D((md.ndof,))
+levels = None
+u_ref = None
+CONFIGS = [{}, {'JSSO_MG_FP16': '1'}, {'JSSO_MG_ASYNC': '4'}, {'JSSO_MG_ASYNC': '8'}, {'JSSO_MG_GRAPH': '1'},
+           {'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '8'}, {'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '8', 'JSSO_MG_FP16': '1'}]
+KEYS = ('JSSO_MG_FP16', 'JSSO_MG_ASYNC', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64')
+for cfg in CONFIGS:
+    for k in KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(cfg)
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    if levels is None:
+        rp, ci = h.pattern()
+        t0 = time.perf_counter()
+        levels = multigrid.build_hierarchy(rp, ci)
+        print('symbolic hierarchy %.1f s' % (time.perf_counter() - t0), flush=True)
+    h.mg_setup(levels=levels)
+    for deg in (1, 2):
+        best = None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond='multigrid', cheb_degree=deg))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        # setup share: one iteration only
+        t0 = time.perf_counter()
+        try:
+            h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond='multigrid', cheb_degree=deg, maxiter=1))
+        except nat.JssoError:
+            pass
+        t_setup = time.perf_counter() - t0
+        st = h.forward(crds, pq, pb, f, u, opts=nat.make_opts(rtol=rtol, precond='multigrid', cheb_degree=deg))
+        uh = u.download()
+        if u_ref is None:
+            u_ref = uh.copy()
+        print('MG_SWITCH ' + json.dumps({'cfg': cfg, 'cheb': deg, 'forward_s': best, 'setup_plus_1it_s': t_setup,
+                                         'iterations': st.iterations, 'relres': st.relres,
+                                         'ms_per_iteration': 1e3 * (best - t_setup) / max(st.iterations - 1, 1),
+                                         'u_rel_diff_vs_default': float(np.linalg.norm(uh - u_ref) / np.linalg.norm(u_ref))}),
+              flush=True)
+    h.close()

@@ -56,8 +56,8 @@ def test_chunked_host_pipeline_equals_unchunked(emu_api):
 @pytest.mark.parametrize('fp16', ['0', '1'])
 def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
     """mg_numeric_setup (power iteration, smoothed prolongator, Galerkin products, dense coarse inverse) + V-cycle
-    PCG; with JSSO_MG_FP16=1 the fine-level V-cycle matrix is stored in binary16 (the path that has not run on
-    hardware yet): same solution, iteration count within 2."""
+    PCG (fused iteration, device scalars); the fine-level V-cycle matrix is stored in binary16 by default,
+    JSSO_MG_FP16=0 keeps FP32: same solution, iteration count within 2."""
     res = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_FP16': fp16})
     assert res['mg_converged'] and res['bj_converged']
     assert res['mg_err'] <= 1e-8 and res['bj_err'] <= 1e-8
@@ -122,16 +122,18 @@ def test_bench_distributed_leg_on_rank_threads(emu_api):
     assert pm['u_rel_diff_vs_replicated_solve'] <= 1e-8
 
 
-def test_device_scalar_pcg_single_and_distributed(emu_api):
-    """JSSO_MG_ASYNC=k (opt-in): alpha / beta formed on the device, one host poll every k iterations -- same
-    solution, at most k - 1 extra iterations, on one GPU and on two rank threads."""
-    base = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_ASYNC': '0'})
-    res = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_ASYNC': '4'})
-    assert res['mg_converged'] and res['mg_err'] <= 1e-8
-    assert base['mg_iters'] <= res['mg_iters'] <= base['mg_iters'] + 3 and res['mg_iters'] % 4 == 0
-    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_ASYNC': '3'})
+def test_device_scalar_pcg_poll_period(emu_api):
+    """The PCG scalars live on the device; the host polls the residual every JSSO_MG_POLL iterations and the
+    launches enqueued past convergence are no-ops: the iteration count and the solution do not depend on the poll
+    period, on one GPU and on two rank threads."""
+    base = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_POLL': '1'})
+    for k in ('4', '8'):
+        res = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_POLL': k})
+        assert res['mg_converged'] and res['mg_err'] <= 1e-8
+        assert res['mg_iters'] == base['mg_iters']
+    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_POLL': '3'})
     assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
-    assert all(d['iters_single'] <= i <= d['iters_single'] + 2 for i in d['iters_dist'])
+    assert all(i == d['iters_single'] for i in d['iters_dist'])
 
 
 @pytest.mark.parametrize('p2p', ['', 'p2p'])
@@ -158,24 +160,24 @@ def test_full_size_property_tests_run_on_the_emulator(emu_api):
 
 
 def test_graph_captured_vcycle(emu_api):
-    """JSSO_MG_GRAPH=1 (opt-in): the V-cycle is captured once per numeric setup and replayed as one graph launch
-    (the emulator records the launches with their arguments by value and replays them): same iterations and
-    solution with far fewer launches, alone and combined with the device-scalar PCG and binary16 storage; on rank
-    threads the replicated coarse levels are the captured part."""
-    base = run(emu_api, 'mg', 12, 1)
-    g = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_GRAPH': '1'})
+    """The coarse part of the V-cycle (levels >= 1; the whole V-cycle for Chebyshev degrees other than 1) is captured
+    once per numeric setup and replayed as one graph launch (the emulator records the launches with their arguments
+    by value and replays them); JSSO_MG_GRAPH=0 launches the kernels one by one: same iterations and solution, far
+    fewer launches; on rank threads the replicated coarse levels are the captured part."""
+    base = run(emu_api, 'mg', 12, 1, env={'JSSO_MG_GRAPH': '0'})
+    g = run(emu_api, 'mg', 12, 1)
     assert g['mg_converged'] and g['mg_iters'] == base['mg_iters'] and g['mg_err'] <= 1e-8
-    assert g['mg_launches'] <= base['mg_launches'] - 10 * g['mg_iters']      # every V-cycle became one launch
-    c = run(emu_api, 'mg', 12, 2, env={'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '4', 'JSSO_MG_FP16': '1'})
+    assert g['mg_launches'] <= base['mg_launches'] - 5 * g['mg_iters']      # the coarse levels became one launch
+    c = run(emu_api, 'mg', 12, 2, env={'JSSO_MG_POLL': '4', 'JSSO_MG_FP16': '0'})
     assert c['mg_converged'] and c['mg_err'] <= 1e-8
-    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_GRAPH': '1'})
+    d = run(emu_api, 'dist', 2, 12, 10, 1, env={'JSSO_MG_GRAPH': '0'})
     assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
     assert all(i == d['iters_single'] for i in d['iters_dist'])
 
 
 @pytest.mark.parametrize('world,size,min_dist,deg,env', [
     (2, 12, 10, 1, {}), (4, 12, 10, 1, {'EMU_JITTER': '3000'}),
-    (4, 16, 10, 2, {'JSSO_MG_ASYNC': '3', 'JSSO_MG_GRAPH': '1', 'EMU_JITTER': '1000'})])
+    (4, 16, 10, 2, {'JSSO_MG_POLL': '3', 'EMU_JITTER': '1000'})])
 def test_peer_memory_distributed_multigrid(emu_api, world, size, min_dist, deg, env):
     """jsso_mg_p2p_connect: halo exchanges as push + wait/unpack kernels over "peer memory" (stores into the peers'
     double-buffered receive arenas, release/acquire flags) and mailbox all-reduces, no NCCL on the iteration path.
@@ -185,6 +187,5 @@ def test_peer_memory_distributed_multigrid(emu_api, world, size, min_dist, deg, 
     bit-identical).  Same iterations as the undistributed solve, identical u on every rank."""
     res = run(emu_api, 'dist', world, size, min_dist, deg, 'p2p', env=env)
     assert res['peer_memory'] and res['converged'] and res['identical_on_all_ranks']
-    k = int(env.get('JSSO_MG_ASYNC', '1'))
-    assert all(res['iters_single'] <= i <= res['iters_single'] + k - 1 + 1 for i in res['iters_dist'])
+    assert all(abs(i - res['iters_single']) <= 1 for i in res['iters_dist'])
     assert res['err_vs_single'] <= 1e-10 and res['err_vs_oracle'] <= 1e-8
