@@ -198,8 +198,10 @@ class SSO_model:
         opts = nat.make_opts(rtol=self.rtol)
         if self.objective == 'strain energy':
             u0 = self._u_prev if (self.warm_start and self._u_prev is not None) else None
+            if u0 is not None and u0.size != 6 * h.n_node:      # the model was rebuilt with another mesh
+                u0 = self._u_prev = None
             val, u, dc, dq, db, fs, bs = h.value_and_grad_host(crds, pq, pb, self.model.nodal_loads, opts=opts,
-                                                               u0=u0)
+                                                               u0=u0, allow_noconv=True)
             self._u_prev = u
             self.last_stats = {'forward': fs.as_dict(), 'backward': bs.as_dict()}
             self.model.u = u

@@ -475,13 +475,15 @@ class Handle:
                                      C.byref(o), C.byref(st), stream))
         return st
 
-    def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None, u0=None):
+    def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None, u0=None,
+                            allow_noconv=False):
         """End-to-end strain-energy value + gradient with HOST (NumPy) buffers.  ``u0``: initial
         guess for the solve (e.g. the previous design's u); needs opts.use_x0."""
         crds = np.ascontiguousarray(crds, np.float64)
         prop_q = np.ascontiguousarray(prop_q, np.float64)
         prop_b = np.ascontiguousarray(prop_b, np.float64)
         f = np.ascontiguousarray(f, np.float64)
+        self._check_shapes(crds, prop_q, prop_b, f=f, u0=u0)
         u = np.empty(6 * self.n_node) if u0 is None else np.array(u0, dtype=np.float64).ravel()
         dc = np.empty((self.n_node, 3)) if 'crds' in want else None
         dq = np.empty((self.n_quad, 5)) if ('prop_q' in want and self.n_quad) else None
@@ -491,13 +493,37 @@ class Handle:
         o = opts or make_opts()
         if u0 is not None:
             o.use_x0 = 1
-        self._ck(lib().jsso_value_and_grad_host(self.h, _ptr(crds), _ptr(prop_q), _ptr(prop_b), _ptr(f),
-                                                C.byref(val), _ptr(u), _ptr(dc), _ptr(dq), _ptr(db),
-                                                C.byref(o), C.byref(fs), C.byref(bs)))
+        rc = self._ck(lib().jsso_value_and_grad_host(self.h, _ptr(crds), _ptr(prop_q), _ptr(prop_b), _ptr(f),
+                                                     C.byref(val), _ptr(u), _ptr(dc), _ptr(dq), _ptr(db),
+                                                     C.byref(o), C.byref(fs), C.byref(bs)),
+                      allow=(JSSO_ERR_NOCONV,) if allow_noconv else ())
+        if rc == JSSO_ERR_NOCONV:
+            # the solver stopped at its attainable accuracy (or maxiter): u and the gradients of the best iterate are
+            # returned, as the reference's direct solvers return whatever accuracy they reach; fs.relres says how far
+            import warnings
+            warnings.warn('jaxsso_b200: ' + lib().jsso_last_error(self.h).decode(), RuntimeWarning, stacklevel=2)
         return val.value, u, dc, dq, db, fs, bs
+
+    def _check_shapes(self, crds, prop_q, prop_b, f=None, u0=None, u=None, lam=None):
+        """The C entry points copy n_node / n_quad / n_beam sized blocks from these pointers: refuse anything else."""
+        def need(a, size, name):
+            if a is None:
+                if size:
+                    raise ValueError(f'{name} is required ({size} values)')
+                return
+            a = np.asarray(a)
+            if a.size != size or a.dtype != np.float64 or not a.flags['C_CONTIGUOUS']:
+                raise ValueError(f'{name}: expected {size} contiguous float64 values, got {a.size} of {a.dtype}')
+        need(crds, 3 * self.n_node, 'crds')
+        need(prop_q, 5 * self.n_quad, 'prop_q')
+        need(prop_b, 6 * self.n_beam, 'prop_b')
+        for a, name in ((f, 'f'), (u0, 'u0'), (u, 'u'), (lam, 'lam')):
+            if a is not None:
+                need(a, 6 * self.n_node, name)
 
     def assemble_adjoint_host(self, crds, prop_q, prop_b, u, lam, out=None):
         """Ke+assembly+adjoint with HOST buffers; `out` = (d_crds, d_prop_q, d_prop_b) to reuse."""
+        self._check_shapes(crds, prop_q, prop_b, u=u, lam=lam)
         if out is None:
             out = (np.empty((self.n_node, 3)), np.empty((self.n_quad, 5)) if self.n_quad else None,
                    np.empty((self.n_beam, 6)) if self.n_beam else None)

@@ -167,7 +167,8 @@ struct jsso_handle {
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
   double* mg_scal_host = nullptr;  // pinned
   bool mg_ready = false;           // numeric hierarchy matches the current matrix
-  const double* last_crds = nullptr;
+  const double* last_crds = nullptr;   // = crds_keep after an assembly (handle-owned copy: the caller's array may be gone by the time of the solve)
+  double* crds_keep = nullptr;
   // row-range distributed multigrid solve (jsso_mg_set_dist): the hierarchy above stays replicated on every
   // rank, the V-cycle / PCG products are computed by row ranges with halo exchanges between the ranks
   struct MgDistPeer { int rank, send_off, send_cnt, recv_off, recv_cnt; };   // node counts
@@ -200,10 +201,11 @@ struct jsso_handle {
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
   cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
   cudaEvent_t ev_b = nullptr;
-  // opt-in chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K > 1): u / lam arrive in K node
-  // ranges, the quad adjoint runs in K quad ranges as soon as the rows a range reads have arrived, and every
-  // range's d_prop_q goes back to the host while the next range is differentiated
-  int e2e_chunks = 1;
+  // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 4; 1 = one launch): u / lam arrive
+  // in K node ranges, the quad adjoint runs in K quad ranges as soon as the rows a range reads have arrived, and
+  // every range's d_prop_q goes back to the host while the next range is differentiated (measured at 1M quads on a
+  // B200, PCIe-bound step: 5.04 ms unchunked, 4.25 ms with K = 4)
+  int e2e_chunks = 4;
   cudaStream_t st_c = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_adj;
   std::vector<int> e2e_qb, e2e_nb, e2e_wait;   // quad bounds, node bounds, upload range each quad range waits for
@@ -436,7 +438,7 @@ void jsso_destroy(jsso_handle* h) {
     for (void* p : lv) if (p) cudaFree(p);
   }
   {
-    void* mgp[] = {h->Lfac, h->vals32, h->vals16, h->mg_dense, h->mg_cb, h->mg_cx, h->mg_scal};
+    void* mgp[] = {h->Lfac, h->vals32, h->vals16, h->mg_dense, h->mg_cb, h->mg_cx, h->mg_scal, h->crds_keep};
     for (void* p : mgp) if (p) cudaFree(p);
     if (h->mg_scal_host) cudaFreeHost(h->mg_scal_host);
   }
@@ -577,7 +579,12 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     CKL("assemble_fused_kernel");
   }
   h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
-  h->last_crds = crds;
+  h->last_crds = nullptr;
+  if (!h->mg.empty() && crds) {   // the numeric multigrid setup reads the coordinates at the time of the solve
+    if (!h->crds_keep) CK(dalloc(&h->crds_keep, 3 * (size_t)h->sym.n_node));
+    CK(cudaMemcpyAsync(h->crds_keep, crds, 3 * (size_t)h->sym.n_node * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    h->last_crds = h->crds_keep;
+  }
   return JSSO_OK;
 }
 
@@ -636,7 +643,13 @@ int jsso_get_values(jsso_handle* h, double* vals_d, void* stream) {
   NEED_GPU();
   if (!h->assembled) return fail(h, JSSO_ERR_STATE, "no assembled matrix");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(vals_d, h->vals, (size_t)h->sym.nnzb() * 36 * sizeof(double), cudaMemcpyDeviceToDevice,
+  const long long nnzb = h->sym.nnzb();
+  if (h->scaled && nnzb > 0) {   // after a solve h->vals holds W K W^T: hand back K
+    unscale_blocks_kernel<<<cdiv(nnzb, 128), 128, 0, (cudaStream_t)stream>>>(nnzb, h->blk_row, h->colidx, h->W, h->vals, vals_d);
+    CKL("unscale_blocks_kernel");
+    return JSSO_OK;
+  }
+  CK(cudaMemcpyAsync(vals_d, h->vals, (size_t)nnzb * 36 * sizeof(double), cudaMemcpyDeviceToDevice,
                      (cudaStream_t)stream));
   return JSSO_OK;
 }
@@ -647,7 +660,16 @@ int jsso_get_values_host(jsso_handle* h, double* vals_h) {
   if (!h->assembled) return fail(h, JSSO_ERR_STATE, "no assembled matrix");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(vals_h, h->vals, (size_t)h->sym.nnzb() * 36 * sizeof(double), cudaMemcpyDeviceToHost));
+  const size_t bytes = (size_t)h->sym.nnzb() * 36 * sizeof(double);
+  if (h->scaled && bytes > 0) {   // after a solve h->vals holds W K W^T: hand back K (through a scratch copy)
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, bytes));
+    int rc = jsso_get_values(h, tmp, nullptr);
+    if (!rc && cudaMemcpy(vals_h, tmp, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(h, JSSO_ERR_CUDA, "copy of the unscaled values failed");
+    cudaFree(tmp);
+    return rc;
+  }
+  CK(cudaMemcpy(vals_h, h->vals, bytes, cudaMemcpyDeviceToHost));
   return JSSO_OK;
 }
 
@@ -798,7 +820,19 @@ int jsso_spmv(jsso_handle* h, const double* x, double* y, void* stream) {
   NEED_GPU();
   if (!h->assembled) return fail(h, JSSO_ERR_STATE, "spmv before assemble");
   CK(cudaSetDevice(h->device));
-  return spmv_plain(h, x, y, (cudaStream_t)stream);
+  if (!h->scaled) return spmv_plain(h, x, y, (cudaStream_t)stream);
+  // a solve has replaced the values by the block-Jacobi-scaled A^ = W K W^T: K x = W^-1 (A^ (W^-T x))
+  if (h->n_rank > 1) return fail(h, JSSO_ERR_STATE, "jsso_spmv after a solve is single-GPU only (the values are scaled)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_row = h->sym.n_row;
+  if (n_row == 0) return JSSO_OK;
+  block_solve_wt_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, x, nullptr, h->tmp_lam);
+  CKL("block_solve_wt_kernel");
+  int rc = spmv_plain(h, h->tmp_lam, h->tmp_g, st);
+  if (rc) return rc;
+  block_solve_w_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->tmp_g, y);
+  CKL("block_solve_w_kernel");
+  return JSSO_OK;
 }
 
 // block-Jacobi scaling of the assembled matrix (once per assembly)
@@ -2043,6 +2077,7 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
                              const double* f_h, double* value_out, double* u_h, double* dc_h, double* dpq_h,
                              double* dpb_h, const jsso_solve_opts* opts, jsso_stats* fs, jsso_stats* bs) {
   if (!h || !crds_h || !f_h) return JSSO_ERR_ARG;
+  if ((h->sym.n_quad > 0 && !pq_h) || (h->sym.n_beam > 0 && !pb_h)) return fail(h, JSSO_ERR_ARG, "null property array");
   NEED_GPU();
   CK(cudaSetDevice(h->device));
   int rc = ensure_host_staging(h);
@@ -2069,7 +2104,9 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
     o.use_x0 = 0;
   }
   rc = jsso_forward(h, d_crds, d_pq, d_pb, d_f, d_u, &o, fs, st);
-  if (rc) return rc;
+  const int rc_solve = rc;   // JSSO_ERR_NOCONV still delivers the best iterate (attainable accuracy): finish, then report it
+  if (rc && rc != JSSO_ERR_NOCONV) return rc;
+  const std::string solve_msg = h->err;
   o.compliance = 1; o.use_x0 = 0;
   const bool want_grad = dc_h || dpq_h || dpb_h;
   if (want_grad) {
@@ -2089,6 +2126,7 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
   if (dc_h) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
   if (dpq_h && nq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
   if (dpb_h && nb) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  if (rc_solve) return fail(h, rc_solve, solve_msg);
   return JSSO_OK;
 }
 

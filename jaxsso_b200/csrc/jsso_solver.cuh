@@ -1024,6 +1024,72 @@ block_solve_wt_kernel(int n_row, const double* __restrict__ W, const double* __r
   for (int i = 0; i < 6; ++i) y[6 * (size_t)r + i] = v[i];
 }
 
+// y_r = W_r^-1 x_r  (forward substitution with the lower-triangular W_r): with block_solve_wt_kernel it applies
+// the UNSCALED operator from the scaled values, K x = W^-1 (A^ (W^-T x))  (jsso_spmv after a solve)
+__global__ void __launch_bounds__(128)
+block_solve_w_kernel(int n_row, const double* __restrict__ W, const double* __restrict__ x, double* __restrict__ y) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_row) return;
+  const double* w = W + (size_t)r * 36;
+  double v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = x[6 * (size_t)r + i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= w[i * 6 + k] * v[k];
+    v[i] = t / w[i * 6 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[6 * (size_t)r + i] = v[i];
+}
+
+// out_rc = W_r^-1 A^_rc W_c^-T: the unscaled block from the scaled one (jsso_get_values after a solve); thread per block
+__device__ inline void tri_inverse_lower(const double* __restrict__ w, double (&L)[6][6]) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i < j) { L[i][j] = 0.0; continue; }
+      double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = j; k < i; ++k) t -= w[i * 6 + k] * L[k][j];
+      L[i][j] = t / w[i * 6 + i];
+    }
+}
+__global__ void __launch_bounds__(128)
+unscale_blocks_kernel(long long nnzb, const int32_t* __restrict__ blk_row, const int32_t* __restrict__ colidx,
+                      const double* __restrict__ W, const double* __restrict__ vals, double* __restrict__ out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnzb) return;
+  double Lr[6][6], Lc[6][6], A[6][6], T[6][6];
+  tri_inverse_lower(W + (size_t)blk_row[s] * 36, Lr);
+  tri_inverse_lower(W + (size_t)colidx[s] * 36, Lc);
+  const double* a = vals + (size_t)s * 36;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[i][j] = a[j * 6 + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k <= i; ++k) t += Lr[i][k] * A[k][j];
+      T[i][j] = t;
+    }
+  double* o = out + (size_t)s * 36;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k <= j; ++k) t += T[i][k] * Lc[j][k];
+      o[j * 6 + i] = t;
+    }
+}
+
 // ---- CG vector kernels ---------------------------------------------------------------
 // r = b - q (q = A x0 or 0), p = r, rr[0] = bb-candidate.  SETBB: also bb = |b|^2.
 template <int SETBB>

@@ -32,7 +32,12 @@ static ffi::Error BackwardImpl(cudaStream_t stream, int64_t handle, double rtol,
   jsso_solve_opts o{rtol, 0, 0, 0, 0};
   jsso_stats st;
   jsso_handle* h = reinterpret_cast<jsso_handle*>(handle);
-  int rc = jsso_backward(h, crds.typed_data(), prop_q.typed_data(), prop_b.typed_data(), u.typed_data(),
+  // The adjoint solve uses the matrix the handle holds.  In a traced program several fea_solve calls may share one
+  // handle before their backward passes run (two designs in one loss, jacrev, XLA reordering), so the matrix of
+  // THIS design is re-assembled first (1.2 ms + the numeric multigrid setup at 1M quads, against a solve of > 0.1 s).
+  int rc = jsso_assemble(h, crds.typed_data(), prop_q.typed_data(), prop_b.typed_data(), 1, stream);
+  if (rc) return ffi::Error(ffi::ErrorCode::kInternal, jsso_last_error(h));
+  rc = jsso_backward(h, crds.typed_data(), prop_q.typed_data(), prop_b.typed_data(), u.typed_data(),
                          g.typed_data(), d_crds->typed_data(), d_prop_q->typed_data(), d_prop_b->typed_data(),
                          nullptr, &o, &st, stream);
   return rc ? ffi::Error(ffi::ErrorCode::kInternal, jsso_last_error(h)) : ffi::Error::Success();

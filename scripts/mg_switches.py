@@ -14,9 +14,8 @@ crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(
 u = D((md.ndof,))
 levels = None
 u_ref = None
-CONFIGS = [{}, {'JSSO_MG_FP16': '1'}, {'JSSO_MG_ASYNC': '4'}, {'JSSO_MG_ASYNC': '8'}, {'JSSO_MG_GRAPH': '1'},
-           {'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '8'}, {'JSSO_MG_GRAPH': '1', 'JSSO_MG_ASYNC': '8', 'JSSO_MG_FP16': '1'}]
-KEYS = ('JSSO_MG_FP16', 'JSSO_MG_ASYNC', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64')
+CONFIGS = [{}, {'JSSO_MG_FP16': '0'}, {'JSSO_MG_GRAPH': '0'}, {'JSSO_MG_POLL': '1'}, {'JSSO_MG_POLL': '16'}]
+KEYS = ('JSSO_MG_FP16', 'JSSO_MG_POLL', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64')
 for cfg in CONFIGS:
     for k in KEYS:
         os.environ.pop(k, None)

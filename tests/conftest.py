@@ -14,18 +14,24 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box via gpurun)')
-    config.addinivalue_line('markers', 'unverified: GPU path written after the round\'s GPU budget was spent; it '
-                                       'compiles but has not run on hardware yet (JSSO_RUN_UNVERIFIED=1 runs it)')
+
+
+def _device_count():
+    try:
+        from jaxsso_b200 import _native as nat
+        return int(nat.lib().jsso_device_count())
+    except Exception:
+        return 0
 
 
 def pytest_collection_modifyitems(config, items):
-    """Tests of GPU code that has never run on hardware are opt-in, so that a first failure there cannot
-    mask the verified parity tests under `-x`; they run with JSSO_RUN_UNVERIFIED=1."""
-    if os.environ.get('JSSO_RUN_UNVERIFIED', '0') == '1':
+    """`gpu` tests are skipped (not failed) where there is no CUDA device, so that a plain `pytest tests` works in
+    the build container; `-m gpu` on a GPU box runs them all."""
+    if not any('gpu' in it.keywords for it in items) or _device_count() > 0:
         return
-    skip = pytest.mark.skip(reason='not yet run on hardware; set JSSO_RUN_UNVERIFIED=1')
+    skip = pytest.mark.skip(reason='no CUDA device (the product path has no CPU fallback)')
     for it in items:
-        if 'unverified' in it.keywords:
+        if 'gpu' in it.keywords:
             it.add_marker(skip)
 
 

@@ -101,6 +101,22 @@ def main():
                'db_err': float(np.abs(db - rdb).max() / np.abs(rdb).max()),
                'sum': [float(dc.sum()), float(dq.sum()), float(db.sum()), float(np.abs(K).sum())],
                'hash': [hash(dc.tobytes()), hash(dq.tobytes()), hash(db.tobytes())]}
+    elif mode == 'afterpcg':
+        # jsso_spmv / jsso_get_values_host after a solve (the stored values are then the scaled W K W^T)
+        md = mixed(int(sys.argv[2]))
+        h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+        c, q, b, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
+        h.assemble(c, q, b, apply_bc=True)
+        K0 = h.values_host().copy()
+        x = np.random.default_rng(4).standard_normal(md.ndof)
+        xd, yd, ud = D.from_host(x), D((md.ndof,)), D((md.ndof,))
+        h.spmv(xd, yd)
+        y0 = yd.download()
+        h.pcg(f, ud, opts=nat.make_opts(rtol=1e-10))
+        K1 = h.values_host()
+        h.spmv(xd, yd)
+        res = {'K_err': float(np.abs(K1 - K0).max() / np.abs(K0).max()),
+               'y_err': float(np.abs(yd.download() - y0).max() / np.abs(y0).max())}
     elif mode == 'mg':
         md, deg = meshes.plate(int(sys.argv[2])), int(sys.argv[3])
         l0 = int(nat.lib().jsso_launch_count())

@@ -41,6 +41,12 @@ def test_value_and_gradient_through_the_emulated_driver(emu_api):
     assert res['launches'] > 100
 
 
+def test_spmv_and_values_after_a_solve(emu_api):
+    """A solve scales the stored matrix in place (W K W^T); jsso_spmv and jsso_get_values_host must still return K."""
+    res = run(emu_api, 'afterpcg', 5)
+    assert res['K_err'] <= 1e-12 and res['y_err'] <= 1e-12
+
+
 def test_chunked_host_pipeline_equals_unchunked(emu_api):
     """JSSO_E2E_CHUNKS=K (opt-in): u / lam uploaded in K node ranges, the quad adjoint in K quad ranges with offset
     pointers, d_prop_q returned range by range -- bitwise the same gradients as the single-launch path, and within

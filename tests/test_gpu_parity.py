@@ -155,6 +155,25 @@ def test_spmv():
     assert relmax(y, K @ x) <= 1e-13
 
 
+def test_spmv_and_values_after_a_solve_are_the_unscaled_operator():
+    """A solve replaces the stored values by the block-Jacobi-scaled matrix W K W^T (once per assembly); jsso_spmv and
+    jsso_get_values* must keep returning K itself afterwards (include/jsso.h: "y = K x with the current values")."""
+    md = meshes.plate(16)
+    d = Dev(md)
+    d.h.assemble(d.crds, d.pq, d.pb, apply_bc=True)
+    K0 = d.h.values_host().copy()
+    x = np.random.default_rng(4).standard_normal(md.ndof)
+    xd, yd = nat.DeviceArray.from_host(x), nat.DeviceArray((md.ndof,))
+    d.h.spmv(xd, yd)
+    y0 = yd.download()
+    u_d = nat.DeviceArray((md.ndof,))
+    d.h.pcg(d.f, u_d, opts=nat.make_opts(rtol=1e-10))
+    K1 = d.h.values_host()
+    assert np.abs(K1 - K0).max() <= 1e-12 * np.abs(K0).max()
+    d.h.spmv(xd, yd)
+    assert relmax(yd.download(), y0) <= 1e-12
+
+
 # ------------------------------------------------------------------ solve
 @pytest.mark.parametrize('case', ['barrel', 'mannheim', 'frames10', 'beam_arch', 'plate32'])
 def test_forward_displacements(case, mannheim_data, golden):

@@ -27,7 +27,6 @@ def test_partitioned_equals_single(world):
     assert res['u_err'] < 1e-8 and res['grad_err'] < 1e-7 and res['dprop_err'] < 1e-7
 
 
-@pytest.mark.unverified
 @pytest.mark.parametrize('p2p', ['', 'p2p'])
 @pytest.mark.parametrize('world,min_dist', [(2, 500), (2, 100000), (4, 500), (8, 500)])
 def test_distributed_multigrid_equals_single(world, min_dist, p2p):
