@@ -246,74 +246,70 @@ def run_reference(args):
 
 
 
-def distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, device, opts, min_dist_nodes, dev, barrier,
-                          max_over_ranks, bcast, allgather=None, on_partial=None):
-    """One gradient evaluation with the V-cycle PCG distributed by row ranges (jsso_mg_set_dist): every rank
-    assembles the whole mesh renumbered by owner and solves collectively, then the partitioned handle `h` runs the
-    adjoint on its part.  `dev`: the rank's device arrays (crds, pq, pb of the local mesh; uu = local part of an
-    earlier solve of the same system, overwritten; dc, dq outputs).  `bcast(obj)`: rank 0's object on every rank.
-    Collective; returns the report dict.  (A function so that the CPU suite can run it on rank threads against
-    the emulated library, tests/emu/driver_check.py.)"""
+def distributed_solve_handle(nat, gmd, rank, world, device, bcast, allgather, min_dist_nodes, use_p2p=True,
+                             partition_kind='auto'):
+    """Whole-mesh handle whose multigrid V-cycle PCG is distributed by row ranges over the ranks (collective).
+
+    The partition of the SOLVE is `dist_multigrid.solve_partition`: contiguous ranges of the mesh's own numbering when
+    it is banded (the benchmark plate: no renumbering, so the hierarchy and the iteration count are exactly the
+    single-GPU ones), else RCB + ownership renumbering with the aggregates still formed in the original order
+    (`build_hierarchy_invariant`).  Exchanges and scalar all-reduces run over NVLink peer memory (CUDA IPC) unless
+    use_p2p is false (NCCL send/recv).  Returns (handle, solve mesh, new->old node permutation or None, info, levels).
+    (A function so that the CPU suite can run it on rank threads against the emulated library.)"""
     from jaxsso_b200 import dist_multigrid as dmg
-    D = nat.DeviceArray
-    L = nat.lib()
-    t_s = time.perf_counter()
-    perm, bounds = dmg.owner_permutation(owner, world)
-    rmd = dmg.renumber_mesh(gmd, perm)
-    inv_perm = np.empty(gmd.n_node, np.int64)
-    inv_perm[perm] = np.arange(gmd.n_node)
-    hd = nat.Handle(rmd.n_node, rmd.cnct_quads, rmd.cnct_beams, rmd.known, device=device)
-    levels = hd.mg_setup()
-    rp_, ci_ = hd.pattern()
-    plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=min_dist_nodes)
-    del levels
-    nid = bcast(nat.nccl_unique_id() if rank == 0 else None)
-    hd.mg_set_dist(nid, rank, world, plan)
-    rc_d, rq_d, rb_d = D.from_host(rmd.crds), D.from_host(rmd.prop_quads), D.from_host(rmd.prop_beams)
-    rf_d, ru_d = D.from_host(rmd.loads), D((rmd.ndof,))
-    rl2g_d = D.from_host(inv_perm[lm.l2g].astype(np.int32))
-    u_rep = dev['uu'].download()                      # local part of the earlier (replicated) solve
-    t_s = time.perf_counter() - t_s
-    barrier()
     t0 = time.perf_counter()
-    fsd = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
-    nat.gather_rows(ru_d, rl2g_d, 6, out=dev['uu'])
-    h.backward(dev['crds'], dev['pq'], dev['pb'], dev['uu'], None, dev['dc'], dev['dq'], None, opts=opts)
-    L.jsso_stream_sync(None)
-    dtd = max_over_ranks(time.perf_counter() - t0)
-    u_dst = dev['uu'].download()
-    diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
-    ex, ar = hd.mg_dist_counters()
-    res = {'seconds': dtd, 'evals_per_s': 1.0 / dtd, 'pcg_iterations': fsd.iterations,
-           'true_relres': fsd.relres, 'ms_per_pcg_iteration': 1e3 * dtd / max(fsd.iterations, 1),
-           'u_rel_diff_vs_replicated_solve': diff, 'halo_exchanges': ex, 'scalar_allreduces': ar,
-           'setup_s': t_s, 'plan': dmg.plan_summary(plan),
-           'solve': 'V-cycle PCG distributed by row ranges over NCCL send/recv (replicated assembly + numeric '
-                    'multigrid setup), adjoint partitioned'}
-    if on_partial:
-        on_partial(dict(res))
-    if allgather is not None:
-        # the same solve again with the exchanges over peer memory (jsso_mg_p2p_connect): push + wait/unpack kernels
-        # and mailbox all-reduces instead of NCCL calls
-        try:
-            hd.mg_p2p_connect(plan, allgather)
-            barrier()
-            t0 = time.perf_counter()
-            fsp = hd.forward(rc_d, rq_d, rb_d, rf_d, ru_d, opts=opts)
-            nat.gather_rows(ru_d, rl2g_d, 6, out=dev['uu'])
-            h.backward(dev['crds'], dev['pq'], dev['pb'], dev['uu'], None, dev['dc'], dev['dq'], None, opts=opts)
-            L.jsso_stream_sync(None)
-            dtp = max_over_ranks(time.perf_counter() - t0)
-            u_p2p = dev['uu'].download()
-            dfp = max_over_ranks(float(np.linalg.norm(u_p2p - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
-            hd.mg_dist_counters()
-            res['peer_memory'] = {'seconds': dtp, 'evals_per_s': 1.0 / dtp, 'pcg_iterations': fsp.iterations,
-                                  'ms_per_pcg_iteration': 1e3 * dtp / max(fsp.iterations, 1),
-                                  'u_rel_diff_vs_replicated_solve': dfp, 'active': bool(hd.mg_dist_p2p)}
-        except nat.JssoError as e:
-            res['peer_memory'] = {'error': str(e)}
-    hd.close()
-    return res
+    hd = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=device)
+    rp, ci = hd.pattern()
+    if partition_kind == 'rcb':
+        from jaxsso_b200 import partition
+        perm, bounds = dmg.owner_permutation(partition.rcb_owner(gmd.crds[:, :2], world), world)
+        kind = 'rcb'
+    elif partition_kind == 'natural':
+        perm, bounds, kind = None, dmg.natural_bounds(gmd.n_node, world), 'natural'
+    else:
+        perm, bounds, kind = dmg.solve_partition(gmd.crds, rp, ci, world)
+    smd = gmd
+    if kind == 'rcb':
+        hd.close()
+        smd = dmg.renumber_mesh(gmd, perm)
+        hd = nat.Handle(smd.n_node, smd.cnct_quads, smd.cnct_beams, smd.known, device=device)
+        rp, ci = hd.pattern()
+        levels = hd.mg_setup(levels=dmg.build_hierarchy_invariant(rp, ci, perm))
+    else:
+        perm = None
+        levels = hd.mg_setup()
+    plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist_nodes)
+    hd.mg_set_dist(bcast(nat.nccl_unique_id() if rank == 0 else None), rank, world, plan)
+    if use_p2p:
+        hd.mg_p2p_connect(plan, allgather)
+    info = {'nodes_per_level': [a for a, _ in hd.mg_levels] + [hd.mg_levels[-1][1]],
+            'symbolic_setup_s': time.perf_counter() - t0, 'partition': kind,
+            'exchange': 'NVLink peer memory (push / wait kernels, mailbox all-reduce)' if use_p2p else 'NCCL send/recv',
+            'distributed': dmg.plan_summary(plan)}
+    return hd, smd, perm, info, levels
+
+
+def pcg_iteration_bytes(nnzb0, levels):
+    """Algorithmic HBM bytes of ONE fused multigrid-PCG iteration (Chebyshev-1), whole system, from the hierarchy's
+    sizes.  Matrix blocks: 288 B (FP64), 144 B (FP32), 72 B (binary16) + 4 B column index; a vector pass = 48 B per
+    node.  Fine level: q = A p in FP64 (nnzb*292 + n*100), two binary16 products (r0 = b - A b / theta,
+    z = x + (b - A x) / theta: rowptr, gathered x, b, y), restriction and prolongation (FP32 P^T, P), direction
+    update (3 passes) and x / r update (6 passes).  Coarse level l: two FP32 products with A_l, P_l^T, P_l, two
+    smoother updates (3 + 4 passes incl. the 288-byte D^-1 block per node), b / x traffic."""
+    n0 = levels[0]['n_f']
+    fine = {'outer_spmv_fp64': nnzb0 * 292 + n0 * 100,
+            'vcycle_fine_products_fp16': 2 * (nnzb0 * 76 + n0 * (4 + 3 * 48)),
+            'restrict_prolong_fp32': 2 * levels[0]['nnz_p'] * 148 + (n0 + levels[0]['n_c']) * 2 * 48 + n0 * 48,
+            'pcg_vector_updates': 9 * n0 * 48}
+    coarse = 0
+    for l in range(1, len(levels)):
+        lv, nl = levels[l], levels[l]['n_f']
+        nnz_a = levels[l - 1]['nnz_c']
+        coarse += 2 * (nnz_a * 148 + nl * (4 + 3 * 48)) + 2 * lv['nnz_p'] * 148 + (nl + lv['n_c']) * 2 * 48 + nl * 48
+        coarse += nl * (7 * 48 + 2 * 288)
+    fine['coarse_levels'] = coarse
+    fine['total'] = sum(fine.values())
+    return fine
 
 
 # ------------------------------------------------------------------------------ own arm
@@ -379,40 +375,46 @@ def run_b200(args):
             dist.all_gather_object(hs, h.p2p_export())
             h.p2p_connect(hs, lm.remote_start)
     mg_info = None
+    mg_levels = None
     hg = None
+    smd, solve_perm = gmd, None     # the mesh the solve handle sees; new -> old node order if it is renumbered
     if world > 1 and args.solve and args.precond != 'block_jacobi':
-        # N > 1 (measured default): the solve is > 99 % of a gradient evaluation, so every
-        # rank keeps a handle of the WHOLE mesh and runs the multigrid solve redundantly (1.2 ms of redundant
-        # assembly, no communication); Ke+assembly+adjoint of the metric stay partitioned.  --precond
-        # block_jacobi runs the distributed CG (halo pushes over NVLink peer memory) instead.
-        t_mg = time.perf_counter()
-        smd, inv_perm = gmd, None     # the mesh the solve handle sees
-        if args.dist_mg:
-            # row-range distributed V-cycle PCG (jsso_mg_set_dist): the whole mesh renumbered so that every rank's
-            # nodes are one range; assembly + numeric multigrid setup stay replicated, the iteration is distributed
-            from jaxsso_b200 import dist_multigrid as dmg
-            perm, bounds = dmg.owner_permutation(owner, world)
-            smd = dmg.renumber_mesh(gmd, perm)
-            inv_perm = np.empty(gmd.n_node, np.int64)
-            inv_perm[perm] = np.arange(gmd.n_node)
-        hg = nat.Handle(smd.n_node, smd.cnct_quads, smd.cnct_beams, smd.known, device=local_rank)
-        levels = hg.mg_setup()
-        mg_info = {'nodes_per_level': [a for a, _ in hg.mg_levels] + [hg.mg_levels[-1][1]],
-                   'symbolic_setup_s': time.perf_counter() - t_mg}
-        if args.dist_mg:
-            rp_, ci_ = hg.pattern()
-            plan = dmg.build_plan(rp_, ci_, levels, bounds, min_dist_nodes=args.min_dist_nodes)
-            idbuf2 = [nat.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(idbuf2, src=0)
-            hg.mg_set_dist(idbuf2[0], rank, world, plan)
-            mg_info['distributed'] = dmg.plan_summary(plan)
-        del levels
+        # N > 1: the solve is > 95 % of a gradient evaluation.  Every rank keeps a handle of the WHOLE mesh whose
+        # multigrid V-cycle PCG is distributed by row ranges (jsso_mg_set_dist), halo exchanges and all-reduces over
+        # NVLink peer memory; Ke+assembly+adjoint of the metric stay partitioned (RCB, ghost elements).
+        # --replicated-solve: the same handle without the distribution (every rank solves redundantly).
+        # --precond block_jacobi: the distributed CG over the RCB partition instead.
+        def bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        def allgather_obj(obj):
+            box = [None] * world
+            dist.all_gather_object(box, obj)
+            return box
+
+        if args.replicated_solve:
+            t_mg = time.perf_counter()
+            hg = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=local_rank)
+            mg_levels = hg.mg_setup()
+            mg_info = {'nodes_per_level': [a for a, _ in hg.mg_levels] + [hg.mg_levels[-1][1]],
+                       'symbolic_setup_s': time.perf_counter() - t_mg}
+        else:
+            hg, smd, solve_perm, mg_info, mg_levels = distributed_solve_handle(
+                nat, gmd, rank, world, local_rank, bcast, allgather_obj, args.min_dist_nodes, use_p2p=args.p2p,
+                partition_kind=args.solve_partition)
     if world == 1 and args.solve and args.precond != 'block_jacobi':
         # single GPU: smoothed-aggregation multigrid preconditioner (symbolic hierarchy, once per model)
         t_mg = time.perf_counter()
-        h.mg_setup()
+        mg_levels = h.mg_setup()
         mg_info = {'nodes_per_level': [a for a, _ in h.mg_levels] + [h.mg_levels[-1][1]],
                    'symbolic_setup_s': time.perf_counter() - t_mg}
+    mg_bytes_it = None
+    if mg_info is not None and args.cheb_degree == 1:
+        mg_bytes_it = pcg_iteration_bytes(h.sizes.nnzb if world == 1 else hg.sizes.nnzb, mg_levels)
+    if world == 1:
+        mg_levels = None        # (at N > 1 the replicated check handle re-uses them)
     D = nat.DeviceArray
     crds_d, pq_d, pb_d = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams)
     u_d, lam_d, f_d = D.from_host(u), D.from_host(lam), D.from_host(md.loads)
@@ -486,49 +488,131 @@ def run_b200(args):
     h2d = 8 * (md.crds.size + md.prop_quads.size + md.prop_beams.size + 2 * u.size)
     d2h = 8 * (out_bufs[0].size + out_bufs[1].size)
 
-    # full shape-gradient evaluation incl. the solve (metric M2), once
+    # full shape-gradient evaluation incl. the solve (metric M2): one warm-up evaluation, then the mean of
+    # --grad-evals timed ones (each: Ke+assembly, block-Jacobi scaling, numeric multigrid setup, PCG for u to the TRUE
+    # relative residual rtol, lam = u/2, adjoint)
     grad_eval = None
+    dist_fail = None
     if args.solve:
         precond = args.precond if (world == 1 or hg is not None) else 'block_jacobi'
         opts = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, check_every=100, compliance=True,
                              precond=precond, cheb_degree=args.cheb_degree)
         uu_d = D((md.ndof,))
-        if hg is not None:   # replicated multigrid solve on the whole mesh, partitioned adjoint
+        hs = hg if hg is not None else h           # the handle that solves
+        distributed = hg is not None and not args.replicated_solve
+        if hg is not None:   # whole-mesh solve handle (distributed or replicated), partitioned adjoint
             gc_d, gq_d, gb_d = D.from_host(smd.crds), D.from_host(smd.prop_quads), D.from_host(smd.prop_beams)
             gf_d, gu_d = D.from_host(smd.loads), D((smd.ndof,))
-            l2g_d = D.from_host((lm.l2g if inv_perm is None else inv_perm[lm.l2g]).astype(np.int32))
-        barrier()
-        t0 = time.perf_counter()
-        try:
-            if hg is not None:
-                fs = hg.forward(gc_d, gq_d, gb_d, gf_d, gu_d, opts=opts)
-                nat.gather_rows(gu_d, l2g_d, 6, out=uu_d)
+            if solve_perm is None:
+                l2s = lm.l2g
             else:
-                fs = h.forward(crds_d, pq_d, pb_d, f_d, uu_d, opts=opts)
-            h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=opts)
+                inv_perm = np.empty(gmd.n_node, np.int64)
+                inv_perm[solve_perm] = np.arange(gmd.n_node)
+                l2s = inv_perm[lm.l2g]
+            l2g_d = D.from_host(l2s.astype(np.int32))
+        else:
+            gc_d, gq_d, gb_d, gf_d, gu_d = crds_d, pq_d, pb_d, f_d, uu_d
+
+        def one_eval(o_):
+            fs_ = hs.forward(gc_d, gq_d, gb_d, gf_d, gu_d, opts=o_)
+            if hg is not None:
+                nat.gather_rows(gu_d, l2g_d, 6, out=uu_d)
+            h.backward(crds_d, pq_d, pb_d, uu_d, None, dc_d, dq_d, None, opts=o_)
             L.jsso_stream_sync(None)
-            ok = True
+            return fs_
+
+        fs, ok, dts = None, True, []
+        try:
+            one_eval(opts)                       # warm-up (graph capture, lazy peer mappings, clocks)
+            for _ in range(max(1, args.grad_evals)):
+                barrier()
+                t0 = time.perf_counter()
+                fs = one_eval(opts)
+                dts.append(max_over_ranks(time.perf_counter() - t0))
         except nat.JssoError as e:
             fs, ok = None, str(e)
-        dt = max_over_ranks(time.perf_counter() - t0)
         if fs is not None:
-            grad_eval = {'seconds': dt, 'evals_per_s': 1.0 / dt, 'pcg_iterations': fs.iterations,
-                         'pcg_restarts': fs.restarts, 'true_relres': fs.relres, 'rtol': args.rtol,
-                         'ms_per_pcg_iteration': 1e3 * dt / max(fs.iterations, 1),
-                         'preconditioner': (f'smoothed-aggregation multigrid (V-cycle, Chebyshev-{args.cheb_degree}, FP32 level matrices)'
+            dt = float(np.mean(dts))
+            u_est = None
+            # how accurate is u at this rtol?  The same system solved 100x tighter (or to the attainable accuracy of
+            # FP64, whichever comes first): u_err_estimate = ||u(rtol) - u(tight)|| / ||u(tight)||
+            if args.u_check and precond != 'block_jacobi':
+                u_loose = gu_d.download()
+                ot = nat.make_opts(rtol=args.rtol * 1e-2, maxiter=args.maxiter, compliance=True, precond=precond,
+                                   cheb_degree=args.cheb_degree, use_x0=True)
+                t0 = time.perf_counter()
+                st_t = hs.pcg(gf_d, gu_d, opts=ot, allow_noconv=True)
+                u_tight = gu_d.download()
+                u_est = {
+                    'value': float(np.linalg.norm(u_loose - u_tight) / np.linalg.norm(u_tight)),
+                    'vs': f'the same system continued to rtol {args.rtol * 1e-2:g} or the attainable accuracy',
+                    'tight_relres': st_t.relres, 'tight_extra_iterations': st_t.iterations,
+                    'seconds': time.perf_counter() - t0, 'target': 1e-8}
+            # stages of one evaluation (same call sequence, timed one by one)
+            barrier()
+            t0 = time.perf_counter()
+            hs.assemble(gc_d, gq_d, gb_d, apply_bc=True)
+            L.jsso_stream_sync(None)
+            t_asm = max_over_ranks(time.perf_counter() - t0)
+            o1 = nat.make_opts(rtol=args.rtol, maxiter=1, compliance=True, precond=precond, cheb_degree=args.cheb_degree)
+            t0 = time.perf_counter()
+            try:
+                hs.pcg(gf_d, gu_d, opts=o1, allow_noconv=True)     # scaling + numeric multigrid setup + 1 iteration
+            except nat.JssoError:
+                pass
+            L.jsso_stream_sync(None)
+            t_setup1 = max_over_ranks(time.perf_counter() - t0)
+            it = max(fs.iterations, 1)
+            ms_it = 1e3 * max(dt - t_asm - t_setup1 - ms_adj * 1e-3, 0.0) / max(it - 1, 1)
+            grad_eval = {'seconds': dt, 'evals_per_s': 1.0 / dt, 'evals_timed': len(dts), 'seconds_each': dts,
+                         'pcg_iterations': fs.iterations, 'pcg_restarts': fs.restarts, 'true_relres': fs.relres,
+                         'rtol': args.rtol,
+                         'ms_per_pcg_iteration': ms_it,
+                         'stage_s': {'assembly_whole_mesh': t_asm, 'scaling_numeric_mg_setup_first_iteration': t_setup1,
+                                     'pcg_iterations': ms_it * 1e-3 * (it - 1), 'adjoint': ms_adj * 1e-3},
+                         'preconditioner': (f'smoothed-aggregation multigrid (V-cycle, Chebyshev-{args.cheb_degree}; fine level '
+                                            f'binary16, coarse levels FP32 storage, FP64 vectors and accumulation; fused iteration, '
+                                            f'device-resident PCG scalars)'
                                             if precond != 'block_jacobi' else 'block-Jacobi'),
                          'solve': ('single GPU' if world == 1 else
-                                   (('V-cycle PCG distributed by row ranges (replicated assembly + numeric setup), '
-                                     'adjoint partitioned') if (hg is not None and args.dist_mg) else
-                                    'replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
-                                    else 'distributed CG over the partition')),
+                                   ('V-cycle PCG distributed by row ranges over ' + mg_info['exchange'] +
+                                    ' (assembly + numeric setup replicated), adjoint partitioned') if distributed else
+                                   'replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
+                                   else 'distributed CG over the partition'),
                          'multigrid': mg_info,
+                         'u_err_estimate': u_est,
                          'note': 'Ke+assembly, PCG for u (numeric multigrid setup included), lam = u/2 '
-                                 '(compliance), adjoint'}
-            if hg is not None and args.dist_mg:
+                                 '(compliance), adjoint; mean of the timed evaluations after one warm-up evaluation'}
+            if distributed:
                 grad_eval['halo_exchanges'], grad_eval['scalar_allreduces'] = hg.mg_dist_counters()
+            # N > 1: the distributed solve against the SAME handle logic without the distribution (replicated solve on
+            # rank 0's device only would need another handle; every rank solves redundantly here) -- fail loudly
+            if distributed and args.dist_check:
+                hr = nat.Handle(smd.n_node, smd.cnct_quads, smd.cnct_beams, smd.known, device=local_rank)
+                hr.mg_setup(levels=mg_levels)
+                ur_d = D((smd.ndof,))
+                fr = hr.forward(gc_d, gq_d, gb_d, gf_d, ur_d, opts=opts)
+                hs.forward(gc_d, gq_d, gb_d, gf_d, gu_d, opts=opts)
+                u_rep, u_dst = ur_d.download(), gu_d.download()
+                diff = max_over_ranks(float(np.linalg.norm(u_dst - u_rep) / max(np.linalg.norm(u_rep), 1e-300)))
+                grad_eval['u_rel_diff_vs_replicated_solve'] = diff
+                grad_eval['replicated_pcg_iterations'] = fr.iterations
+                hr.close()
+                if not (diff <= 1e-8):
+                    dist_fail = f'distributed solve differs from the replicated solve: {diff:.3e} > 1e-8'
         else:
-            grad_eval = {'error': ok, 'seconds': dt}
+            grad_eval = {'error': ok, 'seconds': float(np.mean(dts)) if dts else None}
+            dist_fail = ok if world > 1 else None
+
+    # FP64 peak of this device, measured in this run (DFMA chains, jsso_fp64_peak) -- the denominator of the FP64-bound
+    # roofline; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s if the measurement is skipped
+    fp64_peak, fp64_src = 37.2, 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)'
+    if args.fp64_peak_seconds > 0:
+        try:
+            tf, sec = nat.fp64_peak(local_rank, args.fp64_peak_seconds)
+            fp64_peak, fp64_src = tf, f'measured in this run: DFMA-chain microbenchmark (jsso_fp64_peak), {sec:.2f} s sustained'
+        except Exception:
+            pass
 
     def build_out():
         hbm, peak_src = peaks()
@@ -572,8 +656,8 @@ def run_b200(args):
                      'algorithmic_bytes_per_launch': spmv_bytes, 'ms': ms_spmv, 'peak_source': peak_src}
         adj_flops = 14000.0 * s.n_quad
         roof_adj = {'kernel': 'quad_adjoint_kernel(+node_gather)', 'bound': 'fp64', 'achieved': adj_flops / (ms_adj * 1e-3) / 1e12,
-                    'peak': 37.2, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / 37.2,
-                    'peak_source': 'nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)', 'ms': ms_adj,
+                    'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': adj_flops / (ms_adj * 1e-3) / 1e12 / fp64_peak,
+                    'peak_source': fp64_src, 'ms': ms_adj,
                     'traffic': ncu.get('quad_adjoint_kernel'),
                     'algorithmic_flops_per_launch': adj_flops}
         value = n_quad_total / (ms_step * 1e-3)
@@ -583,7 +667,11 @@ def run_b200(args):
                'config': {'workload': f'synthetic {N}x{N * world if args.scaling == "weak" else N} MITC4 shell plate '
                                       f'(BASELINE configs[2]), jittered; {n_quad_total} quads, '
                                       f'{6 * gmd.n_node} dof; step = Ke+assembly (geometry records + warp tasks) + adjoint reduction',
-                          'parallelism': (f'rcb{world}+' + ('p2p' if args.p2p else 'nccl')) if world > 1 else 'single',
+                          'parallelism': ((f'rcb{world} element work (ghost elements, no collective) + ' +
+                                           ('distributed CG, ' if (hg is None and args.solve) else
+                                            'replicated multigrid solve, ' if args.replicated_solve else
+                                            'row-range distributed multigrid solve, ' if args.solve else '') +
+                                           ('NVLink peer memory' if args.p2p else 'NCCL')) if world > 1 else 'single'),
                           'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
                           'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
                'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -594,6 +682,23 @@ def run_b200(args):
                'kernel_ms': {'assembly': ms_asm, 'quad_geometry': ms_geo, 'assemble_tasks': ms_tasks, 'adjoint': ms_adj,
                              'spmv': ms_spmv}, 'setup_s': t_setup,
                'grad_eval': grad_eval}
+        if grad_eval and 'error' not in grad_eval:
+            # metric M2 (the second half of BASELINE.json's metric) as a first-class entry of the line
+            out['m2'] = {'metric': 'full shape-gradient evaluations/s (Ke, assembly, solve, adjoint) at '
+                                   f'{n_quad_total} quads', 'value': grad_eval['evals_per_s'], 'unit': 'evals/s',
+                         'seconds_per_eval': grad_eval['seconds'], 'n_gpus': world, 'rtol': args.rtol,
+                         'pcg_iterations': grad_eval['pcg_iterations'],
+                         'ms_per_pcg_iteration': grad_eval['ms_per_pcg_iteration'],
+                         'u_err_estimate': (grad_eval.get('u_err_estimate') or {}).get('value')}
+            if mg_bytes_it:
+                bi = mg_bytes_it['total'] / max(world, 1)     # row ranges: every rank streams 1/N of every level it distributes
+                ms_it = grad_eval['ms_per_pcg_iteration']
+                out['roofline_pcg_iteration'] = {
+                    'kernel': 'one multigrid-PCG iteration (4 fine-level V-cycle products, coarse levels, direction, q = A p, update)',
+                    'bound': 'hbm', 'achieved': bi / (ms_it * 1e-3) / 1e9 if ms_it > 0 else None, 'peak': hbm, 'unit': 'GB/s',
+                    'frac': (bi / (ms_it * 1e-3) / 1e9 / hbm) if ms_it > 0 else None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_iteration_per_gpu': bi, 'breakdown_bytes_whole_system': mg_bytes_it, 'ms': ms_it,
+                    'traffic': None}
         if world == 1 and args.cpu_baseline:
             cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
                    '--ref-size', str(args.ref_size), '--ref-serial', '--ref-grad']
@@ -607,49 +712,13 @@ def run_b200(args):
 
     out = build_out() if rank == 0 else None
 
-    # N > 1, extra leg: the same gradient evaluation with the V-cycle PCG DISTRIBUTED by row ranges
-    # (jsso_mg_set_dist).  That path was written after round 1's GPU budget was spent: its logic is verified on the
-    # CPU (emulated driver, rank threads), it had not run on hardware when this was committed.  So it runs LAST,
-    # after the bench line is complete, under a watchdog: if it hangs, rank 0 prints the line without it and every
-    # rank exits; its u is compared with the replicated solve of the same run.
-    if world > 1 and hg is not None and not args.dist_mg and args.dist_leg and grad_eval and 'error' not in grad_eval:
-        import threading
-
-        partial = {}
-
-        def on_timeout():
-            if rank == 0:
-                leg_ = dict(partial) if partial else {}
-                leg_['error'] = f'timeout after {args.dist_leg_timeout} s (watchdog)' + \
-                                (' in the peer-memory part' if partial else '')
-                out['grad_eval_dist'] = leg_
-                print(json.dumps(out), flush=True)
-            os._exit(0)
-
-        wd = threading.Timer(args.dist_leg_timeout, on_timeout)
-        wd.daemon = True
-        wd.start()
-        def bcast(obj):
-            box = [obj]
-            dist.broadcast_object_list(box, src=0)
-            return box[0]
-
-        def allgather_obj(obj):
-            box = [None] * world
-            dist.all_gather_object(box, obj)
-            return box
-
-        try:
-            leg = distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, local_rank, opts, args.min_dist_nodes,
-                                        dict(crds=crds_d, pq=pq_d, pb=pb_d, uu=uu_d, dc=dc_d, dq=dq_d),
-                                        barrier, max_over_ranks, bcast,
-                                        allgather=(allgather_obj if args.dist_leg_p2p else None),
-                                        on_partial=partial.update)
-        except Exception as e:   # an error on one rank only would leave the others in a collective: the watchdog ends them
-            leg = {'error': f'{type(e).__name__}: {e}'}
-        wd.cancel()
+    if dist_fail:
         if rank == 0:
-            out['grad_eval_dist'] = leg
+            out['error'] = dist_fail
+            print(json.dumps(out), flush=True)
+        if dist:
+            dist.destroy_process_group()
+        sys.exit(1)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -670,16 +739,21 @@ def main():
     ap.add_argument('--no-solve', dest='solve', action='store_false')
     ap.add_argument('--no-p2p', dest='p2p', action='store_false',
                     help='distributed CG over NCCL send/recv + all-reduce instead of peer-memory kernels')
-    ap.add_argument('--dist-mg', action='store_true',
-                    help='N > 1: distribute the multigrid V-cycle PCG by row ranges (jsso_mg_set_dist) instead of '
-                         'solving redundantly on every rank')
-    ap.add_argument('--no-dist-leg', dest='dist_leg', action='store_false',
-                    help='N > 1: skip the extra distributed-multigrid gradient evaluation at the end')
-    ap.add_argument('--no-dist-leg-p2p', dest='dist_leg_p2p', action='store_false',
-                    help='that leg: skip the second solve with the exchanges over peer memory')
-    ap.add_argument('--dist-leg-timeout', type=float, default=240.0, help='watchdog of that leg, seconds')
+    ap.add_argument('--replicated-solve', action='store_true',
+                    help='N > 1: every rank solves the whole system redundantly instead of the row-range distributed '
+                         'V-cycle PCG')
+    ap.add_argument('--solve-partition', default='auto', choices=['auto', 'natural', 'rcb'],
+                    help='N > 1: row partition of the distributed solve (auto: contiguous ranges of the mesh numbering '
+                         'when it is banded, else RCB with renumbering)')
+    ap.add_argument('--no-dist-check', dest='dist_check', action='store_false',
+                    help='N > 1: skip the comparison of the distributed solve with a replicated solve of the same system')
+    ap.add_argument('--fp64-peak-seconds', type=float, default=1.0,
+                    help='duration of the FP64 DFMA microbenchmark behind roofline_adjoint.peak (0: nominal peak)')
+    ap.add_argument('--grad-evals', type=int, default=3, help='timed full gradient evaluations (after one warm-up)')
+    ap.add_argument('--no-u-check', dest='u_check', action='store_false',
+                    help='skip the tighter solve that estimates the error of u at --rtol')
     ap.add_argument('--min-dist-nodes', type=int, default=20000,
-                    help='multigrid levels with fewer nodes run replicated under --dist-mg')
+                    help='multigrid levels with fewer nodes run replicated in the distributed solve')
     ap.add_argument('--rtol', type=float, default=1e-8)
     ap.add_argument('--precond', default='auto', choices=['auto', 'block_jacobi', 'multigrid'])
     ap.add_argument('--maxiter', type=int, default=400000)

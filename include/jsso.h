@@ -211,7 +211,10 @@ int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_level_desc* le
  * uploaded; assembly and the numeric multigrid setup stay replicated, the V-cycle and PCG products are computed
  * by row ranges with the halo exchanges described per level below, levels >= n_dist run replicated.  Collective
  * over the communicator of `nccl_id` (jsso_nccl_unique_id on rank 0, distributed by the caller).
- * bounds_h: (n_dist + 1) x (n_rank + 1) int32, row-range bounds of levels 0..n_dist. */
+ * bounds_h: (n_dist + 1) x (n_rank + 1) int32, row-range bounds of levels 0..n_dist.
+ * halo: n_halo entries -- one per distributed level, plus (n_halo = n_dist + 1) the all-gather of the first
+ * replicated level written as an exchange plan ("every rank reads every other rank's whole range"), so that over
+ * peer memory it needs no NCCL call either. */
 typedef struct {
   int32_t n_peer;
   const int32_t *peer_rank;          /* [n_peer] */
@@ -221,7 +224,7 @@ typedef struct {
                                        * (needed by the peer-memory path only) */
 } jsso_mg_halo_desc;
 int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
-                     const int32_t* bounds_h, const jsso_mg_halo_desc* halo);
+                     const int32_t* bounds_h, int32_t n_halo, const jsso_mg_halo_desc* halo);
 /* Optional peer-memory path of the distributed solve (NVLink, CUDA IPC; the distributed CG's counterpart is
  * jsso_p2p_export / jsso_p2p_connect): halo exchanges become a push kernel storing straight into the peers'
  * receive arenas + a wait/unpack kernel, scalar all-reduces a mailbox kernel -- no library call on the iteration

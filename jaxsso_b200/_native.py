@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get('JSSO_LIB') or os.path.join(_HERE, 'libjsso.so')   # J
 ERR_NAMES = {0: 'OK', 1: 'ARG', 2: 'CUDA', 3: 'NOCONV', 4: 'NAN', 5: 'BADJAC', 6: 'DEGENERATE_BEAM',
              7: 'NOT_SPD', 8: 'NCCL', 9: 'STATE'}
 JSSO_ERR_NOCONV = 3
+JSSO_DEVICE_NONE = -1   # symbolic-only handle (host pattern / task lists, no device)
 
 
 class JssoError(RuntimeError):
@@ -119,7 +120,7 @@ def lib():
     L.jsso_spmv.argtypes = [vp, vp, vp, vp]
     L.jsso_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_mg_setup.argtypes = [vp, i32, C.POINTER(MgLevelDesc)]
-    L.jsso_mg_set_dist.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(MgHaloDesc)]
+    L.jsso_mg_set_dist.argtypes = [vp, vp, i32, i32, i32, vp, i32, C.POINTER(MgHaloDesc)]
     L.jsso_mg_dist_counters.argtypes = [vp, vp]
     L.jsso_mg_p2p_reserve.argtypes = [vp, i32]
     L.jsso_mg_p2p_export.argtypes = [vp, vp]
@@ -423,7 +424,7 @@ class Handle:
         mine = dist_multigrid.rank_plan(plan, rank)
         n_dist = plan['n_dist']
         bounds = np.ascontiguousarray(np.stack(plan['bounds'][:n_dist + 1]), np.int32)
-        descs = (MgHaloDesc * max(n_dist, 1))()
+        descs = (MgHaloDesc * max(len(mine), 1))()      # n_dist levels (+ the all-gather plan of the first replicated one)
         keep = []
         for d, lv in zip(descs, mine):
             d.n_peer = int(lv['peer_rank'].shape[0])
@@ -432,7 +433,8 @@ class Handle:
                 keep.append(a)
                 setattr(d, k, a.ctypes.data)
         idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
-        self._ck(lib().jsso_mg_set_dist(self.h, _ptr(idb), int(rank), int(n_rank), int(n_dist), _ptr(bounds), descs))
+        self._ck(lib().jsso_mg_set_dist(self.h, _ptr(idb), int(rank), int(n_rank), int(n_dist), _ptr(bounds),
+                                        len(mine), descs))
 
     def mg_p2p_connect(self, plan, allgather):
         """Switch the distributed multigrid solve to the peer-memory exchange (collective).  `allgather(bytes)` returns

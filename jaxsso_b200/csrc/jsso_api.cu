@@ -1103,8 +1103,10 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
 // (jaxsso_b200/dist_multigrid.py), with the hierarchy already uploaded by jsso_mg_setup.  Collective: every rank
 // calls it (ncclCommInitRank).  bounds: (n_dist + 1) x (n_rank + 1) row-range bounds per level; halo: n_dist entries.
 extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
-                                const int32_t* bounds, const jsso_mg_halo_desc* halo) {
+                                const int32_t* bounds, int32_t n_halo, const jsso_mg_halo_desc* halo) {
   if (!h || !nccl_id || !bounds || (n_dist > 0 && !halo)) return JSSO_ERR_ARG;
+  if (n_halo != n_dist && n_halo != n_dist + 1)
+    return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: n_halo is n_dist, or n_dist + 1 with the all-gather plan of the first replicated level");
   NEED_GPU();
   CK(cudaSetDevice(h->device));
   if (h->mg.empty()) return fail(h, JSSO_ERR_STATE, "jsso_mg_set_dist needs the hierarchy (jsso_mg_setup) first");
@@ -1125,7 +1127,7 @@ extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int3
       if (b[r + 1] < b[r]) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bounds not monotone");
     D.bounds.emplace_back(b, b + n_rank + 1);
   }
-  for (int l = 0; l < n_dist; ++l) {
+  for (int l = 0; l < n_halo; ++l) {   // entry n_dist (optional): "halo" = everybody's whole range, i.e. the all-gather
     const jsso_mg_halo_desc& d = halo[l];
     const int n_l = (l == 0) ? h->sym.n_row : h->mg[l - 1].n_c;
     const int lo = D.bounds[l][rank], hi = D.bounds[l][rank + 1];
@@ -1166,8 +1168,8 @@ extern "C" int jsso_mg_p2p_export(jsso_handle* h, uint8_t out[128]) {
   CK(cudaSetDevice(h->device));
   jsso_handle::MgDist& D = h->mgd;
   if (D.n_rank < 2 || !D.comm) return fail(h, JSSO_ERR_STATE, "jsso_mg_p2p_export needs jsso_mg_set_dist first");
-  if (D.n_rank > P2P_MAX_RANKS || D.n_dist > MGD_MAX_LEVELS)
-    return fail(h, JSSO_ERR_STATE, "peer-memory multigrid: at most 16 ranks and 4 distributed levels");
+  if (D.n_rank > P2P_MAX_RANKS || (int)D.lv.size() > MGD_MAX_LEVELS)
+    return fail(h, JSSO_ERR_STATE, "peer-memory multigrid: at most 16 ranks and 4 exchange plans (distributed levels + the all-gather)");
   for (const auto& L : D.lv)
     if (L.remote_off.size() != L.peers.size() || L.peers.size() > (size_t)P2P_MAX_RANKS)
       return fail(h, JSSO_ERR_STATE, "peer-memory multigrid: the plan has no remote offsets");
@@ -1538,6 +1540,9 @@ static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st) {
 
 // every rank's row range of a level-l vector to every other rank (ranges are contiguous: no packing)
 static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st) {
+  // the first replicated level has its own exchange plan (everybody's whole range): over peer memory it is a push +
+  // wait/unpack kernel pair like every halo exchange, no NCCL call on the iteration path
+  if (h->mgd.ctx && l == h->mgd.n_dist && (int)h->mgd.lv.size() > l) return mgd_exchange(h, l, v, st);
   const std::vector<int32_t>& b = h->mgd.bounds[l];
   const int me = h->mgd.rank;
   const size_t mine = 6 * (size_t)(b[me + 1] - b[me]);

@@ -49,6 +49,88 @@ def renumber_mesh(md: MeshData, perm):
                     loads=md.loads.reshape(-1, 6)[perm].reshape(-1), design_nodes=inv[md.design_nodes])
 
 
+def natural_bounds(n_node, n_rank):
+    """Equal contiguous ranges of the mesh's own numbering (no renumbering at all)."""
+    return np.array([(n_node * r) // n_rank for r in range(n_rank + 1)], np.int32)
+
+
+def halo_fraction(rowptr, colidx, bounds):
+    """Largest ratio (nodes a rank reads from other ranks) / (nodes it owns) over the ranks, for row ranges
+    `bounds` of the block-CSR pattern: small for a banded numbering cut into contiguous ranges."""
+    worst = 0.0
+    for r in range(bounds.shape[0] - 1):
+        s, e = int(bounds[r]), int(bounds[r + 1])
+        if e <= s:
+            continue
+        cols = np.unique(colidx[rowptr[s]:rowptr[e]])
+        worst = max(worst, float(np.count_nonzero((cols < s) | (cols >= e))) / (e - s))
+    return worst
+
+
+def solve_partition(crds, rowptr, colidx, n_rank, max_halo_fraction=0.05):
+    """Row partition of the distributed multigrid solve: (perm, bounds, kind).
+
+    * 'natural': the mesh numbering is banded enough (structured grids numbered row by row, meshes already ordered
+      by a bandwidth-reducing permutation) that equal contiguous ranges of it have small halos -- no renumbering, so
+      the aggregates, the hierarchy and hence the PCG iteration count are EXACTLY those of the single-GPU solve;
+    * 'rcb': recursive coordinate bisection + ownership renumbering (`owner_permutation`); use
+      `build_hierarchy_invariant` so that the aggregates are still formed in the mesh's own order."""
+    from . import partition
+    n = rowptr.shape[0] - 1
+    nb = natural_bounds(n, n_rank)
+    if halo_fraction(rowptr, colidx, nb) <= max_halo_fraction:
+        return np.arange(n, dtype=np.int64), nb, 'natural'
+    owner = partition.rcb_owner(np.asarray(crds)[:, :2], n_rank)
+    perm, bounds = owner_permutation(owner, n_rank)
+    return perm, bounds, 'rcb'
+
+
+def _permute_pattern(rowptr, colidx, new_of_old):
+    """Block-CSR pattern with node `o` renamed `new_of_old[o]` (columns sorted per row)."""
+    import scipy.sparse as sp
+    n = rowptr.shape[0] - 1
+    A = sp.csr_matrix((np.ones(colidx.shape[0], np.int8), colidx, rowptr), shape=(n, n)).tocoo()
+    B = sp.csr_matrix((A.data, (new_of_old[A.row], new_of_old[A.col])), shape=(n, n))
+    B.sort_indices()
+    return B.indptr.astype(np.int32), B.indices.astype(np.int32)
+
+
+def build_hierarchy_invariant(rowptr_perm, colidx_perm, perm, max_coarse_nodes=64, max_levels=12):
+    """Smoothed-aggregation hierarchy for a RENUMBERED mesh (`perm`: new -> old node order, e.g. from
+    `owner_permutation`) whose aggregates are those of the ORIGINAL numbering: the greedy aggregation
+    (`multigrid.aggregate`) is order dependent, so aggregating the renumbered graph gives a different -- in
+    practice worse -- hierarchy for every rank count (1M quads: 164 PCG iterations on one GPU, 234 on 8 ranks).
+    Here every level is aggregated in its original order and only then renumbered: coarse nodes are numbered by
+    their first member in the renumbered fine order, which keeps every rank's coarse nodes contiguous
+    (`coarse_bounds`).  The hierarchy is the single-GPU one up to numbering; iteration counts agree to rounding."""
+    from . import multigrid
+    perm = np.asarray(perm, np.int64)
+    n = perm.shape[0]
+    new_of_old = np.empty(n, np.int64)
+    new_of_old[perm] = np.arange(n)
+    rp_p, ci_p = np.asarray(rowptr_perm, np.int32), np.asarray(colidx_perm, np.int32)
+    old_of_new = perm                                        # level-l node: new id -> original id
+    levels = []
+    while rp_p.shape[0] - 1 > max_coarse_nodes and len(levels) < max_levels:
+        n_f = rp_p.shape[0] - 1
+        inv = np.empty(n_f, np.int64)
+        inv[old_of_new] = np.arange(n_f)                     # original id -> new id
+        rp_o, ci_o = _permute_pattern(rp_p, ci_p, old_of_new)   # the level's graph in its original numbering
+        agg_o, n_c = multigrid.aggregate(rp_o, ci_o)         # aggregates as the single-GPU hierarchy forms them
+        if n_c >= n_f:
+            break
+        agg_by_new = agg_o[old_of_new]                       # original coarse id of every (new-numbered) fine node
+        first = np.full(n_c, n_f, np.int64)
+        np.minimum.at(first, agg_by_new, np.arange(n_f))
+        c_old_of_new = np.argsort(first, kind='stable')      # coarse: new id -> original id
+        c_new_of_old = np.empty(n_c, np.int64)
+        c_new_of_old[c_old_of_new] = np.arange(n_c)
+        lv = multigrid.build_level(rp_p, ci_p, c_new_of_old[agg_by_new].astype(np.int32), n_c)
+        levels.append(lv)
+        rp_p, ci_p, old_of_new = lv['c_rowptr'], lv['c_col'], c_old_of_new
+    return levels
+
+
 def coarse_bounds(lv, fine_bounds):
     """Range bounds of the coarse level of one coarsening step: an aggregate goes to the rank that owns its
     first (lowest) member, made monotone in the aggregate id (ids ascend with the root, so this moves only the
@@ -102,14 +184,20 @@ def build_plan(rowptr, colidx, levels, fine_bounds, min_dist_nodes=20000, max_di
         if l >= 1:
             pats.append((levels[l - 1]['p_rowptr'], levels[l - 1]['p_col'], bounds[l - 1]))   # P_{l-1} x_l
         need.append(level_halo(pats, bounds[l]))
-    return dict(n_dist=n_dist, n_rank=fine_bounds.shape[0] - 1, bounds=bounds, need=need)
+    # the first replicated level: its restricted right-hand side is all-gathered once per V-cycle; as an exchange
+    # plan "every rank needs every other rank's whole range" it runs over the same peer-memory push / wait kernels
+    n_rank = fine_bounds.shape[0] - 1
+    gb = bounds[n_dist]
+    gather = [[(np.arange(gb[s], gb[s + 1], dtype=np.int32) if s != r else np.zeros(0, np.int32)) for s in range(n_rank)]
+              for r in range(n_rank)]
+    return dict(n_dist=n_dist, n_rank=n_rank, bounds=bounds, need=need, gather=gather)
 
 
 def rank_plan(plan, rank):
     """What `jsso_mg_set_dist` takes on one rank: per distributed level the peers and the packed
     send / receive node-id lists (a peer appears if either direction is non-empty)."""
     out = []
-    for need in plan['need']:
+    for need in list(plan['need']) + ([plan['gather']] if plan.get('gather') is not None else []):
         n_rank = len(need)
         peers = [s for s in range(n_rank) if s != rank and (need[rank][s].size or need[s][rank].size)]
         send = [need[s][rank] for s in peers]
@@ -126,7 +214,8 @@ def rank_plan(plan, rank):
 def common_max_recv(plan):
     """Largest number of nodes any rank receives in one exchange of any level (the stride of the peer-memory
     receive arenas, which must be the same on every rank)."""
-    return int(max([sum(x.size for x in need[r]) for need in plan['need'] for r in range(plan['n_rank'])] + [1]))
+    needs = list(plan['need']) + ([plan['gather']] if plan.get('gather') is not None else [])
+    return int(max([sum(x.size for x in need[r]) for need in needs for r in range(plan['n_rank'])] + [1]))
 
 
 def plan_summary(plan):

@@ -6,7 +6,7 @@ emulator).  Launched as a subprocess by tests/test_emu_driver.py; prints one JSO
   driver_check.py e2e   SIZE                         jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS from the environment)
   driver_check.py mg    SIZE DEG                     multigrid PCG vs block-Jacobi CG vs the oracle
   driver_check.py part  WORLD SIZE                   partitioned handles + distributed block-Jacobi CG (hardware-measured path)
-  driver_check.py benchleg WORLD SIZE MIN_DIST       bench.py's distributed_grad_eval on rank threads vs the oracle
+  driver_check.py benchleg WORLD SIZE MIN_DIST [rcb] bench.py's N > 1 gradient evaluation (distributed_solve_handle) on rank threads
   driver_check.py dist  WORLD SIZE MIN_DIST DEG      row-range distributed multigrid solve on WORLD rank THREADS
                                                      (fake NCCL between them) vs the undistributed solve
 """
@@ -202,10 +202,13 @@ def main():
                'g_err': float(np.abs(G - rdc).max() / np.abs(rdc).max()),
                'dq_err': float(np.abs(Q - rdq).max() / np.abs(rdq).max()), 'iterations': [o[5] for o in out]}
     elif mode == 'benchleg':
-        # bench.py's extra leg (distributed_grad_eval) on rank threads: partitioned handles for the adjoint, a
-        # replicated solve first, then the distributed one; gradients against the oracle
+        # bench.py's N > 1 gradient evaluation on rank threads: partitioned handles (RCB) for the adjoint, the whole-mesh
+        # solve handle of bench.distributed_solve_handle (row-range distributed V-cycle PCG over "peer memory", the
+        # row partition chosen by solve_partition or forced to 'rcb' = renumbering + invariant aggregation), gather of
+        # the local rows, partitioned adjoint; u against an undistributed solve, gradients against the oracle
         import bench
         world, size, min_dist = (int(a) for a in sys.argv[2:5])
+        kind = sys.argv[5] if len(sys.argv) > 5 else 'auto'
         gmd = meshes.plate(size)
         owner = partition.rcb_owner(gmd.crds[:, :2], world)
         bar = threading.Barrier(world)
@@ -214,56 +217,74 @@ def main():
         opts = nat.make_opts(rtol=1e-10, compliance=True, precond='multigrid', cheb_degree=1)
 
         def worker(rank):
-            lm = partition.local_mesh(gmd, owner, rank, world)
-            h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, device=0, n_row=lm.n_owned)
-            hg = nat.Handle(gmd.n_node, gmd.cnct_quads, gmd.cnct_beams, gmd.known, device=0)
-            hg.mg_setup(max_coarse_nodes=8)
-            gu = D((gmd.ndof,))
-            hg.forward(D.from_host(gmd.crds), D.from_host(gmd.prop_quads), D.from_host(gmd.prop_beams),
-                       D.from_host(gmd.loads), gu, opts=opts)
-            dev = dict(crds=D.from_host(lm.md.crds), pq=D.from_host(lm.md.prop_quads), pb=D.from_host(lm.md.prop_beams),
-                       uu=D((lm.md.ndof,)), dc=D((lm.md.n_node, 3)), dq=D((lm.md.n_quad, 5)))
-            nat.gather_rows(gu, D.from_host(lm.l2g.astype(np.int32)), 6, out=dev['uu'])
+            try:
+                lm = partition.local_mesh(gmd, owner, rank, world)
+                h = nat.Handle(lm.md.n_node, lm.md.cnct_quads, lm.md.cnct_beams, lm.md.known, device=0, n_row=lm.n_owned)
 
-            def max_over_ranks(x):
-                shared['vals'][rank] = x
-                bar.wait()
-                m = max(shared['vals'])
-                bar.wait()
-                return m
+                def bcast(obj):
+                    if rank == 0:
+                        shared['id'] = obj
+                    bar.wait()
+                    got = shared['id']
+                    bar.wait()
+                    return got
 
-            def bcast(obj):
-                if rank == 0:
-                    shared['id'] = obj
-                bar.wait()
-                return shared['id']
+                def allgather(obj):
+                    shared.setdefault('box', [None] * world)[rank] = obj
+                    bar.wait()
+                    got = list(shared['box'])
+                    bar.wait()
+                    return got
 
-            def allgather(obj):
-                shared.setdefault('box', [None] * world)[rank] = obj
-                bar.wait()
-                got = list(shared['box'])
-                bar.wait()
-                return got
-
-            leg = bench.distributed_grad_eval(nat, gmd, owner, lm, h, rank, world, 0, opts, min_dist, dev, bar.wait,
-                                              max_over_ranks, bcast, allgather=allgather)
-            out[rank] = (leg, lm.l2g[:lm.n_owned], dev['dc'].download()[:lm.n_owned], lm.quad_ids, dev['dq'].download())
+                hd, smd, perm, info, levels = bench.distributed_solve_handle(nat, gmd, rank, world, 0, bcast, allgather,
+                                                                             min_dist, use_p2p=True, partition_kind=kind)
+                gu = D((smd.ndof,))
+                fs = hd.forward(D.from_host(smd.crds), D.from_host(smd.prop_quads), D.from_host(smd.prop_beams),
+                                D.from_host(smd.loads), gu, opts=opts)
+                l2s = lm.l2g
+                if perm is not None:
+                    inv = np.empty(gmd.n_node, np.int64)
+                    inv[perm] = np.arange(gmd.n_node)
+                    l2s = inv[lm.l2g]
+                uu, dc, dq = D((lm.md.ndof,)), D((lm.md.n_node, 3)), D((lm.md.n_quad, 5))
+                nat.gather_rows(gu, D.from_host(l2s.astype(np.int32)), 6, out=uu)
+                h.backward(D.from_host(lm.md.crds), D.from_host(lm.md.prop_quads), D.from_host(lm.md.prop_beams), uu, None,
+                           dc, dq, None, opts=opts)
+                ug = gu.download().reshape(-1, 6)
+                if perm is not None:
+                    tmp = np.empty_like(ug)
+                    tmp[perm] = ug
+                    ug = tmp
+                ex, ar = hd.mg_dist_counters()
+                out[rank] = (dict(info, pcg_iterations=fs.iterations, halo_exchanges=ex, scalar_allreduces=ar,
+                                  peer_memory=bool(hd.mg_dist_p2p)),
+                             lm.l2g[:lm.n_owned], dc.download()[:lm.n_owned], lm.quad_ids, dq.download(), ug.reshape(-1))
+            except BaseException as e:      # the other ranks would wait for this one forever
+                import traceback
+                traceback.print_exc()
+                print(f'EMU_RANK_ERROR rank {rank}: {e}', flush=True)
+                os._exit(3)
 
         import jaxsso_b200.multigrid as mgmod
         _bh = mgmod.build_hierarchy
         mgmod.build_hierarchy = lambda rp, ci, max_coarse_nodes=64, **kw: _bh(rp, ci, max_coarse_nodes=8, **kw)  # small meshes
+        _bi = dmg.build_hierarchy_invariant
+        dmg.build_hierarchy_invariant = lambda rp, ci, perm, max_coarse_nodes=64, **kw: _bi(rp, ci, perm, max_coarse_nodes=8, **kw)
         th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
         for t in th:
             t.start()
         for t in th:
             t.join()
         G, Q = np.zeros((gmd.n_node, 3)), np.zeros((gmd.n_quad, 5))
-        for leg, ids, g, qi, q in out:
+        for leg, ids, g, qi, q, ug in out:
             G[ids] = g
             Q[qi] = q
+        us, its, _, _, _, _ = solve(gmd, 'multigrid', 1)
         rv, ru, rl, rdc, rdq, rdb = orc.value_and_grad(omesh(gmd))
         res = {'leg': out[0][0], 'g_err': float(np.abs(G - rdc).max() / np.abs(rdc).max()),
-               'dq_err': float(np.abs(Q - rdq).max() / np.abs(rdq).max())}
+               'dq_err': float(np.abs(Q - rdq).max() / np.abs(rdq).max()), 'iters_single': its,
+               'u_err_vs_single': float(max(np.linalg.norm(o[5] - us) for o in out) / np.linalg.norm(us)),
+               'u_err_vs_oracle': float(np.linalg.norm(out[0][5] - ru) / np.linalg.norm(ru))}
     else:
         raise SystemExit('unknown mode')
     print('EMU_RESULT ' + json.dumps(res))

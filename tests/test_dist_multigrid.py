@@ -150,6 +150,92 @@ def test_block_ordering_keeps_the_iteration_count():
         assert iters(dmg.renumber_mesh(md0, perm)) <= base * 1.25 + 2
 
 
+def _pcg_iterations(Ah, ref, Ainv, seed=1):
+    b = np.random.default_rng(seed).standard_normal(Ah.shape[0])
+    x = np.zeros_like(b); r = b.copy()
+    z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+    p = z.copy(); rz = r @ z
+    for it in range(1, 300):
+        q = Ah @ p
+        a = rz / (p @ q)
+        x += a * p; r -= a * q
+        if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b):
+            return it, x
+        z = mgref.reference_vcycle(ref, Ainv, r, deg=1)
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+    return 300, x
+
+
+@pytest.mark.parametrize('n_rank', [2, 8])
+def test_invariant_hierarchy_has_the_aggregates_of_the_original_numbering(n_rank):
+    """`build_hierarchy_invariant`: on the owner-renumbered mesh the aggregates of EVERY level are those the
+    single-GPU hierarchy forms on the original numbering (as sets of original nodes), coarse ranges stay contiguous
+    per rank, and the PCG takes the same number of iterations as on the original mesh (the plain renumbered
+    hierarchy does not)."""
+    md0 = meshes.plate(32)
+    A0, L0, mask0 = scaled_system(md0)
+    lev0 = mg.build_hierarchy(A0.indptr.astype(np.int32), A0.indices.astype(np.int32), max_coarse_nodes=30)
+    perm, bounds = dmg.owner_permutation(partition.rcb_owner(md0.crds[:, :2], n_rank), n_rank)
+    md = dmg.renumber_mesh(md0, perm)
+    Ah, L, mask = scaled_system(md)
+    rp, ci = Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32)
+    lev = dmg.build_hierarchy_invariant(rp, ci, perm, max_coarse_nodes=30)
+    assert [l['n_c'] for l in lev] == [l['n_c'] for l in lev0]
+    # level 0: same partition of the original nodes into aggregates
+    sets0 = {frozenset(np.flatnonzero(lev0[0]['agg'] == a).tolist()) for a in range(lev0[0]['n_c'])}
+    sets1 = {frozenset(perm[np.flatnonzero(lev[0]['agg'] == a)].tolist()) for a in range(lev[0]['n_c'])}
+    assert sets0 == sets1
+    # coarse ranges per rank are contiguous and cover the level; first members ascend with the coarse id
+    b = bounds
+    for l in lev:
+        first = l['mem'][l['mem_ptr'][:-1]]
+        assert np.all(np.diff(first) > 0)
+        b = dmg.coarse_bounds(l, b)
+        assert b[0] == 0 and b[-1] == l['n_c'] and np.all(np.diff(b) >= 0)
+    ref0, Ac0 = mgref.reference_setup(A0.data, A0.indptr, A0.indices, md0.crds, mask0, lev0, Lt0=L0.transpose(0, 2, 1))
+    ref1, Ac1 = mgref.reference_setup(Ah.data, Ah.indptr, Ah.indices, md.crds, mask, lev, Lt0=L.transpose(0, 2, 1))
+    it0, x0 = _pcg_iterations(A0, ref0, np.linalg.inv(Ac0.toarray()))
+    # the same right-hand side in the renumbered dof order
+    d = (6 * perm[:, None] + np.arange(6)[None, :]).ravel()
+    b0 = np.random.default_rng(1).standard_normal(A0.shape[0])
+    Ainv1 = np.linalg.inv(Ac1.toarray())
+    x = np.zeros(Ah.shape[0]); r = b0[d].copy()
+    z = mgref.reference_vcycle(ref1, Ainv1, r, deg=1)
+    p = z.copy(); rz = r @ z
+    for it1 in range(1, 300):
+        q = Ah @ p
+        a = rz / (p @ q)
+        x += a * p; r -= a * q
+        if np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b0):
+            break
+        z = mgref.reference_vcycle(ref1, Ainv1, r, deg=1)
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+    assert abs(it1 - it0) <= 1
+    assert np.linalg.norm(x - x0[d]) <= 1e-7 * np.linalg.norm(x0)
+
+
+def test_structured_plate_is_partitioned_without_renumbering():
+    """`solve_partition`: a grid numbered row by row is cut into contiguous ranges of its own numbering (identity
+    permutation: the distributed solve then has the single-GPU hierarchy); a scrambled numbering falls back to RCB."""
+    md = meshes.plate(32)
+    Ah, _, _ = scaled_system(meshes.plate(8))      # only the pattern matters; use a small one for the scrambled case
+    from jaxsso_b200 import _native as nat
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=nat.JSSO_DEVICE_NONE)
+    rp, ci = h.pattern()
+    perm, bounds, kind = dmg.solve_partition(md.crds, rp, ci, 4, max_halo_fraction=0.3)
+    assert kind == 'natural' and np.array_equal(perm, np.arange(md.n_node))
+    assert np.array_equal(bounds, dmg.natural_bounds(md.n_node, 4)) and dmg.halo_fraction(rp, ci, bounds) < 0.3
+    rng = np.random.default_rng(0)
+    scr = rng.permutation(md.n_node)
+    md2 = dmg.renumber_mesh(md, scr)
+    h2 = nat.Handle(md2.n_node, md2.cnct_quads, md2.cnct_beams, md2.known, device=nat.JSSO_DEVICE_NONE)
+    rp2, ci2 = h2.pattern()
+    perm2, bounds2, kind2 = dmg.solve_partition(md2.crds, rp2, ci2, 4, max_halo_fraction=0.3)
+    assert kind2 == 'rcb' and bounds2[-1] == md.n_node
+
+
 # ------------------------------------------------------------------------------- gloo, world_size 2
 def _free_port():
     s = socket.socket()

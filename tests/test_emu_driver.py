@@ -113,19 +113,20 @@ def test_memcheck_under_address_sanitizer(args, env):
         assert r2.returncode != 0 and 'heap-buffer-overflow' in r2.stderr and 'gather_rows_kernel' in r2.stderr
 
 
-def test_bench_distributed_leg_on_rank_threads(emu_api):
-    """bench.py's `distributed_grad_eval` (the extra N > 1 leg: whole renumbered mesh per rank, distributed
-    V-cycle PCG, gather to the partitioned handle, partitioned adjoint) on two rank threads: u equals the replicated
-    solve, the gathered gradients equal the oracle's."""
-    res = run(emu_api, 'benchleg', 2, 12, 10)
+@pytest.mark.parametrize('kind', ['natural', 'rcb'])
+def test_bench_distributed_gradient_evaluation_on_rank_threads(emu_api, kind):
+    """bench.py's N > 1 gradient evaluation (`distributed_solve_handle`: whole-mesh handle, V-cycle PCG distributed by
+    row ranges over peer memory incl. the all-gather of the first replicated level, gather to the partitioned handle,
+    partitioned adjoint) on two rank threads.  'natural' cuts the plate into contiguous ranges of its own numbering
+    (identical hierarchy: the iteration count is the single-GPU one); 'rcb' renumbers by owner and aggregates in
+    the original order (`build_hierarchy_invariant`): within one iteration."""
+    res = run(emu_api, 'benchleg', 2, 12, 10, kind)
     leg = res['leg']
-    assert 'error' not in leg and leg['pcg_iterations'] > 0
-    assert leg['u_rel_diff_vs_replicated_solve'] <= 1e-8
+    assert leg['partition'] == kind and leg['peer_memory']
+    assert leg['distributed']['n_dist'] == 2 and leg['halo_exchanges'] > 0
+    assert abs(leg['pcg_iterations'] - res['iters_single']) <= (0 if kind == 'natural' else 1)
+    assert res['u_err_vs_single'] <= 1e-9 and res['u_err_vs_oracle'] <= 1e-8
     assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
-    assert leg['plan']['n_dist'] == 2 and leg['halo_exchanges'] > 0
-    pm = leg['peer_memory']
-    assert 'error' not in pm and pm['active'] and pm['pcg_iterations'] == leg['pcg_iterations']
-    assert pm['u_rel_diff_vs_replicated_solve'] <= 1e-8
 
 
 def test_device_scalar_pcg_poll_period(emu_api):
