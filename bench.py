@@ -160,13 +160,24 @@ def synthetic_state(md):
 
 
 # ------------------------------------------------------------------------------ reference arm
-def _oracle_chunk(args):
-    """Ke + adjoint element sensitivities of one chunk of quads (worker process)."""
+_REF = {}     # per worker process: the mesh arrays of the sample (set once by the pool initializer, not per job)
+
+
+def _ref_init(crds, cnct, prop, u, lam, ndof):
+    _REF.update(crds=crds, cnct=cnct, prop=prop, u=u, lam=lam, ndof=ndof)
+
+
+def _oracle_chunk(rng):
+    """Ke + COO->CSR (sum_duplicates) + adjoint element sensitivities of the quads [a, b) (worker process)."""
+    import scipy.sparse as sp
     from oracle import jaxsso_oracle as orc
-    crds, cnct, prop, u, lam = args
+    a, b = rng
+    crds, cnct, prop, u, lam = _REF['crds'], _REF['cnct'][a:b], _REF['prop'][a:b], _REF['u'], _REF['lam']
     n = cnct.shape[0]
     e = crds[cnct].reshape(n, 12)
     K = orc.element_K_quad(e, prop)
+    r, c = orc.quad_indices(cnct)
+    Kc = sp.coo_matrix((K.reshape(-1), (r, c)), shape=(_REF['ndof'], _REF['ndof'])).tocsr()
     dof = (6 * cnct.astype(np.int64)[:, :, None] + np.arange(6)[None, None, :]).reshape(n, 24)
     W = -lam[dof][:, :, None] * u[dof][:, None, :]
     dx = np.zeros((n, 12))
@@ -178,72 +189,88 @@ def _oracle_chunk(args):
     for k in range(5):
         pc = prop.astype(complex); pc[:, k] += 1j * h
         dp[:, k] = np.sum(W * (orc.element_K_quad(e, pc).imag / h), axis=(1, 2))
-    return K, dx, dp
+    return Kc, dx, dp
 
 
-def reference_step(md, u, lam, pool, n_workers):
-    """The reference's algorithm for the path on host cores: vmap(element_K_quad) ->
-    raw COO -> sort/sum_duplicates (scipy tocsr) -> element-wise adjoint reduction."""
-    import scipy.sparse as sp
-    from oracle import jaxsso_oracle as orc
-    parts = np.array_split(np.arange(md.n_quad), n_workers)
-    jobs = [(md.crds, md.cnct_quads[p], md.prop_quads[p], u, lam) for p in parts if p.size]
+def reference_step(md, pool, n_workers):
+    """The reference's algorithm for the path on host cores: vmap(element_K_quad) -> raw COO -> sort /
+    sum_duplicates (scipy tocsr per chunk, chunks added) -> element-wise adjoint reduction (complex-step dK_e)."""
+    bounds = np.linspace(0, md.n_quad, n_workers + 1).astype(int)
+    jobs = [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_workers) if bounds[i + 1] > bounds[i]]
     res = list(pool.map(_oracle_chunk, jobs)) if pool else [_oracle_chunk(j) for j in jobs]
-    K = np.concatenate([r[0] for r in res])
-    r, c = orc.quad_indices(md.cnct_quads)
-    Kg = sp.coo_matrix((K.reshape(-1), (r, c)), shape=(md.ndof, md.ndof)).tocsr()
+    Kg = res[0][0]
+    for r_ in res[1:]:
+        Kg = Kg + r_[0]
     d_crds = np.zeros((md.n_node, 3))
     dx = np.concatenate([r_[1] for r_ in res]).reshape(-1, 4, 3)
     np.add.at(d_crds, md.cnct_quads, dx)
     return Kg, d_crds
 
 
+def _reference_rate(size, steps, warmup, n_workers):
+    from concurrent.futures import ProcessPoolExecutor
+    md = meshes.plate(size)
+    u, lam = synthetic_state(md)
+    init = (md.crds, md.cnct_quads, md.prop_quads, u, lam, md.ndof)
+    pool = ProcessPoolExecutor(n_workers, initializer=_ref_init, initargs=init) if n_workers > 1 else None
+    if pool is None:
+        _ref_init(*init)
+    try:
+        for _ in range(warmup):
+            reference_step(md, pool, n_workers)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            reference_step(md, pool, n_workers)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        if pool:
+            pool.shutdown()
+    return md, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from concurrent.futures import ProcessPoolExecutor
     cores = os.cpu_count() or 1
-    n_workers = max(1, min(cores, 32))
+    n_workers = max(1, min(cores, 64))
     size = args.ref_size
-    md = meshes.plate(size)
-    u, lam = synthetic_state(md)
-    pool = ProcessPoolExecutor(n_workers) if n_workers > 1 else None
-    try:
-        for _ in range(args.warmup):
-            reference_step(md, u, lam, pool, n_workers)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            reference_step(md, u, lam, pool, n_workers)
-        dt = (time.perf_counter() - t0) / args.steps
-    finally:
-        if pool:
-            pool.shutdown()
+    md, dt = _reference_rate(size, args.steps, args.warmup, n_workers)
     v = md.n_quad / dt
-    # metric M2 on the host: one full gradient evaluation of the same bounded sample in the reference's
-    # LITERAL formulation (raw COO -> CSR, augmented Lagrange system, SuperLU twice, element derivatives)
+    # the rate is size independent (element-wise work): one step of the 64 x 64 sub-mesh of the same generator beside it
+    rate64 = None
+    if size != 64 and not args.ref_serial:
+        md64, dt64 = _reference_rate(64, 1, 1, n_workers)
+        rate64 = md64.n_quad / dt64
+    # metric M2 on the host: full gradient evaluations of bounded samples in the reference's LITERAL formulation
+    # (raw COO -> CSR, augmented Lagrange system, SuperLU twice, element derivatives), one process
     ge = None
     if args.ref_grad:
         from oracle import jaxsso_oracle as orc
-        m = orc.Mesh(md.crds, md.cnct_quads, md.prop_quads, md.cnct_beams, md.prop_beams, md.known, md.loads)
-        t0 = time.perf_counter()
-        orc.value_and_grad(m, literal=True)
-        ge = {'seconds': time.perf_counter() - t0, 'quads': int(md.n_quad),
+        pts = []
+        for gs in [int(x) for x in str(args.ref_grad_sizes or size).split(',') if x]:
+            gmd = meshes.plate(gs)
+            m = orc.Mesh(gmd.crds, gmd.cnct_quads, gmd.prop_quads, gmd.cnct_beams, gmd.prop_beams, gmd.known, gmd.loads)
+            t0 = time.perf_counter()
+            orc.value_and_grad(m, literal=True)
+            pts.append({'size': gs, 'quads': int(gmd.n_quad), 'seconds': time.perf_counter() - t0})
+        ge = {'seconds': pts[0]['seconds'], 'quads': pts[0]['quads'], 'points': pts,
               'what': 'oracle value_and_grad(literal=True): augmented SuperLU solve x2 + complex-step element '
-                      'derivatives, one process'}
-    sample = (f'{size}x{size} jittered plate ({md.n_quad} quads) per step: NumPy/SciPy restatement of '
-              f'vmap(element_K_quad) + COO->CSR sum_duplicates + complex-step adjoint reduction, '
-              f'{n_workers} worker processes')
+                      'derivatives, one process; the points show how the CPU solve scales with the mesh'}
+    sample = (f'{size}x{size} jittered plate ({md.n_quad} quads), a sub-mesh of the same generator as the {args.size}x{args.size} '
+              f'workload, per step: NumPy/SciPy restatement of vmap(element_K_quad) + COO->CSR sum_duplicates + '
+              f'complex-step adjoint reduction, {n_workers} worker processes (mesh arrays shared once per worker)')
     out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': f'synthetic {args.size}x{args.size} MITC4 shell plate (BASELINE configs[2]); '
-                                  f'reference arm timed on a bounded {size}x{size} sample of it'},
+           'config': {'workload': f'synthetic {args.size}x{args.size} MITC4 shell plate (BASELINE configs[2]); the reference '
+                                  f'arm (the oracle port: jax is not installable here) is timed on a bounded {size}x{size} '
+                                  f'sub-mesh of the same generator; elements/s is size independent (rate_at_64x64 beside it)',
+                      'rate_at_64x64': rate64},
            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': n_workers, 'kind': 'port', 'sample': sample,
                             'grad_eval': ge},
            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
-
 
 
 def distributed_solve_handle(nat, gmd, rank, world, device, bcast, allgather, min_dist_nodes, use_p2p=True,
@@ -701,7 +728,8 @@ def run_b200(args):
                     'traffic': None}
         if world == 1 and args.cpu_baseline:
             cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0',
-                   '--ref-size', str(args.ref_size), '--ref-serial', '--ref-grad']
+                   '--ref-size', str(args.cpu_baseline_size), '--ref-serial', '--ref-grad', '--ref-grad-sizes', '64,128',
+                   '--size', str(args.size)]
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
@@ -759,7 +787,10 @@ def main():
     ap.add_argument('--maxiter', type=int, default=400000)
     ap.add_argument('--cheb-degree', type=int, default=1, help='Chebyshev smoother degree of the V-cycle')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
-    ap.add_argument('--ref-size', type=int, default=64, help='plate size of the bounded CPU sample')
+    ap.add_argument('--ref-size', type=int, default=256, help='plate size of the bounded CPU sample (reference arm)')
+    ap.add_argument('--cpu-baseline-size', type=int, default=64, help='plate size of the one-core cpu_baseline leg')
+    ap.add_argument('--ref-grad-sizes', default=None,
+                    help='comma-separated plate sizes of the literal CPU gradient evaluations (--ref-grad; default: --ref-size)')
     ap.add_argument('--ref-serial', action='store_true', help='reference arm on one core (cpu_baseline leg)')
     ap.add_argument('--ref-grad', action='store_true', help='also time one literal gradient evaluation of the sample')
     args = ap.parse_args()

@@ -119,6 +119,7 @@ struct jsso_handle {
   bool pattern_only = false;     // created by jsso_create_from_bsr: no element kernels
   int red_blocks = 148 * 4;
   int spmv_blocks = 148 * 8;
+  int rp_blocks = 148 * 3;       // persistent grid of bsr_spmv_rp_kernel (co-resident CTAs)
   int coop_blocks = 0;          // max co-resident blocks of cg_persistent_kernel (0: unsupported)
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -302,9 +303,14 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, bsr_spmv_kernel<1>, RED_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, bsr_spmv_axpby_kernel<2, float>, RED_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, bsr_spmv_axpby_kernel<2, double>, RED_BLOCK, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, bsr_spmv_lin_kernel<double, 2>, RED_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, bsr_spmv_dot_kernel, RED_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, bsr_spmv_lin_kernel<float, 1>, RED_BLOCK, 0));
     const int occ = std::max(1, std::min(std::min(o1, o2), std::min(o3, std::min(o4, o5))));
+    int o6 = 0, o7 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o6, bsr_spmv_rp_kernel<float, 1>, RED_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, bsr_spmv_rp_kernel<__half, 1>, RED_BLOCK, 0));
+    h->rp_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * std::max(1, std::min(o6, o7)));
+    if (const char* e = std::getenv("JSSO_RP_BLOCKS")) h->rp_blocks = std::max(1, std::min(RED_MAX_BLOCKS, std::atoi(e)));
     h->spmv_blocks = std::min(RED_MAX_BLOCKS, prop.multiProcessorCount * occ);
     if (const char* e = std::getenv("JSSO_SPMV_BLOCKS")) h->spmv_blocks = std::max(1, std::min(RED_MAX_BLOCKS, std::atoi(e)));
   }
@@ -1266,14 +1272,34 @@ static int mg_spmv(jsso_handle* h, const int32_t* rp, const int32_t* ci, const d
   CKL("bsr_spmv_axpby_kernel");
   return JSSO_OK;
 }
-// same with single-precision block storage (falls back to the FP64 values when fp32 is off)
+#ifndef JSSO_MG_RP
+#define JSSO_MG_RP 1   // FP32 / binary16 products by the row-pair kernel (bsr_spmv_rp_kernel); 0: warp-per-row kernels (A/B builds)
+#endif
+static inline int rp_grid(jsso_handle* h, int n_row) { return std::max(1, std::min(h->rp_blocks, cdiv(3LL * n_row, RED_BLOCK))); }
+// same with single-precision (or binary16) block storage (falls back to the FP64 values when fp32 is off)
 template <int MODE>
 static int mg_spmv_p(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, const float* v32,
                      int n_row, const double* x, double* y, const double* b, cudaStream_t st,
                      bool short_rows = false, const __half* v16 = nullptr) {
   if (!h->mg_fp32 || !v32) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
   if (n_row == 0) return JSSO_OK;
-  if (v16 && !short_rows) {   // fine level, binary16 blocks (JSSO_MG_FP16=1)
+#if JSSO_MG_RP
+  {
+    // MODE 0: y = A x;  2: y = b - A x;  3: y += A x   as  ca * b + cb * y_row + cc * A x
+    const double ca = (MODE == 2) ? 1.0 : 0.0, cb = (MODE == 3) ? 1.0 : 0.0, cc = (MODE == 2) ? -1.0 : 1.0;
+    const double* bv = (MODE == 2) ? b : nullptr;
+    const double* xr = (MODE == 3) ? y : nullptr;
+    if (v16 && !short_rows)
+      bsr_spmv_rp_kernel<__half, 0><<<rp_grid(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v16, x, y, bv, xr, ca, cb, cc, nullptr,
+                                                                            h->partials, h->counters + 2, nullptr);
+    else
+      bsr_spmv_rp_kernel<float, 0><<<rp_grid(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v32, x, y, bv, xr, ca, cb, cc, nullptr,
+                                                                           h->partials, h->counters + 2, nullptr);
+    CKL("bsr_spmv_rp_kernel");
+    return JSSO_OK;
+  }
+#endif
+  if (v16 && !short_rows) {   // fine level, binary16 blocks
     bsr_spmv_axpby_kernel<MODE, __half><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, rp, ci, v16, x, y, b);
     CKL("bsr_spmv_axpby_kernel<half>");
     return JSSO_OK;
@@ -1679,6 +1705,20 @@ static int mg_lin_level0(jsso_handle* h, int s, int n, const double* x, double* 
   const MgMat A = mg_matrix(h, 0);
   const int g = mg_blocks(h, n);
   const double* stop = h->mg_scal;
+#if JSSO_MG_RP
+  if (h->mg_fp32 && A.v16) {
+    bsr_spmv_rp_kernel<__half, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc,
+                                                                        stop, h->partials, h->counters + 2, dot_out);
+    CKL("bsr_spmv_rp_kernel<half>");
+    return JSSO_OK;
+  }
+  if (h->mg_fp32 && A.v32) {
+    bsr_spmv_rp_kernel<float, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v32, x, y, bvec, xrow, ca, cb, cc,
+                                                                       stop, h->partials, h->counters + 2, dot_out);
+    CKL("bsr_spmv_rp_kernel<float>");
+    return JSSO_OK;
+  }
+#endif
   if (h->mg_fp32 && A.v16)
     bsr_spmv_lin_kernel<__half, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc, stop,
                                                              h->partials, h->counters + 2, dot_out);
@@ -1731,7 +1771,11 @@ static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaSt
   }
   // x1 = b / theta + P x_c into m.d
   if (n > 0) {
-    if (h->mg_fp32 && m.P32 && m.nnz_p <= 5LL * m.n_f) {
+    if (h->mg_fp32 && m.P32 && JSSO_MG_RP) {
+      bsr_spmv_rp_kernel<float, 0><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, m.p_rowptr + s, m.p_col, m.P32, xc, m.d + off, b + off,
+                                                                       nullptr, it, 0.0, 1.0, h->mg_scal, h->partials,
+                                                                       h->counters + 2, nullptr);
+    } else if (h->mg_fp32 && m.P32 && m.nnz_p <= 5LL * m.n_f) {
       bsr_spmv_short_kernel<5><<<cdiv(3LL * n, 256), 256, 0, st>>>(n, m.p_rowptr + s, m.p_col, m.P32, xc, m.d + off,
                                                                     b + off, it, h->mg_scal);
     } else if (h->mg_fp32 && m.P32) {
@@ -1795,10 +1839,9 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
       first = false;
       if (dist) { if ((rc = mgd_exchange(h, 0, p, st))) return rc; }
       if (n_row > 0) {
-        bsr_spmv_lin_kernel<double, 2><<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(
-            n_row, A.rp + s, A.ci, A.v, p, q + off, nullptr, p + off, 0.0, 0.0, 1.0, scal, h->partials, h->counters + 2,
-            mgs_dot_target(h, MGS_PQ));
-        CKL("bsr_spmv_lin_kernel<double, 2>");
+        bsr_spmv_dot_kernel<<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, A.rp + s, A.ci, A.v, p, p + off, q + off, scal,
+                                                                     h->partials, h->counters + 2, mgs_dot_target(h, MGS_PQ));
+        CKL("bsr_spmv_dot_kernel");
       } else {
         CK(cudaMemsetAsync(mgs_dot_target(h, MGS_PQ), 0, sizeof(double), st));
       }

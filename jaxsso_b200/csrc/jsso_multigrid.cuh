@@ -351,8 +351,15 @@ __global__ void mg_pcg_dir_kernel(long long n, const double* __restrict__ z, dou
                                   const double* __restrict__ scal, int first) {
   if (mgs_stopped(scal)) return;
   const double beta = first ? 0.0 : scal[MGS_RZ] / scal[MGS_RZ_OLD];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    p[i] = first ? z[i] : z[i] + beta * p[i];
+  const long long n2 = n >> 1;   // n = 6 x nodes is even and the vectors are 16-byte aligned: 16-byte accesses
+  const double2* z2 = (const double2*)z;
+  double2* p2 = (double2*)p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const double2 zv = z2[i];
+    if (first) { p2[i] = zv; continue; }
+    const double2 pv = p2[i];
+    p2[i] = make_double2(fma(beta, pv.x, zv.x), fma(beta, pv.y, zv.y));
+  }
 }
 // alpha = rz / pq;  x += alpha p;  r -= alpha q;  *rr_out = r.r;  the block that finalises the sum also latches
 // rz_old = rz and counts the iteration (it runs after every block has read alpha and passed the stop test).
@@ -365,11 +372,18 @@ mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __
   const double rz = scal[MGS_RZ], pq = scal[MGS_PQ];
   const double alpha = rz / pq;
   double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    x[i] = fma(alpha, p[i], x[i]);
-    const double ri = fma(-alpha, q[i], r[i]);
-    r[i] = ri;
-    acc = fma(ri, ri, acc);
+  const long long n2 = n >> 1;
+  const double2* p2 = (const double2*)p;
+  const double2* q2 = (const double2*)q;
+  double2* x2 = (double2*)x;
+  double2* r2 = (double2*)r;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
+    x2[i] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+    const double2 rn = make_double2(fma(-alpha, qv.x, rv.x), fma(-alpha, qv.y, rv.y));
+    r2[i] = rn;
+    acc = fma(rn.x, rn.x, acc);
+    acc = fma(rn.y, rn.y, acc);
   }
   double total;
   if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {

@@ -140,6 +140,19 @@ __device__ inline void p2p_wait_halo(const P2PCtx* c, unsigned long long seq) {
 constexpr int RED_BLOCK = 256;
 constexpr int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8
 
+// ---- fused multigrid-PCG iteration (device-resident scalars) -------------------------------------------
+// Slots of the scalar block `scal` (doubles): the outer PCG keeps every scalar on the device, so an iteration
+// needs no host round trip.  A kernel that gets a `stop` pointer (= scal) returns at once when the recurrence
+// residual has reached the tolerance (r.r <= tol2 |b|^2, also true for NaN), so the launches the host enqueued
+// past convergence (it polls every few iterations) are no-ops.  On several GPUs every dot product is written to
+// its MGS_LOC + slot partial and summed over the ranks OUT OF PLACE into the slot itself (idempotent when the
+// producing kernel was a no-op).
+constexpr int MGS_BB = 1, MGS_RR = 2, MGS_RZ = 3, MGS_PQ = 4, MGS_RZ_OLD = 6, MGS_TOL = 7, MGS_ITER = 8,
+              MGS_LOC = 16, MGS_COUNT = 32;
+__device__ inline bool mgs_stopped(const double* stop) {
+  return stop && !(stop[MGS_RR] > stop[MGS_TOL]);
+}
+
 __device__ inline double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -571,6 +584,28 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
   }
 }
 
+// q = A p and *dot_out = p.q on the rows [0, n_row) (outer product of the multigrid PCG; the plain FP64 pipeline of
+// bsr_spmv_kernel without the linear epilogue's extra operands: 60 registers, no spills)
+__global__ void __launch_bounds__(RED_BLOCK, 4)
+bsr_spmv_dot_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                    const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ xrow,
+                    double* __restrict__ y, const double* stop, double* partials, unsigned* counter, double* dot_out) {
+  if (mgs_stopped(stop)) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warp = (gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, [&](int r, double u0, double u1) {
+    if (lane < 3) {
+      *(double2*)(y + 6 * (size_t)r + 2 * lane) = make_double2(u0, u1);
+      const double2 xr = *(const double2*)(xrow + 6 * (size_t)r + 2 * lane);
+      dot += u0 * xr.x + u1 * xr.y;
+    }
+  });
+  double total;
+  if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+}
+
 // MODE 0: y = A x;  2: y = b - A x;  3: y += A x;  5 (short-row kernel only): y = s b + A x
 // (any 6x6 block-CSR, also rectangular)
 #ifndef JSSO_SPMV_MINB
@@ -601,19 +636,6 @@ bsr_spmv_axpby_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32
   };
   if constexpr (RowPair<VT>::value && JSSO_SPMV_PAIRED) bsr_rows_paired(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
   else bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
-}
-
-// ---- fused multigrid-PCG iteration (device-resident scalars) -------------------------------------------
-// Slots of the scalar block `scal` (doubles): the outer PCG keeps every scalar on the device, so an iteration
-// needs no host round trip.  A kernel that gets a `stop` pointer (= scal) returns at once when the recurrence
-// residual has reached the tolerance (r.r <= tol2 |b|^2, also true for NaN), so the launches the host enqueued
-// past convergence (it polls every few iterations) are no-ops.  On several GPUs every dot product is written to
-// its MGS_LOC + slot partial and summed over the ranks OUT OF PLACE into the slot itself (idempotent when the
-// producing kernel was a no-op).
-constexpr int MGS_BB = 1, MGS_RR = 2, MGS_RZ = 3, MGS_PQ = 4, MGS_RZ_OLD = 6, MGS_TOL = 7, MGS_ITER = 8,
-              MGS_LOC = 16, MGS_COUNT = 32;
-__device__ inline bool mgs_stopped(const double* stop) {
-  return stop && !(stop[MGS_RR] > stop[MGS_TOL]);
 }
 
 // y_r = ca * bvec_r + cb * xrow_r + cc * (A x)_r  for the block rows [0, n_row) of (rowptr, y, bvec, xrow);
@@ -649,6 +671,99 @@ bsr_spmv_lin_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
   double dot;
   if constexpr (RowPair<VT>::value && JSSO_SPMV_PAIRED) dot = bsr_rows_paired(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
   else dot = bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
+  if (DOT != 0) {
+    double total;
+    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+  }
+}
+
+// ---- row-pair SpMV for FP32 / binary16 block storage (the V-cycle's fine-level products) ---------------------
+// One THREAD per (block row, row pair): the thread streams its 2 x 6 slice of every block of the row (12 values:
+// three 16-byte loads in FP32, three 8-byte loads in binary16 -- the three threads of a row read 144 / 72
+// contiguous bytes per block) and the block's six x entries, and keeps its two row sums in registers: no shuffles,
+// no idle lanes, and ~36 instructions per (thread, block) instead of the ~200 warp instructions per row of the
+// warp-per-row kernels above, which at half / a quarter of the FP64 bytes are bound by instruction issue and the LSU
+// pipe, not by HBM (ncu at 1M quads, binary16: issue active 62 %, LSU 48 %, 2.5 TB/s).  Two blocks per loop
+// iteration are issued before the first FMA.  Same epilogue and dot options as bsr_spmv_lin_kernel; persistent
+// grid-stride over the (row, pair) items.
+template <class VT> struct RpLoad;
+template <> struct RpLoad<float> {
+  struct Raw { float4 a, b, c; };
+  __device__ static inline Raw ld(const float* vals, size_t blk, int sub) {
+    const float4* p = (const float4*)(vals + blk * 36) + 3 * sub;
+    return Raw{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+  }
+  __device__ static inline void unpack(const Raw& r, float (&f)[12]) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+    f[8] = r.c.x; f[9] = r.c.y; f[10] = r.c.z; f[11] = r.c.w;
+  }
+};
+template <> struct RpLoad<__half> {
+  struct Raw { uint2 a, b, c; };
+  __device__ static inline Raw ld(const __half* vals, size_t blk, int sub) {
+    const uint2* p = (const uint2*)(vals + blk * 36) + 3 * sub;
+    return Raw{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+  }
+  __device__ static inline void unpack(const Raw& r, float (&f)[12]) {
+    half4_to_float(r.a, f[0], f[1], f[2], f[3]);
+    half4_to_float(r.b, f[4], f[5], f[6], f[7]);
+    half4_to_float(r.c, f[8], f[9], f[10], f[11]);
+  }
+};
+// row-pair-major block: f[2 j + r] = A[2 sub + r][j]
+__device__ inline void rp_fma(const float (&f)[12], const double2 x0, const double2 x1, const double2 x2, double& acc0,
+                              double& acc1) {
+  acc0 = fma((double)f[0], x0.x, acc0); acc1 = fma((double)f[1], x0.x, acc1);
+  acc0 = fma((double)f[2], x0.y, acc0); acc1 = fma((double)f[3], x0.y, acc1);
+  acc0 = fma((double)f[4], x1.x, acc0); acc1 = fma((double)f[5], x1.x, acc1);
+  acc0 = fma((double)f[6], x1.y, acc0); acc1 = fma((double)f[7], x1.y, acc1);
+  acc0 = fma((double)f[8], x2.x, acc0); acc1 = fma((double)f[9], x2.x, acc1);
+  acc0 = fma((double)f[10], x2.y, acc0); acc1 = fma((double)f[11], x2.y, acc1);
+}
+template <class VT, int DOT>
+__global__ void __launch_bounds__(RED_BLOCK, 3)
+bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                   const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                   const double* __restrict__ bvec, const double* __restrict__ xrow, double ca, double cb, double cc,
+                   const double* stop, double* partials, unsigned* counter, double* dot_out) {
+  if (mgs_stopped(stop)) return;
+  double dot = 0.0;
+  const long long n_item = 3LL * n_row;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_item; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
+    const int b0 = rowptr[r], b1 = rowptr[r + 1];
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = b0;
+    for (; k + 1 < b1; k += 2) {
+      const int c0 = colidx[k], c1 = colidx[k + 1];
+      const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub), rb = RpLoad<VT>::ld(vals, (size_t)k + 1, sub);
+      const double2* xa = (const double2*)(x + 6 * (size_t)c0);
+      const double2* xb = (const double2*)(x + 6 * (size_t)c1);
+      const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2], xb0 = xb[0], xb1 = xb[1], xb2 = xb[2];
+      float f[12];
+      RpLoad<VT>::unpack(ra, f);
+      rp_fma(f, xa0, xa1, xa2, acc0, acc1);
+      RpLoad<VT>::unpack(rb, f);
+      rp_fma(f, xb0, xb1, xb2, acc0, acc1);
+    }
+    if (k < b1) {
+      const int c0 = colidx[k];
+      const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub);
+      const double2* xa = (const double2*)(x + 6 * (size_t)c0);
+      const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2];
+      float f[12];
+      RpLoad<VT>::unpack(ra, f);
+      rp_fma(f, xa0, xa1, xa2, acc0, acc1);
+    }
+    const size_t o = 6 * (size_t)r + 2 * sub;
+    double2 v = make_double2(cc * acc0, cc * acc1);
+    double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+    if (bvec) { bv = *(const double2*)(bvec + o); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
+    if (xrow) { xv = *(const double2*)(xrow + o); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
+    *(double2*)(y + o) = v;
+    if (DOT == 1) dot += bv.x * v.x + bv.y * v.y;
+    if (DOT == 2) dot += xv.x * acc0 + xv.y * acc1;
+  }
   if (DOT != 0) {
     double total;
     if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;

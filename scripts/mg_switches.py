@@ -14,7 +14,7 @@ crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(
 u = D((md.ndof,))
 levels = None
 u_ref = None
-CONFIGS = [{}, {'JSSO_MG_FP16': '0'}, {'JSSO_MG_GRAPH': '0'}, {'JSSO_MG_POLL': '1'}, {'JSSO_MG_POLL': '16'}]
+CONFIGS = [{}, {'JSSO_MG_FP16': '0'}, {'JSSO_MG_GRAPH': '0'}] if len(sys.argv) <= 3 else [{}]
 KEYS = ('JSSO_MG_FP16', 'JSSO_MG_POLL', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64')
 for cfg in CONFIGS:
     for k in KEYS:

@@ -22,6 +22,8 @@ def test_reference_arm_line():
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] == 1 and cb['value'] == d['value']
     assert cb['grad_eval']['quads'] == 36 and cb['grad_eval']['seconds'] > 0
+    assert [p['size'] for p in cb['grad_eval']['points']] == [6]
+    assert 'sub-mesh of the same generator' in cb['sample'] and 'rate_at_64x64' in d['config']
 
 
 def test_reference_arm_other_ranks_are_silent():
