@@ -316,6 +316,56 @@ def distributed_solve_handle(nat, gmd, rank, world, device, bcast, allgather, mi
     return hd, smd, perm, info, levels
 
 
+def batch_designs_eval(nat, n_designs, grid, rank, world, device, dist, barrier, max_over_ranks, rtol=1e-8):
+    """BASELINE config 5: `n_designs` synthetic grid x grid beam-column gridshell designs, design k
+    on rank k % world (one handle per GPU: same connectivity, the symbolic state and the multigrid hierarchy are built
+    once); every design is one value + shape-gradient evaluation through the host-buffer entry point
+    (jsso_value_and_grad_host: H2D, Ke + assembly, multigrid PCG, adjoint, D2H).  The compliances and the gradients
+    (n_designs x n_node x 3) are all-gathered over NCCL at the end, inside the timed region."""
+    md0 = meshes.gridshell(grid, 0)
+    mine = list(range(rank, n_designs, world))
+    t0 = time.perf_counter()
+    h = nat.Handle(md0.n_node, md0.cnct_quads, md0.cnct_beams, md0.known, device=device)
+    h.mg_setup()
+    designs = [meshes.gridshell(grid, k) for k in mine]
+    t_setup = time.perf_counter() - t0
+    opts = nat.make_opts(rtol=rtol, precond='multigrid')
+    if designs:
+        h.value_and_grad_host(designs[0].crds, md0.prop_quads, md0.prop_beams, md0.loads, want=('crds',), opts=opts)   # warm-up
+    n_max = (n_designs + world - 1) // world
+    vals = np.zeros(n_max)
+    grads = np.zeros((n_max, md0.n_node, 3))
+    its = []
+    barrier()
+    t0 = time.perf_counter()
+    for i, d in enumerate(designs):
+        v, u, dc, _, _, fs, _ = h.value_and_grad_host(d.crds, md0.prop_quads, md0.prop_beams, md0.loads, want=('crds',), opts=opts)
+        vals[i] = v
+        grads[i] = dc
+        its.append(int(fs.iterations))
+    if dist is not None:
+        import torch
+        tv = torch.from_numpy(vals).cuda()
+        tg = torch.from_numpy(grads).cuda()
+        av = torch.empty((world,) + tuple(tv.shape), dtype=tv.dtype, device='cuda')
+        ag = torch.empty((world,) + tuple(tg.shape), dtype=tg.dtype, device='cuda')
+        dist.all_gather_into_tensor(av, tv)
+        dist.all_gather_into_tensor(ag, tg)
+        torch.cuda.synchronize()
+        all_vals = av.cpu().numpy()            # [rank][i] = design rank + i * world
+        g_bytes = int(ag.numel() * 8)
+    else:
+        all_vals, g_bytes = vals[None, :], 0
+    dt = max_over_ranks(time.perf_counter() - t0)
+    h.close()
+    by_design = [float(all_vals[k % world][k // world]) for k in range(n_designs)]
+    return {'designs': n_designs, 'designs_per_s': n_designs / dt, 'seconds': dt, 'ms_per_design_per_gpu': 1e3 * dt / max(len(mine), 1),
+            'beams_per_design': int(md0.n_beam), 'dof_per_design': int(md0.ndof), 'pcg_iterations_first': its[:4],
+            'compliance_first_last': [by_design[0], by_design[-1]], 'gathered_gradient_bytes': g_bytes,
+            'setup_s': t_setup, 'sharding': f'design k on rank k % {world} (replicas; all-gather of compliances and gradients at the end)',
+            'workload': f'BASELINE configs[4]: {n_designs} synthetic {grid}x{grid} gridshell designs'}
+
+
 def pcg_iteration_bytes(nnzb0, levels):
     """Algorithmic HBM bytes of ONE fused multigrid-PCG iteration (Chebyshev-1), whole system, from the hierarchy's
     sizes.  Matrix blocks: 288 B (FP64), 144 B (FP32), 72 B (binary16) + 4 B column index; a vector pass = 48 B per
@@ -641,6 +691,31 @@ def run_b200(args):
         except Exception:
             pass
 
+    # BASELINE config 5: a batch of independent gridshell designs (beam-columns) sharded over the ranks -- replicas,
+    # no collective on the hot path; the 64 compliances and shape gradients are all-gathered at the end
+    batch_eval = None
+    if args.batch_designs > 0:
+        try:
+            batch_eval = batch_designs_eval(nat, args.batch_designs, args.batch_grid, rank, world, local_rank, dist,
+                                            barrier, max_over_ranks, rtol=args.rtol)
+        except nat.JssoError as e:
+            batch_eval = {'error': str(e)}
+
+    # BASELINE config 4 (N = 1 only): simultaneous shape + topology optimisation loop on a 512^2 shell through the
+    # public host-buffer API (filters both sides, warm-started multigrid PCG); scripts/topo_shape_512.py
+    topo_eval = None
+    if world == 1 and args.topo_iters > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+            import topo_shape_512 as ts
+            o_ = ts.run(args.topo_size, args.topo_iters, rtol=1e-6, device=local_rank)
+            hist_, its_ = o_.pop('history'), o_.pop('pcg_iterations')
+            topo_eval = dict(o_, strain_energy_first_last=[hist_[0], hist_[-1]], pcg_iterations_first_last=[its_[0], its_[-1]],
+                             monotone_fraction=float(np.mean(np.diff(hist_) <= 0)) if len(hist_) > 1 else None,
+                             workload=f'BASELINE configs[3] at {args.topo_size}^2, {args.topo_iters} of its 100 iterations')
+        except Exception as e:
+            topo_eval = {'error': f'{type(e).__name__}: {e}'}
+
     def build_out():
         hbm, peak_src = peaks()
         s = h.sizes
@@ -708,7 +783,7 @@ def run_b200(args):
                'roofline_spmv': roof_spmv,
                'kernel_ms': {'assembly': ms_asm, 'quad_geometry': ms_geo, 'assemble_tasks': ms_tasks, 'adjoint': ms_adj,
                              'spmv': ms_spmv}, 'setup_s': t_setup,
-               'grad_eval': grad_eval}
+               'grad_eval': grad_eval, 'batch_eval': batch_eval, 'topo_eval': topo_eval}
         if grad_eval and 'error' not in grad_eval:
             # metric M2 (the second half of BASELINE.json's metric) as a first-class entry of the line
             out['m2'] = {'metric': 'full shape-gradient evaluations/s (Ke, assembly, solve, adjoint) at '
@@ -775,6 +850,11 @@ def main():
                          'when it is banded, else RCB with renumbering)')
     ap.add_argument('--no-dist-check', dest='dist_check', action='store_false',
                     help='N > 1: skip the comparison of the distributed solve with a replicated solve of the same system')
+    ap.add_argument('--topo-iters', type=int, default=10, help='BASELINE config 4 leg at N = 1: optimiser iterations (0: skip)')
+    ap.add_argument('--topo-size', type=int, default=512)
+    ap.add_argument('--batch-designs', type=int, default=64,
+                    help='BASELINE config 5 leg: gridshell designs sharded over the ranks (0: skip)')
+    ap.add_argument('--batch-grid', type=int, default=224, help='nodes per side of a gridshell design')
     ap.add_argument('--fp64-peak-seconds', type=float, default=1.0,
                     help='duration of the FP64 DFMA microbenchmark behind roofline_adjoint.peak (0: nominal peak)')
     ap.add_argument('--grad-evals', type=int, default=3, help='timed full gradient evaluations (after one warm-up)')

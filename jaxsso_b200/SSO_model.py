@@ -166,9 +166,11 @@ class SSO_model:
     # ---- objective (SSO_model.py:275-306) ------------------------------------------------
     def set_objective(self, objective='strain energy', func=None, func_args=None):
         """'strain energy': 0.5 f.u (SSO_model.py:297-301).
-        'user': ``func(sso_model, u, *args)`` must return ``(value, dvalue_du)`` -- without
-        JAX on the host the adjoint right-hand side g = dL/du is supplied by the caller
-        (the reference gets it from jax.grad; see jaxsso_b200.jax_ffi for the traced path)."""
+        'user': ``func(sso_model, u, *args)`` as in the reference (SSO_model.py:303-306).  The reference traces it with
+        JAX and gets the adjoint right-hand side g = dL/du from reverse mode; here it may
+          * return the scalar value alone, as in the reference: g comes from ``jax.grad`` when jax is importable,
+            else from PyTorch autograd (``u`` is then a float64 ``torch.Tensor``; write the objective with torch ops);
+          * or return ``(value, dvalue_du)`` with the gradient supplied by the caller (plain NumPy)."""
         if objective == 'strain energy':
             self.objective = 'strain energy'
         elif objective == 'user':
@@ -183,8 +185,32 @@ class SSO_model:
         u = self.params_u(parameter_values, which_solver, enforce_scipy_sparse)
         if self.objective == 'strain energy':
             return 0.5 * self.model.nodal_loads @ u
+        return self._user_objective(u)[0]
+
+    def _user_objective(self, u):
+        """(value, dL/du) of the user objective at u (NumPy), by whichever route the callable supports."""
         args = self.objective_args or ()
-        return self.objective(self, u, *args)[0]
+        try:
+            out = self.objective(self, u, *args)
+        except (TypeError, AttributeError, ValueError):
+            out = None     # a callable written for jax / torch arrays may not accept NumPy input
+        if isinstance(out, tuple) and len(out) == 2:
+            return float(out[0]), np.asarray(out[1], dtype=np.float64).ravel()
+        try:
+            import jax
+            import jax.numpy as jnp
+            val, g = jax.value_and_grad(lambda uu: self.objective(self, uu, *args))(jnp.asarray(u))
+            return float(val), np.asarray(g, dtype=np.float64).ravel()
+        except ImportError:
+            pass
+        import torch
+        ut = torch.tensor(np.asarray(u, dtype=np.float64), dtype=torch.float64, requires_grad=True)
+        val = self.objective(self, ut, *args)
+        if not torch.is_tensor(val):
+            raise TypeError("a 'user' objective must return (value, dvalue_du), or a scalar computed with jax / torch "
+                            "operations from u so that its gradient can be taken")
+        g, = torch.autograd.grad(val, ut)
+        return float(val.detach()), g.detach().numpy().astype(np.float64).ravel()
 
     def params_to_objective(self, which_solver='b200', enforce_scipy_sparse=True):
         return self.helper_params_to_objective(self.parameter_values, which_solver, enforce_scipy_sparse)
@@ -216,8 +242,7 @@ class SSO_model:
         u_d = nat.DeviceArray((m.ndof,))
         fs = h.forward(d['crds'], d['pq'], d['pb'], d['f'], u_d, opts=opts)
         u = u_d.download()
-        args = self.objective_args or ()
-        val, g = self.objective(self, u, *args)
+        val, g = self._user_objective(u)
         g_d = nat.DeviceArray.from_host(np.asarray(g, dtype=float))
         dc, dq, db = nat.DeviceArray((m.crds.shape[0], 3)), nat.DeviceArray((m.n_quad, 5)), nat.DeviceArray((m.n_beamcol, 6))
         bs = h.backward(d['crds'], d['pq'], d['pb'], u_d, g_d, dc, dq if m.n_quad else None,

@@ -153,6 +153,8 @@ struct jsso_handle {
   bool mg_fp32 = true;
   __half* vals16 = nullptr;        // binary16 copy of the scaled fine matrix (V-cycle only; JSSO_MG_FP16=1)
   bool mg_fp16 = false;
+  int mg_power_iters = 10;         // steps of the power iteration for lambda_max per level (JSSO_MG_POWER_ITERS)
+  double mg_power_safety = 1.2;
   int mg_poll = 8;                 // the PCG scalars stay on the device; the host polls the residual every mg_poll iterations
   // opt-in CUDA graph of the V-cycle's launch-bound part (JSSO_MG_GRAPH=1): the whole V-cycle on one GPU, the
   // replicated coarse levels of the distributed solve.  Captured once per numeric setup (the smoother
@@ -1082,7 +1084,6 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     if (nc > 6000) return fail(h, JSSO_ERR_ARG, "multigrid: coarsest level too large for the dense solve");
     CK(dalloc(&h->mg_dense, 2 * nc * nc)); CK(dalloc(&h->mg_cb, nc)); CK(dalloc(&h->mg_cx, nc));
     CK(dalloc(&h->Lfac, 36 * (size_t)h->sym.n_node));
-    CK(dalloc(&h->vals32, 36 * (size_t)h->sym.nnzb()));
     CK(dalloc(&h->mg_scal, MGS_COUNT));
     CK(cudaMemset(h->mg_scal, 0, MGS_COUNT * sizeof(double)));
     CK(cudaMallocHost((void**)&h->mg_scal_host, MGS_COUNT * sizeof(double)));
@@ -1091,12 +1092,17 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
     h->mg_fp32 = !(e && e[0] == '1');
     if (const char* ea = std::getenv("JSSO_MG_POLL")) h->mg_poll = std::max(1, std::min(64, std::atoi(ea)));
+    if (const char* ep = std::getenv("JSSO_MG_POWER_ITERS")) {   // A/B: 30 restores round 1's estimate (x 1.15)
+      h->mg_power_iters = std::max(3, std::min(200, std::atoi(ep)));
+      if (h->mg_power_iters >= 30) h->mg_power_safety = 1.15;
+    }
     if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] != '0';   // A/B switch (default on)
     // binary16 storage of the fine-level V-cycle matrix (the block-Jacobi-scaled matrix has unit diagonal blocks and
     // |entries| <= 1); JSSO_MG_FP16=0 keeps FP32 (A/B switch)
     const char* e16 = std::getenv("JSSO_MG_FP16");
     h->mg_fp16 = h->mg_fp32 && n_levels > 0 && !(e16 && e16[0] == '0');
     if (h->mg_fp16) CK(dalloc(&h->vals16, 36 * (size_t)h->sym.nnzb()));
+    else if (n_levels > 0) CK(dalloc(&h->vals32, 36 * (size_t)h->sym.nnzb()));   // the fine level needs ONE reduced-precision copy
   }
   h->mg_ready = false;
   h->assembled = false;   // the fine factor L is produced by the scaling of the NEXT assembly
@@ -1255,11 +1261,11 @@ extern "C" int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out) {
   return JSSO_OK;
 }
 
-struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; const __half* v16; };
+struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; const __half* v16; long long nnz; };
 static MgMat mg_matrix(jsso_handle* h, int l) {
-  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32, h->mg_fp16 ? h->vals16 : nullptr};
+  if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32, h->mg_fp16 ? h->vals16 : nullptr, h->sym.nnzb()};
   const jsso_handle::MgLevel& p = h->mg[l - 1];
-  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c, p.Ac32, nullptr};
+  return MgMat{p.c_rowptr, p.c_col, p.Ac, p.n_c, p.Ac32, nullptr, p.nnz_c};
 }
 static inline int mg_blocks(jsso_handle* h, int n_row) {
   return std::max(1, std::min(h->spmv_blocks, cdiv(n_row, RED_BLOCK / 32)));
@@ -1280,11 +1286,14 @@ static inline int rp_grid(jsso_handle* h, int n_row) { return std::max(1, std::m
 template <int MODE>
 static int mg_spmv_p(jsso_handle* h, const int32_t* rp, const int32_t* ci, const double* v, const float* v32,
                      int n_row, const double* x, double* y, const double* b, cudaStream_t st,
-                     bool short_rows = false, const __half* v16 = nullptr) {
-  if (!h->mg_fp32 || !v32) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
+                     bool short_rows = false, const __half* v16 = nullptr, double blocks_per_row = 0.0) {
+  if (!h->mg_fp32 || (!v32 && !v16)) return mg_spmv<MODE>(h, rp, ci, v, n_row, x, y, b, st);
   if (n_row == 0) return JSSO_OK;
 #if JSSO_MG_RP
-  {
+  // thread per (row, row pair) when the rows are short enough for a thread to stream one alone and there are enough
+  // of them to fill the GPU (measured at 1M quads: 9-block rows 180 vs 306 us); long rows (restrictions: ~26 blocks
+  // per coarse row) and the small coarse levels keep a warp per row
+  if (short_rows || v16 || (blocks_per_row > 0.0 && blocks_per_row <= 12.0 && n_row >= 4096)) {
     // MODE 0: y = A x;  2: y = b - A x;  3: y += A x   as  ca * b + cb * y_row + cc * A x
     const double ca = (MODE == 2) ? 1.0 : 0.0, cb = (MODE == 3) ? 1.0 : 0.0, cc = (MODE == 2) ? -1.0 : 1.0;
     const double* bv = (MODE == 2) ? b : nullptr;
@@ -1351,8 +1360,11 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       mg_diag_inverse_kernel<<<cdiv(n, 128), 128, 0, st>>>(n, h->mg[l - 1].c_diag, A.v, m.Dinv);
       CKL("mg_diag_inverse_kernel");
     }
-    // lambda_max(D^-1 A): power iteration from a pseudo-random vector (30 steps, x1.15 safety); an
-    // underestimate would make the Chebyshev smoother amplify the top modes and the V-cycle indefinite
+    // lambda_max(D^-1 A): power iteration from a pseudo-random vector; an underestimate would make the Chebyshev
+    // smoother amplify the top modes and the V-cycle indefinite.  The estimate grows monotonically: 0.93-0.95 of the
+    // true value after 10 steps, 0.98 after 30 (CPU study on three levels of a 64^2 plate), so 10 steps x 1.2 is as
+    // safe as the 30 steps x 1.15 of round 1 at a third of the cost (the 150 SpMVs were 22 of the 40 ms of a numeric
+    // setup at 1M quads)
     const long long nd = 6LL * n;
     const int vb = std::max(1, std::min(h->red_blocks, cdiv(nd, 256)));
     mg_hash_fill_kernel<<<vb, 256, 0, st>>>(nd, m.r);
@@ -1368,7 +1380,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       const size_t off = 6 * (size_t)rs;
       const long long ndl = 6LL * rn;
       const int vbl = std::max(1, std::min(h->red_blocks, cdiv(ndl, 256)));
-      for (int it = 0; it < 30; ++it) {
+      for (int it = 0; it < h->mg_power_iters; ++it) {
         if (it > 0) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
         if ((rc = mg_spmv<0>(h, A.rp + rs, A.ci, A.v, rn, m.r, m.d + off, nullptr, st))) return rc;
         if (m.Dinv && rn > 0) {
@@ -1384,7 +1396,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
         CKL("mg_axpby_kernel");
       }
     }
-    for (int it = 0; it < 30 && !dist_pow; ++it) {
+    for (int it = 0; it < h->mg_power_iters && !dist_pow; ++it) {
       if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n, m.r, m.d, nullptr, st))) return rc;
       if (m.Dinv) {
         block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
@@ -1398,7 +1410,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       mg_axpby_kernel<<<vb, 256, 0, st>>>(nd, 1.0 / std::sqrt(h->mg_scal_host[0]), m.d, 0.0, m.r);
       CKL("mg_axpby_kernel");
     }
-    m.lam = 1.15 * lam;
+    m.lam = h->mg_power_safety * lam;
     mg_centroid_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.mem_ptr, m.mem, X, m.Xc);
     CKL("mg_centroid_kernel");
     mg_smooth_prolongator_kernel<<<cdiv(m.nnz_p, 128), 128, 0, st>>>(
@@ -1418,7 +1430,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     }
     X = m.Xc;
   }
-  if (h->mg_fp32 && nl > 0) {
+  if (h->mg_fp32 && nl > 0 && h->vals32) {
     if ((rc = mg_to_float(h, 36LL * h->sym.nnzb(), h->vals, h->vals32, st))) return rc;
   }
   if (h->mg_fp16 && nl > 0 && h->sym.nnzb() > 0) {
@@ -1451,12 +1463,12 @@ static int mg_smooth(jsso_handle* h, int l, const double* b, double* x, bool zer
   if (zero_guess) {
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, b, m.d, x, 0.0, 1.0 / theta, 1);
   } else {
-    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;
     mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, 0.0, 1.0 / theta, 0);
   }
   CKL("mg_cheb_kernel<1>");
   for (int k = 1; k < deg; ++k) {
-    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, n, x, m.r, b, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, m.Dinv, m.r, m.d, x, rho_new * rho, 2.0 * rho_new / delta, 0);
     CKL("mg_cheb_kernel<0>");
@@ -1479,8 +1491,8 @@ static int mg_vcycle(jsso_handle* h, int l, const double* b, double* x, int deg,
   double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
   if ((rc = mg_smooth(h, l, b, x, true, deg, st))) return rc;
-  if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st, false, A.v16))) return rc;          // r = b - A x
-  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.Pt32, m.n_c, m.r, bc, nullptr, st))) return rc;   // b_c = P^T r
+  if ((rc = mg_spmv_p<2>(h, A.rp, A.ci, A.v, A.v32, m.n_f, x, m.r, b, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;          // r = b - A x
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr, m.pt_col, m.Pt, m.Pt32, m.n_c, m.r, bc, nullptr, st, false, nullptr, (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;   // b_c = P^T r
   if ((rc = mg_vcycle(h, l + 1, bc, xc, deg, st))) return rc;
   if ((rc = mg_spmv_p<3>(h, m.p_rowptr, m.p_col, m.P, m.P32, m.n_f, xc, x, nullptr, st,
                          m.nnz_p <= 5LL * m.n_f))) return rc;                                        // x += P x_c
@@ -1620,7 +1632,7 @@ static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, boo
     }
   } else {
     if ((rc = mgd_exchange(h, l, x, st))) return rc;
-    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;
     if (n > 0) {
       mg_cheb_kernel<1><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, 0.0, 1.0 / theta, 0);
       CKL("mg_cheb_kernel<1>");
@@ -1628,7 +1640,7 @@ static int mg_smooth_dist(jsso_handle* h, int l, const double* b, double* x, boo
   }
   for (int k = 1; k < deg; ++k) {
     if ((rc = mgd_exchange(h, l, x, st))) return rc;
-    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;
+    if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     if (n > 0) {
       mg_cheb_kernel<0><<<nb, 128, 0, st>>>(n, Dinv, m.r + off, m.d + off, x + off, rho_new * rho, 2.0 * rho_new / delta, 0);
@@ -1655,9 +1667,9 @@ static int mg_vcycle_dist(jsso_handle* h, int l, double* b, double* x, int deg, 
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
   if ((rc = mg_smooth_dist(h, l, b, x, true, deg, st))) return rc;
   if ((rc = mgd_exchange(h, l, x, st))) return rc;
-  if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16))) return rc;        // r = b - A x
+  if ((rc = mg_spmv_p<2>(h, A.rp + s, A.ci, A.v, A.v32, n, x, m.r + off, b + off, st, false, A.v16, (double)A.nnz / std::max(A.n, 1)))) return rc;        // r = b - A x
   if ((rc = mgd_exchange(h, l, m.r, st))) return rc;
-  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st))) return rc;   // b_c = P^T r
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st, false, nullptr, (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;   // b_c = P^T r
   if (l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; }
   if ((rc = mg_vcycle_dist(h, l + 1, bc, xc, deg, st))) return rc;
   if (l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; }
@@ -1761,7 +1773,7 @@ static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaSt
   if (dist) { if ((rc = mgd_exchange(h, 0, b, st))) return rc; }
   if ((rc = mg_lin_level0<0>(h, s, n, b, m.r + off, b + off, nullptr, 1.0, 0.0, -it, nullptr, st))) return rc;
   if (dist) { if ((rc = mgd_exchange(h, 0, m.r, st))) return rc; }
-  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st))) return rc;
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st, false, nullptr, (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;
   if (dist) {
     if (1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, 1, bc, st))) return rc; }
     if ((rc = mg_vcycle_dist(h, 1, bc, xc, deg, st))) return rc;

@@ -132,6 +132,32 @@ def test_user_objective():
     assert np.abs(sens - ref).max() / np.abs(ref).max() < 1e-6
 
 
+def test_user_objective_scalar_valued_as_in_the_reference():
+    """The reference's signature: func(sso_model, u, *args) -> scalar, differentiated by reverse mode
+    (SSO_model.py:303-306, 333-339).  Without jax in this image the gradient dL/du comes from PyTorch autograd: the
+    same penalty written with torch ops gives the same value and sensitivities as the (value, gradient) form."""
+    import torch
+    md = meshes.plate(10)
+    w = np.random.default_rng(0).uniform(0.5, 1.5, md.ndof)
+    w[md.known] = 0
+    out = []
+    for form in ('scalar', 'pair'):
+        sso = jb.SSO_model(build_model(md))
+        for node in md.design_nodes:
+            sso.add_nodeparameter(jb.NodeParameter(int(node), 2))
+        sso.initialize_parameters_values()
+        if form == 'scalar':
+            sso.set_objective('user', func=lambda m_, u, weight: 0.5 * torch.sum(torch.as_tensor(weight) * u * u),
+                              func_args=(w,))
+        else:
+            sso.set_objective('user', func=lambda m_, u, weight: (float(0.5 * np.sum(weight * u * u)), weight * u),
+                              func_args=(w,))
+        sso.rtol = 1e-12
+        out.append(sso.value_grad_params())
+    assert abs(out[0][0] - out[1][0]) <= 1e-12 * abs(out[1][0])
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-10 * np.abs(out[1][1]).max()
+
+
 def test_warm_started_optimiser_steps():
     """Three projected-gradient steps with sso.warm_start: fewer PCG iterations after the first,
     same objective as cold starts."""
