@@ -274,7 +274,7 @@ def run_reference(args):
 
 
 def distributed_solve_handle(nat, gmd, rank, world, device, bcast, allgather, min_dist_nodes, use_p2p=True,
-                             partition_kind='auto'):
+                             partition_kind='auto', dist_setup=True):
     """Whole-mesh handle whose multigrid V-cycle PCG is distributed by row ranges over the ranks (collective).
 
     The partition of the SOLVE is `dist_multigrid.solve_partition`: contiguous ranges of the mesh's own numbering when
@@ -307,10 +307,13 @@ def distributed_solve_handle(nat, gmd, rank, world, device, bcast, allgather, mi
         levels = hd.mg_setup()
     plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist_nodes)
     hd.mg_set_dist(bcast(nat.nccl_unique_id() if rank == 0 else None), rank, world, plan)
+    if dist_setup:
+        hd.mg_set_dist_setup(rp, ci, levels, plan, rank)
     if use_p2p:
         hd.mg_p2p_connect(plan, allgather)
     info = {'nodes_per_level': [a for a, _ in hd.mg_levels] + [hd.mg_levels[-1][1]],
             'symbolic_setup_s': time.perf_counter() - t0, 'partition': kind,
+            'numeric_setup': 'distributed by row ranges (ghost rows recomputed, coarse matrices all-gathered)' if dist_setup else 'replicated',
             'exchange': 'NVLink peer memory (push / wait kernels, mailbox all-reduce)' if use_p2p else 'NCCL send/recv',
             'distributed': dmg.plan_summary(plan)}
     return hd, smd, perm, info, levels
@@ -480,7 +483,7 @@ def run_b200(args):
         else:
             hg, smd, solve_perm, mg_info, mg_levels = distributed_solve_handle(
                 nat, gmd, rank, world, local_rank, bcast, allgather_obj, args.min_dist_nodes, use_p2p=args.p2p,
-                partition_kind=args.solve_partition)
+                partition_kind=args.solve_partition, dist_setup=args.dist_setup)
     if world == 1 and args.solve and args.precond != 'block_jacobi':
         # single GPU: smoothed-aggregation multigrid preconditioner (symbolic hierarchy, once per model)
         t_mg = time.perf_counter()
@@ -653,7 +656,7 @@ def run_b200(args):
                                             if precond != 'block_jacobi' else 'block-Jacobi'),
                          'solve': ('single GPU' if world == 1 else
                                    ('V-cycle PCG distributed by row ranges over ' + mg_info['exchange'] +
-                                    ' (assembly + numeric setup replicated), adjoint partitioned') if distributed else
+                                    (' (assembly + numeric setup distributed too)' if args.dist_setup else ' (assembly + numeric setup replicated)') + ', adjoint partitioned') if distributed else
                                    'replicated on every rank (whole-mesh handle), adjoint partitioned' if hg is not None
                                    else 'distributed CG over the partition'),
                          'multigrid': mg_info,
@@ -848,6 +851,8 @@ def main():
     ap.add_argument('--solve-partition', default='auto', choices=['auto', 'natural', 'rcb'],
                     help='N > 1: row partition of the distributed solve (auto: contiguous ranges of the mesh numbering '
                          'when it is banded, else RCB with renumbering)')
+    ap.add_argument('--replicated-setup', dest='dist_setup', action='store_false',
+                    help='N > 1: every rank assembles the whole matrix and builds the whole multigrid hierarchy (A/B)')
     ap.add_argument('--no-dist-check', dest='dist_check', action='store_false',
                     help='N > 1: skip the comparison of the distributed solve with a replicated solve of the same system')
     ap.add_argument('--topo-iters', type=int, default=10, help='BASELINE config 4 leg at N = 1: optimiser iterations (0: skip)')

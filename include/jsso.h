@@ -234,6 +234,24 @@ int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, i
 int jsso_mg_p2p_reserve(jsso_handle* h, int32_t max_recv_common);
 int jsso_mg_p2p_export(jsso_handle* h, uint8_t out[128]);
 int jsso_mg_p2p_connect(jsso_handle* h, const uint8_t* all_handles, const int32_t* max_recv_all);
+/* Optional: distribute the NUMERIC SETUP of the distributed levels too (after jsso_mg_set_dist; no reference
+ * counterpart, see above).  Without it every rank assembles the whole matrix and builds the whole hierarchy
+ * redundantly (24 ms at 1M quads: the Amdahl term of an 8-GPU gradient evaluation).  With it a rank assembles,
+ * factors and scales only the rows it reads (row hulls of level 0), computes at every distributed level the
+ * Galerkin blocks of its own coarse rows and the P / AP blocks they read -- rows of neighbouring ranks are
+ * recomputed as ghost rows, no communication -- and the ranks all-gather the coarse matrices (NCCL, by slot ranges).
+ * jsso_get_values* / jsso_spmv of such a handle are valid on this rank's rows only; u is still returned whole.
+ * One descriptor per distributed level (jaxsso_b200/dist_multigrid.py::setup_plan). */
+typedef struct {
+  int32_t n_p_slots, n_ap_slots;
+  const int32_t *p_slots, *ap_slots;   /* sorted slot ids of the P and AP blocks this rank computes */
+  const int32_t* ac_bounds;            /* [n_rank + 1] slot ranges of the coarse matrix owned by the ranks */
+  int32_t p_own_lo, p_own_hi;          /* slot range of this rank's prolongation rows P[fs:fe] (FP32 copy) */
+  int32_t pt_own_lo, pt_own_hi;        /* slot range of this rank's restriction rows P^T[cs:ce] (transposed here) */
+  int32_t scale_row_lo, scale_row_hi;  /* level 0 only: rows whose scaled blocks are read ... */
+  int32_t factor_row_lo, factor_row_hi; /* ... and rows whose block-Jacobi factor is needed (assembly hull) */
+} jsso_mg_setup_desc;
+int jsso_mg_set_dist_setup(jsso_handle* h, int32_t n_dist, const jsso_mg_setup_desc* desc);
 /* out[3]: halo exchanges and scalar all-reduces issued by the distributed solve so far, and whether they run over
  * peer memory (1) or NCCL (0). */
 int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out);

@@ -67,13 +67,20 @@ class MgHaloDesc(C.Structure):
     _fields_ = [('n_peer', C.c_int32)] + [(k, C.c_void_p) for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr',
                                                                       'recv_idx', 'remote_off')]
 
+class MgSetupDesc(C.Structure):
+    _fields_ = [('n_p_slots', C.c_int32), ('n_ap_slots', C.c_int32), ('p_slots', C.c_void_p), ('ap_slots', C.c_void_p),
+                ('ac_bounds', C.c_void_p), ('p_own_lo', C.c_int32), ('p_own_hi', C.c_int32), ('pt_own_lo', C.c_int32),
+                ('pt_own_hi', C.c_int32), ('scale_row_lo', C.c_int32), ('scale_row_hi', C.c_int32),
+                ('factor_row_lo', C.c_int32), ('factor_row_hi', C.c_int32)]
+
+
 PRECOND = {'auto': 0, 'block_jacobi': 1, 'multigrid': 2}
 
 
 # every symbol include/jsso.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['jsso_create', 'jsso_create_from_bsr', 'jsso_set_values_host', 'jsso_destroy', 'jsso_last_error', 'jsso_get_sizes', 'jsso_pattern', 'jsso_mg_aggregate', 'jsso_mg_pattern_lists', 'jsso_assembly_tasks',
            'jsso_quad_ke', 'jsso_beam_ke', 'jsso_quad_area', 'jsso_csr_spmv', 'jsso_assemble', 'jsso_gather_rows', 'jsso_profile', 'jsso_profile_read', 'jsso_assemble_from_ke', 'jsso_get_values',
-           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_mg_set_dist', 'jsso_mg_p2p_reserve', 'jsso_mg_p2p_export', 'jsso_mg_p2p_connect', 'jsso_mg_dist_counters', 'jsso_adjoint',
+           'jsso_get_values_host', 'jsso_get_flags', 'jsso_spmv', 'jsso_pcg', 'jsso_mg_setup', 'jsso_mg_set_dist', 'jsso_mg_p2p_reserve', 'jsso_mg_p2p_export', 'jsso_mg_p2p_connect', 'jsso_mg_set_dist_setup', 'jsso_mg_dist_counters', 'jsso_adjoint',
            'jsso_forward', 'jsso_backward', 'jsso_value_and_grad_host', 'jsso_assemble_adjoint_host', 'jsso_nccl_unique_id',
            'jsso_set_halo', 'jsso_p2p_export', 'jsso_p2p_connect', 'jsso_halo_exchange', 'jsso_set_device', 'jsso_dev_alloc', 'jsso_dev_free',
            'jsso_host_alloc_pinned', 'jsso_host_free_pinned', 'jsso_memcpy_h2d', 'jsso_memcpy_d2h',
@@ -121,6 +128,7 @@ def lib():
     L.jsso_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats), vp]
     L.jsso_mg_setup.argtypes = [vp, i32, C.POINTER(MgLevelDesc)]
     L.jsso_mg_set_dist.argtypes = [vp, vp, i32, i32, i32, vp, i32, C.POINTER(MgHaloDesc)]
+    L.jsso_mg_set_dist_setup.argtypes = [vp, i32, C.POINTER(MgSetupDesc)]
     L.jsso_mg_dist_counters.argtypes = [vp, vp]
     L.jsso_mg_p2p_reserve.argtypes = [vp, i32]
     L.jsso_mg_p2p_export.argtypes = [vp, vp]
@@ -448,6 +456,28 @@ class Handle:
         blob = np.frombuffer(b''.join(blobs), dtype=np.uint8).copy()
         mr = np.full(plan['n_rank'], common, np.int32)
         self._ck(lib().jsso_mg_p2p_connect(self.h, _ptr(blob), _ptr(mr)))
+
+    def mg_set_dist_setup(self, rowptr, colidx, levels, plan, rank, _drop_ghost=False):
+        """Distribute the numeric multigrid setup of the distributed levels as well (after mg_set_dist): this rank
+        assembles / scales only the rows it reads and computes only its share of every Galerkin product
+        (jaxsso_b200.dist_multigrid.setup_plan)."""
+        from . import dist_multigrid
+        sp = dist_multigrid.setup_plan(rowptr, colidx, levels, plan, rank, drop_ghost=_drop_ghost)
+        descs = (MgSetupDesc * max(len(sp), 1))()
+        keep = []
+        for d, lv in zip(descs, sp):
+            for k in ('p_slots', 'ap_slots', 'ac_bounds'):
+                a = np.ascontiguousarray(lv[k], dtype=np.int32)
+                keep.append(a)
+                setattr(d, k, a.ctypes.data)
+            d.n_p_slots, d.n_ap_slots = int(lv['p_slots'].shape[0]), int(lv['ap_slots'].shape[0])
+            d.p_own_lo, d.p_own_hi = (int(v) for v in lv['p_own'])
+            d.pt_own_lo, d.pt_own_hi = (int(v) for v in lv['pt_own'])
+            if 'scale_rows' in lv:
+                d.scale_row_lo, d.scale_row_hi = (int(v) for v in lv['scale_rows'])
+                d.factor_row_lo, d.factor_row_hi = (int(v) for v in lv['factor_rows'])
+        self._ck(lib().jsso_mg_set_dist_setup(self.h, len(sp), descs))
+        return sp
 
     def mg_dist_counters(self):
         out = np.zeros(3, np.int64)

@@ -198,6 +198,17 @@ struct jsso_handle {
     unsigned* push_counter = nullptr;
     unsigned long long red_seq = 0;
     std::vector<void*> ipc_opened;
+    // distributed numeric setup (jsso_mg_set_dist_setup)
+    struct SetupLevel {
+      int32_t *p_list = nullptr, *ap_list = nullptr;
+      int n_p = 0, n_ap = 0;
+      std::vector<int32_t> ac_bounds;   // [n_rank + 1] slot ranges of the coarse matrix
+      int p_lo = 0, p_hi = 0, pt_lo = 0, pt_hi = 0;   // slot ranges of the own prolongation / restriction rows
+    };
+    bool setup_on = false;
+    std::vector<SetupLevel> setup;
+    int sc_lo = 0, sc_hi = 0, w_lo = 0, w_hi = 0;      // level-0 row hulls: scaled blocks, block-Jacobi factors
+    int asm_t0 = 0, asm_t1 = 0, asm_q0 = 0, asm_q1 = 0;   // assembly: task range and quad range covering [w_lo, w_hi)
   } mgd;
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
@@ -565,22 +576,29 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
   A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
   if (h->sym.nnzb() > 0 && h->asm_tasks) {
     const int nq = h->sym.n_quad;
+    // distributed numeric setup (jsso_mg_set_dist_setup): only the tasks that touch the rows this rank reads, and
+    // the geometry records of the quads they stage
+    const bool part = h->mgd.setup_on;
+    const int q0 = part ? h->mgd.asm_q0 : 0, q1 = part ? h->mgd.asm_q1 : nq;
+    const int t0 = part ? h->mgd.asm_t0 : 0, t1 = part ? h->mgd.asm_t1 : h->sym.n_task();
     if (h->prof) CK(cudaEventRecord(h->ev_prof[0], st));
-    if (nq > 0) {
-      quad_geometry_kernel<<<cdiv(nq, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
-          nq, crds, h->cnct_q, prop_q, h->quad_rec, h->flags);
+    if (q1 > q0) {
+      quad_geometry_kernel<<<cdiv(q1 - q0, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
+          q1 - q0, crds, h->cnct_q + 4 * (size_t)q0, prop_q + 5 * (size_t)q0, h->quad_rec + (size_t)q0 * REC_GLD, h->flags);
       CKL("quad_geometry_kernel");
     }
     if (h->prof) CK(cudaEventRecord(h->ev_prof[1], st));
     TaskArgs T;
-    T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta; T.task_els = h->task_els;
+    T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta + t0; T.task_els = h->task_els;
     T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
     T.blk_item_ptr = h->blk_item_ptr;
     T.crds = crds; T.cnct_b = h->cnct_b; T.prop_b = prop_b;
-    T.vals = h->vals; T.flags = h->flags; T.n_quad = nq; T.n_task = h->sym.n_task(); T.apply_bc = apply_bc;
-    assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
-                            TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
-    CKL("assemble_tasks_kernel");
+    T.vals = h->vals; T.flags = h->flags; T.n_quad = nq; T.n_task = t1 - t0; T.apply_bc = apply_bc;
+    if (T.n_task > 0) {
+      assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
+                              TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
+      CKL("assemble_tasks_kernel");
+    }
     if (h->prof) CK(cudaEventRecord(h->ev_prof[2], st));
   } else if (h->sym.nnzb() > 0) {
     assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
@@ -847,6 +865,23 @@ int jsso_spmv(jsso_handle* h, const double* x, double* y, void* stream) {
 static int ensure_scaled(jsso_handle* h, cudaStream_t st) {
   if (h->scaled) return JSSO_OK;
   const int n_row = h->sym.n_row;
+  if (h->mgd.setup_on) {
+    // distributed numeric setup: factors of the rows [w_lo, w_hi), scaled blocks of the rows [sc_lo, sc_hi)
+    const jsso_handle::MgDist& D = h->mgd;
+    if (D.w_hi > D.w_lo) {
+      diag_factor_kernel<<<cdiv(D.w_hi - D.w_lo, 128), 128, 0, st>>>(D.w_hi - D.w_lo, h->diag_slot + D.w_lo, h->vals,
+                                                                    h->W + 36 * (size_t)D.w_lo,
+                                                                    h->Lfac ? h->Lfac + 36 * (size_t)D.w_lo : nullptr, h->flags);
+      CKL("diag_factor_kernel");
+    }
+    const long long b0 = h->sym.rowptr[D.sc_lo], b1 = h->sym.rowptr[D.sc_hi];
+    if (b1 > b0) {
+      scale_blocks_kernel<<<cdiv(b1 - b0, 128), 128, 0, st>>>(b1 - b0, h->blk_row + b0, h->colidx + b0, h->W, h->vals + 36 * b0);
+      CKL("scale_blocks_kernel");
+    }
+    h->scaled = true;
+    return JSSO_OK;
+  }
   if (n_row > 0) {
     diag_factor_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->diag_slot, h->vals, h->W, h->Lfac, h->flags);
     CKL("diag_factor_kernel");
@@ -1261,6 +1296,61 @@ extern "C" int jsso_mg_dist_counters(const jsso_handle* h, int64_t* out) {
   return JSSO_OK;
 }
 
+static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n);
+extern "C" int jsso_mg_set_dist_setup(jsso_handle* h, int32_t n_dist, const jsso_mg_setup_desc* desc) {
+  if (!h || !desc) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  jsso_handle::MgDist& D = h->mgd;
+  if (D.n_rank < 2 || !D.comm) return fail(h, JSSO_ERR_STATE, "jsso_mg_set_dist_setup needs jsso_mg_set_dist first");
+  if (n_dist != D.n_dist) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: one descriptor per distributed level");
+  if (!h->asm_tasks && h->sym.n_quad + h->sym.n_beam > 0)
+    return fail(h, JSSO_ERR_STATE, "jsso_mg_set_dist_setup: needs the warp-task assembly (partial assembly by task ranges)");
+  D.setup.clear();
+  for (int l = 0; l < n_dist; ++l) {
+    const jsso_mg_setup_desc& d = desc[l];
+    const jsso_handle::MgLevel& m = h->mg[l];
+    if (d.n_p_slots < 0 || d.n_ap_slots < 0 || !d.ac_bounds || (d.n_p_slots && !d.p_slots) || (d.n_ap_slots && !d.ap_slots))
+      return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: bad descriptor");
+    jsso_handle::MgDist::SetupLevel L;
+    std::vector<int32_t> pl(d.p_slots, d.p_slots + d.n_p_slots), al(d.ap_slots, d.ap_slots + d.n_ap_slots);
+    for (int v : pl) if (v < 0 || v >= m.nnz_p) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: P slot out of range");
+    for (int v : al) if (v < 0 || v >= m.nnz_ap) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: AP slot out of range");
+    CK(upload(&L.p_list, pl)); CK(upload(&L.ap_list, al));
+    L.n_p = d.n_p_slots; L.n_ap = d.n_ap_slots;
+    L.ac_bounds.assign(d.ac_bounds, d.ac_bounds + D.n_rank + 1);
+    L.p_lo = d.p_own_lo; L.p_hi = d.p_own_hi; L.pt_lo = d.pt_own_lo; L.pt_hi = d.pt_own_hi;
+    if (!(0 <= L.p_lo && L.p_lo <= L.p_hi && L.p_hi <= m.nnz_p && 0 <= L.pt_lo && L.pt_lo <= L.pt_hi && L.pt_hi <= m.nnz_p))
+      return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: bad own slot ranges");
+    if (L.ac_bounds[0] != 0 || L.ac_bounds[D.n_rank] != m.nnz_c) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: ac_bounds do not cover the coarse matrix");
+    D.setup.push_back(L);
+  }
+  const int n_row = h->sym.n_row;
+  D.sc_lo = desc[0].scale_row_lo; D.sc_hi = desc[0].scale_row_hi;
+  D.w_lo = desc[0].factor_row_lo; D.w_hi = desc[0].factor_row_hi;
+  int s0, n0;
+  mgd_range(h, 0, s0, n0);
+  if (!(0 <= D.w_lo && D.w_lo <= D.sc_lo && D.sc_lo <= s0 && s0 + n0 <= D.sc_hi && D.sc_hi <= D.w_hi && D.w_hi <= n_row))
+    return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist_setup: row hulls must nest: factor >= scale >= own rows");
+  // assembly: the tasks (runs of block slots) that touch the rows [w_lo, w_hi), and the quads they stage
+  const Symbolic& S = h->sym;
+  const int nt = S.n_task();
+  const int slot_lo = S.rowptr[D.w_lo], slot_hi = S.rowptr[D.w_hi];
+  int t0 = 0, t1 = nt;
+  while (t0 + 1 < nt && S.task_meta[4 * (size_t)(t0 + 1)] <= slot_lo) ++t0;
+  while (t1 > t0 + 1 && S.task_meta[4 * (size_t)(t1 - 1)] >= slot_hi) --t1;
+  int q0 = S.n_quad, q1 = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int el0 = S.task_meta[4 * (size_t)t + 2], n_el = (S.task_meta[4 * (size_t)t + 3] >> 16) & 255;
+    for (int k = 0; k < n_el; ++k) { const int e = S.task_els[el0 + k]; q0 = std::min(q0, e); q1 = std::max(q1, e + 1); }
+  }
+  if (q1 < q0) { q0 = 0; q1 = 0; }
+  D.asm_t0 = t0; D.asm_t1 = t1; D.asm_q0 = q0; D.asm_q1 = q1;
+  D.setup_on = true;
+  h->assembled = false; h->scaled = false; h->mg_ready = false;
+  return JSSO_OK;
+}
+
 struct MgMat { const int32_t* rp; const int32_t* ci; const double* v; int n; const float* v32; const __half* v16; long long nnz; };
 static MgMat mg_matrix(jsso_handle* h, int l) {
   if (l == 0) return MgMat{h->rowptr, h->colidx, h->vals, h->sym.n_row, h->vals32, h->mg_fp16 ? h->vals16 : nullptr, h->sym.nnzb()};
@@ -1413,6 +1503,50 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     m.lam = h->mg_power_safety * lam;
     mg_centroid_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.mem_ptr, m.mem, X, m.Xc);
     CKL("mg_centroid_kernel");
+    if (h->mgd.setup_on && l < h->mgd.n_dist) {
+      // distributed numeric setup of this level (jsso_mg_set_dist_setup): the Galerkin blocks of the own coarse rows
+      // and the P / AP blocks they read (ghost rows recomputed); the coarse matrix is all-gathered by slot ranges
+      const jsso_handle::MgDist::SetupLevel& SL = h->mgd.setup[l];
+      const int me = h->mgd.rank;
+      if (SL.n_p > 0) {
+        mg_smooth_prolongator_kernel<<<cdiv(SL.n_p, 128), 128, 0, st>>>(
+            SL.n_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, m.Dinv, l == 0 ? h->Lfac : nullptr,
+            l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P, SL.p_list);
+        CKL("mg_smooth_prolongator_kernel");
+      }
+      // restriction rows of the own coarse nodes: P^T blocks [pt0, pt1); prolongation rows: P blocks [pr0, pr1)
+      const int pt[2] = {SL.pt_lo, SL.pt_hi}, pr[2] = {SL.p_lo, SL.p_hi};
+      if (pt[1] > pt[0]) {
+        mg_transpose_blocks_kernel<<<cdiv(36LL * (pt[1] - pt[0]), 256), 256, 0, st>>>(pt[1] - pt[0], m.pt_src, m.P, m.Pt, pt[0]);
+        CKL("mg_transpose_blocks_kernel");
+      }
+      if (SL.n_ap > 0) {
+        mg_block_product_kernel<0><<<cdiv(SL.n_ap, 128), 128, 0, st>>>(SL.n_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP,
+                                                                       SL.ap_list, 0);
+        CKL("mg_block_product_kernel<0>");
+      }
+      const int a0 = SL.ac_bounds[me], a1 = SL.ac_bounds[me + 1];
+      if (a1 > a0) {
+        mg_block_product_kernel<1><<<cdiv(a1 - a0, 128), 128, 0, st>>>(a1 - a0, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac,
+                                                                       nullptr, a0);
+        CKL("mg_block_product_kernel<1>");
+      }
+      CKN(g_nccl.GroupStart());
+      for (int r = 0; r < h->mgd.n_rank; ++r) {
+        if (r == me) continue;
+        const size_t mine = 36 * (size_t)(a1 - a0), theirs = 36 * (size_t)(SL.ac_bounds[r + 1] - SL.ac_bounds[r]);
+        if (mine) CKN(g_nccl.Send(m.Ac + 36 * (size_t)a0, mine, ncclDouble, r, h->mgd.comm, st));
+        if (theirs) CKN(g_nccl.Recv(m.Ac + 36 * (size_t)SL.ac_bounds[r], theirs, ncclDouble, r, h->mgd.comm, st));
+      }
+      CKN(g_nccl.GroupEnd());
+      if (h->mg_fp32) {
+        if ((rc = mg_to_float(h, 36LL * (pr[1] - pr[0]), m.P + 36 * (size_t)pr[0], m.P32 + 36 * (size_t)pr[0], st))) return rc;
+        if ((rc = mg_to_float(h, 36LL * (pt[1] - pt[0]), m.Pt + 36 * (size_t)pt[0], m.Pt32 + 36 * (size_t)pt[0], st))) return rc;
+        if ((rc = mg_to_float(h, 36LL * m.nnz_c, m.Ac, m.Ac32, st))) return rc;
+      }
+      X = m.Xc;
+      continue;
+    }
     mg_smooth_prolongator_kernel<<<cdiv(m.nnz_p, 128), 128, 0, st>>>(
         m.nnz_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, m.Dinv, l == 0 ? h->Lfac : nullptr,
         l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P);
@@ -1430,13 +1564,22 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     }
     X = m.Xc;
   }
-  if (h->mg_fp32 && nl > 0 && h->vals32) {
-    if ((rc = mg_to_float(h, 36LL * h->sym.nnzb(), h->vals, h->vals32, st))) return rc;
-  }
-  if (h->mg_fp16 && nl > 0 && h->sym.nnzb() > 0) {
-    const long long n16 = 36LL * h->sym.nnzb();
-    mg_to_half_kernel<<<std::max(1, std::min(1184, cdiv(n16, 256))), 256, 0, st>>>(n16, h->vals, h->vals16);
-    CKL("mg_to_half_kernel");
+  {
+    // reduced-precision copy of the fine matrix for the V-cycle: all rows, or this rank's own rows (distributed setup)
+    long long v0 = 0, v1 = h->sym.nnzb();
+    if (h->mgd.setup_on) {
+      int s0, n0;
+      mgd_range(h, 0, s0, n0);
+      v0 = h->sym.rowptr[s0]; v1 = h->sym.rowptr[s0 + n0];
+    }
+    if (h->mg_fp32 && nl > 0 && h->vals32) {
+      if ((rc = mg_to_float(h, 36LL * (v1 - v0), h->vals + 36 * v0, h->vals32 + 36 * v0, st))) return rc;
+    }
+    if (h->mg_fp16 && nl > 0 && v1 > v0) {
+      const long long n16 = 36LL * (v1 - v0);
+      mg_to_half_kernel<<<std::max(1, std::min(1184, cdiv(n16, 256))), 256, 0, st>>>(n16, h->vals + 36 * v0, h->vals16 + 36 * v0);
+      CKL("mg_to_half_kernel");
+    }
   }
   // coarsest level: dense inverse
   const MgMat C = mg_matrix(h, nl);
@@ -1818,7 +1961,8 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
   double* scal = h->mg_scal;
   const MgMat A = mg_matrix(h, 0);
   if (use_x0) {
-    if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;   // x is whole on every rank
+    if (dist) { if ((rc = mgd_exchange(h, 0, x, st))) return rc; }   // the rows of the other ranks were scaled there
+    if ((rc = mg_spmv<2>(h, A.rp + s, A.ci, A.v, n_row, x, r + off, b + off, st))) return rc;
   } else {
     CK(cudaMemsetAsync(x + off, 0, n * sizeof(double), st));
     CK(cudaMemcpyAsync(r + off, b + off, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1890,7 +2034,7 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
       first = true;
     }
   }
-  if (dist) { if ((rc = mgd_allgather(h, 0, x, st))) return rc; }
+  if (dist && !h->mgd.setup_on) { if ((rc = mgd_allgather(h, 0, x, st))) return rc; }   // else: after the unscaling
   if (stats) {
     stats->iterations = it; stats->restarts = restarts; stats->converged = converged ? 1 : 0;
     stats->relres = bb > 0 ? std::sqrt(rr / bb) : 0.0; stats->relres_recur = stats->relres;
@@ -1976,24 +2120,34 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
   const int n_row = h->sym.n_row;
   if (n_row == 0) return JSSO_OK;
   // b^ = W b (prescribed dofs zeroed); an initial guess x0 maps to y0 = W^-T x0 (x = W^T y)
-  block_apply_kernel<0><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, b, h->node_mask, h->vb);
-  CKL("block_apply_kernel<0>");
-  if (o.use_x0) {
-    block_solve_wt_kernel<<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, x, h->node_mask, h->vx);
-    CKL("block_solve_wt_kernel");
+  int rs = 0, rn = n_row;       // rows this rank scales / unscales: all, or its own range (distributed setup)
+  if (h->mgd.setup_on) mgd_range(h, 0, rs, rn);
+  const size_t ro = 6 * (size_t)rs;
+  if (rn > 0) {
+    block_apply_kernel<0><<<cdiv(rn, 128), 128, 0, st>>>(rn, h->W + 6 * ro, b + ro, h->node_mask + rs, h->vb + ro);
+    CKL("block_apply_kernel<0>");
+    if (o.use_x0) {
+      block_solve_wt_kernel<<<cdiv(rn, 128), 128, 0, st>>>(rn, h->W + 6 * ro, x + ro, h->node_mask + rs, h->vx + ro);
+      CKL("block_solve_wt_kernel");
+    }
   }
   // preconditioner: 0 auto (multigrid when a hierarchy is set, the system is not tiny and the
   // handle is single-GPU), 1 block-Jacobi CG, 2 smoothed-aggregation multigrid
   const bool have_mg = !h->mg.empty() && h->n_rank <= 1;
   const bool use_mg = (o.precond == 2) || (o.precond == 0 && have_mg && h->sym.n_row >= 20000);
   if (use_mg && !have_mg) return fail(h, JSSO_ERR_STATE, "precond = multigrid but no hierarchy (jsso_mg_setup)");
+  if (h->mgd.setup_on && !use_mg)
+    return fail(h, JSSO_ERR_STATE, "a handle with the distributed numeric setup holds only this rank's rows: multigrid solve only");
   if (stats) stats->flags = fl;
   if (use_mg) rc = mg_solve_fused(h, o, o.use_x0 != 0, stats, st);
   else rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
   if (rc && rc != JSSO_ERR_NOCONV) return rc;
-  block_apply_kernel<1><<<cdiv(n_row, 128), 128, 0, st>>>(n_row, h->W, h->vx, nullptr, x);
-  CKL("block_apply_kernel<1>");
+  if (rn > 0) {
+    block_apply_kernel<1><<<cdiv(rn, 128), 128, 0, st>>>(rn, h->W + 6 * ro, h->vx + ro, nullptr, x + ro);
+    CKL("block_apply_kernel<1>");
+  }
+  if (h->mgd.setup_on) { int r2 = mgd_allgather(h, 0, x, st); if (r2) return r2; }   // every rank unscaled its own rows
   if (h->n_rank > 1) { int r2 = halo_exchange_w(h, x, 6, st); if (r2) return r2; }
   CK(cudaStreamSynchronize(st));
   return rc;

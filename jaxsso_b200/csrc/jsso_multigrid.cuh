@@ -155,9 +155,11 @@ mg_smooth_prolongator_kernel(int nnz_p, const int32_t* __restrict__ p_row, const
                              const double* __restrict__ Dinv /* row-major or null */,
                              const double* __restrict__ Lfac /* row-major L per node or null */,
                              const uint8_t* __restrict__ mask, const double* __restrict__ X,
-                             const double* __restrict__ Xc, double omega, double* __restrict__ P) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nnz_p) return;
+                             const double* __restrict__ Xc, double omega, double* __restrict__ P,
+                             const int32_t* __restrict__ list = nullptr /* nnz_p slots to compute, or all */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz_p) return;
+  const int s = list ? list[t] : t;
   const int i = p_row[s];
   double acc[36];
 #pragma unroll
@@ -199,9 +201,11 @@ template <int TRANS>
 __global__ void __launch_bounds__(128)
 mg_block_product_kernel(int nnz_out, const int32_t* __restrict__ ptr, const int32_t* __restrict__ li,
                         const int32_t* __restrict__ ri, const double* __restrict__ Lv,
-                        const double* __restrict__ Rv, double* __restrict__ out) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nnz_out) return;
+                        const double* __restrict__ Rv, double* __restrict__ out,
+                        const int32_t* __restrict__ list = nullptr /* nnz_out slots to compute */, int first = 0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz_out) return;
+  const int s = list ? list[t] : first + t;
   double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
@@ -216,12 +220,12 @@ mg_block_product_kernel(int nnz_out, const int32_t* __restrict__ ptr, const int3
 
 // Pt[s] = P[src[s]]^T
 __global__ void mg_transpose_blocks_kernel(int nnz, const int32_t* __restrict__ src, const double* __restrict__ P,
-                                           double* __restrict__ Pt) {
+                                           double* __restrict__ Pt, int first = 0 /* slots [first, first + nnz) */) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 36LL * nnz) return;
-  const int s = (int)(t / 36), k = (int)(t % 36);
+  const int s = first + (int)(t / 36), k = (int)(t % 36);
   const int r = k % 6, c = k / 6;
-  Pt[t] = P[(size_t)src[s] * 36 + 6 * r + c];
+  Pt[(size_t)s * 36 + k] = P[(size_t)src[s] * 36 + 6 * r + c];
 }
 
 // Chebyshev smoother step on D^-1 A, thread per node:

@@ -211,6 +211,65 @@ def rank_plan(plan, rank):
     return out
 
 
+def _concat_ranges(ptr, ids):
+    """Concatenation of arange(ptr[i], ptr[i + 1]) for i in ids (vectorised)."""
+    ids = np.asarray(ids, np.int64)
+    cnt = (ptr[ids + 1] - ptr[ids]).astype(np.int64)
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, np.int64)
+    start = np.repeat(ptr[ids].astype(np.int64), cnt)
+    return start + (np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+
+
+def setup_plan(rowptr, colidx, levels, plan, rank, drop_ghost=False):
+    """What ONE rank has to compute of the numeric multigrid setup at the distributed levels (jsso_mg_set_dist_setup).
+
+    Level l < n_dist, own fine rows [fs, fe), own coarse rows [cs, ce):
+      * Galerkin blocks Ac of the own coarse rows (a contiguous slot range; all-gathered afterwards, so that the next
+        level sees its whole matrix);
+      * the AP blocks those Ac blocks read (`ap_slots`);
+      * the P blocks read by those AP blocks, by those Ac blocks, by the restriction rows P^T[cs:ce] and by the
+        prolongation rows P[fs:fe] (`p_slots`) -- rows of neighbouring ranks are recomputed (ghost rows), which
+        needs no communication because every rank can assemble any row of the fine matrix.
+    Level 0 also gets the row hulls the fine matrix must be assembled / scaled on: `scale_rows` = every row whose
+    scaled blocks are read (own rows, rows of p_slots and ap_slots), `factor_rows` = those plus their columns (the
+    block-Jacobi factors W_r, W_c of a scaled block)."""
+    n_dist = plan['n_dist']
+    out = []
+    for l in range(n_dist):
+        lv = levels[l]
+        fs, fe = int(plan['bounds'][l][rank]), int(plan['bounds'][l][rank + 1])
+        cs, ce = int(plan['bounds'][l + 1][rank]), int(plan['bounds'][l + 1][rank + 1])
+        ac0, ac1 = int(lv['c_rowptr'][cs]), int(lv['c_rowptr'][ce])
+        terms = np.arange(lv['cl_ptr'][ac0], lv['cl_ptr'][ac1], dtype=np.int64)
+        ap_slots = np.unique(lv['cl_ap'][terms])
+        ap_terms = _concat_ranges(lv['apl_ptr'], ap_slots)
+        p_slots = np.unique(np.concatenate([
+            lv['cl_p'][terms].astype(np.int64), lv['apl_p'][ap_terms].astype(np.int64),
+            lv['pt_src'][lv['pt_rowptr'][cs]:lv['pt_rowptr'][ce]].astype(np.int64),
+            np.arange(lv['p_rowptr'][fs], lv['p_rowptr'][fe], dtype=np.int64)]))
+        if drop_ghost and l == 0 and rank == 0:     # test hook: a ghost block missing from the plan must be noticed
+            ghost = p_slots[p_slots >= lv['p_rowptr'][fe]]
+            p_slots = np.setdiff1d(p_slots, ghost[-1:])
+        ac_bounds = lv['c_rowptr'][plan['bounds'][l + 1]].astype(np.int32)
+        d = dict(p_slots=p_slots.astype(np.int32), ap_slots=ap_slots.astype(np.int32), ac_bounds=ac_bounds,
+                 p_own=(int(lv['p_rowptr'][fs]), int(lv['p_rowptr'][fe])),
+                 pt_own=(int(lv['pt_rowptr'][cs]), int(lv['pt_rowptr'][ce])))
+        if l == 0:
+            n_f = lv['n_f']
+            p_row = np.repeat(np.arange(n_f, dtype=np.int64), np.diff(lv['p_rowptr']))
+            ap_row = np.repeat(np.arange(n_f, dtype=np.int64), np.diff(lv['ap_rowptr']))
+            rows = np.concatenate([[fs, max(fe - 1, fs)], p_row[p_slots], ap_row[ap_slots]])
+            lo, hi = int(rows.min()), int(rows.max()) + 1
+            cols = colidx[rowptr[lo]:rowptr[hi]]
+            wlo, whi = min(lo, int(cols.min())), max(hi, int(cols.max()) + 1)
+            d['scale_rows'] = (lo, hi)
+            d['factor_rows'] = (wlo, whi)
+        out.append(d)
+    return out
+
+
 def common_max_recv(plan):
     """Largest number of nodes any rank receives in one exchange of any level (the stride of the peer-memory
     receive arenas, which must be the same on every rank)."""

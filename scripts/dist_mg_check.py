@@ -26,7 +26,8 @@ dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 min_dist = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 deg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-use_p2p = len(sys.argv) > 4 and sys.argv[4] == 'p2p'    # exchanges over peer memory (jsso_mg_p2p_connect) instead of NCCL
+use_p2p = 'p2p' in sys.argv[4:]    # exchanges over peer memory (jsso_mg_p2p_connect) instead of NCCL
+dist_setup = 'setup' in sys.argv[4:]   # numeric setup distributed too (jsso_mg_set_dist_setup)
 rtol = 1e-10
 nat.lib().jsso_set_device(local)
 md0 = meshes.plate(size)
@@ -46,6 +47,8 @@ def solve(distributed):
         ids = [nat.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         h.mg_set_dist(ids[0], rank, world, plan)
+        if dist_setup:
+            h.mg_set_dist_setup(rp, ci, levels, plan, rank)
         if use_p2p:
             def allgather(obj):
                 box = [None] * world
@@ -86,7 +89,7 @@ if rank == 0:
     _, u0, *_ = h0.value_and_grad_host(md0.crds, md0.prop_quads, md0.prop_beams, md0.loads,
                                        opts=nat.make_opts(rtol=1e-11, precond='block_jacobi'))
     e0 = np.linalg.norm(ud.reshape(-1, 6) - u0.reshape(-1, 6)[perm]) / np.linalg.norm(u0)
-    res = {'world': world, 'size': size, 'cheb_degree': deg, 'peer_memory': use_p2p, 'u_err_vs_single_mg': eu, 'u_err_vs_block_jacobi': e0,
+    res = {'world': world, 'size': size, 'cheb_degree': deg, 'peer_memory': use_p2p, 'distributed_setup': dist_setup, 'u_err_vs_single_mg': eu, 'u_err_vs_block_jacobi': e0,
            'iters_dist': std.iterations, 'iters_single': sts.iterations, 'relres_dist': std.relres,
            'seconds_dist': dtd, 'seconds_single': dts, 'same_on_all_ranks': same, 'plan': info,
            'exchanges': cnt[0], 'allreduces': cnt[1]}

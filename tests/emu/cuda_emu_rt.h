@@ -20,7 +20,14 @@ namespace emurt {
 
 inline cudaError_t ok() { return cudaSuccess; }
 
-inline cudaError_t Malloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// EMU_POISON=1: fresh "device" memory is filled with 0xFF (NaN as a double, -1 as an index) instead of zeros, so that a
+// kernel reading something nobody computed (e.g. a ghost row missing from a distributed setup plan) shows up
+inline cudaError_t Malloc(void** p, size_t n) {
+  static const bool poison = std::getenv("EMU_POISON") && std::getenv("EMU_POISON")[0] == '1';
+  *p = std::calloc(n ? n : 1, 1);
+  if (*p && poison) std::memset(*p, 0xFF, n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T> inline cudaError_t Malloc(T** p, size_t n) { return Malloc((void**)p, n); }
 inline cudaError_t Free(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t MallocHost(void** p, size_t n) { return Malloc(p, n); }

@@ -50,6 +50,8 @@ def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=8):
             rp, ci = h.pattern()
             plan = dmg.build_plan(rp, ci, levels, bounds, min_dist_nodes=min_dist)
             h.mg_set_dist(nid, rank, world, plan)
+            if os.environ.get('EMU_DIST_SETUP', '0') == '1':   # numeric setup distributed as well
+                h.mg_set_dist_setup(rp, ci, levels, plan, rank, _drop_ghost=os.environ.get('EMU_DROP_GHOST', '0') == '1')
             if len(dist) > 5 and dist[5] is not None:      # peer-memory exchange: gather the IPC bytes between the threads
                 box, bar = dist[5]
 

@@ -87,7 +87,26 @@ def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size,
     assert res['exchanges'] > 0 and res['allreduces'] >= 3 * res['iters_single']
 
 
-@pytest.mark.parametrize('args,env', [(('grad', 4), {}), (('dist', 2, 6, 5, 1), {'JSSO_MG_FP16': '1'})])
+@pytest.mark.parametrize('world,size,min_dist,deg,p2p', [(2, 12, 10, 1, ''), (4, 16, 10, 1, 'p2p'), (2, 12, 1000, 2, 'p2p')])
+def test_distributed_numeric_setup(emu_api, world, size, min_dist, deg, p2p):
+    """jsso_mg_set_dist_setup: every rank assembles / scales only the row hull it reads and computes only its share of
+    the prolongators and Galerkin products (ghost rows recomputed, coarse matrices all-gathered).  Fresh "device"
+    memory is poisoned (EMU_POISON: NaN / -1), so anything read but not computed would surface: same iteration count
+    and solution as the undistributed solve, identical u on every rank -- and with ONE ghost block dropped from the
+    plan (negative control) the solve must fail."""
+    env = {'EMU_POISON': '1', 'EMU_DIST_SETUP': '1'}
+    res = run(emu_api, 'dist', world, size, min_dist, deg, *([p2p] if p2p else []), env=env)
+    assert res['converged'] and res['identical_on_all_ranks']
+    assert all(abs(i - res['iters_single']) <= 1 for i in res['iters_dist'])
+    assert res['err_vs_single'] <= 1e-10 and res['err_vs_oracle'] <= 1e-8
+    if world == 2 and not p2p:
+        e = dict(os.environ, JSSO_LIB=emu_api, EMU_DROP_GHOST='1', **env)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'emu', 'driver_check.py'), 'dist', '2', '12', '10', '1'],
+                           capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
+        assert r.returncode != 0 or 'EMU_RESULT' not in r.stdout or '"converged": false' in r.stdout
+
+
+@pytest.mark.parametrize('args,env', [(('grad', 4), {}), (('dist', 2, 6, 5, 1), {'JSSO_MG_FP16': '1', 'EMU_DIST_SETUP': '1'})])
 def test_memcheck_under_address_sanitizer(args, env):
     """The emulated driver built with -fsanitize=address: every "device" buffer is a heap block, so an out-of-bounds
     access of a kernel (or of the host driver) aborts with a report naming the .cuh line -- compute-sanitizer

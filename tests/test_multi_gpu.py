@@ -27,16 +27,17 @@ def test_partitioned_equals_single(world):
     assert res['u_err'] < 1e-8 and res['grad_err'] < 1e-7 and res['dprop_err'] < 1e-7
 
 
-@pytest.mark.parametrize('p2p', ['', 'p2p'])
+@pytest.mark.parametrize('p2p', ['', 'p2p', 'p2p setup'])
 @pytest.mark.parametrize('world,min_dist', [(2, 500), (2, 100000), (4, 500), (8, 500)])
 def test_distributed_multigrid_equals_single(world, min_dist, p2p):
     """Row-range distributed V-cycle PCG (jsso_mg_set_dist): same u and iteration count as the single-GPU
-    multigrid solve; min_dist 500 distributes two levels at 96^2, 100000 only the fine one."""
+    multigrid solve; min_dist 500 distributes two levels at 96^2, 100000 only the fine one; 'p2p': exchanges over
+    peer memory; 'setup': the numeric multigrid setup distributed as well (jsso_mg_set_dist_setup)."""
     if nat.lib().jsso_device_count() < world:
         pytest.skip(f'needs {world} GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
            '--master-addr', '127.0.0.1', '--master-port', str(29530 + world),
-           os.path.join(ROOT, 'scripts', 'dist_mg_check.py'), '96', str(min_dist), '1'] + ([p2p] if p2p else [])
+           os.path.join(ROOT, 'scripts', 'dist_mg_check.py'), '96', str(min_dist), '1'] + p2p.split()
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith('DIST_MG_CHECK')]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
