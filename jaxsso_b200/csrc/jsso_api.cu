@@ -196,7 +196,7 @@ struct jsso_handle {
     size_t max_recv = 0;
     MgdCtx* ctx = nullptr;              // device copy; null = NCCL send/recv path
     unsigned* push_counter = nullptr;
-    unsigned long long red_seq = 0;
+    unsigned long long* red_seq_dev = nullptr;   // sequence number of the mailbox all-reduces (device resident)
     std::vector<void*> ipc_opened;
     // distributed numeric setup (jsso_mg_set_dist_setup)
     struct SetupLevel {
@@ -464,7 +464,8 @@ void jsso_destroy(jsso_handle* h) {
   for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); }
   for (auto& dl : h->mgd.lv) if (dl.dev) cudaFree(dl.dev);
   for (void* p : h->mgd.ipc_opened) cudaIpcCloseMemHandle(p);
-  { void* pp[] = {h->mgd.mbox, h->mgd.arena, h->mgd.ctx, h->mgd.push_counter}; for (void* p : pp) if (p) cudaFree(p); }
+  { void* pp[] = {h->mgd.mbox, h->mgd.arena, h->mgd.ctx, h->mgd.push_counter, h->mgd.red_seq_dev}; for (void* p : pp) if (p) cudaFree(p); }
+  for (auto& sl : h->mgd.setup) { if (sl.p_list) cudaFree(sl.p_list); if (sl.ap_list) cudaFree(sl.ap_list); }
   if (h->mgd.send_buf) cudaFree(h->mgd.send_buf);
   if (h->mgd.recv_buf) cudaFree(h->mgd.recv_buf);
   if (h->mgd.comm && g_nccl.ok) g_nccl.CommDestroy(h->mgd.comm);
@@ -1226,6 +1227,8 @@ extern "C" int jsso_mg_p2p_export(jsso_handle* h, uint8_t out[128]) {
     CK(dalloc(&D.arena, (size_t)MGD_MAX_LEVELS * 2 * 6 * std::max<size_t>(D.max_recv, 1)));
     CK(dalloc(&D.push_counter, 1));
     CK(cudaMemset(D.push_counter, 0, sizeof(unsigned)));
+    CK(dalloc(&D.red_seq_dev, 1));
+    CK(cudaMemset(D.red_seq_dev, 0, sizeof(unsigned long long)));
   }
   cudaIpcMemHandle_t a, b;
   CK(cudaIpcGetMemHandle(&a, D.mbox));
@@ -1690,12 +1693,19 @@ static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st) {
   if (d.peers.empty()) return JSSO_OK;
   if (h->mgd.ctx) {   // peer-memory path: two kernels, no library call
     const unsigned long long seq = ++d.seq;
-    const int pb = std::max(1, std::min(32, cdiv(6LL * d.n_send, RED_BLOCK)));
-    mgd_push_kernel<<<pb, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.send_idx, v, h->mgd.push_counter, seq);
-    CKL("mgd_push_kernel");
-    const int ub = std::max(1, std::min(32, cdiv(6LL * d.n_recv, RED_BLOCK)));
-    mgd_wait_unpack_kernel<<<ub, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.recv_idx, v, seq);
-    CKL("mgd_wait_unpack_kernel");
+    const long long nmax = 6LL * std::max(d.n_send, d.n_recv);
+    if (nmax <= MGD_ONE_BLOCK_MAX) {
+      const int threads = (int)std::max(32LL, std::min(1024LL, ((nmax + 31) / 32) * 32));
+      mgd_exchange_kernel<<<1, threads, 0, st>>>(h->mgd.ctx, d.dev, l, d.send_idx, d.recv_idx, v, h->mgd.push_counter, seq);
+      CKL("mgd_exchange_kernel");
+    } else {
+      const int pb = std::max(1, std::min(32, cdiv(6LL * d.n_send, RED_BLOCK)));
+      mgd_push_kernel<<<pb, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.send_idx, v, h->mgd.push_counter, seq);
+      CKL("mgd_push_kernel");
+      const int ub = std::max(1, std::min(32, cdiv(6LL * d.n_recv, RED_BLOCK)));
+      mgd_wait_unpack_kernel<<<ub, RED_BLOCK, 0, st>>>(h->mgd.ctx, d.dev, l, d.recv_idx, v, seq);
+      CKL("mgd_wait_unpack_kernel");
+    }
     ++h->mgd.n_exchange;
     return JSSO_OK;
   }
@@ -1742,8 +1752,7 @@ static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st) {
 static int mgd_reduce(jsso_handle* h, int slot, int count, cudaStream_t st) {
   if (h->mgd.ctx) {
     if (count > 2) return fail(h, JSSO_ERR_ARG, "peer-memory all-reduce: at most 2 scalars");
-    const unsigned long long seq = ++h->mgd.red_seq;
-    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + slot, h->mg_scal + slot, count, seq);
+    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + slot, h->mg_scal + slot, count, h->mgd.red_seq_dev);
     CKL("mgd_allreduce_kernel");
   } else {
     CKN(g_nccl.AllReduce(h->mg_scal + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum, h->mgd.comm, st));
@@ -1829,22 +1838,26 @@ static int mg_vcycle_dist(jsso_handle* h, int l, double* b, double* x, int deg, 
 // the default): 4 SpMV-shaped kernels of the V-cycle with the smoother folded into their epilogues
 // (mg_vcycle_fused), the direction update, q = A p with p.q, and the x / r update with r.r: 7 launches + the coarse
 // levels, against 18 launches and 4 host synchronisations of the first (host-driven) version.
+// Where a fused dot product goes, and how it is summed over the ranks:
+//   one GPU                    -> straight into the slot;
+//   peer-memory distributed    -> the kernel's last block all-reduces through the mailboxes and stores the SUM into the
+//                                 slot (mgs_store_dot; no extra launch);
+//   NCCL distributed           -> the partial goes to MGS_LOC + slot, mgs_reduce sums it out of place into the slot.
 static inline double* mgs_dot_target(jsso_handle* h, int slot) {
-  return h->mg_scal + ((h->mgd.n_rank > 1) ? MGS_LOC + slot : slot);
+  return h->mg_scal + ((h->mgd.n_rank > 1 && !h->mgd.ctx) ? MGS_LOC + slot : slot);
 }
-// several GPUs: slot[0..count) = sum over the ranks of the partials at MGS_LOC + slot (out of place)
+static inline const MgdCtx* mgs_ctx(jsso_handle* h) { return h->mgd.n_rank > 1 ? h->mgd.ctx : nullptr; }
 static int mgs_reduce(jsso_handle* h, int slot, int count, cudaStream_t st) {
-  if (h->mgd.n_rank <= 1) return JSSO_OK;
-  if (h->mgd.ctx) {
-    if (count > 2) return fail(h, JSSO_ERR_ARG, "peer-memory all-reduce: at most 2 scalars");
-    const unsigned long long seq = ++h->mgd.red_seq;
-    mgd_allreduce_kernel<<<1, 32, 0, st>>>(h->mgd.ctx, h->mg_scal + MGS_LOC + slot, h->mg_scal + slot, count, seq);
-    CKL("mgd_allreduce_kernel");
-  } else {
-    CKN(g_nccl.AllReduce(h->mg_scal + MGS_LOC + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum,
-                         h->mgd.comm, st));
-  }
-  ++h->mgd.n_allreduce;
+  if (h->mgd.n_rank <= 1 || h->mgd.ctx) return JSSO_OK;
+  CKN(g_nccl.AllReduce(h->mg_scal + MGS_LOC + slot, h->mg_scal + slot, (size_t)count, ncclDouble, ncclSum,
+                       h->mgd.comm, st));
+  h->mgd.n_allreduce += count;
+  return JSSO_OK;
+}
+// a rank whose row range is empty still has to take part in the reduction of a fused dot product
+static int mgs_zero_dot(jsso_handle* h, int slot, cudaStream_t st) {
+  mgs_zero_dot_kernel<<<1, 1, 0, st>>>(h->mg_scal, mgs_dot_target(h, slot), mgs_ctx(h), h->mgd.red_seq_dev);
+  CKL("mgs_zero_dot_kernel");
   return JSSO_OK;
 }
 
@@ -1853,8 +1866,13 @@ static int mgs_reduce(jsso_handle* h, int slot, int count, cudaStream_t st) {
 template <int DOT>
 static int mg_lin_level0(jsso_handle* h, int s, int n, const double* x, double* y, const double* bvec,
                          const double* xrow, double ca, double cb, double cc, double* dot_out, cudaStream_t st) {
+  const MgdCtx* rc_ = (DOT != 0) ? mgs_ctx(h) : nullptr;
+  unsigned long long* rs_ = h->mgd.red_seq_dev;
   if (n <= 0) {
-    if (DOT != 0) CK(cudaMemsetAsync(dot_out, 0, sizeof(double), st));
+    if (DOT != 0) {
+      mgs_zero_dot_kernel<<<1, 1, 0, st>>>(h->mg_scal, dot_out, rc_, rs_);
+      CKL("mgs_zero_dot_kernel");
+    }
     return JSSO_OK;
   }
   const MgMat A = mg_matrix(h, 0);
@@ -1863,26 +1881,26 @@ static int mg_lin_level0(jsso_handle* h, int s, int n, const double* x, double* 
 #if JSSO_MG_RP
   if (h->mg_fp32 && A.v16) {
     bsr_spmv_rp_kernel<__half, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc,
-                                                                        stop, h->partials, h->counters + 2, dot_out);
+                                                                        stop, h->partials, h->counters + 2, dot_out, rc_, rs_);
     CKL("bsr_spmv_rp_kernel<half>");
     return JSSO_OK;
   }
   if (h->mg_fp32 && A.v32) {
     bsr_spmv_rp_kernel<float, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v32, x, y, bvec, xrow, ca, cb, cc,
-                                                                       stop, h->partials, h->counters + 2, dot_out);
+                                                                       stop, h->partials, h->counters + 2, dot_out, rc_, rs_);
     CKL("bsr_spmv_rp_kernel<float>");
     return JSSO_OK;
   }
 #endif
   if (h->mg_fp32 && A.v16)
     bsr_spmv_lin_kernel<__half, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc, stop,
-                                                             h->partials, h->counters + 2, dot_out);
+                                                             h->partials, h->counters + 2, dot_out, rc_, rs_);
   else if (h->mg_fp32 && A.v32)
     bsr_spmv_lin_kernel<float, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v32, x, y, bvec, xrow, ca, cb, cc, stop,
-                                                            h->partials, h->counters + 2, dot_out);
+                                                            h->partials, h->counters + 2, dot_out, rc_, rs_);
   else
     bsr_spmv_lin_kernel<double, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v, x, y, bvec, xrow, ca, cb, cc, stop,
-                                                             h->partials, h->counters + 2, dot_out);
+                                                             h->partials, h->counters + 2, dot_out, rc_, rs_);
   CKL("bsr_spmv_lin_kernel");
   return JSSO_OK;
 }
@@ -1905,7 +1923,7 @@ static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaSt
     rc = dist ? mg_vcycle_dist(h, 0, b, z, deg, st) : mg_vcycle_graphed(h, 0, b, z, deg, st);
     if (rc) return rc;
     mg_dot_kernel<<<std::max(1, std::min(h->red_blocks, cdiv(6LL * n, 256))), 256, 0, st>>>(
-        6LL * n, b + off, z + off, h->partials, h->counters + 2, mgs_dot_target(h, MGS_RZ));
+        6LL * n, b + off, z + off, h->partials, h->counters + 2, mgs_dot_target(h, MGS_RZ), mgs_ctx(h), h->mgd.red_seq_dev);
     CKL("mg_dot_kernel");
     return JSSO_OK;
   }
@@ -1969,7 +1987,8 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
   }
   CK(cudaMemsetAsync(scal, 0, MGS_COUNT * sizeof(double), st));
   auto dot = [&](const double* a_, const double* b_, int slot) -> int {
-    mg_dot_kernel<<<vb, 256, 0, st>>>(n, a_, b_, h->partials, h->counters + 2, mgs_dot_target(h, slot));
+    mg_dot_kernel<<<vb, 256, 0, st>>>(n, a_, b_, h->partials, h->counters + 2, mgs_dot_target(h, slot), mgs_ctx(h),
+                                      h->mgd.red_seq_dev);
     CKL("mg_dot_kernel");
     return JSSO_OK;
   };
@@ -1996,14 +2015,15 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
       if (dist) { if ((rc = mgd_exchange(h, 0, p, st))) return rc; }
       if (n_row > 0) {
         bsr_spmv_dot_kernel<<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, A.rp + s, A.ci, A.v, p, p + off, q + off, scal,
-                                                                     h->partials, h->counters + 2, mgs_dot_target(h, MGS_PQ));
+                                                                     h->partials, h->counters + 2, mgs_dot_target(h, MGS_PQ),
+                                                                     mgs_ctx(h), h->mgd.red_seq_dev);
         CKL("bsr_spmv_dot_kernel");
       } else {
-        CK(cudaMemsetAsync(mgs_dot_target(h, MGS_PQ), 0, sizeof(double), st));
+        if ((rc = mgs_zero_dot(h, MGS_PQ, st))) return rc;
       }
       if ((rc = mgs_reduce(h, MGS_PQ, 1, st))) return rc;
       mg_pcg_update_kernel<<<vb, 256, 0, st>>>(n, p + off, q + off, x + off, r + off, scal, h->partials, h->counters + 2,
-                                              mgs_dot_target(h, MGS_RR));
+                                              mgs_dot_target(h, MGS_RR), mgs_ctx(h), h->mgd.red_seq_dev);
       CKL("mg_pcg_update_kernel");
       if ((rc = mgs_reduce(h, MGS_RR, 1, st))) return rc;
     }

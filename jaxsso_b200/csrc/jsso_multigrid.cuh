@@ -333,12 +333,12 @@ __global__ void mg_dense_matvec_kernel(int n, const double* __restrict__ M, cons
 // out[0] = a.b (deterministic two-stage); n entries
 __global__ void __launch_bounds__(256)
 mg_dot_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b, double* partials,
-              unsigned* counter, double* out) {
+              unsigned* counter, double* out, const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr) {
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc = fma(a[i], b[i], acc);
   double total;
-  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) *out = total;
+  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, out, rctx, rseq);
 }
 // y = a*x + b*y
 __global__ void mg_axpby_kernel(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
@@ -371,7 +371,8 @@ __global__ void mg_pcg_dir_kernel(long long n, const double* __restrict__ z, dou
 __global__ void __launch_bounds__(256)
 mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __restrict__ q,
                      double* __restrict__ x, double* __restrict__ r, double* __restrict__ scal,
-                     double* partials, unsigned* counter, double* rr_out) {
+                     double* partials, unsigned* counter, double* rr_out, const MgdCtx* rctx = nullptr,
+                     unsigned long long* rseq = nullptr) {
   if (mgs_stopped(scal)) return;
   const double rz = scal[MGS_RZ], pq = scal[MGS_PQ];
   const double alpha = rz / pq;
@@ -391,9 +392,10 @@ mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __
   }
   double total;
   if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
-    *rr_out = (pq > 0.0 && rz > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL);
     scal[MGS_RZ_OLD] = rz;
     scal[MGS_ITER] += 1.0;
+    // (after the bookkeeping: in the distributed solve the store waits for the other ranks)
+    mgs_store_dot((pq > 0.0 && rz > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL), rr_out, rctx, rseq);
   }
 }
 // scal[MGS_TOL] = rtol^2 |b|^2 and the iteration counter (start of a solve; one thread)

@@ -153,6 +153,12 @@ __device__ inline bool mgs_stopped(const double* stop) {
   return stop && !(stop[MGS_RR] > stop[MGS_TOL]);
 }
 
+struct MgdCtx;
+// Store a finished dot product: on one GPU straight into *out; in the peer-memory distributed solve (ctx != null) publish
+// this rank's partial to every rank's mailbox, wait for all ranks and store the sum (rank order: bitwise identical
+// everywhere).  Called by ONE thread of the block that finalised the sum; defined below the mailbox structs.
+__device__ inline void mgs_store_dot(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr);
+
 __device__ inline double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -589,7 +595,8 @@ bsr_spmv_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __
 __global__ void __launch_bounds__(RED_BLOCK, 4)
 bsr_spmv_dot_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                     const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ xrow,
-                    double* __restrict__ y, const double* stop, double* partials, unsigned* counter, double* dot_out) {
+                    double* __restrict__ y, const double* stop, double* partials, unsigned* counter, double* dot_out,
+                    const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr) {
   if (mgs_stopped(stop)) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -603,7 +610,7 @@ bsr_spmv_dot_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
     }
   });
   double total;
-  if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+  if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
 }
 
 // MODE 0: y = A x;  2: y = b - A x;  3: y += A x;  5 (short-row kernel only): y = s b + A x
@@ -649,7 +656,8 @@ __global__ void __launch_bounds__(RED_BLOCK, (JSSO_SPMV_PAIRED ? RowPair<VT>::mi
 bsr_spmv_lin_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                     const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                     const double* __restrict__ bvec, const double* __restrict__ xrow, double ca, double cb, double cc,
-                    const double* stop, double* partials, unsigned* counter, double* dot_out) {
+                    const double* stop, double* partials, unsigned* counter, double* dot_out,
+                    const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr) {
   if (mgs_stopped(stop)) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -673,7 +681,7 @@ bsr_spmv_lin_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
   else dot = bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
   if (DOT != 0) {
     double total;
-    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
   }
 }
 
@@ -725,7 +733,8 @@ __global__ void __launch_bounds__(RED_BLOCK, 3)
 bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                    const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                    const double* __restrict__ bvec, const double* __restrict__ xrow, double ca, double cb, double cc,
-                   const double* stop, double* partials, unsigned* counter, double* dot_out) {
+                   const double* stop, double* partials, unsigned* counter, double* dot_out,
+                   const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr) {
   if (mgs_stopped(stop)) return;
   double dot = 0.0;
   const long long n_item = 3LL * n_row;
@@ -766,7 +775,7 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   }
   if (DOT != 0) {
     double total;
-    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) *dot_out = total;
+    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
   }
 }
 
@@ -902,23 +911,79 @@ mgd_wait_unpack_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const i
     v[6 * (size_t)recv_idx[t / 6] + t % 6] = ld_relaxed_sys_f64(src + t);
 }
 
-// dst[0..count) <- sum over the ranks of src[0..count) (rank order: bitwise identical everywhere); one block,
-// count <= 2.  dst may be src (in place) or another slot (out of place: idempotent when repeated).
-__global__ void mgd_allreduce_kernel(const MgdCtx* c, const double* src, double* dst, int count, unsigned long long seq) {
-  const int par = (int)(seq & 1ull);
-  if (threadIdx.x == 0) {
-    for (int r = 0; r < c->n_rank; ++r)
-      for (int k = 0; k < count; ++k) st_relaxed_sys_f64(&c->mbox[r]->red_val[par][c->rank][k], src[k]);
-    __threadfence_system();
-    for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->red_tag[par][c->rank], seq);
-    const MgdMailbox* m = c->mbox[c->rank];
-    double acc[2] = {0.0, 0.0};
-    for (int r = 0; r < c->n_rank; ++r) {
-      while (ld_acquire_sys(&m->red_tag[par][r]) < seq) { }
-      for (int k = 0; k < count; ++k) acc[k] += ld_relaxed_sys_f64(&m->red_val[par][r][k]);
-    }
-    for (int k = 0; k < count; ++k) dst[k] = acc[k];
+// A small exchange as ONE kernel of ONE block: push this rank's entries into the peers' arenas and raise the flags, then
+// wait for the peers' flags and scatter the own arena into the ghost positions.  Every rank pushes before it waits,
+// so the kernels of the ranks cannot wait for each other in a cycle; a single block keeps that true without relying
+// on the co-residency of several blocks (a block that waits never holds back a block that still has to push).
+// Halos of a strip partition are a few thousand nodes: one block of 1024 threads moves them in a few microseconds
+// and saves a launch per exchange; larger exchanges (the all-gather level) use the two-kernel form above.
+constexpr int MGD_ONE_BLOCK_MAX = 24576;   // doubles
+__global__ void __launch_bounds__(1024)
+mgd_exchange_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const int32_t* __restrict__ send_idx,
+                    const int32_t* __restrict__ recv_idx, double* __restrict__ v, unsigned* counter, unsigned long long seq) {
+  __shared__ bool last;
+  const long long slot = (long long)level * c->arena_level_stride + (long long)(seq & 1ull) * c->arena_slot_stride;
+  for (int pi = 0; pi < L->n_peer; ++pi) {
+    double* dst = c->arena[L->peer_rank[pi]] + slot + 6 * (long long)L->remote_off[pi];
+    const int32_t* idx = send_idx + L->send_off[pi];
+    const int n = 6 * L->send_cnt[pi];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+      dst[t] = v[6 * (size_t)idx[t / 6] + t % 6];
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < L->n_peer) {
+    __threadfence();
+    st_release_sys(&c->mbox[L->peer_rank[threadIdx.x]]->halo[level][c->rank], seq);
+  }
+  if ((int)threadIdx.x < L->n_peer) {
+    const MgdMailbox* m = c->mbox[c->rank];
+    while (ld_acquire_sys(&m->halo[level][L->peer_rank[threadIdx.x]]) < seq) { }
+  }
+  __syncthreads();
+  const double* src = c->arena[c->rank] + slot;
+  const int n = 6 * L->n_recv;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    v[6 * (size_t)recv_idx[t / 6] + t % 6] = ld_relaxed_sys_f64(src + t);
+}
+
+// Mailbox all-reduce of `count` <= 2 scalars by ONE thread.  The sequence number lives on the device (*seq_ctr) and
+// advances only when a reduction really runs, so that kernels skipped after convergence (mgs_stopped) keep the
+// parity double buffer of the mailbox consistent on every rank.
+__device__ inline void mgd_allreduce_thread(const MgdCtx* c, const double* src, double* dst, int count,
+                                            unsigned long long* seq_ctr) {
+  const unsigned long long seq = *seq_ctr + 1ull;
+  *seq_ctr = seq;
+  const int par = (int)(seq & 1ull);
+  for (int r = 0; r < c->n_rank; ++r)
+    for (int k = 0; k < count; ++k) st_relaxed_sys_f64(&c->mbox[r]->red_val[par][c->rank][k], src[k]);
+  __threadfence_system();
+  for (int r = 0; r < c->n_rank; ++r) st_release_sys(&c->mbox[r]->red_tag[par][c->rank], seq);
+  const MgdMailbox* m = c->mbox[c->rank];
+  double acc[2] = {0.0, 0.0};
+  for (int r = 0; r < c->n_rank; ++r) {
+    while (ld_acquire_sys(&m->red_tag[par][r]) < seq) { }
+    for (int k = 0; k < count; ++k) acc[k] += ld_relaxed_sys_f64(&m->red_val[par][r][k]);
+  }
+  for (int k = 0; k < count; ++k) dst[k] = acc[k];
+}
+// dst[0..count) <- sum over the ranks of src[0..count) (rank order: bitwise identical everywhere); one block,
+// count <= 2.  dst may be src (in place) or another slot.
+__global__ void mgd_allreduce_kernel(const MgdCtx* c, const double* src, double* dst, int count, unsigned long long* seq_ctr) {
+  if (threadIdx.x == 0) mgd_allreduce_thread(c, src, dst, count, seq_ctr);
+}
+__device__ inline void mgs_store_dot(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr) {
+  if (!ctx) { *out = total; return; }
+  mgd_allreduce_thread(ctx, &total, out, 1, seq_ctr);
+}
+// a rank with an empty row range still takes part in the reduction of a fused dot product
+__global__ void mgs_zero_dot_kernel(const double* stop, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr) {
+  if (mgs_stopped(stop)) return;
+  mgs_store_dot(0.0, out, ctx, seq_ctr);
 }
 
 // ---- persistent CG (single GPU) ------------------------------------------------------
