@@ -143,6 +143,10 @@ struct jsso_handle {
             *cl_ap = nullptr;
     int32_t *pt_rowptr = nullptr, *pt_col = nullptr, *pt_src = nullptr, *mem_ptr = nullptr, *mem = nullptr;
     double *P = nullptr, *Pt = nullptr, *AP = nullptr, *Ac = nullptr, *Xc = nullptr, *Dinv = nullptr;
+    // every level is kept in block-Jacobi-scaled form (unit diagonal blocks): factors of THIS level's coarse matrix,
+    // W_c = L_c^-1 and L_c (row-major 6x6 per coarse node), and the row index of every coarse block
+    double *Wc = nullptr, *Lc = nullptr;
+    int32_t* c_row = nullptr;
     float *P32 = nullptr, *Pt32 = nullptr, *Ac32 = nullptr;   // single-precision copies used by the V-cycle
     double *b = nullptr, *x = nullptr, *r = nullptr, *d = nullptr;   // level vectors (b, x unused at level 0)
     double lam = 0.0;
@@ -453,7 +457,7 @@ void jsso_destroy(jsso_handle* h) {
   for (auto& m : h->mg) {
     void* lv[] = {m.agg, m.p_row, m.p_rowptr, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.apl_ptr, m.apl_a, m.apl_p,
                   m.c_rowptr, m.c_col, m.c_diag, m.cl_ptr, m.cl_p, m.cl_ap, m.pt_rowptr, m.pt_col, m.pt_src, m.mem_ptr,
-                  m.mem, m.P, m.Pt, m.AP, m.Ac, m.Xc, m.Dinv, m.P32, m.Pt32, m.Ac32, m.b, m.x, m.r, m.d};
+                  m.mem, m.P, m.Pt, m.AP, m.Ac, m.Xc, m.Dinv, m.P32, m.Pt32, m.Ac32, m.b, m.x, m.r, m.d, m.Wc, m.Lc, m.c_row};
     for (void* p : lv) if (p) cudaFree(p);
   }
   {
@@ -1110,7 +1114,14 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     CK(dalloc(&m.Xc, 3 * (size_t)d.n_c));
     CK(dalloc(&m.P32, 36 * (size_t)d.nnz_p)); CK(dalloc(&m.Pt32, 36 * (size_t)d.nnz_p));
     CK(dalloc(&m.Ac32, 36 * (size_t)d.nnz_c));
-    if (l > 0) { CK(dalloc(&m.Dinv, 36 * (size_t)d.n_f)); CK(dalloc(&m.b, 6 * (size_t)d.n_f)); CK(dalloc(&m.x, 6 * (size_t)d.n_f)); }
+    if (l > 0) { CK(dalloc(&m.b, 6 * (size_t)d.n_f)); CK(dalloc(&m.x, 6 * (size_t)d.n_f)); }
+    CK(dalloc(&m.Wc, 36 * (size_t)d.n_c)); CK(dalloc(&m.Lc, 36 * (size_t)d.n_c));
+    {
+      std::vector<int32_t> crow(d.nnz_c);
+      for (int i = 0; i < d.n_c; ++i)
+        for (int s = d.c_rowptr[i]; s < d.c_rowptr[i + 1]; ++s) crow[s] = i;
+      CK(upload(&m.c_row, crow));
+    }
     CK(dalloc(&m.r, 6 * (size_t)d.n_f)); CK(dalloc(&m.d, 6 * (size_t)d.n_f));
     h->mg.push_back(m);
     n_prev = d.n_c;
@@ -1436,6 +1447,29 @@ static int mg_read_scalars(jsso_handle* h, cudaStream_t st) {
 static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n);
 static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st);
 static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st);
+static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st);
+static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st);
+
+// The coarse matrix of coarsening step l in block-Jacobi-scaled form: factor its diagonal blocks (W_c = L_c^-1),
+// A_c <- W_c A_c W_c^T in place, and the prolongator into the scaled coarse coordinates, P <- P W_c^T (the blocks
+// of `p_list`, or all n_p of them).  The scaled matrix has unit diagonal blocks, so the smoother of the next level
+// needs no D^-1 and its V-cycle products take the fused form of the fine level (mg_vcycle_fused).
+static int mg_scale_coarse(jsso_handle* h, int l, const int32_t* p_list, int n_p, cudaStream_t st) {
+  jsso_handle::MgLevel& m = h->mg[l];
+  if (m.n_c > 0) {
+    diag_factor_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.c_diag, m.Ac, m.Wc, m.Lc, h->flags, 1);
+    CKL("diag_factor_kernel");
+  }
+  if (m.nnz_c > 0) {
+    scale_blocks_kernel<<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.c_row, m.c_col, m.Wc, m.Ac);
+    CKL("scale_blocks_kernel");
+  }
+  if (n_p > 0) {
+    mg_scale_cols_kernel<<<cdiv(n_p, 128), 128, 0, st>>>(n_p, m.p_col, m.Wc, m.P, p_list);
+    CKL("mg_scale_cols_kernel");
+  }
+  return JSSO_OK;
+}
 
 // numeric hierarchy for the current (block-Jacobi-scaled) matrix
 static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
@@ -1449,10 +1483,9 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     jsso_handle::MgLevel& m = h->mg[l];
     const MgMat A = mg_matrix(h, l);
     const int n = m.n_f;
-    if (l > 0) {
-      mg_diag_inverse_kernel<<<cdiv(n, 128), 128, 0, st>>>(n, h->mg[l - 1].c_diag, A.v, m.Dinv);
-      CKL("mg_diag_inverse_kernel");
-    }
+    // every level matrix is block-Jacobi scaled (unit diagonal blocks): no D^-1 anywhere.  Lf: the Cholesky factors of
+    // this level's unscaled diagonal blocks (the rigid-body modes enter the prolongator as L^T T)
+    const double* Lf = (l == 0) ? h->Lfac : h->mg[l - 1].Lc;
     // lambda_max(D^-1 A): power iteration from a pseudo-random vector; an underestimate would make the Chebyshev
     // smoother amplify the top modes and the V-cycle indefinite.  The estimate grows monotonically: 0.93-0.95 of the
     // true value after 10 steps, 0.98 after 30 (CPU study on three levels of a 64^2 plate), so 10 steps x 1.2 is as
@@ -1513,16 +1546,12 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       const int me = h->mgd.rank;
       if (SL.n_p > 0) {
         mg_smooth_prolongator_kernel<<<cdiv(SL.n_p, 128), 128, 0, st>>>(
-            SL.n_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, m.Dinv, l == 0 ? h->Lfac : nullptr,
+            SL.n_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, nullptr, Lf,
             l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P, SL.p_list);
         CKL("mg_smooth_prolongator_kernel");
       }
       // restriction rows of the own coarse nodes: P^T blocks [pt0, pt1); prolongation rows: P blocks [pr0, pr1)
       const int pt[2] = {SL.pt_lo, SL.pt_hi}, pr[2] = {SL.p_lo, SL.p_hi};
-      if (pt[1] > pt[0]) {
-        mg_transpose_blocks_kernel<<<cdiv(36LL * (pt[1] - pt[0]), 256), 256, 0, st>>>(pt[1] - pt[0], m.pt_src, m.P, m.Pt, pt[0]);
-        CKL("mg_transpose_blocks_kernel");
-      }
       if (SL.n_ap > 0) {
         mg_block_product_kernel<0><<<cdiv(SL.n_ap, 128), 128, 0, st>>>(SL.n_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP,
                                                                        SL.ap_list, 0);
@@ -1542,6 +1571,12 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
         if (theirs) CKN(g_nccl.Recv(m.Ac + 36 * (size_t)SL.ac_bounds[r], theirs, ncclDouble, r, h->mgd.comm, st));
       }
       CKN(g_nccl.GroupEnd());
+      // the coarse level in scaled form: factor its diagonal blocks, A_c <- W_c A_c W_c^T, P <- P W_c^T (then P^T)
+      if ((rc = mg_scale_coarse(h, l, SL.p_list, SL.n_p, st))) return rc;
+      if (pt[1] > pt[0]) {
+        mg_transpose_blocks_kernel<<<cdiv(36LL * (pt[1] - pt[0]), 256), 256, 0, st>>>(pt[1] - pt[0], m.pt_src, m.P, m.Pt, pt[0]);
+        CKL("mg_transpose_blocks_kernel");
+      }
       if (h->mg_fp32) {
         if ((rc = mg_to_float(h, 36LL * (pr[1] - pr[0]), m.P + 36 * (size_t)pr[0], m.P32 + 36 * (size_t)pr[0], st))) return rc;
         if ((rc = mg_to_float(h, 36LL * (pt[1] - pt[0]), m.Pt + 36 * (size_t)pt[0], m.Pt32 + 36 * (size_t)pt[0], st))) return rc;
@@ -1551,15 +1586,16 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       continue;
     }
     mg_smooth_prolongator_kernel<<<cdiv(m.nnz_p, 128), 128, 0, st>>>(
-        m.nnz_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, m.Dinv, l == 0 ? h->Lfac : nullptr,
+        m.nnz_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, nullptr, Lf,
         l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P);
     CKL("mg_smooth_prolongator_kernel");
-    mg_transpose_blocks_kernel<<<cdiv(36LL * m.nnz_p, 256), 256, 0, st>>>(m.nnz_p, m.pt_src, m.P, m.Pt);
-    CKL("mg_transpose_blocks_kernel");
     mg_block_product_kernel<0><<<cdiv(m.nnz_ap, 128), 128, 0, st>>>(m.nnz_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP);
     CKL("mg_block_product_kernel<0>");
     mg_block_product_kernel<1><<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
     CKL("mg_block_product_kernel<1>");
+    if ((rc = mg_scale_coarse(h, l, nullptr, m.nnz_p, st))) return rc;
+    mg_transpose_blocks_kernel<<<cdiv(36LL * m.nnz_p, 256), 256, 0, st>>>(m.nnz_p, m.pt_src, m.P, m.Pt);
+    CKL("mg_transpose_blocks_kernel");
     if (h->mg_fp32) {
       if ((rc = mg_to_float(h, 36LL * m.nnz_p, m.P, m.P32, st))) return rc;
       if ((rc = mg_to_float(h, 36LL * m.nnz_p, m.Pt, m.Pt32, st))) return rc;
@@ -1861,11 +1897,11 @@ static int mgs_zero_dot(jsso_handle* h, int slot, cudaStream_t st) {
   return JSSO_OK;
 }
 
-// y = ca * bvec + cb * xrow + cc * A x on the rows [s, s + n) of the level-0 V-cycle matrix (binary16 / FP32 / FP64
-// storage, whichever the handle runs the V-cycle with)
+// y = ca * bvec + cb * xrow + cc * A_l x on the rows [s, s + n) of the level-l V-cycle matrix (fine level: binary16 /
+// FP32 / FP64 storage, whichever the handle runs the V-cycle with; coarse levels: FP32)
 template <int DOT>
-static int mg_lin_level0(jsso_handle* h, int s, int n, const double* x, double* y, const double* bvec,
-                         const double* xrow, double ca, double cb, double cc, double* dot_out, cudaStream_t st) {
+static int mg_lin_level(jsso_handle* h, int l, int s, int n, const double* x, double* y, const double* bvec,
+                        const double* xrow, double ca, double cb, double cc, double* dot_out, cudaStream_t st) {
   const MgdCtx* rc_ = (DOT != 0) ? mgs_ctx(h) : nullptr;
   unsigned long long* rs_ = h->mgd.red_seq_dev;
   if (n <= 0) {
@@ -1875,82 +1911,77 @@ static int mg_lin_level0(jsso_handle* h, int s, int n, const double* x, double* 
     }
     return JSSO_OK;
   }
-  const MgMat A = mg_matrix(h, 0);
+  const MgMat A = mg_matrix(h, l);
   const int g = mg_blocks(h, n);
   const double* stop = h->mg_scal;
-#if JSSO_MG_RP
-  if (h->mg_fp32 && A.v16) {
+  // thread per (row, row pair) for short rows on levels large enough to fill the GPU, else a warp per row
+  const bool rp = JSSO_MG_RP && ((double)A.nnz <= 12.0 * std::max(A.n, 1)) && (l == 0 || n >= 4096);
+  if (h->mg_fp32 && A.v16 && rp) {
     bsr_spmv_rp_kernel<__half, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc,
                                                                         stop, h->partials, h->counters + 2, dot_out, rc_, rs_);
     CKL("bsr_spmv_rp_kernel<half>");
-    return JSSO_OK;
-  }
-  if (h->mg_fp32 && A.v32) {
+  } else if (h->mg_fp32 && A.v32 && rp) {
     bsr_spmv_rp_kernel<float, DOT><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v32, x, y, bvec, xrow, ca, cb, cc,
                                                                        stop, h->partials, h->counters + 2, dot_out, rc_, rs_);
     CKL("bsr_spmv_rp_kernel<float>");
-    return JSSO_OK;
-  }
-#endif
-  if (h->mg_fp32 && A.v16)
+  } else if (h->mg_fp32 && A.v16) {
     bsr_spmv_lin_kernel<__half, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v16, x, y, bvec, xrow, ca, cb, cc, stop,
                                                              h->partials, h->counters + 2, dot_out, rc_, rs_);
-  else if (h->mg_fp32 && A.v32)
+    CKL("bsr_spmv_lin_kernel<half>");
+  } else if (h->mg_fp32 && A.v32) {
     bsr_spmv_lin_kernel<float, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v32, x, y, bvec, xrow, ca, cb, cc, stop,
                                                             h->partials, h->counters + 2, dot_out, rc_, rs_);
-  else
+    CKL("bsr_spmv_lin_kernel<float>");
+  } else {
     bsr_spmv_lin_kernel<double, DOT><<<g, RED_BLOCK, 0, st>>>(n, A.rp + s, A.ci, A.v, x, y, bvec, xrow, ca, cb, cc, stop,
                                                              h->partials, h->counters + 2, dot_out, rc_, rs_);
-  CKL("bsr_spmv_lin_kernel");
+    CKL("bsr_spmv_lin_kernel<double>");
+  }
   return JSSO_OK;
 }
 
-// z = M^-1 b (one V-cycle from the fine level) on this rank's rows and r.z = b.z into slot MGS_RZ (this rank's
-// partial on several GPUs).  Chebyshev-1 on the fine level (whose scaled matrix has unit diagonal blocks, so
-// D^-1 = I) is folded into the products:
+// x = M_l^-1 b: one V-cycle from level l with Chebyshev-1 smoothing folded into the products.  Every level matrix is
+// block-Jacobi scaled (unit diagonal blocks, D^-1 = I), so with theta = 5 lam / 8:
 //   pre-smoother from a zero guess x0 = b / theta   =>  r0 = b - A x0 = b - (1/theta) A b      (one SpMV of b)
 //   x1 = x0 + P x_c                                  =>  x1 = (1/theta) b + P x_c               (prolongation epilogue)
-//   post-smoother z = x1 + (1/theta)(b - A x1), r.z  =>  one SpMV of x1 with the dot in its epilogue
-// i.e. 4 launches and ~9 vector passes instead of 8 launches and ~20.  Other degrees take the generic V-cycle.
-static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaStream_t st) {
-  const bool dist = h->mgd.n_rank > 1;
+//   post-smoother x = x1 + (1/theta)(b - A x1)       =>  one SpMV of x1 (+ b.x in its epilogue at the fine level)
+// i.e. 4 launches and ~9 vector passes per level instead of 8 launches and ~20.  On several GPUs the levels
+// l < n_dist work on this rank's rows, with a halo exchange before every product that gathers a vector other ranks
+// have just written; b / x are full-length level vectors.
+static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bool want_dot, cudaStream_t st) {
   const int nl = (int)h->mg.size();
   int rc;
-  int s = 0, n = h->sym.n_row, s1 = 0, n1 = nl ? h->mg[0].n_c : 0;
-  if (dist) { mgd_range(h, 0, s, n); mgd_range(h, 1, s1, n1); }
-  const size_t off = 6 * (size_t)s, off1 = 6 * (size_t)s1;
-  if (deg != 1 || nl == 0) {
-    rc = dist ? mg_vcycle_dist(h, 0, b, z, deg, st) : mg_vcycle_graphed(h, 0, b, z, deg, st);
-    if (rc) return rc;
-    mg_dot_kernel<<<std::max(1, std::min(h->red_blocks, cdiv(6LL * n, 256))), 256, 0, st>>>(
-        6LL * n, b + off, z + off, h->partials, h->counters + 2, mgs_dot_target(h, MGS_RZ), mgs_ctx(h), h->mgd.red_seq_dev);
-    CKL("mg_dot_kernel");
+  if (l == nl) {
+    const int nc = 6 * mg_matrix(h, nl).n;
+    mg_dense_matvec_kernel<<<cdiv(32LL * nc, 256), 256, 0, st>>>(nc, h->mg_dense, b, x);
+    CKL("mg_dense_matvec_kernel");
     return JSSO_OK;
   }
-  jsso_handle::MgLevel& m = h->mg[0];
+  jsso_handle::MgLevel& m = h->mg[l];
+  const bool dist = h->mgd.n_rank > 1 && l < h->mgd.n_dist;
+  int s = 0, n = m.n_f, s1 = 0, n1 = m.n_c;
+  if (dist) { mgd_range(h, l, s, n); mgd_range(h, l + 1, s1, n1); }
+  const size_t off = 6 * (size_t)s, off1 = 6 * (size_t)s1;
   const double it = 1.0 / (0.625 * m.lam);   // 1 / theta, theta = (lam + lam / 4) / 2
-  double* bc = (1 < nl) ? h->mg[1].b : h->mg_cb;
-  double* xc = (1 < nl) ? h->mg[1].x : h->mg_cx;
-  if (dist) { if ((rc = mgd_exchange(h, 0, b, st))) return rc; }
-  if ((rc = mg_lin_level0<0>(h, s, n, b, m.r + off, b + off, nullptr, 1.0, 0.0, -it, nullptr, st))) return rc;
-  if (dist) { if ((rc = mgd_exchange(h, 0, m.r, st))) return rc; }
-  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st, false, nullptr, (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;
-  if (dist) {
-    if (1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, 1, bc, st))) return rc; }
-    if ((rc = mg_vcycle_dist(h, 1, bc, xc, deg, st))) return rc;
-    if (1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, 1, xc, st))) return rc; }
-  } else {
-    if ((rc = mg_vcycle_graphed(h, 1, bc, xc, deg, st))) return rc;
-  }
+  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
+  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
+  if (dist) { if ((rc = mgd_exchange(h, l, b, st))) return rc; }
+  if ((rc = mg_lin_level<0>(h, l, s, n, b, m.r + off, b + off, nullptr, 1.0, 0.0, -it, nullptr, st))) return rc;
+  if (dist) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
+  if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st, false, nullptr,
+                         (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;
+  if (dist && l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; }
+  // the levels below are the same on every rank (replicated tail of the distributed solve / coarse levels of one GPU)
+  if ((h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0)) rc = mg_coarse_graphed(h, l + 1, bc, xc, st);
+  else rc = mg_vcycle_fused_level(h, l + 1, bc, xc, false, st);
+  if (rc) return rc;
+  if (dist && l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; }
   // x1 = b / theta + P x_c into m.d
   if (n > 0) {
-    if (h->mg_fp32 && m.P32 && JSSO_MG_RP) {
+    if (h->mg_fp32 && m.P32 && JSSO_MG_RP && m.nnz_p <= 6LL * m.n_f) {
       bsr_spmv_rp_kernel<float, 0><<<rp_grid(h, n), RED_BLOCK, 0, st>>>(n, m.p_rowptr + s, m.p_col, m.P32, xc, m.d + off, b + off,
                                                                        nullptr, it, 0.0, 1.0, h->mg_scal, h->partials,
                                                                        h->counters + 2, nullptr);
-    } else if (h->mg_fp32 && m.P32 && m.nnz_p <= 5LL * m.n_f) {
-      bsr_spmv_short_kernel<5><<<cdiv(3LL * n, 256), 256, 0, st>>>(n, m.p_rowptr + s, m.p_col, m.P32, xc, m.d + off,
-                                                                    b + off, it, h->mg_scal);
     } else if (h->mg_fp32 && m.P32) {
       bsr_spmv_lin_kernel<float, 0><<<mg_blocks(h, n), RED_BLOCK, 0, st>>>(n, m.p_rowptr + s, m.p_col, m.P32, xc, m.d + off,
                                                                           b + off, nullptr, it, 0.0, 1.0, h->mg_scal,
@@ -1962,8 +1993,55 @@ static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaSt
     }
     CKL("prolongation");
   }
-  if (dist) { if ((rc = mgd_exchange(h, 0, m.d, st))) return rc; }
-  return mg_lin_level0<1>(h, s, n, m.d, z + off, b + off, m.d + off, it, 1.0, -it, mgs_dot_target(h, MGS_RZ), st);
+  if (dist) { if ((rc = mgd_exchange(h, l, m.d, st))) return rc; }
+  if (want_dot) return mg_lin_level<1>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, mgs_dot_target(h, MGS_RZ), st);
+  return mg_lin_level<0>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, nullptr, st);
+}
+
+// The part of the fused V-cycle that is the same on every rank and launch-latency bound -- the coarse levels on one
+// GPU (l = 1), the replicated levels of the distributed solve (l = n_dist) -- as ONE graph launch: captured once per
+// numeric setup on a private stream (the smoother coefficients are kernel arguments), replayed into the caller's.
+static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st) {
+  if (!h->mg_graph) return mg_vcycle_fused_level(h, l, b, x, false, st);
+  if (h->mg_graph_exec && (h->mg_graph_level != l || h->mg_graph_b != b || h->mg_graph_x != x || h->mg_graph_deg != -1)) {
+    cudaGraphExecDestroy(h->mg_graph_exec);
+    h->mg_graph_exec = nullptr;
+  }
+  if (!h->mg_graph_exec) {
+    if (!h->st_cap) CK(cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(h->st_cap, cudaStreamCaptureModeThreadLocal));
+    const long long launched = g_launches.load();
+    const int rc = mg_vcycle_fused_level(h, l, b, x, false, h->st_cap);
+    g_launches.store(launched);                       // captured, not launched
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->st_cap, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(h, JSSO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&h->mg_graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { h->mg_graph_exec = nullptr; return fail(h, JSSO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2)); }
+    h->mg_graph_level = l; h->mg_graph_b = b; h->mg_graph_x = x; h->mg_graph_deg = -1;   // -1: the fused form
+  }
+  CK(cudaGraphLaunch(h->mg_graph_exec, st));
+  LAUNCHED();
+  return JSSO_OK;
+}
+
+// z = M^-1 b (one V-cycle from the fine level) on this rank's rows and r.z = b.z into slot MGS_RZ.  Chebyshev degree 1
+// (the default) takes the fused form above; other degrees the generic V-cycle.
+static int mg_vcycle_fused(jsso_handle* h, double* b, double* z, int deg, cudaStream_t st) {
+  const bool dist = h->mgd.n_rank > 1;
+  const int nl = (int)h->mg.size();
+  if (deg == 1 && nl > 0) return mg_vcycle_fused_level(h, 0, b, z, true, st);
+  int s = 0, n = h->sym.n_row;
+  if (dist) mgd_range(h, 0, s, n);
+  const size_t off = 6 * (size_t)s;
+  const int rc = dist ? mg_vcycle_dist(h, 0, b, z, deg, st) : mg_vcycle_graphed(h, 0, b, z, deg, st);
+  if (rc) return rc;
+  mg_dot_kernel<<<std::max(1, std::min(h->red_blocks, cdiv(6LL * n, 256))), 256, 0, st>>>(
+      6LL * n, b + off, z + off, h->partials, h->counters + 2, mgs_dot_target(h, MGS_RZ), mgs_ctx(h), h->mgd.red_seq_dev);
+  CKL("mg_dot_kernel");
+  return JSSO_OK;
 }
 
 static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0, jsso_stats* stats, cudaStream_t st) {

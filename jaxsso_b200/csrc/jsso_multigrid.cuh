@@ -218,6 +218,31 @@ mg_block_product_kernel(int nnz_out, const int32_t* __restrict__ ptr, const int3
   for (int k = 0; k < 36; ++k) o[k] = acc[k];
 }
 
+// P[s] <- P[s] W_c^T, c = p_col[s] (W_c lower triangular, row-major): the prolongator into the block-Jacobi-SCALED
+// coordinates of the coarse level (every level of the hierarchy is kept in scaled form, x_l = W_l^T y_l, so that its
+// diagonal blocks are the identity and the Chebyshev smoother needs no D^-1); thread per block
+__global__ void __launch_bounds__(128)
+mg_scale_cols_kernel(int n, const int32_t* __restrict__ p_col, const double* __restrict__ Wc, double* __restrict__ P,
+                     const int32_t* __restrict__ list = nullptr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int s = list ? list[t] : t;
+  const double* w = Wc + (size_t)p_col[s] * 36;
+  double* pb = P + (size_t)s * 36;
+  double a[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) a[k] = pb[k];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k <= j; ++k) v += a[6 * k + i] * w[j * 6 + k];   // (P W^T)[i][j] = sum_k P[i][k] W[j][k]
+      pb[6 * j + i] = v;
+    }
+}
+
 // Pt[s] = P[src[s]]^T
 __global__ void mg_transpose_blocks_kernel(int nnz, const int32_t* __restrict__ src, const double* __restrict__ P,
                                            double* __restrict__ Pt, int first = 0 /* slots [first, first + nnz) */) {

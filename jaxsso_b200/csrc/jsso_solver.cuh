@@ -1073,18 +1073,25 @@ cg_persistent_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_
 // W_r = L_r^-1 (lower triangular, stored dense row-major 6x6) from the diagonal blocks.
 __global__ void __launch_bounds__(128)
 diag_factor_kernel(int n_row, const int32_t* __restrict__ diag_slot, const double* __restrict__ vals,
-                   double* __restrict__ W, double* __restrict__ Lout /* optional: L row-major */, int* flags) {
+                   double* __restrict__ W, double* __restrict__ Lout /* optional: L row-major */, int* flags,
+                   int tolerant = 0 /* coarse multigrid levels: a (near) zero pivot -> that dof keeps L = 1, no flag */) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_row) return;
   const double* d = vals + (size_t)diag_slot[r] * 36;
   double L[6][6];
   bool ok = true;
+  double scale = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) scale = fmax(scale, fabs(d[j * 6 + j]));
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double s = d[j * 6 + j];
 #pragma unroll
     for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    // coarse levels: aggregates made of prescribed dofs give empty rows / columns -- those dofs stay unscaled
+    const bool dead = tolerant && !(s > 1e-14 * scale);
     if (!(s > 0.0)) { ok = false; s = 1.0; }
+    if (dead) s = 1.0;
     const double ljj = sqrt(s);
     L[j][j] = ljj;
 #pragma unroll
@@ -1092,10 +1099,10 @@ diag_factor_kernel(int n_row, const int32_t* __restrict__ diag_slot, const doubl
       double t = 0.5 * (d[j * 6 + i] + d[i * 6 + j]);   // symmetrised lower entry (i,j)
 #pragma unroll
       for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
-      L[i][j] = t / ljj;
+      L[i][j] = dead ? 0.0 : t / ljj;
     }
   }
-  if (!ok) atomicOr(flags, 8);
+  if (!ok && !tolerant) atomicOr(flags, 8);
   if (Lout) {
     double* lo = Lout + (size_t)r * 36;
 #pragma unroll
