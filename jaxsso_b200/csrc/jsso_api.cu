@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -1471,9 +1472,32 @@ static int mg_scale_coarse(jsso_handle* h, int l, const int32_t* p_list, int n_p
   return JSSO_OK;
 }
 
+// JSSO_MG_TIMING=1: synchronise between the phases of the numeric setup and print their wall times (diagnostics)
+struct PhaseTimer {
+  bool on; cudaStream_t st; double t0; std::string out; int rank;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  PhaseTimer(cudaStream_t s, int r) : st(s), rank(r) {
+    const char* e = std::getenv("JSSO_MG_TIMING");
+    on = e && e[0] == '1';
+    if (on) { cudaStreamSynchronize(st); t0 = now(); }
+  }
+  void mark(const char* name, int l = -1) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const double t = now();
+    char buf[96];
+    if (l >= 0) std::snprintf(buf, sizeof buf, " %s[%d]=%.3f", name, l, 1e3 * (t - t0));
+    else std::snprintf(buf, sizeof buf, " %s=%.3f", name, 1e3 * (t - t0));
+    out += buf;
+    t0 = now();
+  }
+  ~PhaseTimer() { if (on && rank == 0) std::fprintf(stderr, "JSSO_MG_TIMING (ms):%s\n", out.c_str()); }
+};
+
 // numeric hierarchy for the current (block-Jacobi-scaled) matrix
 static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_ready) return JSSO_OK;
+  PhaseTimer pt_(st, h->mgd.rank);
   if (h->mg_graph_exec) { cudaGraphExecDestroy(h->mg_graph_exec); h->mg_graph_exec = nullptr; }   // coefficients change
   if (!h->last_crds) return fail(h, JSSO_ERR_STATE, "multigrid needs the coordinates of the last jsso_assemble");
   const int nl = (int)h->mg.size();
@@ -1537,6 +1561,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       CKL("mg_axpby_kernel");
     }
     m.lam = h->mg_power_safety * lam;
+    pt_.mark("power", l);
     mg_centroid_kernel<<<cdiv(m.n_c, 128), 128, 0, st>>>(m.n_c, m.mem_ptr, m.mem, X, m.Xc);
     CKL("mg_centroid_kernel");
     if (h->mgd.setup_on && l < h->mgd.n_dist) {
@@ -1563,6 +1588,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
                                                                        nullptr, a0);
         CKL("mg_block_product_kernel<1>");
       }
+      pt_.mark("P_AP_Ac", l);
       CKN(g_nccl.GroupStart());
       for (int r = 0; r < h->mgd.n_rank; ++r) {
         if (r == me) continue;
@@ -1571,6 +1597,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
         if (theirs) CKN(g_nccl.Recv(m.Ac + 36 * (size_t)SL.ac_bounds[r], theirs, ncclDouble, r, h->mgd.comm, st));
       }
       CKN(g_nccl.GroupEnd());
+      pt_.mark("allgather_Ac", l);
       // the coarse level in scaled form: factor its diagonal blocks, A_c <- W_c A_c W_c^T, P <- P W_c^T (then P^T)
       if ((rc = mg_scale_coarse(h, l, SL.p_list, SL.n_p, st))) return rc;
       if (pt[1] > pt[0]) {
@@ -1582,6 +1609,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
         if ((rc = mg_to_float(h, 36LL * (pt[1] - pt[0]), m.Pt + 36 * (size_t)pt[0], m.Pt32 + 36 * (size_t)pt[0], st))) return rc;
         if ((rc = mg_to_float(h, 36LL * m.nnz_c, m.Ac, m.Ac32, st))) return rc;
       }
+      pt_.mark("scale_transpose_convert", l);
       X = m.Xc;
       continue;
     }
@@ -1593,6 +1621,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     CKL("mg_block_product_kernel<0>");
     mg_block_product_kernel<1><<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
     CKL("mg_block_product_kernel<1>");
+    pt_.mark("P_AP_Ac", l);
     if ((rc = mg_scale_coarse(h, l, nullptr, m.nnz_p, st))) return rc;
     mg_transpose_blocks_kernel<<<cdiv(36LL * m.nnz_p, 256), 256, 0, st>>>(m.nnz_p, m.pt_src, m.P, m.Pt);
     CKL("mg_transpose_blocks_kernel");
@@ -1601,6 +1630,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       if ((rc = mg_to_float(h, 36LL * m.nnz_p, m.Pt, m.Pt32, st))) return rc;
       if ((rc = mg_to_float(h, 36LL * m.nnz_c, m.Ac, m.Ac32, st))) return rc;
     }
+    pt_.mark("scale_transpose_convert", l);
     X = m.Xc;
   }
   {
@@ -1620,6 +1650,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       CKL("mg_to_half_kernel");
     }
   }
+  pt_.mark("fine_copy");
   // coarsest level: dense inverse
   const MgMat C = mg_matrix(h, nl);
   const int nc = 6 * C.n;
@@ -1629,6 +1660,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   CKL("mg_dense_fill_kernel");
   mg_dense_invert_kernel<<<1, 1024, 0, st>>>(nc, h->mg_dense);
   CKL("mg_dense_invert_kernel");
+  pt_.mark("dense_inverse");
   h->mg_ready = true;
   return JSSO_OK;
 }
@@ -2205,8 +2237,10 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
                         cudaStream_t st) {
   if (!h->assembled || !h->assembled_bc)
     return fail(h, JSSO_ERR_STATE, "solve needs a matrix assembled with apply_bc=1");
+  PhaseTimer pts_(st, h->mgd.rank);
   int rc = ensure_scaled(h, st);
   if (rc) return rc;
+  pts_.mark("block_jacobi_scaling");
   CK(cudaMemcpyAsync(h->flags_host, h->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const int fl = *h->flags_host;
@@ -2240,6 +2274,7 @@ static int solve_system(jsso_handle* h, const double* b, double* x, const jsso_s
   if (use_mg) rc = mg_solve_fused(h, o, o.use_x0 != 0, stats, st);
   else rc = cg_solve_scaled(h, o, o.use_x0 != 0, stats, st);
   if (stats) stats->flags = fl;
+  pts_.mark("setup_and_pcg");
   if (rc && rc != JSSO_ERR_NOCONV) return rc;
   if (rn > 0) {
     block_apply_kernel<1><<<cdiv(rn, 128), 128, 0, st>>>(rn, h->W + 6 * ro, h->vx + ro, nullptr, x + ro);
