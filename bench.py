@@ -567,6 +567,29 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     h2d = 8 * (md.crds.size + md.prop_quads.size + md.prop_beams.size + 2 * u.size)
     d2h = 8 * (out_bufs[0].size + out_bufs[1].size)
+    # what PCIe allows for this step: pinned-memory copy bandwidth both ways, measured here (rank 0's device)
+    pcie = None
+    try:
+        nb = 256 << 20
+        hbuf = nat.pinned_empty((nb // 8,))
+        dbuf = D((nb // 8,))
+        bw = {}
+        for name, fn in (('h2d', lambda: L.jsso_memcpy_h2d(dbuf.ptr, hbuf.ctypes.data, nb, None)),
+                         ('d2h', lambda: L.jsso_memcpy_d2h(hbuf.ctypes.data, dbuf.ptr, nb, None))):
+            fn(); L.jsso_stream_sync(None)
+            t0 = time.perf_counter()
+            for _ in range(4):
+                fn()
+            L.jsso_stream_sync(None)
+            bw[name] = 4 * nb / (time.perf_counter() - t0) / 1e9
+        pcie = {'h2d_gbs': bw['h2d'], 'd2h_gbs': bw['d2h'],
+                'copy_bound_ms': 1e3 * max(h2d / (bw['h2d'] * 1e9), d2h / (bw['d2h'] * 1e9)),
+                'copies_serial_ms': 1e3 * (h2d / (bw['h2d'] * 1e9) + d2h / (bw['d2h'] * 1e9)),
+                'note': 'copy_bound_ms: both directions fully overlapped (full duplex); copies_serial_ms: upload then '
+                        'download.  The gradients can only leave after the adjoint, which needs every upload.'}
+        dbuf.free()
+    except Exception as e:
+        pcie = {'error': str(e)}
 
     # full shape-gradient evaluation incl. the solve (metric M2): one warm-up evaluation, then the mean of
     # --grad-evals timed ones (each: Ke+assembly, block-Jacobi scaling, numeric multigrid setup, PCG for u to the TRUE
@@ -694,6 +717,24 @@ def run_b200(args):
         except Exception:
             pass
 
+    # metric M2 end to end through the host-buffer entry point (N = 1): H2D of coordinates / properties / loads, the
+    # whole gradient evaluation, D2H of u and the gradients inside the timed region
+    m2_e2e = None
+    if world == 1 and grad_eval and 'error' not in grad_eval and args.precond != 'block_jacobi':
+        try:
+            o_ = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, precond=args.precond, cheb_degree=args.cheb_degree)
+            h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads, want=('crds', 'prop_q'), opts=o_)
+            t0 = time.perf_counter()
+            v_, u_, dc_, dq_, _, fs_, _ = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads,
+                                                                want=('crds', 'prop_q'), opts=o_)
+            dt_ = time.perf_counter() - t0
+            m2_e2e = {'seconds': dt_, 'evals_per_s': 1.0 / dt_, 'call': 'jsso_value_and_grad_host (C ABI, host buffers)',
+                      'h2d_bytes': int(8 * (md.crds.size + md.prop_quads.size + md.prop_beams.size + md.loads.size)),
+                      'd2h_bytes': int(8 * (u_.size + dc_.size + dq_.size)), 'pcg_iterations': int(fs_.iterations),
+                      'compliance': float(v_)}
+        except nat.JssoError as e:
+            m2_e2e = {'error': str(e)}
+
     # BASELINE config 5: a batch of independent gridshell designs (beam-columns) sharded over the ranks -- replicas,
     # no collective on the hot path; the 64 compliances and shape gradients are all-gathered at the end
     batch_eval = None
@@ -780,7 +821,7 @@ def run_b200(args):
                           'l2_note': 'working set per step (2.7 GB of block-CSR values at N=1) is larger than the 126 MB L2',
                           'rank0_local': {'n_quad': s.n_quad, 'n_node': s.n_node, 'n_row': s.n_row, 'nnzb': s.nnzb}},
                'e2e': {'value': n_quad_total / s_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                       'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)'},
+                       'ms_per_step': s_e2e * 1e3, 'call': 'jsso_assemble_adjoint_host (C ABI, host buffers)', 'pcie': pcie},
                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_assembly': roof_asm,
                'roofline_adjoint': roof_adj,
                'roofline_spmv': roof_spmv,
@@ -795,6 +836,8 @@ def run_b200(args):
                          'pcg_iterations': grad_eval['pcg_iterations'],
                          'ms_per_pcg_iteration': grad_eval['ms_per_pcg_iteration'],
                          'u_err_estimate': (grad_eval.get('u_err_estimate') or {}).get('value')}
+            if m2_e2e is not None:
+                out['m2']['e2e'] = m2_e2e
             if mg_bytes_it:
                 bi = mg_bytes_it['total'] / max(world, 1)     # row ranges: every rank streams 1/N of every level it distributes
                 ms_it = grad_eval['ms_per_pcg_iteration']

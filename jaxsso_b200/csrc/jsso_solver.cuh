@@ -917,38 +917,61 @@ mgd_wait_unpack_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const i
 // on the co-residency of several blocks (a block that waits never holds back a block that still has to push).
 // Halos of a strip partition are a few thousand nodes: one block of 1024 threads moves them in a few microseconds
 // and saves a launch per exchange; larger exchanges (the all-gather level) use the two-kernel form above.
-constexpr int MGD_ONE_BLOCK_MAX = 24576;   // doubles
+constexpr int MGD_ONE_BLOCK_MAX = 49152;   // doubles
+// 16-byte pieces (a node's six doubles = three pieces), four independent load / store pairs per thread and round:
+// a single block is bound by memory latency, not bandwidth, so the rounds must be few (a strip's halo of ~3 700 nodes
+// took 17 + 22 dependent rounds = ~30 us with one 8-byte element per thread and round, measured at 8 GPUs)
+__device__ inline void mgd_gather_pieces(double* __restrict__ dst, const double* __restrict__ v,
+                                         const int32_t* __restrict__ idx, int n_node, int tid, int nthr) {
+  const int n = 3 * n_node;
+  for (int t0 = tid; t0 < n; t0 += 4 * nthr) {
+    double2 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+      if (t < n) r[u] = *(const double2*)(v + 6 * (size_t)idx[t / 3] + 2 * (t % 3));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+      if (t < n) *(double2*)(dst + 2 * (size_t)t) = r[u];
+    }
+  }
+}
+__device__ inline void mgd_scatter_pieces(double* __restrict__ v, const double* __restrict__ src,
+                                          const int32_t* __restrict__ idx, int n_node, int tid, int nthr) {
+  const int n = 3 * n_node;
+  for (int t0 = tid; t0 < n; t0 += 4 * nthr) {
+    double2 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+      if (t < n) { r[u].x = ld_relaxed_sys_f64(src + 2 * (size_t)t); r[u].y = ld_relaxed_sys_f64(src + 2 * (size_t)t + 1); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * nthr;
+      if (t < n) *(double2*)(v + 6 * (size_t)idx[t / 3] + 2 * (t % 3)) = r[u];
+    }
+  }
+}
 __global__ void __launch_bounds__(1024)
 mgd_exchange_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const int32_t* __restrict__ send_idx,
                     const int32_t* __restrict__ recv_idx, double* __restrict__ v, unsigned* counter, unsigned long long seq) {
-  __shared__ bool last;
+  // ONE block (see above): the push is complete at the barrier, thread p then releases the flag of peer p
   const long long slot = (long long)level * c->arena_level_stride + (long long)(seq & 1ull) * c->arena_slot_stride;
-  for (int pi = 0; pi < L->n_peer; ++pi) {
-    double* dst = c->arena[L->peer_rank[pi]] + slot + 6 * (long long)L->remote_off[pi];
-    const int32_t* idx = send_idx + L->send_off[pi];
-    const int n = 6 * L->send_cnt[pi];
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-      dst[t] = v[6 * (size_t)idx[t / 6] + t % 6];
-  }
+  for (int pi = 0; pi < L->n_peer; ++pi)
+    mgd_gather_pieces(c->arena[L->peer_rank[pi]] + slot + 6 * (long long)L->remote_off[pi], v, send_idx + L->send_off[pi],
+                      L->send_cnt[pi], threadIdx.x, blockDim.x);
+  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && (int)threadIdx.x < L->n_peer) {
-    __threadfence();
-    st_release_sys(&c->mbox[L->peer_rank[threadIdx.x]]->halo[level][c->rank], seq);
-  }
   if ((int)threadIdx.x < L->n_peer) {
+    st_release_sys(&c->mbox[L->peer_rank[threadIdx.x]]->halo[level][c->rank], seq);
     const MgdMailbox* m = c->mbox[c->rank];
     while (ld_acquire_sys(&m->halo[level][L->peer_rank[threadIdx.x]]) < seq) { }
   }
   __syncthreads();
-  const double* src = c->arena[c->rank] + slot;
-  const int n = 6 * L->n_recv;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-    v[6 * (size_t)recv_idx[t / 6] + t % 6] = ld_relaxed_sys_f64(src + t);
+  mgd_scatter_pieces(v, c->arena[c->rank] + slot, recv_idx, L->n_recv, threadIdx.x, blockDim.x);
 }
 
 // Mailbox all-reduce of `count` <= 2 scalars by ONE thread.  The sequence number lives on the device (*seq_ctr) and
