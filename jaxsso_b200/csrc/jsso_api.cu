@@ -160,6 +160,37 @@ struct jsso_handle {
   bool mg_fp16 = false;
   int mg_power_iters = 10;         // steps of the power iteration for lambda_max per level (JSSO_MG_POWER_ITERS)
   double mg_power_safety = 1.2;
+  // JSSO_MG_TIMING=2: CUDA events between the steps of ONE PCG iteration (the 4th of a solve), printed afterwards
+  struct IterProbe {
+    bool armed = false, active = false, done = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    void mark(const char* name, int l, cudaStream_t st) {
+      if (!active) return;
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      cudaEventRecord(e, st);
+      ev.push_back(e);
+      names.push_back(l >= 0 ? std::string(name) + "[" + std::to_string(l) + "]" : std::string(name));
+    }
+    void report(int rank) {
+      if (ev.size() < 2) return;
+      cudaEventSynchronize(ev.back());
+      std::string out;
+      float tot = 0.f;
+      for (size_t i = 1; i < ev.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        tot += ms;
+        char buf[96];
+        std::snprintf(buf, sizeof buf, " %s=%.1f", names[i].c_str(), 1e3 * ms);
+        out += buf;
+      }
+      std::fprintf(stderr, "JSSO_MG_ITER rank %d (us, one iteration = %.1f):%s\n", rank, 1e3 * tot, out.c_str());
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+      ev.clear(); names.clear();
+    }
+  } probe;
   int mg_poll = 8;                 // the PCG scalars stay on the device; the host polls the residual every mg_poll iterations
   // opt-in CUDA graph of the V-cycle's launch-bound part (JSSO_MG_GRAPH=1): the whole V-cycle on one GPU, the
   // replicated coarse levels of the distributed solve.  Captured once per numeric setup (the smoother
@@ -1140,6 +1171,7 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     const char* e = std::getenv("JSSO_MG_FP64");   // A/B switch: keep the V-cycle matrices in FP64
     h->mg_fp32 = !(e && e[0] == '1');
     if (const char* ea = std::getenv("JSSO_MG_POLL")) h->mg_poll = std::max(1, std::min(64, std::atoi(ea)));
+    if (const char* et = std::getenv("JSSO_MG_TIMING")) h->probe.armed = et[0] == '2';
     if (const char* ep = std::getenv("JSSO_MG_POWER_ITERS")) {   // A/B: 30 restores round 1's estimate (x 1.15)
       h->mg_power_iters = std::max(3, std::min(200, std::atoi(ep)));
       if (h->mg_power_iters >= 30) h->mg_power_safety = 1.15;
@@ -1997,17 +2029,20 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
   const double it = 1.0 / (0.625 * m.lam);   // 1 / theta, theta = (lam + lam / 4) / 2
   double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
   double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
-  if (dist) { if ((rc = mgd_exchange(h, l, b, st))) return rc; }
+  if (dist) { if ((rc = mgd_exchange(h, l, b, st))) return rc; h->probe.mark("xch_b", l, st); }
   if ((rc = mg_lin_level<0>(h, l, s, n, b, m.r + off, b + off, nullptr, 1.0, 0.0, -it, nullptr, st))) return rc;
-  if (dist) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
+  h->probe.mark("K1_resid", l, st);
+  if (dist) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; h->probe.mark("xch_r", l, st); }
   if ((rc = mg_spmv_p<0>(h, m.pt_rowptr + s1, m.pt_col, m.Pt, m.Pt32, n1, m.r, bc + off1, nullptr, st, false, nullptr,
                          (double)m.nnz_p / std::max(m.n_c, 1)))) return rc;
-  if (dist && l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; }
+  h->probe.mark("K2_restrict", l, st);
+  if (dist && l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; h->probe.mark("allgather", l + 1, st); }
   // the levels below are the same on every rank (replicated tail of the distributed solve / coarse levels of one GPU)
   if ((h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0)) rc = mg_coarse_graphed(h, l + 1, bc, xc, st);
   else rc = mg_vcycle_fused_level(h, l + 1, bc, xc, false, st);
   if (rc) return rc;
-  if (dist && l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; }
+  if ((h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0)) h->probe.mark("coarse_tail_graph", l + 1, st);
+  if (dist && l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; h->probe.mark("xch_xc", l + 1, st); }
   // x1 = b / theta + P x_c into m.d
   if (n > 0) {
     if (h->mg_fp32 && m.P32 && JSSO_MG_RP && m.nnz_p <= 6LL * m.n_f) {
@@ -2025,9 +2060,12 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
     }
     CKL("prolongation");
   }
-  if (dist) { if ((rc = mgd_exchange(h, l, m.d, st))) return rc; }
-  if (want_dot) return mg_lin_level<1>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, mgs_dot_target(h, MGS_RZ), st);
-  return mg_lin_level<0>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, nullptr, st);
+  h->probe.mark("K3_prolong", l, st);
+  if (dist) { if ((rc = mgd_exchange(h, l, m.d, st))) return rc; h->probe.mark("xch_x1", l, st); }
+  if (want_dot) rc = mg_lin_level<1>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, mgs_dot_target(h, MGS_RZ), st);
+  else rc = mg_lin_level<0>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, nullptr, st);
+  h->probe.mark(want_dot ? "K4_post_rz" : "K4_post", l, st);
+  return rc;
 }
 
 // The part of the fused V-cycle that is the same on every rank and launch-latency bound -- the coarse levels on one
@@ -2117,12 +2155,14 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
   while (!converged && it < o.maxiter) {
     const int batch = std::max(1, std::min(h->mg_poll, o.maxiter - it));
     for (int k = 0; k < batch; ++k) {
+      if (h->probe.armed && !h->probe.done && it + k == 3) { h->probe.active = true; h->probe.mark("start", -1, st); }
       if ((rc = mg_vcycle_fused(h, r, z, o.cheb_degree, st))) return rc;
       if ((rc = mgs_reduce(h, MGS_RZ, 1, st))) return rc;
       mg_pcg_dir_kernel<<<vb, 256, 0, st>>>(n, z + off, p + off, scal, first ? 1 : 0);
       CKL("mg_pcg_dir_kernel");
       first = false;
-      if (dist) { if ((rc = mgd_exchange(h, 0, p, st))) return rc; }
+      h->probe.mark("dir", -1, st);
+      if (dist) { if ((rc = mgd_exchange(h, 0, p, st))) return rc; h->probe.mark("xch_p", 0, st); }
       if (n_row > 0) {
         bsr_spmv_dot_kernel<<<mg_blocks(h, n_row), RED_BLOCK, 0, st>>>(n_row, A.rp + s, A.ci, A.v, p, p + off, q + off, scal,
                                                                      h->partials, h->counters + 2, mgs_dot_target(h, MGS_PQ),
@@ -2132,12 +2172,15 @@ static int mg_solve_fused(jsso_handle* h, const jsso_solve_opts& o, bool use_x0,
         if ((rc = mgs_zero_dot(h, MGS_PQ, st))) return rc;
       }
       if ((rc = mgs_reduce(h, MGS_PQ, 1, st))) return rc;
+      h->probe.mark("K6_Ap_pq", -1, st);
       mg_pcg_update_kernel<<<vb, 256, 0, st>>>(n, p + off, q + off, x + off, r + off, scal, h->partials, h->counters + 2,
                                               mgs_dot_target(h, MGS_RR), mgs_ctx(h), h->mgd.red_seq_dev);
       CKL("mg_pcg_update_kernel");
       if ((rc = mgs_reduce(h, MGS_RR, 1, st))) return rc;
+      if (h->probe.active) { h->probe.mark("K7_update_rr", -1, st); h->probe.active = false; h->probe.done = true; }
     }
     if ((rc = mg_read_scalars(h, st))) return rc;
+    if (h->probe.done && !h->probe.ev.empty()) h->probe.report(h->mgd.rank);
     const int it_new = (int)h->mg_scal_host[MGS_ITER];
     rr = h->mg_scal_host[MGS_RR];
     if (!(rr == rr)) {

@@ -363,7 +363,7 @@ mg_dot_kernel(long long n, const double* __restrict__ a, const double* __restric
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc = fma(a[i], b[i], acc);
   double total;
-  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, out, rctx, rseq);
+  if (grid_sum(acc, partials, counter, total)) mgs_store_dot_block(total, out, rctx, rseq);
 }
 // y = a*x + b*y
 __global__ void mg_axpby_kernel(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
@@ -416,11 +416,14 @@ mg_pcg_update_kernel(long long n, const double* __restrict__ p, const double* __
     acc = fma(rn.y, rn.y, acc);
   }
   double total;
-  if (grid_sum(acc, partials, counter, total) && threadIdx.x == 0) {
-    scal[MGS_RZ_OLD] = rz;
-    scal[MGS_ITER] += 1.0;
+  if (grid_sum(acc, partials, counter, total)) {
+    if (threadIdx.x == 0) {
+      scal[MGS_RZ_OLD] = rz;
+      scal[MGS_ITER] += 1.0;
+      if (!(pq > 0.0 && rz > 0.0)) total = __longlong_as_double(0x7ff8000000000000LL);
+    }
     // (after the bookkeeping: in the distributed solve the store waits for the other ranks)
-    mgs_store_dot((pq > 0.0 && rz > 0.0) ? total : __longlong_as_double(0x7ff8000000000000LL), rr_out, rctx, rseq);
+    mgs_store_dot_block(total, rr_out, rctx, rseq);
   }
 }
 // scal[MGS_TOL] = rtol^2 |b|^2 and the iteration counter (start of a solve; one thread)

@@ -158,6 +158,9 @@ struct MgdCtx;
 // this rank's partial to every rank's mailbox, wait for all ranks and store the sum (rank order: bitwise identical
 // everywhere).  Called by ONE thread of the block that finalised the sum; defined below the mailbox structs.
 __device__ inline void mgs_store_dot(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr);
+// the same called by ALL threads of that block (total valid in thread 0): lane r of the first warp talks to rank r, so
+// the remote stores, the fences and the polls of the ranks run in parallel instead of one after the other
+__device__ inline void mgs_store_dot_block(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr);
 
 __device__ inline double warp_sum(double v) {
 #pragma unroll
@@ -610,7 +613,7 @@ bsr_spmv_dot_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
     }
   });
   double total;
-  if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
+  if (grid_sum(dot, partials, counter, total)) mgs_store_dot_block(total, dot_out, rctx, rseq);
 }
 
 // MODE 0: y = A x;  2: y = b - A x;  3: y += A x;  5 (short-row kernel only): y = s b + A x
@@ -681,7 +684,7 @@ bsr_spmv_lin_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
   else dot = bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, epilogue);
   if (DOT != 0) {
     double total;
-    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
+    if (grid_sum(dot, partials, counter, total)) mgs_store_dot_block(total, dot_out, rctx, rseq);
   }
 }
 
@@ -775,7 +778,7 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   }
   if (DOT != 0) {
     double total;
-    if (grid_sum(dot, partials, counter, total) && threadIdx.x == 0) mgs_store_dot(total, dot_out, rctx, rseq);
+    if (grid_sum(dot, partials, counter, total)) mgs_store_dot_block(total, dot_out, rctx, rseq);
   }
 }
 
@@ -1002,6 +1005,30 @@ __global__ void mgd_allreduce_kernel(const MgdCtx* c, const double* src, double*
 __device__ inline void mgs_store_dot(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr) {
   if (!ctx) { *out = total; return; }
   mgd_allreduce_thread(ctx, &total, out, 1, seq_ctr);
+}
+__device__ inline void mgs_store_dot_block(double total, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr) {
+  if (!ctx) { if (threadIdx.x == 0) *out = total; return; }
+  __shared__ double sh_total;
+  if (threadIdx.x == 0) sh_total = total;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    const unsigned long long seq = *seq_ctr + 1ull;
+    const int par = (int)(seq & 1ull);
+    __syncwarp();
+    double v = 0.0;
+    if (r < ctx->n_rank) {
+      st_relaxed_sys_f64(&ctx->mbox[r]->red_val[par][ctx->rank][0], sh_total);
+      __threadfence_system();
+      st_release_sys(&ctx->mbox[r]->red_tag[par][ctx->rank], seq);
+      const MgdMailbox* m = ctx->mbox[ctx->rank];
+      while (ld_acquire_sys(&m->red_tag[par][r]) < seq) { }
+      v = ld_relaxed_sys_f64(&m->red_val[par][r][0]);
+    }
+    double acc = 0.0;
+    for (int k = 0; k < ctx->n_rank; ++k) acc += __shfl_sync(0xffffffffu, v, k);   // rank order: identical on every rank
+    if (r == 0) { *out = acc; *seq_ctr = seq; }
+  }
 }
 // a rank with an empty row range still takes part in the reduction of a fused dot product
 __global__ void mgs_zero_dot_kernel(const double* stop, double* out, const MgdCtx* ctx, unsigned long long* seq_ctr) {
