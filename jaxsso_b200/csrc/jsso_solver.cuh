@@ -604,14 +604,39 @@ bsr_spmv_dot_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warp = (gridDim.x * blockDim.x) >> 5;
+  // the row's own x entries (for p.q) are loaded BEFORE the row product is reduced, so that their latency hides behind
+  // the product instead of extending every row's critical path (the first version of this kernel loaded them in the
+  // epilogue: 518 us against 466 us of the plain SpMV at 1M quads)
+  constexpr int U = RowU<double>::U;
   double dot = 0.0;
-  bsr_rows_pipelined(warp, n_warp, lane, n_row, rowptr, colidx, vals, x, [&](int r, double u0, double u1) {
-    if (lane < 3) {
-      *(double2*)(y + 6 * (size_t)r + 2 * lane) = make_double2(u0, u1);
-      const double2 xr = *(const double2*)(xrow + 6 * (size_t)r + 2 * lane);
-      dot += u0 * xr.x + u1 * xr.y;
+  int r = warp;
+  if (r < n_row) {
+    int b0 = rowptr[r], b1 = rowptr[r + 1];
+    int ci[U];
+    row_colidx(lane, b0, b1, colidx, ci, vals);
+    int nb0 = 0, nb1 = 0;
+    if (r + n_warp < n_row) { nb0 = rowptr[r + n_warp]; nb1 = rowptr[r + n_warp + 1]; }
+    for (; r < n_row; r += n_warp) {
+      const int r1 = r + n_warp, r2 = r + 2 * n_warp;
+      int nci[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) nci[u] = -1;
+      if (r1 < n_row) row_colidx(lane, nb0, nb1, colidx, nci, vals);
+      int nnb0 = 0, nnb1 = 0;
+      if (r2 < n_row) { nnb0 = rowptr[r2]; nnb1 = rowptr[r2 + 1]; }
+      double2 xr = make_double2(0.0, 0.0);
+      if (lane < 3) xr = *(const double2*)(xrow + 6 * (size_t)r + 2 * lane);
+      double u0, u1;
+      bsr_row_product(b0, b1, ci, lane, colidx, vals, x, u0, u1);
+      if (lane < 3) {
+        *(double2*)(y + 6 * (size_t)r + 2 * lane) = make_double2(u0, u1);
+        dot += u0 * xr.x + u1 * xr.y;
+      }
+      b0 = nb0; b1 = nb1; nb0 = nnb0; nb1 = nnb1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) ci[u] = nci[u];
     }
-  });
+  }
   double total;
   if (grid_sum(dot, partials, counter, total)) mgs_store_dot_block(total, dot_out, rctx, rseq);
 }
@@ -744,6 +769,11 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_item; t += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
     const int b0 = rowptr[r], b1 = rowptr[r + 1];
+    const size_t o = 6 * (size_t)r + 2 * sub;
+    // the epilogue's operands are requested now, their latency hides behind the block loop
+    double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+    if (bvec) bv = *(const double2*)(bvec + o);
+    if (xrow) xv = *(const double2*)(xrow + o);
     double acc0 = 0.0, acc1 = 0.0;
     int k = b0;
     for (; k + 1 < b1; k += 2) {
@@ -767,11 +797,9 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
       RpLoad<VT>::unpack(ra, f);
       rp_fma(f, xa0, xa1, xa2, acc0, acc1);
     }
-    const size_t o = 6 * (size_t)r + 2 * sub;
     double2 v = make_double2(cc * acc0, cc * acc1);
-    double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
-    if (bvec) { bv = *(const double2*)(bvec + o); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
-    if (xrow) { xv = *(const double2*)(xrow + o); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
+    if (bvec) { v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
+    if (xrow) { v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
     *(double2*)(y + o) = v;
     if (DOT == 1) dot += bv.x * v.x + bv.y * v.y;
     if (DOT == 2) dot += xv.x * acc0 + xv.y * acc1;
