@@ -473,12 +473,53 @@ struct TaskArgs {
   double* vals; int* flags; int n_quad; int n_task; int apply_bc;
 };
 
+#ifndef JSSO_T_BULK
+#define JSSO_T_BULK 1      // records staged by 1-D bulk async copies (cp.async.bulk + mbarrier: the TMA unit) instead of per-lane cp.async
+#endif
 #ifdef JSSO_EMU   // CPU test harness: a synchronous copy (a missing wait is not detected there)
 __device__ inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
 __device__ inline void prefetch_l2(const void*) {}
 __device__ inline void cp_async_commit() {}
 __device__ inline void cp_async_wait_all() {}
+__device__ inline void mbar_init(unsigned long long*, int) {}
+__device__ inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ inline void bulk_copy_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) { memcpy(smem_dst, gsrc, bytes); }
+__device__ inline void mbar_wait(unsigned long long*, unsigned) {}
+__device__ inline void fence_proxy_async() {}
 #else
+// ---- 1-D bulk asynchronous copies (sm_90+: cp.async.bulk, executed by the TMA unit; SASS UBLKCP) ------------------
+// One instruction of ONE lane moves a whole 496-byte record global -> shared; completion is counted in bytes on an
+// mbarrier in shared memory, which the warp polls with try_wait.  No per-lane LDGSTS, no LSU wavefronts per lane --
+// the LSU data pipe is what bounds assemble_tasks_kernel (85 % of peak with the cp.async staging).
+__device__ inline void mbar_init(unsigned long long* bar, int count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {   // one arrival + the bytes to wait for
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ inline void bulk_copy_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(a) : "memory");
+}
+__device__ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "JSSO_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra JSSO_MBAR_DONE;\n"
+      "bra JSSO_MBAR_WAIT;\n"
+      "JSSO_MBAR_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
+__device__ inline void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 __device__ inline void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -508,14 +549,25 @@ __device__ inline void task_load(const TaskArgs& A, const int4 m, int lane, Task
   t.beam_el = ((t.desc & kDescBeam) && lane < n_item) ? (A.item_code[m.y + lane] >> 4) - A.n_quad : 0;
 }
 
-// records of the task's quads -> this warp's record buffer, 16-byte asynchronous copies
-__device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, int lane, double* rec) {
+// records of the task's quads -> this warp's record buffer: one bulk copy per record issued by lane `le` (JSSO_T_BULK),
+// or 16-byte cp.async by 31 lanes per record
+__device__ inline void task_stage_records(const TaskArgs& A, const TaskRegs& t, int lane, double* rec, unsigned long long* bar) {
   const int n_el = (t.cnt >> 16) & 255;
+#if JSSO_T_BULK
+  // the warp has finished reading the buffer (the caller's __syncwarp); make that visible to the async proxy, arm the
+  // barrier with the byte count, then every lane < n_el sends its record
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(bar, (unsigned)(n_el * REC * sizeof(double)));
+  __syncwarp();
+  if (lane < n_el) bulk_copy_g2s(rec + lane * REC_LD, A.rec + (size_t)t.el * REC_GLD, (unsigned)(REC * sizeof(double)), bar);
+#else
   for (int le = 0; le < n_el; ++le) {
     const int e = __shfl_sync(0xffffffffu, t.el, le);
     if (lane < REC / 2) cp_async16(rec + le * REC_LD + 2 * lane, A.rec + (size_t)e * REC_GLD + 2 * lane);
   }
   cp_async_commit();
+#endif
 }
 
 // Persistent warps: warp gw handles tasks gw, gw + W, gw + 2W, ...  Software pipeline per warp:
@@ -532,11 +584,18 @@ assemble_tasks_kernel(TaskArgs A) {
   if (task >= A.n_task) return;                       // whole warp; no CTA-wide barrier anywhere
   double* rec = sm + w * TASK_SMEM_DOUBLES;
   double* buf = rec + kTaskQuads * REC_LD;
+  __shared__ unsigned long long bars[TASK_WARPS];   // one mbarrier per warp (bulk-copy completion of its record buffer)
+  unsigned long long* bar = &bars[w];
+  unsigned phase = 0;
+#if JSSO_T_BULK
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+#endif
   // lane -> (block of the triple, 16-byte pieces k and k + 9 of its 18) in the output phase
   const int c0 = lane / 9, kp = lane - 9 * c0;
   TaskRegs cur, nxt, nn;
   task_load(A, A.task_meta[task], lane, cur);
-  task_stage_records(A, cur, lane, rec);
+  task_stage_records(A, cur, lane, rec, bar);
   nxt = cur; nn = cur;
   if (task + stride < A.n_task) task_load(A, A.task_meta[task + stride], lane, nxt);
   int4 m2 = make_int4(0, 0, 0, 0);                    // meta word of task + 2 stride (one iteration ahead of its use)
@@ -557,7 +616,12 @@ assemble_tasks_kernel(TaskArgs A) {
       if (has_next && (lane >> 2) < ((nxt.cnt >> 16) & 255)) prefetch_l2(A.rec + (size_t)e * REC_GLD + 16 * (lane & 3));
     }
 #endif
+#if JSSO_T_BULK
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+#else
     cp_async_wait_all();
+#endif
     __syncwarp();
     if (lane < n_item) {
       double out[36];
@@ -571,7 +635,7 @@ assemble_tasks_kernel(TaskArgs A) {
       for (int k2 = 0; k2 < 18; ++k2) dst[k2] = make_double2(out[2 * k2], out[2 * k2 + 1]);
     }
     __syncwarp();                                     // item rows complete; record buffer free
-    if (has_next) task_stage_records(A, nxt, lane, rec);
+    if (has_next) task_stage_records(A, nxt, lane, rec, bar);
 #if !JSSO_T_DEEP
     if (has_next2) task_load(A, m2, lane, nn);
 #endif

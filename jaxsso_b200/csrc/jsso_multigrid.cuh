@@ -97,55 +97,6 @@ __global__ void mg_centroid_kernel(int n_c, const int32_t* __restrict__ mem_ptr,
   Xc[3 * (size_t)a] = s0 * inv; Xc[3 * (size_t)a + 1] = s1 * inv; Xc[3 * (size_t)a + 2] = s2 * inv;
 }
 
-// inverse of the diagonal blocks (row-major out, like W); a (near) zero block -> identity
-// (aggregates made of fully prescribed nodes give an empty coarse row/column)
-__global__ void __launch_bounds__(128)
-mg_diag_inverse_kernel(int n, const int32_t* __restrict__ diag_slot, const double* __restrict__ vals,
-                       double* __restrict__ Dinv) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const double* d = vals + (size_t)diag_slot[r] * 36;
-  double M[6][12];
-  double scale = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(d[6 * i + i]));
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      M[i][j] = 0.5 * (d[6 * j + i] + d[6 * i + j]);
-      M[i][6 + j] = (i == j) ? 1.0 : 0.0;
-    }
-  // Gauss-Jordan without pivoting (SPD blocks); tiny pivots -> that row/col becomes identity
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    double p = M[k][k];
-    if (!(fabs(p) > 1e-14 * scale) || scale == 0.0) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) M[k][j] = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) M[i][k] = 0.0;
-      M[k][k] = 1.0; M[k][6 + k] = 1.0;
-      p = 1.0;
-    }
-    const double ip = 1.0 / p;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) M[k][j] *= ip;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      if (i == k) continue;
-      const double f = M[i][k];
-#pragma unroll
-      for (int j = 0; j < 12; ++j) M[i][j] = fma(-f, M[k][j], M[i][j]);
-    }
-  }
-  double* o = Dinv + (size_t)r * 36;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) o[i * 6 + j] = M[i][6 + j];
-}
-
 // P[s] = own(s) T~_i - omega * Dinv_i * sum_k A[a_k] T~_{j_k},  T~ = (Lt) T;  thread per P block
 __global__ void __launch_bounds__(128)
 mg_smooth_prolongator_kernel(int nnz_p, const int32_t* __restrict__ p_row, const int32_t* __restrict__ p_col,
@@ -369,10 +320,6 @@ mg_dot_kernel(long long n, const double* __restrict__ a, const double* __restric
 __global__ void mg_axpby_kernel(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = a * x[i] + b * y[i];
-}
-__global__ void mg_fill_kernel(long long n, double v, double* __restrict__ y) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = v;
 }
 // ---- outer PCG with the scalars kept on the device (slots: MGS_* in jsso_solver.cuh)
 // p = z + (rz / rz_old) p   (first: p = z)
