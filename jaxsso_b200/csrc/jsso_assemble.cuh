@@ -475,6 +475,7 @@ struct TaskArgs {
 
 #ifndef JSSO_T_BULK
 #define JSSO_T_BULK 1      // records staged by 1-D bulk async copies (cp.async.bulk + mbarrier: the TMA unit) instead of per-lane cp.async
+                           // (A/B at 1M quads, profiles/r2_asm_bulk_copy_ab.txt: 1.202 vs 1.220 ms for the assembly stage)
 #endif
 #ifdef JSSO_EMU   // CPU test harness: a synchronous copy (a missing wait is not detected there)
 __device__ inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
