@@ -25,9 +25,11 @@
  *   jsso_create_from_bsr / jsso_set_values_host          the (K_aug, f_aug) -> u_aug solver plugin of
  *                                                       Model.select_solver, JaxSSO/model.py:340-356
  * Without a counterpart in the reference (it has no multi-GPU path, no iterative solver and no profiler
- * hooks): jsso_mg_setup / jsso_mg_aggregate / jsso_mg_pattern_lists (multigrid preconditioner), jsso_set_halo / jsso_p2p_* /
- * jsso_halo_exchange / jsso_nccl_unique_id (partitioned meshes), jsso_gather_rows, jsso_assembly_tasks,
- * jsso_profile* (tests and measurement), and the memory / stream / event helpers at the end of this file.
+ * hooks): jsso_mg_setup / jsso_mg_aggregate / jsso_mg_pattern_lists (multigrid preconditioner), jsso_mg_set_dist /
+ * jsso_mg_set_dist_setup / jsso_mg_p2p_* / jsso_mg_dist_counters (its row-range distribution over several GPUs),
+ * jsso_set_halo / jsso_p2p_* / jsso_halo_exchange / jsso_nccl_unique_id (partitioned meshes), jsso_gather_rows,
+ * jsso_assembly_tasks, jsso_profile* / jsso_profiler_range / jsso_fp64_peak (tests and measurement), and the memory /
+ * stream / event helpers at the end of this file.
  *
  * Conventions
  *   - all floating point is FP64, all indices int32 (model.py:284-313).
@@ -57,7 +59,8 @@ enum {
   JSSO_OK = 0,
   JSSO_ERR_ARG = 1,             /* bad argument / inconsistent mesh */
   JSSO_ERR_CUDA = 2,            /* a CUDA runtime call or kernel failed */
-  JSSO_ERR_NOCONV = 3,          /* PCG hit maxiter before reaching rtol */
+  JSSO_ERR_NOCONV = 3,          /* PCG hit maxiter, or stagnated at its attainable accuracy, before reaching rtol;
+                                   the best iterate is still returned (u, and the gradients computed from it) */
   JSSO_ERR_NAN = 4,             /* NaN/Inf met in the solve */
   JSSO_ERR_BADJAC = 5,          /* non-positive Jacobian determinant in a quad */
   JSSO_ERR_DEGENERATE_BEAM = 6, /* beam exactly parallel to global Y (element.py:92-94) */
@@ -191,7 +194,9 @@ int jsso_get_values_host(jsso_handle* h, double* vals_h);
 int jsso_get_flags(jsso_handle* h, int32_t* flags_out);
 
 /* ---- linear algebra on the assembled matrix ------------------------------------- */
-/* y = K x with the current values (x has 6*n_node entries, y 6*n_row). */
+/* y = K x with the current values (x has 6*n_node entries, y 6*n_row).  A solve scales the stored matrix in place
+ * (block-Jacobi: W K W^T); jsso_spmv and jsso_get_values* keep returning the UNSCALED operator afterwards
+ * (K x = W^-1 (A^ (W^-T x)), blocks unscaled on the fly; single-GPU handles). */
 int jsso_spmv(jsso_handle* h, const double* x_d, double* y_d, void* stream);
 /* Block-Jacobi preconditioned CG on the assembled (BC-imposed) matrix:
  * K x = b with b zeroed at prescribed dofs.  Synchronises `stream`. */
