@@ -227,6 +227,9 @@ typedef struct {
   const int32_t *recv_ptr, *recv_idx; /* [n_peer + 1], node ids the peer owns and this rank's rows read */
   const int32_t *remote_off;          /* [n_peer] or NULL: start of this rank's block in the peer's receive list
                                        * (needed by the peer-memory path only) */
+  int32_t n_ghost;                    /* distributed levels: rows of other ranks that this rank's rows of A_l read */
+  const int32_t *ghost_rows;          /* [n_ghost] sorted; the fused V-cycle recomputes its corrected iterate on them
+                                       * instead of exchanging it (0 / NULL: exchange) */
 } jsso_mg_halo_desc;
 int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int32_t rank, int32_t n_rank, int32_t n_dist,
                      const int32_t* bounds_h, int32_t n_halo, const jsso_mg_halo_desc* halo);

@@ -65,7 +65,8 @@ class MgLevelDesc(C.Structure):
 
 class MgHaloDesc(C.Structure):
     _fields_ = [('n_peer', C.c_int32)] + [(k, C.c_void_p) for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr',
-                                                                      'recv_idx', 'remote_off')]
+                                                                      'recv_idx', 'remote_off')] + \
+               [('n_ghost', C.c_int32), ('ghost_rows', C.c_void_p)]
 
 class MgSetupDesc(C.Structure):
     _fields_ = [('n_p_slots', C.c_int32), ('n_ap_slots', C.c_int32), ('p_slots', C.c_void_p), ('ap_slots', C.c_void_p),
@@ -436,10 +437,11 @@ class Handle:
         keep = []
         for d, lv in zip(descs, mine):
             d.n_peer = int(lv['peer_rank'].shape[0])
-            for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr', 'recv_idx', 'remote_off'):
+            for k in ('peer_rank', 'send_ptr', 'send_idx', 'recv_ptr', 'recv_idx', 'remote_off', 'ghost_rows'):
                 a = np.ascontiguousarray(lv[k], dtype=np.int32)
                 keep.append(a)
                 setattr(d, k, a.ctypes.data)
+            d.n_ghost = int(lv['ghost_rows'].shape[0])
         idb = np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy()
         self._ck(lib().jsso_mg_set_dist(self.h, _ptr(idb), int(rank), int(n_rank), int(n_dist), _ptr(bounds),
                                         len(mine), descs))

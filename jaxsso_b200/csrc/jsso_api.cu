@@ -215,6 +215,8 @@ struct jsso_handle {
     std::vector<MgDistPeer> peers;
     int32_t *send_idx = nullptr, *recv_idx = nullptr;   // device: node ids of this level
     int n_send = 0, n_recv = 0;
+    int32_t* ghost_rows = nullptr;                      // device: rows of other ranks this rank's rows of A_l read
+    int n_ghost = 0;
     std::vector<int32_t> remote_off;                    // where my block starts in each peer's receive list (nodes)
     MgdLevelDev* dev = nullptr;                         // device copy for the peer-memory kernels
     unsigned long long seq = 0;                         // exchange counter of this level
@@ -497,7 +499,7 @@ void jsso_destroy(jsso_handle* h) {
     for (void* p : mgp) if (p) cudaFree(p);
     if (h->mg_scal_host) cudaFreeHost(h->mg_scal_host);
   }
-  for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); }
+  for (auto& dl : h->mgd.lv) { if (dl.send_idx) cudaFree(dl.send_idx); if (dl.recv_idx) cudaFree(dl.recv_idx); if (dl.ghost_rows) cudaFree(dl.ghost_rows); }
   for (auto& dl : h->mgd.lv) if (dl.dev) cudaFree(dl.dev);
   for (void* p : h->mgd.ipc_opened) cudaIpcCloseMemHandle(p);
   { void* pp[] = {h->mgd.mbox, h->mgd.arena, h->mgd.ctx, h->mgd.push_counter, h->mgd.red_seq_dev}; for (void* p : pp) if (p) cudaFree(p); }
@@ -1239,6 +1241,12 @@ extern "C" int jsso_mg_set_dist(jsso_handle* h, const uint8_t nccl_id[128], int3
     for (int v : si) if (v < lo || v >= hi) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: send index not owned");
     for (int v : ri) if (v < 0 || v >= n_l || (v >= lo && v < hi)) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad receive index");
     CK(upload(&L.send_idx, si)); CK(upload(&L.recv_idx, ri));
+    if (l < n_dist && d.n_ghost > 0 && d.ghost_rows) {
+      std::vector<int32_t> gr(d.ghost_rows, d.ghost_rows + d.n_ghost);
+      for (int v : gr) if (v < 0 || v >= n_l || (v >= lo && v < hi)) return fail(h, JSSO_ERR_ARG, "jsso_mg_set_dist: bad ghost row");
+      CK(upload(&L.ghost_rows, gr));
+      L.n_ghost = d.n_ghost;
+    }
     max_send = std::max(max_send, (size_t)L.n_send); max_recv = std::max(max_recv, (size_t)L.n_recv);
     D.lv.push_back(L);
   }
@@ -2060,8 +2068,21 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
     }
     CKL("prolongation");
   }
+  // the ghost entries of x1 that the post-smoother gathers: recomputed from local data (b on the ghost rows arrived
+  // with the exchange of b, x_c on their coarse columns with the exchange of x_c / the replicated coarse solve) --
+  // one synchronisation point fewer than exchanging them
+  bool ghosts_done = false;
+  if (dist && h->mg_fp32 && m.P32 && JSSO_MG_RP && h->mgd.lv[l].n_ghost > 0 && h->mgd.lv[l].ghost_rows) {
+    const jsso_handle::MgDistLevel& DL = h->mgd.lv[l];
+    bsr_spmv_rp_kernel<float, 0><<<rp_grid(h, DL.n_ghost), RED_BLOCK, 0, st>>>(DL.n_ghost, m.p_rowptr, m.p_col, m.P32, xc, m.d, b,
+                                                                              nullptr, it, 0.0, 1.0, h->mg_scal, h->partials,
+                                                                              h->counters + 2, nullptr, nullptr, nullptr,
+                                                                              DL.ghost_rows);
+    CKL("prolongation (ghost rows)");
+    ghosts_done = true;
+  }
   h->probe.mark("K3_prolong", l, st);
-  if (dist) { if ((rc = mgd_exchange(h, l, m.d, st))) return rc; h->probe.mark("xch_x1", l, st); }
+  if (dist && !ghosts_done) { if ((rc = mgd_exchange(h, l, m.d, st))) return rc; h->probe.mark("xch_x1", l, st); }
   if (want_dot) rc = mg_lin_level<1>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, mgs_dot_target(h, MGS_RZ), st);
   else rc = mg_lin_level<0>(h, l, s, n, m.d, x + off, b + off, m.d + off, it, 1.0, -it, nullptr, st);
   h->probe.mark(want_dot ? "K4_post_rz" : "K4_post", l, st);

@@ -762,12 +762,14 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
                    const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                    const double* __restrict__ bvec, const double* __restrict__ xrow, double ca, double cb, double cc,
                    const double* stop, double* partials, unsigned* counter, double* dot_out,
-                   const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr) {
+                   const MgdCtx* rctx = nullptr, unsigned long long* rseq = nullptr,
+                   const int32_t* __restrict__ row_list = nullptr /* n_row row ids (then rowptr, y, bvec, xrow are un-offset) */) {
   if (mgs_stopped(stop)) return;
   double dot = 0.0;
   const long long n_item = 3LL * n_row;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_item; t += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
+    const int ri = (int)(t / 3), sub = (int)(t - 3LL * ri);
+    const int r = row_list ? row_list[ri] : ri;
     const int b0 = rowptr[r], b1 = rowptr[r + 1];
     const size_t o = 6 * (size_t)r + 2 * sub;
     // the epilogue's operands are requested now, their latency hides behind the block loop
@@ -994,9 +996,12 @@ mgd_exchange_kernel(const MgdCtx* c, const MgdLevelDev* L, int level, const int3
   for (int pi = 0; pi < L->n_peer; ++pi)
     mgd_gather_pieces(c->arena[L->peer_rank[pi]] + slot + 6 * (long long)L->remote_off[pi], v, send_idx + L->send_off[pi],
                       L->send_cnt[pi], threadIdx.x, blockDim.x);
-  __threadfence_system();
+  // block barrier, then the flag threads fence system-wide and release: the barrier makes every thread's stores
+  // observed by them, the fence / release is cumulative over what its thread has observed (PTX memory model) -- the
+  // same pattern as mgd_push_kernel, and one fence per peer instead of one per thread on the critical path
   __syncthreads();
   if ((int)threadIdx.x < L->n_peer) {
+    __threadfence_system();
     st_release_sys(&c->mbox[L->peer_rank[threadIdx.x]]->halo[level][c->rank], seq);
     const MgdMailbox* m = c->mbox[c->rank];
     while (ld_acquire_sys(&m->halo[level][L->peer_rank[threadIdx.x]]) < seq) { }

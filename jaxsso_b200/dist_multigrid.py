@@ -145,13 +145,16 @@ def _cols_of_rows(rowptr, col, s, e):
     return col[rowptr[s]:rowptr[e]]
 
 
-def level_halo(patterns, bounds):
+def level_halo(patterns, bounds, extra=None):
     """need[r][s] = sorted node ids of this level that rank r reads and rank s owns (r != s).
-    `patterns`: list of (rowptr, col, row_bounds) whose rows [row_bounds[r], row_bounds[r+1]) rank r computes."""
+    `patterns`: list of (rowptr, col, row_bounds) whose rows [row_bounds[r], row_bounds[r+1]) rank r computes;
+    `extra[r]`: further ids rank r reads (columns of rows it recomputes as ghost rows)."""
     n_rank = bounds.shape[0] - 1
     need = [[np.zeros(0, np.int32) for _ in range(n_rank)] for _ in range(n_rank)]
     for r in range(n_rank):
         cols = [_cols_of_rows(rp, ci, int(rb[r]), int(rb[r + 1])) for rp, ci, rb in patterns]
+        if extra is not None:
+            cols.append(np.asarray(extra[r]))
         ids = np.unique(np.concatenate(cols)) if cols else np.zeros(0, np.int32)
         ids = ids[(ids < bounds[r]) | (ids >= bounds[r + 1])]
         cut = np.searchsorted(ids, bounds)
@@ -176,21 +179,38 @@ def build_plan(rowptr, colidx, levels, fine_bounds, min_dist_nodes=20000, max_di
     bounds = [fine_bounds]
     for l in range(n_dist):
         bounds.append(coarse_bounds(levels[l], bounds[l]))
+    n_rank_ = fine_bounds.shape[0] - 1
+    # ghost rows of level l: the rows other ranks own whose entries this rank's rows of A_l read.  The corrected
+    # iterate x1 = b / theta + P x_c of the fused V-cycle is RECOMPUTED on them (b is there after its exchange, the
+    # prolongator rows are local data) instead of being exchanged: one synchronisation point fewer per level and
+    # V-cycle, for a slightly larger exchange of x_c (the coarse columns of the ghost rows' prolongator)
+    ghost = []
+    for l in range(n_dist):
+        a_rp, a_ci = (rowptr, colidx) if l == 0 else (levels[l - 1]['c_rowptr'], levels[l - 1]['c_col'])
+        gl = []
+        for r in range(n_rank_):
+            s_, e_ = int(bounds[l][r]), int(bounds[l][r + 1])
+            ids = np.unique(a_ci[a_rp[s_]:a_rp[e_]]) if e_ > s_ else np.zeros(0, np.int32)
+            gl.append(ids[(ids < s_) | (ids >= e_)].astype(np.int32))
+        ghost.append(gl)
     need = []
     for l in range(n_dist):
         a_rp, a_ci = (rowptr, colidx) if l == 0 else (levels[l - 1]['c_rowptr'], levels[l - 1]['c_col'])
         pats = [(a_rp, a_ci, bounds[l]),                                              # A_l x, rows of level l
                 (levels[l]['pt_rowptr'], levels[l]['pt_col'], bounds[l + 1])]        # P_l^T r, rows of level l+1
+        extra = None
         if l >= 1:
             pats.append((levels[l - 1]['p_rowptr'], levels[l - 1]['p_col'], bounds[l - 1]))   # P_{l-1} x_l
-        need.append(level_halo(pats, bounds[l]))
+            pl = levels[l - 1]                                                        # ... and on the ghost rows of level l-1
+            extra = [pl['p_col'][_concat_ranges(pl['p_rowptr'], ghost[l - 1][r])] for r in range(n_rank_)]
+        need.append(level_halo(pats, bounds[l], extra))
     # the first replicated level: its restricted right-hand side is all-gathered once per V-cycle; as an exchange
     # plan "every rank needs every other rank's whole range" it runs over the same peer-memory push / wait kernels
     n_rank = fine_bounds.shape[0] - 1
     gb = bounds[n_dist]
     gather = [[(np.arange(gb[s], gb[s + 1], dtype=np.int32) if s != r else np.zeros(0, np.int32)) for s in range(n_rank)]
               for r in range(n_rank)]
-    return dict(n_dist=n_dist, n_rank=n_rank, bounds=bounds, need=need, gather=gather)
+    return dict(n_dist=n_dist, n_rank=n_rank, bounds=bounds, need=need, gather=gather, ghost=ghost)
 
 
 def rank_plan(plan, rank):
@@ -207,7 +227,10 @@ def rank_plan(plan, rank):
         # peer-memory path: where my block starts in each peer's receive list (its peers in ascending rank order)
         remote_off = [int(sum(need[s][q].size for q in range(rank) if q != s)) for s in peers]
         out.append(dict(peer_rank=np.array(peers, np.int32), send_ptr=ptr(send), send_idx=cat(send),
-                        recv_ptr=ptr(recv), recv_idx=cat(recv), remote_off=np.array(remote_off, np.int32)))
+                        recv_ptr=ptr(recv), recv_idx=cat(recv), remote_off=np.array(remote_off, np.int32),
+                        ghost_rows=np.zeros(0, np.int32)))
+    for l, gl in enumerate(plan.get('ghost') or []):
+        out[l]['ghost_rows'] = np.ascontiguousarray(gl[rank], np.int32)
     return out
 
 
@@ -220,6 +243,14 @@ def _concat_ranges(ptr, ids):
         return np.zeros(0, np.int64)
     start = np.repeat(ptr[ids].astype(np.int64), cnt)
     return start + (np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+
+
+def _slot_hull(ptr, s, e, extra_rows):
+    lo, hi = int(ptr[s]), int(ptr[e])
+    if len(extra_rows):
+        lo = min(lo, int(ptr[int(np.min(extra_rows))]))
+        hi = max(hi, int(ptr[int(np.max(extra_rows)) + 1]))
+    return lo, hi
 
 
 def setup_plan(rowptr, colidx, levels, plan, rank, drop_ghost=False):
@@ -248,13 +279,15 @@ def setup_plan(rowptr, colidx, levels, plan, rank, drop_ghost=False):
         p_slots = np.unique(np.concatenate([
             lv['cl_p'][terms].astype(np.int64), lv['apl_p'][ap_terms].astype(np.int64),
             lv['pt_src'][lv['pt_rowptr'][cs]:lv['pt_rowptr'][ce]].astype(np.int64),
-            np.arange(lv['p_rowptr'][fs], lv['p_rowptr'][fe], dtype=np.int64)]))
+            np.arange(lv['p_rowptr'][fs], lv['p_rowptr'][fe], dtype=np.int64),
+            _concat_ranges(lv['p_rowptr'], (plan.get('ghost') or [[np.zeros(0, np.int32)] * plan['n_rank']] * n_dist)[l][rank])]))
         if drop_ghost and l == 0 and rank == 0:     # test hook: a ghost block missing from the plan must be noticed
             ghost = p_slots[p_slots >= lv['p_rowptr'][fe]]
             p_slots = np.setdiff1d(p_slots, ghost[-1:])
         ac_bounds = lv['c_rowptr'][plan['bounds'][l + 1]].astype(np.int32)
         d = dict(p_slots=p_slots.astype(np.int32), ap_slots=ap_slots.astype(np.int32), ac_bounds=ac_bounds,
-                 p_own=(int(lv['p_rowptr'][fs]), int(lv['p_rowptr'][fe])),
+                 # slot hull of the prolongation rows this rank applies (own rows + ghost rows): the FP32 copy
+                 p_own=_slot_hull(lv['p_rowptr'], fs, fe, (plan.get('ghost') or [[np.zeros(0, np.int32)] * plan['n_rank']] * n_dist)[l][rank]),
                  pt_own=(int(lv['pt_rowptr'][cs]), int(lv['pt_rowptr'][ce])))
         if l == 0:
             n_f = lv['n_f']
