@@ -201,6 +201,15 @@ struct jsso_handle {
   int mg_graph_level = -1, mg_graph_deg = 0;
   const double* mg_graph_b = nullptr;
   double* mg_graph_x = nullptr;
+  // the same part as ONE cooperative kernel (mg_tail_kernel; default when the device supports cooperative launches,
+  // JSSO_MG_TAIL=0 keeps the graph): the plan is rebuilt with every numeric setup
+  bool mg_tail = true;
+  int tail_blocks = 0;             // co-resident blocks of mg_tail_kernel (0: unsupported)
+  MgTailPlan* mg_tail_dev = nullptr;
+  MgTailPlan mg_tail_host;
+  int mg_tail_level = -1, mg_tail_grid = 0;
+  const double* mg_tail_b = nullptr;
+  double* mg_tail_x = nullptr;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -370,6 +379,13 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_persistent_kernel, RED_BLOCK, 0));
     h->coop_blocks = coop ? std::min(RED_MAX_BLOCKS, occ * prop.multiProcessorCount) : 0;
+    occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mg_tail_kernel, RED_BLOCK, 0));
+    h->tail_blocks = coop ? occ * prop.multiProcessorCount : 0;
+    if (const char* e = std::getenv("JSSO_MG_TAIL_BLOCKS")) h->tail_blocks = std::max(0, std::min(h->tail_blocks, std::atoi(e)));
+#ifdef JSSO_EMU   // CPU test harness: grid.sync() exists for a one-CTA grid only; opt-in so that the graph path stays covered
+    if (std::getenv("EMU_TAIL_KERNEL")) h->tail_blocks = 1;
+#endif
   }
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
@@ -483,6 +499,7 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_c) cudaStreamDestroy(h->st_c);
   if (h->mg_graph_exec) cudaGraphExecDestroy(h->mg_graph_exec);
   if (h->st_cap) cudaStreamDestroy(h->st_cap);
+  if (h->mg_tail_dev) cudaFree(h->mg_tail_dev);
   for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_adj) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
@@ -1179,6 +1196,8 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
       if (h->mg_power_iters >= 30) h->mg_power_safety = 1.15;
     }
     if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] != '0';   // A/B switch (default on)
+    if (!h->mg_graph) h->mg_tail = false;                                            // JSSO_MG_GRAPH=0: kernel by kernel
+    if (const char* eg = std::getenv("JSSO_MG_TAIL")) h->mg_tail = eg[0] != '0';     // A/B switch (default on)
     // binary16 storage of the fine-level V-cycle matrix (the block-Jacobi-scaled matrix has unit diagonal blocks and
     // |entries| <= 1); JSSO_MG_FP16=0 keeps FP32 (A/B switch)
     const char* e16 = std::getenv("JSSO_MG_FP16");
@@ -1539,6 +1558,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_ready) return JSSO_OK;
   PhaseTimer pt_(st, h->mgd.rank);
   if (h->mg_graph_exec) { cudaGraphExecDestroy(h->mg_graph_exec); h->mg_graph_exec = nullptr; }   // coefficients change
+  h->mg_tail_level = -1;
   if (!h->last_crds) return fail(h, JSSO_ERR_STATE, "multigrid needs the coordinates of the last jsso_assemble");
   const int nl = (int)h->mg.size();
   const double* X = h->last_crds;
@@ -2092,7 +2112,71 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
 // The part of the fused V-cycle that is the same on every rank and launch-latency bound -- the coarse levels on one
 // GPU (l = 1), the replicated levels of the distributed solve (l = n_dist) -- as ONE graph launch: captured once per
 // numeric setup on a private stream (the smoother coefficients are kernel arguments), replayed into the caller's.
+// The list of products of the fused V-cycle from level l down and up again, for mg_tail_kernel.  False when a level
+// does not have the FP32 storage the kernel reads or the list does not fit.
+static bool mg_tail_ops(jsso_handle* h, int l, double* b, double* x, MgTailPlan& T, int& need_blocks) {
+  const int nl = (int)h->mg.size();
+  auto push = [&](const MgTailOp& o) {
+    if (T.n_ops >= MG_TAIL_MAX_OPS) return false;
+    T.op[T.n_ops++] = o;
+    const long long want = (o.kind == 0) ? cdiv(3LL * o.n_row, RED_BLOCK) : cdiv((long long)o.n_row, RED_BLOCK / 32);
+    need_blocks = (int)std::max<long long>(need_blocks, std::min<long long>(want, 1 << 20));
+    return true;
+  };
+  if (l == nl) {
+    MgTailOp o{};
+    o.kind = 1; o.n_row = 6 * mg_matrix(h, nl).n; o.xrow = h->mg_dense; o.x = b; o.y = x;
+    return push(o);
+  }
+  jsso_handle::MgLevel& m = h->mg[l];
+  const MgMat A = mg_matrix(h, l);
+  if (!A.v32 || !m.P32 || !m.Pt32) return false;
+  const double it = 1.0 / (0.625 * m.lam);
+  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
+  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
+  auto product = [&](const int32_t* rp, const int32_t* ci, const float* v, int n_row, long long nnz, const double* xin, double* y,
+                     const double* bvec, const double* xrow, double ca, double cb, double cc) {
+    MgTailOp o{};
+    o.rp = rp; o.ci = ci; o.v = v; o.x = xin; o.y = y; o.bvec = bvec; o.xrow = xrow; o.ca = ca; o.cb = cb; o.cc = cc;
+    o.n_row = n_row;
+    o.kind = ((double)nnz <= 12.0 * std::max(n_row, 1) && n_row >= 4096) ? 0 : 2;   // as mg_lin_level / mg_spmv_p choose
+    return push(o);
+  };
+  if (!product(A.rp, A.ci, A.v32, m.n_f, A.nnz, b, m.r, b, nullptr, 1.0, 0.0, -it)) return false;          // r0 = b - A b / theta
+  if (!product(m.pt_rowptr, m.pt_col, m.Pt32, m.n_c, m.nnz_p, m.r, bc, nullptr, nullptr, 0.0, 0.0, 1.0)) return false;   // b_c = P^T r0
+  if (!mg_tail_ops(h, l + 1, bc, xc, T, need_blocks)) return false;
+  if (!product(m.p_rowptr, m.p_col, m.P32, m.n_f, m.nnz_p, xc, m.d, b, nullptr, it, 0.0, 1.0)) return false;   // x1 = b / theta + P x_c
+  return product(A.rp, A.ci, A.v32, m.n_f, A.nnz, m.d, x, b, m.d, it, 1.0, -it);                             // x = x1 + (b - A x1) / theta
+}
+
 static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st) {
+  if (h->mg_tail && h->mg_fp32 && h->tail_blocks > 0) {
+    if (h->mg_tail_level != l || h->mg_tail_b != b || h->mg_tail_x != x) {
+      h->mg_tail_level = -2;                            // -2: this hierarchy cannot take the kernel (graph below)
+      MgTailPlan& T = h->mg_tail_host;
+      T.n_ops = 0; T.pad = 0;
+      int need = 1;
+      if (mg_tail_ops(h, l, b, x, T, need)) {
+        if (!h->mg_tail_dev) CK(cudaMalloc(&h->mg_tail_dev, sizeof(MgTailPlan)));
+        CK(cudaMemcpyAsync(h->mg_tail_dev, &T, sizeof(MgTailPlan), cudaMemcpyHostToDevice, st));
+        h->mg_tail_level = l; h->mg_tail_grid = std::max(1, std::min(h->tail_blocks, need));
+      }
+      h->mg_tail_b = b; h->mg_tail_x = x;
+    }
+    if (h->mg_tail_level == l) {
+      const MgTailPlan* plan = h->mg_tail_dev;
+      const double* stop = h->mg_scal;
+      void* args[] = {(void*)&plan, (void*)&stop};
+#ifdef JSSO_EMU
+      (void)args;
+      mg_tail_kernel<<<1, RED_BLOCK, 0, st>>>(plan, stop);
+#else
+      CK(cudaLaunchCooperativeKernel((void*)mg_tail_kernel, dim3(h->mg_tail_grid), dim3(RED_BLOCK), args, 0, st));
+#endif
+      LAUNCHED();
+      return JSSO_OK;
+    }
+  }
   if (!h->mg_graph) return mg_vcycle_fused_level(h, l, b, x, false, st);
   if (h->mg_graph_exec && (h->mg_graph_level != l || h->mg_graph_b != b || h->mg_graph_x != x || h->mg_graph_deg != -1)) {
     cudaGraphExecDestroy(h->mg_graph_exec);

@@ -756,6 +756,34 @@ __device__ inline void rp_fma(const float (&f)[12], const double2 x0, const doub
   acc0 = fma((double)f[8], x2.x, acc0); acc1 = fma((double)f[9], x2.x, acc1);
   acc0 = fma((double)f[10], x2.y, acc0); acc1 = fma((double)f[11], x2.y, acc1);
 }
+// rows (2 sub, 2 sub + 1) of block row [b0, b1) times x: two blocks issued per round
+template <class VT>
+__device__ inline void rp_row_pair(int b0, int b1, int sub, const int32_t* __restrict__ colidx, const VT* __restrict__ vals,
+                                   const double* __restrict__ x, double& acc0, double& acc1) {
+  int k = b0;
+  for (; k + 1 < b1; k += 2) {
+    const int c0 = colidx[k], c1 = colidx[k + 1];
+    const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub), rb = RpLoad<VT>::ld(vals, (size_t)k + 1, sub);
+    const double2* xa = (const double2*)(x + 6 * (size_t)c0);
+    const double2* xb = (const double2*)(x + 6 * (size_t)c1);
+    const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2], xb0 = xb[0], xb1 = xb[1], xb2 = xb[2];
+    float f[12];
+    RpLoad<VT>::unpack(ra, f);
+    rp_fma(f, xa0, xa1, xa2, acc0, acc1);
+    RpLoad<VT>::unpack(rb, f);
+    rp_fma(f, xb0, xb1, xb2, acc0, acc1);
+  }
+  if (k < b1) {
+    const int c0 = colidx[k];
+    const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub);
+    const double2* xa = (const double2*)(x + 6 * (size_t)c0);
+    const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2];
+    float f[12];
+    RpLoad<VT>::unpack(ra, f);
+    rp_fma(f, xa0, xa1, xa2, acc0, acc1);
+  }
+}
+
 template <class VT, int DOT>
 __global__ void __launch_bounds__(RED_BLOCK, 3)
 bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
@@ -777,28 +805,7 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
     if (bvec) bv = *(const double2*)(bvec + o);
     if (xrow) xv = *(const double2*)(xrow + o);
     double acc0 = 0.0, acc1 = 0.0;
-    int k = b0;
-    for (; k + 1 < b1; k += 2) {
-      const int c0 = colidx[k], c1 = colidx[k + 1];
-      const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub), rb = RpLoad<VT>::ld(vals, (size_t)k + 1, sub);
-      const double2* xa = (const double2*)(x + 6 * (size_t)c0);
-      const double2* xb = (const double2*)(x + 6 * (size_t)c1);
-      const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2], xb0 = xb[0], xb1 = xb[1], xb2 = xb[2];
-      float f[12];
-      RpLoad<VT>::unpack(ra, f);
-      rp_fma(f, xa0, xa1, xa2, acc0, acc1);
-      RpLoad<VT>::unpack(rb, f);
-      rp_fma(f, xb0, xb1, xb2, acc0, acc1);
-    }
-    if (k < b1) {
-      const int c0 = colidx[k];
-      const typename RpLoad<VT>::Raw ra = RpLoad<VT>::ld(vals, (size_t)k, sub);
-      const double2* xa = (const double2*)(x + 6 * (size_t)c0);
-      const double2 xa0 = xa[0], xa1 = xa[1], xa2 = xa[2];
-      float f[12];
-      RpLoad<VT>::unpack(ra, f);
-      rp_fma(f, xa0, xa1, xa2, acc0, acc1);
-    }
+    rp_row_pair(b0, b1, sub, colidx, vals, x, acc0, acc1);
     double2 v = make_double2(cc * acc0, cc * acc1);
     if (bvec) { v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
     if (xrow) { v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
@@ -809,6 +816,74 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   if (DOT != 0) {
     double total;
     if (grid_sum(dot, partials, counter, total)) mgs_store_dot_block(total, dot_out, rctx, rseq);
+  }
+}
+
+// ---- the coarse tail of the fused V-cycle as ONE persistent kernel ------------------------------------------------
+// The levels below the last bandwidth-bound one (levels >= 1 on one GPU, the replicated levels of the distributed solve)
+// are 4 products per level on a few thousand rows: as separate kernels -- even replayed from a CUDA graph -- each costs
+// a launch gap and a ramp (13 kernels = 91 us at 1M quads).  Here one cooperative grid runs the whole list of products,
+// separated by grid-wide barriers: `plan->op[i]` is  y = ca b + cb x_row + cc A x  on FP32 row-pair-major blocks with one
+// thread per (row, row pair) (kind 0) or one warp per row (kind 2: long rows, small levels), or the dense coarsest
+// solve  y = M x  (kind 1: warp per row of the stored inverse).
+constexpr int MG_TAIL_MAX_OPS = 41;
+struct MgTailOp {
+  const int32_t* rp; const int32_t* ci; const float* v;
+  const double* x; double* y; const double* bvec; const double* xrow;   // kind 1: xrow = dense [A | A^-1], row-major
+  double ca, cb, cc;
+  int n_row, kind;
+};
+struct MgTailPlan { int n_ops, pad; MgTailOp op[MG_TAIL_MAX_OPS]; };
+
+__global__ void __launch_bounds__(RED_BLOCK)
+mg_tail_kernel(const MgTailPlan* __restrict__ plan, const double* stop) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  if (mgs_stopped(stop)) return;                       // the same decision in every block: nobody reaches a barrier
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  const int n_ops = plan->n_ops;
+  for (int i = 0; i < n_ops; ++i) {
+    const MgTailOp& o = plan->op[i];
+    if (o.kind == 0) {
+      const long long n_item = 3LL * o.n_row;
+      for (long long t = tid; t < n_item; t += nthr) {
+        const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
+        const size_t off = 6 * (size_t)r + 2 * sub;
+        double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+        if (o.bvec) bv = *(const double2*)(o.bvec + off);
+        if (o.xrow) xv = *(const double2*)(o.xrow + off);
+        double acc0 = 0.0, acc1 = 0.0;
+        rp_row_pair(o.rp[r], o.rp[r + 1], sub, o.ci, o.v, o.x, acc0, acc1);
+        *(double2*)(o.y + off) = make_double2(fma(o.ca, bv.x, fma(o.cb, xv.x, o.cc * acc0)),
+                                              fma(o.ca, bv.y, fma(o.cb, xv.y, o.cc * acc1)));
+      }
+    } else if (o.kind == 2) {
+      const int lane = threadIdx.x & 31;
+      const double* bvec = o.bvec;
+      const double* xrow = o.xrow;
+      double* y = o.y;
+      const double ca = o.ca, cb = o.cb, cc = o.cc;
+      auto epilogue = [=](int r, double u0, double u1) -> double {
+        if (lane < 3) {
+          const size_t off = 6 * (size_t)r + 2 * lane;
+          double2 v = make_double2(cc * u0, cc * u1);
+          if (bvec) { const double2 bv = *(const double2*)(bvec + off); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
+          if (xrow) { const double2 xv = *(const double2*)(xrow + off); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
+          *(double2*)(y + off) = v;
+        }
+        return 0.0;
+      };
+      bsr_rows_pipelined((int)(tid >> 5), (int)(nthr >> 5), lane, o.n_row, o.rp, o.ci, o.v, o.x, epilogue);
+    } else {
+      const int n = o.n_row, lane = threadIdx.x & 31;
+      for (long long row = tid >> 5; row < n; row += nthr >> 5) {
+        const double* a = o.xrow + (size_t)row * 2 * n + n;
+        double sum = 0.0;
+        for (int j = lane; j < n; j += 32) sum = fma(a[j], o.x[j], sum);
+        sum = warp_sum(sum);
+        if (lane == 0) o.y[row] = sum;
+      }
+    }
+    grid.sync();
   }
 }
 

@@ -211,3 +211,35 @@ def test_fp16_fine_level_keeps_the_iteration_count(monkeypatch):
     assert res['fp16'][2] and res['fp32'][2]
     assert abs(res['fp16'][1] - res['fp32'][1]) <= 2
     assert np.linalg.norm(res['fp16'][0] - res['fp32'][0]) <= 1e-8 * np.linalg.norm(res['fp32'][0])
+
+
+@pytest.mark.gpu
+def test_coarse_tail_kernel_equals_the_graph_of_kernels(monkeypatch):
+    """The coarse levels of the fused V-cycle run as ONE cooperative kernel (mg_tail_kernel: a device-resident list of
+    products with grid barriers in between); JSSO_MG_TAIL=0 replays the same products as a CUDA graph of separate
+    kernels, JSSO_MG_GRAPH=0 launches them one by one.  Same iteration count, u equal to rounding, fewer launches;
+    a second solve on the same handle after a re-assembly (plan rebuilt) converges the same way."""
+    from jaxsso_b200 import _native as nat
+    md = meshes.plate(128)        # level 1 has > 4096 rows: both the row-pair and the warp-per-row form are on the list
+    D = nat.DeviceArray
+    res = {}
+    for tag, env in (('tail', {}), ('graph', {'JSSO_MG_TAIL': '0'}), ('kernels', {'JSSO_MG_GRAPH': '0'})):
+        for k in ('JSSO_MG_TAIL', 'JSSO_MG_GRAPH'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+        h.mg_setup(max_coarse_nodes=100)
+        crds, pq, pb, f = D.from_host(md.crds), D.from_host(md.prop_quads), D.from_host(md.prop_beams), D.from_host(md.loads)
+        u = D((md.ndof,))
+        opts = nat.make_opts(rtol=1e-10, precond='multigrid', cheb_degree=1)
+        h.forward(crds, pq, pb, f, u, opts=opts)
+        l0 = int(nat.lib().jsso_launch_count())
+        st = h.forward(crds, pq, pb, f, u, opts=opts)
+        res[tag] = (u.download(), st.iterations, st.converged, int(nat.lib().jsso_launch_count()) - l0)
+        h.close()
+    assert all(r[2] for r in res.values())
+    assert res['tail'][1] == res['graph'][1] == res['kernels'][1]
+    for tag in ('graph', 'kernels'):
+        assert np.linalg.norm(res['tail'][0] - res[tag][0]) <= 1e-10 * np.linalg.norm(res[tag][0])
+    assert res['tail'][3] == res['graph'][3] < res['kernels'][3] - 3 * res['tail'][1]
