@@ -205,6 +205,9 @@ struct jsso_handle {
   // JSSO_MG_TAIL=0 keeps the graph): the plan is rebuilt with every numeric setup
   bool mg_tail = true;
   int tail_blocks = 0;             // co-resident blocks of mg_tail_kernel (0: unsupported)
+  int tail_rows = 32768;           // one GPU: the kernel takes the levels from the first one with at most this many block rows
+                                   // (measured at 1M quads: level 1, 117k rows, is bandwidth bound and loses in a 3-CTA/SM
+                                   // cooperative grid -- 305 us for levels >= 1 against 188 us as separate kernels)
   MgTailPlan* mg_tail_dev = nullptr;
   MgTailPlan mg_tail_host;
   int mg_tail_level = -1, mg_tail_grid = 0;
@@ -1198,6 +1201,7 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] != '0';   // A/B switch (default on)
     if (!h->mg_graph) h->mg_tail = false;                                            // JSSO_MG_GRAPH=0: kernel by kernel
     if (const char* eg = std::getenv("JSSO_MG_TAIL")) h->mg_tail = eg[0] != '0';     // A/B switch (default on)
+    if (const char* er = std::getenv("JSSO_MG_TAIL_ROWS")) h->tail_rows = std::max(0, std::atoi(er));
     // binary16 storage of the fine-level V-cycle matrix (the block-Jacobi-scaled matrix has unit diagonal blocks and
     // |entries| <= 1); JSSO_MG_FP16=0 keeps FP32 (A/B switch)
     const char* e16 = std::getenv("JSSO_MG_FP16");
@@ -2040,6 +2044,17 @@ static int mg_lin_level(jsso_handle* h, int l, int s, int n, const double* x, do
 // i.e. 4 launches and ~9 vector passes per level instead of 8 launches and ~20.  On several GPUs the levels
 // l < n_dist work on this rank's rows, with a halo exchange before every product that gathers a vector other ranks
 // have just written; b / x are full-length level vectors.
+// First level of the part of the V-cycle that goes out as ONE launch (cooperative kernel or graph): the replicated levels
+// of the distributed solve; on one GPU the levels small enough to be launch bound when the cooperative kernel takes
+// them, else everything below the fine level (graph).
+static int mg_one_launch_from(jsso_handle* h) {
+  if (h->mgd.n_rank > 1) return h->mgd.n_dist;
+  const int nl = (int)h->mg.size();
+  if (!(h->mg_tail && h->mg_fp32 && h->tail_blocks > 0)) return 1;
+  for (int l = 1; l <= nl; ++l) if (mg_matrix(h, l).n <= h->tail_rows) return l;
+  return nl;
+}
+
 static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bool want_dot, cudaStream_t st) {
   const int nl = (int)h->mg.size();
   int rc;
@@ -2066,10 +2081,11 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
   h->probe.mark("K2_restrict", l, st);
   if (dist && l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; h->probe.mark("allgather", l + 1, st); }
   // the levels below are the same on every rank (replicated tail of the distributed solve / coarse levels of one GPU)
-  if ((h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0)) rc = mg_coarse_graphed(h, l + 1, bc, xc, st);
+  const bool one_launch = (l + 1 == mg_one_launch_from(h));
+  if (one_launch) rc = mg_coarse_graphed(h, l + 1, bc, xc, st);
   else rc = mg_vcycle_fused_level(h, l + 1, bc, xc, false, st);
   if (rc) return rc;
-  if ((h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0)) h->probe.mark("coarse_tail_graph", l + 1, st);
+  if (one_launch) h->probe.mark("coarse_tail", l + 1, st);
   if (dist && l + 1 < h->mgd.n_dist) { if ((rc = mgd_exchange(h, l + 1, xc, st))) return rc; h->probe.mark("xch_xc", l + 1, st); }
   // x1 = b / theta + P x_c into m.d
   if (n > 0) {

@@ -220,7 +220,7 @@ def test_coarse_tail_kernel_equals_the_graph_of_kernels(monkeypatch):
     kernels, JSSO_MG_GRAPH=0 launches them one by one.  Same iteration count, u equal to rounding, fewer launches;
     a second solve on the same handle after a re-assembly (plan rebuilt) converges the same way."""
     from jaxsso_b200 import _native as nat
-    md = meshes.plate(128)        # level 1 has > 4096 rows: both the row-pair and the warp-per-row form are on the list
+    md = meshes.plate(256)        # level 1 has ~7 300 rows of 9 blocks: both the row-pair and the warp-per-row form are on the list
     D = nat.DeviceArray
     res = {}
     for tag, env in (('tail', {}), ('graph', {'JSSO_MG_TAIL': '0'}), ('kernels', {'JSSO_MG_GRAPH': '0'})):
