@@ -201,18 +201,6 @@ struct jsso_handle {
   int mg_graph_level = -1, mg_graph_deg = 0;
   const double* mg_graph_b = nullptr;
   double* mg_graph_x = nullptr;
-  // the same part as ONE cooperative kernel (mg_tail_kernel; default when the device supports cooperative launches,
-  // JSSO_MG_TAIL=0 keeps the graph): the plan is rebuilt with every numeric setup
-  bool mg_tail = true;
-  int tail_blocks = 0;             // co-resident blocks of mg_tail_kernel (0: unsupported)
-  int tail_rows = 32768;           // one GPU: the kernel takes the levels from the first one with at most this many block rows
-                                   // (measured at 1M quads: level 1, 117k rows, is bandwidth bound and loses in a 3-CTA/SM
-                                   // cooperative grid -- 305 us for levels >= 1 against 188 us as separate kernels)
-  MgTailPlan* mg_tail_dev = nullptr;
-  MgTailPlan mg_tail_host;
-  int mg_tail_level = -1, mg_tail_grid = 0;
-  const double* mg_tail_b = nullptr;
-  double* mg_tail_x = nullptr;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -382,13 +370,6 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_persistent_kernel, RED_BLOCK, 0));
     h->coop_blocks = coop ? std::min(RED_MAX_BLOCKS, occ * prop.multiProcessorCount) : 0;
-    occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mg_tail_kernel, RED_BLOCK, 0));
-    h->tail_blocks = coop ? occ * prop.multiProcessorCount : 0;
-    if (const char* e = std::getenv("JSSO_MG_TAIL_BLOCKS")) h->tail_blocks = std::max(0, std::min(h->tail_blocks, std::atoi(e)));
-#ifdef JSSO_EMU   // CPU test harness: grid.sync() exists for a one-CTA grid only; opt-in so that the graph path stays covered
-    if (std::getenv("EMU_TAIL_KERNEL")) h->tail_blocks = 1;
-#endif
   }
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
@@ -502,7 +483,6 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_c) cudaStreamDestroy(h->st_c);
   if (h->mg_graph_exec) cudaGraphExecDestroy(h->mg_graph_exec);
   if (h->st_cap) cudaStreamDestroy(h->st_cap);
-  if (h->mg_tail_dev) cudaFree(h->mg_tail_dev);
   for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_adj) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
@@ -1199,9 +1179,6 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
       if (h->mg_power_iters >= 30) h->mg_power_safety = 1.15;
     }
     if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] != '0';   // A/B switch (default on)
-    if (!h->mg_graph) h->mg_tail = false;                                            // JSSO_MG_GRAPH=0: kernel by kernel
-    if (const char* eg = std::getenv("JSSO_MG_TAIL")) h->mg_tail = eg[0] != '0';     // A/B switch (default on)
-    if (const char* er = std::getenv("JSSO_MG_TAIL_ROWS")) h->tail_rows = std::max(0, std::atoi(er));
     // binary16 storage of the fine-level V-cycle matrix (the block-Jacobi-scaled matrix has unit diagonal blocks and
     // |entries| <= 1); JSSO_MG_FP16=0 keeps FP32 (A/B switch)
     const char* e16 = std::getenv("JSSO_MG_FP16");
@@ -1562,11 +1539,29 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   if (h->mg_ready) return JSSO_OK;
   PhaseTimer pt_(st, h->mgd.rank);
   if (h->mg_graph_exec) { cudaGraphExecDestroy(h->mg_graph_exec); h->mg_graph_exec = nullptr; }   // coefficients change
-  h->mg_tail_level = -1;
   if (!h->last_crds) return fail(h, JSSO_ERR_STATE, "multigrid needs the coordinates of the last jsso_assemble");
   const int nl = (int)h->mg.size();
   const double* X = h->last_crds;
   int rc;
+  {
+    // reduced-precision copy of the fine matrix for the V-cycle: all rows, or this rank's own rows (distributed setup).
+    // First, because the power iterations below already run on it
+    long long v0 = 0, v1 = h->sym.nnzb();
+    if (h->mgd.setup_on) {
+      int s0, n0;
+      mgd_range(h, 0, s0, n0);
+      v0 = h->sym.rowptr[s0]; v1 = h->sym.rowptr[s0 + n0];
+    }
+    if (h->mg_fp32 && nl > 0 && h->vals32) {
+      if ((rc = mg_to_float(h, 36LL * (v1 - v0), h->vals + 36 * v0, h->vals32 + 36 * v0, st))) return rc;
+    }
+    if (h->mg_fp16 && nl > 0 && v1 > v0) {
+      const long long n16 = 36LL * (v1 - v0);
+      mg_to_half_kernel<<<std::max(1, std::min(1184, cdiv(n16, 256))), 256, 0, st>>>(n16, h->vals + 36 * v0, h->vals16 + 36 * v0);
+      CKL("mg_to_half_kernel");
+    }
+  }
+  pt_.mark("fine_copy");
   for (int l = 0; l < nl; ++l) {
     jsso_handle::MgLevel& m = h->mg[l];
     const MgMat A = mg_matrix(h, l);
@@ -1584,6 +1579,9 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     mg_hash_fill_kernel<<<vb, 256, 0, st>>>(nd, m.r);
     CKL("mg_hash_fill_kernel");
     double lam = 1.0;
+    // on the storage the V-cycle runs on (binary16 / FP32: the smoother's operator, and 0.18 instead of 0.46 ms per
+    // product at 1M quads); the estimate needs two digits
+    const double bpr = (double)A.nnz / std::max(A.n, 1);
     const bool dist_pow = h->mgd.n_rank > 1 && l < h->mgd.n_dist;
     if (dist_pow) {
       // distributed levels: the power iteration (30 SpMVs, 18 of the 42 ms of this setup at 1M quads) by row
@@ -1596,7 +1594,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       const int vbl = std::max(1, std::min(h->red_blocks, cdiv(ndl, 256)));
       for (int it = 0; it < h->mg_power_iters; ++it) {
         if (it > 0) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
-        if ((rc = mg_spmv<0>(h, A.rp + rs, A.ci, A.v, rn, m.r, m.d + off, nullptr, st))) return rc;
+        if ((rc = mg_spmv_p<0>(h, A.rp + rs, A.ci, A.v, A.v32, rn, m.r, m.d + off, nullptr, st, false, A.v16, bpr))) return rc;
         if (m.Dinv && rn > 0) {
           block_apply_kernel<0><<<cdiv(rn, 128), 128, 0, st>>>(rn, m.Dinv + 36 * (size_t)rs, m.d + off, nullptr, m.d + off);
           CKL("block_apply_kernel<0>");
@@ -1611,7 +1609,7 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       }
     }
     for (int it = 0; it < h->mg_power_iters && !dist_pow; ++it) {
-      if ((rc = mg_spmv<0>(h, A.rp, A.ci, A.v, n, m.r, m.d, nullptr, st))) return rc;
+      if ((rc = mg_spmv_p<0>(h, A.rp, A.ci, A.v, A.v32, n, m.r, m.d, nullptr, st, false, A.v16, bpr))) return rc;
       if (m.Dinv) {
         block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
         CKL("block_apply_kernel<0>");
@@ -1697,24 +1695,6 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     pt_.mark("scale_transpose_convert", l);
     X = m.Xc;
   }
-  {
-    // reduced-precision copy of the fine matrix for the V-cycle: all rows, or this rank's own rows (distributed setup)
-    long long v0 = 0, v1 = h->sym.nnzb();
-    if (h->mgd.setup_on) {
-      int s0, n0;
-      mgd_range(h, 0, s0, n0);
-      v0 = h->sym.rowptr[s0]; v1 = h->sym.rowptr[s0 + n0];
-    }
-    if (h->mg_fp32 && nl > 0 && h->vals32) {
-      if ((rc = mg_to_float(h, 36LL * (v1 - v0), h->vals + 36 * v0, h->vals32 + 36 * v0, st))) return rc;
-    }
-    if (h->mg_fp16 && nl > 0 && v1 > v0) {
-      const long long n16 = 36LL * (v1 - v0);
-      mg_to_half_kernel<<<std::max(1, std::min(1184, cdiv(n16, 256))), 256, 0, st>>>(n16, h->vals + 36 * v0, h->vals16 + 36 * v0);
-      CKL("mg_to_half_kernel");
-    }
-  }
-  pt_.mark("fine_copy");
   // coarsest level: dense inverse
   const MgMat C = mg_matrix(h, nl);
   const int nc = 6 * C.n;
@@ -2044,17 +2024,6 @@ static int mg_lin_level(jsso_handle* h, int l, int s, int n, const double* x, do
 // i.e. 4 launches and ~9 vector passes per level instead of 8 launches and ~20.  On several GPUs the levels
 // l < n_dist work on this rank's rows, with a halo exchange before every product that gathers a vector other ranks
 // have just written; b / x are full-length level vectors.
-// First level of the part of the V-cycle that goes out as ONE launch (cooperative kernel or graph): the replicated levels
-// of the distributed solve; on one GPU the levels small enough to be launch bound when the cooperative kernel takes
-// them, else everything below the fine level (graph).
-static int mg_one_launch_from(jsso_handle* h) {
-  if (h->mgd.n_rank > 1) return h->mgd.n_dist;
-  const int nl = (int)h->mg.size();
-  if (!(h->mg_tail && h->mg_fp32 && h->tail_blocks > 0)) return 1;
-  for (int l = 1; l <= nl; ++l) if (mg_matrix(h, l).n <= h->tail_rows) return l;
-  return nl;
-}
-
 static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bool want_dot, cudaStream_t st) {
   const int nl = (int)h->mg.size();
   int rc;
@@ -2081,7 +2050,7 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
   h->probe.mark("K2_restrict", l, st);
   if (dist && l + 1 == h->mgd.n_dist) { if ((rc = mgd_allgather(h, l + 1, bc, st))) return rc; h->probe.mark("allgather", l + 1, st); }
   // the levels below are the same on every rank (replicated tail of the distributed solve / coarse levels of one GPU)
-  const bool one_launch = (l + 1 == mg_one_launch_from(h));
+  const bool one_launch = (h->mgd.n_rank > 1) ? (l + 1 == h->mgd.n_dist) : (l == 0);
   if (one_launch) rc = mg_coarse_graphed(h, l + 1, bc, xc, st);
   else rc = mg_vcycle_fused_level(h, l + 1, bc, xc, false, st);
   if (rc) return rc;
@@ -2128,71 +2097,10 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
 // The part of the fused V-cycle that is the same on every rank and launch-latency bound -- the coarse levels on one
 // GPU (l = 1), the replicated levels of the distributed solve (l = n_dist) -- as ONE graph launch: captured once per
 // numeric setup on a private stream (the smoother coefficients are kernel arguments), replayed into the caller's.
-// The list of products of the fused V-cycle from level l down and up again, for mg_tail_kernel.  False when a level
-// does not have the FP32 storage the kernel reads or the list does not fit.
-static bool mg_tail_ops(jsso_handle* h, int l, double* b, double* x, MgTailPlan& T, int& need_blocks) {
-  const int nl = (int)h->mg.size();
-  auto push = [&](const MgTailOp& o) {
-    if (T.n_ops >= MG_TAIL_MAX_OPS) return false;
-    T.op[T.n_ops++] = o;
-    const long long want = (o.kind == 0) ? cdiv(3LL * o.n_row, RED_BLOCK) : cdiv((long long)o.n_row, RED_BLOCK / 32);
-    need_blocks = (int)std::max<long long>(need_blocks, std::min<long long>(want, 1 << 20));
-    return true;
-  };
-  if (l == nl) {
-    MgTailOp o{};
-    o.kind = 1; o.n_row = 6 * mg_matrix(h, nl).n; o.xrow = h->mg_dense; o.x = b; o.y = x;
-    return push(o);
-  }
-  jsso_handle::MgLevel& m = h->mg[l];
-  const MgMat A = mg_matrix(h, l);
-  if (!A.v32 || !m.P32 || !m.Pt32) return false;
-  const double it = 1.0 / (0.625 * m.lam);
-  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
-  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
-  auto product = [&](const int32_t* rp, const int32_t* ci, const float* v, int n_row, long long nnz, const double* xin, double* y,
-                     const double* bvec, const double* xrow, double ca, double cb, double cc) {
-    MgTailOp o{};
-    o.rp = rp; o.ci = ci; o.v = v; o.x = xin; o.y = y; o.bvec = bvec; o.xrow = xrow; o.ca = ca; o.cb = cb; o.cc = cc;
-    o.n_row = n_row;
-    o.kind = ((double)nnz <= 12.0 * std::max(n_row, 1) && n_row >= 4096) ? 0 : 2;   // as mg_lin_level / mg_spmv_p choose
-    return push(o);
-  };
-  if (!product(A.rp, A.ci, A.v32, m.n_f, A.nnz, b, m.r, b, nullptr, 1.0, 0.0, -it)) return false;          // r0 = b - A b / theta
-  if (!product(m.pt_rowptr, m.pt_col, m.Pt32, m.n_c, m.nnz_p, m.r, bc, nullptr, nullptr, 0.0, 0.0, 1.0)) return false;   // b_c = P^T r0
-  if (!mg_tail_ops(h, l + 1, bc, xc, T, need_blocks)) return false;
-  if (!product(m.p_rowptr, m.p_col, m.P32, m.n_f, m.nnz_p, xc, m.d, b, nullptr, it, 0.0, 1.0)) return false;   // x1 = b / theta + P x_c
-  return product(A.rp, A.ci, A.v32, m.n_f, A.nnz, m.d, x, b, m.d, it, 1.0, -it);                             // x = x1 + (b - A x1) / theta
-}
-
+// (Tried in round 2 and removed: the same products as ONE cooperative kernel walking a device-resident list with grid
+// barriers in between -- ~11 us per phase against ~7 us per kernel node of the graph, 1.41 vs 1.37 ms per iteration at 1M
+// quads, 0.94 vs 0.89 ms on two GPUs; profiles/r2t_coarse_tail_cooperative_kernel_ab.txt.)
 static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st) {
-  if (h->mg_tail && h->mg_fp32 && h->tail_blocks > 0) {
-    if (h->mg_tail_level != l || h->mg_tail_b != b || h->mg_tail_x != x) {
-      h->mg_tail_level = -2;                            // -2: this hierarchy cannot take the kernel (graph below)
-      MgTailPlan& T = h->mg_tail_host;
-      T.n_ops = 0; T.pad = 0;
-      int need = 1;
-      if (mg_tail_ops(h, l, b, x, T, need)) {
-        if (!h->mg_tail_dev) CK(cudaMalloc(&h->mg_tail_dev, sizeof(MgTailPlan)));
-        CK(cudaMemcpyAsync(h->mg_tail_dev, &T, sizeof(MgTailPlan), cudaMemcpyHostToDevice, st));
-        h->mg_tail_level = l; h->mg_tail_grid = std::max(1, std::min(h->tail_blocks, need));
-      }
-      h->mg_tail_b = b; h->mg_tail_x = x;
-    }
-    if (h->mg_tail_level == l) {
-      const MgTailPlan* plan = h->mg_tail_dev;
-      const double* stop = h->mg_scal;
-      void* args[] = {(void*)&plan, (void*)&stop};
-#ifdef JSSO_EMU
-      (void)args;
-      mg_tail_kernel<<<1, RED_BLOCK, 0, st>>>(plan, stop);
-#else
-      CK(cudaLaunchCooperativeKernel((void*)mg_tail_kernel, dim3(h->mg_tail_grid), dim3(RED_BLOCK), args, 0, st));
-#endif
-      LAUNCHED();
-      return JSSO_OK;
-    }
-  }
   if (!h->mg_graph) return mg_vcycle_fused_level(h, l, b, x, false, st);
   if (h->mg_graph_exec && (h->mg_graph_level != l || h->mg_graph_b != b || h->mg_graph_x != x || h->mg_graph_deg != -1)) {
     cudaGraphExecDestroy(h->mg_graph_exec);

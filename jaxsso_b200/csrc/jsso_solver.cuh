@@ -819,74 +819,6 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   }
 }
 
-// ---- the coarse tail of the fused V-cycle as ONE persistent kernel ------------------------------------------------
-// The levels below the last bandwidth-bound one (levels >= 1 on one GPU, the replicated levels of the distributed solve)
-// are 4 products per level on a few thousand rows: as separate kernels -- even replayed from a CUDA graph -- each costs
-// a launch gap and a ramp (13 kernels = 91 us at 1M quads).  Here one cooperative grid runs the whole list of products,
-// separated by grid-wide barriers: `plan->op[i]` is  y = ca b + cb x_row + cc A x  on FP32 row-pair-major blocks with one
-// thread per (row, row pair) (kind 0) or one warp per row (kind 2: long rows, small levels), or the dense coarsest
-// solve  y = M x  (kind 1: warp per row of the stored inverse).
-constexpr int MG_TAIL_MAX_OPS = 41;
-struct MgTailOp {
-  const int32_t* rp; const int32_t* ci; const float* v;
-  const double* x; double* y; const double* bvec; const double* xrow;   // kind 1: xrow = dense [A | A^-1], row-major
-  double ca, cb, cc;
-  int n_row, kind;
-};
-struct MgTailPlan { int n_ops, pad; MgTailOp op[MG_TAIL_MAX_OPS]; };
-
-__global__ void __launch_bounds__(RED_BLOCK)
-mg_tail_kernel(const MgTailPlan* __restrict__ plan, const double* stop) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  if (mgs_stopped(stop)) return;                       // the same decision in every block: nobody reaches a barrier
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
-  const int n_ops = plan->n_ops;
-  for (int i = 0; i < n_ops; ++i) {
-    const MgTailOp& o = plan->op[i];
-    if (o.kind == 0) {
-      const long long n_item = 3LL * o.n_row;
-      for (long long t = tid; t < n_item; t += nthr) {
-        const int r = (int)(t / 3), sub = (int)(t - 3LL * r);
-        const size_t off = 6 * (size_t)r + 2 * sub;
-        double2 bv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
-        if (o.bvec) bv = *(const double2*)(o.bvec + off);
-        if (o.xrow) xv = *(const double2*)(o.xrow + off);
-        double acc0 = 0.0, acc1 = 0.0;
-        rp_row_pair(o.rp[r], o.rp[r + 1], sub, o.ci, o.v, o.x, acc0, acc1);
-        *(double2*)(o.y + off) = make_double2(fma(o.ca, bv.x, fma(o.cb, xv.x, o.cc * acc0)),
-                                              fma(o.ca, bv.y, fma(o.cb, xv.y, o.cc * acc1)));
-      }
-    } else if (o.kind == 2) {
-      const int lane = threadIdx.x & 31;
-      const double* bvec = o.bvec;
-      const double* xrow = o.xrow;
-      double* y = o.y;
-      const double ca = o.ca, cb = o.cb, cc = o.cc;
-      auto epilogue = [=](int r, double u0, double u1) -> double {
-        if (lane < 3) {
-          const size_t off = 6 * (size_t)r + 2 * lane;
-          double2 v = make_double2(cc * u0, cc * u1);
-          if (bvec) { const double2 bv = *(const double2*)(bvec + off); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
-          if (xrow) { const double2 xv = *(const double2*)(xrow + off); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
-          *(double2*)(y + off) = v;
-        }
-        return 0.0;
-      };
-      bsr_rows_pipelined((int)(tid >> 5), (int)(nthr >> 5), lane, o.n_row, o.rp, o.ci, o.v, o.x, epilogue);
-    } else {
-      const int n = o.n_row, lane = threadIdx.x & 31;
-      for (long long row = tid >> 5; row < n; row += nthr >> 5) {
-        const double* a = o.xrow + (size_t)row * 2 * n + n;
-        double sum = 0.0;
-        for (int j = lane; j < n; j += 32) sum = fma(a[j], o.x[j], sum);
-        sum = warp_sum(sum);
-        if (lane == 0) o.y[row] = sum;
-      }
-    }
-    grid.sync();
-  }
-}
-
 // Short rows (prolongators: 1-4 blocks per row) in the FP32 row-pair-major layout: one THREAD per
 // (block row, row pair), no shuffles -- a warp works on ten rows at once instead of one, which is what
 // hides the rowptr -> colidx -> x load chain when rows are this short.  MODE as above.

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, GPU call 11 (one GPU): the coarse tail as one cooperative kernel (mg_tail_kernel) on hardware -- full GPU
+# Round 2, GPU call 11 (one GPU): the coarse tail as one cooperative kernel (mg_tail_kernel, since removed) on hardware -- full GPU
 # test suite, A/B against the graph of kernels and over the grid size, launch list of one iteration, the bench line.
 set -u
 mkdir -p gpurun_out

@@ -1,12 +1,13 @@
 #!/bin/bash
-# Round 2, GPU call 13 (eight GPUs): the bench line at N = 8 with the final code (ghost rows + cooperative tail).
+# Round 2, GPU call 13 (eight GPUs): bench lines at N = 8 and 4 with the final code (ghost-row recomputation of the
+# corrected iterate, power iterations on the reduced-precision storage).
 set -u
 mkdir -p gpurun_out
-N=8
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2958$N \
-   bench.py --gpus $N > gpurun_out/r2v_bench_n$N.json 2> gpurun_out/r2v_bench_n$N.err; echo "bench n$N rc=$?"
-grep -v "OMP_NUM_THREADS\|\*\*\*\*" gpurun_out/r2v_bench_n$N.err | tail -2
-python - $N <<'PY'
+for N in 8 4; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2958$N \
+     bench.py --gpus $N > gpurun_out/r2v_bench_n$N.json 2> gpurun_out/r2v_bench_n$N.err; echo "bench n$N rc=$?"
+  grep -v "OMP_NUM_THREADS\|\*\*\*\*" gpurun_out/r2v_bench_n$N.err | tail -2
+  python - $N <<'PY'
 import json, sys
 try:
     d = json.loads(open('gpurun_out/r2v_bench_n%s.json' % sys.argv[1]).read().strip().splitlines()[-1])
@@ -17,3 +18,4 @@ try:
 except Exception as e:
     print('parse failed', e)
 PY
+done

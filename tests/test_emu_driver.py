@@ -201,27 +201,6 @@ def test_graph_captured_vcycle(emu_api):
     assert all(i == d['iters_single'] for i in d['iters_dist'])
 
 
-def test_persistent_coarse_tail_kernel(emu_api):
-    """mg_tail_kernel: the coarse part of the fused V-cycle as one cooperative kernel walking a device-resident list of
-    products with grid barriers between them (the emulator runs it as a one-CTA grid, EMU_TAIL_KERNEL=1).  Same
-    iterations and solution as the graph of separate kernels, one launch per V-cycle for the coarse part, also as the
-    replicated tail of the distributed solve and after a second numeric setup (the plan is rebuilt)."""
-    g = run(emu_api, 'mg', 12, 1)
-    t = run(emu_api, 'mg', 12, 1, env={'EMU_TAIL_KERNEL': '1'})
-    assert t['mg_converged'] and t['mg_iters'] == g['mg_iters'] and t['mg_err'] <= 1e-8
-    assert t['mg_launches'] == g['mg_launches']              # one launch either way; the emulator counts a graph as one
-    # with the graph switched off the tail kernel is what keeps the launch count down: it really ran
-    t2 = run(emu_api, 'mg', 12, 1, env={'EMU_TAIL_KERNEL': '1', 'JSSO_MG_GRAPH': '0', 'JSSO_MG_TAIL': '1'})
-    off = run(emu_api, 'mg', 12, 1, env={'EMU_TAIL_KERNEL': '1', 'JSSO_MG_GRAPH': '0'})
-    assert t2['mg_launches'] == g['mg_launches'] and off['mg_launches'] >= g['mg_launches'] + 3 * g['mg_iters']
-    assert off['mg_iters'] == g['mg_iters']
-    d = run(emu_api, 'dist', 2, 12, 10, 1, 'p2p', env={'EMU_TAIL_KERNEL': '1'})
-    assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
-    assert all(i == d['iters_single'] for i in d['iters_dist'])
-    res = run(emu_api, 'benchleg', 2, 12, 10, 'natural', env={'EMU_TAIL_KERNEL': '1'})
-    assert res['leg']['pcg_iterations'] == res['iters_single'] and res['u_err_vs_oracle'] <= 1e-8 and res['g_err'] <= 1e-6
-
-
 @pytest.mark.parametrize('world,size,min_dist,deg,env', [
     (2, 12, 10, 1, {}), (4, 12, 10, 1, {'EMU_JITTER': '3000'}),
     (4, 16, 10, 2, {'JSSO_MG_POLL': '3', 'EMU_JITTER': '1000'})])
