@@ -723,12 +723,19 @@ def run_b200(args):
     if world == 1 and grad_eval and 'error' not in grad_eval and args.precond != 'block_jacobi':
         try:
             o_ = nat.make_opts(rtol=args.rtol, maxiter=args.maxiter, precond=args.precond, cheb_degree=args.cheb_degree)
-            h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads, want=('crds', 'prop_q'), opts=o_)
+            # page-locked host buffers on both sides, as for the M1 leg: the copies are DMA from / into the caller's arrays
+            hin = [nat.pinned_copy(a) for a in (md.crds, md.prop_quads, md.prop_beams, md.loads)]
+            hout = (nat.pinned_empty((md.ndof,)), nat.pinned_empty((md.n_node, 3)), nat.pinned_empty((md.n_quad, 5)), None)
+            h.value_and_grad_host(*hin, want=('crds', 'prop_q'), opts=o_, out=hout)
             t0 = time.perf_counter()
-            v_, u_, dc_, dq_, _, fs_, _ = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads,
-                                                                want=('crds', 'prop_q'), opts=o_)
+            v_, u_, dc_, dq_, _, fs_, _ = h.value_and_grad_host(*hin, want=('crds', 'prop_q'), opts=o_, out=hout)
             dt_ = time.perf_counter() - t0
+            # the same call with ordinary (pageable) NumPy arrays and freshly allocated results: staged by the library
+            t0 = time.perf_counter()
+            h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads, want=('crds', 'prop_q'), opts=o_)
+            dt_pageable = time.perf_counter() - t0
             m2_e2e = {'seconds': dt_, 'evals_per_s': 1.0 / dt_, 'call': 'jsso_value_and_grad_host (C ABI, host buffers)',
+                      'host_buffers': 'page-locked', 'seconds_pageable_buffers': dt_pageable,
                       'h2d_bytes': int(8 * (md.crds.size + md.prop_quads.size + md.prop_beams.size + md.loads.size)),
                       'd2h_bytes': int(8 * (u_.size + dc_.size + dq_.size)), 'pcg_iterations': int(fs_.iterations),
                       'compliance': float(v_)}

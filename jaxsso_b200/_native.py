@@ -510,18 +510,32 @@ class Handle:
         return st
 
     def value_and_grad_host(self, crds, prop_q, prop_b, f, want=('crds', 'prop_q', 'prop_b'), opts=None, u0=None,
-                            allow_noconv=False):
+                            allow_noconv=False, out=None):
         """End-to-end strain-energy value + gradient with HOST (NumPy) buffers.  ``u0``: initial
-        guess for the solve (e.g. the previous design's u); needs opts.use_x0."""
+        guess for the solve (e.g. the previous design's u); needs opts.use_x0.  ``out``: optional
+        ``(u, d_crds, d_prop_q, d_prop_b)`` arrays to fill instead of fresh ones (entries may be None) -- with
+        page-locked arrays (``pinned_empty``) for inputs and ``out`` the library copies by DMA straight from / into
+        them; pageable arrays are staged through its own pinned buffers (threaded memcpy), which at 1M quads costs
+        tens of milliseconds per call, most of it page faults of freshly allocated results."""
         crds = np.ascontiguousarray(crds, np.float64)
         prop_q = np.ascontiguousarray(prop_q, np.float64)
         prop_b = np.ascontiguousarray(prop_b, np.float64)
         f = np.ascontiguousarray(f, np.float64)
         self._check_shapes(crds, prop_q, prop_b, f=f, u0=u0)
-        u = np.empty(6 * self.n_node) if u0 is None else np.array(u0, dtype=np.float64).ravel()
-        dc = np.empty((self.n_node, 3)) if 'crds' in want else None
-        dq = np.empty((self.n_quad, 5)) if ('prop_q' in want and self.n_quad) else None
-        db = np.empty((self.n_beam, 6)) if ('prop_b' in want and self.n_beam) else None
+        ou, oc, oq, ob = out if out is not None else (None, None, None, None)
+        for a, size, name in ((ou, 6 * self.n_node, 'out[0] (u)'), (oc, 3 * self.n_node, 'out[1] (d_crds)'),
+                              (oq, 5 * self.n_quad, 'out[2] (d_prop_q)'), (ob, 6 * self.n_beam, 'out[3] (d_prop_b)')):
+            if a is not None and (a.size != size or a.dtype != np.float64 or not a.flags['C_CONTIGUOUS']):
+                raise ValueError(f'{name}: expected {size} contiguous float64 values')
+        if ou is not None:
+            u = ou
+            if u0 is not None and u0 is not ou:
+                u.ravel()[:] = np.asarray(u0, np.float64).ravel()
+        else:
+            u = np.empty(6 * self.n_node) if u0 is None else np.array(u0, dtype=np.float64).ravel()
+        dc = (oc if oc is not None else np.empty((self.n_node, 3))) if 'crds' in want else None
+        dq = (oq if oq is not None else np.empty((self.n_quad, 5))) if ('prop_q' in want and self.n_quad) else None
+        db = (ob if ob is not None else np.empty((self.n_beam, 6))) if ('prop_b' in want and self.n_beam) else None
         val = C.c_double()
         fs, bs = Stats(), Stats()
         o = opts or make_opts()

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "jsso_adjoint.cuh"
@@ -251,6 +252,9 @@ struct jsso_handle {
   // host staging for the host-buffer entry point
   double *h_crds = nullptr, *h_pq = nullptr, *h_pb = nullptr, *h_f = nullptr, *h_u = nullptr;
   double *h_dc = nullptr, *h_dpq = nullptr, *h_dpb = nullptr;
+  double* val_dev = nullptr;       // f.u of jsso_value_and_grad_host (device dot product instead of a host loop over 6 n_node entries)
+  double* val_host = nullptr;      // pinned
+  cudaEvent_t ev_out[4] = {nullptr, nullptr, nullptr, nullptr};   // D2H of u / d_crds / d_prop_q / d_prop_b done
   cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
   cudaEvent_t ev_b = nullptr;
   // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 4; 1 = one launch): u / lam arrive
@@ -472,11 +476,12 @@ void jsso_destroy(jsso_handle* h) {
                  h->task_meta, h->task_els, h->item_desc, h->blk_bc, h->quad_rec, h->node_inc_ptr, h->node_inc, h->vals, h->W, h->vb, h->vx, h->vr, h->vp, h->vq,
                  h->corner_q, h->corner_b, h->tmp_lam, h->tmp_g, h->sc, h->partials, h->counters, h->flags,
                  h->send_idx, h->send_buf, h->mbox, h->p2p, h->s_crds, h->s_pq, h->s_pb, h->s_f, h->s_u, h->s_dc, h->s_dpq,
-                 h->s_dpb};
+                 h->s_dpb, h->val_dev};
   for (void* p : dev) if (p) cudaFree(p);
   void* hst[] = {h->sc_host, h->flags_host, h->h_crds, h->h_pq, h->h_pb, h->h_f, h->h_u, h->h_dc, h->h_dpq,
-                 h->h_dpb};
+                 h->h_dpb, h->val_host};
   for (void* p : hst) if (p) cudaFreeHost(p);
+  for (cudaEvent_t e : h->ev_out) if (e) cudaEventDestroy(e);
   if (h->st_a) cudaStreamDestroy(h->st_a);
   if (h->st_b) cudaStreamDestroy(h->st_b);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -2442,6 +2447,41 @@ int jsso_backward(jsso_handle* h, const double* crds, const double* prop_q, cons
   return jsso_adjoint(h, crds, prop_q, prop_b, u, l, d_crds, d_prop_q, d_prop_b, stream);
 }
 
+// memcpy of a large host block on several threads: a single thread moves ~8 GB/s and pays every page fault of a
+// freshly allocated destination itself (117 MB of results at 1M quads: 15 ms into touched memory, 45 ms into fresh);
+// JSSO_HOST_THREADS=1 switches it off
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  static const unsigned max_threads = [] {
+    unsigned n = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = std::getenv("JSSO_HOST_THREADS")) n = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+    return n;
+  }();
+#ifdef JSSO_EMU   // CPU test harness: tiny meshes still take the threaded path
+  const size_t min_chunk = 256;
+#else
+  const size_t min_chunk = (size_t)4 << 20;
+#endif
+  const unsigned nt = (unsigned)std::min<size_t>(max_threads, bytes / min_chunk);
+  if (nt <= 1) { std::memcpy(dst, src, bytes); return; }
+  const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t o = (size_t)t * chunk;
+    if (o >= bytes) break;
+    const size_t n = std::min(chunk, bytes - o);
+    th.emplace_back([=] { std::memcpy((char*)dst + o, (const char*)src + o, n); });
+  }
+  for (std::thread& t : th) t.join();
+}
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory can be the source / target of an asynchronous DMA
+static bool host_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int ensure_host_staging(jsso_handle* h) {
   if (h->h_crds) return JSSO_OK;
   const Symbolic& S = h->sym;
@@ -2453,6 +2493,9 @@ static int ensure_host_staging(jsso_handle* h) {
   CK(cudaMallocHost((void**)&h->h_dc, sizeof(double) * 3 * (size_t)S.n_node));
   CK(cudaMallocHost((void**)&h->h_dpq, sizeof(double) * (5 * (size_t)S.n_quad + 1)));
   CK(cudaMallocHost((void**)&h->h_dpb, sizeof(double) * (6 * (size_t)S.n_beam + 1)));
+  CK(cudaMallocHost((void**)&h->val_host, sizeof(double)));
+  CK(dalloc(&h->val_dev, 1));
+  for (cudaEvent_t& e : h->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(dalloc(&h->s_crds, 3 * (size_t)S.n_node)); CK(dalloc(&h->s_pq, 5 * (size_t)S.n_quad));
   CK(dalloc(&h->s_pb, 6 * (size_t)S.n_beam)); CK(dalloc(&h->s_f, 6 * (size_t)S.n_node));
   CK(dalloc(&h->s_u, 6 * (size_t)S.n_node)); CK(dalloc(&h->s_dc, 3 * (size_t)S.n_node));
@@ -2507,18 +2550,20 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
   double *d_crds = h->s_crds, *d_pq = h->s_pq, *d_pb = h->s_pb, *d_f = h->s_f, *d_u = h->s_u, *d_dc = h->s_dc,
          *d_dpq = h->s_dpq, *d_dpb = h->s_dpb;
   cudaStream_t st = 0;
-  std::memcpy(h->h_crds, crds_h, nc * sizeof(double));
-  if (nq) std::memcpy(h->h_pq, pq_h, nq * sizeof(double));
-  if (nb) std::memcpy(h->h_pb, pb_h, nb * sizeof(double));
-  std::memcpy(h->h_f, f_h, nd * sizeof(double));
-  CK(cudaMemcpyAsync(d_crds, h->h_crds, nc * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (nq) CK(cudaMemcpyAsync(d_pq, h->h_pq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (nb) CK(cudaMemcpyAsync(d_pb, h->h_pb, nb * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_f, h->h_f, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  // pinned caller buffers are DMA sources / targets themselves; pageable ones go through the handle's pinned staging
+  // (threaded memcpy; the DMA of one array overlaps the staging of the next)
+  auto h2d = [&](double* dst, const double* src, double* stage, size_t n) -> cudaError_t {
+    if (!n) return cudaSuccess;
+    if (!host_pinned(src)) { par_memcpy(stage, src, n * sizeof(double)); src = stage; }
+    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+  };
+  CK(h2d(d_crds, crds_h, h->h_crds, nc));
+  CK(h2d(d_pq, pq_h, h->h_pq, nq));
+  CK(h2d(d_pb, pb_h, h->h_pb, nb));
+  CK(h2d(d_f, f_h, h->h_f, nd));
   jsso_solve_opts o; default_opts(opts, o);
   if (o.use_x0 && u_h) {   // warm start: u_h holds the previous design's displacements
-    std::memcpy(h->h_u, u_h, nd * sizeof(double));
-    CK(cudaMemcpyAsync(d_u, h->h_u, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(h2d(d_u, u_h, h->h_u, nd));
   } else {
     o.use_x0 = 0;
   }
@@ -2533,18 +2578,30 @@ int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double*
                        (dpb_h && nb) ? d_dpb : nullptr, nullptr, &o, bs, st);
     if (rc) return rc;
   }
-  CK(cudaMemcpyAsync(h->h_u, d_u, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (dc_h) CK(cudaMemcpyAsync(h->h_dc, d_dc, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (dpq_h && nq) CK(cudaMemcpyAsync(h->h_dpq, d_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (dpb_h && nb) CK(cudaMemcpyAsync(h->h_dpb, d_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  // value = f.u / 2 on the device (deterministic grid sum)
+  mg_dot_kernel<<<std::max(1, std::min(h->red_blocks, cdiv((long long)nd, 256))), 256, 0, st>>>((long long)nd, d_f, d_u, h->partials,
+                                                                                           h->counters + 2, h->val_dev);
+  CKL("mg_dot_kernel");
+  CK(cudaMemcpyAsync(h->val_host, h->val_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  // results: straight into pinned caller buffers, else into the staging and from there while the next array is in flight
+  struct Out { double* dst; double* stage; const double* src; size_t n; bool direct; };
+  Out outs[4] = {{u_h, h->h_u, d_u, nd, false}, {dc_h, h->h_dc, d_dc, nc, false}, {dpq_h, h->h_dpq, d_dpq, nq, false},
+                 {dpb_h, h->h_dpb, d_dpb, nb, false}};
+  for (int k = 0; k < 4; ++k) {
+    Out& O = outs[k];
+    if (!O.dst || !O.n) continue;
+    O.direct = host_pinned(O.dst);
+    CK(cudaMemcpyAsync(O.direct ? O.dst : O.stage, O.src, O.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev_out[k], st));
+  }
+  for (int k = 0; k < 4; ++k) {
+    const Out& O = outs[k];
+    if (!O.dst || !O.n || O.direct) continue;
+    CK(cudaEventSynchronize(h->ev_out[k]));
+    par_memcpy(O.dst, O.stage, O.n * sizeof(double));
+  }
   CK(cudaStreamSynchronize(st));
-  double v = 0.0;
-  for (size_t i = 0; i < nd; ++i) v += h->h_f[i] * h->h_u[i];
-  if (value_out) *value_out = 0.5 * v;
-  if (u_h) std::memcpy(u_h, h->h_u, nd * sizeof(double));
-  if (dc_h) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
-  if (dpq_h && nq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
-  if (dpb_h && nb) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  if (value_out) *value_out = 0.5 * h->val_host[0];
   if (rc_solve) return fail(h, rc_solve, solve_msg);
   return JSSO_OK;
 }
@@ -2569,14 +2626,10 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   cudaStream_t st = h->st_a, st2 = h->st_b;
   // DMA straight from / to the caller's buffers when they are pinned (cudaHostAlloc / registered);
   // pageable buffers are staged through the handle's pinned scratch so the copies stay asynchronous
-  auto pinned = [](const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-  };
+  auto pinned = [](const void* p) { return host_pinned(p); };
   auto h2d = [&](double* dst, const double* src, double* stage, size_t n, cudaStream_t s_) -> cudaError_t {
     if (!n) return cudaSuccess;
-    if (!pinned(src)) { std::memcpy(stage, src, n * sizeof(double)); src = stage; }
+    if (!pinned(src)) { par_memcpy(stage, src, n * sizeof(double)); src = stage; }
     return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s_);
   };
   CK(h2d(h->s_crds, crds_h, h->h_crds, nc, st));
@@ -2587,8 +2640,8 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
     // chunked pipeline (opt-in, JSSO_E2E_CHUNKS): see the handle fields
     const int K = h->e2e_chunks;
     const bool want_dq = dpq_h && nq;
-    if (!pinned(u_h)) { std::memcpy(h->h_f, u_h, nd * sizeof(double)); u_h = h->h_f; }
-    if (!pinned(lam_h)) { std::memcpy(h->h_u, lam_h, nd * sizeof(double)); lam_h = h->h_u; }
+    if (!pinned(u_h)) { par_memcpy(h->h_f, u_h, nd * sizeof(double)); u_h = h->h_f; }
+    if (!pinned(lam_h)) { par_memcpy(h->h_u, lam_h, nd * sizeof(double)); lam_h = h->h_u; }
     for (int c = 0; c < K; ++c) {
       const size_t o = 6 * (size_t)h->e2e_nb[c], cnt = 6 * (size_t)(h->e2e_nb[c + 1] - h->e2e_nb[c]);
       CK(cudaMemcpyAsync(h->s_f + o, u_h + o, cnt * sizeof(double), cudaMemcpyHostToDevice, st2));
@@ -2627,9 +2680,9 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
     if (dpb_h && nb) CK(cudaMemcpyAsync(p_db ? dpb_h : h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(h->st_c));
-    if (dc_h && !p_dc) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
-    if (want_dq && !p_dq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
-    if (dpb_h && nb && !p_db) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+    if (dc_h && !p_dc) par_memcpy(dc_h, h->h_dc, nc * sizeof(double));
+    if (want_dq && !p_dq) par_memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+    if (dpb_h && nb && !p_db) par_memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
     return JSSO_OK;
   }
   CK(h2d(h->s_f, u_h, h->h_f, nd, st2));
@@ -2644,9 +2697,9 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   if (dpq_h && nq) CK(cudaMemcpyAsync(p_dq ? dpq_h : h->h_dpq, h->s_dpq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (dpb_h && nb) CK(cudaMemcpyAsync(p_db ? dpb_h : h->h_dpb, h->s_dpb, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (dc_h && !p_dc) std::memcpy(dc_h, h->h_dc, nc * sizeof(double));
-  if (dpq_h && nq && !p_dq) std::memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
-  if (dpb_h && nb && !p_db) std::memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
+  if (dc_h && !p_dc) par_memcpy(dc_h, h->h_dc, nc * sizeof(double));
+  if (dpq_h && nq && !p_dq) par_memcpy(dpq_h, h->h_dpq, nq * sizeof(double));
+  if (dpb_h && nb && !p_db) par_memcpy(dpb_h, h->h_dpb, nb * sizeof(double));
   return JSSO_OK;
 }
 

@@ -66,7 +66,14 @@ inline cudaError_t GetDeviceProperties(cudaDeviceProp* p, int) { std::memset(p, 
 inline cudaError_t DeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 0; return cudaSuccess; }   // no cooperative launch
 template <class F> inline cudaError_t OccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 template <class F> inline cudaError_t FuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-inline cudaError_t PointerGetAttributes(cudaPointerAttributes* a, const void*) { std::memset(a, 0, sizeof *a); a->type = cudaMemoryTypeHost; return cudaSuccess; }
+// every "device" and host pointer is heap memory; EMU_PAGEABLE=1 reports host pointers as pageable so that the driver's
+// staging path (threaded memcpy through its pinned buffers) runs instead of the direct DMA
+inline cudaError_t PointerGetAttributes(cudaPointerAttributes* a, const void*) {
+  static const bool pageable = std::getenv("EMU_PAGEABLE") != nullptr;
+  std::memset(a, 0, sizeof *a);
+  a->type = pageable ? cudaMemoryTypeUnregistered : cudaMemoryTypeHost;
+  return cudaSuccess;
+}
 // "IPC" between rank threads of one process: the handle carries the pointer
 inline cudaError_t IpcGetMemHandle(cudaIpcMemHandle_t* hd, void* p) { std::memset(hd, 0, sizeof *hd); std::memcpy(hd, &p, sizeof p); return cudaSuccess; }
 inline cudaError_t IpcOpenMemHandle(void** p, cudaIpcMemHandle_t hd, unsigned) { std::memcpy(p, &hd, sizeof *p); return cudaSuccess; }

@@ -39,6 +39,10 @@ def test_value_and_gradient_through_the_emulated_driver(emu_api):
     assert res['u_err'] <= 1e-8 and res['c_err'] <= 1e-8
     assert res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6 and res['db_err'] <= 1e-6
     assert res['launches'] > 100
+    # host buffers reported as pageable: staged through the handle's pinned buffers with the threaded memcpy
+    # (default: reported as pinned, DMA straight from / into the caller's arrays) -- the same numbers
+    pg = run(emu_api, 'grad', 6, env={'EMU_PAGEABLE': '1'})
+    assert all(pg[k] == res[k] for k in ('u_err', 'c_err', 'g_err', 'dq_err', 'db_err', 'iterations'))
 
 
 def test_spmv_and_values_after_a_solve(emu_api):

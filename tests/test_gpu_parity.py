@@ -341,3 +341,26 @@ def test_host_buffer_assemble_adjoint_matches_device_path():
     K = nat.bsr_to_scipy(*d.h.pattern(), d.h.values_host())
     Kref = d.K_scipy(apply_bc=True)
     assert abs(K - Kref).max() == 0.0
+
+
+def test_value_and_grad_host_pinned_and_pageable_buffers_agree():
+    """jsso_value_and_grad_host copies by DMA straight from / into page-locked caller buffers (`out=`), and stages
+    pageable ones through its own pinned buffers with a threaded memcpy: bitwise the same u and gradients, the value
+    (a device dot product) equal to f.u / 2, and a warm start through a pinned `out` buffer works."""
+    md = meshes.plate(40)
+    h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
+    opts = nat.make_opts(rtol=1e-11)
+    v0, u0, dc0, dq0, _, fs0, _ = h.value_and_grad_host(md.crds, md.prop_quads, md.prop_beams, md.loads, want=('crds', 'prop_q'),
+                                                        opts=opts)
+    pin = [nat.pinned_copy(a) for a in (md.crds, md.prop_quads, md.prop_beams, md.loads)]
+    out = (nat.pinned_empty((md.ndof,)), nat.pinned_empty((md.n_node, 3)), nat.pinned_empty((md.n_quad, 5)), None)
+    v1, u1, dc1, dq1, _, fs1, _ = h.value_and_grad_host(*pin, want=('crds', 'prop_q'), opts=opts, out=out)
+    assert u1 is out[0] and dc1 is out[1] and dq1 is out[2]
+    assert np.array_equal(np.asarray(u1), u0) and np.array_equal(np.asarray(dc1), dc0) and np.array_equal(np.asarray(dq1), dq0)
+    assert v1 == v0 and abs(v0 - 0.5 * float(np.ravel(md.loads) @ np.ravel(u0))) <= 1e-12 * abs(v0)
+    o2 = nat.make_opts(rtol=1e-11, use_x0=True, check_every=5)
+    v2, u2, *_rest, fs2, _ = h.value_and_grad_host(*pin, want=('crds',), opts=o2, u0=out[0], out=out)
+    assert fs2.converged and fs2.iterations <= 5 and abs(v2 - v0) <= 1e-9 * abs(v0)
+    with pytest.raises(ValueError):
+        h.value_and_grad_host(*pin, want=('crds',), opts=opts, out=(np.empty(3), None, None, None))
+    h.close()
