@@ -1645,13 +1645,13 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       // restriction rows of the own coarse nodes: P^T blocks [pt0, pt1); prolongation rows: P blocks [pr0, pr1)
       const int pt[2] = {SL.pt_lo, SL.pt_hi}, pr[2] = {SL.p_lo, SL.p_hi};
       if (SL.n_ap > 0) {
-        mg_block_product_kernel<0><<<cdiv(SL.n_ap, 128), 128, 0, st>>>(SL.n_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP,
+        mg_block_product_kernel<0><<<cdiv(6LL * (SL.n_ap), MG_PROD_THREADS), MG_PROD_THREADS, 0, st>>>(SL.n_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP,
                                                                        SL.ap_list, 0);
         CKL("mg_block_product_kernel<0>");
       }
       const int a0 = SL.ac_bounds[me], a1 = SL.ac_bounds[me + 1];
       if (a1 > a0) {
-        mg_block_product_kernel<1><<<cdiv(a1 - a0, 128), 128, 0, st>>>(a1 - a0, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac,
+        mg_block_product_kernel<1><<<cdiv(6LL * (a1 - a0), MG_PROD_THREADS), MG_PROD_THREADS, 0, st>>>(a1 - a0, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac,
                                                                        nullptr, a0);
         CKL("mg_block_product_kernel<1>");
       }
@@ -1684,9 +1684,9 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
         m.nnz_p, m.p_row, m.p_col, m.p_own, m.ps_ptr, m.ps_a, m.ps_j, m.agg, A.v, nullptr, Lf,
         l == 0 ? h->node_mask : nullptr, X, m.Xc, 4.0 / (3.0 * m.lam), m.P);
     CKL("mg_smooth_prolongator_kernel");
-    mg_block_product_kernel<0><<<cdiv(m.nnz_ap, 128), 128, 0, st>>>(m.nnz_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP);
+    mg_block_product_kernel<0><<<cdiv(6LL * (m.nnz_ap), MG_PROD_THREADS), MG_PROD_THREADS, 0, st>>>(m.nnz_ap, m.apl_ptr, m.apl_a, m.apl_p, A.v, m.P, m.AP);
     CKL("mg_block_product_kernel<0>");
-    mg_block_product_kernel<1><<<cdiv(m.nnz_c, 128), 128, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
+    mg_block_product_kernel<1><<<cdiv(6LL * (m.nnz_c), MG_PROD_THREADS), MG_PROD_THREADS, 0, st>>>(m.nnz_c, m.cl_ptr, m.cl_p, m.cl_ap, m.P, m.AP, m.Ac);
     CKL("mg_block_product_kernel<1>");
     pt_.mark("P_AP_Ac", l);
     if ((rc = mg_scale_coarse(h, l, nullptr, m.nnz_p, st))) return rc;

@@ -147,26 +147,42 @@ mg_smooth_prolongator_kernel(int nnz_p, const int32_t* __restrict__ p_row, const
   for (int k = 0; k < 36; ++k) o[k] = out[k];
 }
 
-// out[s] = sum_k op(L[l_k]) * R[r_k]   (TRANS: op = transpose); thread per output block
+// out[s] = sum_k op(L[l_k]) * R[r_k]   (TRANS: op = transpose).  Six threads per output block, thread c owns column
+// c: it reads column c of R (48 contiguous bytes) and the whole L block (the six threads read the same 288 bytes, one
+// set of sectors), and the six columns leave as 288 contiguous bytes.  Every entry is summed in the order of the
+// thread-per-block form it replaces (4.3 + 2.5 ms for the two Galerkin products of a numeric setup at 1M quads: 36
+// accumulators and 72 strided 8-byte loads per product and thread) -- bitwise the same hierarchy.
+constexpr int MG_PROD_THREADS = 192;   // 32 output blocks per CTA
 template <int TRANS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MG_PROD_THREADS)
 mg_block_product_kernel(int nnz_out, const int32_t* __restrict__ ptr, const int32_t* __restrict__ li,
                         const int32_t* __restrict__ ri, const double* __restrict__ Lv,
                         const double* __restrict__ Rv, double* __restrict__ out,
                         const int32_t* __restrict__ list = nullptr /* nnz_out slots to compute */, int first = 0) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (int)(g / 6), c = (int)(g - 6LL * t);
   if (t >= nnz_out) return;
   const int s = list ? list[t] : first + t;
-  double acc[36];
+  double acc[6];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  for (int r = 0; r < 6; ++r) acc[r] = 0.0;
   for (int k = ptr[s]; k < ptr[s + 1]; ++k) {
-    if (TRANS) blk_mma_t(Lv + (size_t)li[k] * 36, Rv + (size_t)ri[k] * 36, acc);
-    else blk_mma(Lv + (size_t)li[k] * 36, Rv + (size_t)ri[k] * 36, acc);
-  }
-  double* o = out + (size_t)s * 36;
+    const double2* A2 = (const double2*)(Lv + (size_t)li[k] * 36);
+    const double2* B2 = (const double2*)(Rv + (size_t)ri[k] * 36 + 6 * c);
+    const double2 b01 = B2[0], b23 = B2[1], b45 = B2[2];
+    const double b[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+    double a[36];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) o[k] = acc[k];
+    for (int q = 0; q < 18; ++q) { const double2 v = A2[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[r] = fma(TRANS ? a[6 * r + kk] : a[6 * kk + r], b[kk], acc[r]);
+  }
+  double2* o = (double2*)(out + (size_t)s * 36 + 6 * c);
+  o[0] = make_double2(acc[0], acc[1]);
+  o[1] = make_double2(acc[2], acc[3]);
+  o[2] = make_double2(acc[4], acc[5]);
 }
 
 // P[s] <- P[s] W_c^T, c = p_col[s] (W_c lower triangular, row-major): the prolongator into the block-Jacobi-SCALED
