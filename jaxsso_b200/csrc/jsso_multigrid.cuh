@@ -150,8 +150,9 @@ mg_smooth_prolongator_kernel(int nnz_p, const int32_t* __restrict__ p_row, const
 // out[s] = sum_k op(L[l_k]) * R[r_k]   (TRANS: op = transpose).  Six threads per output block, thread c owns column
 // c: it reads column c of R (48 contiguous bytes) and the whole L block (the six threads read the same 288 bytes, one
 // set of sectors), and the six columns leave as 288 contiguous bytes.  Every entry is summed in the order of the
-// thread-per-block form it replaces (4.3 + 2.5 ms for the two Galerkin products of a numeric setup at 1M quads: 36
-// accumulators and 72 strided 8-byte loads per product and thread) -- bitwise the same hierarchy.
+// thread-per-block form it replaced -- bitwise the same hierarchy.  Measured at 1M quads: 4.4 + 2.4 ms for the two
+// Galerkin products of a numeric setup, the same as the thread-per-block form (4.3 + 2.5 ms): coalescing was not the
+// limit (profiles/r2x_launches_numeric_setup.txt); ~7 GB of DRAM traffic would be 1.1 ms.
 constexpr int MG_PROD_THREADS = 192;   // 32 output blocks per CTA
 template <int TRANS>
 __global__ void __launch_bounds__(MG_PROD_THREADS)
