@@ -286,7 +286,10 @@ int jsso_backward(jsso_handle* h, const double* crds_d, const double* prop_q_d, 
 
 /* ---- host-buffer convenience (end-to-end path: H2D, forward, backward, D2H) ------- */
 /* Strain-energy objective 0.5 f.u (SSO_model.py:297-301) and its gradient.
- * All pointers are HOST pointers; d_* outputs may be NULL. */
+ * All pointers are HOST pointers; d_* outputs may be NULL.  Page-locked buffers (jsso_host_alloc_pinned,
+ * cudaHostAlloc, cudaHostRegister) are the source / target of the DMA themselves; pageable ones are staged through the
+ * handle's pinned buffers with a threaded memcpy (JSSO_HOST_THREADS, default min(8, cores)).  With opts->use_x0 the
+ * content of u_h is the initial guess of the solve.  JSSO_ERR_NOCONV still fills every output (best iterate). */
 int jsso_value_and_grad_host(jsso_handle* h, const double* crds_h, const double* prop_q_h,
                              const double* prop_b_h, const double* f_h, double* value_out, double* u_h,
                              double* d_crds_h, double* d_prop_q_h, double* d_prop_b_h,
