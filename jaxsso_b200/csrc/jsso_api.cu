@@ -202,15 +202,6 @@ struct jsso_handle {
   int mg_graph_level = -1, mg_graph_deg = 0;
   const double* mg_graph_b = nullptr;
   double* mg_graph_x = nullptr;
-  // the smallest levels (<= cluster_rows block rows; default on, JSSO_MG_CLUSTER=0 off) as one thread-block cluster
-  // walking a device-resident list of products (mg_tail_cluster_kernel): a node of the coarse graph
-  bool mg_cluster = true;
-  int cluster_rows = 3000, cluster_size = 0;   // size 0: cluster launches not available
-  int mg_cluster_level = -1;                   // first level the cluster kernel takes (-1: none), set by the numeric setup
-  MgTailPlan* mg_tail_dev = nullptr;
-  MgTailPlan mg_tail_host;
-  const double* mg_tail_b = nullptr;
-  double* mg_tail_x = nullptr;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
@@ -384,31 +375,6 @@ static int handle_upload(jsso_handle* h, const std::vector<int32_t>& cq, const s
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_persistent_kernel, RED_BLOCK, 0));
     h->coop_blocks = coop ? std::min(RED_MAX_BLOCKS, occ * prop.multiProcessorCount) : 0;
   }
-#ifdef JSSO_EMU   // CPU test harness: the cluster kernel runs as ONE CTA; opt-in so that the graph of kernels stays covered
-  h->cluster_size = std::getenv("EMU_CLUSTER_KERNEL") ? 1 : 0;
-#else
-  {
-    // largest cluster of mg_tail_cluster_kernel CTAs the device schedules: 16 (non-portable size) or 8
-    int want = 16;
-    if (const char* e = std::getenv("JSSO_MG_CLUSTER_SIZE")) want = std::max(1, std::min(16, std::atoi(e)));
-    if (want > 8 && cudaFuncSetAttribute(mg_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-      cudaGetLastError();
-      want = 8;
-    }
-    for (; want >= 1 && h->cluster_size == 0; want = (want > 8 ? 8 : want / 2)) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(want); cfg.blockDim = dim3(MG_TAIL_THREADS);
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int n_cl = 0;
-      if (cudaOccupancyMaxActiveClusters(&n_cl, mg_tail_cluster_kernel, &cfg) == cudaSuccess && n_cl >= 1) h->cluster_size = want;
-      else cudaGetLastError();
-      if (want == 1) break;
-    }
-  }
-#endif
   CK(cudaFuncSetAttribute(assemble_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           FUSED_SMEM_DOUBLES * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(assemble_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -522,7 +488,6 @@ void jsso_destroy(jsso_handle* h) {
   if (h->st_c) cudaStreamDestroy(h->st_c);
   if (h->mg_graph_exec) cudaGraphExecDestroy(h->mg_graph_exec);
   if (h->st_cap) cudaStreamDestroy(h->st_cap);
-  if (h->mg_tail_dev) cudaFree(h->mg_tail_dev);
   for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_adj) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_prof) if (e) cudaEventDestroy(e);
@@ -1219,8 +1184,6 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
       if (h->mg_power_iters >= 30) h->mg_power_safety = 1.15;
     }
     if (const char* eg = std::getenv("JSSO_MG_GRAPH")) h->mg_graph = eg[0] != '0';   // A/B switch (default on)
-    if (const char* ec = std::getenv("JSSO_MG_CLUSTER")) h->mg_cluster = ec[0] != '0';   // A/B switch (default on)
-    if (const char* er = std::getenv("JSSO_MG_CLUSTER_ROWS")) h->cluster_rows = std::max(0, std::atoi(er));
     // binary16 storage of the fine-level V-cycle matrix (the block-Jacobi-scaled matrix has unit diagonal blocks and
     // |entries| <= 1); JSSO_MG_FP16=0 keeps FP32 (A/B switch)
     const char* e16 = std::getenv("JSSO_MG_FP16");
@@ -1531,7 +1494,6 @@ static inline void mgd_range(const jsso_handle* h, int l, int& s, int& n);
 static int mgd_exchange(jsso_handle* h, int l, double* v, cudaStream_t st);
 static int mgd_reduce_read(jsso_handle* h, int slot, int count, cudaStream_t st);
 static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st);
-static int mg_tail_prepare(jsso_handle* h, cudaStream_t st);
 static int mgd_allgather(jsso_handle* h, int l, double* v, cudaStream_t st);
 
 // The coarse matrix of coarsening step l in block-Jacobi-scaled form: factor its diagonal blocks (W_c = L_c^-1),
@@ -1748,7 +1710,6 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   mg_dense_invert_kernel<<<1, 1024, 0, st>>>(nc, h->mg_dense);
   CKL("mg_dense_invert_kernel");
   pt_.mark("dense_inverse");
-  if ((rc = mg_tail_prepare(h, st))) return rc;
   h->mg_ready = true;
   return JSSO_OK;
 }
@@ -2068,82 +2029,8 @@ static int mg_lin_level(jsso_handle* h, int l, int s, int n, const double* x, do
 // i.e. 4 launches and ~9 vector passes per level instead of 8 launches and ~20.  On several GPUs the levels
 // l < n_dist work on this rank's rows, with a halo exchange before every product that gathers a vector other ranks
 // have just written; b / x are full-length level vectors.
-// The list of products of the fused V-cycle from level l down and up again, for mg_tail_cluster_kernel.  False when a
-// level does not have the FP32 storage the kernel reads or the list does not fit.
-static bool mg_tail_ops(jsso_handle* h, int l, double* b, double* x, MgTailPlan& T) {
-  const int nl = (int)h->mg.size();
-  auto push = [&](const MgTailOp& o) {
-    if (T.n_ops >= MG_TAIL_MAX_OPS) return false;
-    T.op[T.n_ops++] = o;
-    return true;
-  };
-  if (l == nl) {
-    MgTailOp o{};
-    o.kind = 1; o.n_row = 6 * mg_matrix(h, nl).n; o.xrow = h->mg_dense; o.x = b; o.y = x;
-    return push(o);
-  }
-  jsso_handle::MgLevel& m = h->mg[l];
-  const MgMat A = mg_matrix(h, l);
-  if (!A.v32 || !m.P32 || !m.Pt32) return false;
-  const double it = 1.0 / (0.625 * m.lam);
-  double* bc = (l + 1 < nl) ? h->mg[l + 1].b : h->mg_cb;
-  double* xc = (l + 1 < nl) ? h->mg[l + 1].x : h->mg_cx;
-  auto product = [&](const int32_t* rp, const int32_t* ci, const float* v, int n_row, const double* xin, double* y,
-                     const double* bvec, const double* xrow, double ca, double cb, double cc) {
-    MgTailOp o{};
-    o.rp = rp; o.ci = ci; o.v = v; o.x = xin; o.y = y; o.bvec = bvec; o.xrow = xrow; o.ca = ca; o.cb = cb; o.cc = cc;
-    o.n_row = n_row; o.kind = 2;
-    return push(o);
-  };
-  if (!product(A.rp, A.ci, A.v32, m.n_f, b, m.r, b, nullptr, 1.0, 0.0, -it)) return false;            // r0 = b - A b / theta
-  if (!product(m.pt_rowptr, m.pt_col, m.Pt32, m.n_c, m.r, bc, nullptr, nullptr, 0.0, 0.0, 1.0)) return false;   // b_c = P^T r0
-  if (!mg_tail_ops(h, l + 1, bc, xc, T)) return false;
-  if (!product(m.p_rowptr, m.p_col, m.P32, m.n_f, xc, m.d, b, nullptr, it, 0.0, 1.0)) return false;     // x1 = b / theta + P x_c
-  return product(A.rp, A.ci, A.v32, m.n_f, m.d, x, b, m.d, it, 1.0, -it);                               // x = x1 + (b - A x1) / theta
-}
-// called at the end of every numeric setup (the smoother coefficients are part of the list): which levels the cluster
-// kernel takes, and its list of products on the device
-static int mg_tail_prepare(jsso_handle* h, cudaStream_t st) {
-  h->mg_cluster_level = -1;
-  if (!(h->mg_cluster && h->mg_fp32 && h->cluster_size > 0)) return JSSO_OK;
-  const int nl = (int)h->mg.size();
-  const int l_min = std::max(1, h->mgd.n_rank > 1 ? h->mgd.n_dist : 1);   // only levels that are whole on this rank
-  int lc = -1;
-  for (int l = l_min; l < nl; ++l) if (mg_matrix(h, l).n <= h->cluster_rows) { lc = l; break; }
-  if (lc < 0) return JSSO_OK;
-  MgTailPlan& T = h->mg_tail_host;
-  T.n_ops = 0; T.pad = 0;
-  double* b = h->mg[lc].b;
-  double* x = h->mg[lc].x;
-  if (!mg_tail_ops(h, lc, b, x, T)) return JSSO_OK;
-  if (!h->mg_tail_dev) CK(cudaMalloc(&h->mg_tail_dev, sizeof(MgTailPlan)));
-  CK(cudaMemcpyAsync(h->mg_tail_dev, &T, sizeof(MgTailPlan), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));                       // the host copy may change with the next setup
-  h->mg_cluster_level = lc; h->mg_tail_b = b; h->mg_tail_x = x;
-  return JSSO_OK;
-}
-static int mg_tail_launch(jsso_handle* h, cudaStream_t st) {
-  const MgTailPlan* plan = h->mg_tail_dev;
-  const double* stop = h->mg_scal;
-#ifdef JSSO_EMU
-  mg_tail_cluster_kernel<<<1, MG_TAIL_THREADS, 0, st>>>(plan, stop);
-  CKL("mg_tail_cluster_kernel");
-#else
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(h->cluster_size); cfg.blockDim = dim3(MG_TAIL_THREADS); cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = h->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, mg_tail_cluster_kernel, plan, stop));
-  LAUNCHED();
-#endif
-  return JSSO_OK;
-}
-
 static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bool want_dot, cudaStream_t st) {
   const int nl = (int)h->mg.size();
-  if (l == h->mg_cluster_level && b == h->mg_tail_b && x == h->mg_tail_x && !want_dot) return mg_tail_launch(h, st);
   int rc;
   if (l == nl) {
     const int nc = 6 * mg_matrix(h, nl).n;
@@ -2217,7 +2104,9 @@ static int mg_vcycle_fused_level(jsso_handle* h, int l, double* b, double* x, bo
 // numeric setup on a private stream (the smoother coefficients are kernel arguments), replayed into the caller's.
 // (Tried in round 2 and removed: the same products as ONE cooperative kernel walking a device-resident list with grid
 // barriers in between -- ~11 us per phase against ~7 us per kernel node of the graph, 1.41 vs 1.37 ms per iteration at 1M
-// quads, 0.94 vs 0.89 ms on two GPUs; profiles/r2t_coarse_tail_cooperative_kernel_ab.txt.)
+// quads, 0.94 vs 0.89 ms on two GPUs; profiles/r2t_coarse_tail_cooperative_kernel_ab.txt.  And the smallest levels only
+// (<= 3000 rows) as one thread-block CLUSTER with the hardware cluster barrier: 7.4 us per phase, no better than a graph
+// node -- these levels cost their chains of dependent L2 loads, not launch gaps; profiles/r2y_smallest_levels_cluster_kernel_ab.txt.)
 static int mg_coarse_graphed(jsso_handle* h, int l, double* b, double* x, cudaStream_t st) {
   if (!h->mg_graph) return mg_vcycle_fused_level(h, l, b, x, false, st);
   if (h->mg_graph_exec && (h->mg_graph_level != l || h->mg_graph_b != b || h->mg_graph_x != x || h->mg_graph_deg != -1)) {

@@ -819,79 +819,6 @@ bsr_spmv_rp_kernel(int n_row, const int32_t* __restrict__ rowptr, const int32_t*
   }
 }
 
-// ---- the smallest levels of the fused V-cycle as ONE thread-block cluster -----------------------------------------
-// Levels with a few thousand rows are pure latency: as separate kernels (nodes of the coarse graph) each of their four
-// products costs ~7 us for ~3 us of dependent loads.  One cluster of CTAs walks the whole list of products instead --
-// y = ca b + cb x_row + cc A x on FP32 row-pair-major blocks with a warp per row (kind 2), the dense coarsest solve
-// y = M x (kind 1) -- separated by the hardware cluster barrier (barrier.cluster, release / acquire: ~0.2 us, and it
-// invalidates L1, so the vectors written by the other CTAs of the cluster are read from L2).  A grid-wide cooperative
-// barrier in the same role was measured at ~11 us per phase and lost against the graph
-// (profiles/r2t_coarse_tail_cooperative_kernel_ab.txt).  The descriptors are copied to shared memory once.
-constexpr int MG_TAIL_MAX_OPS = 41;
-constexpr int MG_TAIL_THREADS = 512;
-struct MgTailOp {
-  const int32_t* rp; const int32_t* ci; const float* v;
-  const double* x; double* y; const double* bvec; const double* xrow;   // kind 1: xrow = dense [A | A^-1], row-major
-  double ca, cb, cc;
-  int n_row, kind;
-};
-struct MgTailPlan { int n_ops, pad; MgTailOp op[MG_TAIL_MAX_OPS]; };
-static_assert(sizeof(MgTailOp) % 8 == 0, "descriptors are copied as 8-byte words");
-
-__device__ inline void cluster_barrier() {
-#ifdef JSSO_EMU   // CPU test harness: the kernel runs as ONE CTA there
-  __syncthreads();
-#else
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-#endif
-}
-
-__global__ void __launch_bounds__(MG_TAIL_THREADS)
-mg_tail_cluster_kernel(const MgTailPlan* __restrict__ plan, const double* stop) {
-  if (mgs_stopped(stop)) return;                       // the same decision in every CTA: nobody reaches a barrier
-  __shared__ MgTailOp ops[MG_TAIL_MAX_OPS];
-  const int n_ops = plan->n_ops;
-  {
-    const unsigned long long* src = (const unsigned long long*)plan->op;
-    unsigned long long* dst = (unsigned long long*)ops;
-    const int n_word = n_ops * (int)(sizeof(MgTailOp) / 8);
-    for (int i = threadIdx.x; i < n_word; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warp = (gridDim.x * blockDim.x) >> 5;
-  for (int i = 0; i < n_ops; ++i) {
-    const MgTailOp& o = ops[i];
-    if (o.kind == 2) {
-      const double* bvec = o.bvec;
-      const double* xrow = o.xrow;
-      double* y = o.y;
-      const double ca = o.ca, cb = o.cb, cc = o.cc;
-      auto epilogue = [=](int r, double u0, double u1) -> double {
-        if (lane < 3) {
-          const size_t off = 6 * (size_t)r + 2 * lane;
-          double2 v = make_double2(cc * u0, cc * u1);
-          if (bvec) { const double2 bv = *(const double2*)(bvec + off); v.x = fma(ca, bv.x, v.x); v.y = fma(ca, bv.y, v.y); }
-          if (xrow) { const double2 xv = *(const double2*)(xrow + off); v.x = fma(cb, xv.x, v.x); v.y = fma(cb, xv.y, v.y); }
-          *(double2*)(y + off) = v;
-        }
-        return 0.0;
-      };
-      bsr_rows_pipelined(warp, n_warp, lane, o.n_row, o.rp, o.ci, o.v, o.x, epilogue);
-    } else {
-      const int n = o.n_row;
-      for (int row = warp; row < n; row += n_warp) {
-        const double* a = o.xrow + (size_t)row * 2 * n + n;
-        double sum = 0.0;
-        for (int j = lane; j < n; j += 32) sum = fma(a[j], o.x[j], sum);
-        sum = warp_sum(sum);
-        if (lane == 0) o.y[row] = sum;
-      }
-    }
-    cluster_barrier();
-  }
-}
-
 // Short rows (prolongators: 1-4 blocks per row) in the FP32 row-pair-major layout: one THREAD per
 // (block row, row pair), no shuffles -- a warp works on ten rows at once instead of one, which is what
 // hides the rowptr -> colidx -> x load chain when rows are this short.  MODE as above.

@@ -18,7 +18,7 @@ CONFIGS = [{}, {'JSSO_MG_FP16': '0'}, {'JSSO_MG_GRAPH': '0'}] if len(sys.argv) <
 if os.environ.get('MG_SWITCH_CONFIGS'):        # a JSON list of environments, e.g. '[{}, {"JSSO_MG_POLL": "4"}]'
     CONFIGS = json.loads(os.environ['MG_SWITCH_CONFIGS'])
 DEGREES = tuple(int(d) for d in os.environ.get('MG_SWITCH_DEGREES', '1,2').split(','))
-KEYS = tuple(sorted({k for c in CONFIGS for k in c})) + ('JSSO_MG_FP16', 'JSSO_MG_POLL', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64', 'JSSO_MG_CLUSTER')
+KEYS = tuple(sorted({k for c in CONFIGS for k in c})) + ('JSSO_MG_FP16', 'JSSO_MG_POLL', 'JSSO_MG_GRAPH', 'JSSO_MG_FP64')
 for cfg in CONFIGS:
     for k in KEYS:
         os.environ.pop(k, None)

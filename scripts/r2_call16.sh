@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, GPU call 16 (one GPU): the smallest multigrid levels as one thread-block-cluster kernel
+# Round 2, GPU call 16 (one GPU): the smallest multigrid levels as one thread-block-cluster kernel (since removed)
 # (mg_tail_cluster_kernel) -- GPU tests, A/B against separate graph nodes over cluster size and row threshold, launch list.
 set -u
 mkdir -p gpurun_out

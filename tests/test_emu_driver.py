@@ -205,27 +205,6 @@ def test_graph_captured_vcycle(emu_api):
     assert all(i == d['iters_single'] for i in d['iters_dist'])
 
 
-def test_smallest_levels_as_one_cluster_kernel(emu_api):
-    """mg_tail_cluster_kernel: the levels with at most JSSO_MG_CLUSTER_ROWS rows run as one kernel that walks a
-    device-resident list of products with a cluster barrier between them (a node of the coarse graph).  The emulator
-    runs it as a one-CTA grid (EMU_CLUSTER_KERNEL=1): same iteration count (+-1: the prolongation rows are summed by a
-    warp instead of a thread) and solution as the separate kernels, fewer launches without the graph, also as the
-    replicated tail of the distributed solve and across repeated numeric setups (the list is rebuilt)."""
-    base = run(emu_api, 'mg', 30, 1, env={'JSSO_MG_GRAPH': '0'})
-    c = run(emu_api, 'mg', 30, 1, env={'JSSO_MG_GRAPH': '0', 'EMU_CLUSTER_KERNEL': '1'})
-    assert c['mg_converged'] and abs(c['mg_iters'] - base['mg_iters']) <= 1 and c['mg_err'] <= 1e-8
-    assert c['mg_launches'] <= base['mg_launches'] - 3 * c['mg_iters']      # level 1: 4 kernels + dense solve -> 1 launch
-    off = run(emu_api, 'mg', 30, 1, env={'JSSO_MG_GRAPH': '0', 'EMU_CLUSTER_KERNEL': '1', 'JSSO_MG_CLUSTER': '0'})
-    assert off['mg_launches'] == base['mg_launches'] and off['mg_iters'] == base['mg_iters']
-    g = run(emu_api, 'mg', 30, 1, env={'EMU_CLUSTER_KERNEL': '1'})           # as a node of the graph
-    assert g['mg_converged'] and g['mg_iters'] == c['mg_iters'] and g['mg_err'] <= 1e-8
-    d = run(emu_api, 'dist', 2, 30, 500, 1, 'p2p', env={'EMU_CLUSTER_KERNEL': '1'})
-    assert d['converged'] and d['identical_on_all_ranks'] and d['err_vs_oracle'] <= 1e-8
-    assert all(abs(i - d['iters_single']) <= 1 for i in d['iters_dist'])
-    res = run(emu_api, 'benchleg', 2, 30, 500, 'natural', env={'EMU_CLUSTER_KERNEL': '1'})
-    assert abs(res['leg']['pcg_iterations'] - res['iters_single']) <= 1 and res['u_err_vs_oracle'] <= 1e-8 and res['g_err'] <= 1e-6
-
-
 @pytest.mark.parametrize('world,size,min_dist,deg,env', [
     (2, 12, 10, 1, {}), (4, 12, 10, 1, {'EMU_JITTER': '3000'}),
     (4, 16, 10, 2, {'JSSO_MG_POLL': '3', 'EMU_JITTER': '1000'})])

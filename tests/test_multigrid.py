@@ -216,15 +216,13 @@ def test_fp16_fine_level_keeps_the_iteration_count(monkeypatch):
 @pytest.mark.gpu
 def test_coarse_levels_graph_equals_kernel_by_kernel(monkeypatch):
     """The coarse levels of the fused V-cycle are replayed as one CUDA graph (captured once per numeric setup);
-    JSSO_MG_GRAPH=0 launches the same kernels one by one: same iteration count, u equal to rounding, fewer launches.
-    The smallest levels are one thread-block-cluster kernel in both; JSSO_MG_CLUSTER=0 switches that off."""
+    JSSO_MG_GRAPH=0 launches the same kernels one by one: same iteration count, u equal to rounding, fewer launches."""
     from jaxsso_b200 import _native as nat
     md = meshes.plate(256)        # level 1 has ~7 300 rows of 9 blocks: row-pair and warp-per-row products in the graph
     D = nat.DeviceArray
     res = {}
-    for tag, env in (('graph', {}), ('kernels', {'JSSO_MG_GRAPH': '0'}), ('no_cluster', {'JSSO_MG_CLUSTER': '0'})):
+    for tag, env in (('graph', {}), ('kernels', {'JSSO_MG_GRAPH': '0'})):
         monkeypatch.delenv('JSSO_MG_GRAPH', raising=False)
-        monkeypatch.delenv('JSSO_MG_CLUSTER', raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
@@ -240,8 +238,3 @@ def test_coarse_levels_graph_equals_kernel_by_kernel(monkeypatch):
     assert res['graph'][2] and res['kernels'][2] and res['graph'][1] == res['kernels'][1]
     assert np.linalg.norm(res['graph'][0] - res['kernels'][0]) <= 1e-10 * np.linalg.norm(res['kernels'][0])
     assert res['graph'][3] < res['kernels'][3] - 3 * res['graph'][1]
-    # the levels with <= 3 000 rows (here levels 2 and 3 + the dense solve) are ONE cluster kernel inside that graph
-    # (mg_tail_cluster_kernel); JSSO_MG_CLUSTER=0 keeps them as separate kernels: same solve up to the summation order
-    # of the prolongation rows
-    assert res['no_cluster'][2] and abs(res['no_cluster'][1] - res['graph'][1]) <= 1
-    assert np.linalg.norm(res['graph'][0] - res['no_cluster'][0]) <= 1e-9 * np.linalg.norm(res['no_cluster'][0])
