@@ -203,6 +203,7 @@ struct jsso_handle {
   const double* mg_graph_b = nullptr;
   double* mg_graph_x = nullptr;
   double* mg_dense = nullptr;      // [A | A^-1] of the coarsest level
+  double* mg_dense_ws = nullptr;   // blocked inverse: pivot-block inverse, row panel, column-panel copy
   double *mg_cb = nullptr, *mg_cx = nullptr;   // coarsest-level vectors
   double* mg_scal = nullptr;       // device scalars of the host-driven PCG
   double* mg_scal_host = nullptr;  // pinned
@@ -500,7 +501,7 @@ void jsso_destroy(jsso_handle* h) {
     for (void* p : lv) if (p) cudaFree(p);
   }
   {
-    void* mgp[] = {h->Lfac, h->vals32, h->vals16, h->mg_dense, h->mg_cb, h->mg_cx, h->mg_scal, h->crds_keep};
+    void* mgp[] = {h->Lfac, h->vals32, h->vals16, h->mg_dense, h->mg_dense_ws, h->mg_cb, h->mg_cx, h->mg_scal, h->crds_keep};
     for (void* p : mgp) if (p) cudaFree(p);
     if (h->mg_scal_host) cudaFreeHost(h->mg_scal_host);
   }
@@ -1169,6 +1170,7 @@ extern "C" int jsso_mg_setup(jsso_handle* h, int32_t n_levels, const jsso_mg_lev
     const size_t nc = 6 * (size_t)n_prev;
     if (nc > 6000) return fail(h, JSSO_ERR_ARG, "multigrid: coarsest level too large for the dense solve");
     CK(dalloc(&h->mg_dense, 2 * nc * nc)); CK(dalloc(&h->mg_cb, nc)); CK(dalloc(&h->mg_cx, nc));
+    CK(dalloc(&h->mg_dense_ws, (size_t)MG_DB * MG_DB + (size_t)MG_DB * 2 * nc + (size_t)MG_DB * nc));
     CK(dalloc(&h->Lfac, 36 * (size_t)h->sym.n_node));
     CK(dalloc(&h->mg_scal, MGS_COUNT));
     CK(cudaMemset(h->mg_scal, 0, MGS_COUNT * sizeof(double)));
@@ -1707,8 +1709,26 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
   CKL("mg_dense_from_bsr_kernel");
   mg_dense_fill_kernel<<<C.n, 64, 0, st>>>(C.n, C.rp, C.ci, C.v, h->mg_dense);
   CKL("mg_dense_fill_kernel");
-  mg_dense_invert_kernel<<<1, 1024, 0, st>>>(nc, h->mg_dense);
-  CKL("mg_dense_invert_kernel");
+  static const int dense_single_max = [] { const char* e = std::getenv("JSSO_MG_DENSE_SINGLE_MAX"); return e ? std::atoi(e) : 96; }();
+  if (nc <= dense_single_max) {
+    mg_dense_invert_kernel<<<1, 1024, 0, st>>>(nc, h->mg_dense);
+    CKL("mg_dense_invert_kernel");
+  } else {
+    // blocked Gauss-Jordan over all SMs (see jsso_multigrid.cuh)
+    const int w = 2 * nc;
+    double* pinv = h->mg_dense_ws;
+    double* rpanel = pinv + MG_DB * MG_DB;
+    double* cpanel = rpanel + (size_t)MG_DB * w;
+    for (int k0 = 0; k0 < nc; k0 += MG_DB) {
+      const int nb = std::min(MG_DB, nc - k0);
+      mg_dense_pivot_kernel<<<1, MG_DB * MG_DB, 0, st>>>(w, k0, nb, h->mg_dense, pinv);
+      CKL("mg_dense_pivot_kernel");
+      mg_dense_panel_kernel<<<cdiv((long long)w + (long long)nc * MG_DB, 256), 256, 0, st>>>(nc, w, k0, nb, h->mg_dense, pinv, rpanel, cpanel);
+      CKL("mg_dense_panel_kernel");
+      mg_dense_update_kernel<<<cdiv(w, MG_DU_COLS) * cdiv(nc, MG_DU_ROWS), MG_DU_COLS, 0, st>>>(nc, w, k0, nb, h->mg_dense, rpanel, cpanel);
+      CKL("mg_dense_update_kernel");
+    }
+  }
   pt_.mark("dense_inverse");
   h->mg_ready = true;
   return JSSO_OK;

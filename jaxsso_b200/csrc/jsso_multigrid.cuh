@@ -309,6 +309,92 @@ mg_dense_invert_kernel(int n, double* __restrict__ M) {
     __syncthreads();
   }
 }
+// ---- blocked Gauss-Jordan for a coarsest level of up to a few thousand unknowns ----------------------------------
+// [A | I] -> [I | A^-1] in pivot blocks of MG_DB rows, three launches per block, all SMs: (1) invert the pivot block
+// W[K,K] in shared memory (no pivoting: A is SPD, so is every pivot block of its Schur complements; an empty row becomes
+// an identity row as in the one-CTA kernel above), (2) row panel W[K,:] <- P^-1 W[K,:] (kept in `rpanel`) and a copy of
+// the column panel W[:,K] (`cpanel`), (3) W[i,:] -= cpanel[i,:] rpanel for every other row.  2 n^3 multiply-adds in
+// n / 32 steps: 0.5 ms for n = 1020 where the one-CTA kernel (every pivot a sweep of the whole matrix through one SM)
+// would need tens of milliseconds -- which is what lets the hierarchy stop one level earlier (section 4 of DESIGN.md:
+// a level of 170 nodes costs four latency-bound products + the dense solve per V-cycle, a dense solve of it ~5 us).
+constexpr int MG_DB = 32;
+__global__ void __launch_bounds__(MG_DB * MG_DB)
+mg_dense_pivot_kernel(int w, int k0, int nb, const double* __restrict__ W, double* __restrict__ pinv) {
+  __shared__ double A[MG_DB][MG_DB + 1], B[MG_DB][MG_DB + 1];
+  __shared__ double piv;
+  const int i = threadIdx.x / MG_DB, j = threadIdx.x % MG_DB;
+  A[i][j] = (i < nb && j < nb) ? W[(size_t)(k0 + i) * w + k0 + j] : (i == j ? 1.0 : 0.0);
+  B[i][j] = (i == j) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    if (i == 0 && j == 0) {
+      double p = A[k][k];
+      if (!(fabs(p) > 1e-300)) { p = 1.0; A[k][k] = 1.0; }
+      piv = 1.0 / p;
+    }
+    __syncthreads();
+    if (i == k) { A[k][j] *= piv; B[k][j] *= piv; }
+    __syncthreads();
+    const double f = A[i][k];
+    __syncthreads();
+    if (i != k) { A[i][j] = fma(-f, A[k][j], A[i][j]); B[i][j] = fma(-f, B[k][j], B[i][j]); }
+    __syncthreads();
+  }
+  pinv[i * MG_DB + j] = (i < nb && j < nb) ? B[i][j] : 0.0;
+}
+// threads [0, w): column j of the row panel; threads [w, w + n * MG_DB): one entry of the column-panel copy
+__global__ void __launch_bounds__(256)
+mg_dense_panel_kernel(int n, int w, int k0, int nb, double* __restrict__ W, const double* __restrict__ pinv,
+                      double* __restrict__ rpanel, double* __restrict__ cpanel) {
+  __shared__ double P[MG_DB * MG_DB];
+  for (int t = threadIdx.x; t < MG_DB * MG_DB; t += blockDim.x) P[t] = pinv[t];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < w) {
+    const int j = (int)t;
+    double old[MG_DB];
+#pragma unroll
+    for (int k = 0; k < MG_DB; ++k) old[k] = (k < nb) ? W[(size_t)(k0 + k) * w + j] : 0.0;
+    for (int i = 0; i < nb; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < MG_DB; ++k) v = fma(P[i * MG_DB + k], old[k], v);
+      W[(size_t)(k0 + i) * w + j] = v;
+      rpanel[(size_t)i * w + j] = v;
+    }
+  } else if (t < (long long)w + (long long)n * MG_DB) {
+    const long long q = t - w;
+    const int i = (int)(q / MG_DB), k = (int)(q - (long long)i * MG_DB);
+    const bool pivot_row = i >= k0 && i < k0 + nb;            // rewritten by the threads above and not used by the update
+    cpanel[q] = (k < nb && !pivot_row) ? W[(size_t)i * w + k0 + k] : 0.0;
+  }
+}
+constexpr int MG_DU_ROWS = 16, MG_DU_COLS = 128;
+__global__ void __launch_bounds__(MG_DU_COLS)
+mg_dense_update_kernel(int n, int w, int k0, int nb, double* __restrict__ W, const double* __restrict__ rpanel,
+                       const double* __restrict__ cpanel) {
+  __shared__ double R[MG_DB][MG_DU_COLS];
+  __shared__ double Cs[MG_DU_ROWS][MG_DB];
+  const int n_col_tile = (w + MG_DU_COLS - 1) / MG_DU_COLS;       // 1-D grid: column tiles fastest
+  const int j = (blockIdx.x % n_col_tile) * MG_DU_COLS + threadIdx.x, i0 = (blockIdx.x / n_col_tile) * MG_DU_ROWS;
+  for (int k = 0; k < MG_DB; ++k) R[k][threadIdx.x] = (k < nb && j < w) ? rpanel[(size_t)k * w + j] : 0.0;
+  for (int t = threadIdx.x; t < MG_DU_ROWS * MG_DB; t += MG_DU_COLS) {
+    const int r = t / MG_DB, k = t - r * MG_DB;
+    Cs[r][k] = (i0 + r < n) ? cpanel[(size_t)(i0 + r) * MG_DB + k] : 0.0;    // zero on the pivot rows themselves
+  }
+  __syncthreads();
+  if (j >= w) return;
+#pragma unroll 4
+  for (int r = 0; r < MG_DU_ROWS; ++r) {
+    const int i = i0 + r;
+    if (i >= n || (i >= k0 && i < k0 + nb)) continue;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < MG_DB; ++k) acc = fma(Cs[r][k], R[k][threadIdx.x], acc);
+    W[(size_t)i * w + j] -= acc;
+  }
+}
+
 // x = Ainv b with Ainv = right half of M; one warp per row
 __global__ void mg_dense_matvec_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
                                        double* __restrict__ x) {

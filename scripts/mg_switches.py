@@ -22,14 +22,16 @@ KEYS = tuple(sorted({k for c in CONFIGS for k in c})) + ('JSSO_MG_FP16', 'JSSO_M
 for cfg in CONFIGS:
     for k in KEYS:
         os.environ.pop(k, None)
-    os.environ.update(cfg)
+    os.environ.update({k: v for k, v in cfg.items() if k != 'MAX_COARSE'})
     h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
-    if levels is None:
+    mc = int(cfg.get('MAX_COARSE', 256))      # not an environment switch: nodes of the coarsest (dense) level
+    if levels is None or mc not in levels:
         rp, ci = h.pattern()
         t0 = time.perf_counter()
-        levels = multigrid.build_hierarchy(rp, ci)
-        print('symbolic hierarchy %.1f s' % (time.perf_counter() - t0), flush=True)
-    h.mg_setup(levels=levels)
+        levels = dict(levels or {})
+        levels[mc] = multigrid.build_hierarchy(rp, ci, max_coarse_nodes=mc)
+        print('symbolic hierarchy (max_coarse_nodes %d): %.1f s, %d levels' % (mc, time.perf_counter() - t0, len(levels[mc])), flush=True)
+    h.mg_setup(levels=levels[mc])
     for deg in DEGREES:
         best = None
         for rep in range(3):

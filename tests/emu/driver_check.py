@@ -40,7 +40,7 @@ def mixed(n):
     return md
 
 
-def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=8):
+def solve(md, precond, deg=1, rtol=1e-10, dist=None, max_coarse=int(os.environ.get('EMU_MAX_COARSE', '8'))):
     h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
     info, cnt = None, (0, 0)
     if precond == 'multigrid':

@@ -77,6 +77,19 @@ def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
         assert abs(res['mg_iters'] - base['mg_iters']) <= 2
 
 
+def test_blocked_dense_inverse_of_a_larger_coarsest_level(emu_api):
+    """The hierarchy stops at <= 256 nodes by default and the coarsest level is inverted by a blocked Gauss-Jordan over
+    all SMs (pivot blocks of 32 rows, three kernels per block; a partial last block here: 660 = 20 x 32 + 20 unknowns):
+    the same solve as with the one-CTA kernel, and fewer levels mean fewer iterations than coarsening down to 8 nodes."""
+    blocked = run(emu_api, 'mg', 30, 1, env={'EMU_MAX_COARSE': '256'})
+    single = run(emu_api, 'mg', 30, 1, env={'EMU_MAX_COARSE': '256', 'JSSO_MG_DENSE_SINGLE_MAX': '100000'})
+    deep = run(emu_api, 'mg', 30, 1)
+    assert blocked['mg_converged'] and blocked['mg_err'] <= 1e-8
+    assert blocked['mg_iters'] == single['mg_iters'] and abs(blocked['mg_err'] - single['mg_err']) <= 1e-10
+    assert blocked['mg_launches'] > single['mg_launches'] + 40          # 21 pivot blocks x 3 kernels against 1
+    assert blocked['mg_iters'] <= deep['mg_iters']
+
+
 @pytest.mark.parametrize('world,size,min_dist,deg', [(2, 12, 10, 1), (2, 12, 1000, 2), (4, 16, 10, 2)])
 def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size, min_dist, deg):
     """jsso_mg_set_dist + mg_solve_dist (the REAL C++ driver, not its Python replay) on `world` rank threads with
