@@ -407,7 +407,7 @@ class Handle:
                  allow=(JSSO_ERR_NOCONV,) if allow_noconv else ())
         return st
 
-    def mg_setup(self, levels=None, max_coarse_nodes=256):
+    def mg_setup(self, levels=None, max_coarse_nodes=64):
         """Build (or take) the symbolic smoothed-aggregation hierarchy and upload it."""
         from . import multigrid
         if levels is None:

@@ -314,9 +314,11 @@ mg_dense_invert_kernel(int n, double* __restrict__ M) {
 // W[K,K] in shared memory (no pivoting: A is SPD, so is every pivot block of its Schur complements; an empty row becomes
 // an identity row as in the one-CTA kernel above), (2) row panel W[K,:] <- P^-1 W[K,:] (kept in `rpanel`) and a copy of
 // the column panel W[:,K] (`cpanel`), (3) W[i,:] -= cpanel[i,:] rpanel for every other row.  2 n^3 multiply-adds in
-// n / 32 steps: 0.5 ms for n = 1020 where the one-CTA kernel (every pivot a sweep of the whole matrix through one SM)
-// would need tens of milliseconds -- which is what lets the hierarchy stop one level earlier (section 4 of DESIGN.md:
-// a level of 170 nodes costs four latency-bound products + the dense solve per V-cycle, a dense solve of it ~5 us).
+// n / 32 steps.  Measured at 1M quads: the default coarsest level (20 nodes, n = 120) 0.51 -> 0.05 ms per numeric setup;
+// n = 1020 (hierarchy stopped one level earlier, max_coarse_nodes = 256) 1.9 ms, where the one-CTA kernel -- every pivot
+// a sweep of the whole matrix through one SM -- would need tens of milliseconds.  Stopping there did NOT pay, which is
+// why 64 nodes stays the default: the 8 MB dense solve costs what the four small products it replaces cost, and the
+// PCG needed 167 instead of 166 iterations (profiles/r2aa_coarsest_level_ab.txt).
 constexpr int MG_DB = 32;
 __global__ void __launch_bounds__(MG_DB * MG_DB)
 mg_dense_pivot_kernel(int w, int k0, int nb, const double* __restrict__ W, double* __restrict__ pinv) {

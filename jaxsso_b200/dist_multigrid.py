@@ -95,7 +95,7 @@ def _permute_pattern(rowptr, colidx, new_of_old):
     return B.indptr.astype(np.int32), B.indices.astype(np.int32)
 
 
-def build_hierarchy_invariant(rowptr_perm, colidx_perm, perm, max_coarse_nodes=256, max_levels=12):
+def build_hierarchy_invariant(rowptr_perm, colidx_perm, perm, max_coarse_nodes=64, max_levels=12):
     """Smoothed-aggregation hierarchy for a RENUMBERED mesh (`perm`: new -> old node order, e.g. from
     `owner_permutation`) whose aggregates are those of the ORIGINAL numbering: the greedy aggregation
     (`multigrid.aggregate`) is order dependent, so aggregating the renumbered graph gives a different -- in

@@ -137,7 +137,7 @@ def build_level(rowptr, colidx, agg, n_c):
                 mem_ptr=mem_ptr, mem=morder, nnz_p=nnz_p, nnz_ap=nnz_ap, nnz_c=c_col.shape[0])
 
 
-def build_hierarchy(rowptr, colidx, max_coarse_nodes=256, max_levels=12):
+def build_hierarchy(rowptr, colidx, max_coarse_nodes=64, max_levels=12):
     """Coarsen until the coarsest level has <= max_coarse_nodes nodes (dense solve there)."""
     levels = []
     rp, ci = np.asarray(rowptr, np.int32), np.asarray(colidx, np.int32)

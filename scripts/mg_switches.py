@@ -24,7 +24,7 @@ for cfg in CONFIGS:
         os.environ.pop(k, None)
     os.environ.update({k: v for k, v in cfg.items() if k != 'MAX_COARSE'})
     h = nat.Handle(md.n_node, md.cnct_quads, md.cnct_beams, md.known, device=0)
-    mc = int(cfg.get('MAX_COARSE', 256))      # not an environment switch: nodes of the coarsest (dense) level
+    mc = int(cfg.get('MAX_COARSE', 64))      # not an environment switch: nodes of the coarsest (dense) level
     if levels is None or mc not in levels:
         rp, ci = h.pattern()
         t0 = time.perf_counter()

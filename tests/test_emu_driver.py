@@ -78,9 +78,9 @@ def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
 
 
 def test_blocked_dense_inverse_of_a_larger_coarsest_level(emu_api):
-    """The hierarchy stops at <= 256 nodes by default and the coarsest level is inverted by a blocked Gauss-Jordan over
-    all SMs (pivot blocks of 32 rows, three kernels per block; a partial last block here: 660 = 20 x 32 + 20 unknowns):
-    the same solve as with the one-CTA kernel, and fewer levels mean fewer iterations than coarsening down to 8 nodes."""
+    """A coarsest level of more than 96 unknowns is inverted by a blocked Gauss-Jordan over all SMs (pivot blocks of 32
+    rows, three kernels per block; a partial last block here: 660 = 20 x 32 + 20 unknowns for max_coarse_nodes = 256):
+    the same solve as with the one-CTA kernel, and fewer levels mean no more iterations than coarsening down to 8 nodes."""
     blocked = run(emu_api, 'mg', 30, 1, env={'EMU_MAX_COARSE': '256'})
     single = run(emu_api, 'mg', 30, 1, env={'EMU_MAX_COARSE': '256', 'JSSO_MG_DENSE_SINGLE_MAX': '100000'})
     deep = run(emu_api, 'mg', 30, 1)
