@@ -314,8 +314,8 @@ mg_dense_invert_kernel(int n, double* __restrict__ M) {
 // W[K,K] in shared memory (no pivoting: A is SPD, so is every pivot block of its Schur complements; an empty row becomes
 // an identity row as in the one-CTA kernel above), (2) row panel W[K,:] <- P^-1 W[K,:] (kept in `rpanel`) and a copy of
 // the column panel W[:,K] (`cpanel`), (3) W[i,:] -= cpanel[i,:] rpanel for every other row.  2 n^3 multiply-adds in
-// n / 32 steps.  Measured at 1M quads: n = 1020 (hierarchy stopped one level earlier, max_coarse_nodes = 256) 1.9 ms,
-// where the one-CTA kernel (0.51 ms for the default coarsest level of 20 nodes, n = 120) -- every pivot
+// n / 32 steps.  Measured at 1M quads: the default coarsest level (20 nodes, n = 120) 0.51 -> 0.16 ms per numeric setup;
+// n = 1020 (hierarchy stopped one level earlier, max_coarse_nodes = 256) 1.9 ms, where the one-CTA kernel -- every pivot
 // a sweep of the whole matrix through one SM -- would need tens of milliseconds.  Stopping there did NOT pay, which is
 // why 64 nodes stays the default: the 8 MB dense solve costs what the four small products it replaces cost, and the
 // PCG needed 167 instead of 166 iterations (profiles/r2aa_coarsest_level_ab.txt).
