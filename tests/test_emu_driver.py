@@ -79,13 +79,13 @@ def test_multigrid_pcg_through_the_emulated_driver(emu_api, fp16):
 
 def test_blocked_dense_inverse_of_a_larger_coarsest_level(emu_api):
     """A coarsest level of more than 96 unknowns is inverted by a blocked Gauss-Jordan over all SMs (pivot blocks of 32
-    rows, three kernels per block; a partial last block here: 49 nodes = 294 = 9 x 32 + 6 unknowns for max_coarse_nodes = 256):
+    rows, three kernels per block; a partial last block here: 36 nodes = 216 = 6 x 32 + 24 unknowns for max_coarse_nodes = 256):
     the same solve as with the one-CTA kernel."""
-    blocked = run(emu_api, 'mg', 20, 1, env={'EMU_MAX_COARSE': '256'})
-    single = run(emu_api, 'mg', 20, 1, env={'EMU_MAX_COARSE': '256', 'JSSO_MG_DENSE_SINGLE_MAX': '100000'})
+    blocked = run(emu_api, 'mg', 16, 1, env={'EMU_MAX_COARSE': '256'})
+    single = run(emu_api, 'mg', 16, 1, env={'EMU_MAX_COARSE': '256', 'JSSO_MG_DENSE_SINGLE_MAX': '100000'})
     assert blocked['mg_converged'] and blocked['mg_err'] <= 1e-8
     assert blocked['mg_iters'] == single['mg_iters'] and abs(blocked['mg_err'] - single['mg_err']) <= 1e-10
-    assert blocked['mg_launches'] > single['mg_launches'] + 20          # 10 pivot blocks x 3 kernels against 1
+    assert blocked['mg_launches'] > single['mg_launches'] + 10          # 7 pivot blocks x 3 kernels against 1
 
 
 @pytest.mark.parametrize('world,size,min_dist,deg', [(2, 12, 10, 1), (2, 12, 1000, 2), (4, 16, 10, 2)])
