@@ -606,49 +606,32 @@ int jsso_beam_ke(jsso_handle* h, const double* crds, const double* prop_b, doubl
   return JSSO_OK;
 }
 
-int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, int apply_bc,
-                  void* stream) {
-  if (!h) return JSSO_ERR_ARG;
-  NEED_GPU();
-  CK(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
-  AsmArgs A;
-  A.crds = crds; A.cnct_q = h->cnct_q; A.prop_q = prop_q; A.cnct_b = h->cnct_b; A.prop_b = prop_b;
-  A.chunk_blk = h->chunk_blk; A.chunk_el_ptr = h->chunk_el_ptr; A.chunk_els = h->chunk_els;
-  A.blk_perm = h->blk_perm; A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
-  A.blk_row = h->blk_row; A.colidx = h->colidx; A.node_mask = h->node_mask;
-  A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
-  if (h->sym.nnzb() > 0 && h->asm_tasks) {
-    const int nq = h->sym.n_quad;
-    // distributed numeric setup (jsso_mg_set_dist_setup): only the tasks that touch the rows this rank reads, and
-    // the geometry records of the quads they stage
-    const bool part = h->mgd.setup_on;
-    const int q0 = part ? h->mgd.asm_q0 : 0, q1 = part ? h->mgd.asm_q1 : nq;
-    const int t0 = part ? h->mgd.asm_t0 : 0, t1 = part ? h->mgd.asm_t1 : h->sym.n_task();
-    if (h->prof) CK(cudaEventRecord(h->ev_prof[0], st));
-    if (q1 > q0) {
-      quad_geometry_kernel<<<cdiv(q1 - q0, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
-          q1 - q0, crds, h->cnct_q + 4 * (size_t)q0, prop_q + 5 * (size_t)q0, h->quad_rec + (size_t)q0 * REC_GLD, h->flags);
-      CKL("quad_geometry_kernel");
-    }
-    if (h->prof) CK(cudaEventRecord(h->ev_prof[1], st));
-    TaskArgs T;
-    T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta + t0; T.task_els = h->task_els;
-    T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
-    T.blk_item_ptr = h->blk_item_ptr;
-    T.crds = crds; T.cnct_b = h->cnct_b; T.prop_b = prop_b;
-    T.vals = h->vals; T.flags = h->flags; T.n_quad = nq; T.n_task = t1 - t0; T.apply_bc = apply_bc;
-    if (T.n_task > 0) {
-      assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
-                              TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
-      CKL("assemble_tasks_kernel");
-    }
-    if (h->prof) CK(cudaEventRecord(h->ev_prof[2], st));
-  } else if (h->sym.nnzb() > 0) {
-    assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
-    CKL("assemble_fused_kernel");
-  }
+// The two kernels of the warp-task assembly by ranges: geometry records of quads [q0, q1), tasks [t0, t1).  A task
+// writes its own run of block slots and reads only the records of the quads it stages, so any split into ranges gives
+// bitwise the same matrix (used by the distributed numeric setup and by the interleaved host pipeline).
+static int assemble_geometry_range(jsso_handle* h, const double* crds, const double* prop_q, int q0, int q1, cudaStream_t st) {
+  if (q1 <= q0) return JSSO_OK;
+  quad_geometry_kernel<<<cdiv(q1 - q0, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
+      q1 - q0, crds, h->cnct_q + 4 * (size_t)q0, prop_q + 5 * (size_t)q0, h->quad_rec + (size_t)q0 * REC_GLD, h->flags);
+  CKL("quad_geometry_kernel");
+  return JSSO_OK;
+}
+static int assemble_task_range(jsso_handle* h, const double* crds, const double* prop_b, int apply_bc, int t0, int t1,
+                               cudaStream_t st) {
+  if (t1 <= t0) return JSSO_OK;
+  TaskArgs T;
+  T.rec = h->quad_rec; T.task_meta = (const int4*)h->task_meta + t0; T.task_els = h->task_els;
+  T.item_desc = h->item_desc; T.blk_bc = h->blk_bc; T.item_code = h->item_code;
+  T.blk_item_ptr = h->blk_item_ptr;
+  T.crds = crds; T.cnct_b = h->cnct_b; T.prop_b = prop_b;
+  T.vals = h->vals; T.flags = h->flags; T.n_quad = h->sym.n_quad; T.n_task = t1 - t0; T.apply_bc = apply_bc;
+  assemble_tasks_kernel<<<std::min(cdiv(T.n_task, TASK_WARPS), h->task_ctas), 32 * TASK_WARPS,
+                          TASK_WARPS * TASK_SMEM_DOUBLES * sizeof(double), st>>>(T);
+  CKL("assemble_tasks_kernel");
+  return JSSO_OK;
+}
+// bookkeeping after the last kernel of an assembly
+static int assemble_done(jsso_handle* h, const double* crds, int apply_bc, cudaStream_t st) {
   h->assembled = true; h->assembled_bc = apply_bc != 0; h->scaled = false; h->mg_ready = false;
   h->last_crds = nullptr;
   if (!h->mg.empty() && crds) {   // the numeric multigrid setup reads the coordinates at the time of the solve
@@ -657,6 +640,39 @@ int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, cons
     h->last_crds = h->crds_keep;
   }
   return JSSO_OK;
+}
+
+int jsso_assemble(jsso_handle* h, const double* crds, const double* prop_q, const double* prop_b, int apply_bc,
+                  void* stream) {
+  if (!h) return JSSO_ERR_ARG;
+  NEED_GPU();
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  int rc;
+  if (h->sym.nnzb() > 0 && h->asm_tasks) {
+    const int nq = h->sym.n_quad;
+    // distributed numeric setup (jsso_mg_set_dist_setup): only the tasks that touch the rows this rank reads, and
+    // the geometry records of the quads they stage
+    const bool part = h->mgd.setup_on;
+    const int q0 = part ? h->mgd.asm_q0 : 0, q1 = part ? h->mgd.asm_q1 : nq;
+    const int t0 = part ? h->mgd.asm_t0 : 0, t1 = part ? h->mgd.asm_t1 : h->sym.n_task();
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[0], st));
+    if ((rc = assemble_geometry_range(h, crds, prop_q, q0, q1, st))) return rc;
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[1], st));
+    if ((rc = assemble_task_range(h, crds, prop_b, apply_bc, t0, t1, st))) return rc;
+    if (h->prof) CK(cudaEventRecord(h->ev_prof[2], st));
+  } else if (h->sym.nnzb() > 0) {
+    AsmArgs A;
+    A.crds = crds; A.cnct_q = h->cnct_q; A.prop_q = prop_q; A.cnct_b = h->cnct_b; A.prop_b = prop_b;
+    A.chunk_blk = h->chunk_blk; A.chunk_el_ptr = h->chunk_el_ptr; A.chunk_els = h->chunk_els;
+    A.blk_perm = h->blk_perm; A.blk_item_ptr = h->blk_item_ptr; A.item_code = h->item_code; A.item_lel = h->item_lel;
+    A.blk_row = h->blk_row; A.colidx = h->colidx; A.node_mask = h->node_mask;
+    A.vals = h->vals; A.flags = h->flags; A.n_quad = h->sym.n_quad; A.apply_bc = apply_bc;
+    assemble_fused_kernel<<<h->sym.n_chunk(), kChunkBlocks, FUSED_SMEM_DOUBLES * sizeof(double), st>>>(A);
+    CKL("assemble_fused_kernel");
+  }
+  return assemble_done(h, crds, apply_bc, st);
 }
 
 // dst[i*width + k] = src[idx[i]*width + k]: node-row gather between numberings (e.g. the local part
@@ -2657,7 +2673,17 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   CK(h2d(h->s_crds, crds_h, h->h_crds, nc, st));
   CK(h2d(h->s_pq, pq_h, h->h_pq, nq, st));
   CK(h2d(h->s_pb, pb_h, h->h_pb, nb, st));
-  if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
+  // chunked pipeline on the warp-task assembly: the assembly is cut into as many task ranges as the adjoint has quad
+  // ranges and the two alternate on the stream -- tasks k, adjoint k, tasks k + 1, ... -- so that adjoint range k starts
+  // as soon as its slice of u / lam has arrived instead of behind the whole assembly, and its gradients travel back
+  // while the later slices are still coming in (the kernels do not depend on each other: the adjoint recomputes its
+  // geometry).  JSSO_E2E_INTERLEAVE=0: the whole assembly first.
+  static const bool interleave_on = [] { const char* e = std::getenv("JSSO_E2E_INTERLEAVE"); return !(e && e[0] == '0'); }();
+  const bool interleave = interleave_on && h->e2e_chunks > 1 && h->asm_tasks && S.nnzb() > 0 && !h->mgd.setup_on;
+  if (interleave) {
+    CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+    if ((rc = assemble_geometry_range(h, h->s_crds, h->s_pq, 0, S.n_quad, st))) return rc;
+  } else if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
   if (h->e2e_chunks > 1) {
     // chunked pipeline (opt-in, JSSO_E2E_CHUNKS): see the handle fields
     const int K = h->e2e_chunks;
@@ -2673,7 +2699,13 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
     const bool p_dq = want_dq && pinned(dpq_h);
     double* dq_dst = want_dq ? (p_dq ? dpq_h : h->h_dpq) : nullptr;
     int waited = -1;
+    const int n_task = S.n_task();
     for (int c = 0; c < K; ++c) {
+      if (interleave) {
+        const int t0 = (int)((long long)n_task * c / K), t1 = (int)((long long)n_task * (c + 1) / K);
+        if ((rc = assemble_task_range(h, h->s_crds, h->s_pb, 1, t0, t1, st))) return rc;
+        if (c == K - 1 && (rc = assemble_done(h, h->s_crds, 1, st))) return rc;
+      }
       if (h->e2e_wait[c] > waited) { waited = h->e2e_wait[c]; CK(cudaStreamWaitEvent(st, h->ev_up[waited], 0)); }
       const int q0 = h->e2e_qb[c], nqc = h->e2e_qb[c + 1] - q0;
       if ((rc = adjoint_quad_range(h, q0, nqc, h->s_crds, h->s_pq, h->s_f, h->s_u, dc_h != nullptr,
