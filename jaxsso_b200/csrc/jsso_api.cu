@@ -608,7 +608,7 @@ int jsso_beam_ke(jsso_handle* h, const double* crds, const double* prop_b, doubl
 
 // The two kernels of the warp-task assembly by ranges: geometry records of quads [q0, q1), tasks [t0, t1).  A task
 // writes its own run of block slots and reads only the records of the quads it stages, so any split into ranges gives
-// bitwise the same matrix (used by the distributed numeric setup and by the interleaved host pipeline).
+// bitwise the same matrix (the distributed numeric setup assembles only the ranges a rank reads).
 static int assemble_geometry_range(jsso_handle* h, const double* crds, const double* prop_q, int q0, int q1, cudaStream_t st) {
   if (q1 <= q0) return JSSO_OK;
   quad_geometry_kernel<<<cdiv(q1 - q0, G_QUADS), G_THREADS, G_QUADS * QS * sizeof(double), st>>>(
@@ -2673,17 +2673,10 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
   CK(h2d(h->s_crds, crds_h, h->h_crds, nc, st));
   CK(h2d(h->s_pq, pq_h, h->h_pq, nq, st));
   CK(h2d(h->s_pb, pb_h, h->h_pb, nb, st));
-  // chunked pipeline on the warp-task assembly: the assembly is cut into as many task ranges as the adjoint has quad
-  // ranges and the two alternate on the stream -- tasks k, adjoint k, tasks k + 1, ... -- so that adjoint range k starts
-  // as soon as its slice of u / lam has arrived instead of behind the whole assembly, and its gradients travel back
-  // while the later slices are still coming in (the kernels do not depend on each other: the adjoint recomputes its
-  // geometry).  JSSO_E2E_INTERLEAVE=0: the whole assembly first.
-  static const bool interleave_on = [] { const char* e = std::getenv("JSSO_E2E_INTERLEAVE"); return !(e && e[0] == '0'); }();
-  const bool interleave = interleave_on && h->e2e_chunks > 1 && h->asm_tasks && S.nnzb() > 0 && !h->mgd.setup_on;
-  if (interleave) {
-    CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
-    if ((rc = assemble_geometry_range(h, h->s_crds, h->s_pq, 0, S.n_quad, st))) return rc;
-  } else if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
+  // (Tried and removed: the assembly cut into task ranges that alternate with the adjoint's quad ranges on the stream, so
+  // that gradients leave while later uploads still arrive -- 4.50 vs 4.18 ms at 4 chunks, 4.12 ms at 16: the extra ramps and
+  // tails of the persistent kernels cost more than the overlap gains; scripts/r2_call21.sh.)
+  if ((rc = jsso_assemble(h, h->s_crds, h->s_pq, h->s_pb, 1, st))) return rc;
   if (h->e2e_chunks > 1) {
     // chunked pipeline (opt-in, JSSO_E2E_CHUNKS): see the handle fields
     const int K = h->e2e_chunks;
@@ -2699,13 +2692,7 @@ int jsso_assemble_adjoint_host(jsso_handle* h, const double* crds_h, const doubl
     const bool p_dq = want_dq && pinned(dpq_h);
     double* dq_dst = want_dq ? (p_dq ? dpq_h : h->h_dpq) : nullptr;
     int waited = -1;
-    const int n_task = S.n_task();
     for (int c = 0; c < K; ++c) {
-      if (interleave) {
-        const int t0 = (int)((long long)n_task * c / K), t1 = (int)((long long)n_task * (c + 1) / K);
-        if ((rc = assemble_task_range(h, h->s_crds, h->s_pb, 1, t0, t1, st))) return rc;
-        if (c == K - 1 && (rc = assemble_done(h, h->s_crds, 1, st))) return rc;
-      }
       if (h->e2e_wait[c] > waited) { waited = h->e2e_wait[c]; CK(cudaStreamWaitEvent(st, h->ev_up[waited], 0)); }
       const int q0 = h->e2e_qb[c], nqc = h->e2e_qb[c + 1] - q0;
       if ((rc = adjoint_quad_range(h, q0, nqc, h->s_crds, h->s_pq, h->s_f, h->s_u, dc_h != nullptr,
