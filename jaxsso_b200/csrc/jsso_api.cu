@@ -2504,12 +2504,17 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
   const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;
   th.reserve(nt);
-  for (unsigned t = 0; t < nt; ++t) {
-    const size_t o = (size_t)t * chunk;
-    if (o >= bytes) break;
-    const size_t n = std::min(chunk, bytes - o);
-    th.emplace_back([=] { std::memcpy((char*)dst + o, (const char*)src + o, n); });
+  size_t done = 0;                                     // bytes handed to a thread so far
+  try {
+    for (unsigned t = 0; t < nt && done < bytes; ++t) {
+      const size_t o = done, n = std::min(chunk, bytes - o);
+      th.emplace_back([=] { std::memcpy((char*)dst + o, (const char*)src + o, n); });
+      done += n;
+    }
+  } catch (...) {
+    // no more threads to be had (resource limits): the rest on this one -- never let an exception cross the C ABI
   }
+  if (done < bytes) std::memcpy((char*)dst + done, (const char*)src + done, bytes - done);
   for (std::thread& t : th) t.join();
 }
 // page-locked (cudaHostAlloc / cudaHostRegister) host memory can be the source / target of an asynchronous DMA
