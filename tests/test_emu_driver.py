@@ -102,7 +102,8 @@ def test_distributed_multigrid_through_the_emulated_driver(emu_api, world, size,
     assert res['exchanges'] > 0 and res['allreduces'] >= 3 * res['iters_single']
 
 
-@pytest.mark.parametrize('world,size,min_dist,deg,p2p', [(2, 12, 10, 1, ''), (4, 16, 10, 1, 'p2p'), (2, 12, 1000, 2, 'p2p')])
+@pytest.mark.parametrize('world,size,min_dist,deg,p2p', [(2, 12, 10, 1, ''), (4, 16, 10, 1, 'p2p'), (2, 12, 1000, 2, 'p2p'),
+                                                       (8, 24, 10, 1, 'p2p')])
 def test_distributed_numeric_setup(emu_api, world, size, min_dist, deg, p2p):
     """jsso_mg_set_dist_setup: every rank assembles / scales only the row hull it reads and computes only its share of
     the prolongators and Galerkin products (ghost rows recomputed, coarse matrices all-gathered).  Fresh "device"
@@ -145,6 +146,15 @@ def test_memcheck_under_address_sanitizer(args, env):
                "nat.gather_rows(s, i, 6)\n" % ROOT)
         r2 = subprocess.run([sys.executable, '-c', neg], capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
         assert r2.returncode != 0 and 'heap-buffer-overflow' in r2.stderr and 'gather_rows_kernel' in r2.stderr
+
+
+def test_bench_distributed_gradient_evaluation_on_four_rank_threads(emu_api):
+    """The same leg on four rank threads (ranks with two neighbours, an empty range at the first replicated level),
+    fresh "device" memory poisoned: the ghost-row recomputation of the corrected iterate reads only what the plan's
+    exchanges delivered."""
+    res = run(emu_api, 'benchleg', 4, 24, 10, 'natural', env={'EMU_POISON': '1'})
+    assert res['leg']['pcg_iterations'] == res['iters_single'] and res['leg']['distributed']['n_dist'] == 2
+    assert res['u_err_vs_single'] <= 1e-9 and res['u_err_vs_oracle'] <= 1e-8 and res['g_err'] <= 1e-6 and res['dq_err'] <= 1e-6
 
 
 @pytest.mark.parametrize('kind', ['natural', 'rcb'])
