@@ -258,11 +258,11 @@ struct jsso_handle {
   cudaEvent_t ev_out[4] = {nullptr, nullptr, nullptr, nullptr};   // D2H of u / d_crds / d_prop_q / d_prop_b done
   cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
   cudaEvent_t ev_b = nullptr;
-  // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 4; 1 = one launch): u / lam arrive
+  // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 8; 1 = one launch): u / lam arrive
   // in K node ranges, the quad adjoint runs in K quad ranges as soon as the rows a range reads have arrived, and
   // every range's d_prop_q goes back to the host while the next range is differentiated (measured at 1M quads on a
-  // B200, PCIe-bound step: 5.04 ms unchunked, 4.25 ms with K = 4)
-  int e2e_chunks = 4;
+  // B200, PCIe-bound step: 5.04 ms unchunked, 4.17 / 4.22 ms with K = 4, 4.06 / 4.08 with K = 8, 4.07 / 4.13 with K = 16)
+  int e2e_chunks = 8;
   cudaStream_t st_c = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_adj;
   std::vector<int> e2e_qb, e2e_nb, e2e_wait;   // quad bounds, node bounds, upload range each quad range waits for
