@@ -258,7 +258,7 @@ struct jsso_handle {
   cudaEvent_t ev_out[4] = {nullptr, nullptr, nullptr, nullptr};   // D2H of u / d_crds / d_prop_q / d_prop_b done
   cudaStream_t st_a = nullptr, st_b = nullptr;   // non-blocking streams of the host-buffer entry point
   cudaEvent_t ev_b = nullptr;
-  // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 8; 1 = one launch): u / lam arrive
+  // chunked pipeline of jsso_assemble_adjoint_host (JSSO_E2E_CHUNKS = K, default 8 from 400 000 quads, else 4; 1 = one launch): u / lam arrive
   // in K node ranges, the quad adjoint runs in K quad ranges as soon as the rows a range reads have arrived, and
   // every range's d_prop_q goes back to the host while the next range is differentiated (measured at 1M quads on a
   // B200, PCIe-bound step: 5.04 ms unchunked, 4.17 / 4.22 ms with K = 4, 4.06 / 4.08 with K = 8, 4.07 / 4.13 with K = 16)
@@ -2547,6 +2547,7 @@ static int ensure_host_staging(jsso_handle* h) {
   CK(cudaStreamCreateWithFlags(&h->st_b, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
   if (const char* e = std::getenv("JSSO_E2E_CHUNKS")) h->e2e_chunks = std::max(1, std::min(64, std::atoi(e)));
+  else if (S.n_quad < 400000) h->e2e_chunks = 4;      // smaller systems (the per-rank parts at 4 and 8 GPUs): measured with 4
   if (h->e2e_chunks > 1 && S.n_quad >= h->e2e_chunks && S.n_node >= h->e2e_chunks) {
     const int K = h->e2e_chunks;
     CK(cudaStreamCreateWithFlags(&h->st_c, cudaStreamNonBlocking));
