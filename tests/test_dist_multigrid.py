@@ -294,3 +294,36 @@ def test_rank_plans_over_gloo():
         p.join(180)
     assert all(p.exitcode == 0 for p in procs)
     assert all(ret[r] for r in range(world))
+
+
+@pytest.mark.parametrize('n_rank', [2, 4, 8])
+def test_ghost_rows_of_the_corrected_iterate_read_only_delivered_data(n_rank):
+    """The fused distributed V-cycle recomputes x1 = b / theta + P x_c on the ghost rows of every distributed level
+    instead of exchanging it (`plan['ghost']`).  Pure bookkeeping check of the plan: (i) the ghost rows of a rank are
+    exactly the foreign columns its own rows of A_l read -- what the post-smoother gathers; (ii) every one of them is in
+    the halo of the level's exchanges, so b has arrived there; (iii) every coarse column of a ghost row's prolongator is
+    either owned by the rank or in the halo of level l + 1 (distributed) -- x_c is there -- or level l + 1 is replicated."""
+    _, md, _, Ah, levels, _, _, plan = _setup(24, n_rank, min_dist_nodes=40)
+    rp, ci = Ah.indptr.astype(np.int32), Ah.indices.astype(np.int32)
+    n_dist = plan['n_dist']
+    assert n_dist == 2
+    for l in range(n_dist):
+        a_rp, a_ci = (rp, ci) if l == 0 else (levels[l - 1]['c_rowptr'], levels[l - 1]['c_col'])
+        lv = levels[l]
+        for r in range(n_rank):
+            lo, hi = int(plan['bounds'][l][r]), int(plan['bounds'][l][r + 1])
+            cols = np.unique(a_ci[a_rp[lo]:a_rp[hi]]) if hi > lo else np.zeros(0, np.int32)
+            foreign = cols[(cols < lo) | (cols >= hi)]
+            ghost = np.asarray(plan['ghost'][l][r])
+            assert np.array_equal(np.sort(ghost), foreign)                                      # (i)
+            halo_l = np.concatenate([np.asarray(plan['need'][l][r][s]) for s in range(n_rank)] + [np.zeros(0, np.int32)])
+            assert np.all(np.isin(ghost, halo_l))                                               # (ii)
+            if ghost.size and l + 1 < n_dist:                                                   # (iii)
+                pc = np.unique(np.concatenate([lv['p_col'][lv['p_rowptr'][g]:lv['p_rowptr'][g + 1]] for g in ghost]))
+                lo1, hi1 = int(plan['bounds'][l + 1][r]), int(plan['bounds'][l + 1][r + 1])
+                halo_1 = np.concatenate([np.asarray(plan['need'][l + 1][r][s]) for s in range(n_rank)] + [np.zeros(0, np.int32)])
+                missing = pc[((pc < lo1) | (pc >= hi1)) & ~np.isin(pc, halo_1)]
+                assert missing.size == 0
+        rps = [dmg.rank_plan(plan, r) for r in range(n_rank)]
+        for r in range(n_rank):
+            assert np.array_equal(np.sort(rps[r][l]['ghost_rows']), np.sort(np.asarray(plan['ghost'][l][r])))
