@@ -1618,10 +1618,6 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
       for (int it = 0; it < h->mg_power_iters; ++it) {
         if (it > 0) { if ((rc = mgd_exchange(h, l, m.r, st))) return rc; }
         if ((rc = mg_spmv_p<0>(h, A.rp + rs, A.ci, A.v, A.v32, rn, m.r, m.d + off, nullptr, st, false, A.v16, bpr))) return rc;
-        if (m.Dinv && rn > 0) {
-          block_apply_kernel<0><<<cdiv(rn, 128), 128, 0, st>>>(rn, m.Dinv + 36 * (size_t)rs, m.d + off, nullptr, m.d + off);
-          CKL("block_apply_kernel<0>");
-        }
         if ((rc = mg_dot(h, ndl, m.d + off, m.d + off, 0, st))) return rc;
         if ((rc = mg_dot(h, ndl, m.r + off, m.r + off, 1, st))) return rc;
         if ((rc = mgd_reduce_read(h, 0, 2, st))) return rc;
@@ -1633,10 +1629,6 @@ static int mg_numeric_setup(jsso_handle* h, cudaStream_t st) {
     }
     for (int it = 0; it < h->mg_power_iters && !dist_pow; ++it) {
       if ((rc = mg_spmv_p<0>(h, A.rp, A.ci, A.v, A.v32, n, m.r, m.d, nullptr, st, false, A.v16, bpr))) return rc;
-      if (m.Dinv) {
-        block_apply_kernel<0><<<cdiv(n, 128), 128, 0, st>>>(n, m.Dinv, m.d, nullptr, m.d);
-        CKL("block_apply_kernel<0>");
-      }
       if ((rc = mg_dot(h, nd, m.d, m.d, 0, st))) return rc;
       if ((rc = mg_dot(h, nd, m.r, m.r, 5, st))) return rc;
       if ((rc = mg_read_scalars(h, st))) return rc;
